@@ -1,0 +1,1028 @@
+// extern "C" boundary of libgpet_b200.so (see include/gpet_b200.h for the reference call each entry replaces).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ctx.hpp"
+#include "planner.hpp"
+
+using namespace gpet;
+
+namespace {
+
+int fail(const gpet_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(c, GPET_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+    } while (0)
+
+#define NEED_DEVICE()                                                                                      \
+    do {                                                                                                   \
+        if (!c) return GPET_ERR_ARG;                                                                       \
+        if (!c->has_device)                                                                                \
+            return fail(c, GPET_ERR_NO_DEVICE, "compute entry point called on a host-only context (no CPU fallback)"); \
+    } while (0)
+
+template <typename T>
+int dev_alloc(gpet_ctx* c, T** p, size_t n) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    c->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return GPET_OK;
+}
+
+int alloc_queue(gpet_ctx* c, PhotonQueue& q, size_t cap) {
+    int r;
+    if ((r = dev_alloc(c, &q.pos_e, cap))) return r;
+    if ((r = dev_alloc(c, &q.dir_n, cap))) return r;
+    if ((r = dev_alloc(c, &q.t, cap))) return r;
+    if ((r = dev_alloc(c, &q.ids, cap))) return r;
+    if ((r = dev_alloc(c, &q.count, 4))) return r;
+    q.capacity = (unsigned)cap;
+    CK(cudaMemset(q.count, 0, 16));
+    return GPET_OK;
+}
+
+int alloc_events(gpet_ctx* c, EventSoA& e, size_t cap) {
+    int r;
+    int** ints[6] = {&e.parn, &e.pann, &e.modn, &e.cryn, &e.siten, &e.eventid};
+    for (auto p : ints)
+        if ((r = dev_alloc(c, p, cap))) return r;
+    if ((r = dev_alloc(c, &e.t, cap))) return r;
+    float** flts[4] = {&e.E, &e.x, &e.y, &e.z};
+    for (auto p : flts)
+        if ((r = dev_alloc(c, p, cap))) return r;
+    if ((r = dev_alloc(c, &e.count, 4))) return r;
+    e.capacity = (unsigned)cap;
+    CK(cudaMemset(e.count, 0, 16));
+    return GPET_OK;
+}
+
+int ensure_buffers(gpet_ctx* c) {
+    if (c->dev_buffers) return GPET_OK;
+    int r;
+    const size_t cp = c->cap_photons, ch = c->cap_hits, ce = c->cap_events;
+    if ((r = alloc_queue(c, c->q[0], cp))) return r;
+    if ((r = alloc_queue(c, c->q[1], cp))) return r;
+    if ((r = dev_alloc(c, &c->hits.id, 5 * ch))) return r;
+    if ((r = dev_alloc(c, &c->hits.f, 5 * ch))) return r;
+    if ((r = dev_alloc(c, &c->hits.t, ch))) return r;
+    if ((r = dev_alloc(c, &c->hits.count, 4))) return r;
+    c->hits.capacity = (unsigned)ch;
+    CK(cudaMemset(c->hits.count, 0, 16));
+    if ((r = alloc_events(c, c->ev, ce))) return r;
+    if ((r = alloc_events(c, c->singles, ce))) return r;
+    DigitizerWorkspace& w = c->ws;
+    for (int k = 0; k < 2; k++) {
+        if ((r = dev_alloc(c, &w.sort.keys[k], ce))) return r;
+        if ((r = dev_alloc(c, &w.sort.vals[k], ce))) return r;
+    }
+    w.sort.capacity = (unsigned)ce;
+    w.sort.max_tiles = (unsigned)((ce + 2047) / 2048);
+    if ((r = dev_alloc(c, &w.sort.tile_hist, (size_t)256 * w.sort.max_tiles))) return r;
+    if ((r = dev_alloc(c, &w.order_t, ce))) return r;
+    if ((r = dev_alloc(c, &w.order_s, ce))) return r;
+    if ((r = dev_alloc(c, &w.kill, ce))) return r;
+    if ((r = dev_alloc(c, &w.flags, ce))) return r;
+    if ((r = dev_alloc(c, &w.scan_tmp, (size_t)w.sort.max_tiles + 1024))) return r;
+    if ((r = dev_alloc(c, &w.counters, 32))) return r;
+    CK(cudaMemset(w.counters, 0, 32 * sizeof(unsigned)));
+    w.site_sorted = nullptr;
+    if (w.spectrum_bins > 0) {
+        if ((r = dev_alloc(c, &w.spectrum, (size_t)w.spectrum_bins))) return r;
+        CK(cudaMemset(w.spectrum, 0, sizeof(unsigned long long) * w.spectrum_bins));
+    }
+    {
+        void* p = nullptr;
+        CK(cudaMalloc(&p, ce * sizeof(gpet_event)));
+        c->allocs.push_back(p);
+        c->singles_aos = p;
+        c->coinc_cap = (unsigned)(ce / 2);
+        CK(cudaMalloc(&p, (size_t)c->coinc_cap * sizeof(gpet_coincidence)));
+        c->allocs.push_back(p);
+        c->coinc_aos = p;
+        c->stage_bytes = std::max(std::max(ce * sizeof(gpet_event), cp * sizeof(gpet_photon)), ch * sizeof(gpet_hit));
+        CK(cudaMalloc(&p, c->stage_bytes));
+        c->allocs.push_back(p);
+        c->stage_aos = p;
+    }
+    if ((r = dev_alloc(c, &c->d_totals, 32))) return r;
+    CK(cudaMemset(c->d_totals, 0, 32 * sizeof(unsigned long long)));
+    CK(cudaMallocHost((void**)&c->h_counters, 64 * sizeof(unsigned)));
+    CK(cudaMallocHost((void**)&c->h_totals, 32 * sizeof(unsigned long long)));
+    c->dev_buffers = true;
+    return GPET_OK;
+}
+
+int upload_tables(gpet_ctx* c) {
+    if (c->dev_tables) return GPET_OK;
+    if (!c->tab.loaded()) return fail(c, GPET_ERR_ARG, "cross-section tables not loaded");
+    const Tables& t = c->tab;
+    std::vector<float4> xs((size_t)t.nmat * t.nen);
+    for (size_t k = 0; k < xs.size(); k++) xs[k] = make_float4(t.lamph[k], t.compt[k], t.rayle[k], t.phote[k]);
+    int r;
+    if ((r = dev_alloc(c, &c->d_xs, xs.size()))) return r;
+    CK(cudaMemcpy(c->d_xs, xs.data(), xs.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    if ((r = dev_alloc(c, &c->d_cmpsf, t.cmpsf.size()))) return r;
+    CK(cudaMemcpy(c->d_cmpsf, t.cmpsf.data(), t.cmpsf.size() * 4, cudaMemcpyHostToDevice));
+    if ((r = dev_alloc(c, &c->d_rayff, t.rayff.size()))) return r;
+    CK(cudaMemcpy(c->d_rayff, t.rayff.data(), t.rayff.size() * 4, cudaMemcpyHostToDevice));
+    if ((r = dev_alloc(c, &c->d_maj_ph, (size_t)t.nen))) return r;
+    if ((r = dev_alloc(c, &c->d_maj_det, (size_t)t.nen))) return r;
+    c->dev_tables = true;
+    return GPET_OK;
+}
+
+TablesDev tables_dev(const gpet_ctx* c) {
+    const Tables& t = c->tab;
+    TablesDev d{};
+    d.xs = c->d_xs;
+    d.maj_phantom = c->d_maj_ph;
+    d.maj_detector = c->d_maj_det;
+    d.cmpsf = c->d_cmpsf;
+    d.rayff = c->d_rayff;
+    d.nmat = t.nmat;
+    d.nen = t.nen;
+    d.e0 = t.energy.empty() ? 0.f : t.energy[0];
+    d.ide = t.nen > 1 ? (float)(t.nen - 1) / (t.energy[t.nen - 1] - t.energy[0]) : 0.f;  // idleph (initialize.cu:421)
+    d.cm_ncp = t.cm_ncp; d.cm_ne = t.cm_ne; d.rl_ncp = t.rl_ncp; d.rl_ne = t.rl_ne;
+    d.cm_idcp = 1.0f / t.cm_dcp; d.cm_ide = 1.0f / t.cm_de;   // initialize.cu:526-527
+    d.rl_idcp = 1.0f / t.rl_dcp; d.rl_ide = 1.0f / t.rl_de;   // initialize.cu:707-708
+    return d;
+}
+
+int upload_phantom(gpet_ctx* c) {
+    if (c->dev_phantom) return GPET_OK;
+    if (!c->have_ph) return fail(c, GPET_ERR_ARG, "phantom not loaded");
+    int r;
+    if ((r = upload_tables(c))) return r;
+    const Phantom& ph = c->ph;
+    const size_t n = ph.nvox();
+    std::vector<uint32_t> vox(n);
+    for (size_t k = 0; k < n; k++) {
+        uint32_t b;
+        float d = ph.dens[k];
+        memcpy(&b, &d, 4);
+        vox[k] = (b & ~15u) | ((uint32_t)ph.mat[k] & 15u);
+    }
+    if ((r = dev_alloc(c, &c->d_vox, n))) return r;
+    CK(cudaMemcpy(c->d_vox, vox.data(), n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_maj_ph, c->maj_ph.data(), c->maj_ph.size() * 4, cudaMemcpyHostToDevice));
+    // keep the voxel grid resident in L2 (persisting access-policy window) when the carve-out allows it
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+    if (max_persist > 0 && max_window > 0) {
+        size_t bytes = std::min<size_t>(n * 4, (size_t)max_window);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)max_persist));
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = c->d_vox;
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)max_persist / (float)bytes);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError();
+    }
+    c->dev_phantom = true;
+    return GPET_OK;
+}
+
+PhantomDev phantom_dev(const gpet_ctx* c) {
+    PhantomDev d{};
+    const Phantom& ph = c->ph;
+    d.vox = c->d_vox;
+    d.nx = ph.dim[0]; d.ny = ph.dim[1]; d.nz = ph.dim[2];
+    d.ox = ph.offset[0]; d.oy = ph.offset[1]; d.oz = ph.offset[2];
+    d.idx = 1.0f / ph.d[0]; d.idy = 1.0f / ph.d[1]; d.idz = 1.0f / ph.d[2];  // initialize.cu:846-851
+    return d;
+}
+
+int upload_geometry(gpet_ctx* c) {
+    if (c->dev_geo) return GPET_OK;
+    if (!c->have_geo) return fail(c, GPET_ERR_ARG, "detector geometry not loaded");
+    int r;
+    if ((r = upload_tables(c))) return r;
+    const Geometry& g = c->geo;
+    std::vector<PanelDev> pd(g.panels.size());
+    for (size_t i = 0; i < pd.size(); i++) {
+        const gpet_panel& p = g.panels[i];
+        PanelDev& d = pd[i];
+        memset(&d, 0, sizeof(d));
+        d.ox = p.offsetx; d.oy = p.offsety; d.oz = p.offsetz;
+        d.uxx = p.UniXx; d.uxy = p.UniXy; d.uxz = p.UniXz;
+        d.uyx = p.UniYx; d.uyy = p.UniYy; d.uyz = p.UniYz;
+        d.uzx = p.UniZx; d.uzy = p.UniZy; d.uzz = p.UniZz;
+        d.lx = p.lengthx; d.ly = p.lengthy; d.lz = p.lengthz;
+        d.dirx = p.directionx;
+        d.mody = p.MODy; d.modz = p.MODz; d.mspy = p.Mspacey; d.mspz = p.Mspacez;
+        d.lsoy = p.LSOy; d.lsoz = p.LSOz; d.spy = p.spacey; d.spz = p.spacez;
+        d.id = p.panel;
+    }
+    if ((r = dev_alloc(c, &c->d_panels, pd.size()))) return r;
+    CK(cudaMemcpy(c->d_panels, pd.data(), pd.size() * sizeof(PanelDev), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_maj_det, c->maj_det.data(), c->maj_det.size() * 4, cudaMemcpyHostToDevice));
+    c->dev_geo = true;
+    return GPET_OK;
+}
+
+DetectorDev detector_dev(const gpet_ctx* c) {
+    DetectorDev d{};
+    const Geometry& g = c->geo;
+    d.panels = c->d_panels;
+    d.npanels = (int)g.panels.size();
+    d.moduleNy = g.moduleNy; d.crystalNy = g.crystalNy; d.moduleN = g.moduleN; d.crystalN = g.crystalN;
+    d.mat[0] = g.mat[0]; d.mat[1] = g.mat[1];
+    d.dens[0] = g.dens[0]; d.dens[1] = g.dens[1];
+    d.nsurface = c->tr.nsurface;
+    memcpy(d.surface, c->tr.surface, sizeof(float) * 10 * GPET_MAX_SURFACES);
+    return d;
+}
+
+DigitizerDev digitizer_dev(const gpet_ctx* c) {
+    DigitizerDev d{};
+    const gpet_digitizer_params& p = c->dig;
+    d.readout_depth = p.readout_depth; d.readout_policy = p.readout_policy;
+    d.Eth = p.threshold_eV;
+    d.blur_policy = p.blur_policy; d.Eref = p.blur_Eref; d.Rref = p.blur_Rref; d.slope = p.blur_slope; d.sblur = p.blur_space;
+    d.dlevel = p.dead_level; d.dtype = p.dead_type; d.dtime = p.dead_time_us;
+    d.Ewinmin = p.ewin_min; d.Ewinmax = p.ewin_max;
+    d.tblur = p.time_blur_sigma_us; d.cwin = p.coinc_window_us; d.cpolicy = p.coinc_policy; d.cmindiff = p.coinc_min_panel_diff;
+    d.npanels = (int)c->geo.panels.size();
+    d.moduleN = c->geo.moduleN; d.crystalN = c->geo.crystalN;
+    return d;
+}
+
+void rebuild_majorants(gpet_ctx* c) {
+    if (!c->tab.loaded()) return;
+    if (c->have_ph) {
+        // largest density per material present in the phantom (initialize.cu:794-802)
+        std::vector<float> maxden((size_t)c->tab.nmat, 0.f);
+        for (size_t k = 0; k < c->ph.nvox(); k++) {
+            int m = c->ph.mat[k];
+            if (m >= 0 && m < c->tab.nmat && c->ph.dens[k] > maxden[m]) maxden[m] = c->ph.dens[k];
+        }
+        c->maj_ph = build_majorant(c->tab, maxden);
+        c->dev_phantom = false;
+    }
+    if (c->have_geo) {
+        std::vector<float> maxden((size_t)c->tab.nmat, 0.f);
+        for (int i = 0; i < 2; i++) {  // initialize.cu:932-936
+            int m = c->geo.mat[i];
+            if (m >= 0 && m < c->tab.nmat && c->geo.dens[i] > maxden[m]) maxden[m] = c->geo.dens[i];
+        }
+        c->maj_det = build_majorant(c->tab, maxden);
+        c->dev_geo = false;
+    }
+}
+
+int validate_materials(gpet_ctx* c) {
+    if (!c->tab.loaded()) return GPET_OK;
+    if (c->have_ph) {
+        for (size_t k = 0; k < c->ph.nvox(); k++)
+            if (c->ph.mat[k] < 0 || c->ph.mat[k] >= c->tab.nmat || c->ph.mat[k] > 15)
+                return fail(c, GPET_ERR_FORMAT, "phantom material id outside the loaded table set");
+    }
+    if (c->have_geo) {
+        for (int i = 0; i < 2; i++)
+            if (c->geo.mat[i] < 0 || c->geo.mat[i] >= c->tab.nmat)
+                return fail(c, GPET_ERR_FORMAT, "detector material id outside the loaded table set");
+    }
+    return GPET_OK;
+}
+
+int read_counters(gpet_ctx* c) {  // synchronises the stream
+    CK(cudaMemcpyAsync(c->h_counters, c->ws.counters, 16 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_counters + 16, c->ev.count, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_counters + 17, c->hits.count, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_counters + 18, c->q[0].count, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_counters + 19, c->q[1].count, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_counters + 20, c->singles.count, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return GPET_OK;
+}
+
+}  // namespace
+
+// =================================================================================================== lifecycle
+extern "C" {
+
+int gpet_abi_version(void) { return GPET_ABI_VERSION; }
+
+int gpet_create(int device, gpet_ctx** out) {
+    if (!out) return GPET_ERR_ARG;
+    gpet_ctx* c = new gpet_ctx();
+    c->device = device;
+    // defaults = the shipped example's digitizer block would be set by gpet_load_config_file; keep neutral values
+    c->dig.readout_depth = 2; c->dig.readout_policy = 1;
+    c->dig.dead_level = 3; c->dig.ewin_max = 2.0e6f;
+    c->tr.eabs_eV = 1.0e3f; c->tr.record_hits = 1;
+    if (device >= 0) {
+        cudaError_t e = cudaSetDevice(device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            std::string msg = std::string("gpet_create: ") + cudaGetErrorString(e);
+            delete c;
+            *out = nullptr;
+            fprintf(stderr, "%s\n", msg.c_str());
+            return GPET_ERR_CUDA;
+        }
+        c->stream = c->own_stream;
+        cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device);
+        c->has_device = true;
+    }
+    *out = c;
+    return GPET_OK;
+}
+
+void gpet_destroy(gpet_ctx* c) {
+    if (!c) return;
+    if (c->has_device) {
+        cudaSetDevice(c->device);
+        cudaDeviceSynchronize();
+        for (void* p : c->allocs) cudaFree(p);
+        if (c->h_counters) cudaFreeHost(c->h_counters);
+        if (c->h_totals) cudaFreeHost(c->h_totals);
+        if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    }
+    delete c;
+}
+
+const char* gpet_last_error(const gpet_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int gpet_set_stream(gpet_ctx* c, void* s) {
+    if (!c) return GPET_ERR_ARG;
+    c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+    return GPET_OK;
+}
+
+int gpet_set_seed(gpet_ctx* c, uint64_t seed) {
+    if (!c) return GPET_ERR_ARG;
+    c->seed = seed;
+    c->planned = false;
+    return GPET_OK;
+}
+
+int gpet_set_capacity(gpet_ctx* c, uint64_t max_photons, uint64_t max_hits, uint64_t max_events) {
+    if (!c) return GPET_ERR_ARG;
+    if (c->dev_buffers) return fail(c, GPET_ERR_ARG, "capacity must be set before the first compute call");
+    if (max_photons < 64 || max_hits < 64 || max_events < 64 || max_photons > (1ull << 31) || max_hits > (1ull << 29) ||
+        max_events > (1ull << 31))
+        return fail(c, GPET_ERR_ARG, "capacity out of range");
+    c->cap_photons = max_photons; c->cap_hits = max_hits; c->cap_events = max_events;
+    c->planned = false;
+    return GPET_OK;
+}
+
+// =================================================================================================== loaders
+int gpet_load_tables(gpet_ctx* c, const char* prefix) {
+    if (!c || !prefix) return GPET_ERR_ARG;
+    std::string p(prefix), e;
+    if (p.size() > 8 && p.compare(p.size() - 8, 8, ".gpettab") == 0) e = load_tables_packed(p, c->tab);
+    else e = load_tables_ascii(p, c->tab);
+    if (!e.empty()) { c->tab = Tables(); return fail(c, GPET_ERR_IO, e); }
+    if (c->dev_tables) return fail(c, GPET_ERR_ARG, "tables already uploaded; create a new context");
+    rebuild_majorants(c);
+    return validate_materials(c);
+}
+
+int gpet_save_tables_packed(gpet_ctx* c, const char* path) {
+    if (!c || !path) return GPET_ERR_ARG;
+    if (!c->tab.loaded()) return fail(c, GPET_ERR_ARG, "no tables loaded");
+    std::string e = save_tables_packed(path, c->tab);
+    return e.empty() ? GPET_OK : fail(c, GPET_ERR_IO, e);
+}
+
+int gpet_load_phantom_files(gpet_ctx* c, const char* mat_file, const char* den_file, const int32_t dim[3],
+                            const float offset[3], const float size[3]) {
+    if (!c || !mat_file || !den_file) return GPET_ERR_ARG;
+    if (c->dev_phantom) return fail(c, GPET_ERR_ARG, "phantom already uploaded; create a new context");
+    std::string e = load_phantom(mat_file, den_file, dim, offset, size, c->ph);
+    if (!e.empty()) { c->have_ph = false; return fail(c, GPET_ERR_IO, e); }
+    c->have_ph = true;
+    rebuild_majorants(c);
+    return validate_materials(c);
+}
+
+int gpet_set_phantom(gpet_ctx* c, const int32_t* mat, const float* dens, const int32_t dim[3], const float offset[3],
+                     const float size[3]) {
+    if (!c || !mat || !dens) return GPET_ERR_ARG;
+    if (c->dev_phantom) return fail(c, GPET_ERR_ARG, "phantom already uploaded; create a new context");
+    Phantom& ph = c->ph;
+    for (int i = 0; i < 3; i++) {
+        if (dim[i] < 1) return fail(c, GPET_ERR_ARG, "phantom dimension must be positive");
+        ph.dim[i] = dim[i]; ph.offset[i] = offset[i]; ph.size[i] = size[i]; ph.d[i] = size[i] / dim[i];
+    }
+    ph.mat.assign(mat, mat + ph.nvox());
+    ph.dens.assign(dens, dens + ph.nvox());
+    c->have_ph = true;
+    rebuild_majorants(c);
+    return validate_materials(c);
+}
+
+int gpet_load_geometry(gpet_ctx* c, const char* geo_file) {
+    if (!c || !geo_file) return GPET_ERR_ARG;
+    if (c->dev_geo) return fail(c, GPET_ERR_ARG, "geometry already uploaded; create a new context");
+    Geometry g;
+    std::string e = parse_geometry(geo_file, g);
+    if (!e.empty()) return fail(c, GPET_ERR_IO, e);
+    c->geo = g;
+    c->have_geo = true;
+    rebuild_majorants(c);
+    return validate_materials(c);
+}
+
+int gpet_load_isotopes(gpet_ctx* c, const char* f) {
+    if (!c || !f) return GPET_ERR_ARG;
+    std::string e = parse_isotopes(f, c->iso);
+    if (!e.empty()) { c->have_iso = false; return fail(c, GPET_ERR_IO, e); }
+    c->have_iso = true;
+    c->planned = false;
+    return GPET_OK;
+}
+
+int gpet_load_source(gpet_ctx* c, const char* f) {
+    if (!c || !f) return GPET_ERR_ARG;
+    std::string e = parse_sources(f, c->src);
+    if (!e.empty()) { c->have_src = false; return fail(c, GPET_ERR_IO, e); }
+    c->have_src = true;
+    c->usepsf = 0;
+    c->planned = false;
+    return GPET_OK;
+}
+
+int gpet_load_psf(gpet_ctx* c, const char* f, int64_t max_particles, int ptype) {
+    if (!c || !f) return GPET_ERR_ARG;
+    if (ptype != 0 && ptype != 1) return fail(c, GPET_ERR_ARG, "psf particle type must be 0 (positron) or 1 (photon)");
+    std::string e = load_psf(f, max_particles, ptype, c->psf);
+    if (!e.empty()) { c->have_psf = false; return fail(c, GPET_ERR_IO, e); }
+    c->have_psf = true;
+    c->usepsf = 1;
+    return GPET_OK;
+}
+
+int gpet_set_digitizer(gpet_ctx* c, const gpet_digitizer_params* p) {
+    if (!c || !p) return GPET_ERR_ARG;
+    if (p->readout_depth < 0 || p->readout_depth > 3 || p->readout_policy < 0 || p->readout_policy > 1 ||
+        p->dead_level < 0 || p->dead_level > 3 || p->dead_type < 0 || p->dead_type > 1 || p->blur_policy < 0 ||
+        p->blur_policy > 1)
+        return fail(c, GPET_ERR_ARG, "digitizer parameter out of range");
+    c->dig = *p;
+    return GPET_OK;
+}
+
+int gpet_get_digitizer(const gpet_ctx* c, gpet_digitizer_params* p) {
+    if (!c || !p) return GPET_ERR_ARG;
+    *p = c->dig;
+    return GPET_OK;
+}
+
+int gpet_set_transport(gpet_ctx* c, const gpet_transport_params* p) {
+    if (!c || !p) return GPET_ERR_ARG;
+    if (p->nsurface < 0 || p->nsurface > GPET_MAX_SURFACES) return fail(c, GPET_ERR_ARG, "too many quadric surfaces (MAXSURFACE)");
+    if (p->use_positron_range) return fail(c, GPET_ERR_ARG, "positron range sampling is not implemented yet");
+    c->tr = *p;
+    return GPET_OK;
+}
+
+int gpet_get_transport(const gpet_ctx* c, gpet_transport_params* p) {
+    if (!c || !p) return GPET_ERR_ARG;
+    *p = c->tr;
+    return GPET_OK;
+}
+
+int gpet_set_time_window(gpet_ctx* c, float t0, float t1) {
+    if (!c) return GPET_ERR_ARG;
+    if (!(t1 > t0) || t0 < 0.f) return fail(c, GPET_ERR_ARG, "time window must satisfy 0 <= tstart < tend");
+    c->tstart = t0; c->tend = t1;
+    c->planned = false;
+    return GPET_OK;
+}
+
+int gpet_set_source_atoms(gpet_ctx* c, int i, uint64_t natom) {
+    if (!c || !c->have_src || i < 0 || i >= c->src.n()) return GPET_ERR_ARG;
+    c->src.natom[i] = natom;
+    c->planned = false;
+    return GPET_OK;
+}
+
+int gpet_set_shard(gpet_ctx* c, int rank, int world) {
+    if (!c || world < 1 || rank < 0 || rank >= world) return GPET_ERR_ARG;
+    c->rank = rank; c->world = world;
+    return GPET_OK;
+}
+
+int gpet_load_config_file(gpet_ctx* c, const char* input_file, const char* base_dir, const char* data_dir) {
+    if (!c || !input_file) return GPET_ERR_ARG;
+    std::string base = base_dir ? base_dir : "";
+    Config cfg;
+    std::string e = parse_config(input_file, cfg);
+    if (!e.empty()) return fail(c, GPET_ERR_IO, e);
+    c->cfg = cfg;
+    int r;
+    gpet_transport_params tr{};
+    tr.noncollinearity_rad = cfg.nonangle;
+    tr.use_positron_range = cfg.useprange;
+    tr.eabs_eV = cfg.eabsph;
+    tr.nsurface = cfg.nsurface;
+    for (int i = 0; i < 10 * cfg.nsurface; i++) tr.surface[i] = cfg.surface[i];
+    tr.record_hits = 1;
+    if ((r = gpet_set_transport(c, &tr))) return r;
+    gpet_digitizer_params d = c->dig;
+    d.readout_depth = cfg.rdepth; d.readout_policy = cfg.rpolicy;
+    d.threshold_eV = cfg.Eth;
+    d.blur_policy = cfg.blurpolicy; d.blur_Eref = cfg.Eref; d.blur_Rref = cfg.Rref; d.blur_slope = cfg.Eslope; d.blur_space = cfg.Sblur;
+    d.dead_level = cfg.dlevel; d.dead_type = cfg.dtype; d.dead_time_us = cfg.dtime;
+    d.ewin_min = cfg.Ewinmin; d.ewin_max = cfg.Ewinmax;
+    if ((r = gpet_set_digitizer(c, &d))) return r;
+    std::string dd = data_dir ? data_dir : join_path(base, "data");
+    if (!c->tab.loaded()) {
+        std::string packed = join_path(dd, "input4gPET.gpettab");
+        FILE* f = fopen(packed.c_str(), "rb");
+        if (f) { fclose(f); r = gpet_load_tables(c, packed.c_str()); }
+        else r = gpet_load_tables(c, join_path(dd, "input4gPET").c_str());
+        if (r) return r;
+    }
+    if (c->tr.eabs_eV < c->tab.eminph) return fail(c, GPET_ERR_ARG, "init: Eabs out of range");  // initialize.cu:898-902
+    if ((r = gpet_load_phantom_files(c, join_path(base, cfg.matfile).c_str(), join_path(base, cfg.denfile).c_str(), cfg.pdim,
+                                     cfg.poffset, cfg.psize)))
+        return r;
+    if ((r = gpet_load_geometry(c, join_path(base, cfg.geofile).c_str()))) return r;
+    if (cfg.usepsf) {
+        if ((r = gpet_load_psf(c, join_path(base, cfg.sourcefile).c_str(), cfg.nhist, cfg.ptype))) return r;
+    } else {
+        if ((r = gpet_load_isotopes(c, join_path(dd, "isotopes.txt").c_str()))) return r;
+        if ((r = gpet_load_source(c, join_path(base, cfg.sourcefile).c_str()))) return r;
+        if ((r = gpet_set_time_window(c, cfg.tstart, cfg.tend))) return r;
+    }
+    return GPET_OK;
+}
+
+// =================================================================================================== getters
+int gpet_get_num_panels(const gpet_ctx* c) { return c ? (int)c->geo.panels.size() : GPET_ERR_ARG; }
+
+int gpet_get_panels(const gpet_ctx* c, gpet_panel* out, int cap) {
+    if (!c || !out) return GPET_ERR_ARG;
+    int n = std::min<int>(cap, (int)c->geo.panels.size());
+    for (int i = 0; i < n; i++) out[i] = c->geo.panels[i];
+    return n;
+}
+
+int gpet_get_geometry_counts(const gpet_ctx* c, int32_t counts[4], int32_t mat[2], float dens[2]) {
+    if (!c || !c->have_geo) return GPET_ERR_ARG;
+    counts[0] = c->geo.moduleNy; counts[1] = c->geo.crystalNy; counts[2] = c->geo.moduleN; counts[3] = c->geo.crystalN;
+    mat[0] = c->geo.mat[0]; mat[1] = c->geo.mat[1];
+    dens[0] = c->geo.dens[0]; dens[1] = c->geo.dens[1];
+    return GPET_OK;
+}
+
+int gpet_get_table_dims(const gpet_ctx* c, int32_t* nmat, int32_t* nen, float* e0, float* e1, int32_t cmd[2], float cms[2],
+                        int32_t rld[2], float rls[2]) {
+    if (!c || !c->tab.loaded()) return GPET_ERR_ARG;
+    const Tables& t = c->tab;
+    *nmat = t.nmat; *nen = t.nen; *e0 = t.energy.front(); *e1 = t.energy.back();
+    cmd[0] = t.cm_ncp; cmd[1] = t.cm_ne; cms[0] = t.cm_dcp; cms[1] = t.cm_de;
+    rld[0] = t.rl_ncp; rld[1] = t.rl_ne; rls[0] = t.rl_dcp; rls[1] = t.rl_de;
+    return GPET_OK;
+}
+
+int64_t gpet_get_table(const gpet_ctx* c, int which, float* out, int64_t cap) {
+    if (!c || !out || !c->tab.loaded()) return GPET_ERR_ARG;
+    const Tables& t = c->tab;
+    const std::vector<float>* v = nullptr;
+    switch (which) {
+        case 0: v = &t.lamph; break;
+        case 1: v = &t.compt; break;
+        case 2: v = &t.phote; break;
+        case 3: v = &t.rayle; break;
+        case 4: v = &t.cmpsf; break;
+        case 5: v = &t.rayff; break;
+        case 6: v = &c->maj_ph; break;
+        case 7: v = &c->maj_det; break;
+        case 8: v = &t.energy; break;
+        default: return GPET_ERR_ARG;
+    }
+    int64_t n = std::min<int64_t>(cap, (int64_t)v->size());
+    memcpy(out, v->data(), (size_t)n * 4);
+    return n;
+}
+
+int gpet_get_num_sources(const gpet_ctx* c) { return c ? c->src.n() : GPET_ERR_ARG; }
+
+int gpet_get_source(const gpet_ctx* c, int i, uint64_t* natom, int32_t* type, int32_t* shape, float coeff[6]) {
+    if (!c || i < 0 || i >= c->src.n()) return GPET_ERR_ARG;
+    *natom = c->src.natom[i]; *type = c->src.type[i]; *shape = c->src.shape[i];
+    for (int j = 0; j < 6; j++) coeff[j] = c->src.coeff[6 * i + j];
+    return GPET_OK;
+}
+
+int gpet_get_num_isotopes(const gpet_ctx* c) { return c ? c->iso.n() : GPET_ERR_ARG; }
+
+int gpet_get_isotope(const gpet_ctx* c, int i, float* hl, float* ratio, float coef[8]) {
+    if (!c || i < 0 || i >= c->iso.n()) return GPET_ERR_ARG;
+    *hl = c->iso.halftime[i]; *ratio = c->iso.ratio[i];
+    for (int j = 0; j < 8; j++) coef[j] = c->iso.coef[8 * i + j];
+    return GPET_OK;
+}
+
+int64_t gpet_get_num_psf(const gpet_ctx* c) { return c ? (int64_t)c->psf.p.size() : GPET_ERR_ARG; }
+
+// =================================================================================================== planning
+int64_t gpet_plan_frames(gpet_ctx* c, uint64_t max_pairs) {
+    if (!c) return GPET_ERR_ARG;
+    if (!c->have_src || !c->have_iso) return fail(c, GPET_ERR_ARG, "source and isotope files must be loaded before planning");
+    for (int i = 0; i < c->src.n(); i++)
+        if (c->src.type[i] < 0 || c->src.type[i] >= c->iso.n()) return fail(c, GPET_ERR_FORMAT, "source isotope type out of range");
+    uint64_t cap_pairs = c->cap_photons / 2;
+    if (max_pairs == 0 || max_pairs > cap_pairs) max_pairs = cap_pairs;
+    c->max_pairs_per_frame = max_pairs;
+    std::string e = plan_frames(c->src, c->iso, c->tstart, c->tend, max_pairs, c->seed, c->frames);
+    if (!e.empty()) return fail(c, GPET_ERR_ARG, e);
+    c->planned = true;
+    if (c->has_device) {
+        // upload the per-frame source descriptors
+        std::vector<SourceDev> fr(c->frames.size());
+        for (size_t f = 0; f < fr.size(); f++) fill_source_dev(c->src, c->iso, c->frames[f], c->tr.noncollinearity_rad, c->tr.use_positron_range, fr[f]);
+        cudaSetDevice(c->device);
+        if (fr.size() > c->d_frames_n) {
+            int r;
+            if ((r = dev_alloc(c, &c->d_frames, fr.size()))) return r;
+            c->d_frames_n = fr.size();
+        }
+        if (!fr.empty()) CK(cudaMemcpy(c->d_frames, fr.data(), fr.size() * sizeof(SourceDev), cudaMemcpyHostToDevice));
+    }
+    return (int64_t)c->frames.size();
+}
+
+int64_t gpet_frame_pairs(const gpet_ctx* c, int64_t f) {
+    if (!c || !c->planned || f < 0 || f >= (int64_t)c->frames.size()) return GPET_ERR_ARG;
+    return (int64_t)c->frames[(size_t)f].npairs;
+}
+
+// =================================================================================================== stages
+int gpet_stage_source(gpet_ctx* c, int64_t f) {
+    NEED_DEVICE();
+    if (!c->planned) return fail(c, GPET_ERR_ARG, "gpet_plan_frames must be called first");
+    if (f < 0 || f >= (int64_t)c->frames.size()) return fail(c, GPET_ERR_ARG, "frame index out of range");
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    const FramePlan& fp = c->frames[(size_t)f];
+    if (2 * fp.npairs > c->cap_photons) return fail(c, GPET_ERR_CAPACITY, "frame exceeds the photon capacity");
+    c->stats.kernel_launches += launch_source(c->d_frames + f, fp.npairs, PhantomDev{}, c->q[0], c->seed, c->num_sms, c->stream);
+    CK(cudaGetLastError());
+    return GPET_OK;
+}
+
+int gpet_stage_psf(gpet_ctx* c, int64_t first, int64_t n) {
+    NEED_DEVICE();
+    if (!c->have_psf) return fail(c, GPET_ERR_ARG, "no PSF loaded");
+    if (first < 0 || n < 0 || first + n > (int64_t)c->psf.p.size()) return fail(c, GPET_ERR_ARG, "PSF range out of bounds");
+    if (c->psf.ptype == 0) return fail(c, GPET_ERR_ARG, "positron PSF input is not implemented yet");
+    return gpet_put_photons(c, 0, c->psf.p.data() + first, n);
+}
+
+int gpet_stage_phantom(gpet_ctx* c) {
+    NEED_DEVICE();
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((r = upload_phantom(c))) return r;
+    c->stats.kernel_launches += launch_phantom(c->q[0], c->q[1], phantom_dev(c), tables_dev(c), c->tr.eabs_eV, c->seed, c->num_sms, c->stream);
+    CK(cudaGetLastError());
+    return GPET_OK;
+}
+
+int gpet_stage_detector(gpet_ctx* c) {
+    NEED_DEVICE();
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((r = upload_geometry(c))) return r;
+    c->stats.kernel_launches += launch_detector(c->q[1], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth,
+                                                c->dig.readout_policy, c->tr.record_hits, c->hits, c->ev, c->ws.counters,
+                                                c->seed, c->num_sms, c->stream);
+    CK(cudaGetLastError());
+    return GPET_OK;
+}
+
+int gpet_stage_digitize(gpet_ctx* c) {
+    NEED_DEVICE();
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    DigitizerDev d = digitizer_dev(c);
+    c->stats.kernel_launches += launch_digitize(c->ev, c->singles, c->singles_aos, c->coinc_aos, c->coinc_cap, d, c->ws, c->seed, c->num_sms, c->stream);
+    CK(cudaGetLastError());
+    return GPET_OK;
+}
+
+// =================================================================================================== buffer access
+int64_t gpet_queue_size(gpet_ctx* c, int which) {
+    NEED_DEVICE();
+    if (which < 0 || which > 1) return GPET_ERR_ARG;
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((r = read_counters(c))) return r;
+    return (int64_t)std::min<unsigned>(c->h_counters[18 + which], c->q[which].capacity);
+}
+
+int gpet_put_photons(gpet_ctx* c, int which, const gpet_photon* in, int64_t n) {
+    NEED_DEVICE();
+    if (which < 0 || which > 1 || n < 0 || (n > 0 && !in)) return GPET_ERR_ARG;
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((uint64_t)n > c->cap_photons) return fail(c, GPET_ERR_CAPACITY, "photon batch exceeds capacity");
+    if (n) CK(cudaMemcpyAsync(c->stage_aos, in, (size_t)n * sizeof(gpet_photon), cudaMemcpyHostToDevice, c->stream));
+    c->stats.kernel_launches += launch_photons_aos_to_queue(c->stage_aos, c->q[which], (unsigned)n, c->stream);
+    CK(cudaGetLastError());
+    return GPET_OK;
+}
+
+int64_t gpet_fetch_photons(gpet_ctx* c, int which, gpet_photon* out, int64_t cap) {
+    int64_t n = gpet_queue_size(c, which);
+    if (n < 0) return n;
+    n = std::min(n, cap);
+    if (n == 0) return 0;
+    c->stats.kernel_launches += launch_queue_to_photons_aos(c->q[which], c->stage_aos, c->stream);
+    CK(cudaMemcpyAsync(out, c->stage_aos, (size_t)n * sizeof(gpet_photon), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return n;
+}
+
+int gpet_put_events(gpet_ctx* c, const gpet_event* in, int64_t n) {
+    NEED_DEVICE();
+    if (n < 0 || (n > 0 && !in)) return GPET_ERR_ARG;
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((uint64_t)n > c->cap_events) return fail(c, GPET_ERR_CAPACITY, "event list exceeds capacity");
+    if (n) CK(cudaMemcpyAsync(c->stage_aos, in, (size_t)n * sizeof(gpet_event), cudaMemcpyHostToDevice, c->stream));
+    c->stats.kernel_launches += launch_events_aos_to_soa(c->stage_aos, c->ev, (unsigned)n, c->stream);
+    CK(cudaGetLastError());
+    return GPET_OK;
+}
+
+int64_t gpet_fetch_events(gpet_ctx* c, gpet_event* out, int64_t cap) {
+    NEED_DEVICE();
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((r = read_counters(c))) return r;
+    int64_t n = std::min<int64_t>(std::min<unsigned>(c->h_counters[16], c->ev.capacity), cap);
+    if (n <= 0) return 0;
+    c->stats.kernel_launches += launch_events_soa_to_aos(c->ev, c->stage_aos, c->stream);
+    CK(cudaMemcpyAsync(out, c->stage_aos, (size_t)n * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return n;
+}
+
+int64_t gpet_fetch_hits(gpet_ctx* c, gpet_hit* out, int64_t cap) {
+    NEED_DEVICE();
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((r = read_counters(c))) return r;
+    int64_t n = std::min<int64_t>(std::min<unsigned>(c->h_counters[17], c->hits.capacity), cap);
+    if (n <= 0) return 0;
+    std::vector<int32_t> id((size_t)5 * n);
+    std::vector<float> f((size_t)5 * n);
+    std::vector<double> t((size_t)n);
+    CK(cudaMemcpyAsync(id.data(), c->hits.id, id.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(f.data(), c->hits.f, f.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(t.data(), c->hits.t, t.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int64_t k = 0; k < n; k++) {
+        gpet_hit& h = out[k];
+        h.parn = id[5 * k]; h.pann = id[5 * k + 1]; h.modn = id[5 * k + 2]; h.cryn = id[5 * k + 3]; h.type = id[5 * k + 4];
+        h.E = f[5 * k]; h.t32 = f[5 * k + 1]; h.x = f[5 * k + 2]; h.y = f[5 * k + 3]; h.z = f[5 * k + 4];
+        h.t = t[k];
+    }
+    return n;
+}
+
+int64_t gpet_fetch_singles(gpet_ctx* c, gpet_event* out, int64_t cap) {
+    NEED_DEVICE();
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((r = read_counters(c))) return r;
+    int64_t n = std::min<int64_t>(std::min<unsigned>(c->h_counters[3], c->singles.capacity), cap);
+    if (n <= 0) return 0;
+    CK(cudaMemcpyAsync(out, c->singles_aos, (size_t)n * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return n;
+}
+
+int64_t gpet_fetch_coincidences(gpet_ctx* c, gpet_coincidence* out, int64_t cap) {
+    NEED_DEVICE();
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((r = read_counters(c))) return r;
+    int64_t n = std::min<int64_t>(std::min<unsigned>(c->h_counters[4], c->coinc_cap), cap);
+    if (n <= 0) return 0;
+    CK(cudaMemcpyAsync(out, c->coinc_aos, (size_t)n * sizeof(gpet_coincidence), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return n;
+}
+
+int gpet_last_counts(gpet_ctx* c, uint64_t counts[4]) {
+    NEED_DEVICE();
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((r = read_counters(c))) return r;
+    for (int k = 0; k < 4; k++) counts[k] = c->h_counters[k];
+    return GPET_OK;
+}
+
+// =================================================================================================== whole path
+int gpet_digitize(gpet_ctx* c, const gpet_event* in, int64_t n, gpet_event* out, int64_t cap, int64_t* n_out,
+                  uint64_t counts[4]) {
+    NEED_DEVICE();
+    int r;
+    if ((r = gpet_put_events(c, in, n))) return r;
+    if ((r = gpet_stage_digitize(c))) return r;
+    if ((r = read_counters(c))) return r;
+    if (counts)
+        for (int k = 0; k < 4; k++) counts[k] = c->h_counters[k];
+    int64_t ns = c->h_counters[3];
+    if (n_out) *n_out = ns;
+    if (ns > cap) return fail(c, GPET_ERR_CAPACITY, "output buffer too small for the singles list");
+    if (ns > 0 && out) {
+        CK(cudaMemcpyAsync(out, c->singles_aos, (size_t)ns * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return GPET_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// append `bytes` from a device pointer to a file (outputData / outevents, detector.cu:287-307, 387-408)
+int append_device(gpet_ctx* c, const std::string& path, const void* dptr, size_t bytes, std::vector<char>& tmp) {
+    if (!bytes) return GPET_OK;
+    tmp.resize(bytes);
+    CK(cudaMemcpyAsync(tmp.data(), dptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    FILE* f = fopen(path.c_str(), "ab");
+    if (!f) return fail(c, GPET_ERR_IO, "cannot open " + path + " for appending");
+    fwrite(tmp.data(), 1, bytes, f);
+    fclose(f);
+    return GPET_OK;
+}
+
+int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* stats_out) {
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    const bool psf_mode = c->usepsf != 0;
+    if (!psf_mode && !c->planned) {
+        int64_t nf = gpet_plan_frames(c, c->max_pairs_per_frame);
+        if (nf < 0) return (int)nf;
+    }
+    if (psf_mode && !c->have_psf) return fail(c, GPET_ERR_ARG, "no PSF loaded");
+    gpet_stats st{};
+    const uint64_t launches0 = c->stats.kernel_launches;
+    c->res_singles.clear();
+    c->res_coinc.clear();
+    std::vector<char> tmp;
+    std::string od = output_dir ? output_dir : "";
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, c->stream));
+    const int64_t psf_batch = (int64_t)c->cap_photons;  // simulateParticle batches of NPART photons (gPET.cu:33-44)
+    const int64_t nframes = psf_mode ? ((int64_t)c->psf.p.size() + psf_batch - 1) / psf_batch : (int64_t)c->frames.size();
+    for (int64_t f = 0; f < nframes; f++) {
+        if (f % c->world != c->rank) continue;
+        if (psf_mode) {
+            int64_t first = f * psf_batch, n = std::min<int64_t>(psf_batch, (int64_t)c->psf.p.size() - first);
+            if ((r = gpet_stage_psf(c, first, n))) return r;
+            st.pairs += (uint64_t)n / 2;
+        } else {
+            if (c->frames[(size_t)f].npairs == 0) continue;
+            if ((r = gpet_stage_source(c, f))) return r;
+            st.pairs += c->frames[(size_t)f].npairs;
+        }
+        if ((r = gpet_stage_phantom(c))) return r;
+        if ((r = gpet_stage_detector(c))) return r;
+        if ((r = gpet_stage_digitize(c))) return r;
+        st.frames++;
+        if ((r = read_counters(c))) return r;   // one small D2H + sync per frame
+        const unsigned* h = c->h_counters;
+        const uint64_t n_ev = h[16], n_hits = h[17], n_q1 = h[19];
+        st.photons_phantom_out += n_q1;
+        st.photons_on_panel += h[8];
+        st.hits += n_hits;
+        st.events_adder += h[0];
+        st.events_threshold += h[1];
+        st.events_deadtime += h[2];
+        st.singles += h[3];
+        st.coincidences += h[4];
+        st.overflow_adder += h[9];
+        if (n_hits > c->hits.capacity) st.overflow_hits += n_hits - c->hits.capacity;
+        if (n_ev > c->ev.capacity) st.overflow_events += n_ev - c->ev.capacity;
+        if (n_q1 > c->q[1].capacity) st.overflow_events += n_q1 - c->q[1].capacity;
+        if (h[4] > c->coinc_cap) st.overflow_events += h[4] - c->coinc_cap;
+        if (resident) continue;
+        const size_t ns = std::min<size_t>(h[3], c->singles.capacity), nc = std::min<size_t>(h[4], c->coinc_cap);
+        if (ns) {
+            size_t old = c->res_singles.size();
+            c->res_singles.resize(old + ns);
+            CK(cudaMemcpyAsync(c->res_singles.data() + old, c->singles_aos, ns * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (nc && c->dig.coinc_window_us > 0.f) {
+            size_t old = c->res_coinc.size();
+            c->res_coinc.resize(old + nc);
+            CK(cudaMemcpyAsync(c->res_coinc.data() + old, c->coinc_aos, nc * sizeof(gpet_coincidence), cudaMemcpyDeviceToHost, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        if (!od.empty()) {
+            const size_t nh = std::min<size_t>(n_hits, c->hits.capacity), ne = std::min<size_t>(n_ev, c->ev.capacity);
+            if (c->tr.record_hits) {
+                if ((r = append_device(c, join_path(od, "HitsID.dat"), c->hits.id, nh * 5 * sizeof(int32_t), tmp))) return r;
+                if ((r = append_device(c, join_path(od, "Hits.dat"), c->hits.f, nh * 5 * sizeof(float), tmp))) return r;
+            }
+            // note: adder.dat of the reference is written before blur; blur runs in place, so with blur enabled the
+            // energies in this dump are the blurred ones
+            c->stats.kernel_launches += launch_events_soa_to_aos(c->ev, c->stage_aos, c->stream);
+            if ((r = append_device(c, join_path(od, "adder.dat"), c->stage_aos, ne * sizeof(gpet_event), tmp))) return r;
+            FILE* fs = fopen(join_path(od, "singles.dat").c_str(), "ab");
+            if (!fs) return fail(c, GPET_ERR_IO, "cannot open singles.dat for appending");
+            if (ns) fwrite(c->res_singles.data() + (c->res_singles.size() - ns), sizeof(gpet_event), ns, fs);
+            fclose(fs);
+            if (c->dig.coinc_window_us > 0.f) {
+                FILE* fc = fopen(join_path(od, "coincidences.dat").c_str(), "ab");
+                if (!fc) return fail(c, GPET_ERR_IO, "cannot open coincidences.dat for appending");
+                if (nc) fwrite(c->res_coinc.data() + (c->res_coinc.size() - nc), sizeof(gpet_coincidence), nc, fc);
+                fclose(fc);
+            }
+        }
+    }
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    st.ms_total = ms;
+    st.kernel_launches = c->stats.kernel_launches - launches0;
+    const uint64_t keep = c->stats.kernel_launches;
+    c->stats = st;
+    c->stats.kernel_launches = keep;
+    if (stats_out) *stats_out = st;
+    if (st.overflow_hits || st.overflow_events)
+        return fail(c, GPET_ERR_CAPACITY, "a device buffer overflowed; raise gpet_set_capacity");
+    return GPET_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpet_run(gpet_ctx* c, const char* output_dir, gpet_stats* stats) {
+    NEED_DEVICE();
+    return run_impl(c, output_dir, false, stats);
+}
+
+int gpet_run_resident(gpet_ctx* c, gpet_stats* stats) {
+    NEED_DEVICE();
+    return run_impl(c, nullptr, true, stats);
+}
+
+int64_t gpet_result_singles(gpet_ctx* c, const gpet_event** ptr) {
+    if (!c || !ptr) return GPET_ERR_ARG;
+    *ptr = c->res_singles.data();
+    return (int64_t)c->res_singles.size();
+}
+
+int64_t gpet_result_coincidences(gpet_ctx* c, const gpet_coincidence** ptr) {
+    if (!c || !ptr) return GPET_ERR_ARG;
+    *ptr = c->res_coinc.data();
+    return (int64_t)c->res_coinc.size();
+}
+
+int gpet_get_stats(const gpet_ctx* c, gpet_stats* s) {
+    if (!c || !s) return GPET_ERR_ARG;
+    *s = c->stats;
+    return GPET_OK;
+}
+
+int gpet_set_spectrum(gpet_ctx* c, int nbins, float emin, float emax) {
+    if (!c || nbins < 1 || nbins > (1 << 20) || !(emax > emin)) return GPET_ERR_ARG;
+    if (c->dev_buffers) return fail(c, GPET_ERR_ARG, "spectrum must be configured before the first compute call");
+    c->ws.spectrum_bins = nbins; c->ws.spec_emin = emin; c->ws.spec_emax = emax;
+    return GPET_OK;
+}
+
+int gpet_get_spectrum(gpet_ctx* c, uint64_t* bins, int nbins) {
+    NEED_DEVICE();
+    if (!bins || nbins != c->ws.spectrum_bins || !c->ws.spectrum) return fail(c, GPET_ERR_ARG, "spectrum not configured");
+    CK(cudaMemcpyAsync(bins, c->ws.spectrum, sizeof(uint64_t) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return GPET_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+// The library context: host-side inputs (parsed files), device buffers, frame plan, results.
+// Replaces the reference's host globals (gPETInternal.h:6-63) and static __device__ arrays (gPET_kernals.h:5-73).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "device_types.cuh"
+#include "host_io.hpp"
+#include "kernels.hpp"
+
+struct FramePlan {
+    double t0_s = 0.0, dt_s = 0.0;             // absolute start (s) and length of the slice
+    std::vector<uint64_t> pairs;               // per source
+    uint64_t npairs = 0, first_pair = 0;
+};
+
+struct gpet_ctx {
+    int device = -1;
+    bool has_device = false;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    mutable std::string err;
+    uint64_t seed = 0x67504554ull;  // "gPET"
+
+    // ---- host inputs
+    gpet::Config cfg;
+    gpet::Geometry geo;
+    gpet::Isotopes iso;
+    gpet::Sources src;
+    gpet::Phantom ph;
+    gpet::Psf psf;
+    gpet::Tables tab;
+    bool have_geo = false, have_iso = false, have_src = false, have_ph = false, have_psf = false;
+    int usepsf = 0;
+    gpet_digitizer_params dig{};
+    gpet_transport_params tr{};
+    float tstart = 0.f, tend = 1.f;
+    std::vector<float> maj_ph, maj_det;
+    int rank = 0, world = 1;
+
+    // ---- capacities
+    uint64_t cap_photons = 1ull << 22, cap_hits = 1ull << 23, cap_events = 1ull << 22;
+    uint64_t max_pairs_per_frame = 0;
+
+    // ---- device state
+    bool dev_buffers = false, dev_tables = false, dev_phantom = false, dev_geo = false;
+    gpet::PhotonQueue q[2]{};
+    gpet::HitBuffer hits{};
+    gpet::EventSoA ev{}, singles{};
+    gpet::DigitizerWorkspace ws{};
+    void* singles_aos = nullptr;
+    void* coinc_aos = nullptr;
+    unsigned coinc_cap = 0;
+    void* stage_aos = nullptr;       // cap * 48 B staging for AoS <-> SoA conversion
+    size_t stage_bytes = 0;
+    gpet::PanelDev* d_panels = nullptr;
+    uint32_t* d_vox = nullptr;
+    float4* d_xs = nullptr;
+    float *d_maj_ph = nullptr, *d_maj_det = nullptr, *d_cmpsf = nullptr, *d_rayff = nullptr;
+    gpet::SourceDev* d_frames = nullptr;
+    size_t d_frames_n = 0;
+    unsigned long long* d_totals = nullptr;  // accumulated counters of all frames (resident runs)
+    unsigned* h_counters = nullptr;          // pinned, 32 words
+    unsigned long long* h_totals = nullptr;  // pinned, 32 words
+    std::vector<void*> allocs;
+
+    // ---- frames / results
+    std::vector<FramePlan> frames;
+    bool planned = false;
+    std::vector<gpet_event> res_singles;
+    std::vector<gpet_coincidence> res_coinc;
+    gpet_stats stats{};
+    uint64_t last_counts[4] = {0, 0, 0, 0};
+    int64_t psf_first = 0;  // global index of photon 0 of the current PSF batch
+};

@@ -1,0 +1,119 @@
+// Device-side data layout shared by the kernels and the ABI layer.  All buffers are SoA in HBM.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gpet {
+
+constexpr double kSpeedOfLight = 29979.2458;          // cm/us (gPET_kernals.cu:264)
+constexpr double kInvSpeedOfLight = 1.0 / 29979.2458;
+constexpr float kMC2 = 510.9991e3f;                   // constants.h:33
+constexpr float kIMC2 = 1.95695060911e-6f;            // constants.h:34
+constexpr float kTwoPi = 6.2831853071795864769252867f;
+constexpr double kMaxT = 1e20;                        // constants.h:18 MAXT
+
+// Philox stream ids (counter word 2, high byte)
+enum Stage : uint32_t {
+    kStageSource = 1, kStagePhantom = 2, kStageDetector = 3, kStageBlur = 4, kStagePlan = 5, kStagePsfPositron = 6
+};
+
+// Photon phase-space queue: 48 B per photon, 16-byte vector accesses.
+struct PhotonQueue {
+    float4* pos_e;        // x, y, z, E
+    float4* dir_n;        // vx, vy, vz, bit-cast nscat
+    double* t;            // us; <= 0 dead
+    int2* ids;            // eventid, parn
+    unsigned int* count;  // device counter
+    unsigned int capacity;
+};
+
+// Hits in file layout: row k occupies id[5k..5k+4] (HitsID.dat) and f[5k..5k+4] (Hits.dat).
+struct HitBuffer {
+    int* id;              // parn, pann, modn, cryn, type
+    float* f;             // E, t(float32), x, y, z
+    double* t;            // fp64 time (extension)
+    unsigned int* count;
+    unsigned int capacity;
+};
+
+// Post-readout events / singles as SoA.
+struct EventSoA {
+    int* parn; int* pann; int* modn; int* cryn; int* siten; int* eventid;
+    double* t;
+    float* E; float* x; float* y; float* z;
+    unsigned int* count;
+    unsigned int capacity;
+};
+
+struct PanelDev {  // one panel, 128 B
+    float ox, oy, oz;          // offset (front-face centre)
+    float uxx, uxy, uxz;       // local x axis in global frame
+    float uyx, uyy, uyz;
+    float uzx, uzy, uzz;
+    float lx, ly, lz;          // panel dimensions
+    float dirx;                // expansion direction along local x (+-1)
+    float mody, modz;          // module size
+    float mspy, mspz;          // module gap
+    float lsoy, lsoz;          // crystal size
+    float spy, spz;            // crystal gap
+    int id;
+    float pad[7];
+};
+static_assert(sizeof(PanelDev) == 128, "PanelDev must be 128 B");
+
+struct DetectorDev {
+    const PanelDev* panels;
+    int npanels;
+    int moduleNy, crystalNy, moduleN, crystalN;
+    int mat[2];
+    float dens[2];
+    int nsurface;
+    float surface[50];
+};
+
+struct PhantomDev {
+    const uint32_t* vox;   // packed: fp32 density with the material id in the 4 low mantissa bits
+    int nx, ny, nz;
+    float ox, oy, oz;      // offset
+    float idx, idy, idz;   // 1/voxel size
+};
+
+struct TablesDev {
+    // float4 per (material, energy node): Sigma_tot, Sigma_compton, Sigma_rayleigh, Sigma_photo (cm^2/g)
+    const float4* xs;
+    const float* maj_phantom;   // Sigma_max(E) 1/cm on the same grid
+    const float* maj_detector;
+    const float* cmpsf;         // [mat][icp][ie]
+    const float* rayff;
+    int nmat, nen;
+    float e0, ide;              // index = ide * (E - e0)
+    int cm_ncp, cm_ne, rl_ncp, rl_ne;
+    float cm_idcp, cm_ide, rl_idcp, rl_ide;
+};
+
+struct SourceDev {   // per-frame source description (<= GPET_MAX_SOURCES entries)
+    int nsource;
+    unsigned long long cum_pairs[64];  // inclusive prefix of pairs per source in this frame
+    int type[64], shape[64];
+    float coeff[64 * 6];
+    double tau_s[64];       // mean life (s) = T_half * 1.442695 as in gPET_kernals.cu:519
+    double frac[64];        // 1 - exp(-dt/tau): truncated-exponential normaliser for this frame
+    float iso_coef[16 * 8];
+    double t0_s;            // frame start (s, absolute acquisition time)
+    unsigned long long first_pair;  // global index of pair 0 of this frame
+    float nonangle;
+    int use_prange;
+};
+
+struct DigitizerDev {
+    int readout_depth, readout_policy;
+    float Eth;
+    int blur_policy; float Eref, Rref, slope, sblur;
+    int dlevel, dtype; float dtime;
+    float Ewinmin, Ewinmax;
+    float tblur; float cwin; int cpolicy; int cmindiff;
+    int npanels;
+    int moduleN, crystalN;
+};
+
+}  // namespace gpet

@@ -1,0 +1,264 @@
+/*
+ * gpet_b200.h -- C ABI of libgpet_b200.so, the B200-native (sm_100a) implementation of gPET's
+ * Monte-Carlo hot path (source sampling -> phantom transport -> detector transport -> digitizer).
+ *
+ * The reference (utaresearch/gPET) has no FFI/plugin layer: its surface is the CLI `./gPET input_PET.in`,
+ * the input/output file formats and the host call sequence declared in gPET.h:128-166.  Every entry point
+ * below names the reference host function (file:line under /root/reference) whose job it takes over.
+ * Only plain pointers, sizes and POD structs cross this boundary (no C++/torch types).
+ *
+ * Conventions
+ *   - every function returns GPET_OK (0) or a negative gpet_status; gpet_last_error() gives the text.
+ *     The library never calls exit() (the reference's CUDA_CALL/FILEEXIST macros do, gPET.h:17-18).
+ *   - a context is single-threaded and owns one GPU (reference: one device, default stream, main.cu:54,192).
+ *   - device = -1 creates a HOST-ONLY context: loaders/parsers/getters work, every compute entry point fails
+ *     with GPET_ERR_NO_DEVICE.  There is no CPU fallback for the hot path.
+ *   - units follow the reference: length cm, energy eV, time us (fp64), c = 29979.2458 cm/us.
+ */
+#ifndef GPET_B200_H
+#define GPET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPET_ABI_VERSION 1
+
+typedef enum gpet_status {
+    GPET_OK = 0,
+    GPET_ERR_ARG = -1,        /* bad argument / state (e.g. stage called before its inputs were loaded) */
+    GPET_ERR_IO = -2,         /* file missing / short / malformed */
+    GPET_ERR_CUDA = -3,       /* CUDA runtime error (text in gpet_last_error) */
+    GPET_ERR_NO_DEVICE = -4,  /* compute call on a host-only context */
+    GPET_ERR_CAPACITY = -5,   /* a device buffer overflowed (hits / events); rerun with larger capacity */
+    GPET_ERR_FORMAT = -6      /* table/geometry content inconsistent (e.g. material id out of range) */
+} gpet_status;
+
+typedef struct gpet_ctx gpet_ctx;
+
+/* ---- records ------------------------------------------------------------------------------------------ */
+
+/* 48-byte single/event record, byte-identical to the reference `Event` (gPET.h:87-92) and to what
+ * output/readOutput.m:18-34 reads: 6 x int32, 1 x float64, 4 x float32. */
+typedef struct gpet_event {
+    int32_t parn, pann, modn, cryn, siten, eventid;
+    double  t;          /* us */
+    float   E, x, y, z; /* eV; panel-local cm */
+} gpet_event;
+
+/* 96-byte coincidence record (extension: the reference has no coincidence sorter):
+ * the two singles of the pair, earlier one first. */
+typedef struct gpet_coincidence {
+    gpet_event a, b;
+} gpet_coincidence;
+
+/* One detector hit = one row of HitsID.dat (5 x int32) + one row of Hits.dat (5 x float32)
+ * (gPET_kernals.cu:1062-1080, readOutput.m:3-16).  t is also carried in fp64 (extension). */
+typedef struct gpet_hit {
+    int32_t parn, pann, modn, cryn, type; /* type: 1 Compton, 2 Compton below Eabs, 3 Rayleigh, 4 photoelectric */
+    float   E, t32, x, y, z;
+    double  t;
+} gpet_hit;
+
+/* Photon phase-space record (host side), same quantities as the reference's x/vx/d_time/d_eventid
+ * arrays (gPET_kernals.h:6-9).  t <= 0 marks a dead/empty photon. */
+typedef struct gpet_photon {
+    float   x, y, z, E;
+    float   vx, vy, vz;
+    int32_t nscat;      /* phantom scatter count (extension) */
+    double  t;
+    int32_t eventid, parn;
+} gpet_photon;
+
+/* Panel geometry, same fields as the reference `object_t` (gPET.h:54-78). */
+typedef struct gpet_panel {
+    int32_t panel;
+    float lengthx, lengthy, lengthz;
+    float MODx, MODy, MODz;
+    float Mspacex, Mspacey, Mspacez;
+    float LSOx, LSOy, LSOz;
+    float spacex, spacey, spacez;
+    float offsetx, offsety, offsetz;
+    float directionx, directiony, directionz;
+    float UniXx, UniXy, UniXz;
+    float UniYx, UniYy, UniYz;
+    float UniZx, UniZy, UniZz;
+} gpet_panel;
+
+#define GPET_MAX_SURFACES 5  /* constants.h:19 MAXSURFACE */
+#define GPET_MAX_SOURCES 64
+#define GPET_MAX_ISOTOPES 16
+#define GPET_MAX_MATERIALS 16
+
+/* Digitizer parameters = input_PET.in fields 18-22 (main.cu:149-182) + extensions. */
+typedef struct gpet_digitizer_params {
+    int32_t readout_depth;   /* 0 world, 1 panel, 2 module, 3 crystal (gPET_kernals.cu:756-784) */
+    int32_t readout_policy;  /* 0 winner-take-all, 1 energy centroid (forces depth 2) */
+    float   threshold_eV;    /* Eth: first energy window is [Eth, 2e6] (gPET.cu:155,393) */
+    int32_t blur_policy;     /* 0: R = sqrt(Eref/E)*Rref ; 1: R = Rref + slope*(E-Eref)/1e6 (gPET_kernals.cu:822-823) */
+    float   blur_Eref, blur_Rref, blur_slope, blur_space;
+    int32_t dead_level;      /* 0..3; 3 = keep the siten left by readout (gPET.cu:164-169) */
+    int32_t dead_type;       /* 0 paralyzable, 1 non-paralyzable (gPET_kernals.cu:657-698) */
+    float   dead_time_us;
+    float   ewin_min, ewin_max;
+    /* --- extensions (no reference counterpart; 0 disables) --- */
+    float   time_blur_sigma_us;  /* Gaussian blur of t */
+    float   coinc_window_us;     /* coincidence window; 0 = no coincidence sorting */
+    int32_t coinc_policy;        /* 0 drop multiples (window with != 2 singles), 1 all pairs with the window opener */
+    int32_t coinc_min_panel_diff;/* minimum |panel difference| (cyclic) for a valid pair; 0 = any two distinct sites */
+} gpet_digitizer_params;
+
+/* Transport parameters = input_PET.in fields 2, 12, 15, 17 (main.cu:57-60, 117-120, 135-147). */
+typedef struct gpet_transport_params {
+    float   noncollinearity_rad; /* sigma of the Gaussian acollinearity */
+    int32_t use_positron_range;
+    float   eabs_eV;             /* photon absorption energy */
+    int32_t nsurface;
+    float   surface[10 * GPET_MAX_SURFACES];
+    int32_t record_hits;         /* OUTPUTHIT (constants.h:6): keep Hits/HitsID rows */
+} gpet_transport_params;
+
+/* Run counters (the numbers the reference prints per epoch, gPET.cu:293,364,382,398,415,423). */
+typedef struct gpet_stats {
+    uint64_t pairs;            /* annihilation pairs emitted */
+    uint64_t photons_phantom_out; /* photons alive after the phantom */
+    uint64_t photons_on_panel; /* photons that entered a panel front face */
+    uint64_t hits;             /* rows of Hits.dat */
+    uint64_t events_adder;     /* "counts of events after adder" */
+    uint64_t events_threshold; /* "after thresholder" */
+    uint64_t events_deadtime;  /* "after deadtime" */
+    uint64_t singles;          /* "counts of singles" */
+    uint64_t coincidences;     /* extension */
+    uint64_t overflow_hits, overflow_events, overflow_adder; /* dropped records (must be 0) */
+    uint64_t frames;
+    uint64_t kernel_launches;  /* launches of this library's own kernels */
+    double   ms_source, ms_phantom, ms_detector, ms_digitizer, ms_total; /* CUDA-event times */
+} gpet_stats;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------------- */
+
+int gpet_abi_version(void);
+/* iniDevice(deviceNo) (iniDevice.cu:42-58).  device < 0: host-only context. */
+int gpet_create(int device, gpet_ctx** out);
+void gpet_destroy(gpet_ctx* ctx);
+const char* gpet_last_error(const gpet_ctx* ctx);
+/* Run all kernels on an external cudaStream_t (e.g. torch's current stream). NULL = library-owned stream. */
+int gpet_set_stream(gpet_ctx* ctx, void* cuda_stream);
+/* Philox key.  Replaces srand(time(NULL)) + curand_init (initialize.cu:256-272). */
+int gpet_set_seed(gpet_ctx* ctx, uint64_t seed);
+/* Capacities in photons/hits/events per frame (reference: NPART, NSSTACK/5, 3*NPART; constants.h:13-16). */
+int gpet_set_capacity(gpet_ctx* ctx, uint64_t max_photons, uint64_t max_hits, uint64_t max_events);
+
+/* ---- loaders: the reference's input contract ------------------------------------------------------------ */
+
+/* main.cu:50-184 positional parse of input_PET.in + the whole init chain (main.cu:192-229): loads the phantom,
+ * geometry and source/PSF files it names (relative to base_dir, NULL = cwd) and the table set
+ * `<data_dir>/input4gPET.*` (NULL = "<base_dir>/data"). */
+int gpet_load_config_file(gpet_ctx* ctx, const char* input_file, const char* base_dir, const char* data_dir);
+/* rmater/rlamph/rcompt/rcmpsf/rphote/rrayle/rrayff (initialize.cu:279-748).  prefix e.g. "data/input4gPET".
+ * Table dimensions come from the file headers.  A prefix ending in ".gpettab" loads a packed binary set. */
+int gpet_load_tables(gpet_ctx* ctx, const char* prefix);
+int gpet_save_tables_packed(gpet_ctx* ctx, const char* path);
+/* loadPhantom + initPhantom + iniwck(phantom) (initialize.cu:32-74, 831-884, 773-829). int32 mat, float32 density, x fastest. */
+int gpet_load_phantom_files(gpet_ctx* ctx, const char* mat_file, const char* den_file,
+                            const int32_t dim[3], const float offset[3], const float size[3]);
+int gpet_set_phantom(gpet_ctx* ctx, const int32_t* mat, const float* dens,
+                     const int32_t dim[3], const float offset[3], const float size[3]);
+/* read_file_ro + iniPanel + iniwck(detector) (detector.cu:64-285, initialize.cu:969-1224, 919-966). */
+int gpet_load_geometry(gpet_ctx* ctx, const char* geo_file);
+/* loadIsotopes / readSource (initialize.cu:10-31, 116-144). */
+int gpet_load_isotopes(gpet_ctx* ctx, const char* isotopes_file);
+int gpet_load_source(gpet_ctx* ctx, const char* source_file);
+/* readParticle (initialize.cu:76-115): 8 x fp64 per record (x y z t vx vy vz E). ptype 0 positron, 1 photon. */
+int gpet_load_psf(gpet_ctx* ctx, const char* psf_file, int64_t max_particles, int ptype);
+int gpet_set_digitizer(gpet_ctx* ctx, const gpet_digitizer_params* p);
+int gpet_get_digitizer(const gpet_ctx* ctx, gpet_digitizer_params* p);
+int gpet_set_transport(gpet_ctx* ctx, const gpet_transport_params* p);
+int gpet_get_transport(const gpet_ctx* ctx, gpet_transport_params* p);
+/* tstart, tend in seconds (input_PET.in field 13). */
+int gpet_set_time_window(gpet_ctx* ctx, float tstart_s, float tend_s);
+/* Override the atom count of one source (synthetic scaling of the activity). */
+int gpet_set_source_atoms(gpet_ctx* ctx, int source_index, uint64_t natom);
+
+/* ---- getters (host state; used by the parity tests) --------------------------------------------------- */
+
+int gpet_get_num_panels(const gpet_ctx* ctx);
+int gpet_get_panels(const gpet_ctx* ctx, gpet_panel* out, int cap);
+/* moduleNy, crystalNy, moduleN, crystalN (initialize.cu:1074-1086) and the two panel materials/densities. */
+int gpet_get_geometry_counts(const gpet_ctx* ctx, int32_t counts[4], int32_t mat[2], float dens[2]);
+/* nmat, n energies, e0, de of the 1-D tables; surface dims of cmpsf and rayff. */
+int gpet_get_table_dims(const gpet_ctx* ctx, int32_t* nmat, int32_t* nen, float* e0, float* e1,
+                        int32_t cmpsf_dims[2], float cmpsf_step[2], int32_t rayff_dims[2], float rayff_step[2]);
+/* which: 0 lamph, 1 compt, 2 phote, 3 rayle (nmat*nen floats); 4 cmpsf surface, 5 rayff surface (nmat*ncp*ne);
+ * 6 phantom majorant Sigma_max(E) (nen floats, 1/cm), 7 detector majorant. Returns number of floats written. */
+int64_t gpet_get_table(const gpet_ctx* ctx, int which, float* out, int64_t cap);
+int gpet_get_num_sources(const gpet_ctx* ctx);
+int gpet_get_source(const gpet_ctx* ctx, int i, uint64_t* natom, int32_t* type, int32_t* shape, float coeff[6]);
+int gpet_get_num_isotopes(const gpet_ctx* ctx);
+int gpet_get_isotope(const gpet_ctx* ctx, int i, float* halflife, float* ratio, float coef[8]);
+int64_t gpet_get_num_psf(const gpet_ctx* ctx);
+
+/* ---- the hot path, stage by stage (device-resident between stages) ------------------------------------- */
+
+/* Frame planning: sampleParticle's epoch loop (gPET.cu:204-208, 260-282) + findT (gPET.cu:439-452), with
+ * the per-atom Bernoulli sweep of setPosition replaced by binomial thinning per source.
+ * Returns the number of frames planned for [tstart, tend]; max_pairs_per_frame 0 = capacity/2. */
+int64_t gpet_plan_frames(gpet_ctx* ctx, uint64_t max_pairs_per_frame);
+/* npairs of frame f (after planning). */
+int64_t gpet_frame_pairs(const gpet_ctx* ctx, int64_t frame);
+
+/* S2/S3/S4/S5 setPosition (gPET_kernals.cu:483-561): sample the pairs of frame f into photon queue 0. */
+int gpet_stage_source(gpet_ctx* ctx, int64_t frame);
+/* Load PSF photons [first, first+n) into queue 0 (simulateParticle batch upload, gPET.cu:47-61);
+ * positron PSF (ptype 0) goes through setPositionForPhoton (gPET_kernals.cu:563-604). */
+int gpet_stage_psf(gpet_ctx* ctx, int64_t first, int64_t n);
+/* P1 photon (gPET_kernals.cu:256-345): queue 0 -> queue 1 (photons alive after the phantom). */
+int gpet_stage_phantom(gpet_ctx* ctx);
+/* X1 photonde + D1 adder + D2 readout (gPET_kernals.cu:839-1233, 737-813): queue 1 -> hits + events. */
+int gpet_stage_detector(gpet_ctx* ctx);
+/* D3-D7 blur, energywindow, sort by t, setSitenum, orderevents, deadtime, energywindow (gPET.cu:385-424)
+ * + the coincidence sorter extension: events -> singles (time sorted) [+ coincidences]. */
+int gpet_stage_digitize(gpet_ctx* ctx);
+
+/* Host <-> device access to the stage buffers. which_queue: 0 after source, 1 after phantom. */
+int64_t gpet_queue_size(gpet_ctx* ctx, int which_queue);
+int gpet_put_photons(gpet_ctx* ctx, int which_queue, const gpet_photon* in, int64_t n);
+int64_t gpet_fetch_photons(gpet_ctx* ctx, int which_queue, gpet_photon* out, int64_t cap);
+int gpet_put_events(gpet_ctx* ctx, const gpet_event* in, int64_t n);
+int64_t gpet_fetch_events(gpet_ctx* ctx, gpet_event* out, int64_t cap);    /* post adder/readout ("adder.dat") */
+int64_t gpet_fetch_hits(gpet_ctx* ctx, gpet_hit* out, int64_t cap);
+int64_t gpet_fetch_singles(gpet_ctx* ctx, gpet_event* out, int64_t cap);   /* "singles.dat" of the last frame */
+int64_t gpet_fetch_coincidences(gpet_ctx* ctx, gpet_coincidence* out, int64_t cap);
+/* counts[0..3] = events in, after thresholder, after deadtime, singles (gPET.cu:382,398,415,423). */
+int gpet_last_counts(gpet_ctx* ctx, uint64_t counts[4]);
+
+/* ---- whole-path entry points --------------------------------------------------------------------------- */
+
+/* The replay entry (bit-exact pin): host list of post-adder events ("adder.dat") -> singles.
+ * Copies H2D, runs gpet_stage_digitize, copies D2H. counts may be NULL. */
+int gpet_digitize(gpet_ctx* ctx, const gpet_event* in, int64_t n, gpet_event* out, int64_t cap,
+                  int64_t* n_out, uint64_t counts[4]);
+/* sampleParticle / simulateParticle (gPET.cu:13-437): all frames, source or PSF mode according to the loaded
+ * inputs.  Singles (and coincidences) of all frames accumulate in pinned host memory owned by the context;
+ * output_dir != NULL additionally appends HitsID.dat/Hits.dat/adder.dat/singles.dat[/coincidences.dat] there
+ * with the reference layouts (gPET.cu:367-383, 424). */
+int gpet_run(gpet_ctx* ctx, const char* output_dir, gpet_stats* stats);
+/* Same, but nothing leaves the device except the counters (bench `value`: inputs resident, no D2H of records). */
+int gpet_run_resident(gpet_ctx* ctx, gpet_stats* stats);
+int64_t gpet_result_singles(gpet_ctx* ctx, const gpet_event** ptr);
+int64_t gpet_result_coincidences(gpet_ctx* ctx, const gpet_coincidence** ptr);
+int gpet_get_stats(const gpet_ctx* ctx, gpet_stats* stats);
+/* Energy spectrum tally of the accumulated singles (nbins over [emin, emax)), kept on device during the run;
+ * this is what multi-GPU runs all-reduce. */
+int gpet_get_spectrum(gpet_ctx* ctx, uint64_t* bins, int nbins);
+int gpet_set_spectrum(gpet_ctx* ctx, int nbins, float emin, float emax);
+/* Shard the planned frames: this context only runs frames f with f % world == rank. */
+int gpet_set_shard(gpet_ctx* ctx, int rank, int world);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPET_B200_H */

@@ -1,0 +1,253 @@
+"""CPU suite (-m "not gpu"): pins the oracle on known-answer vectors, checks the host loaders against the independent
+numpy parsers, and checks that the C-ABI library loads and exports every declared symbol.  No compute calls."""
+import ctypes
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import parity
+from gpet_b200 import api, refio
+from oracle import oracle as orc
+
+REF = parity.ROOT.parent / "reference"
+
+
+# ------------------------------------------------------------------------------------------------ Philox pin
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11)
+    kats = [
+        ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+    ]
+    for ctr, key, want in kats:
+        assert [int(x) for x in orc.philox(ctr, key)] == want
+
+
+# ------------------------------------------------------------------------------------------------ digitizer pins
+@pytest.mark.parametrize("case,d,ev", list(parity.kat_cases()), ids=lambda v: v["name"] if isinstance(v, dict) and "name" in v else None)
+def test_digitizer_known_answers(case, d, ev):
+    p, _ = parity.make_digi_params(**d)
+    singles, counts, coinc = orc.digitize(ev, p)
+    parity.check_kat(case, singles, counts, coinc)
+
+
+def test_digitizer_oracle_invariants():
+    rng = np.random.default_rng(7)
+    ev = parity.random_events(5000, rng, tmax=3.0e4, nsites=50, tie_fraction=0.05, dead_fraction=0.02)
+    for dead_type in (0, 1):
+        p, _ = parity.make_digi_params(dead_type=dead_type, coinc_window_us=0.5)
+        s, counts, co = orc.digitize(ev, p)
+        assert counts[0] == ev.size and counts[0] >= counts[1] >= counts[2] >= counts[3] == s.size
+        assert np.all(np.diff(s["t"]) >= 0)
+        assert np.all((s["E"] >= 30000) & (s["E"] <= 700000))
+        # survivors of one site are at least tau apart (early times: fp32 == fp64 here)
+        for site in np.unique(s["siten"])[:20]:
+            t = s["t"][s["siten"] == site]
+            assert np.all(np.diff(t) >= 2.2 - 1e-2)
+        assert np.all(co["b"]["t"] - co["a"]["t"] < 0.5) and np.all(co["b"]["t"] >= co["a"]["t"])
+        # idempotence: singles are a fixed point of the chain
+        s2, c2, _ = orc.digitize(s, p)
+        assert parity.events_equal(s, s2)
+
+
+# ------------------------------------------------------------------------------------------------ C ABI surface
+def test_library_exports_every_declared_symbol():
+    header = (parity.ROOT / "include" / "gpet_b200.h").read_text()
+    declared = set(re.findall(r"\b(gpet_[a-z_0-9]+)\s*\(", header))
+    declared -= {"gpet_ctx"}
+    assert len(declared) > 40
+    l = ctypes.CDLL(str(api.LIB_PATH))
+    for name in declared:
+        assert hasattr(l, name), f"{name} declared in gpet_b200.h but not exported"
+    assert set(api._SIGS) == declared, declared ^ set(api._SIGS)
+    assert api.lib().gpet_abi_version() == 1
+
+
+def test_record_layouts():
+    assert api.EVENT_DTYPE.itemsize == 48 and api.EVENT_DTYPE.fields["t"][1] == 24 and api.EVENT_DTYPE.fields["E"][1] == 32
+    assert api.COINC_DTYPE.itemsize == 96 and api.HIT_DTYPE.itemsize == 48 and api.PHOTON_DTYPE.itemsize == 48
+
+
+def test_host_only_context_refuses_compute():
+    with api.Context(device=-1) as c:
+        with pytest.raises(api.GpetError) as e:
+            c.stage_digitize()
+        assert e.value.code == -4
+        with pytest.raises(api.GpetError):
+            c.digitize(np.zeros(4, api.EVENT_DTYPE))
+        with pytest.raises(api.GpetError):
+            c.run()
+
+
+# ------------------------------------------------------------------------------------------------ loaders
+def test_config_parser_matches_numpy_parser(tmp_path):
+    cfg = refio.parse_config(parity.EXAMPLE / "input_PET.in")
+    assert cfg["pdim"] == [200, 200, 200] and cfg["rdepth"] == 2 and cfg["rpolicy"] == 1
+    assert cfg["dlevel"] == 3 and cfg["dtype"] == 0 and abs(cfg["dtime"] - 2.2) < 1e-6
+    assert cfg["nsurface"] == 1 and cfg["surface"][-1] == 1 and cfg["sourcefile"] == "input/pointsource.txt"
+    # product loader on the same file (phantom written small to keep it quick)
+    ex = tmp_path / "ex"
+    (ex / "input").mkdir(parents=True)
+    (ex / "data").mkdir()
+    text = (parity.EXAMPLE / "input_PET.in").read_text().replace("200 200 200", "16 16 16")
+    (ex / "input_PET.in").write_text(text)
+    for f in ("config8.geo", "pointsource.txt", "source.txt"):
+        (ex / "input" / f).write_text((parity.EXAMPLE / "input" / f).read_text())
+    (ex / "data" / "isotopes.txt").write_text((parity.EXAMPLE / "data" / "isotopes.txt").read_text())
+    mat, den = parity.gen_inputs.cylinder_phantom(n=16)
+    parity.gen_inputs.write_phantom(mat, den, ex / "input" / "cylinder_phantom_mat.dat", ex / "input" / "cylinder_phantom_den.dat")
+    if not parity.have_tables():
+        pytest.skip("packed tables not built")
+    (ex / "data" / "input4gPET.gpettab").write_bytes(parity.PACKED.read_bytes())
+    with api.Context(device=-1) as c:
+        c.load_config_file(ex / "input_PET.in", base_dir=ex)
+        d = c.get_digitizer()
+        assert (d.readout_depth, d.readout_policy, d.dead_level, d.dead_type) == (2, 1, 3, 0)
+        assert d.threshold_eV == 50000 and d.ewin_min == 30000 and d.ewin_max == 700000
+        assert abs(d.blur_Rref - 0.05) < 1e-7 and d.blur_policy == 1 and d.blur_Eref == 662000
+        t = c.get_transport()
+        assert abs(t.noncollinearity_rad - 0.0037056) < 1e-9 and t.eabs_eV == 1000 and t.nsurface == 1
+        assert len(c.sources()) == 1 and c.sources()[0]["natom"] == 1762974000 and c.sources()[0]["type"] == 3
+        assert len(c.isotopes()) == 4 and abs(c.isotopes()[0]["halftime"] - 6586.26) < 1e-2
+        assert c.plan_frames(0) >= 1
+
+
+def test_geometry_loader_matches_numpy_parser():
+    geo = parity.EXAMPLE / "input" / "config8.geo"
+    panels, mat, dens, counts = refio.parse_geometry(geo)
+    assert list(counts) == [9, 8, 117, 64]  # moduleN=117, crystalN=64
+    with api.Context(device=-1) as c:
+        c.load_geometry(geo)
+        got = c.panels()
+        c4, m2, d2 = c.geometry_counts()
+    assert list(c4) == list(counts) and list(m2) == list(mat) and np.allclose(d2, dens)
+    assert got.size == 8
+    for f in api.PANEL_FIELDS:
+        assert np.allclose(got[f], panels[f], atol=2e-6), f
+    # panel 2 = panel 0 rotated by 90 degrees about z: offset (0,-22.5,0) -> (22.5, 0, 0)
+    assert np.allclose([got["offsetx"][2], got["offsety"][2]], [22.5, 0.0], atol=1e-4)
+
+
+def test_source_and_isotope_loaders():
+    with api.Context(device=-1) as c:
+        c.load_isotopes(parity.EXAMPLE / "data" / "isotopes.txt")
+        c.load_source(parity.EXAMPLE / "input" / "source.txt")
+        src, iso = c.sources(), c.isotopes()
+    ref_src = refio.parse_sources(parity.EXAMPLE / "input" / "source.txt")
+    ref_iso = refio.parse_isotopes(parity.EXAMPLE / "data" / "isotopes.txt")
+    assert len(src) == 7 and len(iso) == 4
+    for a, b in zip(src, ref_src):
+        assert a["natom"] == b["natom"] and a["type"] == b["type"] and a["shape"] == b["shape"]
+        assert np.array_equal(a["coeff"], b["coeff"])
+    for a, b in zip(iso, ref_iso):
+        assert a["halftime"] == b["halftime"] and a["ratio"] == b["ratio"] and np.array_equal(a["coef"], b["coef"])
+
+
+def test_loader_errors_are_reported_not_fatal(tmp_path):
+    with api.Context(device=-1) as c:
+        with pytest.raises(api.GpetError) as e:
+            c.load_geometry(tmp_path / "missing.geo")
+        assert e.value.code == -2
+        bad = tmp_path / "bad.in"
+        bad.write_text("label\n0\nlabel\nnot-a-number\n")
+        with pytest.raises(api.GpetError):
+            c.load_config_file(bad)
+        with pytest.raises(api.GpetError):
+            c.load_tables(tmp_path / "nothing")
+
+
+def test_psf_loader(tmp_path):
+    rec = parity.gen_inputs.back_to_back_psf(1000)
+    rec.tofile(tmp_path / "psf.dat")
+    with api.Context(device=-1) as c:
+        c.load_psf(tmp_path / "psf.dat", 0, 1)
+        assert c.num_psf() == 2000
+        c.load_psf(tmp_path / "psf.dat", 500, 1)
+        assert c.num_psf() == 500  # readParticle clamps to the request (initialize.cu:88-92)
+    back = refio.read_psf(tmp_path / "psf.dat")
+    assert back.shape == (2000, 8) and np.allclose(back[0::2, 4:7], -back[1::2, 4:7])
+
+
+@pytest.mark.skipif(not (REF / "data" / "input4gPET.lamph").exists(), reason="reference checkout not present")
+def test_table_loader_matches_numpy_parser_on_reference_files(tmp_path):
+    # the complete CTD set ships with the reference: ASCII loader (header-driven dims) vs numpy parser
+    t = refio.read_tables(REF / "data" / "input4gCTD")
+    with api.Context(device=-1) as c:
+        c.load_tables(REF / "data" / "input4gCTD")
+        d = c.table_dims()
+        assert (d["nmat"], d["nen"], d["cm_ncp"], d["cm_ne"]) == (7, 2048, 101, 51)
+        assert np.array_equal(c.table(0).reshape(7, 2048), t["lamph"])
+        assert np.array_equal(c.table(1).reshape(7, 2048), t["compt"])
+        assert np.array_equal(c.table(3).reshape(7, 2048), t["rayle"])
+        assert np.array_equal(c.table(4).reshape(7, 101, 51), t["cmpsf"]["surf"])
+        assert np.array_equal(c.table(5).reshape(7, 101, 51), t["rayff"]["surf"])
+        # total = compton + rayleigh + photo, which is why the transport never reads phote
+        tot = c.table(1) + c.table(2) + c.table(3)
+        assert np.allclose(tot, c.table(0), rtol=3e-4)
+        # packed round trip
+        c.save_tables_packed(tmp_path / "ctd.gpettab")
+    with api.Context(device=-1) as c2:
+        c2.load_tables(tmp_path / "ctd.gpettab")
+        assert np.array_equal(c2.table(4).reshape(7, 101, 51), t["cmpsf"]["surf"])
+
+
+@pytest.mark.skipif(not (REF / "data" / "input4gCTD.cmpsf").exists(), reason="reference checkout not present")
+def test_surface_generator_reproduces_shipped_ctd_surfaces():
+    from tools import gen_tables as g
+    ctd = refio.read_matter(REF / "data" / "input4gCTD.matter")
+    cm = refio.read_surface(REF / "data" / "input4gCTD.cmpsf", ctd["nmat"])
+    rl = refio.read_surface(REF / "data" / "input4gCTD.rayff", ctd["nmat"])
+    k = ctd["names"].index("Water")
+    sq = cm["sq"][k].astype(np.float64); fq = rl["sq"][k].astype(np.float64)
+    s = g.compton_surface(sq[:, 0], sq[:, 2], cm["ncp"], cm["ne"], float(cm["de"]), ncos=4001)
+    assert np.abs(s - cm["surf"][k]).max() < 0.012   # grid quantisation of the original generator
+    r = g.rayleigh_surface(fq[:, 0], fq[:, 2], rl["ncp"], rl["ne"], float(rl["de"]), ncos=4001)
+    assert np.abs(r - rl["surf"][k])[:, :2].max() < 0.004  # low energies: exact; higher: the shipped table is coarse
+
+
+@pytest.mark.skipif(not parity.have_tables(), reason="packed tables not built")
+def test_packed_pet_tables_are_sane():
+    with api.Context(device=-1) as c:
+        c.load_tables(parity.PACKED)
+        d = c.table_dims()
+        assert (d["nmat"], d["nen"], d["cm_ncp"], d["cm_ne"], d["rl_ncp"], d["rl_ne"]) == (10, 4096, 301, 151, 301, 151)
+        e = c.table(8)
+        lam = c.table(0).reshape(10, 4096)
+        i511 = int(round((511000 - e[0]) / (e[-1] - e[0]) * 4095))
+        assert abs(lam[1, i511] - 0.09595) < 2e-4     # water at 511 keV
+        assert abs(lam[7, i511] - 0.11674) < 2e-4     # LSO
+        cm = c.table(4).reshape(10, 301, 151)
+        assert np.all(np.diff(cm, axis=1) >= -1e-6) and np.all(cm[:, 0] == -1) and np.all(cm[:, -1] == 1)
+
+
+# ------------------------------------------------------------------------------------------------ planner
+def test_frame_planner_statistics_and_invariance():
+    with api.Context(device=-1) as c:
+        c.load_isotopes(parity.EXAMPLE / "data" / "isotopes.txt")
+        c.load_source(parity.EXAMPLE / "input" / "source.txt")
+        c.set_time_window(0, 120)
+        c.set_capacity(1 << 19, 1 << 20, 1 << 20)
+        nf = c.plan_frames(0)
+        pairs = [c.frame_pairs(f) for f in range(nf)]
+        total = sum(pairs)
+        # 91 875 000 F-18 atoms, 120 s, branching 0.97 -> 1.118e6 pairs
+        expect = 91875000 * (1 - 2 ** (-120 / 6586.26)) * 0.97
+        assert abs(total - expect) < 6 * np.sqrt(expect)
+        assert max(pairs) <= (1 << 19) // 2 and nf >= 5
+        # same seed -> same plan; other seed -> other counts
+        assert c.plan_frames(0) == nf and [c.frame_pairs(f) for f in range(nf)] == pairs
+        c.set_seed(1234)
+        c.plan_frames(0)
+        assert [c.frame_pairs(f) for f in range(nf)] != pairs
+
+
+def test_cli_rejects_missing_argument():
+    exe = parity.ROOT / "bin" / "gpet_b200"
+    if not exe.exists():
+        pytest.skip("CLI not built")
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 1 and "input_file" in r.stdout  # main.cu:28-33
