@@ -104,6 +104,7 @@ _SIGS = {
     "gpet_get_num_psf": (C.c_int64, [_P]),
     "gpet_plan_frames": (C.c_int64, [_P, C.c_uint64]),
     "gpet_frame_pairs": (C.c_int64, [_P, C.c_int64]),
+    "gpet_get_frame": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
     "gpet_stage_source": (C.c_int, [_P, C.c_int64]),
     "gpet_stage_psf": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "gpet_stage_phantom": (C.c_int, [_P]),
@@ -330,6 +331,12 @@ class Context:
 
     def frame_pairs(self, f):
         return self._ck(self._l.gpet_frame_pairs(self._h, f))
+
+    def frame(self, f):
+        ns = self._ck(self._l.gpet_get_num_sources(self._h))
+        t0 = C.c_double(); dt = C.c_double(); fp = C.c_uint64(); pairs = np.zeros(ns, np.uint64)
+        self._ck(self._l.gpet_get_frame(self._h, f, C.byref(t0), C.byref(dt), C.byref(fp), _ptr(pairs)))
+        return dict(t0_s=t0.value, dt_s=dt.value, first_pair=fp.value, pairs=pairs)
 
     def stage_source(self, f):
         self._ck(self._l.gpet_stage_source(self._h, f))

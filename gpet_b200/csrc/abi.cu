@@ -669,6 +669,16 @@ int64_t gpet_frame_pairs(const gpet_ctx* c, int64_t f) {
     return (int64_t)c->frames[(size_t)f].npairs;
 }
 
+int gpet_get_frame(const gpet_ctx* c, int64_t f, double* t0, double* dt, uint64_t* first_pair, uint64_t* pairs) {
+    if (!c || !c->planned || f < 0 || f >= (int64_t)c->frames.size()) return GPET_ERR_ARG;
+    const FramePlan& fp = c->frames[(size_t)f];
+    if (t0) *t0 = fp.t0_s;
+    if (dt) *dt = fp.dt_s;
+    if (first_pair) *first_pair = fp.first_pair;
+    if (pairs) for (size_t i = 0; i < fp.pairs.size(); i++) pairs[i] = fp.pairs[i];
+    return GPET_OK;
+}
+
 // =================================================================================================== stages
 int gpet_stage_source(gpet_ctx* c, int64_t f) {
     NEED_DEVICE();

@@ -209,6 +209,10 @@ int64_t gpet_get_num_psf(const gpet_ctx* ctx);
 int64_t gpet_plan_frames(gpet_ctx* ctx, uint64_t max_pairs_per_frame);
 /* npairs of frame f (after planning). */
 int64_t gpet_frame_pairs(const gpet_ctx* ctx, int64_t frame);
+/* Full description of frame f: start (s), length (s), global index of its first pair, pairs per source
+ * (pairs_per_source must hold gpet_get_num_sources() entries). */
+int gpet_get_frame(const gpet_ctx* ctx, int64_t frame, double* t0_s, double* dt_s, uint64_t* first_pair,
+                   uint64_t* pairs_per_source);
 
 /* S2/S3/S4/S5 setPosition (gPET_kernals.cu:483-561): sample the pairs of frame f into photon queue 0. */
 int gpet_stage_source(gpet_ctx* ctx, int64_t frame);

@@ -1,0 +1,321 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+Bit-exact for the deterministic digitizer stages; per-history agreement + chi-square for the transport (fast-math
+intrinsics differ in the last bits from libm, so a small fraction of histories may branch differently)."""
+import numpy as np
+import pytest
+
+import parity
+from gpet_b200 import api, refio
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def run_both(ctx, ev, **kw):
+    p, d = parity.make_digi_params(**kw)
+    parity.apply_digi_params(ctx, d)
+    got, counts = ctx.digitize(ev)
+    co = ctx.fetch_coincidences() if d["coinc_window_us"] > 0 else np.zeros(0, api.COINC_DTYPE)
+    want, wcounts, wco = orc.digitize(ev, p)
+    return got, counts, co, want.astype(api.EVENT_DTYPE), wcounts, wco.astype(api.COINC_DTYPE)
+
+
+# ------------------------------------------------------------------------------------------------ digitizer: bit exact
+@pytest.mark.parametrize("case,d,ev", list(parity.kat_cases()), ids=lambda v: v["name"] if isinstance(v, dict) and "name" in v else None)
+def test_digitizer_known_answers_on_gpu(ctx, case, d, ev):
+    parity.apply_digi_params(ctx, d)
+    singles, counts = ctx.digitize(ev)
+    coinc = ctx.fetch_coincidences() if d.get("coinc_window_us", 0) > 0 else []
+    parity.check_kat(case, singles, counts, coinc)
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 2047, 2048, 2049, 40000, 300000])
+@pytest.mark.parametrize("dead_type", [0, 1])
+def test_digitizer_bit_exact_sizes(ctx, n, dead_type):
+    rng = np.random.default_rng(100 + n)
+    ev = parity.random_events(n, rng, tmax=max(10.0, n * 0.05), nsites=300)
+    got, counts, _, want, wcounts, _ = run_both(ctx, ev, dead_type=dead_type)
+    assert list(counts) == list(wcounts)
+    assert parity.events_equal(got, want)
+
+
+@pytest.mark.parametrize("dead_level", [0, 1, 2, 3])
+@pytest.mark.parametrize("dead_type", [0, 1])
+def test_digitizer_bit_exact_levels_ties_and_dead_records(ctx, dead_level, dead_type):
+    rng = np.random.default_rng(7 + dead_level)
+    ev = parity.random_events(60000, rng, tmax=2.0e4, nsites=936, tie_fraction=0.1, dead_fraction=0.03)
+    got, counts, co, want, wcounts, wco = run_both(ctx, ev, dead_level=dead_level, dead_type=dead_type,
+                                                   coinc_window_us=0.02, coinc_policy=dead_type, coinc_min_panel_diff=1)
+    assert list(counts) == list(wcounts)
+    assert parity.events_equal(got, want)
+    assert co.size == wco.size and co.tobytes() == wco.tobytes()
+
+
+def test_digitizer_bit_exact_late_times(ctx):
+    # t ~ 1e8 us: fp32 tdead quantised to 8 us; the closed form must still agree bit for bit
+    rng = np.random.default_rng(5)
+    ev = parity.random_events(50000, rng, tmax=3.0e4, nsites=200)
+    ev["t"] += 1.0e8
+    for dead_type in (0, 1):
+        got, counts, _, want, wcounts, _ = run_both(ctx, ev, dead_type=dead_type)
+        assert list(counts) == list(wcounts) and parity.events_equal(got, want)
+
+
+def test_digitizer_negative_site_and_unsorted_input(ctx):
+    rng = np.random.default_rng(11)
+    ev = parity.random_events(5000, rng, tmax=500.0, nsites=64)
+    ev["siten"] -= 32  # std::sort compares siten as signed int
+    got, counts, _, want, wcounts, _ = run_both(ctx, ev)
+    assert list(counts) == list(wcounts) and parity.events_equal(got, want)
+
+
+def test_digitizer_blur_matches_oracle_within_float_tolerance(ctx):
+    # blur on: same Philox normals on both sides; device logf/cosf differ from libm in the last bits
+    rng = np.random.default_rng(3)
+    ev = parity.random_events(40000, rng, tmax=1.0e6, nsites=936)
+    got, counts, _, want, wcounts, _ = run_both(ctx, ev, blur_Rref=0.05, blur_space=0.02, time_blur_sigma_us=1e-4)
+    assert abs(int(counts[3]) - int(wcounts[3])) <= 4
+    a = {(int(p), int(s)): e for p, s, e in zip(got["parn"], got["siten"], got["E"])}
+    b = {(int(p), int(s)): e for p, s, e in zip(want["parn"], want["siten"], want["E"])}
+    common = set(a) & set(b)
+    assert len(common) >= 0.999 * len(b)
+    rel = np.array([abs(a[k] - b[k]) / b[k] for k in common])
+    assert rel.max() < 1e-5
+    # the blur really happened: sigma/E = R/2.35482
+    orig = {(int(p), int(s)): e for p, s, e in zip(ev["parn"], ev["siten"], ev["E"])}
+    z = np.array([(a[k] - orig[k]) / orig[k] for k in common])
+    assert abs(z.std() - 0.05 / 2.35482) < 0.0015
+
+
+def test_digitizer_full_batch_properties(ctx):
+    # reference batch scale: 3 * NPART event slots (gPET.cu:26); size-independent properties
+    rng = np.random.default_rng(9)
+    n = 1_500_000
+    ev = parity.random_events(n, rng, tmax=4.0e6, nsites=59904)
+    p, d = parity.make_digi_params(coinc_window_us=0.01)
+    parity.apply_digi_params(ctx, d)
+    s, counts = ctx.digitize(ev)
+    assert counts[0] == n and counts[0] >= counts[1] >= counts[2] >= counts[3] == s.size
+    assert np.all(np.diff(s["t"]) >= 0)
+    assert np.all((s["E"] >= 30000) & (s["E"] <= 700000))
+    # set property: every single is one of the inputs, unchanged
+    key_in = set(zip(ev["parn"].tolist(), ev["siten"].tolist()))
+    assert set(zip(s["parn"].tolist(), s["siten"].tolist())) <= key_in
+    # idempotence
+    s2, c2 = ctx.digitize(s)
+    assert parity.events_equal(s, s2)
+    # thresholder count is an exact, order-free quantity
+    assert counts[1] == int(((ev["E"] >= 50000) & (ev["E"] <= 2.0e6)).sum())
+    # oracle agrees on the whole thing as well
+    want, wcounts, _ = orc.digitize(ev, p)
+    assert list(counts) == list(wcounts) and parity.events_equal(s, want.astype(api.EVENT_DTYPE))
+
+
+# ------------------------------------------------------------------------------------------------ transport
+needs_tables = pytest.mark.skipif(not parity.have_tables(), reason="packed tables not built")
+
+
+@needs_tables
+def test_source_sampling_matches_oracle():
+    s = parity.Setup(0, phantom="air", n=16, capacity=(1 << 20, 1 << 20, 1 << 20))
+    c = s.ctx
+    c.load_isotopes(parity.EXAMPLE / "data" / "isotopes.txt")
+    c.load_source(parity.EXAMPLE / "input" / "source.txt")
+    c.set_time_window(0, 30)
+    nf = c.plan_frames(0)
+    assert nf >= 1
+    f = nf - 1 if nf > 1 else 0
+    fr = c.frame(f)
+    c.stage_source(f)
+    got = c.fetch_photons(0)
+    src, iso = c.sources(), c.isotopes()
+    tau = np.array([np.float64(iso[x["type"]]["halftime"]) * 1.442695 for x in src])
+    frac = -np.expm1(-fr["dt_s"] / tau)
+    want = orc.source(np.cumsum(fr["pairs"]), [x["shape"] for x in src], np.concatenate([x["coeff"] for x in src]),
+                      tau, frac, fr["t0_s"], fr["first_pair"], 0.0037056, int(fr["pairs"].sum()), s.seed)
+    assert got.size == want.size == 2 * int(fr["pairs"].sum())
+    assert np.array_equal(got["parn"], want["parn"]) and np.array_equal(got["eventid"], want["eventid"])
+    for f_ in ("x", "y", "z", "vx", "vy", "vz"):
+        assert np.allclose(got[f_], want[f_], atol=2e-5), f_
+    assert np.allclose(got["E"], want["E"], rtol=1e-6)
+    assert np.allclose(got["t"], want["t"], rtol=1e-12, atol=1e-6)
+    # physics: times inside the frame, pairs back to back within the acollinearity
+    assert got["t"].min() >= fr["t0_s"] * 1e6 and got["t"].max() <= (fr["t0_s"] + fr["dt_s"]) * 1e6 * (1 + 1e-9)
+    cosang = (got["vx"][0::2] * got["vx"][1::2] + got["vy"][0::2] * got["vy"][1::2] + got["vz"][0::2] * got["vz"][1::2])
+    assert np.all(cosang < -0.999)
+    assert abs(np.degrees(np.arccos(-cosang.clip(-1, 1))).std() - np.degrees(0.0037056) * 0.66) < 0.08
+    s.close()
+
+
+@needs_tables
+def test_phantom_transport_matches_oracle_per_photon():
+    # 10 cm water cube so that a sizeable fraction of photons interacts (Compton, Rayleigh, photo-absorption)
+    n = 48
+    mat = np.ones((n, n, n), np.int32); den = np.ones((n, n, n), np.float32)
+    s = parity.Setup(0, phantom=(mat, den), size=10.0)
+    rng = np.random.default_rng(21)
+    ph = parity.isotropic_photons(200000, rng, pos_sigma=1.0)
+    ph["E"][::3] = 140000.0
+    ph["E"][1::7] = 30000.0
+    s.ctx.put_photons(0, ph)
+    s.ctx.stage_phantom()
+    got = s.ctx.fetch_photons(1)
+    want = orc.phantom(ph, s.mat, s.den, s.offset, s.size, s.tab_ph, s.eabs, s.seed)
+    want = want[want["t"] > 0]
+    ncommon, nmatch, only_g, only_o = parity.compare_photons(got, want)
+    assert abs(got.size - want.size) <= 0.002 * want.size
+    assert only_g + only_o <= 0.004 * want.size
+    assert nmatch >= 0.995 * ncommon
+    # scattered fraction is substantial, otherwise the test proves nothing
+    assert (got["nscat"] > 0).mean() > 0.25
+    s.close()
+
+
+@needs_tables
+def test_detector_transport_matches_oracle_per_photon():
+    s = parity.Setup(0, phantom="air", n=16)
+    rng = np.random.default_rng(22)
+    ph = parity.isotropic_photons(200000, rng)
+    ph["E"][::4] = 250000.0
+    s.ctx.put_photons(1, ph)
+    s.ctx.stage_detector()
+    hits = parity.hits_by_photon(s.ctx.fetch_hits())
+    ev = s.ctx.fetch_events()
+    res = orc.detector(ph, s.panels, s.counts4, s.pmat, s.pdens, s.surfaces, s.tab_det, s.eabs, 2, 1, s.seed)
+    ohits = parity.hits_by_photon(res["hits"]); oev = res["events"]
+    assert res["adder_overflow"] == 0
+    assert abs(hits.size - ohits.size) <= 0.003 * ohits.size
+    assert abs(ev.size - oev.size) <= 0.003 * oev.size
+    # per-photon hit sequences
+    def seqs(h):
+        d = {}
+        for r in h:
+            d.setdefault(int(r["parn"]), []).append((int(r["pann"]), int(r["modn"]), int(r["cryn"]), int(r["type"]), float(r["E"])))
+        return d
+    a, b = seqs(hits), seqs(ohits)
+    common = set(a) & set(b)
+    assert len(common) >= 0.997 * len(b)
+    same = 0
+    for k in common:
+        x, y = a[k], b[k]
+        if len(x) == len(y) and all(u[:4] == v[:4] and abs(u[4] - v[4]) <= 2e-3 * max(v[4], 1.0) for u, v in zip(x, y)):
+            same += 1
+    assert same >= 0.99 * len(common), (same, len(common))
+    # events: energy per (parn, siten) agrees
+    ea = {(int(r["parn"]), int(r["siten"])): float(r["E"]) for r in ev}
+    eb = {(int(r["parn"]), int(r["siten"])): float(r["E"]) for r in oev}
+    ce = set(ea) & set(eb)
+    assert len(ce) >= 0.99 * len(eb)
+    close = sum(abs(ea[k] - eb[k]) <= 2e-3 * eb[k] for k in ce)
+    assert close >= 0.99 * len(ce)
+    # geometry coverage of config8 (~0.41 of photons enter a panel)
+    frac = len(set(int(x) for x in hits["parn"])) / ph.size
+    assert 0.2 < frac < 0.5
+    s.close()
+
+
+@needs_tables
+def test_pipeline_spectra_agree_statistically_with_independent_seeds():
+    # statistical parity: GPU run with one seed vs oracle run with another on the same inputs; chi-square / ndf
+    s = parity.Setup(0, phantom="cylinder", n=32, size=2.0, seed=1111)
+    rng = np.random.default_rng(23)
+    ph = parity.isotropic_photons(400000, rng)
+    s.ctx.put_photons(0, ph)
+    s.ctx.stage_phantom(); s.ctx.stage_detector()
+    hits = s.ctx.fetch_hits(); ev = s.ctx.fetch_events()
+    oph = orc.phantom(ph, s.mat, s.den, s.offset, s.size, s.tab_ph, s.eabs, 2222)
+    res = orc.detector(oph, s.panels, s.counts4, s.pmat, s.pdens, s.surfaces, s.tab_det, s.eabs, 2, 1, 2222)
+    # sensitivity within 1 % (north_star tolerance), spectra by chi-square
+    assert abs(ev.size - res["events"].size) <= 0.01 * res["events"].size + 3 * np.sqrt(res["events"].size)
+    assert abs(hits.size - res["hits"].size) <= 0.01 * res["hits"].size + 3 * np.sqrt(res["hits"].size)
+    bins = np.linspace(0, 520000, 53)
+    chi2, ndf = parity.chi2_hist(hits["E"], res["hits"]["E"], bins)
+    assert ndf > 20 and chi2 / ndf < 1.6, (chi2, ndf)
+    chi2, ndf = parity.chi2_hist(ev["E"], res["events"]["E"], bins)
+    assert ndf > 20 and chi2 / ndf < 1.6, (chi2, ndf)
+    chi2, ndf = parity.chi2_hist(ev["modn"], res["events"]["modn"], np.arange(118) - 0.5)
+    assert chi2 / max(ndf, 1) < 1.6
+    s.close()
+
+
+# ------------------------------------------------------------------------------------------------ whole path
+def make_example_dir(tmp_path, n=32, source="pointsource.txt", window="0 120"):
+    ex = tmp_path / "ex"
+    (ex / "input").mkdir(parents=True); (ex / "data").mkdir(); (ex / "output").mkdir()
+    text = (parity.EXAMPLE / "input_PET.in").read_text().replace("200 200 200", f"{n} {n} {n}")
+    text = text.replace("input/pointsource.txt", f"input/{source}").replace("0 120\n", window + "\n")
+    (ex / "input_PET.in").write_text(text)
+    for f in ("config8.geo", "pointsource.txt", "source.txt"):
+        (ex / "input" / f).write_text((parity.EXAMPLE / "input" / f).read_text())
+    (ex / "data" / "isotopes.txt").write_text((parity.EXAMPLE / "data" / "isotopes.txt").read_text())
+    (ex / "data" / "input4gPET.gpettab").write_bytes(parity.PACKED.read_bytes())
+    mat, den = parity.gen_inputs.cylinder_phantom(n=n)
+    parity.gen_inputs.write_phantom(mat, den, ex / "input" / "cylinder_phantom_mat.dat", ex / "input" / "cylinder_phantom_den.dat")
+    return ex
+
+
+@needs_tables
+def test_run_shipped_example_writes_reference_layouts(tmp_path):
+    ex = make_example_dir(tmp_path)
+    with api.Context(0) as c:
+        c.load_config_file(ex / "input_PET.in", base_dir=ex)
+        c.set_digitizer(coinc_window_us=0.01)
+        st = c.run(ex / "output")
+        singles = c.result_singles()
+    # 1 762 974 000 atoms, T1/2 820 500 s, 120 s -> ~178 711 pairs
+    assert abs(st.pairs - 178711) < 6 * np.sqrt(178711)
+    assert st.overflow_hits == st.overflow_events == st.overflow_adder == 0
+    assert st.events_adder >= st.events_threshold >= st.events_deadtime >= st.singles > 0
+    ids, f = refio.read_hits(ex / "output" / "HitsID.dat", ex / "output" / "Hits.dat")
+    assert ids.shape == f.shape == (st.hits, 5)
+    assert set(np.unique(ids[:, 4])) <= {1, 2, 4} and ids[:, 1].min() >= 0 and ids[:, 1].max() <= 7
+    assert ids[:, 2].max() < 117 and ids[:, 3].max() < 64
+    adder = refio.read_events(ex / "output" / "adder.dat")
+    sing = refio.read_events(ex / "output" / "singles.dat")
+    assert adder.size == st.events_adder and sing.size == st.singles == singles.size
+    assert sing.tobytes() == singles.tobytes()
+    co = refio.read_coincidences(ex / "output" / "coincidences.dat")
+    assert co.size == st.coincidences > 0
+    assert np.all(co["b"]["t"] - co["a"]["t"] < 0.01)
+    # most coincidences are true pairs (same annihilation) for a point source in a 1 cm phantom
+    assert (co["a"]["eventid"] == co["b"]["eventid"]).mean() > 0.9
+    # sensitivity: ~0.41 of the photons reach a panel
+    assert 0.3 < st.photons_on_panel / (2 * st.pairs) < 0.5
+    # replay pin: adder.dat through the digitizer alone reproduces singles.dat bit for bit (blur is on in the shipped
+    # file, and already applied in this dump, so replay with R = 0)
+    with api.Context(0) as c2:
+        c2.load_config_file(ex / "input_PET.in", base_dir=ex)
+        c2.set_digitizer(blur_Rref=0.0)
+        again, _ = c2.digitize(adder)
+    assert again.tobytes() == sing.tobytes()
+
+
+@needs_tables
+def test_run_is_reproducible_and_shards_by_frame(tmp_path):
+    ex = make_example_dir(tmp_path, source="source.txt", window="0 20")
+    def run(rank, world, seed=77):
+        with api.Context(0) as c:
+            c.set_seed(seed)
+            c.set_capacity(1 << 17, 1 << 19, 1 << 18)
+            c.load_config_file(ex / "input_PET.in", base_dir=ex)
+            c.set_shard(rank, world)
+            st = c.run(None)
+            return st, c.result_singles()
+    st_a, s_a = run(0, 1)
+    st_b, s_b = run(0, 1)
+    assert st_a.frames >= 3
+    assert s_a.tobytes() == s_b.tobytes()           # same seed: bit-identical singles
+    st0, s0 = run(0, 2); st1, s1 = run(1, 2)
+    assert st0.pairs + st1.pairs == st_a.pairs and st0.singles + st1.singles == st_a.singles
+    merged = np.concatenate([s0, s1])
+    merged = merged[np.argsort(merged["t"], kind="stable")]
+    assert merged.tobytes() == s_a[np.argsort(s_a["t"], kind="stable")].tobytes()   # G-invariant results
+    _, s_c = run(0, 1, seed=78)
+    assert s_c.tobytes() != s_a.tobytes()
