@@ -133,8 +133,7 @@ def run_reference(args):
     with tempfile.TemporaryDirectory() as tmp:
         ex = make_workdir(tmp)
         line = None
-        sys.path.insert(0, str(ROOT / "oracle"))
-        import run_ref
+        from oracle import run_ref
         have_gpu = shutil.which("nvidia-smi") is not None and subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0
         if run_ref.available() and have_gpu:
             try:
