@@ -41,19 +41,18 @@ int dev_alloc(gpet_ctx* c, T** p, size_t n) {
     return GPET_OK;
 }
 
-int alloc_queue(gpet_ctx* c, PhotonQueue& q, size_t cap) {
+int alloc_queue(gpet_ctx* c, PhotonQueue& q, size_t cap, unsigned* count) {
     int r;
     if ((r = dev_alloc(c, &q.pos_e, cap))) return r;
     if ((r = dev_alloc(c, &q.dir_n, cap))) return r;
     if ((r = dev_alloc(c, &q.t, cap))) return r;
     if ((r = dev_alloc(c, &q.ids, cap))) return r;
-    if ((r = dev_alloc(c, &q.count, 4))) return r;
+    q.count = count;
     q.capacity = (unsigned)cap;
-    CK(cudaMemset(q.count, 0, 16));
     return GPET_OK;
 }
 
-int alloc_events(gpet_ctx* c, EventSoA& e, size_t cap) {
+int alloc_events(gpet_ctx* c, EventSoA& e, size_t cap, unsigned* count) {
     int r;
     int** ints[6] = {&e.parn, &e.pann, &e.modn, &e.cryn, &e.siten, &e.eventid};
     for (auto p : ints)
@@ -62,9 +61,8 @@ int alloc_events(gpet_ctx* c, EventSoA& e, size_t cap) {
     float** flts[4] = {&e.E, &e.x, &e.y, &e.z};
     for (auto p : flts)
         if ((r = dev_alloc(c, p, cap))) return r;
-    if ((r = dev_alloc(c, &e.count, 4))) return r;
+    e.count = count;
     e.capacity = (unsigned)cap;
-    CK(cudaMemset(e.count, 0, 16));
     return GPET_OK;
 }
 
@@ -72,32 +70,42 @@ int ensure_buffers(gpet_ctx* c) {
     if (c->dev_buffers) return GPET_OK;
     int r;
     const size_t cp = c->cap_photons, ch = c->cap_hits, ce = c->cap_events;
-    if ((r = alloc_queue(c, c->q[0], cp))) return r;
-    if ((r = alloc_queue(c, c->q[1], cp))) return r;
+    DigitizerWorkspace& w = c->ws;
+    // every device-side counter lives in one 64-word block, so one small D2H brings all of them back
+    if ((r = dev_alloc(c, &w.counters, 64))) return r;
+    CK(cudaMemset(w.counters, 0, 64 * sizeof(unsigned)));
+    if ((r = alloc_queue(c, c->q[0], cp, w.counters + 16))) return r;
+    if ((r = alloc_queue(c, c->q[1], cp, w.counters + 17))) return r;
     if ((r = dev_alloc(c, &c->hits.id, 5 * ch))) return r;
     if ((r = dev_alloc(c, &c->hits.f, 5 * ch))) return r;
     if ((r = dev_alloc(c, &c->hits.t, ch))) return r;
-    if ((r = dev_alloc(c, &c->hits.count, 4))) return r;
+    c->hits.count = w.counters + 18;
     c->hits.capacity = (unsigned)ch;
-    CK(cudaMemset(c->hits.count, 0, 16));
-    if ((r = alloc_events(c, c->ev, ce))) return r;
-    if ((r = alloc_events(c, c->singles, ce))) return r;
-    DigitizerWorkspace& w = c->ws;
+    if ((r = alloc_events(c, c->ev, ce, w.counters + 19))) return r;
+    if ((r = alloc_events(c, c->singles, ce, w.counters + 20))) return r;
     for (int k = 0; k < 2; k++) {
-        if ((r = dev_alloc(c, &w.sort.keys[k], ce))) return r;
-        if ((r = dev_alloc(c, &w.sort.vals[k], ce))) return r;
+        if ((r = dev_alloc(c, &w.tkeys[k], ce))) return r;
+        if ((r = dev_alloc(c, &w.tvals[k], ce))) return r;
+        if ((r = dev_alloc(c, &w.skeys[k], ce))) return r;
+        if ((r = dev_alloc(c, &w.svals[k], ce))) return r;
     }
-    w.sort.capacity = (unsigned)ce;
-    w.sort.max_tiles = (unsigned)((ce + 2047) / 2048);
-    if ((r = dev_alloc(c, &w.sort.tile_hist, (size_t)256 * w.sort.max_tiles))) return r;
+    w.capacity = (unsigned)ce;
+    w.max_tiles = (unsigned)((ce + 2047) / 2048);
+    for (int k = 0; k < 2; k++) {
+        if ((r = dev_alloc(c, &w.lookback[k], (size_t)256 * w.max_tiles))) return r;
+        CK(cudaMemset(w.lookback[k], 0, (size_t)256 * w.max_tiles * sizeof(unsigned)));
+        if ((r = dev_alloc(c, &w.scan_status[k], (size_t)w.max_tiles))) return r;
+    }
+    {
+        unsigned char* p = nullptr;
+        if ((r = dev_alloc(c, &p, 2 * sort_state_bytes()))) return r;
+        CK(cudaMemset(p, 0, 2 * sort_state_bytes()));
+        w.st_time = reinterpret_cast<rsort::SortState*>(p);
+        w.st_site = reinterpret_cast<rsort::SortState*>(p + sort_state_bytes());
+    }
     if ((r = dev_alloc(c, &w.order_t, ce))) return r;
-    if ((r = dev_alloc(c, &w.order_s, ce))) return r;
     if ((r = dev_alloc(c, &w.kill, ce))) return r;
-    if ((r = dev_alloc(c, &w.flags, ce))) return r;
-    if ((r = dev_alloc(c, &w.scan_tmp, (size_t)w.sort.max_tiles + 1024))) return r;
-    if ((r = dev_alloc(c, &w.counters, 32))) return r;
-    CK(cudaMemset(w.counters, 0, 32 * sizeof(unsigned)));
-    w.site_sorted = nullptr;
+    if ((r = dev_alloc(c, &w.coinc_cnt, ce))) return r;
     if (w.spectrum_bins > 0) {
         if ((r = dev_alloc(c, &w.spectrum, (size_t)w.spectrum_bins))) return r;
         CK(cudaMemset(w.spectrum, 0, sizeof(unsigned long long) * w.spectrum_bins));
@@ -302,12 +310,7 @@ int validate_materials(gpet_ctx* c) {
 }
 
 int read_counters(gpet_ctx* c) {  // synchronises the stream
-    CK(cudaMemcpyAsync(c->h_counters, c->ws.counters, 16 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(c->h_counters + 16, c->ev.count, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(c->h_counters + 17, c->hits.count, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(c->h_counters + 18, c->q[0].count, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(c->h_counters + 19, c->q[1].count, 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(c->h_counters + 20, c->singles.count, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_counters, c->ws.counters, 32 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return GPET_OK;
 }
@@ -740,7 +743,7 @@ int64_t gpet_queue_size(gpet_ctx* c, int which) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((r = read_counters(c))) return r;
-    return (int64_t)std::min<unsigned>(c->h_counters[18 + which], c->q[which].capacity);
+    return (int64_t)std::min<unsigned>(c->h_counters[16 + which], c->q[which].capacity);
 }
 
 int gpet_put_photons(gpet_ctx* c, int which, const gpet_photon* in, int64_t n) {
@@ -783,7 +786,7 @@ int64_t gpet_fetch_events(gpet_ctx* c, gpet_event* out, int64_t cap) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((r = read_counters(c))) return r;
-    int64_t n = std::min<int64_t>(std::min<unsigned>(c->h_counters[16], c->ev.capacity), cap);
+    int64_t n = std::min<int64_t>(std::min<unsigned>(c->h_counters[19], c->ev.capacity), cap);
     if (n <= 0) return 0;
     c->stats.kernel_launches += launch_events_soa_to_aos(c->ev, c->stage_aos, c->stream);
     CK(cudaMemcpyAsync(out, c->stage_aos, (size_t)n * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->stream));
@@ -796,7 +799,7 @@ int64_t gpet_fetch_hits(gpet_ctx* c, gpet_hit* out, int64_t cap) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((r = read_counters(c))) return r;
-    int64_t n = std::min<int64_t>(std::min<unsigned>(c->h_counters[17], c->hits.capacity), cap);
+    int64_t n = std::min<int64_t>(std::min<unsigned>(c->h_counters[18], c->hits.capacity), cap);
     if (n <= 0) return 0;
     std::vector<int32_t> id((size_t)5 * n);
     std::vector<float> f((size_t)5 * n);
@@ -922,7 +925,7 @@ int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* sta
         st.frames++;
         if ((r = read_counters(c))) return r;   // one small D2H + sync per frame
         const unsigned* h = c->h_counters;
-        const uint64_t n_ev = h[16], n_hits = h[17], n_q1 = h[19];
+        const uint64_t n_ev = h[19], n_hits = h[18], n_q1 = h[17];
         st.photons_phantom_out += n_q1;
         st.photons_on_panel += h[8];
         st.hits += n_hits;

@@ -2,8 +2,13 @@
 // -> singles (time sorted) [-> coincidence sorter].  Reference: blur/energywindow/setSitenum/deadtime kernels
 // (gPET_kernals.cu:607-698, 814-837) and the host orchestration with three CPU sorts (gPET.cu:385-424,
 // detector.cu:354-385).  Here nothing leaves the device between stages: counts stay in `counters`, the sorts are
-// radix sorts over the order-preserving u64 image of the fp64 time, and the final singles list is produced by one
-// compaction of the time order (no re-sort after dead time / energy window, since killing keeps the order).
+// one-kernel-per-digit radix sorts over the order-preserving u64 image of the fp64 time (radix_sort.cuh), and the
+// final singles list is produced by one fused flag + scan + compaction of the time order (no re-sort after dead time
+// / energy window, since killing keeps the order).  The launch sequence is static (all sizes live on the device), so
+// the whole chain replays from a CUDA graph.
+//
+// Launches per frame: k_begin, k_prep, 8 x k_onesweep<u64>, k_site_keys, 4 x k_onesweep<u32> (passes whose digit is
+// constant return at once), k_deadtime, k_emit_singles [, k_coinc_count, k_coinc_emit].
 #include "kernels.hpp"
 #include "philox.cuh"
 #include "radix_sort.cuh"
@@ -57,13 +62,32 @@ __global__ void k_soa_to_aos(EventSoA ev, gpet_event* __restrict__ aos) {
         store_event_aos(aos + i, ev, i);
 }
 
+// ------------------------------------------------------------------------------------------- stage 0: reset
+// counters[0..7], both sort states (histograms, tile counters, buffer selectors) and the scan status words.
+__global__ void __launch_bounds__(kThreads) k_begin(unsigned* __restrict__ counters, rsort::SortState* st_time,
+                                                    rsort::SortState* st_site, unsigned* __restrict__ scan_status0,
+                                                    unsigned* __restrict__ scan_status1, unsigned max_tiles) {
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (tid < 8) counters[tid] = 0;
+    constexpr unsigned kWords = sizeof(rsort::SortState) / 4;
+    unsigned* a = reinterpret_cast<unsigned*>(st_time);
+    unsigned* b = reinterpret_cast<unsigned*>(st_site);
+    for (unsigned i = tid; i < kWords; i += nth) { a[i] = 0; b[i] = 0; }
+    for (unsigned i = tid; i < max_tiles; i += nth) { scan_status0[i] = 0; scan_status1[i] = 0; }
+}
+
 // ------------------------------------------------------------------------------------------- stage 1: blur + thresholder + time keys
-// blur (gPET_kernals.cu:814-837) + energywindow(Eth, 2e6) (gPET.cu:393) fused; writes the sort keys.
+// blur (gPET_kernals.cu:814-837) + energywindow(Eth, 2e6) (gPET.cu:393) fused; writes the sort keys into buffer 0 of
+// the time sort, accumulates the digit histograms of all 8 passes and clears the first look-back array.
 __global__ void __launch_bounds__(kThreads) k_prep(EventSoA ev, DigitizerDev p, uint64_t seed,
                                                    unsigned long long* __restrict__ keys, unsigned* __restrict__ vals,
-                                                   unsigned* __restrict__ counters) {
+                                                   unsigned* __restrict__ counters, rsort::SortState* st_time,
+                                                   unsigned* __restrict__ lookback0) {
+    __shared__ unsigned sh_hist[8 * rsort::kBins];
     const unsigned n = min(*ev.count, ev.capacity);
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[0] = n;
+    for (int i = threadIdx.x; i < 8 * rsort::kBins; i += blockDim.x) sh_hist[i] = 0;
+    __syncthreads();
     unsigned alive_cnt = 0;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float E = ev.E[i];
@@ -100,20 +124,31 @@ __global__ void __launch_bounds__(kThreads) k_prep(EventSoA ev, DigitizerDev p, 
         }
         // energywindow: dead iff E < lo || E > hi (gPET_kernals.cu:648); an already dead record (t >= MAXT) stays dead
         bool alive = !(E < p.Eth || E > 2000000.0f) && t < kMaxT * 0.1;
-        keys[i] = alive ? time_key(t) : ~0ull;
+        const unsigned long long key = alive ? time_key(t) : ~0ull;
+        keys[i] = key;
         vals[i] = i;
+        rsort::hist_add<unsigned long long, 8>(sh_hist, key);
         alive_cnt += alive ? 1u : 0u;
     }
     alive_cnt = warp_sum(alive_cnt);
     if ((threadIdx.x & 31) == 0 && alive_cnt) atomicAdd(&counters[1], alive_cnt);
+    __syncthreads();
+    rsort::hist_flush<8>(sh_hist, st_time);
+    rsort::clear_lookback(lookback0, n);
 }
 
 // ------------------------------------------------------------------------------------------- stage 2: site keys
 // setSitenum (gPET_kernals.cu:607-640) fused with building the (site) sort keys over the time order.
-__global__ void __launch_bounds__(kThreads) k_site_keys(EventSoA ev, DigitizerDev p, const unsigned* __restrict__ t_sorted_vals,
+__global__ void __launch_bounds__(kThreads) k_site_keys(EventSoA ev, DigitizerDev p, const unsigned* __restrict__ tvals0,
+                                                        const unsigned* __restrict__ tvals1, const rsort::SortState* st_time,
                                                         unsigned* __restrict__ order_t, unsigned* __restrict__ keys,
-                                                        unsigned* __restrict__ vals, const unsigned* __restrict__ counters) {
+                                                        unsigned* __restrict__ vals, const unsigned* __restrict__ counters,
+                                                        rsort::SortState* st_site, unsigned* __restrict__ lookback0) {
+    __shared__ unsigned sh_hist[4 * rsort::kBins];
     const unsigned n1 = counters[1];
+    const unsigned* __restrict__ t_sorted_vals = st_time->cur ? tvals1 : tvals0;
+    for (int i = threadIdx.x; i < 4 * rsort::kBins; i += blockDim.x) sh_hist[i] = 0;
+    __syncthreads();
     for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n1; j += gridDim.x * blockDim.x) {
         unsigned i = t_sorted_vals[j];
         order_t[j] = i;
@@ -126,23 +161,33 @@ __global__ void __launch_bounds__(kThreads) k_site_keys(EventSoA ev, DigitizerDe
         }
         if (p.dlevel >= 0 && p.dlevel <= 2) ev.siten[i] = site;
         // flip the sign bit: std::sort compares siten as signed int (gPET.h:101-106)
-        keys[j] = (unsigned)site ^ 0x80000000u;
+        const unsigned key = (unsigned)site ^ 0x80000000u;
+        keys[j] = key;
         vals[j] = j;
+        rsort::hist_add<unsigned, 4>(sh_hist, key);
     }
+    __syncthreads();
+    rsort::hist_flush<4>(sh_hist, st_site);
+    rsort::clear_lookback(lookback0, n1);
 }
 
 // ------------------------------------------------------------------------------------------- stage 3: dead time
 // deadtime (gPET_kernals.cu:657-698) with the snapshot-start semantics of SURVEY 8(a) D7: every decision uses the
-// original times; `tdead` is fp32 and `tdead + interval` is an fp32 sum, as in the reference.
+// original times; `tdead` is fp32 and `tdead + interval` is an fp32 sum, as in the reference.  q runs over the
+// (site, t) order; kill flags are stored by position in the time order.
 __global__ void __launch_bounds__(kThreads) k_deadtime(EventSoA ev, DigitizerDev p, const unsigned* __restrict__ order_t,
-                                                       const unsigned* __restrict__ order_s, const unsigned* __restrict__ site_keys,
-                                                       unsigned char* __restrict__ kill, unsigned* __restrict__ counters) {
+                                                       const unsigned* __restrict__ skeys0, const unsigned* __restrict__ skeys1,
+                                                       const unsigned* __restrict__ svals0, const unsigned* __restrict__ svals1,
+                                                       const rsort::SortState* st_site, unsigned char* __restrict__ kill,
+                                                       const unsigned* __restrict__ counters) {
     const unsigned n1 = counters[1];
     const float tau = p.dtime;
-    unsigned killed = 0;
+    const unsigned cur = st_site->cur;
+    const unsigned* __restrict__ site_keys = cur ? skeys1 : skeys0;
+    const unsigned* __restrict__ order_s = cur ? svals1 : svals0;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n1; q += gridDim.x * blockDim.x) {
-        const unsigned i = order_t[order_s[q]];
-        const double t = ev.t[i];
+        const unsigned j = order_s[q];
+        const double t = ev.t[order_t[j]];
         bool same_prev = false;
         double tprev = 0.0;
         if (q > 0 && site_keys[q] == site_keys[q - 1]) {
@@ -153,190 +198,154 @@ __global__ void __launch_bounds__(kThreads) k_deadtime(EventSoA ev, DigitizerDev
         const bool killable = same_prev && t < (double)__fadd_rn((float)tprev, tau);
         if (p.dtype == 0) {
             // paralyzable: tdead follows every event, so the predicate is predecessor-local
-            kill[i] = killable ? 1 : 0;
-            killed += killable ? 1u : 0u;
+            kill[j] = killable ? 1 : 0;
         } else {
             // non-paralyzable: sequential anchor chain per site.  An event its predecessor cannot kill survives any
             // earlier anchor as well (fp32 rounding and the fp32 sum are monotone), so it is a guaranteed anchor and
             // the chain can be cut there: one thread per such run start, runs are short at realistic rates.
             if (killable) continue;
-            kill[i] = 0;
+            kill[j] = 0;
             float tdead = (float)t;
             unsigned r = q + 1;
             while (r < n1 && site_keys[r] == site_keys[q]) {
-                const unsigned ir = order_t[order_s[r]];
-                const double tr = ev.t[ir];
+                const unsigned jr = order_s[r];
+                const double tr = ev.t[order_t[jr]];
                 const double tr_prev = ev.t[order_t[order_s[r - 1]]];
                 if (!(tr < (double)__fadd_rn((float)tr_prev, tau))) break;  // next run start
                 if (tr < (double)__fadd_rn(tdead, tau)) {
-                    kill[ir] = 1;
-                    killed++;
+                    kill[jr] = 1;
                 } else {
-                    kill[ir] = 0;
+                    kill[jr] = 0;
                     tdead = (float)tr;
                 }
                 r++;
             }
         }
     }
-    killed = warp_sum(killed);
-    if ((threadIdx.x & 31) == 0 && killed) atomicAdd(&counters[5], killed);
 }
 
-// ------------------------------------------------------------------------------------------- stage 4: final flags over the time order
-__global__ void __launch_bounds__(kThreads) k_final_flags(EventSoA ev, DigitizerDev p, const unsigned* __restrict__ order_t,
-                                                          const unsigned char* __restrict__ kill, unsigned* __restrict__ flags,
-                                                          unsigned* __restrict__ counters) {
+// ------------------------------------------------------------------------------------------- single-pass exclusive scan
+// Tiles of 2048 elements (thread = 8 consecutive elements) claimed in order from a device counter; the running
+// total travels from tile to tile through one status word per tile (aggregate / inclusive-prefix flags, 30-bit
+// values), so flagging, scanning and compacting happen in ONE kernel.
+constexpr int kScanTile = 2048;
+
+struct TileScan {
+    unsigned excl[8];    // exclusive prefix of each of the thread's 8 elements (global)
+    unsigned tile_total; // sum over the tile
+    unsigned tile_excl;  // sum over all earlier tiles
+};
+
+__device__ __forceinline__ TileScan tile_exclusive_scan(const unsigned v[8], unsigned tile, unsigned* __restrict__ status) {
+    __shared__ unsigned ws[kThreads / 32];
+    __shared__ unsigned s_excl;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += v[k];
+    unsigned x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (unsigned)o) x += y;
+    }
+    if (lane == 31) ws[warp] = x;
+    __syncthreads();
+    unsigned wprefix = 0, total = 0;
+#pragma unroll
+    for (unsigned w = 0; w < kThreads / 32; w++) {
+        unsigned c = ws[w];
+        if (w < warp) wprefix += c;
+        total += c;
+    }
+    if (threadIdx.x == 0) {
+        unsigned excl = 0;
+        if (tile == 0) {
+            rsort::st_volatile(&status[0], rsort::kFlagPrefix | total);
+        } else {
+            rsort::st_volatile(&status[tile], rsort::kFlagAggregate | total);
+            unsigned t = tile - 1;
+            while (true) {
+                unsigned u = rsort::ld_volatile(&status[t]);
+                if ((u >> 30) == 0u) continue;
+                excl += u & rsort::kValueMask;
+                if (u & rsort::kFlagPrefix) break;
+                t--;
+            }
+            rsort::st_volatile(&status[tile], rsort::kFlagPrefix | (excl + total));
+        }
+        s_excl = excl;
+    }
+    __syncthreads();
+    TileScan r;
+    r.tile_total = total;
+    r.tile_excl = s_excl;
+    unsigned e = s_excl + wprefix + (x - s);
+#pragma unroll
+    for (int k = 0; k < 8; k++) { r.excl[k] = e; e += v[k]; }
+    __syncthreads();  // ws / s_excl are reused by the next tile
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------- stage 4: energy window + compaction -> singles
+// energywindow(Ewinmin, Ewinmax) (gPET.cu:418) over the survivors of the dead time, in time order.
+__global__ void __launch_bounds__(kThreads) k_emit_singles(EventSoA ev, DigitizerDev p, EventSoA singles,
+                                                           gpet_event* __restrict__ singles_aos,
+                                                           const unsigned* __restrict__ order_t,
+                                                           const unsigned char* __restrict__ kill, unsigned* __restrict__ counters,
+                                                           unsigned* __restrict__ status, unsigned long long* __restrict__ spectrum,
+                                                           int nbins, float emin, float emax) {
+    __shared__ unsigned s_tile;
     const unsigned n1 = counters[1];
-    unsigned c2 = 0, c3 = 0;
-    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n1; j += gridDim.x * blockDim.x) {
-        unsigned i = order_t[j];
-        bool a2 = kill[i] == 0;
-        float E = ev.E[i];
-        bool a3 = a2 && !(E < p.Ewinmin || E > p.Ewinmax);  // energywindow(Ewinmin, Ewinmax) (gPET.cu:418)
-        flags[j] = a3 ? 1u : 0u;
-        c2 += a2 ? 1u : 0u;
-        c3 += a3 ? 1u : 0u;
+    const unsigned ntiles = (n1 + kScanTile - 1) / kScanTile;
+    if (ntiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) *singles.count = 0;
+    unsigned c2 = 0;
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(&counters[6], 1u);
+        __syncthreads();
+        const unsigned tile = s_tile;
+        if (tile >= ntiles) break;
+        const unsigned j0 = tile * kScanTile + threadIdx.x * 8;
+        unsigned idx[8], flag[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const unsigned j = j0 + k;
+            flag[k] = 0; idx[k] = 0;
+            if (j < n1) {
+                const unsigned i = order_t[j];
+                idx[k] = i;
+                const bool a2 = kill[j] == 0;
+                const float E = ev.E[i];
+                flag[k] = (a2 && !(E < p.Ewinmin || E > p.Ewinmax)) ? 1u : 0u;
+                c2 += a2 ? 1u : 0u;
+            }
+        }
+        TileScan sc = tile_exclusive_scan(flag, tile, status);
+        if (tile == ntiles - 1 && threadIdx.x == 0) {
+            counters[3] = sc.tile_excl + sc.tile_total;
+            *singles.count = sc.tile_excl + sc.tile_total;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (!flag[k]) continue;
+            const unsigned i = idx[k], o = sc.excl[k];
+            if (o >= singles.capacity) continue;
+            singles.parn[o] = ev.parn[i]; singles.pann[o] = ev.pann[i]; singles.modn[o] = ev.modn[i];
+            singles.cryn[o] = ev.cryn[i]; singles.siten[o] = ev.siten[i]; singles.eventid[o] = ev.eventid[i];
+            singles.t[o] = ev.t[i]; singles.E[o] = ev.E[i];
+            singles.x[o] = ev.x[i]; singles.y[o] = ev.y[i]; singles.z[o] = ev.z[i];
+            if (singles_aos) store_event_aos(singles_aos + o, ev, i);
+            if (spectrum && nbins > 0) {
+                float f = (ev.E[i] - emin) / (emax - emin) * nbins;
+                if (f >= 0.f && f < (float)nbins) atomicAdd(&spectrum[(int)f], 1ull);
+            }
+        }
     }
     c2 = warp_sum(c2);
-    c3 = warp_sum(c3);
-    if ((threadIdx.x & 31) == 0) {
-        if (c2) atomicAdd(&counters[2], c2);
-        if (c3) atomicAdd(&counters[3], c3);
-    }
+    if ((threadIdx.x & 31) == 0 && c2) atomicAdd(&counters[2], c2);
 }
 
-// ------------------------------------------------------------------------------------------- exclusive scan (u32), 3 kernels
-constexpr int kScanTile = 2048;  // 256 threads x 8
-
-__global__ void __launch_bounds__(kThreads) k_scan_reduce(const unsigned* __restrict__ in, const unsigned* __restrict__ n_ptr,
-                                                          unsigned* __restrict__ block_sums) {
-    __shared__ unsigned ws[8];
-    const unsigned n = *n_ptr;
-    const unsigned ntiles = (n + kScanTile - 1) / kScanTile;
-    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        unsigned s = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            unsigned i = tile * kScanTile + k * kThreads + threadIdx.x;
-            if (i < n) s += in[i];
-        }
-        s = warp_sum(s);
-        if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned t = 0;
-            for (int w = 0; w < 8; w++) t += ws[w];
-            block_sums[tile] = t;
-        }
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(1024) k_scan_sums(unsigned* __restrict__ block_sums, const unsigned* __restrict__ n_ptr,
-                                                    unsigned* __restrict__ total) {
-    __shared__ unsigned warp_sums[32];
-    __shared__ unsigned carry;
-    const unsigned n = *n_ptr;
-    const unsigned m = (n + kScanTile - 1) / kScanTile;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned base = 0; base < m; base += 1024) {
-        unsigned i = base + threadIdx.x;
-        unsigned v = i < m ? block_sums[i] : 0u;
-        unsigned x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= (unsigned)o) x += y;
-        }
-        if (lane == 31) warp_sums[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned w = warp_sums[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= (unsigned)o) w += y;
-            }
-            warp_sums[lane] = w;
-        }
-        __syncthreads();
-        unsigned excl = carry + (warp ? warp_sums[warp - 1] : 0u) + (x - v);
-        if (i < m) block_sums[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry += warp_sums[31];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && total) *total = carry;
-}
-
-// out[i] = exclusive prefix of in[] (tile-local scan + scanned block sums)
-__global__ void __launch_bounds__(kThreads) k_scan_apply(const unsigned* __restrict__ in, const unsigned* __restrict__ n_ptr,
-                                                         const unsigned* __restrict__ block_sums, unsigned* __restrict__ out) {
-    __shared__ unsigned ws[8];
-    const unsigned n = *n_ptr;
-    const unsigned ntiles = (n + kScanTile - 1) / kScanTile;
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // blocked arrangement: thread owns 8 consecutive elements
-        unsigned i0 = tile * kScanTile + threadIdx.x * 8;
-        unsigned v[8], s = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) { v[k] = (i0 + k < n) ? in[i0 + k] : 0u; s += v[k]; }
-        unsigned x = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= (unsigned)o) x += y;
-        }
-        if (lane == 31) ws[warp] = x;
-        __syncthreads();
-        unsigned wprefix = 0;
-        for (unsigned w = 0; w < warp; w++) wprefix += ws[w];
-        unsigned excl = block_sums[tile] + wprefix + (x - s);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (i0 + k < n) out[i0 + k] = excl;
-            excl += v[k];
-        }
-        __syncthreads();
-    }
-}
-
-int exclusive_scan(const unsigned* in, unsigned* out, const unsigned* n_dev, unsigned* block_sums, unsigned* total,
-                   int grid, cudaStream_t s) {
-    k_scan_reduce<<<grid, kThreads, 0, s>>>(in, n_dev, block_sums);
-    k_scan_sums<<<1, 1024, 0, s>>>(block_sums, n_dev, total);
-    k_scan_apply<<<grid, kThreads, 0, s>>>(in, n_dev, block_sums, out);
-    return 3;
-}
-
-// ------------------------------------------------------------------------------------------- stage 5: singles out
-__global__ void __launch_bounds__(kThreads) k_emit_singles(EventSoA ev, EventSoA singles, gpet_event* __restrict__ singles_aos,
-                                                           const unsigned* __restrict__ order_t, const unsigned* __restrict__ flags,
-                                                           const unsigned* __restrict__ offs, const unsigned* __restrict__ counters,
-                                                           unsigned long long* __restrict__ spectrum, int nbins, float emin, float emax) {
-    const unsigned n1 = counters[1];
-    if (blockIdx.x == 0 && threadIdx.x == 0) *singles.count = counters[3];
-    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n1; j += gridDim.x * blockDim.x) {
-        if (!flags[j]) continue;
-        unsigned i = order_t[j], o = offs[j];
-        if (o >= singles.capacity) continue;
-        singles.parn[o] = ev.parn[i]; singles.pann[o] = ev.pann[i]; singles.modn[o] = ev.modn[i];
-        singles.cryn[o] = ev.cryn[i]; singles.siten[o] = ev.siten[i]; singles.eventid[o] = ev.eventid[i];
-        singles.t[o] = ev.t[i]; singles.E[o] = ev.E[i];
-        singles.x[o] = ev.x[i]; singles.y[o] = ev.y[i]; singles.z[o] = ev.z[i];
-        if (singles_aos) store_event_aos(singles_aos + o, ev, i);
-        if (spectrum && nbins > 0) {
-            float f = (ev.E[i] - emin) / (emax - emin) * nbins;
-            if (f >= 0.f && f < (float)nbins) atomicAdd(&spectrum[(int)f], 1ull);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------- stage 6: coincidence sorter (extension)
+// ------------------------------------------------------------------------------------------- stage 5: coincidence sorter (extension)
 // Windows are opened by the first single that is not inside an earlier window and last cwin us; a thread owns the
 // run of windows starting at a single whose predecessor is at least cwin earlier (guaranteed opener).
 __device__ __forceinline__ bool pair_ok(const EventSoA& s, unsigned a, unsigned b, const DigitizerDev& p) {
@@ -372,33 +381,47 @@ __global__ void __launch_bounds__(kThreads) k_coinc_count(EventSoA s, DigitizerD
 }
 
 __global__ void __launch_bounds__(kThreads) k_coinc_emit(EventSoA s, DigitizerDev p, const unsigned* __restrict__ cnt,
-                                                         const unsigned* __restrict__ offs, gpet_coincidence* __restrict__ out,
-                                                         unsigned cap) {
+                                                         unsigned* __restrict__ counters, unsigned* __restrict__ status,
+                                                         gpet_coincidence* __restrict__ out, unsigned cap) {
+    __shared__ unsigned s_tile;
     const unsigned n = min(*s.count, s.capacity);
+    const unsigned ntiles = (n + kScanTile - 1) / kScanTile;
     const double W = (double)p.cwin;
-    for (unsigned a = blockIdx.x * blockDim.x + threadIdx.x; a < n; a += gridDim.x * blockDim.x) {
-        if (cnt[a] == 0) continue;
-        unsigned o = offs[a];
-        const double tend = s.t[a] + W;
-        for (unsigned b = a + 1; b < n && s.t[b] < tend; b++) {
-            if (!pair_ok(s, a, b, p)) continue;
-            if (o < cap) {
-                store_event_aos(&out[o].a, s, a);
-                store_event_aos(&out[o].b, s, b);
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(&counters[7], 1u);
+        __syncthreads();
+        const unsigned tile = s_tile;
+        if (tile >= ntiles) break;
+        const unsigned a0 = tile * kScanTile + threadIdx.x * 8;
+        unsigned c[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k] = (a0 + k < n) ? cnt[a0 + k] : 0u;
+        TileScan sc = tile_exclusive_scan(c, tile, status);
+        if (tile == ntiles - 1 && threadIdx.x == 0) counters[4] = sc.tile_excl + sc.tile_total;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (c[k] == 0) continue;
+            const unsigned a = a0 + k;
+            unsigned o = sc.excl[k];
+            const double tend = s.t[a] + W;
+            for (unsigned b = a + 1; b < n && s.t[b] < tend; b++) {
+                if (!pair_ok(s, a, b, p)) continue;
+                if (o < cap) {
+                    store_event_aos(&out[o].a, s, a);
+                    store_event_aos(&out[o].b, s, b);
+                }
+                o++;
             }
-            o++;
         }
     }
-}
-
-__global__ void k_zero_counters(unsigned* counters) {
-    if (threadIdx.x < 8) counters[threadIdx.x] = 0;  // [8..] belong to the detector stage
 }
 
 }  // namespace
 
 // ================================================================================================ launchers
-static inline int grid_for(int num_sms) { return num_sms * 4; }
+static inline int grid_for(int num_sms) { return num_sms * 2; }
+
+size_t sort_state_bytes() { return sizeof(rsort::SortState); }
 
 int launch_events_aos_to_soa(const void* aos, EventSoA ev, unsigned int n, cudaStream_t s) {
     unsigned blocks = n ? (n + kThreads - 1) / kThreads : 1;
@@ -412,47 +435,31 @@ int launch_events_soa_to_aos(EventSoA ev, void* aos, cudaStream_t s) {
     return 1;
 }
 
-int launch_radix_sort_pairs(SortWorkspace& ws, const unsigned int* n_dev, int begin_bit, int end_bit, int* result_buffer,
-                            int num_sms, cudaStream_t s) {
-    return radix_sort_pairs<unsigned long long>(ws.keys, ws.vals, ws.tile_hist, n_dev, begin_bit, end_bit, result_buffer,
-                                                grid_for(num_sms), s);
-}
-
 int launch_digitize(EventSoA ev, EventSoA singles, void* singles_aos, void* coinc_aos, unsigned int coinc_cap,
                     const DigitizerDev& p, DigitizerWorkspace& ws, uint64_t seed, int num_sms, cudaStream_t s) {
     const int grid = grid_for(num_sms);
     int launches = 0;
-    k_zero_counters<<<1, 32, 0, s>>>(ws.counters);
-    k_prep<<<grid, kThreads, 0, s>>>(ev, p, seed, ws.sort.keys[0], ws.sort.vals[0], ws.counters);
+    k_begin<<<8, kThreads, 0, s>>>(ws.counters, ws.st_time, ws.st_site, ws.scan_status[0], ws.scan_status[1], ws.max_tiles);
+    k_prep<<<grid, kThreads, 0, s>>>(ev, p, seed, ws.tkeys[0], ws.tvals[0], ws.counters, ws.st_time, ws.lookback[0]);
     launches += 2;
     // time sort over all n_in records (dead ones carry the maximal key and sink to the tail, like MAXT does)
-    int rb = 0;
-    launches += radix_sort_pairs<unsigned long long>(ws.sort.keys, ws.sort.vals, ws.sort.tile_hist, &ws.counters[0], 0, 64,
-                                                     &rb, grid, s);
+    launches += radix_sort_passes<unsigned long long>(ws.tkeys, ws.tvals, &ws.counters[0], ws.st_time, ws.lookback, 8, grid, s);
     // site keys + site sort (stable => (site, t) order == orderevents, detector.cu:369-385)
-    unsigned* k32[2] = {reinterpret_cast<unsigned*>(ws.sort.keys[rb ^ 1]),
-                        reinterpret_cast<unsigned*>(ws.sort.keys[rb ^ 1]) + ws.sort.capacity};
-    unsigned* v32[2] = {ws.order_s, ws.sort.vals[rb ^ 1]};
-    k_site_keys<<<grid, kThreads, 0, s>>>(ev, p, ws.sort.vals[rb], ws.order_t, k32[0], v32[0], ws.counters);
+    k_site_keys<<<grid, kThreads, 0, s>>>(ev, p, ws.tvals[0], ws.tvals[1], ws.st_time, ws.order_t, ws.skeys[0], ws.svals[0],
+                                          ws.counters, ws.st_site, ws.lookback[0]);
     launches += 1;
-    int rb2 = 0;
-    launches += radix_sort_pairs<unsigned>(k32, v32, ws.sort.tile_hist, &ws.counters[1], 0, 32, &rb2, grid, s);
-    // 32 bits = 4 passes -> result back in buffer 0 (k32[0], ws.order_s)
-    k_deadtime<<<grid, kThreads, 0, s>>>(ev, p, ws.order_t, v32[rb2], k32[rb2], ws.kill, ws.counters);
-    k_final_flags<<<grid, kThreads, 0, s>>>(ev, p, ws.order_t, ws.kill, ws.flags, ws.counters);
+    launches += radix_sort_passes<unsigned>(ws.skeys, ws.svals, &ws.counters[1], ws.st_site, ws.lookback, 4, grid, s);
+    k_deadtime<<<grid, kThreads, 0, s>>>(ev, p, ws.order_t, ws.skeys[0], ws.skeys[1], ws.svals[0], ws.svals[1], ws.st_site,
+                                         ws.kill, ws.counters);
+    k_emit_singles<<<grid, kThreads, 0, s>>>(ev, p, singles, static_cast<gpet_event*>(singles_aos), ws.order_t, ws.kill,
+                                             ws.counters, ws.scan_status[0], ws.spectrum, ws.spectrum_bins, ws.spec_emin,
+                                             ws.spec_emax);
     launches += 2;
-    unsigned* offs = ws.sort.vals[rb];  // time-sort payload no longer needed (order_t holds it)
-    launches += exclusive_scan(ws.flags, offs, &ws.counters[1], ws.scan_tmp, nullptr, grid, s);
-    k_emit_singles<<<grid, kThreads, 0, s>>>(ev, singles, static_cast<gpet_event*>(singles_aos), ws.order_t, ws.flags, offs,
-                                             ws.counters, ws.spectrum, ws.spectrum_bins, ws.spec_emin, ws.spec_emax);
-    launches += 1;
     if (p.cwin > 0.f && coinc_aos) {
-        unsigned* cnt = ws.flags;
-        k_coinc_count<<<grid, kThreads, 0, s>>>(singles, p, cnt);
-        launches += 1;
-        launches += exclusive_scan(cnt, offs, singles.count, ws.scan_tmp, &ws.counters[4], grid, s);
-        k_coinc_emit<<<grid, kThreads, 0, s>>>(singles, p, cnt, offs, static_cast<gpet_coincidence*>(coinc_aos), coinc_cap);
-        launches += 1;
+        k_coinc_count<<<grid, kThreads, 0, s>>>(singles, p, ws.coinc_cnt);
+        k_coinc_emit<<<grid, kThreads, 0, s>>>(singles, p, ws.coinc_cnt, ws.counters, ws.scan_status[1],
+                                               static_cast<gpet_coincidence*>(coinc_aos), coinc_cap);
+        launches += 2;
     }
     return launches;
 }

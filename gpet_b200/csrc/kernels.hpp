@@ -8,33 +8,35 @@
 
 namespace gpet {
 
-struct SortWorkspace {
-    unsigned long long* keys[2];  // ping-pong
-    unsigned int* vals[2];
-    unsigned int* tile_hist;      // 256 * max_tiles
-    unsigned int max_tiles;
-    unsigned int capacity;
-};
+namespace rsort { struct SortState; }
 
 struct DigitizerWorkspace {
-    SortWorkspace sort;
-    unsigned int* order_t;     // event index in time order (first count1 entries alive)
-    unsigned int* order_s;     // position-in-time-order, sorted by (site, t)
-    unsigned int* site_sorted; // site of order_s[p]
-    unsigned char* kill;       // per event: 1 = removed by dead time
-    unsigned int* flags;       // per time-order position: survives everything
-    unsigned int* scan_tmp;    // block sums for the compaction scan
-    unsigned int* counters;    // [0] n_in [1] after thresholder [2] after deadtime [3] singles [4] coincidences [5..] scratch
+    unsigned long long* tkeys[2];  // time sort ping-pong: order-preserving u64 image of the fp64 time
+    unsigned int* tvals[2];        //   payload: event index
+    unsigned int* skeys[2];        // site sort ping-pong: site number with the sign bit flipped
+    unsigned int* svals[2];        //   payload: position in the time order
+    unsigned int* lookback[2];     // max_tiles * 256 status words each (radix passes alternate between them)
+    rsort::SortState* st_time;     // device-resident sort bookkeeping (histograms, tile counters, current buffer)
+    rsort::SortState* st_site;
+    unsigned int* scan_status[2];  // max_tiles status words each: singles compaction, coincidence compaction
+    unsigned int max_tiles;
+    unsigned int capacity;
+    unsigned int* order_t;         // event index in time order (first counters[1] entries alive)
+    unsigned char* kill;           // per time-order position: 1 = removed by dead time
+    unsigned int* coinc_cnt;       // per single: coincidences it opens
+    // [0] n_in [1] after thresholder [2] after deadtime [3] singles [4] coincidences [6],[7] tile tickets of the two
+    // compactions [8] photons on a panel [9] adder drops; [16..20] queue 0, queue 1, hits, events, singles counts
+    unsigned int* counters;
     unsigned long long* spectrum; int spectrum_bins; float spec_emin, spec_emax;
 };
+
+size_t sort_state_bytes();
 
 // ---- digitizer (digitizer.cu) --------------------------------------------------------------------------
 int launch_events_aos_to_soa(const void* aos, EventSoA ev, unsigned int n, cudaStream_t s);
 int launch_events_soa_to_aos(EventSoA ev, void* aos, cudaStream_t s);
 int launch_digitize(EventSoA ev, EventSoA singles, void* singles_aos, void* coinc_aos, unsigned int coinc_cap,
                     const DigitizerDev& p, DigitizerWorkspace& ws, uint64_t seed, int num_sms, cudaStream_t s);
-int launch_radix_sort_pairs(SortWorkspace& ws, const unsigned int* n_dev, int begin_bit, int end_bit,
-                            int* result_buffer, int num_sms, cudaStream_t s);
 
 // ---- transport (transport.cu) ----------------------------------------------------------------------------
 int launch_source(const SourceDev* frame_dev, unsigned long long npairs, PhantomDev ph, PhotonQueue q0,
