@@ -128,6 +128,9 @@ _SIGS = {
     "gpet_get_spectrum": (C.c_int, [_P, _P, C.c_int]),
     "gpet_set_spectrum": (C.c_int, [_P, C.c_int, C.c_float, C.c_float]),
     "gpet_set_shard": (C.c_int, [_P, C.c_int, C.c_int]),
+    "gpet_profile_enable": (C.c_int, [_P, C.c_int]),
+    "gpet_profile_count": (C.c_int, [_P]),
+    "gpet_profile_get": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 }
 
 _lib = None
@@ -267,6 +270,23 @@ class Context:
 
     def set_source_atoms(self, i, natom):
         self._ck(self._l.gpet_set_source_atoms(self._h, i, natom))
+
+    def profile(self, on=True):
+        """Switch per-kernel CUDA-event timing on (clears earlier numbers) or off."""
+        self._ck(self._l.gpet_profile_enable(self._h, 1 if on else 0))
+
+    def kernel_times(self):
+        """{kernel name: (total ms, launches)} accumulated since profile(True); synchronises the stream."""
+        n = self._l.gpet_profile_count(self._h)
+        if n < 0:
+            self._ck(n)
+        out = {}
+        buf = C.create_string_buffer(128)
+        for i in range(n):
+            ms, cnt = C.c_double(), C.c_uint64()
+            self._ck(self._l.gpet_profile_get(self._h, i, buf, 128, C.byref(ms), C.byref(cnt)))
+            out[buf.value.decode()] = (ms.value, int(cnt.value))
+        return out
 
     def set_shard(self, rank, world):
         self._ck(self._l.gpet_set_shard(self._h, rank, world))

@@ -11,7 +11,14 @@
 
 using namespace gpet;
 
+namespace gpet { thread_local KernelTimer* g_ktimer = nullptr; }
+
 namespace {
+
+struct ProfScope {   // routes the launchers' event brackets to this context while profiling is on
+    explicit ProfScope(gpet_ctx* c) { g_ktimer = (c && c->profiling) ? &c->ktimer : nullptr; }
+    ~ProfScope() { g_ktimer = nullptr; }
+};
 
 int fail(const gpet_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
@@ -76,6 +83,7 @@ int ensure_buffers(gpet_ctx* c) {
     CK(cudaMemset(w.counters, 0, 64 * sizeof(unsigned)));
     if ((r = alloc_queue(c, c->q[0], cp, w.counters + 16))) return r;
     if ((r = alloc_queue(c, c->q[1], cp, w.counters + 17))) return r;
+    if ((r = alloc_queue(c, c->q[2], cp, w.counters + 21))) return r;   // photons that entered a panel (panel-local frame)
     if ((r = dev_alloc(c, &c->hits.id, 5 * ch))) return r;
     if ((r = dev_alloc(c, &c->hits.f, 5 * ch))) return r;
     if ((r = dev_alloc(c, &c->hits.t, ch))) return r;
@@ -90,10 +98,10 @@ int ensure_buffers(gpet_ctx* c) {
         if ((r = dev_alloc(c, &w.svals[k], ce))) return r;
     }
     w.capacity = (unsigned)ce;
-    w.max_tiles = (unsigned)((ce + 2047) / 2048);
+    w.max_tiles = scan_tiles(ce);
     for (int k = 0; k < 2; k++) {
-        if ((r = dev_alloc(c, &w.lookback[k], (size_t)256 * w.max_tiles))) return r;
-        CK(cudaMemset(w.lookback[k], 0, (size_t)256 * w.max_tiles * sizeof(unsigned)));
+        if ((r = dev_alloc(c, &w.lookback[k], sort_lookback_words(ce)))) return r;
+        CK(cudaMemset(w.lookback[k], 0, sort_lookback_words(ce) * sizeof(unsigned)));
         if ((r = dev_alloc(c, &w.scan_status[k], (size_t)w.max_tiles))) return r;
     }
     {
@@ -685,6 +693,7 @@ int gpet_get_frame(const gpet_ctx* c, int64_t f, double* t0, double* dt, uint64_
 // =================================================================================================== stages
 int gpet_stage_source(gpet_ctx* c, int64_t f) {
     NEED_DEVICE();
+    ProfScope prof(c);
     if (!c->planned) return fail(c, GPET_ERR_ARG, "gpet_plan_frames must be called first");
     if (f < 0 || f >= (int64_t)c->frames.size()) return fail(c, GPET_ERR_ARG, "frame index out of range");
     int r;
@@ -706,6 +715,7 @@ int gpet_stage_psf(gpet_ctx* c, int64_t first, int64_t n) {
 
 int gpet_stage_phantom(gpet_ctx* c) {
     NEED_DEVICE();
+    ProfScope prof(c);
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((r = upload_phantom(c))) return r;
@@ -716,10 +726,11 @@ int gpet_stage_phantom(gpet_ctx* c) {
 
 int gpet_stage_detector(gpet_ctx* c) {
     NEED_DEVICE();
+    ProfScope prof(c);
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((r = upload_geometry(c))) return r;
-    c->stats.kernel_launches += launch_detector(c->q[1], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth,
+    c->stats.kernel_launches += launch_detector(c->q[1], c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth,
                                                 c->dig.readout_policy, c->tr.record_hits, c->hits, c->ev, c->ws.counters,
                                                 c->seed, c->num_sms, c->stream);
     CK(cudaGetLastError());
@@ -728,6 +739,7 @@ int gpet_stage_detector(gpet_ctx* c) {
 
 int gpet_stage_digitize(gpet_ctx* c) {
     NEED_DEVICE();
+    ProfScope prof(c);
     int r;
     if ((r = ensure_buffers(c))) return r;
     DigitizerDev d = digitizer_dev(c);
@@ -748,6 +760,7 @@ int64_t gpet_queue_size(gpet_ctx* c, int which) {
 
 int gpet_put_photons(gpet_ctx* c, int which, const gpet_photon* in, int64_t n) {
     NEED_DEVICE();
+    ProfScope prof(c);
     if (which < 0 || which > 1 || n < 0 || (n > 0 && !in)) return GPET_ERR_ARG;
     int r;
     if ((r = ensure_buffers(c))) return r;
@@ -771,6 +784,7 @@ int64_t gpet_fetch_photons(gpet_ctx* c, int which, gpet_photon* out, int64_t cap
 
 int gpet_put_events(gpet_ctx* c, const gpet_event* in, int64_t n) {
     NEED_DEVICE();
+    ProfScope prof(c);
     if (n < 0 || (n > 0 && !in)) return GPET_ERR_ARG;
     int r;
     if ((r = ensure_buffers(c))) return r;
@@ -1027,6 +1041,31 @@ int gpet_set_spectrum(gpet_ctx* c, int nbins, float emin, float emax) {
     if (!c || nbins < 1 || nbins > (1 << 20) || !(emax > emin)) return GPET_ERR_ARG;
     if (c->dev_buffers) return fail(c, GPET_ERR_ARG, "spectrum must be configured before the first compute call");
     c->ws.spectrum_bins = nbins; c->ws.spec_emin = emin; c->ws.spec_emax = emax;
+    return GPET_OK;
+}
+
+int gpet_profile_enable(gpet_ctx* c, int on) {
+    NEED_DEVICE();
+    CK(cudaStreamSynchronize(c->stream));
+    c->ktimer.reset();
+    c->profiling = on != 0;
+    return GPET_OK;
+}
+
+int gpet_profile_count(gpet_ctx* c) {
+    NEED_DEVICE();
+    CK(cudaStreamSynchronize(c->stream));
+    c->ktimer.collect();
+    return (int)c->ktimer.order.size();
+}
+
+int gpet_profile_get(gpet_ctx* c, int i, char* name, int name_cap, double* total_ms, uint64_t* launches) {
+    if (!c || i < 0 || i >= (int)c->ktimer.order.size() || !name || name_cap < 1) return GPET_ERR_ARG;
+    const std::string& n = c->ktimer.order[(size_t)i];
+    snprintf(name, (size_t)name_cap, "%s", n.c_str());
+    const KernelTimer::Acc& a = c->ktimer.acc[n];
+    if (total_ms) *total_ms = a.ms;
+    if (launches) *launches = a.launches;
     return GPET_OK;
 }
 

@@ -7,6 +7,7 @@
 #include "device_types.cuh"
 #include "host_io.hpp"
 #include "kernels.hpp"
+#include "ktimer.hpp"
 
 struct FramePlan {
     double t0_s = 0.0, dt_s = 0.0;             // absolute start (s) and length of the slice
@@ -45,7 +46,7 @@ struct gpet_ctx {
 
     // ---- device state
     bool dev_buffers = false, dev_tables = false, dev_phantom = false, dev_geo = false;
-    gpet::PhotonQueue q[2]{};
+    gpet::PhotonQueue q[3]{};   // after source, after phantom, entered a panel
     gpet::HitBuffer hits{};
     gpet::EventSoA ev{}, singles{};
     gpet::DigitizerWorkspace ws{};
@@ -72,5 +73,7 @@ struct gpet_ctx {
     std::vector<gpet_coincidence> res_coinc;
     gpet_stats stats{};
     uint64_t last_counts[4] = {0, 0, 0, 0};
+    gpet::KernelTimer ktimer;   // per-kernel CUDA-event times (gpet_profile_enable)
+    bool profiling = false;
     int64_t psf_first = 0;  // global index of photon 0 of the current PSF batch
 };

@@ -9,8 +9,10 @@
 //
 // Launches per frame: k_begin, k_prep, 8 x k_onesweep<u64>, k_site_keys, 4 x k_onesweep<u32> (passes whose digit is
 // constant return at once), k_deadtime, k_emit_singles [, k_coinc_count, k_coinc_emit].
+#include <cstdlib>
 #include "kernels.hpp"
 #include "philox.cuh"
+#include "ktimer.hpp"
 #include "radix_sort.cuh"
 
 #include "../../include/gpet_b200.h"
@@ -54,6 +56,38 @@ __device__ __forceinline__ void store_event_aos(gpet_event* dst, const EventSoA&
     int4 c = make_int4(__float_as_int(ev.E[i]), __float_as_int(ev.x[i]), __float_as_int(ev.y[i]), __float_as_int(ev.z[i]));
     int4* p = reinterpret_cast<int4*>(dst);
     p[0] = a; p[1] = b; p[2] = c;
+}
+
+// One event held in registers: all eleven columns are loaded before anything is stored, so the loads are independent
+// (the SoA columns may alias as far as the compiler can tell, which would otherwise serialise load -> store -> load).
+struct EventRec {
+    int parn, pann, modn, cryn, siten, eventid;
+    double t;
+    float E, x, y, z;
+};
+
+__device__ __forceinline__ EventRec load_event(const EventSoA& ev, unsigned i) {
+    EventRec r;
+    r.parn = ev.parn[i]; r.pann = ev.pann[i]; r.modn = ev.modn[i]; r.cryn = ev.cryn[i];
+    r.siten = ev.siten[i]; r.eventid = ev.eventid[i];
+    r.t = ev.t[i];
+    r.E = ev.E[i]; r.x = ev.x[i]; r.y = ev.y[i]; r.z = ev.z[i];
+    return r;
+}
+
+__device__ __forceinline__ void store_event(const EventSoA& ev, unsigned o, const EventRec& r) {
+    ev.parn[o] = r.parn; ev.pann[o] = r.pann; ev.modn[o] = r.modn; ev.cryn[o] = r.cryn;
+    ev.siten[o] = r.siten; ev.eventid[o] = r.eventid;
+    ev.t[o] = r.t;
+    ev.E[o] = r.E; ev.x[o] = r.x; ev.y[o] = r.y; ev.z[o] = r.z;
+}
+
+__device__ __forceinline__ void store_event_aos(gpet_event* dst, const EventRec& r) {
+    long long tb = __double_as_longlong(r.t);
+    int4* p = reinterpret_cast<int4*>(dst);
+    p[0] = make_int4(r.parn, r.pann, r.modn, r.cryn);
+    p[1] = make_int4(r.siten, r.eventid, (int)(unsigned)(tb & 0xffffffffll), (int)(unsigned)((unsigned long long)tb >> 32));
+    p[2] = make_int4(__float_as_int(r.E), __float_as_int(r.x), __float_as_int(r.y), __float_as_int(r.z));
 }
 
 __global__ void k_soa_to_aos(EventSoA ev, gpet_event* __restrict__ aos) {
@@ -146,7 +180,7 @@ __global__ void __launch_bounds__(kThreads) k_site_keys(EventSoA ev, DigitizerDe
                                                         rsort::SortState* st_site, unsigned* __restrict__ lookback0) {
     __shared__ unsigned sh_hist[4 * rsort::kBins];
     const unsigned n1 = counters[1];
-    const unsigned* __restrict__ t_sorted_vals = st_time->cur ? tvals1 : tvals0;
+    const unsigned* __restrict__ t_sorted_vals = rsort::current_buffer(st_time, 8, counters[0]) ? tvals1 : tvals0;
     for (int i = threadIdx.x; i < 4 * rsort::kBins; i += blockDim.x) sh_hist[i] = 0;
     __syncthreads();
     for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n1; j += gridDim.x * blockDim.x) {
@@ -182,7 +216,7 @@ __global__ void __launch_bounds__(kThreads) k_deadtime(EventSoA ev, DigitizerDev
                                                        const unsigned* __restrict__ counters) {
     const unsigned n1 = counters[1];
     const float tau = p.dtime;
-    const unsigned cur = st_site->cur;
+    const unsigned cur = rsort::current_buffer(st_site, 4, n1);
     const unsigned* __restrict__ site_keys = cur ? skeys1 : skeys0;
     const unsigned* __restrict__ order_s = cur ? svals1 : svals0;
     for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n1; q += gridDim.x * blockDim.x) {
@@ -229,6 +263,7 @@ __global__ void __launch_bounds__(kThreads) k_deadtime(EventSoA ev, DigitizerDev
 // total travels from tile to tile through one status word per tile (aggregate / inclusive-prefix flags, 30-bit
 // values), so flagging, scanning and compacting happen in ONE kernel.
 constexpr int kScanTile = 2048;
+constexpr int kSpecSmemBins = 1024;
 
 struct TileScan {
     unsigned excl[8];    // exclusive prefix of each of the thread's 8 elements (global)
@@ -264,14 +299,7 @@ __device__ __forceinline__ TileScan tile_exclusive_scan(const unsigned v[8], uns
             rsort::st_volatile(&status[0], rsort::kFlagPrefix | total);
         } else {
             rsort::st_volatile(&status[tile], rsort::kFlagAggregate | total);
-            unsigned t = tile - 1;
-            while (true) {
-                unsigned u = rsort::ld_volatile(&status[t]);
-                if ((u >> 30) == 0u) continue;
-                excl += u & rsort::kValueMask;
-                if (u & rsort::kFlagPrefix) break;
-                t--;
-            }
+            excl = rsort::lookback_sum(status, 1, tile);
             rsort::st_volatile(&status[tile], rsort::kFlagPrefix | (excl + total));
         }
         s_excl = excl;
@@ -296,9 +324,14 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventSoA ev, Digitize
                                                            unsigned* __restrict__ status, unsigned long long* __restrict__ spectrum,
                                                            int nbins, float emin, float emax) {
     __shared__ unsigned s_tile;
+    __shared__ unsigned s_idx[kScanTile];
+    __shared__ unsigned s_spec[kSpecSmemBins];   // block-private energy histogram (flushed once per block)
     const unsigned n1 = counters[1];
     const unsigned ntiles = (n1 + kScanTile - 1) / kScanTile;
     if (ntiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) *singles.count = 0;
+    const bool spec_smem = spectrum && nbins > 0 && nbins <= kSpecSmemBins;
+    if (spec_smem)
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x) s_spec[b] = 0;
     unsigned c2 = 0;
     while (true) {
         if (threadIdx.x == 0) s_tile = atomicAdd(&counters[6], 1u);
@@ -325,21 +358,45 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventSoA ev, Digitize
             counters[3] = sc.tile_excl + sc.tile_total;
             *singles.count = sc.tile_excl + sc.tile_total;
         }
+        // survivors of this tile, in order, through shared memory: the emission below is then one single per thread
+        // and iteration, with coalesced column stores
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (!flag[k]) continue;
-            const unsigned i = idx[k], o = sc.excl[k];
-            if (o >= singles.capacity) continue;
-            singles.parn[o] = ev.parn[i]; singles.pann[o] = ev.pann[i]; singles.modn[o] = ev.modn[i];
-            singles.cryn[o] = ev.cryn[i]; singles.siten[o] = ev.siten[i]; singles.eventid[o] = ev.eventid[i];
-            singles.t[o] = ev.t[i]; singles.E[o] = ev.E[i];
-            singles.x[o] = ev.x[i]; singles.y[o] = ev.y[i]; singles.z[o] = ev.z[i];
-            if (singles_aos) store_event_aos(singles_aos + o, ev, i);
+        for (int k = 0; k < 8; k++)
+            if (flag[k]) s_idx[sc.excl[k] - sc.tile_excl] = idx[k];
+        __syncthreads();
+        for (unsigned r = threadIdx.x; r < sc.tile_total; r += 2 * kThreads) {
+            const unsigned r2 = r + kThreads;
+            const bool two = r2 < sc.tile_total;
+            const unsigned o = sc.tile_excl + r, o2 = sc.tile_excl + r2;
+            const EventRec a = load_event(ev, s_idx[r]);
+            EventRec b = a;
+            if (two) b = load_event(ev, s_idx[r2]);
+            if (o < singles.capacity) {
+                store_event(singles, o, a);
+                if (singles_aos) store_event_aos(singles_aos + o, a);
+            }
+            if (two && o2 < singles.capacity) {
+                store_event(singles, o2, b);
+                if (singles_aos) store_event_aos(singles_aos + o2, b);
+            }
             if (spectrum && nbins > 0) {
-                float f = (ev.E[i] - emin) / (emax - emin) * nbins;
-                if (f >= 0.f && f < (float)nbins) atomicAdd(&spectrum[(int)f], 1ull);
+                float f = (a.E - emin) / (emax - emin) * nbins;
+                if (f >= 0.f && f < (float)nbins) {
+                    if (spec_smem) atomicAdd(&s_spec[(int)f], 1u);
+                    else atomicAdd(&spectrum[(int)f], 1ull);
+                }
+                f = (b.E - emin) / (emax - emin) * nbins;
+                if (two && f >= 0.f && f < (float)nbins) {
+                    if (spec_smem) atomicAdd(&s_spec[(int)f], 1u);
+                    else atomicAdd(&spectrum[(int)f], 1ull);
+                }
             }
         }
+    }
+    if (spec_smem) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x)
+            if (s_spec[b]) atomicAdd(&spectrum[b], (unsigned long long)s_spec[b]);
     }
     c2 = warp_sum(c2);
     if ((threadIdx.x & 31) == 0 && c2) atomicAdd(&counters[2], c2);
@@ -382,6 +439,7 @@ __global__ void __launch_bounds__(kThreads) k_coinc_count(EventSoA s, DigitizerD
 
 __global__ void __launch_bounds__(kThreads) k_coinc_emit(EventSoA s, DigitizerDev p, const unsigned* __restrict__ cnt,
                                                          unsigned* __restrict__ counters, unsigned* __restrict__ status,
+                                                         const gpet_event* __restrict__ singles_aos,
                                                          gpet_coincidence* __restrict__ out, unsigned cap) {
     __shared__ unsigned s_tile;
     const unsigned n = min(*s.count, s.capacity);
@@ -406,9 +464,13 @@ __global__ void __launch_bounds__(kThreads) k_coinc_emit(EventSoA s, DigitizerDe
             const double tend = s.t[a] + W;
             for (unsigned b = a + 1; b < n && s.t[b] < tend; b++) {
                 if (!pair_ok(s, a, b, p)) continue;
-                if (o < cap) {
-                    store_event_aos(&out[o].a, s, a);
-                    store_event_aos(&out[o].b, s, b);
+                if (o < cap) {  // 2 x 48-byte records copied as 6 x 16 B from the AoS singles list
+                    const int4* pa = reinterpret_cast<const int4*>(singles_aos + a);
+                    const int4* pb = reinterpret_cast<const int4*>(singles_aos + b);
+                    const int4 a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
+                    const int4 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
+                    int4* po = reinterpret_cast<int4*>(out + o);
+                    po[0] = a0; po[1] = a1; po[2] = a2; po[3] = b0; po[4] = b1; po[5] = b2;
                 }
                 o++;
             }
@@ -422,16 +484,18 @@ __global__ void __launch_bounds__(kThreads) k_coinc_emit(EventSoA s, DigitizerDe
 static inline int grid_for(int num_sms) { return num_sms * 2; }
 
 size_t sort_state_bytes() { return sizeof(rsort::SortState); }
+size_t sort_lookback_words(size_t capacity) { return ((capacity + rsort::kTile - 1) / rsort::kTile) * (size_t)rsort::kBins; }
+unsigned scan_tiles(size_t capacity) { return (unsigned)((capacity + kScanTile - 1) / kScanTile); }
 
 int launch_events_aos_to_soa(const void* aos, EventSoA ev, unsigned int n, cudaStream_t s) {
     unsigned blocks = n ? (n + kThreads - 1) / kThreads : 1;
     if (blocks > 4096) blocks = 4096;
-    k_aos_to_soa<<<blocks, kThreads, 0, s>>>(static_cast<const gpet_event*>(aos), ev, n);
+    GPET_LAUNCH("k_aos_to_soa", s, k_aos_to_soa<<<blocks, kThreads, 0, s>>>(static_cast<const gpet_event*>(aos), ev, n));
     return 1;
 }
 
 int launch_events_soa_to_aos(EventSoA ev, void* aos, cudaStream_t s) {
-    k_soa_to_aos<<<1024, kThreads, 0, s>>>(ev, static_cast<gpet_event*>(aos));
+    GPET_LAUNCH("k_soa_to_aos", s, k_soa_to_aos<<<1024, kThreads, 0, s>>>(ev, static_cast<gpet_event*>(aos)));
     return 1;
 }
 
@@ -439,26 +503,27 @@ int launch_digitize(EventSoA ev, EventSoA singles, void* singles_aos, void* coin
                     const DigitizerDev& p, DigitizerWorkspace& ws, uint64_t seed, int num_sms, cudaStream_t s) {
     const int grid = grid_for(num_sms);
     int launches = 0;
-    k_begin<<<8, kThreads, 0, s>>>(ws.counters, ws.st_time, ws.st_site, ws.scan_status[0], ws.scan_status[1], ws.max_tiles);
-    k_prep<<<grid, kThreads, 0, s>>>(ev, p, seed, ws.tkeys[0], ws.tvals[0], ws.counters, ws.st_time, ws.lookback[0]);
+    GPET_LAUNCH("k_begin", s, k_begin<<<8, kThreads, 0, s>>>(ws.counters, ws.st_time, ws.st_site, ws.scan_status[0], ws.scan_status[1], ws.max_tiles));
+    GPET_LAUNCH("k_prep", s, k_prep<<<grid, kThreads, 0, s>>>(ev, p, seed, ws.tkeys[0], ws.tvals[0], ws.counters, ws.st_time, ws.lookback[0]));
     launches += 2;
     // time sort over all n_in records (dead ones carry the maximal key and sink to the tail, like MAXT does)
     launches += radix_sort_passes<unsigned long long>(ws.tkeys, ws.tvals, &ws.counters[0], ws.st_time, ws.lookback, 8, grid, s);
     // site keys + site sort (stable => (site, t) order == orderevents, detector.cu:369-385)
-    k_site_keys<<<grid, kThreads, 0, s>>>(ev, p, ws.tvals[0], ws.tvals[1], ws.st_time, ws.order_t, ws.skeys[0], ws.svals[0],
-                                          ws.counters, ws.st_site, ws.lookback[0]);
+    GPET_LAUNCH("k_site_keys", s, k_site_keys<<<grid, kThreads, 0, s>>>(ev, p, ws.tvals[0], ws.tvals[1], ws.st_time, ws.order_t, ws.skeys[0], ws.svals[0],
+                                          ws.counters, ws.st_site, ws.lookback[0]));
     launches += 1;
     launches += radix_sort_passes<unsigned>(ws.skeys, ws.svals, &ws.counters[1], ws.st_site, ws.lookback, 4, grid, s);
-    k_deadtime<<<grid, kThreads, 0, s>>>(ev, p, ws.order_t, ws.skeys[0], ws.skeys[1], ws.svals[0], ws.svals[1], ws.st_site,
-                                         ws.kill, ws.counters);
-    k_emit_singles<<<grid, kThreads, 0, s>>>(ev, p, singles, static_cast<gpet_event*>(singles_aos), ws.order_t, ws.kill,
+    GPET_LAUNCH("k_deadtime", s, k_deadtime<<<grid, kThreads, 0, s>>>(ev, p, ws.order_t, ws.skeys[0], ws.skeys[1], ws.svals[0], ws.svals[1], ws.st_site,
+                                         ws.kill, ws.counters));
+    GPET_LAUNCH("k_emit_singles", s, k_emit_singles<<<grid, kThreads, 0, s>>>(ev, p, singles, static_cast<gpet_event*>(singles_aos), ws.order_t, ws.kill,
                                              ws.counters, ws.scan_status[0], ws.spectrum, ws.spectrum_bins, ws.spec_emin,
-                                             ws.spec_emax);
+                                             ws.spec_emax));
     launches += 2;
     if (p.cwin > 0.f && coinc_aos) {
-        k_coinc_count<<<grid, kThreads, 0, s>>>(singles, p, ws.coinc_cnt);
-        k_coinc_emit<<<grid, kThreads, 0, s>>>(singles, p, ws.coinc_cnt, ws.counters, ws.scan_status[1],
-                                               static_cast<gpet_coincidence*>(coinc_aos), coinc_cap);
+        GPET_LAUNCH("k_coinc_count", s, k_coinc_count<<<grid, kThreads, 0, s>>>(singles, p, ws.coinc_cnt));
+        GPET_LAUNCH("k_coinc_emit", s, k_coinc_emit<<<grid, kThreads, 0, s>>>(singles, p, ws.coinc_cnt, ws.counters, ws.scan_status[1],
+                                               static_cast<const gpet_event*>(singles_aos),
+                                               static_cast<gpet_coincidence*>(coinc_aos), coinc_cap));
         launches += 2;
     }
     return launches;

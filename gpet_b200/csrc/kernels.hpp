@@ -15,7 +15,7 @@ struct DigitizerWorkspace {
     unsigned int* tvals[2];        //   payload: event index
     unsigned int* skeys[2];        // site sort ping-pong: site number with the sign bit flipped
     unsigned int* svals[2];        //   payload: position in the time order
-    unsigned int* lookback[2];     // max_tiles * 256 status words each (radix passes alternate between them)
+    unsigned int* lookback[2];     // sort_lookback_words(capacity) status words each (radix passes alternate between them)
     rsort::SortState* st_time;     // device-resident sort bookkeeping (histograms, tile counters, current buffer)
     rsort::SortState* st_site;
     unsigned int* scan_status[2];  // max_tiles status words each: singles compaction, coincidence compaction
@@ -31,6 +31,8 @@ struct DigitizerWorkspace {
 };
 
 size_t sort_state_bytes();
+size_t sort_lookback_words(size_t capacity);   // status words one radix pass needs for `capacity` keys
+unsigned scan_tiles(size_t capacity);          // status words of the compaction scans
 
 // ---- digitizer (digitizer.cu) --------------------------------------------------------------------------
 int launch_events_aos_to_soa(const void* aos, EventSoA ev, unsigned int n, cudaStream_t s);
@@ -45,7 +47,7 @@ int launch_psf_positron(PhotonQueue q0, unsigned int n_positrons, PhantomDev ph,
                         uint64_t seed, int num_sms, cudaStream_t s);
 int launch_phantom(PhotonQueue q0, PhotonQueue q1, PhantomDev ph, TablesDev tb, float eabs, uint64_t seed,
                    int num_sms, cudaStream_t s);
-int launch_detector(PhotonQueue q1, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
+int launch_detector(PhotonQueue q1, PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
                     int record_hits, HitBuffer hits, EventSoA ev, unsigned int* counters, uint64_t seed,
                     int num_sms, cudaStream_t s);
 int launch_photons_aos_to_queue(const void* aos, PhotonQueue q, unsigned int n, cudaStream_t s);

@@ -3,31 +3,35 @@
 //
 // Replaces the reference's D2H -> std::sort -> H2D round trips (quicksort_h / orderevents, detector.cu:354-385).
 // Everything the sort needs to know at run time lives on the device: the element count, which of the two ping-pong
-// buffers currently holds the data (SortState::cur), the per-digit histograms.  The launch sequence is therefore
+// buffers currently holds the data (derived from the per-digit histograms).  The launch sequence is therefore
 // static and can sit inside a CUDA graph:
 //
 //   producer kernel    writes keys/vals into buffer 0, accumulates the histograms of ALL digits (hist_accumulate) and
 //                      clears look-back array 0 (clear_lookback)
 //   k_onesweep x P     pass p: skip if one digit value holds every key (high bytes of fp64 times inside a short frame,
 //                      high bytes of site numbers); else tiles are claimed in order from a device counter, ranked
-//                      inside the tile (warp match-any => stable), chained to their predecessors through a per-digit
+//                      inside the tile (warp ballots => stable), chained to their predecessors through a per-digit
 //                      status word (aggregate / inclusive-prefix flags) and scattered.  Every pass clears the look-back
-//                      array of the next pass; the last block to finish flips SortState::cur.
+//                      array of the next pass.  Which buffer holds the data after p passes follows from the
+//                      histograms alone (current_buffer), so consumers need no flag either.
 //
 // Ranking inside a tile: each warp walks its 32-wide rows in memory order, lanes with equal digits find each other
-// with __match_any_sync, the lowest lane bumps the warp's digit counter, so ranks are stable without per-thread
-// counters.
+// with one ballot per digit bit, the lowest lane bumps the warp's digit counter, so ranks are stable without
+// per-thread counters.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda_runtime.h>
+
+#include "ktimer.hpp"
 
 namespace gpet {
 namespace rsort {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kItems = 8;
-constexpr int kTile = kThreads * kItems;  // 2048 keys per tile
+constexpr int kItems = 4;
+constexpr int kTile = kThreads * kItems;  // 1024 keys per tile: small tiles keep every SM busy at frame sizes of ~1e5 keys
 constexpr int kBins = 256;
 constexpr int kMaxPasses = 8;
 
@@ -37,10 +41,8 @@ constexpr unsigned kValueMask = (1u << 30) - 1u;
 
 // Device-resident bookkeeping of one sort (zeroed by the chain's first kernel).
 struct SortState {
-    unsigned cur;                       // buffer (0/1) that holds the current data
     unsigned tile_counter[kMaxPasses];  // next tile to claim, per pass
-    unsigned done_counter[kMaxPasses];  // blocks that finished, per pass
-    unsigned pad[15];
+    unsigned pad[24];
     unsigned hist[kMaxPasses * kBins];  // global digit histograms, all passes
 };
 
@@ -49,6 +51,29 @@ __device__ __forceinline__ unsigned digit_of(KeyT k, int shift) { return (unsign
 
 __device__ __forceinline__ unsigned ld_volatile(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
 __device__ __forceinline__ void st_volatile(unsigned* p, unsigned v) { *reinterpret_cast<volatile unsigned*>(p) = v; }
+
+// Decoupled look-back: sum of the published values of tiles [0, tile).  Predecessors are read in windows of 16
+// INDEPENDENT loads (one L2 round trip per window instead of one per tile), walking back until a tile that already
+// holds its inclusive prefix; a word that is not published yet is simply read again.
+constexpr int kLookbackWindow = 32;
+__device__ __forceinline__ unsigned lookback_sum(const unsigned* status, unsigned stride, unsigned tile) {
+    unsigned excl = 0;
+    int t = (int)tile - 1;
+    while (t >= 0) {
+        unsigned v[kLookbackWindow];
+#pragma unroll
+        for (int k = 0; k < kLookbackWindow; k++) v[k] = (t - k >= 0) ? ld_volatile(status + (size_t)(t - k) * stride) : kFlagPrefix;
+        int k = 0;
+#pragma unroll
+        for (; k < kLookbackWindow; k++) {
+            if ((v[k] >> 30) == 0u) break;  // not published yet: resume from this tile
+            excl += v[k] & kValueMask;
+            if (v[k] & kFlagPrefix) return excl;
+        }
+        t -= k;
+    }
+    return excl;
+}
 
 // ---- helpers for the producer kernel --------------------------------------------------------------------
 // Block-level accumulation of the digit histograms of all passes: `sh` is [npass * 256] shared counters (zeroed by
@@ -73,6 +98,24 @@ __device__ __forceinline__ void clear_lookback(unsigned* lookback, unsigned n) {
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < words; i += gridDim.x * blockDim.x) lookback[i] = 0u;
 }
 
+// Which ping-pong buffer holds the data before pass `npasses_before` (= after that many passes): a pass whose keys all
+// share one digit value is skipped, every other pass flips the buffer.  Computed by every block from the global
+// histograms (no device-side flag, no completion counter).  Must be called by all kThreads threads of the block.
+__device__ __forceinline__ unsigned current_buffer(const SortState* st, int npasses_before, unsigned n) {
+    __shared__ unsigned s_mask[kWarps];
+    unsigned trivial_mask = 0;
+    for (int q = 0; q < npasses_before; q++)
+        if (st->hist[q * kBins + threadIdx.x] == n) trivial_mask |= 1u << q;
+    trivial_mask = __reduce_or_sync(0xffffffffu, trivial_mask);
+    if ((threadIdx.x & 31) == 0) s_mask[threadIdx.x >> 5] = trivial_mask;
+    __syncthreads();
+    unsigned m = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) m |= s_mask[w];
+    __syncthreads();
+    return (unsigned)(npasses_before - __popc(m)) & 1u;
+}
+
 // ---- one pass -----------------------------------------------------------------------------------------------
 template <typename KeyT>
 __global__ void __launch_bounds__(kThreads) k_onesweep(KeyT* keys0, KeyT* keys1, unsigned* vals0, unsigned* vals1,
@@ -82,9 +125,11 @@ __global__ void __launch_bounds__(kThreads) k_onesweep(KeyT* keys0, KeyT* keys1,
     __shared__ unsigned gbase[kBins];
     __shared__ unsigned wsum[kWarps];
     __shared__ unsigned s_tile;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the tile ticket is requested first: its round trip overlaps the loads below (a skipped pass wastes it, harmlessly)
+    if (tid == 0) s_tile = atomicAdd(&st->tile_counter[pass], 1u);
     const unsigned n = *n_ptr;
     const unsigned ntiles = (n + kTile - 1) / kTile;
-    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int shift = 8 * pass;
     unsigned* lb = (pass & 1) ? lookback1 : lookback0;
@@ -93,6 +138,7 @@ __global__ void __launch_bounds__(kThreads) k_onesweep(KeyT* keys0, KeyT* keys1,
     // exclusive scan over the digits of this pass's global histogram; a pass whose keys all share one digit is the
     // identity permutation and is skipped
     const unsigned cnt_d = st->hist[pass * kBins + tid];
+    const unsigned cur = current_buffer(st, pass, n);
     const int trivial = __syncthreads_or(cnt_d == n);
     if (!trivial) {
         unsigned x = cnt_d;
@@ -106,15 +152,14 @@ __global__ void __launch_bounds__(kThreads) k_onesweep(KeyT* keys0, KeyT* keys1,
         unsigned wp = 0;
         for (unsigned w = 0; w < warp; w++) wp += wsum[w];
         const unsigned digit_base = wp + x - cnt_d;
-        const unsigned cur = st->cur;
         const KeyT* __restrict__ keys_in = cur ? keys1 : keys0;
         const unsigned* __restrict__ vals_in = cur ? vals1 : vals0;
         KeyT* __restrict__ keys_out = cur ? keys0 : keys1;
         unsigned* __restrict__ vals_out = cur ? vals0 : vals1;
+        // with no more tiles than blocks every tile is claimed by some block's first ticket: no second round
+        const bool single_round = ntiles <= gridDim.x;
 
         while (true) {
-            __syncthreads();
-            if (tid == 0) s_tile = atomicAdd(&st->tile_counter[pass], 1u);
 #pragma unroll
             for (int w = 0; w < kWarps; w++) whist[w][tid] = 0;
             __syncthreads();
@@ -133,7 +178,15 @@ __global__ void __launch_bounds__(kThreads) k_onesweep(KeyT* keys0, KeyT* keys1,
             }
 #pragma unroll
             for (int k = 0; k < kItems; k++) {
-                unsigned peers = __match_any_sync(0xffffffffu, dig[k]);
+                // lanes holding the same digit: eight ballots, one per digit bit (constant cost; __match_any_sync walks
+                // the distinct values one by one and is ~8x slower on random digits)
+                unsigned peers = 0xffffffffu;
+#pragma unroll
+                for (int b = 0; b < 8; b++) {
+                    const bool bit = (dig[k] >> b) & 1u;
+                    const unsigned m = __ballot_sync(0xffffffffu, bit);
+                    peers &= bit ? m : ~m;
+                }
                 unsigned leader = __ffs(peers) - 1;
                 unsigned old = 0;
                 if (lane == leader) {
@@ -163,14 +216,7 @@ __global__ void __launch_bounds__(kThreads) k_onesweep(KeyT* keys0, KeyT* keys1,
                 st_volatile(&lb[tid], kFlagPrefix | run);
             } else {
                 st_volatile(&lb[tile * kBins + tid], kFlagAggregate | run);
-                unsigned t = tile - 1;
-                while (true) {
-                    unsigned v = ld_volatile(&lb[t * kBins + tid]);
-                    if ((v >> 30) == 0u) continue;  // predecessor not published yet
-                    excl += v & kValueMask;
-                    if (v & kFlagPrefix) break;
-                    t--;
-                }
+                excl = lookback_sum(lb + tid, kBins, tile);
                 st_volatile(&lb[tile * kBins + tid], kFlagPrefix | (excl + run));
             }
             gbase[tid] = digit_base + excl;
@@ -184,15 +230,13 @@ __global__ void __launch_bounds__(kThreads) k_onesweep(KeyT* keys0, KeyT* keys1,
                     vals_out[pos] = val[k];
                 }
             }
+            if (single_round) break;
+            __syncthreads();
+            if (tid == 0) s_tile = atomicAdd(&st->tile_counter[pass], 1u);
         }
     }
     // clear the look-back array of the next pass (last used two passes ago)
     for (unsigned i = blockIdx.x * kThreads + tid; i < ntiles * kBins; i += gridDim.x * kThreads) lb_next[i] = 0u;
-    __syncthreads();
-    if (tid == 0 && !trivial) {
-        __threadfence();
-        if (atomicAdd(&st->done_counter[pass], 1u) == gridDim.x - 1) st->cur ^= 1u;
-    }
 }
 
 }  // namespace rsort
@@ -203,8 +247,9 @@ template <typename KeyT>
 inline int radix_sort_passes(KeyT* keys[2], unsigned* vals[2], const unsigned* n_dev, rsort::SortState* st,
                              unsigned* lookback[2], int npasses, int grid, cudaStream_t s) {
     for (int p = 0; p < npasses; p++)
-        rsort::k_onesweep<KeyT><<<grid, rsort::kThreads, 0, s>>>(keys[0], keys[1], vals[0], vals[1], n_dev, st, lookback[0],
-                                                                 lookback[1], p);
+        GPET_LAUNCH(sizeof(KeyT) == 8 ? "k_onesweep<u64>" : "k_onesweep<u32>", s,
+                    rsort::k_onesweep<KeyT><<<grid, rsort::kThreads, 0, s>>>(keys[0], keys[1], vals[0], vals[1], n_dev, st,
+                                                                             lookback[0], lookback[1], p));
     return npasses;
 }
 

@@ -10,6 +10,7 @@
 //   * the per-photon adder/readout runs in registers (no local-memory Event[4]); hits leave the SM as contiguous
 //     rows already in the HitsID.dat / Hits.dat layout.
 #include "kernels.hpp"
+#include "ktimer.hpp"
 #include "philox.cuh"
 
 #include "../../include/gpet_b200.h"
@@ -271,8 +272,7 @@ __global__ void __launch_bounds__(kThreads) k_phantom(PhotonQueue q0, PhotonQueu
 }
 
 // ------------------------------------------------------------------------------------------- X1/X2/D1/D2: detector
-constexpr int kSlots = 6;  // distinct crystals per photon kept by the in-register adder (reference: Event events[4])
-
+constexpr int kSlots = 6;  // distinct crystals per photon kept by the adder (reference: Event events[4], no bound check)
 
 __device__ __forceinline__ void crystal_search(const PanelDev& pd, const DetectorDev& det, float px, float py, float pz,
                                                int& m_id, int& M_id, int& L_id) {
@@ -315,71 +315,30 @@ __device__ __forceinline__ void compton_kn(float E, Philox& rng, float& efrac, f
     costh = 1.0f - (1.0f - efrac) / (efrac * e0);
 }
 
-struct Slots {
-    int site[kSlots];
-    float E[kSlots], x[kSlots], y[kSlots], z[kSlots];
-    double t[kSlots];
-    int n;
-};
-
-// D1 adder (gPET_kernals.cu:737-755): merge hits of the same crystal; energy-weighted centroid with the
-// contraction spelled out (SURVEY quirk 15): (x_i*E_i + x*E)/(E_i+E) = fma(x_i, E_i, x*E) / (E_i + E)
-__device__ __forceinline__ bool adder(Slots& sl, int site, float E, float x, float y, float z, double t) {
-    bool merged = false;
-#pragma unroll
-    for (int k = 0; k < kSlots; k++) {
-        if (!merged && k < sl.n && sl.site[k] == site) {
-            float es = __fadd_rn(sl.E[k], E);
-            sl.x[k] = __fdiv_rn(__fmaf_rn(sl.x[k], sl.E[k], __fmul_rn(x, E)), es);
-            sl.y[k] = __fdiv_rn(__fmaf_rn(sl.y[k], sl.E[k], __fmul_rn(y, E)), es);
-            sl.z[k] = __fdiv_rn(__fmaf_rn(sl.z[k], sl.E[k], __fmul_rn(z, E)), es);
-            sl.E[k] = es;
-            merged = true;
-        }
-    }
-    if (merged) return true;
-    if (sl.n >= kSlots) return false;
-#pragma unroll
-    for (int k = 0; k < kSlots; k++) {
-        if (k == sl.n) { sl.site[k] = site; sl.E[k] = E; sl.x[k] = x; sl.y[k] = y; sl.z[k] = z; sl.t[k] = t; }
-    }
-    sl.n++;
-    return true;
-}
-
-__global__ void __launch_bounds__(kThreads) k_detector(PhotonQueue q1, DetectorDev det, TablesDev tb, float eabs,
-                                                       int rdepth, int rpolicy, int record_hits, HitBuffer hits, EventSoA ev,
-                                                       unsigned* __restrict__ counters, uint64_t seed) {
+// Panel entry (gPET_kernals.cu:963-1009): one thread per photon that left the phantom, convergent loop over the
+// panels; photons whose straight line crosses a panel's front face are appended -- already in that panel's local
+// frame, with the time of flight to the face added -- to the compact queue the transport kernel works on.
+// dir_n.w of the output carries the panel index.
+__global__ void __launch_bounds__(kThreads) k_panel_entry(PhotonQueue q1, DetectorDev det, PhotonQueue q2,
+                                                          unsigned* __restrict__ counters) {
     extern __shared__ PanelDev s_panels[];
     for (int i = threadIdx.x; i < det.npanels * (int)(sizeof(PanelDev) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(s_panels)[i] = reinterpret_cast<const uint32_t*>(det.panels)[i];
     __syncthreads();
-
     const unsigned n = min(*q1.count, q1.capacity);
-    const unsigned stride = gridDim.x * blockDim.x;
-    unsigned next = blockIdx.x * blockDim.x + threadIdx.x;
-    const int crysPerPanel = det.moduleN * det.crystalN;
-    bool active = false;
-    float x = 0, y = 0, z = 0, E = 0, vx = 0, vy = 0, vz = 0;
-    double t = 0;
-    int eid = 0, parn = 0, pa = -1;
-    unsigned n_on_panel = 0, n_drop_adder = 0;
-    Slots sl;
-    sl.n = 0;
-    Philox rng(seed, 0, 0);
-    while (true) {
-        // ---- refill + panel entry search (gPET_kernals.cu:963-1009)
-        bool want = !active && next < n;
-        unsigned wmask = __ballot_sync(kFull, want);
-        unsigned amask = __ballot_sync(kFull, active);
-        if (wmask && (__popc(wmask) >= 8 || amask == 0)) {
-            while (!active && next < n) {
-                float4 pe = q1.pos_e[next];
-                float4 dn = q1.dir_n[next];
-                double tt = q1.t[next];
-                int2 id = q1.ids[next];
-                next += stride;
-                if (!(tt > 0.0)) continue;
+    const unsigned nround = (n + 31u) & ~31u;  // whole warps stay in the loop for the collective append
+    unsigned n_on_panel = 0;
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
+        bool ok = false;
+        float4 pe = make_float4(0, 0, 0, 0), ov = make_float4(0, 0, 0, 0);
+        double t = 0.0;
+        int2 id = make_int2(0, 0);
+        if (p < n) {
+            pe = q1.pos_e[p];
+            float4 dn = q1.dir_n[p];
+            const double tt = q1.t[p];
+            id = q1.ids[p];
+            if (tt > 0.0) {
                 for (int i = 0; i < det.npanels; i++) {
                     const PanelDev& pd = s_panels[i];
                     float rx = pe.x - pd.ox, ry = pe.y - pd.oy, rz = pe.z - pd.oz;
@@ -393,27 +352,105 @@ __global__ void __launch_bounds__(kThreads) k_detector(PhotonQueue q1, DetectorD
                         float q = __fdiv_rn(lx, lvx);
                         float y2 = ly - q * lvy, z2 = lz - q * lvz;
                         if (fabsf(y2) < pd.ly / 2 && fabsf(z2) < pd.lz / 2) {
-                            x = 0.f; y = y2; z = z2;
-                            vx = lvx; vy = lvy; vz = lvz;
-                            E = pe.w;
+                            pe = make_float4(0.f, y2, z2, pe.w);
+                            ov = make_float4(lvx, lvy, lvz, __int_as_float(i));
                             t = tt + (-(double)lx / (kSpeedOfLight * (double)lvx));
-                            pa = i;
-                            eid = id.x; parn = id.y;
-                            rng = Philox(seed, (uint64_t)(uint32_t)parn, (uint32_t)kStageDetector << 24);
-                            sl.n = 0;
-                            active = true;
-                            n_on_panel++;
+                            ok = true;
                             break;
                         }
                     }
                 }
             }
+        }
+        unsigned slot = warp_reserve(q2.count, ok ? 1u : 0u);
+        if (ok) {
+            n_on_panel++;
+            if (slot < q2.capacity) {
+                q2.pos_e[slot] = pe;
+                q2.dir_n[slot] = ov;
+                q2.t[slot] = t;
+                q2.ids[slot] = id;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_on_panel += __shfl_xor_sync(kFull, n_on_panel, o);
+    if (lane_id() == 0 && n_on_panel) atomicAdd(&counters[8], n_on_panel);
+}
+
+// Per-thread adder slots in shared memory, [slot][thread] so that a warp's accesses are conflict free.
+struct SlotsSmem {
+    int site[kSlots][kThreads];
+    float E[kSlots][kThreads], x[kSlots][kThreads], y[kSlots][kThreads], z[kSlots][kThreads];
+    double t[kSlots][kThreads];
+};
+
+// D1 adder (gPET_kernals.cu:737-755): merge hits of the same crystal; energy-weighted centroid with the
+// contraction spelled out (SURVEY quirk 15): (x_i*E_i + x*E)/(E_i+E) = fma(x_i, E_i, x*E) / (E_i + E)
+__device__ __forceinline__ bool adder(SlotsSmem& sl, int& n, int site, float E, float x, float y, float z, double t) {
+    const int tid = threadIdx.x;
+    for (int k = 0; k < n; k++) {
+        if (sl.site[k][tid] == site) {
+            const float ek = sl.E[k][tid];
+            const float es = __fadd_rn(ek, E);
+            sl.x[k][tid] = __fdiv_rn(__fmaf_rn(sl.x[k][tid], ek, __fmul_rn(x, E)), es);
+            sl.y[k][tid] = __fdiv_rn(__fmaf_rn(sl.y[k][tid], ek, __fmul_rn(y, E)), es);
+            sl.z[k][tid] = __fdiv_rn(__fmaf_rn(sl.z[k][tid], ek, __fmul_rn(z, E)), es);
+            sl.E[k][tid] = es;
+            return true;
+        }
+    }
+    if (n >= kSlots) return false;
+    sl.site[n][tid] = site; sl.E[n][tid] = E; sl.x[n][tid] = x; sl.y[n][tid] = y; sl.z[n][tid] = z; sl.t[n][tid] = t;
+    n++;
+    return true;
+}
+
+// Photon transport inside a panel (gPET_kernals.cu:1018-1192) over the compact panel-entry queue, persistent warps with
+// lane refill; adder on the fly, readout (gPET_kernals.cu:756-813) when the photon is finished.
+__global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs,
+                                                          int rdepth, int rpolicy, int record_hits, HitBuffer hits, EventSoA ev,
+                                                          unsigned* __restrict__ counters, uint64_t seed) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    SlotsSmem& sl = *reinterpret_cast<SlotsSmem*>(s_raw);
+    PanelDev* s_panels = reinterpret_cast<PanelDev*>(s_raw + sizeof(SlotsSmem));
+    for (int i = threadIdx.x; i < det.npanels * (int)(sizeof(PanelDev) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t*>(s_panels)[i] = reinterpret_cast<const uint32_t*>(det.panels)[i];
+    __syncthreads();
+
+    const int tid = threadIdx.x;
+    const unsigned n = min(*q2.count, q2.capacity);
+    const unsigned stride = gridDim.x * blockDim.x;
+    unsigned next = blockIdx.x * blockDim.x + threadIdx.x;
+    const int crysPerPanel = det.moduleN * det.crystalN;
+    const int depth = (rdepth != 3 && rpolicy == 1) ? 2 : rdepth;
+    bool active = false;
+    float x = 0, y = 0, z = 0, E = 0, vx = 0, vy = 0, vz = 0;
+    double t = 0;
+    int eid = 0, parn = 0, pa = 0, nslot = 0;
+    unsigned n_drop_adder = 0;
+    Philox rng(seed, 0, 0);
+    while (true) {
+        // ---- refill from the compact queue: cheap, so idle lanes are topped up as soon as a quarter of the warp idles
+        unsigned amask = __ballot_sync(kFull, active);
+        unsigned wmask = __ballot_sync(kFull, !active && next < n);
+        if (wmask && (__popc(wmask) >= 8 || amask == 0)) {
+            if (!active && next < n) {
+                float4 pe = q2.pos_e[next];
+                float4 dn = q2.dir_n[next];
+                t = q2.t[next];
+                int2 id = q2.ids[next];
+                next += stride;
+                x = pe.x; y = pe.y; z = pe.z; E = pe.w;
+                vx = dn.x; vy = dn.y; vz = dn.z; pa = __float_as_int(dn.w);
+                eid = id.x; parn = id.y;
+                rng = Philox(seed, (uint64_t)(uint32_t)parn, (uint32_t)kStageDetector << 24);
+                nslot = 0;
+                active = true;
+            }
             amask = __ballot_sync(kFull, active);
         }
-        if (amask == 0) {
-            if (__ballot_sync(kFull, next < n) == 0) break;
-            continue;
-        }
+        if (amask == 0) break;  // nothing active and nothing left to pull for any lane of this warp
         // up to two hits per flight (Compton deposit + absorption of the remainder), both at the same point
         int nh = 0, h_mod = -1, h_cry = -1, h_type0 = 0;
         float h_E0 = 0.f, h_E1 = 0.f;
@@ -469,8 +506,8 @@ __global__ void __launch_bounds__(kThreads) k_detector(PhotonQueue q1, DetectorD
             // adder on the fly
             if (nh >= 1) {
                 int site = pa * crysPerPanel + h_mod * det.crystalN + h_cry;
-                if (!adder(sl, site, h_E0, x, y, z, t)) n_drop_adder++;
-                if (nh == 2 && !adder(sl, site, h_E1, x, y, z, t)) n_drop_adder++;
+                if (!adder(sl, nslot, site, h_E0, x, y, z, t)) n_drop_adder++;
+                if (nh == 2 && !adder(sl, nslot, site, h_E1, x, y, z, t)) n_drop_adder++;
             }
         }
         // ---- hits: rows in file layout, warp-aggregated
@@ -490,79 +527,71 @@ __global__ void __launch_bounds__(kThreads) k_detector(PhotonQueue q1, DetectorD
             }
         }
         // ---- photon finished: readout (gPET_kernals.cu:756-813) and event append
-        unsigned fmask = __ballot_sync(kFull, finished && sl.n > 0);
+        const bool mine = finished && nslot > 0;
+        unsigned fmask = __ballot_sync(kFull, mine);
         if (finished) active = false;
         if (fmask) {
-            // number of events each finishing lane will write
             int cnt = 0;
-            bool mine = finished && sl.n > 0;
-            // merge keys at readout level
-            int key[kSlots];
-            bool dead[kSlots];
-            int depth = (rdepth != 3 && rpolicy == 1) ? 2 : rdepth;
             const int panel_id = mine ? s_panels[pa].id : 0;
-#pragma unroll
-            for (int k = 0; k < kSlots; k++) {
-                dead[k] = !(mine && k < sl.n);
-                int cs = sl.site[k] - pa * crysPerPanel;
-                int mod = cs / det.crystalN;
-                key[k] = depth == 0 ? 0 : depth == 1 ? panel_id : depth == 2 ? panel_id * det.moduleN + mod
-                                                                            : panel_id * crysPerPanel + cs;
-            }
-            if (mine && rdepth != 3) {
-#pragma unroll
-                for (int i = 0; i < kSlots; i++) {
-#pragma unroll
-                    for (int j = i + 1; j < kSlots; j++) {
-                        if (!dead[i] && !dead[j] && key[j] == key[i]) {
+            unsigned deadmask = 0;  // bit k: slot k merged away
+            if (mine) {
+                // rewrite the slot keys at readout level in place (site -> key), keeping the crystal site in a register copy
+                if (rdepth != 3) {
+                    for (int i = 0; i < nslot; i++) {
+                        if (deadmask >> i & 1u) continue;
+                        const int csi = sl.site[i][tid] - pa * crysPerPanel;
+                        const int keyi = depth == 0 ? 0 : depth == 1 ? panel_id : depth == 2 ? panel_id * det.moduleN + csi / det.crystalN
+                                                                                              : panel_id * crysPerPanel + csi;
+                        for (int j = i + 1; j < nslot; j++) {
+                            if (deadmask >> j & 1u) continue;
+                            const int csj = sl.site[j][tid] - pa * crysPerPanel;
+                            const int keyj = depth == 0 ? 0 : depth == 1 ? panel_id : depth == 2 ? panel_id * det.moduleN + csj / det.crystalN
+                                                                                                  : panel_id * crysPerPanel + csj;
+                            if (keyj != keyi) continue;
+                            const float Ei = sl.E[i][tid], Ej = sl.E[j][tid];
                             if (rpolicy == 1) {
-                                float es = __fadd_rn(sl.E[i], sl.E[j]);
-                                sl.x[i] = __fdiv_rn(__fmaf_rn(sl.x[i], sl.E[i], __fmul_rn(sl.x[j], sl.E[j])), es);
-                                sl.y[i] = __fdiv_rn(__fmaf_rn(sl.y[i], sl.E[i], __fmul_rn(sl.y[j], sl.E[j])), es);
-                                sl.z[i] = __fdiv_rn(__fmaf_rn(sl.z[i], sl.E[i], __fmul_rn(sl.z[j], sl.E[j])), es);
-                                sl.E[i] = es;
-                            } else if (!(sl.E[i] > sl.E[j])) {
+                                const float es = __fadd_rn(Ei, Ej);
+                                sl.x[i][tid] = __fdiv_rn(__fmaf_rn(sl.x[i][tid], Ei, __fmul_rn(sl.x[j][tid], Ej)), es);
+                                sl.y[i][tid] = __fdiv_rn(__fmaf_rn(sl.y[i][tid], Ei, __fmul_rn(sl.y[j][tid], Ej)), es);
+                                sl.z[i][tid] = __fdiv_rn(__fmaf_rn(sl.z[i][tid], Ei, __fmul_rn(sl.z[j][tid], Ej)), es);
+                                sl.E[i][tid] = es;
+                            } else if (!(Ei > Ej)) {
                                 // winner-take-all: the larger energy wins the whole record (ties -> the later one)
-                                sl.site[i] = sl.site[j]; sl.E[i] = sl.E[j]; sl.x[i] = sl.x[j]; sl.y[i] = sl.y[j];
-                                sl.z[i] = sl.z[j]; sl.t[i] = sl.t[j];
+                                sl.site[i][tid] = sl.site[j][tid]; sl.E[i][tid] = Ej; sl.x[i][tid] = sl.x[j][tid];
+                                sl.y[i][tid] = sl.y[j][tid]; sl.z[i][tid] = sl.z[j][tid]; sl.t[i][tid] = sl.t[j][tid];
                             }
-                            dead[j] = true;
+                            deadmask |= 1u << j;
                         }
                     }
                 }
+                cnt = nslot - __popc(deadmask);
             }
-#pragma unroll
-            for (int k = 0; k < kSlots; k++) cnt += dead[k] ? 0 : 1;
             unsigned slot = warp_reserve(ev.count, (unsigned)cnt);
             if (mine) {
-#pragma unroll
-                for (int k = 0; k < kSlots; k++) {
-                    if (!dead[k]) {
-                        if (slot < ev.capacity) {
-                            int cs = sl.site[k] - pa * crysPerPanel;
-                            int mod = cs / det.crystalN;
-                            ev.parn[slot] = parn; ev.pann[slot] = panel_id; ev.modn[slot] = mod;
-                            ev.cryn[slot] = cs - mod * det.crystalN;
-                            ev.siten[slot] = key[k];
-                            ev.eventid[slot] = eid;
-                            ev.t[slot] = sl.t[k]; ev.E[slot] = sl.E[k];
-                            ev.x[slot] = sl.x[k]; ev.y[slot] = sl.y[k]; ev.z[slot] = sl.z[k];
-                        }
-                        slot++;
+                for (int k = 0; k < nslot; k++) {
+                    if (deadmask >> k & 1u) continue;
+                    if (slot < ev.capacity) {
+                        const int cs = sl.site[k][tid] - pa * crysPerPanel;
+                        const int mod = cs / det.crystalN;
+                        ev.parn[slot] = parn; ev.pann[slot] = panel_id; ev.modn[slot] = mod;
+                        ev.cryn[slot] = cs - mod * det.crystalN;
+                        ev.siten[slot] = depth == 0 ? 0 : depth == 1 ? panel_id : depth == 2 ? panel_id * det.moduleN + mod
+                                                                                            : panel_id * crysPerPanel + cs;
+                        ev.eventid[slot] = eid;
+                        ev.t[slot] = sl.t[k][tid]; ev.E[slot] = sl.E[k][tid];
+                        ev.x[slot] = sl.x[k][tid]; ev.y[slot] = sl.y[k][tid]; ev.z[slot] = sl.z[k][tid];
                     }
+                    slot++;
                 }
-                sl.n = 0;
+                nslot = 0;
             }
         }
     }
     // per-warp tallies
-    unsigned a = n_on_panel, b = n_drop_adder;
+    unsigned b = n_drop_adder;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(kFull, a, o); b += __shfl_xor_sync(kFull, b, o); }
-    if (lane_id() == 0) {
-        if (a) atomicAdd(&counters[8], a);
-        if (b) atomicAdd(&counters[9], b);
-    }
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(kFull, b, o);
+    if (lane_id() == 0 && b) atomicAdd(&counters[9], b);
 }
 
 // ------------------------------------------------------------------------------------------- host AoS <-> queue
@@ -610,7 +639,7 @@ int launch_source(const SourceDev* frame_dev, unsigned long long npairs, Phantom
     unsigned long long maxb = (unsigned long long)num_sms * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
-    k_source<<<(unsigned)blocks, kThreads, 0, s>>>(frame_dev, npairs, q0, seed);
+    GPET_LAUNCH("k_source", s, k_source<<<(unsigned)blocks, kThreads, 0, s>>>(frame_dev, npairs, q0, seed));
     return 1;
 }
 
@@ -621,38 +650,44 @@ int launch_phantom(PhotonQueue q0, PhotonQueue q1, PhantomDev ph, TablesDev tb, 
     static int grid = 0;
     if (!grid) grid = persistent_grid(k_phantom, num_sms, 0);
     cudaMemsetAsync(q1.count, 0, sizeof(unsigned), s);
-    k_phantom<<<grid, kThreads, 0, s>>>(q0, q1, ph, tb, eabs, seed);
+    GPET_LAUNCH("k_phantom", s, k_phantom<<<grid, kThreads, 0, s>>>(q0, q1, ph, tb, eabs, seed));
     return 1;
 }
 
-int launch_detector(PhotonQueue q1, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
-                    int record_hits, HitBuffer hits, EventSoA ev, unsigned int* counters, uint64_t seed, int num_sms,
-                    cudaStream_t s) {
-    size_t smem = (size_t)det.npanels * sizeof(PanelDev);
-    static int grid = 0;
+int launch_detector(PhotonQueue q1, PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth,
+                    int readout_policy, int record_hits, HitBuffer hits, EventSoA ev, unsigned int* counters, uint64_t seed,
+                    int num_sms, cudaStream_t s) {
+    const size_t smem_panels = (size_t)det.npanels * sizeof(PanelDev);
+    const size_t smem = sizeof(SlotsSmem) + smem_panels;
+    static int grid = 0, grid_entry = 0;
     static size_t grid_smem = 0;
     if (!grid || grid_smem != smem) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_detector, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_detector, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem_panels > 48 * 1024)
+            cudaFuncSetAttribute(k_panel_entry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panels);
         grid = persistent_grid(k_detector, num_sms, smem);
+        grid_entry = persistent_grid(k_panel_entry, num_sms, smem_panels);
         grid_smem = smem;
     }
-    cudaMemsetAsync(hits.count, 0, sizeof(unsigned), s);
-    cudaMemsetAsync(ev.count, 0, sizeof(unsigned), s);
+    // q2.count, hits.count, ev.count and the two tallies are adjacent words of the counter block? no: reset one by one
+    cudaMemsetAsync(q2.count, 0, sizeof(unsigned), s);
+    cudaMemsetAsync(hits.count, 0, 2 * sizeof(unsigned), s);   // hits.count, ev.count (adjacent words of the counter block)
     cudaMemsetAsync(counters + 8, 0, 2 * sizeof(unsigned), s);
-    k_detector<<<grid, kThreads, smem, s>>>(q1, det, tb, eabs, readout_depth, readout_policy, record_hits, hits, ev,
-                                           counters, seed);
-    return 1;
+    GPET_LAUNCH("k_panel_entry", s, k_panel_entry<<<grid_entry, kThreads, smem_panels, s>>>(q1, det, q2, counters));
+    GPET_LAUNCH("k_detector", s, k_detector<<<grid, kThreads, smem, s>>>(q2, det, tb, eabs, readout_depth, readout_policy, record_hits, hits, ev, counters,
+                                           seed));
+    return 2;
 }
 
 int launch_photons_aos_to_queue(const void* aos, PhotonQueue q, unsigned int n, cudaStream_t s) {
     unsigned blocks = n ? (n + kThreads - 1) / kThreads : 1;
     if (blocks > 4096) blocks = 4096;
-    k_aos_to_queue<<<blocks, kThreads, 0, s>>>(static_cast<const gpet_photon*>(aos), q, n);
+    GPET_LAUNCH("k_aos_to_queue", s, k_aos_to_queue<<<blocks, kThreads, 0, s>>>(static_cast<const gpet_photon*>(aos), q, n));
     return 1;
 }
 
 int launch_queue_to_photons_aos(PhotonQueue q, void* aos, cudaStream_t s) {
-    k_queue_to_aos<<<1024, kThreads, 0, s>>>(q, static_cast<gpet_photon*>(aos));
+    GPET_LAUNCH("k_queue_to_aos", s, k_queue_to_aos<<<1024, kThreads, 0, s>>>(q, static_cast<gpet_photon*>(aos)));
     return 1;
 }
 

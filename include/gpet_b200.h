@@ -259,6 +259,12 @@ int gpet_get_stats(const gpet_ctx* ctx, gpet_stats* stats);
  * this is what multi-GPU runs all-reduce. */
 int gpet_get_spectrum(gpet_ctx* ctx, uint64_t* bins, int nbins);
 int gpet_set_spectrum(gpet_ctx* ctx, int nbins, float emin, float emax);
+/* Per-kernel device times (CUDA events bracketing every launch of this library's kernels on the launching stream).
+ * Replaces the reference's clock() prints (main.cu:39-41, gPET.cu:245-247, 432-435).  Off by default; enabling clears
+ * the accumulated numbers.  gpet_profile_count synchronises the stream and returns the number of distinct kernels. */
+int gpet_profile_enable(gpet_ctx* ctx, int on);
+int gpet_profile_count(gpet_ctx* ctx);
+int gpet_profile_get(gpet_ctx* ctx, int i, char* name, int name_cap, double* total_ms, uint64_t* launches);
 /* Shard the planned frames: this context only runs frames f with f % world == rank. */
 int gpet_set_shard(gpet_ctx* ctx, int rank, int world);
 
