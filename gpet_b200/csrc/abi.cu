@@ -120,13 +120,22 @@ int ensure_buffers(gpet_ctx* c) {
     }
     {
         void* p = nullptr;
-        CK(cudaMalloc(&p, ce * sizeof(gpet_event)));
-        c->allocs.push_back(p);
-        c->singles_aos = p;
         c->coinc_cap = (unsigned)(ce / 2);
-        CK(cudaMalloc(&p, (size_t)c->coinc_cap * sizeof(gpet_coincidence)));
-        c->allocs.push_back(p);
-        c->coinc_aos = p;
+        for (int k = 0; k < 2; k++) {
+            CK(cudaMalloc(&p, ce * sizeof(gpet_event)));
+            c->allocs.push_back(p);
+            c->singles_slot[k] = p;
+            CK(cudaMalloc(&p, (size_t)c->coinc_cap * sizeof(gpet_coincidence)));
+            c->allocs.push_back(p);
+            c->coinc_slot[k] = p;
+            CK(cudaMallocHost((void**)&c->h_slot_counters[k], 32 * sizeof(unsigned)));
+            CK(cudaEventCreateWithFlags(&c->ev_counters[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
+        }
+        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        c->out_slot = 0;
+        c->singles_aos = c->singles_slot[0];
+        c->coinc_aos = c->coinc_slot[0];
         c->stage_bytes = std::max(std::max(ce * sizeof(gpet_event), cp * sizeof(gpet_photon)), ch * sizeof(gpet_hit));
         CK(cudaMalloc(&p, c->stage_bytes));
         c->allocs.push_back(p);
@@ -364,6 +373,14 @@ void gpet_destroy(gpet_ctx* c) {
         for (void* p : c->allocs) cudaFree(p);
         if (c->h_counters) cudaFreeHost(c->h_counters);
         if (c->h_totals) cudaFreeHost(c->h_totals);
+        for (int k = 0; k < 2; k++) {
+            if (c->h_slot_counters[k]) cudaFreeHost(c->h_slot_counters[k]);
+            if (c->ev_counters[k]) cudaEventDestroy(c->ev_counters[k]);
+            if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
+        }
+        if (c->res_singles.p) cudaFreeHost(c->res_singles.p);
+        if (c->res_coinc.p) cudaFreeHost(c->res_coinc.p);
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         if (c->own_stream) cudaStreamDestroy(c->own_stream);
     }
     delete c;
@@ -901,6 +918,89 @@ int append_device(gpet_ctx* c, const std::string& path, const void* dptr, size_t
     return GPET_OK;
 }
 
+// grow a pinned arena so that `extra` more bytes fit (contents kept); in-flight copies into it must have completed
+int arena_reserve(gpet_ctx* c, PinnedArena& a, size_t extra) {
+    if (a.size + extra <= a.cap) return GPET_OK;
+    CK(cudaStreamSynchronize(c->copy_stream));
+    size_t ncap = std::max<size_t>(std::max<size_t>(a.cap * 2, a.size + extra), 1u << 20);
+    char* np = nullptr;
+    CK(cudaMallocHost((void**)&np, ncap));
+    if (a.size) memcpy(np, a.p, a.size);
+    if (a.p) cudaFreeHost(a.p);
+    a.p = np;
+    a.cap = ncap;
+    return GPET_OK;
+}
+
+struct RunState {
+    gpet_stats st{};
+    bool resident = false;
+    std::string od;
+    std::vector<char> tmp;
+};
+
+// Take frame results out of slot `slot`: wait for its counters, account, start the D2H copies of the records.
+int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
+    int r;
+    CK(cudaEventSynchronize(c->ev_counters[slot]));
+    const unsigned* h = c->h_slot_counters[slot];
+    gpet_stats& st = rs.st;
+    const uint64_t n_ev = h[19], n_hits = h[18], n_q1 = h[17];
+    st.frames++;
+    st.photons_phantom_out += n_q1;
+    st.photons_on_panel += h[8];
+    st.hits += n_hits;
+    st.events_adder += h[0];
+    st.events_threshold += h[1];
+    st.events_deadtime += h[2];
+    st.singles += h[3];
+    st.coincidences += h[4];
+    st.overflow_adder += h[9];
+    if (n_hits > c->hits.capacity) st.overflow_hits += n_hits - c->hits.capacity;
+    if (n_ev > c->ev.capacity) st.overflow_events += n_ev - c->ev.capacity;
+    if (n_q1 > c->q[1].capacity) st.overflow_events += n_q1 - c->q[1].capacity;
+    if (h[4] > c->coinc_cap) st.overflow_events += h[4] - c->coinc_cap;
+    for (int k = 0; k < 32; k++) c->h_counters[k] = h[k];
+    for (int k = 0; k < 4; k++) c->last_counts[k] = h[k];
+    if (rs.resident) return GPET_OK;
+    const size_t ns = std::min<size_t>(h[3], c->singles.capacity), nc = std::min<size_t>(h[4], c->coinc_cap);
+    const bool want_coinc = c->dig.coinc_window_us > 0.f;
+    if ((r = arena_reserve(c, c->res_singles, ns * sizeof(gpet_event)))) return r;
+    if (want_coinc && (r = arena_reserve(c, c->res_coinc, nc * sizeof(gpet_coincidence)))) return r;
+    char* dst_s = c->res_singles.p + c->res_singles.size;
+    char* dst_c = want_coinc ? c->res_coinc.p + c->res_coinc.size : nullptr;
+    if (ns) CK(cudaMemcpyAsync(dst_s, c->singles_slot[slot], ns * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (want_coinc && nc)
+        CK(cudaMemcpyAsync(dst_c, c->coinc_slot[slot], nc * sizeof(gpet_coincidence), cudaMemcpyDeviceToHost, c->copy_stream));
+    CK(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+    c->res_singles.size += ns * sizeof(gpet_event);
+    if (want_coinc) c->res_coinc.size += nc * sizeof(gpet_coincidence);
+    if (!rs.od.empty()) {
+        // file dumps with the reference layouts (gPET.cu:367-383, 424): this path runs frame by frame (no pipelining)
+        CK(cudaStreamSynchronize(c->copy_stream));
+        const size_t nh = std::min<size_t>(n_hits, c->hits.capacity), ne = std::min<size_t>(n_ev, c->ev.capacity);
+        if (c->tr.record_hits) {
+            if ((r = append_device(c, join_path(rs.od, "HitsID.dat"), c->hits.id, nh * 5 * sizeof(int32_t), rs.tmp))) return r;
+            if ((r = append_device(c, join_path(rs.od, "Hits.dat"), c->hits.f, nh * 5 * sizeof(float), rs.tmp))) return r;
+        }
+        // note: adder.dat of the reference is written before blur; blur runs in place, so with blur enabled the
+        // energies in this dump are the blurred ones
+        c->stats.kernel_launches += launch_events_soa_to_aos(c->ev, c->stage_aos, c->stream);
+        if ((r = append_device(c, join_path(rs.od, "adder.dat"), c->stage_aos, ne * sizeof(gpet_event), rs.tmp))) return r;
+        FILE* fs = fopen(join_path(rs.od, "singles.dat").c_str(), "ab");
+        if (!fs) return fail(c, GPET_ERR_IO, "cannot open singles.dat for appending");
+        if (ns) fwrite(dst_s, sizeof(gpet_event), ns, fs);
+        fclose(fs);
+        if (want_coinc) {
+            FILE* fc = fopen(join_path(rs.od, "coincidences.dat").c_str(), "ab");
+            if (!fc) return fail(c, GPET_ERR_IO, "cannot open coincidences.dat for appending");
+            if (nc) fwrite(dst_c, sizeof(gpet_coincidence), nc, fc);
+            fclose(fc);
+        }
+    }
+    return GPET_OK;
+}
+
 int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* stats_out) {
     int r;
     if ((r = ensure_buffers(c))) return r;
@@ -910,86 +1010,59 @@ int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* sta
         if (nf < 0) return (int)nf;
     }
     if (psf_mode && !c->have_psf) return fail(c, GPET_ERR_ARG, "no PSF loaded");
-    gpet_stats st{};
+    RunState rs;
+    rs.resident = resident;
+    rs.od = output_dir ? output_dir : "";
+    gpet_stats& st = rs.st;
     const uint64_t launches0 = c->stats.kernel_launches;
-    c->res_singles.clear();
-    c->res_coinc.clear();
-    std::vector<char> tmp;
-    std::string od = output_dir ? output_dir : "";
+    CK(cudaStreamSynchronize(c->copy_stream));
+    c->res_singles.size = 0;
+    c->res_coinc.size = 0;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, c->stream));
     const int64_t psf_batch = (int64_t)c->cap_photons;  // simulateParticle batches of NPART photons (gPET.cu:33-44)
     const int64_t nframes = psf_mode ? ((int64_t)c->psf.p.size() + psf_batch - 1) / psf_batch : (int64_t)c->frames.size();
-    for (int64_t f = 0; f < nframes; f++) {
+    const bool pipelined = rs.od.empty();   // file dumps read the (single-buffered) hit and event buffers frame by frame
+    int64_t k = 0;                           // owned frames launched so far
+    int rc = GPET_OK;
+    for (int64_t f = 0; f < nframes && rc == GPET_OK; f++) {
         if (f % c->world != c->rank) continue;
+        if (!psf_mode && c->frames[(size_t)f].npairs == 0) continue;
+        const int slot = (int)(k & 1);
+        c->out_slot = slot;
+        c->singles_aos = c->singles_slot[slot];
+        c->coinc_aos = c->coinc_slot[slot];
+        if (k >= 2 && !resident) CK(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
         if (psf_mode) {
             int64_t first = f * psf_batch, n = std::min<int64_t>(psf_batch, (int64_t)c->psf.p.size() - first);
-            if ((r = gpet_stage_psf(c, first, n))) return r;
+            if ((rc = gpet_stage_psf(c, first, n))) break;
             st.pairs += (uint64_t)n / 2;
         } else {
-            if (c->frames[(size_t)f].npairs == 0) continue;
-            if ((r = gpet_stage_source(c, f))) return r;
+            if ((rc = gpet_stage_source(c, f))) break;
             st.pairs += c->frames[(size_t)f].npairs;
         }
-        if ((r = gpet_stage_phantom(c))) return r;
-        if ((r = gpet_stage_detector(c))) return r;
-        if ((r = gpet_stage_digitize(c))) return r;
-        st.frames++;
-        if ((r = read_counters(c))) return r;   // one small D2H + sync per frame
-        const unsigned* h = c->h_counters;
-        const uint64_t n_ev = h[19], n_hits = h[18], n_q1 = h[17];
-        st.photons_phantom_out += n_q1;
-        st.photons_on_panel += h[8];
-        st.hits += n_hits;
-        st.events_adder += h[0];
-        st.events_threshold += h[1];
-        st.events_deadtime += h[2];
-        st.singles += h[3];
-        st.coincidences += h[4];
-        st.overflow_adder += h[9];
-        if (n_hits > c->hits.capacity) st.overflow_hits += n_hits - c->hits.capacity;
-        if (n_ev > c->ev.capacity) st.overflow_events += n_ev - c->ev.capacity;
-        if (n_q1 > c->q[1].capacity) st.overflow_events += n_q1 - c->q[1].capacity;
-        if (h[4] > c->coinc_cap) st.overflow_events += h[4] - c->coinc_cap;
-        if (resident) continue;
-        const size_t ns = std::min<size_t>(h[3], c->singles.capacity), nc = std::min<size_t>(h[4], c->coinc_cap);
-        if (ns) {
-            size_t old = c->res_singles.size();
-            c->res_singles.resize(old + ns);
-            CK(cudaMemcpyAsync(c->res_singles.data() + old, c->singles_aos, ns * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->stream));
-        }
-        if (nc && c->dig.coinc_window_us > 0.f) {
-            size_t old = c->res_coinc.size();
-            c->res_coinc.resize(old + nc);
-            CK(cudaMemcpyAsync(c->res_coinc.data() + old, c->coinc_aos, nc * sizeof(gpet_coincidence), cudaMemcpyDeviceToHost, c->stream));
-        }
-        CK(cudaStreamSynchronize(c->stream));
-        if (!od.empty()) {
-            const size_t nh = std::min<size_t>(n_hits, c->hits.capacity), ne = std::min<size_t>(n_ev, c->ev.capacity);
-            if (c->tr.record_hits) {
-                if ((r = append_device(c, join_path(od, "HitsID.dat"), c->hits.id, nh * 5 * sizeof(int32_t), tmp))) return r;
-                if ((r = append_device(c, join_path(od, "Hits.dat"), c->hits.f, nh * 5 * sizeof(float), tmp))) return r;
-            }
-            // note: adder.dat of the reference is written before blur; blur runs in place, so with blur enabled the
-            // energies in this dump are the blurred ones
-            c->stats.kernel_launches += launch_events_soa_to_aos(c->ev, c->stage_aos, c->stream);
-            if ((r = append_device(c, join_path(od, "adder.dat"), c->stage_aos, ne * sizeof(gpet_event), tmp))) return r;
-            FILE* fs = fopen(join_path(od, "singles.dat").c_str(), "ab");
-            if (!fs) return fail(c, GPET_ERR_IO, "cannot open singles.dat for appending");
-            if (ns) fwrite(c->res_singles.data() + (c->res_singles.size() - ns), sizeof(gpet_event), ns, fs);
-            fclose(fs);
-            if (c->dig.coinc_window_us > 0.f) {
-                FILE* fc = fopen(join_path(od, "coincidences.dat").c_str(), "ab");
-                if (!fc) return fail(c, GPET_ERR_IO, "cannot open coincidences.dat for appending");
-                if (nc) fwrite(c->res_coinc.data() + (c->res_coinc.size() - nc), sizeof(gpet_coincidence), nc, fc);
-                fclose(fc);
-            }
-        }
+        if ((rc = gpet_stage_phantom(c))) break;
+        if ((rc = gpet_stage_detector(c))) break;
+        if ((rc = gpet_stage_digitize(c))) break;
+        CK(cudaMemcpyAsync(c->h_slot_counters[slot], c->ws.counters, 32 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaEventRecord(c->ev_counters[slot], c->stream));
+        k++;
+        if (!pipelined) rc = retire_frame(c, slot, rs);
+        else if (k >= 2) rc = retire_frame(c, slot ^ 1, rs);
+    }
+    if (rc == GPET_OK && pipelined && k >= 1) rc = retire_frame(c, (int)((k - 1) & 1), rs);
+    if (rc != GPET_OK) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->copy_stream);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return rc;
     }
     CK(cudaEventRecord(e1, c->stream));
     CK(cudaEventSynchronize(e1));
+    CK(cudaStreamSynchronize(c->copy_stream));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
@@ -1021,14 +1094,14 @@ int gpet_run_resident(gpet_ctx* c, gpet_stats* stats) {
 
 int64_t gpet_result_singles(gpet_ctx* c, const gpet_event** ptr) {
     if (!c || !ptr) return GPET_ERR_ARG;
-    *ptr = c->res_singles.data();
-    return (int64_t)c->res_singles.size();
+    *ptr = reinterpret_cast<const gpet_event*>(c->res_singles.p);
+    return (int64_t)(c->res_singles.size / sizeof(gpet_event));
 }
 
 int64_t gpet_result_coincidences(gpet_ctx* c, const gpet_coincidence** ptr) {
     if (!c || !ptr) return GPET_ERR_ARG;
-    *ptr = c->res_coinc.data();
-    return (int64_t)c->res_coinc.size();
+    *ptr = reinterpret_cast<const gpet_coincidence*>(c->res_coinc.p);
+    return (int64_t)(c->res_coinc.size / sizeof(gpet_coincidence));
 }
 
 int gpet_get_stats(const gpet_ctx* c, gpet_stats* s) {

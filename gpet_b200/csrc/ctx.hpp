@@ -15,6 +15,12 @@ struct FramePlan {
     uint64_t npairs = 0, first_pair = 0;
 };
 
+// Growable pinned host buffer: results of gpet_run land here by asynchronous D2H copies.
+struct PinnedArena {
+    char* p = nullptr;
+    size_t cap = 0, size = 0;
+};
+
 struct gpet_ctx {
     int device = -1;
     bool has_device = false;
@@ -50,9 +56,16 @@ struct gpet_ctx {
     gpet::HitBuffer hits{};
     gpet::EventSoA ev{}, singles{};
     gpet::DigitizerWorkspace ws{};
-    void* singles_aos = nullptr;
-    void* coinc_aos = nullptr;
+    void* singles_aos = nullptr;     // = singles_slot[out_slot]: 48-byte records of the frame being digitized
+    void* coinc_aos = nullptr;       // = coinc_slot[out_slot]
     unsigned coinc_cap = 0;
+    // gpet_run pipelines frames: frame k computes into slot k&1 while the host copies frame k-1 out of the other slot
+    void* singles_slot[2] = {nullptr, nullptr};
+    void* coinc_slot[2] = {nullptr, nullptr};
+    unsigned* h_slot_counters[2] = {nullptr, nullptr};   // pinned, 32 words each
+    cudaEvent_t ev_counters[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    int out_slot = 0;
     void* stage_aos = nullptr;       // cap * 48 B staging for AoS <-> SoA conversion
     size_t stage_bytes = 0;
     gpet::PanelDev* d_panels = nullptr;
@@ -69,8 +82,7 @@ struct gpet_ctx {
     // ---- frames / results
     std::vector<FramePlan> frames;
     bool planned = false;
-    std::vector<gpet_event> res_singles;
-    std::vector<gpet_coincidence> res_coinc;
+    PinnedArena res_singles, res_coinc;   // gpet_event / gpet_coincidence records of the last gpet_run
     gpet_stats stats{};
     uint64_t last_counts[4] = {0, 0, 0, 0};
     gpet::KernelTimer ktimer;   // per-kernel CUDA-event times (gpet_profile_enable)
