@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- annihilation pairs/s of the gPET hot path (source -> phantom -> detector -> digitizer) on B200.
 
-One "step" = one complete run of the shipped small-animal example (BASELINE.json configs[0]: input_PET.in, 8-panel
-config8.geo, 1 cm water cylinder in a 200^3 phantom, pointsource.txt, 0-120 s acquisition = ~178.7k pairs), i.e. every
-frame of the acquisition through all four stages.  `value` is measured with the inputs resident in HBM
+One "step" = one complete run of the shipped small-animal example as BASELINE.json configs[0] names it (input_PET.in,
+8-panel config8.geo, 1 cm water cylinder in a 200^3 phantom, the shipped source.txt = 7 F-18 cylinders, 0-120 s
+acquisition = ~1.118 M annihilation pairs), i.e. every frame of the acquisition through all four stages.  (The shipped
+input_PET.in points at input/pointsource.txt, ~179 k pairs; `--source pointsource.txt` runs that variant, and its
+numbers are reported under "extra" in the default line.)  `value` is measured with the inputs resident in HBM
 (gpet_run_resident: only counters leave the device); `e2e` goes through the public C-ABI call a user makes (gpet_run:
 frame planning + descriptor upload + all stages + singles/coincidences copied back to host memory).
 
@@ -34,10 +36,17 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "annihilation_pairs_per_s"
 UNIT = "pairs/s"
-WORKLOAD = "shipped small-animal example: input_PET.in, config8.geo (8 panels), 1 cm water cylinder 200^3, pointsource.txt, 0-120 s"
+DEFAULT_SOURCE = "source.txt"
 
 
-def make_workdir(tmp, n=200, source="pointsource.txt"):
+def workload_name(source):
+    return f"shipped small-animal example: input_PET.in, config8.geo (8 panels), 1 cm water cylinder 200^3, {source}, 0-120 s"
+
+
+WORKLOAD = workload_name(DEFAULT_SOURCE)
+
+
+def make_workdir(tmp, n=200, source=DEFAULT_SOURCE):
     from tools import gen_inputs
     ex_src = ROOT / "examples" / "small_animal"
     ex = Path(tmp) / "ex"
@@ -59,60 +68,82 @@ def make_workdir(tmp, n=200, source="pointsource.txt"):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the measurement (B200_PROFILING.md recipe) through NVML, every 5 ms."""
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.rows = []
-        self.p = None
+        self.sm, self.power, self.reasons = [], [], set()
+        self.max_sm = None
+        self._stop = threading.Event()
+        self._t = None
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                       "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indices follow the physical order; honour CUDA_VISIBLE_DEVICES if it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.idx
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                idx = int(vis.split(",")[self.idx])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            return
+        names = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)}
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    try:
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:  # noqa: BLE001
+                        mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for k, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(k)
+                except Exception:  # noqa: BLE001
+                    pass
+                time.sleep(0.005)
+
+        self._t = threading.Thread(target=loop, daemon=True)
+        self._t.start()
 
     def stop(self):
-        if self.p:
-            self.p.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=1.0)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None}
 
 
-def cpu_baseline(ex, npairs=8_000_000, chunk=1_000_000, seed=12345):
-    """Oracle port on one host core over a bounded sample of the same workload: `npairs` pairs of the shipped point source
-    through source -> phantom -> detector -> digitizer, in chunks of `chunk` pairs (one digitizer pass per chunk)."""
+def cpu_baseline(ex, source=DEFAULT_SOURCE, npairs=6_000_000, chunk=1_000_000, seed=12345):
+    """Oracle port on one host core over a bounded sample of the same workload: `npairs` pairs of the workload's source
+    distribution through source -> phantom -> detector -> digitizer, in chunks of `chunk` pairs (one digitizer pass each)."""
     sys.path.insert(0, str(ROOT / "tests"))
     import parity
     from oracle import oracle as orc
     from gpet_b200 import refio
     s = parity.Setup(device=-1, phantom=parity.gen_inputs.cylinder_phantom(n=200), size=1.0)
-    src = refio.parse_sources(ex / "input" / "pointsource.txt")
+    src = refio.parse_sources(ex / "input" / source)
     iso = refio.parse_isotopes(ex / "data" / "isotopes.txt")
     tau = np.array([np.float64(iso[x["type"]]["halftime"]) * 1.442695 for x in src])
     frac = -np.expm1(-120.0 / tau)
+    weight = np.array([x["natom"] * frac[i] * iso[x["type"]]["ratio"] for i, x in enumerate(src)], np.float64)
     p, _ = parity.make_digi_params(blur_Rref=0.05, coinc_window_us=0.01)
     t0 = time.perf_counter()
     done = 0
     while done < npairs:
         n = min(chunk, npairs - done)
-        ph = orc.source(np.array([n], np.uint64), [x["shape"] for x in src], np.concatenate([x["coeff"] for x in src]),
+        per_src = np.floor(weight / weight.sum() * n).astype(np.uint64)
+        per_src[-1] += np.uint64(n - int(per_src.sum()))
+        ph = orc.source(np.cumsum(per_src), [x["shape"] for x in src], np.concatenate([x["coeff"] for x in src]),
                         tau, frac, 0.0, done, 0.0037056, n, seed)
         ph = orc.phantom(ph, s.mat, s.den, s.offset, s.size, s.tab_ph, s.eabs, seed)
         res = orc.detector(ph, s.panels, s.counts4, s.pmat, s.pdens, s.surfaces, s.tab_det, s.eabs, 2, 1, seed)
@@ -121,53 +152,74 @@ def cpu_baseline(ex, npairs=8_000_000, chunk=1_000_000, seed=12345):
     dt = time.perf_counter() - t0
     s.close()
     return {"value": npairs / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{npairs} pairs of the same workload (shipped point source, 200^3 phantom, config8.geo) through the "
+            "sample": f"{npairs} pairs of the same workload ({source}, 200^3 phantom, config8.geo) through the "
                       f"single-thread C oracle (source+phantom+detector+digitizer) in chunks of {chunk}, {dt:.1f} s"}
 
 
+def have_gpu():
+    return shutil.which("nvidia-smi") is not None and subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0
+
+
+def reference_line(ex, args, source, steps, warmup):
+    """The reference's own implementation of the path, timed on this box: its CUDA build (oracle/_ref, texture-object
+    patch only) when it travelled with the snapshot and a GPU is present -- the reference has no CPU path at all
+    (README.md:31) -- else the single-thread CPU oracle port."""
+    from oracle import run_ref
+    line = None
+    if run_ref.available() and have_gpu():
+        try:
+            line = run_ref.bench_reference(ex, steps=steps, warmup=warmup, metric=METRIC, unit=UNIT, workload=workload_name(source))
+        except Exception as e:  # noqa: BLE001
+            line = None
+            print(f"reference binary unusable ({type(e).__name__}: {e}); falling back to the CPU oracle port", file=sys.stderr)
+    if line is None:
+        base = cpu_baseline(ex, source, npairs=4_000_000)
+        v = base["value"]
+        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+                "ms_per_step": 1e3 * 4_000_000 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(source)}, "cpu_baseline": base,
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line["n_gpus"] = args.gpus
+    line["impl"] = "reference"
+    return line
+
+
 def run_reference(args):
-    """Reference arm: the patched reference CUDA binary when available on a GPU box, else the CPU oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     with tempfile.TemporaryDirectory() as tmp:
-        ex = make_workdir(tmp)
-        line = None
-        from oracle import run_ref
-        have_gpu = shutil.which("nvidia-smi") is not None and subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0
-        if run_ref.available() and have_gpu:
-            try:
-                line = run_ref.bench_reference(ex, steps=max(1, min(args.steps, 5)), warmup=max(1, min(args.warmup, 1)),
-                                               metric=METRIC, unit=UNIT, workload=WORKLOAD)
-                line["n_gpus"] = args.gpus
-            except Exception as e:  # noqa: BLE001
-                line = None
-                print(f"reference binary unusable ({type(e).__name__}: {e}); falling back to the CPU oracle port", file=sys.stderr)
-        if line is None:
-            vals = []
-            base = None
-            for _ in range(max(1, min(args.steps, 3))):
-                base = cpu_baseline(ex, npairs=4_000_000)
-                vals.append(base["value"])
-            v = float(np.mean(vals))
-            base["value"] = v
-            line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": 0,
-                    "ms_per_step": 1e3 * 4_000_000 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                    "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
-                    "cpu_baseline": base,
-                    "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        line["impl"] = "reference"
-        print(json.dumps(line))
+        ex = make_workdir(tmp, source=args.source)
+        print(json.dumps(reference_line(ex, args, args.source, steps=max(1, min(args.steps, 5)), warmup=1)))
+
+
+# algorithmic bytes one launch of each kernel must move (DESIGN.md section 4); c = per-frame counters
+ALG_BYTES = {
+    "k_source": lambda c: 48 * c["photons"],
+    "k_phantom": lambda c: 48 * c["photons"] + 48 * c["q1"],
+    "k_panel_entry": lambda c: 48 * c["q1"] + 48 * c["on_panel"],
+    "k_detector": lambda c: 48 * c["on_panel"] + 48 * c["hits"] + 44 * c["events"],
+    "k_prep": lambda c: 12 * c["events"] + 12 * c["events"],
+    "k_onesweep<u64>": lambda c: 24 * c["events"],
+    "k_site_keys": lambda c: 16 * c["alive"] + 12 * c["alive"],
+    "k_onesweep<u32>": lambda c: 16 * c["alive"],
+    "k_deadtime": lambda c: 20 * c["alive"] + c["alive"],
+    "k_emit_singles": lambda c: 9 * c["alive"] + (44 + 44 + 48) * c["singles"],
+    "k_coinc_count": lambda c: 12 * c["singles"] + 4 * c["singles"],
+    "k_coinc_emit": lambda c: 4 * c["singles"] + 192 * c["coinc"],
+    "k_begin": lambda c: 20000,
+}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--activity-scale", type=float, default=1.0, help="multiply the source atoms (extra line only; default = shipped file)")
+    ap.add_argument("--source", default=DEFAULT_SOURCE, help="source file of the example (source.txt | pointsource.txt)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -186,46 +238,49 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
 
     tmp = tempfile.TemporaryDirectory()
-    ex = make_workdir(tmp.name)
-    ctx = api.Context(local)
     # a real (non-NULL) stream: gpet_set_stream(NULL) means "library-owned stream", and the CUDA events below must be
     # recorded on the stream the kernels are launched on
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
-    ctx.set_seed(0x67504554 + 1000003 * rank)   # disjoint Philox keys per rank
-    ctx.load_config_file(ex / "input_PET.in", base_dir=ex)
-    ctx.set_digitizer(coinc_window_us=0.01)
-    if args.activity_scale != 1.0:
-        ctx.set_source_atoms(0, int(1762974000 * args.activity_scale))
-    ctx.set_spectrum(128, 0.0, 1.0e6)
-    nframes = ctx.plan_frames(0)
-
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     tally = torch.zeros(16, dtype=torch.int64, device=dev)
 
-    def one_step(resident=True):
+    def make_ctx(source, sub):
+        ex = make_workdir(Path(tmp.name) / sub, source=source)
+        ctx = api.Context(local)
+        ctx.set_stream(stream.cuda_stream)
+        ctx.set_seed(0x67504554 + 1000003 * rank)   # disjoint Philox keys per rank: independent decay histories
+        ctx.load_config_file(ex / "input_PET.in", base_dir=ex)
+        ctx.set_digitizer(coinc_window_us=0.01)
+        ctx.set_spectrum(128, 0.0, 1.0e6)
+        ctx.plan_frames(0)
+        return ex, ctx
+
+    def one_step(ctx, resident=True):
         st = ctx.run_resident() if resident else ctx.run(None)
-        if world > 1:
+        if world > 1:   # tally reduction is part of the multi-GPU step
             tally[:9] = torch.tensor([st.pairs, st.photons_phantom_out, st.photons_on_panel, st.hits, st.events_adder,
                                       st.events_threshold, st.events_deadtime, st.singles, st.coincidences],
                                      dtype=torch.int64, device=dev)
             dist.all_reduce(tally)
         return st
 
-    def timed(nsteps, resident=True):
+    def timed(ctx, nsteps, resident=True):
         times, stats = [], []
         for _ in range(nsteps):
             flush.fill_(1)                      # L2 flush between timed iterations
             torch.cuda.synchronize()
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            if not resident:
-                ctx.plan_frames(0)              # e2e: planning + descriptor upload are part of the user's call
             e0.record(stream)
             w0 = time.perf_counter()
-            st = one_step(resident)
+            if not resident:
+                ctx.plan_frames(0)              # e2e: planning + descriptor upload are part of the user's call
+            st = one_step(ctx, resident)
             e1.record(stream)
             torch.cuda.synchronize()
             w1 = time.perf_counter()
@@ -233,90 +288,115 @@ def main():
             stats.append(st)
         return times, stats
 
-    timed(args.warmup)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    times, stats = timed(args.steps)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
-    pairs = torch.tensor([sum(s.pairs for s in stats)], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(pairs)
-    total_ms = float(total_ms.item())
-    total_pairs = int(pairs.item())
-    value = total_pairs / (total_ms * 1e-3)
+    def measure(ctx, steps, warmup):
+        timed(ctx, warmup)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        times, stats = timed(ctx, steps)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        total_ms = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
+        pairs = torch.tensor([sum(s.pairs for s in stats)], dtype=torch.int64, device=dev)
+        coinc = torch.tensor([sum(s.coincidences for s in stats)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(pairs)
+            dist.all_reduce(coinc)
+        # e2e through gpet_run: host results in pinned memory, wall clock around planning + run
+        timed(ctx, 2, resident=False)
+        e_times, e_stats = timed(ctx, max(3, min(steps, 20)), resident=False)
+        e_ms = torch.tensor([sum(e_times)], dtype=torch.float64, device=dev)
+        e_pairs = torch.tensor([sum(s.pairs for s in e_stats)], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(e_pairs)
+        return {"total_ms": float(total_ms.item()), "pairs": int(pairs.item()), "coinc": int(coinc.item()), "stats": stats,
+                "e2e_ms": float(e_ms.item()), "e2e_pairs": int(e_pairs.item()), "e2e_stats": e_stats}
 
-    # ---- e2e through gpet_run (host results), wall clock around the call incl. planning/upload and D2H
-    timed(2, resident=False)
-    e2e_times, e2e_stats = timed(max(3, min(args.steps, 10)), resident=False)
-    e2e_ms = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=dev)
-    e2e_pairs = torch.tensor([sum(s.pairs for s in e2e_stats)], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_pairs)
-    st = e2e_stats[-1]
+    ex, ctx = make_ctx(args.source, "main")
+    m = measure(ctx, args.steps, args.warmup)
+    value = m["pairs"] / (m["total_ms"] * 1e-3)
+    st = m["e2e_stats"][-1]
+    nframes = int(st.frames)
     h2d = nframes * 4096 + 64
-    d2h = int(st.singles * 48 + st.coincidences * 96 + 21 * 4 * st.frames)
+    d2h = int(st.singles * 48 + st.coincidences * 96 + 32 * 4 * st.frames)
+
+    extra = None
+    if not args.no_extra and world == 1 and args.source == DEFAULT_SOURCE:
+        ex2, ctx2 = make_ctx("pointsource.txt", "extra")
+        m2 = measure(ctx2, max(5, min(args.steps, 20)), 3)
+        extra = {"workload": workload_name("pointsource.txt"), "value": m2["pairs"] / (m2["total_ms"] * 1e-3),
+                 "e2e": m2["e2e_pairs"] / (m2["e2e_ms"] * 1e-3), "pairs_per_step": m2["pairs"] / len(m2["stats"]), "unit": UNIT}
+        ctx2.close()
 
     if rank == 0:
-        # ---- per-stage device times (CUDA events on the launching stream) for the roofline of the dominant kernel
-        stage_ms = {"source": [], "phantom": [], "detector": [], "digitizer": []}
-        for _ in range(max(5, args.warmup)):
+        # ---- per-kernel device times (CUDA events around every launch, on the launching stream) -> roofline
+        ctx.profile(True)
+        nprof = 5
+        for _ in range(nprof):
             flush.fill_(1)
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-            ev[0].record(stream); ctx.stage_source(0)
-            ev[1].record(stream); ctx.stage_phantom()
-            ev[2].record(stream); ctx.stage_detector()
-            ev[3].record(stream); ctx.stage_digitize()
-            ev[4].record(stream)
-            torch.cuda.synchronize()
-            for k, name in enumerate(stage_ms):
-                stage_ms[name].append(ev[k].elapsed_time(ev[k + 1]))
-        stage_med = {k: statistics.median(v[1:]) for k, v in stage_ms.items()}
-        s0 = stats[-1]
-        fp = ctx.frame_pairs(0)
-        n_q0 = 2 * fp
-        # algorithmic bytes per launch (DESIGN.md "kernels"): 48 B photon records, 48 B hit rows, 44 B event columns
-        alg = {"source": 48 * n_q0,
-               "phantom": 48 * n_q0 + 48 * s0.photons_phantom_out / max(s0.frames, 1),
-               "detector": 48 * s0.photons_phantom_out / max(s0.frames, 1) + 48 * s0.hits / max(s0.frames, 1) + 44 * s0.events_adder / max(s0.frames, 1),
-               "digitizer": 480 * s0.events_adder / max(s0.frames, 1)}
-        top = max(("source", "phantom", "detector", "digitizer"), key=lambda k: stage_med[k])
+            ctx.run_resident()
+        kt = ctx.kernel_times()
+        ctx.profile(False)
+        s0 = m["stats"][-1]
+        fr = max(int(s0.frames), 1)
+        cnt = {"photons": 2 * s0.pairs / fr, "q1": s0.photons_phantom_out / fr, "on_panel": s0.photons_on_panel / fr,
+               "hits": s0.hits / fr, "events": s0.events_adder / fr, "alive": s0.events_threshold / fr,
+               "singles": s0.singles / fr, "coinc": s0.coincidences / fr}
+        kernels = {}
+        for name, (ms, n) in kt.items():
+            alg = float(ALG_BYTES.get(name, lambda c: 0)(cnt))
+            kernels[name] = {"launches_per_step": n / nprof, "us_per_launch": 1e3 * ms / max(n, 1), "us_per_step": 1e3 * ms / nprof,
+                             "algorithmic_bytes_per_launch": alg, "achieved_gbs": alg / (ms / max(n, 1) * 1e-3) / 1e9 if ms > 0 else 0.0}
+        top = max(kernels, key=lambda k: kernels[k]["us_per_step"])
         peaks = {}
         pk = ROOT / "MEASURED_PEAKS.json"
         if pk.exists():
             peaks = json.loads(pk.read_text())
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = alg[top] / (stage_med[top] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": {"source": "k_source", "phantom": "k_phantom", "detector": "k_detector",
-                                                "digitizer": "digitizer chain (k_prep + radix passes + k_deadtime + compaction)"}[top],
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "peak_source": "MEASURED_PEAKS.json (measured)" if pk.exists() else "fallback",
-                    "stage_ms": stage_med, "algorithmic_bytes": {k: float(v) for k, v in alg.items()},
-                    "note": "latency/issue bound Monte-Carlo: algorithmic bytes are tiny, see DESIGN.md and profiles/"}
-        base = None if args.no_cpu_baseline else cpu_baseline(ex)
+        traffic = None
+        tf = ROOT / "profiles" / "traffic.json"   # dram bytes per launch from the committed `ncu --set full` captures
+        if tf.exists():
+            traffic = json.loads(tf.read_text()).get(args.source, {}).get(top)
+        roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels[top]["achieved_gbs"] / peak, "traffic": traffic,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if pk.exists() else "fallback 6650 GB/s (B200_PROFILING.md)",
+                    "us_per_launch": kernels[top]["us_per_launch"], "share_of_step": kernels[top]["us_per_step"] / sum(k["us_per_step"] for k in kernels.values()),
+                    "timing": "CUDA events bracketing every launch on the launching stream (gpet_profile_enable), 5 steps, L2 flushed between steps",
+                    "note": "Monte-Carlo transport is latency/issue bound: the algorithmic bytes are tiny against HBM (DESIGN.md section 4); see profiles/ for issue-slot and SIMT-efficiency numbers",
+                    "kernels": kernels}
+        base = None
+        if not args.no_cpu_baseline:
+            try:
+                ref = reference_line(ex, args, args.source, steps=2, warmup=1)
+                base = ref["cpu_baseline"]
+                base["value"] = ref["value"]
+                if base.get("kind") == "reference":
+                    base["reference_counters"] = ref.get("reference_counters")
+                    base["oracle_port"] = cpu_baseline(ex, args.source, npairs=3_000_000)
+            except Exception as e:  # noqa: BLE001
+                base = cpu_baseline(ex, args.source)
+                base["note"] = f"reference binary failed: {e}"
+        clocks = sampler.stop()
+        nsteps = len(m["stats"])
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": m["total_ms"] / nsteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": total_pairs / args.steps / world,
-                           "frames_per_step": int(stats[-1].frames), "l2": "flushed between timed steps (256 MiB write)",
-                           "activity_scale": args.activity_scale, "coincidence_window_us": 0.01, "rng": "Philox4x32-10"},
+                "config": {"workload": workload_name(args.source), "pairs_per_step_per_gpu": m["pairs"] / nsteps / world,
+                           "frames_per_step": nframes, "l2": "flushed between timed steps (256 MiB write)",
+                           "coincidence_window_us": 0.01, "rng": "Philox4x32-10, key = 0x67504554 + 1000003*rank",
+                           "time_path": "fp64", "multi_gpu": "independent decay histories per rank (disjoint Philox keys), tallies all-reduced over NCCL"},
                 "clocks": clocks,
-                "e2e": {"value": int(e2e_pairs.item()) / (float(e2e_ms.item()) * 1e-3), "unit": UNIT,
-                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "timing": "wall clock around gpet_plan_frames + gpet_run, max over ranks"},
-                "gpu_launches": int(sum(s.kernel_launches for s in stats)),
+                "e2e": {"value": m["e2e_pairs"] / (m["e2e_ms"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "timing": "wall clock around gpet_plan_frames + gpet_run (singles and coincidences delivered to pinned host memory), max over ranks"},
+                "gpu_launches": int(sum(s.kernel_launches for s in m["stats"])),
                 "roofline": roofline, "cpu_baseline": base,
                 "counters": {"pairs": int(s0.pairs), "hits": int(s0.hits), "events_adder": int(s0.events_adder),
                              "singles": int(s0.singles), "coincidences": int(s0.coincidences),
-                             "coincidences_per_s": float(sum(s.coincidences for s in stats) * world / (total_ms * 1e-3))}}
+                             "coincidences_per_s": float(m["coinc"] / (m["total_ms"] * 1e-3))},
+                "extra": extra}
         print(json.dumps(line))
     ctx.close()
     if world > 1:
