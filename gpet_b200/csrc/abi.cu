@@ -230,6 +230,7 @@ PhantomDev phantom_dev(const gpet_ctx* c) {
     d.nx = ph.dim[0]; d.ny = ph.dim[1]; d.nz = ph.dim[2];
     d.ox = ph.offset[0]; d.oy = ph.offset[1]; d.oz = ph.offset[2];
     d.idx = 1.0f / ph.d[0]; d.idy = 1.0f / ph.d[1]; d.idz = 1.0f / ph.d[2];  // initialize.cu:846-851
+    d.dx = ph.d[0]; d.dy = ph.d[1]; d.dz = ph.d[2];
     return d;
 }
 
@@ -518,7 +519,8 @@ int gpet_get_digitizer(const gpet_ctx* c, gpet_digitizer_params* p) {
 int gpet_set_transport(gpet_ctx* c, const gpet_transport_params* p) {
     if (!c || !p) return GPET_ERR_ARG;
     if (p->nsurface < 0 || p->nsurface > GPET_MAX_SURFACES) return fail(c, GPET_ERR_ARG, "too many quadric surfaces (MAXSURFACE)");
-    if (p->use_positron_range) return fail(c, GPET_ERR_ARG, "positron range sampling is not implemented yet");
+    if (p->use_positron_range != c->tr.use_positron_range || p->noncollinearity_rad != c->tr.noncollinearity_rad)
+        c->planned = false;   // both are baked into the per-frame source descriptors
     c->tr = *p;
     return GPET_OK;
 }
@@ -717,7 +719,12 @@ int gpet_stage_source(gpet_ctx* c, int64_t f) {
     if ((r = ensure_buffers(c))) return r;
     const FramePlan& fp = c->frames[(size_t)f];
     if (2 * fp.npairs > c->cap_photons) return fail(c, GPET_ERR_CAPACITY, "frame exceeds the photon capacity");
-    c->stats.kernel_launches += launch_source(c->d_frames + f, fp.npairs, PhantomDev{}, c->q[0], c->seed, c->num_sms, c->stream);
+    PhantomDev ph{};
+    if (c->tr.use_positron_range) {   // the positron range walks the density grid (gPET_kernals.cu:379-414)
+        if ((r = upload_phantom(c))) return r;
+        ph = phantom_dev(c);
+    }
+    c->stats.kernel_launches += launch_source(c->d_frames + f, fp.npairs, ph, c->q[0], c->seed, c->num_sms, c->stream);
     CK(cudaGetLastError());
     return GPET_OK;
 }
@@ -726,8 +733,22 @@ int gpet_stage_psf(gpet_ctx* c, int64_t first, int64_t n) {
     NEED_DEVICE();
     if (!c->have_psf) return fail(c, GPET_ERR_ARG, "no PSF loaded");
     if (first < 0 || n < 0 || first + n > (int64_t)c->psf.p.size()) return fail(c, GPET_ERR_ARG, "PSF range out of bounds");
-    if (c->psf.ptype == 0) return fail(c, GPET_ERR_ARG, "positron PSF input is not implemented yet");
-    return gpet_put_photons(c, 0, c->psf.p.data() + first, n);
+    if (c->psf.ptype == 1) return gpet_put_photons(c, 0, c->psf.p.data() + first, n);
+    // positron phase space: every record becomes an annihilation photon pair (setPositionForPhoton)
+    ProfScope prof(c);
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((uint64_t)(2 * n) > c->cap_photons) return fail(c, GPET_ERR_CAPACITY, "positron batch exceeds half the photon capacity");
+    PhantomDev ph{};
+    if (c->tr.use_positron_range) {
+        if ((r = upload_phantom(c))) return r;
+        ph = phantom_dev(c);
+    }
+    if (n) CK(cudaMemcpyAsync(c->stage_aos, c->psf.p.data() + first, (size_t)n * sizeof(gpet_photon), cudaMemcpyHostToDevice, c->stream));
+    c->stats.kernel_launches += launch_psf_positron(c->stage_aos, c->q[0], (unsigned)n, (unsigned long long)first, ph,
+                                                    c->tr.noncollinearity_rad, c->tr.use_positron_range, c->seed, c->num_sms, c->stream);
+    CK(cudaGetLastError());
+    return GPET_OK;
 }
 
 int gpet_stage_phantom(gpet_ctx* c) {
@@ -1022,7 +1043,8 @@ int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* sta
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, c->stream));
-    const int64_t psf_batch = (int64_t)c->cap_photons;  // simulateParticle batches of NPART photons (gPET.cu:33-44)
+    // simulateParticle batches: NPART photons, or NPART/2 positrons that become NPART photons (gPET.cu:33-44)
+    const int64_t psf_batch = (psf_mode && c->psf.ptype == 0) ? (int64_t)(c->cap_photons / 2) : (int64_t)c->cap_photons;
     const int64_t nframes = psf_mode ? ((int64_t)c->psf.p.size() + psf_batch - 1) / psf_batch : (int64_t)c->frames.size();
     const bool pipelined = rs.od.empty();   // file dumps read the (single-buffered) hit and event buffers frame by frame
     int64_t k = 0;                           // owned frames launched so far
@@ -1038,7 +1060,7 @@ int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* sta
         if (psf_mode) {
             int64_t first = f * psf_batch, n = std::min<int64_t>(psf_batch, (int64_t)c->psf.p.size() - first);
             if ((rc = gpet_stage_psf(c, first, n))) break;
-            st.pairs += (uint64_t)n / 2;
+            st.pairs += c->psf.ptype == 0 ? (uint64_t)n : (uint64_t)n / 2;
         } else {
             if ((rc = gpet_stage_source(c, f))) break;
             st.pairs += c->frames[(size_t)f].npairs;

@@ -76,6 +76,7 @@ struct PhantomDev {
     int nx, ny, nz;
     float ox, oy, oz;      // offset
     float idx, idy, idz;   // 1/voxel size
+    float dx, dy, dz;      // voxel size
 };
 
 struct TablesDev {

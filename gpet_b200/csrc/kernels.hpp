@@ -43,8 +43,8 @@ int launch_digitize(EventSoA ev, EventSoA singles, void* singles_aos, void* coin
 // ---- transport (transport.cu) ----------------------------------------------------------------------------
 int launch_source(const SourceDev* frame_dev, unsigned long long npairs, PhantomDev ph, PhotonQueue q0,
                   uint64_t seed, int num_sms, cudaStream_t s);
-int launch_psf_positron(PhotonQueue q0, unsigned int n_positrons, PhantomDev ph, float nonangle, int use_prange,
-                        uint64_t seed, int num_sms, cudaStream_t s);
+int launch_psf_positron(const void* positrons_aos, PhotonQueue q0, unsigned int n_positrons, unsigned long long first,
+                        PhantomDev ph, float nonangle, int use_prange, uint64_t seed, int num_sms, cudaStream_t s);
 int launch_phantom(PhotonQueue q0, PhotonQueue q1, PhantomDev ph, TablesDev tb, float eabs, uint64_t seed,
                    int num_sms, cudaStream_t s);
 int launch_detector(PhotonQueue q1, PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,

@@ -129,9 +129,82 @@ __device__ __forceinline__ void sample_shape(int shape, const float* __restrict_
     }
 }
 
+// S4 sampleEkPositron (gPET_kernals.cu:420-443): rejection sampling of the beta+ spectrum from the fitted polynomial
+// (coef[0] = endpoint incl. 0.511 MeV, coef[1] = pdf maximum, coef[2..7] = coefficients of E^5..E^0); kinetic energy in eV.
+// One Philox block per round.  The 0.511 literals are doubles in the reference, hence the fp64 detours.
+__device__ __forceinline__ float sample_ek_positron(const float* __restrict__ coef, Philox& rng) {
+    float E, u, sumE;
+    do {
+        uint4 r = rng.next();
+        E = (float)((double)u01(r.x) * ((double)coef[0] - 0.511) + 0.511);
+        u = coef[1] * u01(r.y);
+        sumE = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; i++) sumE += coef[2 + i] * powf(E, (float)(5 - i));
+    } while (u > sumE);
+    return (float)(((double)E - 0.511) * 1e6);
+}
+
+__device__ __forceinline__ float voxel_density_clamped(const PhantomDev& ph, int ix, int iy, int iz) {
+    // the reference reads a point-filtered, clamp-addressed 3-D texture (tex3D(dens_tex, ...), initialize.cu:880-882)
+    ix = min(max(ix, 0), ph.nx - 1); iy = min(max(iy, 0), ph.ny - 1); iz = min(max(iz, 0), ph.nz - 1);
+    return __uint_as_float(__ldg(ph.vox + ((size_t)iz * ph.ny + iy) * ph.nx + ix) & ~15u);
+}
+
+// S5 setPositronRange (gPET_kernals.cu:347-418): Gaussian displacement with sigma = Rex/2, Rex = 0.1*b1*E^2/(b2+E) (E in MeV,
+// water), then a density-scaled ray march through the voxels.  Restated statement by statement, including its quirks:
+// the density used for a step is that of the voxel being ENTERED, and a positron outside the phantom is moved by
+// 1000 cm + (r - s)/0.0012905 (`step` keeps its 1000 sentinel in the else branch).
+__device__ __forceinline__ void positron_range(const PhantomDev& ph, float& px, float& py, float& pz, float vx, float vy, float vz,
+                                               float ekin_eV, bool usedirection, Philox& rng) {
+    const float ekin = (float)((double)ekin_eV / 1e6);
+    float b1 = 5.44040782f, b2 = 0.369516529f;
+    const float Rex = (float)(0.1 * (double)b1 * (double)ekin * (double)ekin / (double)(b2 + ekin));
+    const float sigma = Rex / (2 * 1.0f);
+    uint4 q = rng.next();
+    const float ra = sqrtf(-2.0f * logf(u01(q.x))), rb = sqrtf(-2.0f * logf(u01(q.z)));
+    float dx = sigma * (ra * cosf(kTwoPi * u01(q.y)));
+    float dy = sigma * (ra * sinf(kTwoPi * u01(q.y)));
+    float dz = sigma * (rb * cosf(kTwoPi * u01(q.w)));
+    const float r = sqrtf(dx * dx + dy * dy + dz * dz);
+    if (usedirection) {
+        const float tmp = sqrtf(vx * vx + vy * vy + vz * vz);
+        dx = r * vx / tmp; dy = r * vy / tmp; dz = r * vz / tmp;
+    }
+    float s = 0.f, step;
+    int ix = (int)((px - ph.ox) * ph.idx), iy = (int)((py - ph.oy) * ph.idy), iz = (int)((pz - ph.oz) * ph.idz);
+    int w = (ix <= 0 || ix >= ph.nx || iy <= 0 || iy >= ph.ny || iz <= 0 || iz >= ph.nz) ? -1 : 1;
+    int guard = 0;
+    while (s < r && guard++ < 100000) {
+        step = 1000.f;
+        if (w > 0) {
+            b1 = (ph.ox + (ix + (dx > 0.f)) * ph.dx - px) / dx;
+            if (step > b1) { step = b1; w = 1; }
+            b1 = (ph.oy + (iy + (dy > 0.f)) * ph.dy - py) / dy;
+            if (step > b1) { step = b1; w = 2; }
+            b1 = (ph.oz + (iz + (dz > 0.f)) * ph.dz - pz) / dz;
+            if (step > b1) { step = b1; w = 3; }
+            if (w == 1) ix += (dx > 0.f) ? 1 : -1;
+            else if (w == 2) iy += (dy > 0.f) ? 1 : -1;
+            else iz += (dz > 0.f) ? 1 : -1;
+            b2 = voxel_density_clamped(ph, ix, iy, iz);
+            step = step * r;
+            s += step * b2;
+            if (s > r) step += (r - s) / b2;
+        } else {
+            step += (float)((double)(r - s) / 0.0012905);
+            s = r + 100.f;
+        }
+        px += step * dx / r; py += step * dy / r; pz += step * dz / r;
+        if (px < ph.ox || px > (ph.ox + ph.nx * ph.dx)) w = -1;
+        if (py < ph.oy || py > (ph.oy + ph.ny * ph.dy)) w = -1;
+        if (pz < ph.oz || pz > (ph.oz + ph.nz * ph.dz)) w = -1;
+    }
+}
+
 // one thread per photon (two threads per annihilation pair; both recompute the shared pair quantities)
 __global__ void __launch_bounds__(kThreads) k_source(const SourceDev* __restrict__ fr, unsigned long long npairs,
-                                                     PhotonQueue q0, uint64_t seed) {
+                                                     PhantomDev ph, PhotonQueue q0, uint64_t seed) {
     const unsigned long long nph = 2ull * npairs;
     if (blockIdx.x == 0 && threadIdx.x == 0) *q0.count = (unsigned)min(nph, (unsigned long long)q0.capacity);
     for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < nph && p < q0.capacity;
@@ -161,6 +234,11 @@ __global__ void __launch_bounds__(kThreads) k_source(const SourceDev* __restrict
         float phi2 = kTwoPi * u01(r2.x);
         float g = sqrtf(-2.f * logf(u01(r2.y))) * cosf(kTwoPi * u01(r2.z));
         float delta = g * fr->nonangle;
+        if (fr->use_prange) {
+            // S4 + S5: positron kinetic energy, then its range (gPET_kernals.cu:529-533); direction is sampled (usedirection 0)
+            const float ek = sample_ek_positron(fr->iso_coef + 8 * fr->type[s], rng);
+            positron_range(ph, x, y, z, 0.f, 0.f, 0.f, ek, false, rng);
+        }
         float E;
         if (which == 0) {
             E = kMC2 + delta * kMC2 * 0.5f;
@@ -621,6 +699,44 @@ __global__ void k_queue_to_aos(PhotonQueue q, gpet_photon* __restrict__ aos) {
     }
 }
 
+// S6 setPositionForPhoton (gPET_kernals.cu:563-604): positron phase space -> annihilation photon pair.  Positron i of
+// the batch gives photons 2i and 2i+1 (the reference puts them at i and i+total); both photons carry the positron's
+// time -- the reference never writes d_time of the second photon, which silently drops it: fixed here.
+__global__ void __launch_bounds__(kThreads) k_psf_positron(const gpet_photon* __restrict__ pos, PhotonQueue q0, unsigned n,
+                                                           unsigned long long first, PhantomDev ph, float nonangle, int use_prange,
+                                                           uint64_t seed) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *q0.count = min(2u * n, q0.capacity);
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < 2u * n && p < q0.capacity; p += gridDim.x * blockDim.x) {
+        const unsigned i = p >> 1;
+        const int which = (int)(p & 1u);
+        const gpet_photon e = pos[i];
+        const unsigned long long gi = first + i;
+        Philox rng(seed, gi, (uint32_t)kStagePsfPositron << 24);
+        uint4 r0 = rng.next();
+        float x = e.x, y = e.y, z = e.z;
+        float ct = -1.f + 2.f * u01(r0.x);
+        float phi = kTwoPi * u01(r0.y);
+        float st = sqrtf(1.f - ct * ct);
+        float vx = st * cosf(phi), vy = st * sinf(phi), vz = ct;
+        float phi2 = kTwoPi * u01(r0.z);
+        uint4 r1 = rng.next();
+        float g = sqrtf(-2.f * logf(u01(r1.x))) * cosf(kTwoPi * u01(r1.y));
+        float delta = g * nonangle;
+        if (use_prange) positron_range(ph, x, y, z, e.vx, e.vy, e.vz, e.E, true, rng);
+        float E;
+        if (which == 0) {
+            E = kMC2 + delta * kMC2 * 0.5f;
+        } else {
+            rotate_dir(vx, vy, vz, -cosf(delta), phi2);
+            E = kMC2 - delta * kMC2 * 0.5f;
+        }
+        q0.pos_e[p] = make_float4(x, y, z, E);
+        q0.dir_n[p] = make_float4(vx, vy, vz, __int_as_float(0));
+        q0.t[p] = e.t;
+        q0.ids[p] = make_int2((int)(unsigned)gi, (int)(unsigned)(2ull * gi + which));
+    }
+}
+
 template <typename K>
 int persistent_grid(K kernel, int num_sms, size_t smem) {
     int per_sm = 1;
@@ -632,18 +748,25 @@ int persistent_grid(K kernel, int num_sms, size_t smem) {
 }  // namespace
 
 // ================================================================================================ launchers
-int launch_source(const SourceDev* frame_dev, unsigned long long npairs, PhantomDev, PhotonQueue q0, uint64_t seed,
+int launch_source(const SourceDev* frame_dev, unsigned long long npairs, PhantomDev ph, PhotonQueue q0, uint64_t seed,
                   int num_sms, cudaStream_t s) {
     unsigned long long nph = 2ull * npairs;
     unsigned long long blocks = (nph + kThreads - 1) / kThreads;
     unsigned long long maxb = (unsigned long long)num_sms * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
-    GPET_LAUNCH("k_source", s, k_source<<<(unsigned)blocks, kThreads, 0, s>>>(frame_dev, npairs, q0, seed));
+    GPET_LAUNCH("k_source", s, k_source<<<(unsigned)blocks, kThreads, 0, s>>>(frame_dev, npairs, ph, q0, seed));
     return 1;
 }
 
-int launch_psf_positron(PhotonQueue, unsigned int, PhantomDev, float, int, uint64_t, int, cudaStream_t) { return 0; }
+int launch_psf_positron(const void* positrons_aos, PhotonQueue q0, unsigned int n_positrons, unsigned long long first,
+                        PhantomDev ph, float nonangle, int use_prange, uint64_t seed, int num_sms, cudaStream_t s) {
+    unsigned blocks = n_positrons ? (2 * n_positrons + kThreads - 1) / kThreads : 1;
+    if (blocks > (unsigned)num_sms * 8) blocks = (unsigned)num_sms * 8;
+    GPET_LAUNCH("k_psf_positron", s, k_psf_positron<<<blocks, kThreads, 0, s>>>(static_cast<const gpet_photon*>(positrons_aos), q0,
+                                                                              n_positrons, first, ph, nonangle, use_prange, seed));
+    return 1;
+}
 
 int launch_phantom(PhotonQueue q0, PhotonQueue q1, PhantomDev ph, TablesDev tb, float eabs, uint64_t seed, int num_sms,
                    cudaStream_t s) {

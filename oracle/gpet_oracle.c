@@ -62,7 +62,7 @@ static double u01d(uint32_t a, uint32_t b) {
     return (double)k * 1.1102230246251565e-16 + 5.551115123125783e-17;
 }
 
-enum { ST_SOURCE = 1, ST_PHANTOM = 2, ST_DETECTOR = 3, ST_BLUR = 4 };
+enum { ST_SOURCE = 1, ST_PHANTOM = 2, ST_DETECTOR = 3, ST_BLUR = 4, ST_PLAN = 5, ST_PSF_POSITRON = 6 };
 
 /* ------------------------------------------------------------------------------------------------ records */
 typedef struct { int32_t parn, pann, modn, cryn, siten, eventid; double t; float E, x, y, z; } orc_event; /* gPET.h:87-92 */
@@ -166,12 +166,149 @@ static void rotate_dir(float* u, float* v, float* w, float costh, float phi) {
     }
 }
 
+/* ------------------------------------------------------------------------------------------------ positron (S4, S5) */
+typedef struct {  /* voxel grid as the range walk sees it */
+    const float* dens; int nx, ny, nz; float ox, oy, oz, dx, dy, dz, idx, idy, idz;
+} orc_grid;
+
+/* sampleEkPositron (gPET_kernals.cu:420-443) */
+static float sample_ek_positron(const float* coef, orc_rng* g) {
+    float E, u, sumE;
+    do {
+        uint32_t r[4];
+        rng_next(g, r);
+        E = (float)((double)u01(r[0]) * ((double)coef[0] - 0.511) + 0.511);
+        u = coef[1] * u01(r[1]);
+        sumE = 0.f;
+        for (int i = 0; i < 6; i++) sumE += coef[2 + i] * powf(E, (float)(5 - i));
+    } while (u > sumE);
+    return (float)(((double)E - 0.511) * 1e6);
+}
+
+static float grid_density_clamped(const orc_grid* gr, int ix, int iy, int iz) {  /* clamp-addressed point texture */
+    if (ix < 0) ix = 0;
+    if (ix > gr->nx - 1) ix = gr->nx - 1;
+    if (iy < 0) iy = 0;
+    if (iy > gr->ny - 1) iy = gr->ny - 1;
+    if (iz < 0) iz = 0;
+    if (iz > gr->nz - 1) iz = gr->nz - 1;
+    return gr->dens[((size_t)iz * gr->ny + iy) * gr->nx + ix];
+}
+
+/* setPositronRange (gPET_kernals.cu:347-418), statement by statement (quirks kept: density of the voxel being
+ * entered; `step` keeps its 1000 sentinel for a positron outside the phantom) */
+static void positron_range(const orc_grid* gr, float* px, float* py, float* pz, float vx, float vy, float vz, float ekin_eV,
+                           int usedirection, orc_rng* g) {
+    const float ekin = (float)((double)ekin_eV / 1e6);
+    float b1 = 5.44040782f, b2 = 0.369516529f;
+    const float Rex = (float)(0.1 * (double)b1 * (double)ekin * (double)ekin / (double)(b2 + ekin));
+    const float sigma = Rex / (2 * 1.0f);
+    uint32_t q[4];
+    rng_next(g, q);
+    const float ra = sqrtf(-2.0f * logf(u01(q[0]))), rb = sqrtf(-2.0f * logf(u01(q[2])));
+    float dx = sigma * (ra * cosf(ORC_TWOPI * u01(q[1])));
+    float dy = sigma * (ra * sinf(ORC_TWOPI * u01(q[1])));
+    float dz = sigma * (rb * cosf(ORC_TWOPI * u01(q[3])));
+    const float r = sqrtf(dx * dx + dy * dy + dz * dz);
+    if (usedirection) {
+        const float tmp = sqrtf(vx * vx + vy * vy + vz * vz);
+        dx = r * vx / tmp; dy = r * vy / tmp; dz = r * vz / tmp;
+    }
+    float s = 0.f, step;
+    int ix = (int)((*px - gr->ox) * gr->idx), iy = (int)((*py - gr->oy) * gr->idy), iz = (int)((*pz - gr->oz) * gr->idz);
+    int w = (ix <= 0 || ix >= gr->nx || iy <= 0 || iy >= gr->ny || iz <= 0 || iz >= gr->nz) ? -1 : 1;
+    int guard = 0;
+    while (s < r && guard++ < 100000) {
+        step = 1000.f;
+        if (w > 0) {
+            b1 = (gr->ox + (ix + (dx > 0.f)) * gr->dx - *px) / dx;
+            if (step > b1) { step = b1; w = 1; }
+            b1 = (gr->oy + (iy + (dy > 0.f)) * gr->dy - *py) / dy;
+            if (step > b1) { step = b1; w = 2; }
+            b1 = (gr->oz + (iz + (dz > 0.f)) * gr->dz - *pz) / dz;
+            if (step > b1) { step = b1; w = 3; }
+            if (w == 1) ix += (dx > 0.f) ? 1 : -1;
+            else if (w == 2) iy += (dy > 0.f) ? 1 : -1;
+            else iz += (dz > 0.f) ? 1 : -1;
+            b2 = grid_density_clamped(gr, ix, iy, iz);
+            step = step * r;
+            s += step * b2;
+            if (s > r) step += (r - s) / b2;
+        } else {
+            step += (float)((double)(r - s) / 0.0012905);
+            s = r + 100.f;
+        }
+        *px += step * dx / r; *py += step * dy / r; *pz += step * dz / r;
+        if (*px < gr->ox || *px > (gr->ox + gr->nx * gr->dx)) w = -1;
+        if (*py < gr->oy || *py > (gr->oy + gr->ny * gr->dy)) w = -1;
+        if (*pz < gr->oz || *pz > (gr->oz + gr->nz * gr->dz)) w = -1;
+    }
+}
+
+static void make_grid(orc_grid* gr, const float* dens, const int32_t dim[3], const float offset[3], const float size[3]) {
+    gr->dens = dens; gr->nx = dim[0]; gr->ny = dim[1]; gr->nz = dim[2];
+    gr->ox = offset[0]; gr->oy = offset[1]; gr->oz = offset[2];
+    gr->dx = size[0] / dim[0]; gr->dy = size[1] / dim[1]; gr->dz = size[2] / dim[2];
+    gr->idx = 1.0f / gr->dx; gr->idy = 1.0f / gr->dy; gr->idz = 1.0f / gr->dz;
+}
+
+/* setPositionForPhoton (gPET_kernals.cu:563-604): positron i -> photons 2i, 2i+1; the second photon's time is set
+ * (the reference leaves it 0 and thereby drops the photon: consciously fixed) */
+void orc_psf_positron(const orc_photon* pos, int64_t n, uint64_t first, const float* dens, const int32_t dim[3],
+                      const float offset[3], const float size[3], float nonangle, int use_prange, uint64_t seed,
+                      orc_photon* out) {
+    orc_grid gr;
+    if (use_prange) make_grid(&gr, dens, dim, offset, size);
+    for (int64_t i = 0; i < n; i++) {
+        const orc_photon* e = pos + i;
+        uint64_t gi = first + (uint64_t)i;
+        orc_rng g;
+        rng_init(&g, seed, gi, (uint32_t)ST_PSF_POSITRON << 24);
+        uint32_t r0[4], r1[4];
+        rng_next(&g, r0);
+        float x = e->x, y = e->y, z = e->z;
+        float ct = -1.f + 2.f * u01(r0[0]);
+        float phi = ORC_TWOPI * u01(r0[1]);
+        float st = sqrtf(1.f - ct * ct);
+        float vx = st * cosf(phi), vy = st * sinf(phi), vz = ct;
+        float phi2 = ORC_TWOPI * u01(r0[2]);
+        rng_next(&g, r1);
+        float gn = sqrtf(-2.f * logf(u01(r1[0]))) * cosf(ORC_TWOPI * u01(r1[1]));
+        float delta = gn * nonangle;
+        if (use_prange) positron_range(&gr, &x, &y, &z, e->vx, e->vy, e->vz, e->E, 1, &g);
+        for (int which = 0; which < 2; which++) {
+            orc_photon* p = out + 2 * i + which;
+            float ax = vx, ay = vy, az = vz, E;
+            if (which == 0) E = ORC_MC2 + delta * ORC_MC2 * 0.5f;
+            else { rotate_dir(&ax, &ay, &az, -cosf(delta), phi2); E = ORC_MC2 - delta * ORC_MC2 * 0.5f; }
+            p->x = x; p->y = y; p->z = z; p->E = E; p->vx = ax; p->vy = ay; p->vz = az; p->nscat = 0;
+            p->t = e->t; p->eventid = (int32_t)(uint32_t)gi; p->parn = (int32_t)(uint32_t)(2 * gi + which);
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------ source (S2, S3) */
 /* One frame: pairs k = 0..npairs-1, source index from the inclusive prefix cum_pairs[]; decay time is the
  * truncated exponential inside [t0, t0+dt) that the per-atom test of gPET_kernals.cu:519-521 induces. */
+void orc_source_ex(int nsource, const uint64_t* cum_pairs, const int32_t* shape, const float* coeff, const double* tau_s,
+                   const double* frac, double t0_s, uint64_t first_pair, float nonangle, uint64_t npairs, uint64_t seed,
+                   int use_prange, const int32_t* type, const float* iso_coef, const float* dens, const int32_t dim[3],
+                   const float offset[3], const float size[3], orc_photon* out);
+
 void orc_source(int nsource, const uint64_t* cum_pairs, const int32_t* shape, const float* coeff, const double* tau_s,
                 const double* frac, double t0_s, uint64_t first_pair, float nonangle, uint64_t npairs, uint64_t seed,
                 orc_photon* out) {
+    orc_source_ex(nsource, cum_pairs, shape, coeff, tau_s, frac, t0_s, first_pair, nonangle, npairs, seed, 0, NULL, NULL, NULL,
+                  NULL, NULL, NULL, out);
+}
+
+/* use_prange = 1 adds S4 + S5 (gPET_kernals.cu:529-533): `type` = isotope row per source, `iso_coef` = 8 floats per row */
+void orc_source_ex(int nsource, const uint64_t* cum_pairs, const int32_t* shape, const float* coeff, const double* tau_s,
+                   const double* frac, double t0_s, uint64_t first_pair, float nonangle, uint64_t npairs, uint64_t seed,
+                   int use_prange, const int32_t* type, const float* iso_coef, const float* dens, const int32_t dim[3],
+                   const float offset[3], const float size[3], orc_photon* out) {
+    orc_grid gr;
+    if (use_prange) make_grid(&gr, dens, dim, offset, size);
     for (uint64_t k = 0; k < npairs; k++) {
         int s = 0;
         while (s < nsource - 1 && k >= cum_pairs[s]) s++;
@@ -210,6 +347,10 @@ void orc_source(int nsource, const uint64_t* cum_pairs, const int32_t* shape, co
         float phi2 = ORC_TWOPI * u01(r2[0]);
         float gn = sqrtf(-2.f * logf(u01(r2[1]))) * cosf(ORC_TWOPI * u01(r2[2]));
         float delta = gn * nonangle;
+        if (use_prange) {
+            float ek = sample_ek_positron(iso_coef + 8 * type[s], &g);
+            positron_range(&gr, &x, &y, &z, 0.f, 0.f, 0.f, ek, 0, &g);
+        }
         for (int which = 0; which < 2; which++) {
             orc_photon* p = out + 2 * k + which;
             float ax = vx, ay = vy, az = vz, E;

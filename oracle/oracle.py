@@ -108,6 +108,33 @@ def source(cum_pairs, shape, coeff, tau_s, frac, t0_s, first_pair, nonangle, npa
     return out
 
 
+def source_with_range(cum_pairs, shape, coeff, tau_s, frac, t0_s, first_pair, nonangle, npairs, seed, types, iso_coef,
+                      dens, offset, size):
+    """orc_source with S4 + S5 (positron kinetic energy and range, gPET_kernals.cu:347-443) switched on."""
+    cum = np.ascontiguousarray(cum_pairs, np.uint64); sh = np.ascontiguousarray(shape, np.int32)
+    co = np.ascontiguousarray(coeff, np.float32); tau = np.ascontiguousarray(tau_s, np.float64)
+    fr = np.ascontiguousarray(frac, np.float64); ty = np.ascontiguousarray(types, np.int32)
+    ic = np.ascontiguousarray(iso_coef, np.float32).ravel(); dens = np.ascontiguousarray(dens, np.float32)
+    nz, ny, nx = dens.shape
+    dim = np.array([nx, ny, nz], np.int32); off = np.asarray(offset, np.float32); sz = np.asarray(size, np.float32)
+    out = np.zeros(2 * npairs, PHOTON_DTYPE)
+    lib().orc_source_ex(C.c_int(len(cum)), _p(cum), _p(sh), _p(co), _p(tau), _p(fr), C.c_double(t0_s), C.c_uint64(first_pair),
+                        C.c_float(nonangle), C.c_uint64(npairs), C.c_uint64(seed), C.c_int(1), _p(ty), _p(ic), _p(dens),
+                        _p(dim), _p(off), _p(sz), _p(out))
+    return out
+
+
+def psf_positron(positrons, first, dens, offset, size, nonangle, use_prange, seed):
+    """setPositionForPhoton (gPET_kernals.cu:563-604): positron records -> photon pairs."""
+    pos = np.ascontiguousarray(positrons, PHOTON_DTYPE); dens = np.ascontiguousarray(dens, np.float32)
+    nz, ny, nx = dens.shape
+    dim = np.array([nx, ny, nz], np.int32); off = np.asarray(offset, np.float32); sz = np.asarray(size, np.float32)
+    out = np.zeros(2 * pos.size, PHOTON_DTYPE)
+    lib().orc_psf_positron(_p(pos), C.c_int64(pos.size), C.c_uint64(first), _p(dens), _p(dim), _p(off), _p(sz),
+                           C.c_float(nonangle), C.c_int(1 if use_prange else 0), C.c_uint64(seed), _p(out))
+    return out
+
+
 def phantom(photons, mat, dens, offset, size, tables: TableSet, eabs, seed):
     ph = np.ascontiguousarray(photons, PHOTON_DTYPE).copy()
     mat = np.ascontiguousarray(mat, np.int32); dens = np.ascontiguousarray(dens, np.float32)

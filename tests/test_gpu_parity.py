@@ -324,3 +324,87 @@ def test_run_is_reproducible_and_shards_by_frame(tmp_path):
     assert merged.tobytes() == s_a[np.argsort(s_a["t"], kind="stable")].tobytes()   # G-invariant results
     _, s_c = run(0, 1, seed=78)
     assert s_c.tobytes() != s_a.tobytes()
+
+
+# ------------------------------------------------------------------------------------------------ positron range / positron PSF
+def water_box(n=40, size=2.0):
+    mat = np.ones((n, n, n), np.int32); den = np.ones((n, n, n), np.float32)
+    den[: n // 2] = 1.85   # a denser half so that the density-scaled march matters
+    return mat, den
+
+
+@needs_tables
+def test_source_with_positron_range_matches_oracle():
+    # S4 + S5 (gPET_kernals.cu:347-443): O-15 (row 2, endpoint 1.738 MeV kinetic) in a 2 cm water/bone box
+    mat, den = water_box()
+    s = parity.Setup(0, phantom=(mat, den), size=2.0, capacity=(1 << 20, 1 << 20, 1 << 20))
+    c = s.ctx
+    c.load_isotopes(parity.EXAMPLE / "data" / "isotopes.txt")
+    src_file = parity.ROOT / "tests" / "golden" / "source_o15_box.txt"
+    c.load_source(src_file)
+    c.set_transport(noncollinearity_rad=0.0037056, use_positron_range=1, eabs_eV=s.eabs, nsurface=1, surface=list(s.surfaces), record_hits=1)
+    c.set_time_window(0, 10)
+    nf = c.plan_frames(0)
+    fr = c.frame(0)
+    c.stage_source(0)
+    got = c.fetch_photons(0)
+    src, iso = c.sources(), c.isotopes()
+    tau = np.array([np.float64(iso[x["type"]]["halftime"]) * 1.442695 for x in src])
+    frac = -np.expm1(-fr["dt_s"] / tau)
+    iso_coef = np.array([i["coef"] for i in iso], np.float32)
+    args = (np.cumsum(fr["pairs"]), [x["shape"] for x in src], np.concatenate([x["coeff"] for x in src]), tau, frac, fr["t0_s"],
+            fr["first_pair"], 0.0037056, int(fr["pairs"].sum()), s.seed)
+    want = orc.source_with_range(*args, [x["type"] for x in src], iso_coef, s.den, s.offset, s.size)
+    plain = orc.source(*args)
+    assert got.size == want.size > 20000
+    d = np.sqrt((got["x"] - want["x"]) ** 2 + (got["y"] - want["y"]) ** 2 + (got["z"] - want["z"]) ** 2)
+    assert (d < 2e-4).mean() > 0.995           # a few walks cross a voxel face differently (powf/logf last bits)
+    for f_ in ("vx", "vy", "vz"):
+        assert np.allclose(got[f_], want[f_], atol=2e-5)
+    assert np.allclose(got["t"], want["t"], rtol=1e-12, atol=1e-6)
+    # the range really moved the annihilation points: mm scale for O-15 in water, both photons of a pair share the point
+    moved = np.sqrt((want["x"] - plain["x"]) ** 2 + (want["y"] - plain["y"]) ** 2 + (want["z"] - plain["z"]) ** 2)
+    inside = np.abs(plain["x"]) < 0.5
+    assert 0.02 < np.median(moved[inside]) < 0.3
+    assert np.array_equal(got["x"][0::2], got["x"][1::2]) and np.array_equal(got["z"][0::2], got["z"][1::2])
+    s.close()
+
+
+@needs_tables
+@pytest.mark.parametrize("use_prange", [0, 1])
+def test_positron_psf_matches_oracle_and_runs_end_to_end(tmp_path, use_prange):
+    # S6 setPositionForPhoton (gPET_kernals.cu:563-604): positron phase space -> photon pairs
+    mat, den = water_box()
+    s = parity.Setup(0, phantom=(mat, den), size=2.0)
+    rng = np.random.default_rng(31)
+    n = 30000
+    ct = rng.uniform(-1, 1, n); phi = rng.uniform(0, 2 * np.pi, n); st = np.sqrt(1 - ct * ct)
+    psf = tmp_path / "positrons.dat"
+    refio.write_psf(psf, rng.uniform(-0.6, 0.6, n), rng.uniform(-0.6, 0.6, n), rng.uniform(-0.6, 0.6, n),
+                    1.0 + np.arange(n) * 2.0, st * np.cos(phi), st * np.sin(phi), ct, rng.uniform(5e4, 1.5e6, n))
+    c = s.ctx
+    c.set_transport(noncollinearity_rad=0.0037056, use_positron_range=use_prange, eabs_eV=s.eabs, nsurface=1,
+                    surface=list(s.surfaces), record_hits=1)
+    c.load_psf(psf, 0, ptype=0)
+    assert c.num_psf() == n
+    c.stage_psf(0, n)
+    got = c.fetch_photons(0)
+    pos = np.zeros(n, api.PHOTON_DTYPE)
+    rec = refio.read_psf(psf)
+    for col, f_ in enumerate(("x", "y", "z", "t", "vx", "vy", "vz", "E")):   # record layout of initialize.cu:79-104
+        pos[f_] = rec[:, col]
+    want = orc.psf_positron(pos, 0, s.den, s.offset, s.size, 0.0037056, use_prange, s.seed)
+    assert got.size == want.size == 2 * n
+    assert np.array_equal(got["parn"], want["parn"]) and np.array_equal(got["eventid"], np.repeat(np.arange(n), 2))
+    d = np.sqrt((got["x"] - want["x"]) ** 2 + (got["y"] - want["y"]) ** 2 + (got["z"] - want["z"]) ** 2)
+    assert (d < 2e-4).mean() > 0.995
+    for f_ in ("vx", "vy", "vz"):
+        assert np.allclose(got[f_], want[f_], atol=2e-5)
+    # both photons of a pair carry the positron's time (the reference drops the second one: consciously fixed)
+    assert np.array_equal(got["t"][0::2], got["t"][1::2]) and np.all(got["t"] > 0)
+    cosang = got["vx"][0::2] * got["vx"][1::2] + got["vy"][0::2] * got["vy"][1::2] + got["vz"][0::2] * got["vz"][1::2]
+    assert np.all(cosang < -0.999)
+    # whole path in PSF mode (simulateParticle, gPET.cu:13-199)
+    st_ = c.run(None)
+    assert st_.pairs == n and st_.singles > 0 and st_.frames == 1
+    s.close()
