@@ -229,7 +229,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from gpet_b200 import api
+    from gpet_b200 import api, multi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -248,7 +248,6 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    tally = torch.zeros(16, dtype=torch.int64, device=dev)
 
     def make_ctx(source, sub):
         ex = make_workdir(Path(tmp.name) / sub, source=source)
@@ -263,11 +262,8 @@ def main():
 
     def one_step(ctx, resident=True):
         st = ctx.run_resident() if resident else ctx.run(None)
-        if world > 1:   # tally reduction is part of the multi-GPU step
-            tally[:9] = torch.tensor([st.pairs, st.photons_phantom_out, st.photons_on_panel, st.hits, st.events_adder,
-                                      st.events_threshold, st.events_deadtime, st.singles, st.coincidences],
-                                     dtype=torch.int64, device=dev)
-            dist.all_reduce(tally)
+        if world > 1:   # tally reduction over NCCL is part of the multi-GPU step (gpet_b200/multi.py)
+            multi.allreduce_tallies(multi.stats_vector(st), device=dev)
         return st
 
     def timed(ctx, nsteps, resident=True):

@@ -1,0 +1,89 @@
+"""World-size-2 tests of the multi-GPU host logic on CPU (gloo): frame sharding and tally reduction.
+The compute itself needs a GPU; what is checked here is that every rank plans the same frames, that the shards are a
+disjoint cover, and that the all-reduced tallies are the sums -- the logic `bench.py --gpus N` and gpet_run rely on."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+EXAMPLE = ROOT / "examples" / "small_animal"
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from gpet_b200 import api, multi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        with api.Context(-1) as c:                       # host-only context: planning works, compute must refuse
+            c.set_seed(1234)
+            c.load_isotopes(EXAMPLE / "data" / "isotopes.txt")
+            c.load_source(EXAMPLE / "input" / "source.txt")
+            c.set_time_window(0, 30)
+            mine, my_pairs, all_pairs = multi.plan_shard(c, max_pairs=40000)
+            n = c.plan_frames(40000)
+            frames = [(c.frame(f)["t0_s"], c.frame(f)["dt_s"], int(c.frame(f)["first_pair"]), c.frame_pairs(f)) for f in range(n)]
+            refused = False
+            try:
+                c.run_resident()
+            except api.GpetError as e:
+                refused = e.code == -4                   # GPET_ERR_NO_DEVICE: no CPU fallback
+        tot = multi.allreduce_tallies([my_pairs, len(mine), 1])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (mine, frames))
+        q.put((rank, mine, my_pairs, all_pairs, tot.tolist(), gathered, refused))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_shard_frames_and_reduce_tallies():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, mine0, pairs0, all0, tot0, gath0, ref0), (r1, mine1, pairs1, all1, tot1, gath1, ref1) = res
+    assert ref0 and ref1
+    # both ranks planned the very same frames (the planner is a pure function of seed and inputs)
+    assert gath0[0][1] == gath0[1][1] and all0 == all1
+    nframes = len(gath0[0][1])
+    assert nframes >= 5
+    # disjoint cover, round robin
+    assert sorted(mine0 + mine1) == list(range(nframes)) and not set(mine0) & set(mine1)
+    assert mine0 == list(range(0, nframes, 2)) and mine1 == list(range(1, nframes, 2))
+    # all-reduced tallies are the sums, identical on both ranks
+    assert tot0 == tot1 == [all0, nframes, 2]
+    assert pairs0 + pairs1 == all0
+    # frames tile the acquisition window and global pair indices are contiguous
+    fr = gath0[0][1]
+    for a, b in zip(fr[:-1], fr[1:]):
+        assert abs(a[0] + a[1] - b[0]) < 1e-9 and a[2] + a[3] == b[2]
+    assert abs(fr[-1][0] + fr[-1][1] - 30.0) < 1e-6
+
+
+def test_owned_frames_rule():
+    from gpet_b200 import multi
+    for world in (1, 2, 3, 8):
+        cover = sorted(f for r in range(world) for f in multi.owned_frames(37, r, world))
+        assert cover == list(range(37))
