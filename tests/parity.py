@@ -107,15 +107,16 @@ class Setup:
         c.load_tables(PACKED)
         geo = geo or (EXAMPLE / "input" / "config8.geo")
         c.load_geometry(geo)
-        if phantom == "cylinder":
+        if isinstance(phantom, str) and phantom == "cylinder":
             mat, den = gen_inputs.cylinder_phantom(n=n, size=size, radius=size / 2)
-        elif phantom == "air":
+        elif isinstance(phantom, str) and phantom == "air":
             mat, den = gen_inputs.air_phantom(n)
         else:
             mat, den = phantom
         self.mat, self.den = mat, den
-        self.offset = np.array([-size / 2] * 3, np.float32)
-        self.size = np.array([size] * 3, np.float32)
+        sz = np.broadcast_to(np.asarray(size, np.float64), (3,))
+        self.offset = (-sz / 2).astype(np.float32)
+        self.size = sz.astype(np.float32)
         c.set_phantom(mat, den, self.offset, self.size)
         # oracle side
         self.panels, self.pmat, self.pdens, self.counts4 = refio.parse_geometry(geo)

@@ -36,6 +36,143 @@ def write_phantom(mat, den, mat_path, den_path):
     np.ascontiguousarray(den, "<f4").tofile(den_path)
 
 
+def mouse_phantom(n=256, size=(3.2, 3.2, 6.4), water_mat=1, bone_mat=3, air_mat=0):
+    """Config 4: water ellipsoid with semi-axes (1.4, 1.4, 3.0) cm, CorticalBone (rho 1.85) cylinder of r = 0.15 cm along z
+    at (0, -0.8), air elsewhere; n^3 voxels over `size` cm centred on the origin.  Returns [z, y, x] volumes."""
+    cx = (np.arange(n, dtype=np.float64) + 0.5) * (size[0] / n) - size[0] / 2
+    cy = (np.arange(n, dtype=np.float64) + 0.5) * (size[1] / n) - size[1] / 2
+    cz = (np.arange(n, dtype=np.float64) + 0.5) * (size[2] / n) - size[2] / 2
+    X, Y, Z = cx[None, None, :], cy[None, :, None], cz[:, None, None]
+    water = (X / 1.4) ** 2 + (Y / 1.4) ** 2 + (Z / 3.0) ** 2 <= 1.0
+    bone = ((X - 0.0) ** 2 + (Y + 0.8) ** 2 <= 0.15 ** 2) & water
+    mat = np.full((n, n, n), air_mat, np.int32)
+    den = np.full((n, n, n), AIR_RHO, np.float32)
+    mat[water] = water_mat; den[water] = 1.0
+    mat[bone] = bone_mat; den[bone] = 1.85
+    return mat, den
+
+
+def water_cylinder_phantom(n=256, voxel=0.1, diameter=20.0, height=20.0, water_mat=1, air_mat=0):
+    """Config 5: `diameter` x `height` cm water cylinder (axis z) centred in an n^3 grid of `voxel` cm voxels."""
+    c = (np.arange(n, dtype=np.float64) + 0.5) * voxel - n * voxel / 2
+    disk = (c[None, :] ** 2 + c[:, None] ** 2) <= (diameter / 2) ** 2   # [y, x]
+    slab = np.abs(c) <= height / 2                                      # [z]
+    inside = slab[:, None, None] & disk[None]
+    mat = np.where(inside, water_mat, air_mat).astype(np.int32)
+    den = np.where(inside, np.float32(1.0), AIR_RHO).astype(np.float32)
+    return mat, den
+
+
+def ring_geo(npanels=32, radius=40.0, modules_y=4, modules_z=13, crystal_mat=7, crystal_rho=7.4):
+    """Config 5: a ring of `npanels` panels at `radius` cm about z in the reference's .geo layout (detector.cu:76-207):
+    the same 1.75 cm modules (0.02 gap) of 8x8 crystals of 0.21 cm (0.01 gap) as config8.geo; only panel 0 is described,
+    the others are rotated copies."""
+    ly = modules_y * 1.75 + (modules_y - 1) * 0.02
+    lz = modules_z * 1.75 + (modules_z - 1) * 0.02
+    return f"""number of panels
+{npanels}
+rotation axis (global frame)
+0 0 1
+rotation step between panels (degrees, counter-clockwise positive)
+{360.0 / npanels:g}
+material id and density (g/cm3): crystal, then gap
+{crystal_mat}          {crystal_rho:g}
+0        0.001025
+-------------------------------------------------
+index of the first panel
+0
+panel size x y z (cm)
+2 {ly:.2f} {lz:.2f}
+module size x y z (cm)
+2 1.75 1.75
+module gap x y z (cm)
+2 0.02 0.02
+crystal size x y z (cm)
+2 0.21 0.21
+crystal gap x y z (cm)
+2 0.01 0.01
+growth direction along local x y z
+-1  1 1
+centre of the panel face looking at the phantom (cm)
+0  {-radius:g}   0
+local x axis in the global frame
+0  1   0
+local y axis in the global frame
+1  0   0
+local z axis in the global frame
+0   0  -1
+-------------------------------------------------
+"""
+
+
+def source_file(rows):
+    """source.txt text (initialize.cu:120-140): rows of (natom, isotope row, shape, c0..c5)."""
+    out = [str(len(rows)), "atoms, isotope row, shape (0 box, 1 cylinder, 2 sphere), centre x y z (cm), three shape parameters#"]
+    for r in rows:
+        out.append(" ".join(str(v) for v in r))
+    return "\n".join(out) + "\n"
+
+
+def atoms_for_decays(decays, halflife_s, window_s, ratio=1.0):
+    """natom such that the expected number of emitted pairs in [0, window_s] is `decays`."""
+    frac = -np.expm1(-window_s * np.log(2.0) / halflife_s)
+    return int(round(decays / (frac * ratio)))
+
+
+def input_file(dims=(200, 200, 200), offset=(-0.5, -0.5, -0.5), extent=(1, 1, 1), mat="input/cylinder_phantom_mat.dat",
+               den="input/cylinder_phantom_den.dat", nhist=1000000, usepsf=0, source="input/pointsource.txt", ptype=0, prange=0,
+               window=(0, 120), eabs=1e3, geo="input/config8.geo", readout=(2, 1), threshold=50000, blur=(1, 662000, 0.05, 0, 0),
+               deadtime=(3, 0, 2.2), ewin=(30000, 700000), acollinearity=0.0037056):
+    """input_PET.in text in the reference's positional label/value layout (main.cu:52-182)."""
+    j = lambda v: " ".join(f"{x:g}" if isinstance(x, float) else str(x) for x in v)   # noqa: E731
+    return f"""GPU index:
+0
+annihilation photon acollinearity, Gaussian sigma (rad):
+{acollinearity:g}
+phantom voxel counts nx ny nz:
+{j(dims)}
+phantom corner offset x y z (cm):
+{j(offset)}
+phantom extent x y z (cm):
+{j(extent)}
+phantom material volume (int32, x fastest):
+{mat}
+phantom density volume (float32, x fastest):
+{den}
+number of phase-space histories (PSF mode only):
+{nhist}
+read a phase-space file as source (0 no, 1 yes):
+{usepsf}
+source description file:
+{source}
+phase-space particle type (0 positron, 1 photon):
+{ptype}
+positron range (0 off, 1 on):
+{prange}
+acquisition start and end (s):
+{j(window)}
+photon-PSF recording sphere centre x y z and radius (cm):
+0 0 0 5
+photon absorption energy (eV):
+{eabs:g}
+detector geometry file:
+{geo}
+quadric exclusion surfaces: count, then ten coefficients each (x2 y2 z2 xy xz yz x y z 1):
+1
+0 0 0 0 0 0 0 0 0 1
+readout depth and policy:
+{j(readout)}
+energy threshold before dead time (eV):
+{threshold:g}
+energy blur policy, reference energy (eV), reference resolution, slope (1/MeV), spatial blur sigma (cm):
+{j(blur)}
+dead-time level, type (0 paralyzable, 1 non-paralyzable), duration (us):
+{j(deadtime)}
+energy window lower and upper bound (eV):
+{j(ewin)}
+"""
+
+
 def back_to_back_psf(npairs, seed=20201001, energy=511000.0, dt_us=1.0):
     """Config 2: back-to-back 511 keV pairs from the origin, isotropic, pair k at t = (k+1)*dt_us."""
     rng = np.random.default_rng(seed)

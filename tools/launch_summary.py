@@ -20,7 +20,7 @@ def load(path):
 
 
 def short(name):
-    name = name.replace("gpet::<unnamed>::", "").replace("gpet::rsort::", "").replace("void ", "")
+    name = name.replace("gpet::<unnamed>::", "").replace("unnamed>::", "").replace("gpet::rsort::", "").replace("rsort::", "").replace("void ", "")
     return name.split("(")[0][:60]
 
 
