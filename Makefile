@@ -8,6 +8,11 @@ LIB := gpet_b200/libgpet_b200.so
 
 all: $(LIB) bin/gpet_b200
 
+# transport.cu: no implicit FMA contraction, so that the staged kernels and the fused front end (same device functions,
+# different surrounding code) produce bit-identical photons, and the arithmetic is the oracle's (-ffp-contract=off);
+# every intended FMA is spelled fmaf() in the source
+build/transport.o: NVFLAGS += -fmad=false
+
 build/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.hpp $(CSRC)/*.cuh include/*.h)
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)

@@ -195,6 +195,7 @@ def run_reference(args):
 
 # algorithmic bytes one launch of each kernel must move; c = per-frame counters
 ALG_BYTES = {
+    "k_front": lambda c: 48 * c["on_panel"],          # fused source+phantom+panel entry: only the entered photons are written
     "k_source": lambda c: 48 * c["photons"],
     "k_phantom": lambda c: 48 * c["photons"] + 48 * c["q1"],
     "k_panel_entry": lambda c: 48 * c["q1"] + 48 * c["on_panel"],

@@ -109,6 +109,8 @@ _SIGS = {
     "gpet_stage_psf": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "gpet_stage_phantom": (C.c_int, [_P]),
     "gpet_stage_detector": (C.c_int, [_P]),
+    "gpet_stage_front": (C.c_int, [_P, C.c_int64]),
+    "gpet_stage_panel_transport": (C.c_int, [_P]),
     "gpet_stage_digitize": (C.c_int, [_P]),
     "gpet_queue_size": (C.c_int64, [_P, C.c_int]),
     "gpet_put_photons": (C.c_int, [_P, C.c_int, _P, C.c_int64]),
@@ -369,6 +371,13 @@ class Context:
 
     def stage_detector(self):
         self._ck(self._l.gpet_stage_detector(self._h))
+
+    def stage_front(self, f=-1):
+        """Fused source (frame f >= 0) or queue 0 (f = -1) -> phantom -> panel entry -> queue 2."""
+        self._ck(self._l.gpet_stage_front(self._h, f))
+
+    def stage_panel_transport(self):
+        self._ck(self._l.gpet_stage_panel_transport(self._h))
 
     def stage_digitize(self):
         self._ck(self._l.gpet_stage_digitize(self._h))

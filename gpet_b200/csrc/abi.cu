@@ -768,7 +768,44 @@ int gpet_stage_detector(gpet_ctx* c) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((r = upload_geometry(c))) return r;
-    c->stats.kernel_launches += launch_detector(c->q[1], c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth,
+    c->stats.kernel_launches += launch_panel_entry(c->q[1], c->q[2], detector_dev(c), c->ws.counters, c->num_sms, c->stream);
+    c->stats.kernel_launches += launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth,
+                                                c->dig.readout_policy, c->tr.record_hits, c->hits, c->ev, c->ws.counters,
+                                                c->seed, c->num_sms, c->stream);
+    CK(cudaGetLastError());
+    return GPET_OK;
+}
+
+int gpet_stage_front(gpet_ctx* c, int64_t f) {
+    NEED_DEVICE();
+    ProfScope prof(c);
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((r = upload_phantom(c))) return r;
+    if ((r = upload_geometry(c))) return r;
+    const gpet::SourceDev* fr = nullptr;
+    unsigned long long npairs = 0;
+    if (f >= 0) {
+        if (!c->planned) return fail(c, GPET_ERR_ARG, "gpet_plan_frames must be called first");
+        if (f >= (int64_t)c->frames.size()) return fail(c, GPET_ERR_ARG, "frame index out of range");
+        const FramePlan& fp = c->frames[(size_t)f];
+        if (2 * fp.npairs > c->cap_photons) return fail(c, GPET_ERR_CAPACITY, "frame exceeds the photon capacity");
+        fr = c->d_frames + f;
+        npairs = fp.npairs;
+    }
+    c->stats.kernel_launches += launch_front(fr, npairs, c->q[0], c->q[1], c->q[2], phantom_dev(c), tables_dev(c), detector_dev(c),
+                                             c->tr.eabs_eV, c->ws.counters, c->seed, c->num_sms, c->stream);
+    CK(cudaGetLastError());
+    return GPET_OK;
+}
+
+int gpet_stage_panel_transport(gpet_ctx* c) {
+    NEED_DEVICE();
+    ProfScope prof(c);
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((r = upload_geometry(c))) return r;
+    c->stats.kernel_launches += launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth,
                                                 c->dig.readout_policy, c->tr.record_hits, c->hits, c->ev, c->ws.counters,
                                                 c->seed, c->num_sms, c->stream);
     CK(cudaGetLastError());
@@ -789,17 +826,17 @@ int gpet_stage_digitize(gpet_ctx* c) {
 // =================================================================================================== buffer access
 int64_t gpet_queue_size(gpet_ctx* c, int which) {
     NEED_DEVICE();
-    if (which < 0 || which > 1) return GPET_ERR_ARG;
+    if (which < 0 || which > 2) return GPET_ERR_ARG;
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((r = read_counters(c))) return r;
-    return (int64_t)std::min<unsigned>(c->h_counters[16 + which], c->q[which].capacity);
+    return (int64_t)std::min<unsigned>(c->h_counters[which == 2 ? 21 : 16 + which], c->q[which].capacity);
 }
 
 int gpet_put_photons(gpet_ctx* c, int which, const gpet_photon* in, int64_t n) {
     NEED_DEVICE();
     ProfScope prof(c);
-    if (which < 0 || which > 1 || n < 0 || (n > 0 && !in)) return GPET_ERR_ARG;
+    if (which < 0 || which > 2 || n < 0 || (n > 0 && !in)) return GPET_ERR_ARG;
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((uint64_t)n > c->cap_photons) return fail(c, GPET_ERR_CAPACITY, "photon batch exceeds capacity");
@@ -1057,16 +1094,17 @@ int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* sta
         c->singles_aos = c->singles_slot[slot];
         c->coinc_aos = c->coinc_slot[slot];
         if (k >= 2 && !resident) CK(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
+        // fused front end: photons stay in registers from birth (or from queue 0 in PSF mode) to the panel face
         if (psf_mode) {
             int64_t first = f * psf_batch, n = std::min<int64_t>(psf_batch, (int64_t)c->psf.p.size() - first);
             if ((rc = gpet_stage_psf(c, first, n))) break;
             st.pairs += c->psf.ptype == 0 ? (uint64_t)n : (uint64_t)n / 2;
+            if ((rc = gpet_stage_front(c, -1))) break;
         } else {
-            if ((rc = gpet_stage_source(c, f))) break;
+            if ((rc = gpet_stage_front(c, f))) break;
             st.pairs += c->frames[(size_t)f].npairs;
         }
-        if ((rc = gpet_stage_phantom(c))) break;
-        if ((rc = gpet_stage_detector(c))) break;
+        if ((rc = gpet_stage_panel_transport(c))) break;
         if ((rc = gpet_stage_digitize(c))) break;
         CK(cudaMemcpyAsync(c->h_slot_counters[slot], c->ws.counters, 32 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaEventRecord(c->ev_counters[slot], c->stream));

@@ -47,7 +47,12 @@ int launch_psf_positron(const void* positrons_aos, PhotonQueue q0, unsigned int 
                         PhantomDev ph, float nonangle, int use_prange, uint64_t seed, int num_sms, cudaStream_t s);
 int launch_phantom(PhotonQueue q0, PhotonQueue q1, PhantomDev ph, TablesDev tb, float eabs, uint64_t seed,
                    int num_sms, cudaStream_t s);
-int launch_detector(PhotonQueue q1, PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
+int launch_panel_entry(PhotonQueue q1, PhotonQueue q2, DetectorDev det, unsigned int* counters, int num_sms, cudaStream_t s);
+// fused source (frame_dev != nullptr) or queue q0 (frame_dev == nullptr) -> phantom -> panel entry -> q2; q1 only counts
+int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQueue q0, PhotonQueue q1, PhotonQueue q2,
+                 PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, unsigned int* counters, uint64_t seed, int num_sms,
+                 cudaStream_t s);
+int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
                     int record_hits, HitBuffer hits, EventSoA ev, unsigned int* counters, uint64_t seed,
                     int num_sms, cudaStream_t s);
 int launch_photons_aos_to_queue(const void* aos, PhotonQueue q, unsigned int n, cudaStream_t s);

@@ -9,6 +9,8 @@
 //   * stage boundaries are compact SoA queues filled with warp-aggregated appends (one atomic per warp);
 //   * the per-photon adder/readout runs in registers (no local-memory Event[4]); hits leave the SM as contiguous
 //     rows already in the HitsID.dat / Hits.dat layout.
+#include <cstdlib>
+
 #include "kernels.hpp"
 #include "ktimer.hpp"
 #include "philox.cuh"
@@ -202,67 +204,130 @@ __device__ __forceinline__ void positron_range(const PhantomDev& ph, float& px, 
     }
 }
 
-// one thread per photon (two threads per annihilation pair; both recompute the shared pair quantities)
+// A photon in registers.
+struct Photon {
+    float x, y, z, E, vx, vy, vz;
+    double t;
+    int eid, parn, nscat;
+};
+
+__device__ __forceinline__ void store_photon(const PhotonQueue& q, unsigned slot, const Photon& p) {
+    q.pos_e[slot] = make_float4(p.x, p.y, p.z, p.E);
+    q.dir_n[slot] = make_float4(p.vx, p.vy, p.vz, __int_as_float(p.nscat));
+    q.t[slot] = p.t;
+    q.ids[slot] = make_int2(p.eid, p.parn);
+}
+
+// S2 setPosition (gPET_kernals.cu:483-561) for pair k of the frame: both annihilation photons.  Photon a keeps the
+// sampled direction, photon b is the acollinear partner; they share the point and the time.
+__device__ __forceinline__ void source_pair(const SourceDev* __restrict__ fr, const PhantomDev& ph, uint64_t seed,
+                                            unsigned long long k, Photon& a, Photon& b) {
+    int s = 0;
+    while (s < fr->nsource - 1 && k >= fr->cum_pairs[s]) s++;
+    const unsigned long long gk = fr->first_pair + k;
+    Philox rng(seed, gk, (uint32_t)kStageSource << 24);
+    uint4 r0 = rng.next();
+    // truncated-exponential decay time inside the frame (statistically identical to the reference's per-atom
+    // test ptime = -T_half*1.442695*log(U) < slice, gPET_kernals.cu:519-521)
+    double ud = u01d(r0.x, r0.y);
+    double ptime = -fr->tau_s[s] * log1p(-ud * fr->frac[s]);
+    double t_us = (fr->t0_s + ptime) * 1e6;
+    uint4 r1 = rng.next();
+    float x, y, z;
+    sample_shape(fr->shape[s], fr->coeff + 6 * s, r1, x, y, z);
+    // isotropic direction (gPET_kernals.cu:536-540)
+    float ct = -1.f + 2.f * u01(r0.z);
+    float phi = kTwoPi * u01(r0.w);
+    float st = sqrtf(1.f - ct * ct);
+    float vx = st * cosf(phi), vy = st * sinf(phi), vz = ct;
+    // acollinearity: delta = N(0,1) * sigma (gPET_kernals.cu:549-555)
+    uint4 r2 = rng.next();
+    float phi2 = kTwoPi * u01(r2.x);
+    float g = sqrtf(-2.f * logf(u01(r2.y))) * cosf(kTwoPi * u01(r2.z));
+    float delta = g * fr->nonangle;
+    if (fr->use_prange) {
+        // S4 + S5: positron kinetic energy, then its range (gPET_kernals.cu:529-533); direction is sampled (usedirection 0)
+        const float ek = sample_ek_positron(fr->iso_coef + 8 * fr->type[s], rng);
+        positron_range(ph, x, y, z, 0.f, 0.f, 0.f, ek, false, rng);
+    }
+    a.x = b.x = x; a.y = b.y = y; a.z = b.z = z;
+    a.t = b.t = t_us;
+    a.eid = b.eid = (int)(unsigned)gk;
+    a.nscat = b.nscat = 0;
+    a.parn = (int)(unsigned)(2ull * gk); b.parn = (int)(unsigned)(2ull * gk + 1ull);
+    a.vx = vx; a.vy = vy; a.vz = vz;
+    a.E = kMC2 + delta * kMC2 * 0.5f;
+    rotate_dir(vx, vy, vz, -cosf(delta), phi2);
+    b.vx = vx; b.vy = vy; b.vz = vz;
+    b.E = kMC2 - delta * kMC2 * 0.5f;
+}
+
+// one thread per annihilation pair: photons 2k and 2k+1 of the queue
 __global__ void __launch_bounds__(kThreads) k_source(const SourceDev* __restrict__ fr, unsigned long long npairs,
                                                      PhantomDev ph, PhotonQueue q0, uint64_t seed) {
     const unsigned long long nph = 2ull * npairs;
     if (blockIdx.x == 0 && threadIdx.x == 0) *q0.count = (unsigned)min(nph, (unsigned long long)q0.capacity);
-    for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < nph && p < q0.capacity;
-         p += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long k = p >> 1;
-        const int which = (int)(p & 1ull);
-        int s = 0;
-        while (s < fr->nsource - 1 && k >= fr->cum_pairs[s]) s++;
-        const unsigned long long gk = fr->first_pair + k;
-        Philox rng(seed, gk, (uint32_t)kStageSource << 24);
-        uint4 r0 = rng.next();
-        // truncated-exponential decay time inside the frame (statistically identical to the reference's per-atom
-        // test ptime = -T_half*1.442695*log(U) < slice, gPET_kernals.cu:519-521)
-        double ud = u01d(r0.x, r0.y);
-        double ptime = -fr->tau_s[s] * log1p(-ud * fr->frac[s]);
-        double t_us = (fr->t0_s + ptime) * 1e6;
-        uint4 r1 = rng.next();
-        float x, y, z;
-        sample_shape(fr->shape[s], fr->coeff + 6 * s, r1, x, y, z);
-        // isotropic direction (gPET_kernals.cu:536-540)
-        float ct = -1.f + 2.f * u01(r0.z);
-        float phi = kTwoPi * u01(r0.w);
-        float st = sqrtf(1.f - ct * ct);
-        float vx = st * cosf(phi), vy = st * sinf(phi), vz = ct;
-        // acollinearity: delta = N(0,1) * sigma (gPET_kernals.cu:549-555)
-        uint4 r2 = rng.next();
-        float phi2 = kTwoPi * u01(r2.x);
-        float g = sqrtf(-2.f * logf(u01(r2.y))) * cosf(kTwoPi * u01(r2.z));
-        float delta = g * fr->nonangle;
-        if (fr->use_prange) {
-            // S4 + S5: positron kinetic energy, then its range (gPET_kernals.cu:529-533); direction is sampled (usedirection 0)
-            const float ek = sample_ek_positron(fr->iso_coef + 8 * fr->type[s], rng);
-            positron_range(ph, x, y, z, 0.f, 0.f, 0.f, ek, false, rng);
-        }
-        float E;
-        if (which == 0) {
-            E = kMC2 + delta * kMC2 * 0.5f;
-        } else {
-            rotate_dir(vx, vy, vz, -cosf(delta), phi2);
-            E = kMC2 - delta * kMC2 * 0.5f;
-        }
-        q0.pos_e[p] = make_float4(x, y, z, E);
-        q0.dir_n[p] = make_float4(vx, vy, vz, __int_as_float(0));
-        q0.t[p] = t_us;
-        q0.ids[p] = make_int2((int)(unsigned)gk, (int)(unsigned)(2ull * gk + which));
+    for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < npairs && 2ull * k + 1ull < q0.capacity;
+         k += (unsigned long long)gridDim.x * blockDim.x) {
+        Photon a, b;
+        source_pair(fr, ph, seed, k, a, b);
+        store_photon(q0, (unsigned)(2ull * k), a);
+        store_photon(q0, (unsigned)(2ull * k + 1ull), b);
     }
 }
 
 // ------------------------------------------------------------------------------------------- P1: phantom transport
+// One Woodcock flight (gPET_kernals.cu:277-335).  Returns 0: still inside, 1: the photon leaves the stage alive (escaped,
+// keeping the overshoot position -- SURVEY quirk 2 -- or below the absorption energy after a Compton, which the reference
+// still hands to the detector stage -- quirk 3), 2: photo-absorbed (tof = -0.5 in the reference).
+__device__ __forceinline__ int phantom_flight(Photon& p, Philox& rng, const PhantomDev& ph, const TablesDev& tb, float eabs) {
+    uint4 r = rng.next();
+    int ie; float fe;
+    energy_index(tb, p.E, ie, fe);
+    float lammin = __fdividef(1.0f, lerp_table(tb.maj_phantom, ie, fe));
+    float s = -lammin * __logf(u01(r.x));
+    p.x = fmaf(s, p.vx, p.x); p.y = fmaf(s, p.vy, p.y); p.z = fmaf(s, p.vz, p.z);
+    p.t += (double)s * kInvSpeedOfLight;
+    int ix = (int)((p.x - ph.ox) * ph.idx), iy = (int)((p.y - ph.oy) * ph.idy), iz = (int)((p.z - ph.oz) * ph.idz);
+    if (ix <= 0 || ix >= ph.nx || iy <= 0 || iy >= ph.ny || iz <= 0 || iz >= ph.nz) return 1;
+    uint32_t vw = __ldg(ph.vox + ((size_t)iz * ph.ny + iy) * ph.nx + ix);
+    int mat = (int)(vw & 15u);
+    float rho = __uint_as_float(vw & ~15u);
+    Xs3 xs = lerp_xs(tb, mat, ie, fe);
+    float lamden = lammin * rho;
+    float prob = 1.0f - lamden * xs.tot;
+    float u = u01(r.y);
+    if (u < prob) return 0;
+    prob += lamden * xs.compt;
+    if (u < prob) {
+        // Compton with binding effects: cos(theta) from the cmpsf surface (gPET_kernals.cu:66-88)
+        float costh = surface_lookup(tb.cmpsf, mat, tb.cm_ncp, tb.cm_ne, p.E * tb.cm_ide, u01(r.z) * tb.cm_idcp);
+        float efrac = 1.0f / (1.0f + p.E * kIMC2 * (1.0f - costh));
+        float phi = kTwoPi * u01(r.w);
+        p.E *= efrac;
+        p.nscat++;
+        if (p.E < eabs) return 1;
+        rotate_dir(p.vx, p.vy, p.vz, costh, phi);
+        return 0;
+    }
+    prob += lamden * xs.rayl;
+    if (u < prob) {
+        float costh = surface_lookup(tb.rayff, mat, tb.rl_ncp, tb.rl_ne, p.E * tb.rl_ide, u01(r.z) * tb.rl_idcp);
+        float phi = kTwoPi * u01(r.w);
+        p.nscat++;
+        rotate_dir(p.vx, p.vy, p.vz, costh, phi);
+        return 0;
+    }
+    return 2;
+}
+
 __global__ void __launch_bounds__(kThreads) k_phantom(PhotonQueue q0, PhotonQueue q1, PhantomDev ph, TablesDev tb,
                                                       float eabs, uint64_t seed) {
     const unsigned n = min(*q0.count, q0.capacity);
     const unsigned stride = gridDim.x * blockDim.x;
     unsigned next = blockIdx.x * blockDim.x + threadIdx.x;
     bool active = false;
-    float x = 0, y = 0, z = 0, E = 0, vx = 0, vy = 0, vz = 0;
-    double t = 0;
-    int eid = 0, parn = 0, nscat = 0;
+    Photon p{};
     Philox rng(seed, 0, 0);
     while (true) {
         // ---- refill: idle lanes pull their next photon; deferred until a quarter of the warp is idle
@@ -277,10 +342,10 @@ __global__ void __launch_bounds__(kThreads) k_phantom(PhotonQueue q0, PhotonQueu
                 int2 id = q0.ids[next];
                 next += stride;
                 if (pe.w < 0.f || tt <= 0.0) continue;  // gPET_kernals.cu:272
-                x = pe.x; y = pe.y; z = pe.z; E = pe.w;
-                vx = dn.x; vy = dn.y; vz = dn.z; nscat = __float_as_int(dn.w);
-                t = tt; eid = id.x; parn = id.y;
-                rng = Philox(seed, (uint64_t)(uint32_t)parn, (uint32_t)kStagePhantom << 24);
+                p.x = pe.x; p.y = pe.y; p.z = pe.z; p.E = pe.w;
+                p.vx = dn.x; p.vy = dn.y; p.vz = dn.z; p.nscat = __float_as_int(dn.w);
+                p.t = tt; p.eid = id.x; p.parn = id.y;
+                rng = Philox(seed, (uint64_t)(uint32_t)p.parn, (uint32_t)kStagePhantom << 24);
                 active = true;
             }
             amask = __ballot_sync(kFull, active);
@@ -291,61 +356,13 @@ __global__ void __launch_bounds__(kThreads) k_phantom(PhotonQueue q0, PhotonQueu
         }
         bool done_alive = false;
         if (active) {
-            // ---- one Woodcock flight (gPET_kernals.cu:277-296)
-            uint4 r = rng.next();
-            int ie; float fe;
-            energy_index(tb, E, ie, fe);
-            float lammin = __fdividef(1.0f, lerp_table(tb.maj_phantom, ie, fe));
-            float s = -lammin * __logf(u01(r.x));
-            x = fmaf(s, vx, x); y = fmaf(s, vy, y); z = fmaf(s, vz, z);
-            t += (double)s * kInvSpeedOfLight;
-            int ix = (int)((x - ph.ox) * ph.idx), iy = (int)((y - ph.oy) * ph.idy), iz = (int)((z - ph.oz) * ph.idz);
-            if (ix <= 0 || ix >= ph.nx || iy <= 0 || iy >= ph.ny || iz <= 0 || iz >= ph.nz) {
-                done_alive = true;  // escaped: keeps the overshoot position
-            } else {
-                uint32_t vw = __ldg(ph.vox + ((size_t)iz * ph.ny + iy) * ph.nx + ix);
-                int mat = (int)(vw & 15u);
-                float rho = __uint_as_float(vw & ~15u);
-                Xs3 xs = lerp_xs(tb, mat, ie, fe);
-                float lamden = lammin * rho;
-                float prob = 1.0f - lamden * xs.tot;
-                float u = u01(r.y);
-                if (u >= prob) {
-                    prob += lamden * xs.compt;
-                    if (u < prob) {
-                        // Compton with binding effects: cos(theta) from the cmpsf surface (gPET_kernals.cu:66-88)
-                        float costh = surface_lookup(tb.cmpsf, mat, tb.cm_ncp, tb.cm_ne, E * tb.cm_ide, u01(r.z) * tb.cm_idcp);
-                        float efrac = 1.0f / (1.0f + E * kIMC2 * (1.0f - costh));
-                        float phi = kTwoPi * u01(r.w);
-                        E *= efrac;
-                        nscat++;
-                        if (E < eabs) done_alive = true;  // still handed to the detector stage
-                        else rotate_dir(vx, vy, vz, costh, phi);
-                    } else {
-                        prob += lamden * xs.rayl;
-                        if (u < prob) {
-                            float costh = surface_lookup(tb.rayff, mat, tb.rl_ncp, tb.rl_ne, E * tb.rl_ide, u01(r.z) * tb.rl_idcp);
-                            float phi = kTwoPi * u01(r.w);
-                            nscat++;
-                            rotate_dir(vx, vy, vz, costh, phi);
-                        } else {
-                            active = false;  // photoelectric absorption: history ends (tof = -0.5 in the reference)
-                        }
-                    }
-                }
-            }
+            const int r = phantom_flight(p, rng, ph, tb, eabs);
+            done_alive = r == 1;
+            if (r) active = false;
         }
         // ---- warp-aggregated append of the photons that left the phantom alive
         unsigned slot = warp_reserve(q1.count, done_alive ? 1u : 0u);
-        if (done_alive) {
-            if (slot < q1.capacity) {
-                q1.pos_e[slot] = make_float4(x, y, z, E);
-                q1.dir_n[slot] = make_float4(vx, vy, vz, __int_as_float(nscat));
-                q1.t[slot] = t;
-                q1.ids[slot] = make_int2(eid, parn);
-            }
-            active = false;
-        }
+        if (done_alive && slot < q1.capacity) store_photon(q1, slot, p);
     }
 }
 
@@ -393,52 +410,60 @@ __device__ __forceinline__ void compton_kn(float E, Philox& rng, float& efrac, f
     costh = 1.0f - (1.0f - efrac) / (efrac * e0);
 }
 
-// Panel entry (gPET_kernals.cu:963-1009): one thread per photon that left the phantom, convergent loop over the
-// panels; photons whose straight line crosses a panel's front face are appended -- already in that panel's local
-// frame, with the time of flight to the face added -- to the compact queue the transport kernel works on.
-// dir_n.w of the output carries the panel index.
-__global__ void __launch_bounds__(kThreads) k_panel_entry(PhotonQueue q1, DetectorDev det, PhotonQueue q2,
-                                                          unsigned* __restrict__ counters) {
-    extern __shared__ PanelDev s_panels[];
+// Panel entry (gPET_kernals.cu:963-1009): the first panel (in index order) whose front face the photon's straight line
+// crosses while moving along the panel's growth direction.  On success the photon is returned in that panel's local
+// frame with the time of flight to the face added; ov.w carries the panel index.
+__device__ __forceinline__ bool panel_entry(const PanelDev* __restrict__ s_panels, int npanels, const Photon& p,
+                                            float4& pe, float4& ov, double& t) {
+    for (int i = 0; i < npanels; i++) {
+        const PanelDev& pd = s_panels[i];
+        const float lvx = fmaf(p.vz, pd.uxz, fmaf(p.vy, pd.uxy, p.vx * pd.uxx));
+        if (!(lvx * pd.dirx >= 0.f)) continue;
+        const float rx = p.x - pd.ox, ry = p.y - pd.oy, rz = p.z - pd.oz;
+        const float lx = fmaf(rz, pd.uxz, fmaf(ry, pd.uxy, rx * pd.uxx));
+        const float q = __fdiv_rn(lx, lvx);
+        const float ly = fmaf(rz, pd.uyz, fmaf(ry, pd.uyy, rx * pd.uyx));
+        const float lvy = fmaf(p.vz, pd.uyz, fmaf(p.vy, pd.uyy, p.vx * pd.uyx));
+        const float y2 = fmaf(-q, lvy, ly);
+        if (!(fabsf(y2) < pd.ly / 2)) continue;
+        const float lz = fmaf(rz, pd.uzz, fmaf(ry, pd.uzy, rx * pd.uzx));
+        const float lvz = fmaf(p.vz, pd.uzz, fmaf(p.vy, pd.uzy, p.vx * pd.uzx));
+        const float z2 = fmaf(-q, lvz, lz);
+        if (!(fabsf(z2) < pd.lz / 2)) continue;
+        pe = make_float4(0.f, y2, z2, p.E);
+        ov = make_float4(lvx, lvy, lvz, __int_as_float(i));
+        t = p.t + (-(double)lx / (kSpeedOfLight * (double)lvx));
+        return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ void stage_panels(PanelDev* s_panels, const DetectorDev& det) {
     for (int i = threadIdx.x; i < det.npanels * (int)(sizeof(PanelDev) / 4); i += blockDim.x)
         reinterpret_cast<uint32_t*>(s_panels)[i] = reinterpret_cast<const uint32_t*>(det.panels)[i];
     __syncthreads();
+}
+
+// staged form: one thread per photon that left the phantom, appended to the compact queue the transport kernel works on
+__global__ void __launch_bounds__(kThreads) k_panel_entry(PhotonQueue q1, DetectorDev det, PhotonQueue q2,
+                                                          unsigned* __restrict__ counters) {
+    extern __shared__ PanelDev s_panels[];
+    stage_panels(s_panels, det);
     const unsigned n = min(*q1.count, q1.capacity);
     const unsigned nround = (n + 31u) & ~31u;  // whole warps stay in the loop for the collective append
     unsigned n_on_panel = 0;
-    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < nround; p += gridDim.x * blockDim.x) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
         bool ok = false;
         float4 pe = make_float4(0, 0, 0, 0), ov = make_float4(0, 0, 0, 0);
         double t = 0.0;
         int2 id = make_int2(0, 0);
-        if (p < n) {
-            pe = q1.pos_e[p];
-            float4 dn = q1.dir_n[p];
-            const double tt = q1.t[p];
-            id = q1.ids[p];
-            if (tt > 0.0) {
-                for (int i = 0; i < det.npanels; i++) {
-                    const PanelDev& pd = s_panels[i];
-                    float rx = pe.x - pd.ox, ry = pe.y - pd.oy, rz = pe.z - pd.oz;
-                    float lx = rx * pd.uxx + ry * pd.uxy + rz * pd.uxz;
-                    float ly = rx * pd.uyx + ry * pd.uyy + rz * pd.uyz;
-                    float lz = rx * pd.uzx + ry * pd.uzy + rz * pd.uzz;
-                    float lvx = dn.x * pd.uxx + dn.y * pd.uxy + dn.z * pd.uxz;
-                    float lvy = dn.x * pd.uyx + dn.y * pd.uyy + dn.z * pd.uyz;
-                    float lvz = dn.x * pd.uzx + dn.y * pd.uzy + dn.z * pd.uzz;
-                    if (lvx * pd.dirx >= 0.f) {
-                        float q = __fdiv_rn(lx, lvx);
-                        float y2 = ly - q * lvy, z2 = lz - q * lvz;
-                        if (fabsf(y2) < pd.ly / 2 && fabsf(z2) < pd.lz / 2) {
-                            pe = make_float4(0.f, y2, z2, pe.w);
-                            ov = make_float4(lvx, lvy, lvz, __int_as_float(i));
-                            t = tt + (-(double)lx / (kSpeedOfLight * (double)lvx));
-                            ok = true;
-                            break;
-                        }
-                    }
-                }
-            }
+        if (i < n) {
+            Photon p;
+            const float4 a = q1.pos_e[i], dn = q1.dir_n[i];
+            p.x = a.x; p.y = a.y; p.z = a.z; p.E = a.w; p.vx = dn.x; p.vy = dn.y; p.vz = dn.z;
+            p.t = q1.t[i];
+            id = q1.ids[i];
+            if (p.t > 0.0) ok = panel_entry(s_panels, det.npanels, p, pe, ov, t);
         }
         unsigned slot = warp_reserve(q2.count, ok ? 1u : 0u);
         if (ok) {
@@ -456,19 +481,123 @@ __global__ void __launch_bounds__(kThreads) k_panel_entry(PhotonQueue q1, Detect
     if (lane_id() == 0 && n_on_panel) atomicAdd(&counters[8], n_on_panel);
 }
 
-// Per-thread adder slots in shared memory, [slot][thread] so that a warp's accesses are conflict free.
+// Fused front end: source sampling (or the photon queue q0 in PSF mode) -> phantom transport -> panel entry, photon state
+// in registers from birth to the panel face; only the photons that enter a panel (about 0.4 of them in the shipped
+// geometry) ever reach HBM.  Same device functions and the same Philox counters as the staged kernels above, hence
+// identical photons.  Persistent warps: a lane is in one of three states, and the two expensive state changes (pair
+// generation, panel search) are run when enough lanes wait for them so that they execute nearly convergent.
+// gen_min / entry_min: waiting lanes that trigger pair generation / the panel search
+
+template <bool kFromQueue>
+__global__ void __launch_bounds__(kThreads) k_front(const SourceDev* __restrict__ fr, unsigned long long npairs, PhotonQueue q0,
+                                                    PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, uint64_t seed,
+                                                    PhotonQueue q2, unsigned* __restrict__ q1_count,
+                                                    unsigned* __restrict__ counters, int gen_min, int entry_min) {
+    extern __shared__ PanelDev s_panels[];
+    stage_panels(s_panels, det);
+    enum { NEED = 0, FLY = 1, ESC = 2 };
+    const unsigned lane = lane_id();
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned nunits = kFromQueue ? min(*q0.count, q0.capacity) : (unsigned)min(npairs, (unsigned long long)(q2.capacity / 2));
+    unsigned* __restrict__ ticket = counters + 11;
+    if (!kFromQueue && blockIdx.x == 0 && threadIdx.x == 0) *q0.count = 2u * nunits;
+    int state = NEED;
+    bool has_b = false, exhausted = false;
+    Photon p{}, b{};
+    unsigned n_out = 0, n_on = 0;
+    Philox rng(seed, 0, 0);
+    while (true) {
+        if (!kFromQueue && state == NEED && has_b) {   // second photon of the pair
+            p = b;
+            has_b = false;
+            rng = Philox(seed, (uint64_t)(uint32_t)p.parn, (uint32_t)kStagePhantom << 24);
+            state = FLY;
+        }
+        unsigned need = __ballot_sync(kFull, state == NEED);
+        unsigned fly = __ballot_sync(kFull, state == FLY);
+        if (!exhausted && need && (__popc(need) >= gen_min || fly == 0)) {
+            const unsigned cnt = __popc(need);
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(ticket, cnt);
+            base = __shfl_sync(kFull, base, 0);
+            if (state == NEED) {
+                const unsigned idx = base + __popc(need & lt_mask);
+                if (idx < nunits) {
+                    bool live = true;
+                    if (kFromQueue) {
+                        const float4 pe = __ldcs(q0.pos_e + idx), dn = __ldcs(q0.dir_n + idx);
+                        p.t = __ldcs(q0.t + idx);
+                        const int2 id = __ldcs(q0.ids + idx);
+                        p.x = pe.x; p.y = pe.y; p.z = pe.z; p.E = pe.w;
+                        p.vx = dn.x; p.vy = dn.y; p.vz = dn.z; p.nscat = __float_as_int(dn.w);
+                        p.eid = id.x; p.parn = id.y;
+                        live = !(pe.w < 0.f || p.t <= 0.0);  // gPET_kernals.cu:272
+                    } else {
+                        source_pair(fr, ph, seed, idx, p, b);
+                        has_b = true;
+                    }
+                    if (live) {
+                        rng = Philox(seed, (uint64_t)(uint32_t)p.parn, (uint32_t)kStagePhantom << 24);
+                        state = FLY;
+                    }
+                }
+            }
+            if (base + cnt >= nunits) exhausted = true;
+        }
+        if (state == FLY) {
+            const int r = phantom_flight(p, rng, ph, tb, eabs);
+            if (r == 1) state = ESC;
+            else if (r == 2) state = NEED;
+        }
+        const unsigned esc = __ballot_sync(kFull, state == ESC);
+        fly = __ballot_sync(kFull, state == FLY);
+        if (esc && (__popc(esc) >= entry_min || fly == 0)) {
+            bool ok = false;
+            float4 pe = make_float4(0, 0, 0, 0), ov = make_float4(0, 0, 0, 0);
+            double t = 0.0;
+            if (state == ESC) {
+                n_out++;
+                ok = panel_entry(s_panels, det.npanels, p, pe, ov, t);
+                state = NEED;
+            }
+            const unsigned slot = warp_reserve(q2.count, ok ? 1u : 0u);
+            if (ok) {
+                n_on++;
+                if (slot < q2.capacity) {
+                    q2.pos_e[slot] = pe;
+                    q2.dir_n[slot] = ov;
+                    q2.t[slot] = t;
+                    q2.ids[slot] = make_int2(p.eid, p.parn);
+                }
+            }
+        }
+        if (exhausted && __ballot_sync(kFull, state != NEED || has_b) == 0) break;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_out += __shfl_xor_sync(kFull, n_out, o);
+        n_on += __shfl_xor_sync(kFull, n_on, o);
+    }
+    if (lane == 0) {
+        if (n_out) atomicAdd(q1_count, n_out);
+        if (n_on) atomicAdd(&counters[8], n_on);
+    }
+}
+
+// Per-thread adder slots in shared memory, [slot][thread] so that a warp's accesses are conflict free.  A slot is one
+// crystal of the photon's panel: key = (module << 16) | crystal-in-module (a photon never leaves its panel).
 struct SlotsSmem {
-    int site[kSlots][kThreads];
+    int key[kSlots][kThreads];
     float E[kSlots][kThreads], x[kSlots][kThreads], y[kSlots][kThreads], z[kSlots][kThreads];
     double t[kSlots][kThreads];
 };
 
 // D1 adder (gPET_kernals.cu:737-755): merge hits of the same crystal; energy-weighted centroid with the
 // contraction spelled out: (x_i*E_i + x*E)/(E_i+E) = fma(x_i, E_i, x*E) / (E_i + E)
-__device__ __forceinline__ bool adder(SlotsSmem& sl, int& n, int site, float E, float x, float y, float z, double t) {
+__device__ __forceinline__ bool adder(SlotsSmem& sl, int& n, int key, float E, float x, float y, float z, double t) {
     const int tid = threadIdx.x;
     for (int k = 0; k < n; k++) {
-        if (sl.site[k][tid] == site) {
+        if (sl.key[k][tid] == key) {
             const float ek = sl.E[k][tid];
             const float es = __fadd_rn(ek, E);
             sl.x[k][tid] = __fdiv_rn(__fmaf_rn(sl.x[k][tid], ek, __fmul_rn(x, E)), es);
@@ -479,58 +608,101 @@ __device__ __forceinline__ bool adder(SlotsSmem& sl, int& n, int site, float E, 
         }
     }
     if (n >= kSlots) return false;
-    sl.site[n][tid] = site; sl.E[n][tid] = E; sl.x[n][tid] = x; sl.y[n][tid] = y; sl.z[n][tid] = z; sl.t[n][tid] = t;
+    sl.key[n][tid] = key; sl.E[n][tid] = E; sl.x[n][tid] = x; sl.y[n][tid] = y; sl.z[n][tid] = z; sl.t[n][tid] = t;
     n++;
     return true;
 }
 
-// Photon transport inside a panel (gPET_kernals.cu:1018-1192) over the compact panel-entry queue, persistent warps with
-// lane refill; adder on the fly, readout (gPET_kernals.cu:756-813) when the photon is finished.
+// D2 readout (gPET_kernals.cu:756-813) of one finished photon: merges the slots whose key agrees at the readout level
+// (depth 0/1: the whole panel, 2: module, else crystal); returns the bit mask of the slots merged away.
+__device__ __forceinline__ unsigned readout_merge(SlotsSmem& sl, int nslot, int depth, int rpolicy) {
+    const int tid = threadIdx.x;
+    unsigned deadmask = 0;
+    for (int i = 0; i < nslot - 1; i++) {
+        if (deadmask >> i & 1u) continue;
+        const int ki = sl.key[i][tid];
+        for (int j = i + 1; j < nslot; j++) {
+            if (deadmask >> j & 1u) continue;
+            const int kj = sl.key[j][tid];
+            const bool same = depth <= 1 ? true : depth == 2 ? (ki >> 16) == (kj >> 16) : ki == kj;
+            if (!same) continue;
+            const float Ei = sl.E[i][tid], Ej = sl.E[j][tid];
+            if (rpolicy == 1) {
+                const float es = __fadd_rn(Ei, Ej);
+                sl.x[i][tid] = __fdiv_rn(__fmaf_rn(sl.x[i][tid], Ei, __fmul_rn(sl.x[j][tid], Ej)), es);
+                sl.y[i][tid] = __fdiv_rn(__fmaf_rn(sl.y[i][tid], Ei, __fmul_rn(sl.y[j][tid], Ej)), es);
+                sl.z[i][tid] = __fdiv_rn(__fmaf_rn(sl.z[i][tid], Ei, __fmul_rn(sl.z[j][tid], Ej)), es);
+                sl.E[i][tid] = es;
+            } else if (!(Ei > Ej)) {
+                // winner-take-all: the larger energy wins the whole record (ties -> the later one)
+                sl.key[i][tid] = kj; sl.E[i][tid] = Ej; sl.x[i][tid] = sl.x[j][tid];
+                sl.y[i][tid] = sl.y[j][tid]; sl.z[i][tid] = sl.z[j][tid]; sl.t[i][tid] = sl.t[j][tid];
+            }
+            deadmask |= 1u << j;
+        }
+    }
+    return deadmask;
+}
+
+// Photon transport inside a panel (gPET_kernals.cu:1018-1192) over the compact panel-entry queue.  Persistent warps;
+// a lane whose photon is finished reads it out (adder slots -> events) and pulls the next photon from a global ticket
+// counter (one atomic per warp and refill), so that lanes stay busy until the queue is empty whatever the lengths of
+// their histories.  Adder on the fly, readout (gPET_kernals.cu:756-813) when the photon is finished.
+// refill_min: idle lanes that trigger a refill (amortises the ticket atomic and the queue loads)
+
 __global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs,
                                                           int rdepth, int rpolicy, int record_hits, HitBuffer hits, EventSoA ev,
-                                                          unsigned* __restrict__ counters, uint64_t seed) {
+                                                          unsigned* __restrict__ counters, uint64_t seed, int refill_min) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     SlotsSmem& sl = *reinterpret_cast<SlotsSmem*>(s_raw);
     PanelDev* s_panels = reinterpret_cast<PanelDev*>(s_raw + sizeof(SlotsSmem));
-    for (int i = threadIdx.x; i < det.npanels * (int)(sizeof(PanelDev) / 4); i += blockDim.x)
-        reinterpret_cast<uint32_t*>(s_panels)[i] = reinterpret_cast<const uint32_t*>(det.panels)[i];
-    __syncthreads();
+    stage_panels(s_panels, det);
 
     const int tid = threadIdx.x;
+    const unsigned lane = lane_id();
+    const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned n = min(*q2.count, q2.capacity);
-    const unsigned stride = gridDim.x * blockDim.x;
-    unsigned next = blockIdx.x * blockDim.x + threadIdx.x;
-    const int crysPerPanel = det.moduleN * det.crystalN;
+    unsigned* __restrict__ ticket = counters + 10;
     const int depth = (rdepth != 3 && rpolicy == 1) ? 2 : rdepth;
-    bool active = false;
+    bool active = false, exhausted = false;
     float x = 0, y = 0, z = 0, E = 0, vx = 0, vy = 0, vz = 0;
     double t = 0;
     int eid = 0, parn = 0, pa = 0, nslot = 0;
     unsigned n_drop_adder = 0;
     Philox rng(seed, 0, 0);
     while (true) {
-        // ---- refill from the compact queue: cheap, so idle lanes are topped up as soon as a quarter of the warp idles
+        // ---- refill idle lanes from the ticket counter
         unsigned amask = __ballot_sync(kFull, active);
-        unsigned wmask = __ballot_sync(kFull, !active && next < n);
-        if (wmask && (__popc(wmask) >= 8 || amask == 0)) {
-            if (!active && next < n) {
-                float4 pe = q2.pos_e[next];
-                float4 dn = q2.dir_n[next];
-                t = q2.t[next];
-                int2 id = q2.ids[next];
-                next += stride;
-                x = pe.x; y = pe.y; z = pe.z; E = pe.w;
-                vx = dn.x; vy = dn.y; vz = dn.z; pa = __float_as_int(dn.w);
-                eid = id.x; parn = id.y;
-                rng = Philox(seed, (uint64_t)(uint32_t)parn, (uint32_t)kStageDetector << 24);
-                nslot = 0;
-                active = true;
+        if (!exhausted && (__popc(~amask) >= refill_min || amask == 0)) {
+            const unsigned need = ~amask;
+            const unsigned cnt = __popc(need);
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(ticket, cnt);
+            base = __shfl_sync(kFull, base, 0);
+            if (!active) {
+                const unsigned idx = base + __popc(need & lt_mask);
+                if (idx < n) {
+                    const float4 pe = __ldcs(q2.pos_e + idx);
+                    const float4 dn = __ldcs(q2.dir_n + idx);
+                    t = __ldcs(q2.t + idx);
+                    const int2 id = __ldcs(q2.ids + idx);
+                    x = pe.x; y = pe.y; z = pe.z; E = pe.w;
+                    vx = dn.x; vy = dn.y; vz = dn.z; pa = __float_as_int(dn.w);
+                    eid = id.x; parn = id.y;
+                    rng = Philox(seed, (uint64_t)(uint32_t)parn, (uint32_t)kStageDetector << 24);
+                    nslot = 0;
+                    active = true;
+                }
             }
+            if (base + cnt >= n) exhausted = true;
             amask = __ballot_sync(kFull, active);
         }
-        if (amask == 0) break;  // nothing active and nothing left to pull for any lane of this warp
+        if (amask == 0) {
+            if (exhausted) break;
+            continue;
+        }
         // up to two hits per flight (Compton deposit + absorption of the remainder), both at the same point
-        int nh = 0, h_mod = -1, h_cry = -1, h_type0 = 0;
+        int nh = 0, h_key = 0, h_type0 = 0;
         float h_E0 = 0.f, h_E1 = 0.f;
         bool finished = false;
         if (active) {
@@ -560,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, Detect
                         compton_kn(E, rng, efrac, costh);
                         float de = E * (1.0f - efrac);
                         float phi = kTwoPi * u01(r.z);
-                        if (m_id == 0) { h_mod = M_id; h_cry = L_id; h_type0 = 1; h_E0 = de; nh = 1; }
+                        if (m_id == 0) { h_type0 = 1; h_E0 = de; nh = 1; }
                         E -= de;
                         if (E < eabs) {
                             if (m_id == 0) { h_E1 = E; nh = 2; }  // type 2: remainder absorbed on the spot
@@ -575,17 +747,17 @@ __global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, Detect
                             float phi = kTwoPi * u01(r.w);
                             rotate_dir(vx, vy, vz, costh, phi);
                         } else {
-                            if (m_id == 0) { h_mod = M_id; h_cry = L_id; h_type0 = 4; h_E0 = E; nh = 1; }
+                            if (m_id == 0) { h_type0 = 4; h_E0 = E; nh = 1; }
                             finished = true;
                         }
                     }
                 }
+                h_key = (M_id << 16) | (L_id & 0xffff);
             }
             // adder on the fly
             if (nh >= 1) {
-                int site = pa * crysPerPanel + h_mod * det.crystalN + h_cry;
-                if (!adder(sl, nslot, site, h_E0, x, y, z, t)) n_drop_adder++;
-                if (nh == 2 && !adder(sl, nslot, site, h_E1, x, y, z, t)) n_drop_adder++;
+                if (!adder(sl, nslot, h_key, h_E0, x, y, z, t)) n_drop_adder++;
+                if (nh == 2 && !adder(sl, nslot, h_key, h_E1, x, y, z, t)) n_drop_adder++;
             }
         }
         // ---- hits: rows in file layout, warp-aggregated
@@ -593,68 +765,39 @@ __global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, Detect
             unsigned hmask = __ballot_sync(kFull, nh > 0);
             if (hmask) {
                 unsigned slot = warp_reserve(hits.count, (unsigned)nh);
-                for (int k = 0; k < nh; k++) {
-                    if (slot + k < hits.capacity) {
-                        int* hi = hits.id + 5ull * (slot + k);
-                        float* hf = hits.f + 5ull * (slot + k);
-                        hi[0] = parn; hi[1] = s_panels[pa].id; hi[2] = h_mod; hi[3] = h_cry; hi[4] = k ? 2 : h_type0;
-                        hf[0] = k ? h_E1 : h_E0; hf[1] = (float)t; hf[2] = x; hf[3] = y; hf[4] = z;
-                        hits.t[slot + k] = t;
+                if (nh > 0) {
+                    const int panel_id = s_panels[pa].id;
+                    for (int k = 0; k < nh; k++) {
+                        if (slot + k < hits.capacity) {
+                            int* hi = hits.id + 5ull * (slot + k);
+                            float* hf = hits.f + 5ull * (slot + k);
+                            hi[0] = parn; hi[1] = panel_id; hi[2] = h_key >> 16; hi[3] = h_key & 0xffff; hi[4] = k ? 2 : h_type0;
+                            hf[0] = k ? h_E1 : h_E0; hf[1] = (float)t; hf[2] = x; hf[3] = y; hf[4] = z;
+                            hits.t[slot + k] = t;
+                        }
                     }
                 }
             }
         }
         // ---- photon finished: readout (gPET_kernals.cu:756-813) and event append
-        const bool mine = finished && nslot > 0;
-        unsigned fmask = __ballot_sync(kFull, mine);
         if (finished) active = false;
+        const bool mine = finished && nslot > 0;
+        const unsigned fmask = __ballot_sync(kFull, mine);
         if (fmask) {
-            int cnt = 0;
-            const int panel_id = mine ? s_panels[pa].id : 0;
-            unsigned deadmask = 0;  // bit k: slot k merged away
-            if (mine) {
-                // rewrite the slot keys at readout level in place (site -> key), keeping the crystal site in a register copy
-                if (rdepth != 3) {
-                    for (int i = 0; i < nslot; i++) {
-                        if (deadmask >> i & 1u) continue;
-                        const int csi = sl.site[i][tid] - pa * crysPerPanel;
-                        const int keyi = depth == 0 ? 0 : depth == 1 ? panel_id : depth == 2 ? panel_id * det.moduleN + csi / det.crystalN
-                                                                                              : panel_id * crysPerPanel + csi;
-                        for (int j = i + 1; j < nslot; j++) {
-                            if (deadmask >> j & 1u) continue;
-                            const int csj = sl.site[j][tid] - pa * crysPerPanel;
-                            const int keyj = depth == 0 ? 0 : depth == 1 ? panel_id : depth == 2 ? panel_id * det.moduleN + csj / det.crystalN
-                                                                                                  : panel_id * crysPerPanel + csj;
-                            if (keyj != keyi) continue;
-                            const float Ei = sl.E[i][tid], Ej = sl.E[j][tid];
-                            if (rpolicy == 1) {
-                                const float es = __fadd_rn(Ei, Ej);
-                                sl.x[i][tid] = __fdiv_rn(__fmaf_rn(sl.x[i][tid], Ei, __fmul_rn(sl.x[j][tid], Ej)), es);
-                                sl.y[i][tid] = __fdiv_rn(__fmaf_rn(sl.y[i][tid], Ei, __fmul_rn(sl.y[j][tid], Ej)), es);
-                                sl.z[i][tid] = __fdiv_rn(__fmaf_rn(sl.z[i][tid], Ei, __fmul_rn(sl.z[j][tid], Ej)), es);
-                                sl.E[i][tid] = es;
-                            } else if (!(Ei > Ej)) {
-                                // winner-take-all: the larger energy wins the whole record (ties -> the later one)
-                                sl.site[i][tid] = sl.site[j][tid]; sl.E[i][tid] = Ej; sl.x[i][tid] = sl.x[j][tid];
-                                sl.y[i][tid] = sl.y[j][tid]; sl.z[i][tid] = sl.z[j][tid]; sl.t[i][tid] = sl.t[j][tid];
-                            }
-                            deadmask |= 1u << j;
-                        }
-                    }
-                }
-                cnt = nslot - __popc(deadmask);
-            }
+            unsigned deadmask = 0;
+            if (mine && nslot > 1 && rdepth != 3) deadmask = readout_merge(sl, nslot, depth, rpolicy);
+            const int cnt = mine ? nslot - __popc(deadmask) : 0;
             unsigned slot = warp_reserve(ev.count, (unsigned)cnt);
             if (mine) {
+                const int panel_id = s_panels[pa].id;
                 for (int k = 0; k < nslot; k++) {
                     if (deadmask >> k & 1u) continue;
                     if (slot < ev.capacity) {
-                        const int cs = sl.site[k][tid] - pa * crysPerPanel;
-                        const int mod = cs / det.crystalN;
-                        ev.parn[slot] = parn; ev.pann[slot] = panel_id; ev.modn[slot] = mod;
-                        ev.cryn[slot] = cs - mod * det.crystalN;
+                        const int key = sl.key[k][tid];
+                        const int mod = key >> 16, cry = key & 0xffff;
+                        ev.parn[slot] = parn; ev.pann[slot] = panel_id; ev.modn[slot] = mod; ev.cryn[slot] = cry;
                         ev.siten[slot] = depth == 0 ? 0 : depth == 1 ? panel_id : depth == 2 ? panel_id * det.moduleN + mod
-                                                                                            : panel_id * crysPerPanel + cs;
+                                                                                            : (panel_id * det.moduleN + mod) * det.crystalN + cry;
                         ev.eventid[slot] = eid;
                         ev.t[slot] = sl.t[k][tid]; ev.E[slot] = sl.E[k][tid];
                         ev.x[slot] = sl.x[k][tid]; ev.y[slot] = sl.y[k][tid]; ev.z[slot] = sl.z[k][tid];
@@ -669,7 +812,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, Detect
     unsigned b = n_drop_adder;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(kFull, b, o);
-    if (lane_id() == 0 && b) atomicAdd(&counters[9], b);
+    if (lane == 0 && b) atomicAdd(&counters[9], b);
 }
 
 // ------------------------------------------------------------------------------------------- host AoS <-> queue
@@ -737,6 +880,12 @@ __global__ void __launch_bounds__(kThreads) k_psf_positron(const gpet_photon* __
     }
 }
 
+// launch-shape knobs, overridable from the environment for tuning runs (tools/kprof.py); defaults are the tuned values
+int tune(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
 template <typename K>
 int persistent_grid(K kernel, int num_sms, size_t smem) {
     int per_sm = 1;
@@ -750,8 +899,7 @@ int persistent_grid(K kernel, int num_sms, size_t smem) {
 // ================================================================================================ launchers
 int launch_source(const SourceDev* frame_dev, unsigned long long npairs, PhantomDev ph, PhotonQueue q0, uint64_t seed,
                   int num_sms, cudaStream_t s) {
-    unsigned long long nph = 2ull * npairs;
-    unsigned long long blocks = (nph + kThreads - 1) / kThreads;
+    unsigned long long blocks = (npairs + kThreads - 1) / kThreads;
     unsigned long long maxb = (unsigned long long)num_sms * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
@@ -777,29 +925,68 @@ int launch_phantom(PhotonQueue q0, PhotonQueue q1, PhantomDev ph, TablesDev tb, 
     return 1;
 }
 
-int launch_detector(PhotonQueue q1, PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth,
-                    int readout_policy, int record_hits, HitBuffer hits, EventSoA ev, unsigned int* counters, uint64_t seed,
-                    int num_sms, cudaStream_t s) {
+int launch_panel_entry(PhotonQueue q1, PhotonQueue q2, DetectorDev det, unsigned int* counters, int num_sms, cudaStream_t s) {
     const size_t smem_panels = (size_t)det.npanels * sizeof(PanelDev);
-    const size_t smem = sizeof(SlotsSmem) + smem_panels;
-    static int grid = 0, grid_entry = 0;
+    static int grid = 0;
+    static size_t grid_smem = 0;
+    if (!grid || grid_smem != smem_panels) {
+        if (smem_panels > 48 * 1024)
+            cudaFuncSetAttribute(k_panel_entry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panels);
+        grid = persistent_grid(k_panel_entry, num_sms, smem_panels);
+        grid_smem = smem_panels;
+    }
+    cudaMemsetAsync(q2.count, 0, sizeof(unsigned), s);
+    cudaMemsetAsync(counters + 8, 0, sizeof(unsigned), s);   // photons on a panel
+    GPET_LAUNCH("k_panel_entry", s, k_panel_entry<<<grid, kThreads, smem_panels, s>>>(q1, det, q2, counters));
+    return 1;
+}
+
+int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQueue q0, PhotonQueue q1, PhotonQueue q2,
+                 PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, unsigned int* counters, uint64_t seed, int num_sms,
+                 cudaStream_t s) {
+    const size_t smem_panels = (size_t)det.npanels * sizeof(PanelDev);
+    static int grid[2] = {0, 0};
+    static size_t grid_smem = 0;
+    if (!grid[0] || grid_smem != smem_panels) {
+        if (smem_panels > 48 * 1024) {
+            cudaFuncSetAttribute(k_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panels);
+            cudaFuncSetAttribute(k_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panels);
+        }
+        grid[0] = persistent_grid(k_front<false>, num_sms, smem_panels);
+        grid[1] = persistent_grid(k_front<true>, num_sms, smem_panels);
+        grid_smem = smem_panels;
+    }
+    const int gen_min = tune("GPET_GEN_MIN", 12), entry_min = tune("GPET_ENTRY_MIN", 12);
+    cudaMemsetAsync(q1.count, 0, sizeof(unsigned), s);       // photons that left the phantom (tally only: q1 is not filled)
+    cudaMemsetAsync(q2.count, 0, sizeof(unsigned), s);
+    cudaMemsetAsync(counters + 8, 0, sizeof(unsigned), s);   // photons on a panel
+    cudaMemsetAsync(counters + 11, 0, sizeof(unsigned), s);  // k_front's ticket
+    if (frame_dev) {
+        GPET_LAUNCH("k_front", s, k_front<false><<<grid[0], kThreads, smem_panels, s>>>(frame_dev, npairs, q0, ph, tb, det, eabs, seed, q2,
+                                                                                      q1.count, counters, gen_min, entry_min));
+    } else {
+        GPET_LAUNCH("k_front<queue>", s, k_front<true><<<grid[1], kThreads, smem_panels, s>>>(nullptr, 0ull, q0, ph, tb, det, eabs, seed, q2,
+                                                                                            q1.count, counters, gen_min, entry_min));
+    }
+    return 1;
+}
+
+int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
+                    int record_hits, HitBuffer hits, EventSoA ev, unsigned int* counters, uint64_t seed, int num_sms,
+                    cudaStream_t s) {
+    const size_t smem = sizeof(SlotsSmem) + (size_t)det.npanels * sizeof(PanelDev);
+    static int grid = 0;
     static size_t grid_smem = 0;
     if (!grid || grid_smem != smem) {
         cudaFuncSetAttribute(k_detector, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (smem_panels > 48 * 1024)
-            cudaFuncSetAttribute(k_panel_entry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panels);
         grid = persistent_grid(k_detector, num_sms, smem);
-        grid_entry = persistent_grid(k_panel_entry, num_sms, smem_panels);
         grid_smem = smem;
     }
-    // q2.count, hits.count, ev.count and the two tallies are adjacent words of the counter block? no: reset one by one
-    cudaMemsetAsync(q2.count, 0, sizeof(unsigned), s);
     cudaMemsetAsync(hits.count, 0, 2 * sizeof(unsigned), s);   // hits.count, ev.count (adjacent words of the counter block)
-    cudaMemsetAsync(counters + 8, 0, 2 * sizeof(unsigned), s);
-    GPET_LAUNCH("k_panel_entry", s, k_panel_entry<<<grid_entry, kThreads, smem_panels, s>>>(q1, det, q2, counters));
-    GPET_LAUNCH("k_detector", s, k_detector<<<grid, kThreads, smem, s>>>(q2, det, tb, eabs, readout_depth, readout_policy, record_hits, hits, ev, counters,
-                                           seed));
-    return 2;
+    cudaMemsetAsync(counters + 9, 0, 2 * sizeof(unsigned), s);   // adder drops, k_detector's ticket
+    GPET_LAUNCH("k_detector", s, k_detector<<<grid, kThreads, smem, s>>>(q2, det, tb, eabs, readout_depth, readout_policy, record_hits, hits, ev,
+                                                                       counters, seed, tune("GPET_REFILL_MIN", 4)));
+    return 1;
 }
 
 int launch_photons_aos_to_queue(const void* aos, PhotonQueue q, unsigned int n, cudaStream_t s) {

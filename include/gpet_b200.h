@@ -223,11 +223,19 @@ int gpet_stage_psf(gpet_ctx* ctx, int64_t first, int64_t n);
 int gpet_stage_phantom(gpet_ctx* ctx);
 /* X1 photonde + D1 adder + D2 readout (gPET_kernals.cu:839-1233, 737-813): queue 1 -> hits + events. */
 int gpet_stage_detector(gpet_ctx* ctx);
+/* The three stages above up to the panel face in ONE kernel (what gpet_run uses): frame >= 0 samples that frame's pairs
+ * (setPosition), frame = -1 starts from queue 0 (PSF batches); then photon (gPET_kernals.cu:256-345) and the panel-entry
+ * prologue of photonde (:963-1009) with the photon state in registers; only photons that entered a panel are written,
+ * to queue 2 (panel-local frame).  Same Philox counters as the staged calls, hence the same photons; queues 0 and 1
+ * are not materialised (their counters still hold the tallies). */
+int gpet_stage_front(gpet_ctx* ctx, int64_t frame);
+/* X1 photonde after its panel-entry prologue + D1 adder + D2 readout: queue 2 -> hits + events. */
+int gpet_stage_panel_transport(gpet_ctx* ctx);
 /* D3-D7 blur, energywindow, sort by t, setSitenum, orderevents, deadtime, energywindow (gPET.cu:385-424)
  * + the coincidence sorter extension: events -> singles (time sorted) [+ coincidences]. */
 int gpet_stage_digitize(gpet_ctx* ctx);
 
-/* Host <-> device access to the stage buffers. which_queue: 0 after source, 1 after phantom. */
+/* Host <-> device access to the stage buffers. which_queue: 0 after source, 1 after phantom, 2 entered a panel. */
 int64_t gpet_queue_size(gpet_ctx* ctx, int which_queue);
 int gpet_put_photons(gpet_ctx* ctx, int which_queue, const gpet_photon* in, int64_t n);
 int64_t gpet_fetch_photons(gpet_ctx* ctx, int which_queue, gpet_photon* out, int64_t cap);

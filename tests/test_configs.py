@@ -66,9 +66,13 @@ def test_config2_photon_psf_full_size(tmp_path):
     assert co.size == st.coincidences and co.tobytes() == wco.astype(api.COINC_DTYPE).tobytes()
     # pairs are 1 us apart and the window is 10 ns: every coincidence is a true pair, eventid>>1 = pair index
     assert np.array_equal(co["a"]["eventid"] >> 1, co["b"]["eventid"] >> 1)
-    # back-to-back geometry: opposite panels (cyclic difference 4 of 8), up to a neighbour for edge/scatter cases
+    # back-to-back geometry: opposite panels (cyclic difference 4 of 8); the rest are the two photons in neighbours of
+    # the opposite panel, or one photon seen in two modules of the same panel (no minimum panel difference is set here)
     d = np.abs(co["a"]["pann"] - co["b"]["pann"]); d = np.minimum(d, 8 - d)
-    assert (d == 4).mean() > 0.9 and d.min() >= 3
+    assert (d == 4).mean() > 0.85
+    same_photon = co["a"]["eventid"] == co["b"]["eventid"]
+    # (a few hundred of the 2e6 photons scatter in the 1 cm of air and lose their partner's direction)
+    assert (d[~same_photon] >= 3).mean() > 0.999 and np.all(d[same_photon] <= 1)
     # event time = pair time + flight (22.5 cm / c = 0.75 ns) + transport in the crystal
     k = adder["eventid"] >> 1
     dt = adder["t"] - (k + 1.0)
@@ -167,9 +171,9 @@ def test_config4_mouse_phantom_256(tmp_path):
     # frames are consecutive time slices: the concatenated singles are globally time ordered
     assert np.all(np.diff(singles["t"]) >= 0)
     assert np.all(co["b"]["t"] - co["a"]["t"] < 0.01) and np.all(co["b"]["t"] >= co["a"]["t"])
-    # water + bone: a visible fraction of the photons scatters in the phantom
-    absorbed_or_scattered = 1.0 - st.photons_phantom_out / (2.0 * st.pairs)
-    assert 0.0005 < absorbed_or_scattered < 0.05
+    # water + bone, ~1.4 cm: photo-absorption in the phantom is a 1e-4 effect at 511 keV (scatter is checked below)
+    absorbed = 1.0 - st.photons_phantom_out / (2.0 * st.pairs)
+    assert 1e-6 < absorbed < 0.01
     # per-photon phantom parity on the first photons of frame 0 (bone voxels included), then spectra with another seed
     s = parity.Setup(0, phantom=(mat, den), size=size, seed=31337)
     s.ctx.put_photons(0, q0); s.ctx.stage_phantom()
@@ -216,9 +220,9 @@ def test_config5_ring_of_32_panels_with_20cm_water(tmp_path):
     assert st.frames >= 2 and abs(st.pairs - decays) < 6 * np.sqrt(decays)
     assert singles["pann"].min() == 0 and singles["pann"].max() == 31 and singles["modn"].max() < 52
     assert np.all(np.diff(singles["t"]) >= 0)
-    # 10 cm of water on average: most photons interact; 20-60 % of the escaping ones have scattered
+    # 10 cm of water on average: most photons scatter (checked below), a few per cent end by photo-absorption
     out_frac = st.photons_phantom_out / (2.0 * st.pairs)
-    assert 0.5 < out_frac < 0.98
+    assert 0.9 < out_frac < 0.999
     d = np.abs(co["a"]["pann"] - co["b"]["pann"]); d = np.minimum(d, 32 - d)
     assert co.size > 0 and d.min() >= 4
     # per-photon parity in the big phantom (multi-step Woodcock, several Comptons per history) and in the ring

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--flush", action="store_true")
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--staged", action="store_true", help="staged source/phantom/entry kernels instead of the fused front end")
     a = ap.parse_args()
     import torch
     from gpet_b200 import api
@@ -38,7 +39,11 @@ def main():
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
         def frame():
-            c.stage_source(0); c.stage_phantom(); c.stage_detector(); c.stage_digitize()
+            if a.staged:
+                c.stage_source(0); c.stage_phantom(); c.stage_detector()
+            else:
+                c.stage_front(0); c.stage_panel_transport()
+            c.stage_digitize()
 
         for _ in range(3):
             frame()
