@@ -59,20 +59,6 @@ int alloc_queue(gpet_ctx* c, PhotonQueue& q, size_t cap, unsigned* count) {
     return GPET_OK;
 }
 
-int alloc_events(gpet_ctx* c, EventSoA& e, size_t cap, unsigned* count) {
-    int r;
-    int** ints[6] = {&e.parn, &e.pann, &e.modn, &e.cryn, &e.siten, &e.eventid};
-    for (auto p : ints)
-        if ((r = dev_alloc(c, p, cap))) return r;
-    if ((r = dev_alloc(c, &e.t, cap))) return r;
-    float** flts[4] = {&e.E, &e.x, &e.y, &e.z};
-    for (auto p : flts)
-        if ((r = dev_alloc(c, p, cap))) return r;
-    e.count = count;
-    e.capacity = (unsigned)cap;
-    return GPET_OK;
-}
-
 int ensure_buffers(gpet_ctx* c) {
     if (c->dev_buffers) return GPET_OK;
     int r;
@@ -89,8 +75,9 @@ int ensure_buffers(gpet_ctx* c) {
     if ((r = dev_alloc(c, &c->hits.t, ch))) return r;
     c->hits.count = w.counters + 18;
     c->hits.capacity = (unsigned)ch;
-    if ((r = alloc_events(c, c->ev, ce, w.counters + 19))) return r;
-    if ((r = alloc_events(c, c->singles, ce, w.counters + 20))) return r;
+    if ((r = dev_alloc(c, &c->ev.rec, ce))) return r;
+    c->ev.count = w.counters + 19;
+    c->ev.capacity = (unsigned)ce;
     for (int k = 0; k < 2; k++) {
         if ((r = dev_alloc(c, &w.tkeys[k], ce))) return r;
         if ((r = dev_alloc(c, &w.tvals[k], ce))) return r;
@@ -104,6 +91,11 @@ int ensure_buffers(gpet_ctx* c) {
         CK(cudaMemset(w.lookback[k], 0, sort_lookback_words(ce) * sizeof(unsigned)));
         if ((r = dev_alloc(c, &w.scan_status[k], (size_t)w.max_tiles))) return r;
     }
+    if ((r = dev_alloc(c, &w.scan_status[2], (size_t)bucket_words() / 2048 + 1))) return r;
+    if ((r = dev_alloc(c, &w.bcount, (size_t)bucket_words()))) return r;
+    if ((r = dev_alloc(c, &w.bstart, (size_t)bucket_words()))) return r;
+    if ((r = dev_alloc(c, &w.bcur, (size_t)bucket_words()))) return r;
+    if ((r = dev_alloc(c, &w.minmax, 2))) return r;
     {
         unsigned char* p = nullptr;
         if ((r = dev_alloc(c, &p, 2 * sort_state_bytes()))) return r;
@@ -818,7 +810,7 @@ int gpet_stage_digitize(gpet_ctx* c) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     DigitizerDev d = digitizer_dev(c);
-    c->stats.kernel_launches += launch_digitize(c->ev, c->singles, c->singles_aos, c->coinc_aos, c->coinc_cap, d, c->ws, c->seed, c->num_sms, c->stream);
+    c->stats.kernel_launches += launch_digitize(c->ev, c->singles_aos, (unsigned)c->cap_events, c->coinc_aos, c->coinc_cap, d, c->ws, c->seed, c->num_sms, c->stream);
     CK(cudaGetLastError());
     return GPET_OK;
 }
@@ -864,9 +856,11 @@ int gpet_put_events(gpet_ctx* c, const gpet_event* in, int64_t n) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((uint64_t)n > c->cap_events) return fail(c, GPET_ERR_CAPACITY, "event list exceeds capacity");
-    if (n) CK(cudaMemcpyAsync(c->stage_aos, in, (size_t)n * sizeof(gpet_event), cudaMemcpyHostToDevice, c->stream));
-    c->stats.kernel_launches += launch_events_aos_to_soa(c->stage_aos, c->ev, (unsigned)n, c->stream);
-    CK(cudaGetLastError());
+    // the device buffer holds the records in the file layout: a plain copy
+    const unsigned n32 = (unsigned)n;
+    if (n) CK(cudaMemcpyAsync(c->ev.rec, in, (size_t)n * sizeof(gpet_event), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->ev.count, &n32, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));   // n32 lives on this stack frame
     return GPET_OK;
 }
 
@@ -877,8 +871,7 @@ int64_t gpet_fetch_events(gpet_ctx* c, gpet_event* out, int64_t cap) {
     if ((r = read_counters(c))) return r;
     int64_t n = std::min<int64_t>(std::min<unsigned>(c->h_counters[19], c->ev.capacity), cap);
     if (n <= 0) return 0;
-    c->stats.kernel_launches += launch_events_soa_to_aos(c->ev, c->stage_aos, c->stream);
-    CK(cudaMemcpyAsync(out, c->stage_aos, (size_t)n * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(out, c->ev.rec, (size_t)n * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return n;
 }
@@ -911,7 +904,7 @@ int64_t gpet_fetch_singles(gpet_ctx* c, gpet_event* out, int64_t cap) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((r = read_counters(c))) return r;
-    int64_t n = std::min<int64_t>(std::min<unsigned>(c->h_counters[3], c->singles.capacity), cap);
+    int64_t n = std::min<int64_t>(std::min<unsigned>(c->h_counters[3], (unsigned)c->cap_events), cap);
     if (n <= 0) return 0;
     CK(cudaMemcpyAsync(out, c->singles_aos, (size_t)n * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1021,7 +1014,7 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
     for (int k = 0; k < 32; k++) c->h_counters[k] = h[k];
     for (int k = 0; k < 4; k++) c->last_counts[k] = h[k];
     if (rs.resident) return GPET_OK;
-    const size_t ns = std::min<size_t>(h[3], c->singles.capacity), nc = std::min<size_t>(h[4], c->coinc_cap);
+    const size_t ns = std::min<size_t>(h[3], (size_t)c->cap_events), nc = std::min<size_t>(h[4], c->coinc_cap);
     const bool want_coinc = c->dig.coinc_window_us > 0.f;
     if ((r = arena_reserve(c, c->res_singles, ns * sizeof(gpet_event)))) return r;
     if (want_coinc && (r = arena_reserve(c, c->res_coinc, nc * sizeof(gpet_coincidence)))) return r;
@@ -1043,8 +1036,7 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
         }
         // note: adder.dat of the reference is written before blur; blur runs in place, so with blur enabled the
         // energies in this dump are the blurred ones
-        c->stats.kernel_launches += launch_events_soa_to_aos(c->ev, c->stage_aos, c->stream);
-        if ((r = append_device(c, join_path(rs.od, "adder.dat"), c->stage_aos, ne * sizeof(gpet_event), rs.tmp))) return r;
+        if ((r = append_device(c, join_path(rs.od, "adder.dat"), c->ev.rec, ne * sizeof(gpet_event), rs.tmp))) return r;
         FILE* fs = fopen(join_path(rs.od, "singles.dat").c_str(), "ab");
         if (!fs) return fail(c, GPET_ERR_IO, "cannot open singles.dat for appending");
         if (ns) fwrite(dst_s, sizeof(gpet_event), ns, fs);

@@ -54,7 +54,7 @@ struct gpet_ctx {
     bool dev_buffers = false, dev_tables = false, dev_phantom = false, dev_geo = false;
     gpet::PhotonQueue q[3]{};   // after source, after phantom, entered a panel
     gpet::HitBuffer hits{};
-    gpet::EventSoA ev{}, singles{};
+    gpet::EventBuf ev{};        // post adder/readout records of the frame ("adder.dat")
     gpet::DigitizerWorkspace ws{};
     void* singles_aos = nullptr;     // = singles_slot[out_slot]: 48-byte records of the frame being digitized
     void* coinc_aos = nullptr;       // = coinc_slot[out_slot]

@@ -36,14 +36,39 @@ struct HitBuffer {
     unsigned int capacity;
 };
 
-// Post-readout events / singles as SoA.
-struct EventSoA {
-    int* parn; int* pann; int* modn; int* cryn; int* siten; int* eventid;
-    double* t;
-    float* E; float* x; float* y; float* z;
+// Post-readout events / singles: 48-byte records in the reference's file layout (Event, gPET.h:87-92), 16-byte
+// aligned, so a record moves as three 16-byte vectors and adder.dat / singles.dat are plain copies of the buffers.
+struct EventRec {
+    int parn, pann, modn, cryn, siten, eventid;
+    double t;
+    float E, x, y, z;
+};
+static_assert(sizeof(EventRec) == 48, "EventRec must match gpet_event");
+
+struct EventBuf {
+    EventRec* rec;
     unsigned int* count;
     unsigned int capacity;
 };
+
+__device__ __forceinline__ void store_event_rec(EventRec* dst, const EventRec& r) {
+    const long long tb = __double_as_longlong(r.t);
+    int4* p = reinterpret_cast<int4*>(dst);
+    p[0] = make_int4(r.parn, r.pann, r.modn, r.cryn);
+    p[1] = make_int4(r.siten, r.eventid, (int)(unsigned)(tb & 0xffffffffll), (int)(unsigned)((unsigned long long)tb >> 32));
+    p[2] = make_int4(__float_as_int(r.E), __float_as_int(r.x), __float_as_int(r.y), __float_as_int(r.z));
+}
+
+__device__ __forceinline__ EventRec load_event_rec(const EventRec* src) {
+    const int4* p = reinterpret_cast<const int4*>(src);
+    const int4 a = p[0], b = p[1], c = p[2];
+    EventRec r;
+    r.parn = a.x; r.pann = a.y; r.modn = a.z; r.cryn = a.w;
+    r.siten = b.x; r.eventid = b.y;
+    r.t = __longlong_as_double((long long)(((unsigned long long)(unsigned)b.w << 32) | (unsigned)b.z));
+    r.E = __int_as_float(c.x); r.x = __int_as_float(c.y); r.y = __int_as_float(c.z); r.z = __int_as_float(c.w);
+    return r;
+}
 
 struct PanelDev {  // one panel, 128 B
     float ox, oy, oz;          // offset (front-face centre)

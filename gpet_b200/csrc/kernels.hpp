@@ -18,14 +18,20 @@ struct DigitizerWorkspace {
     unsigned int* lookback[2];     // sort_lookback_words(capacity) status words each (radix passes alternate between them)
     rsort::SortState* st_time;     // device-resident sort bookkeeping (histograms, tile counters, current buffer)
     rsort::SortState* st_site;
-    unsigned int* scan_status[2];  // max_tiles status words each: singles compaction, coincidence compaction
+    unsigned int* scan_status[3];  // status words of the chained scans: singles compaction, coincidence compaction (max_tiles
+                                   // each), slice counters of the bucket sort (bucket_words() / 2048)
+    unsigned int* bcount;          // bucket sort of the time keys: events per slice, slice starts, scatter cursors
+    unsigned int* bstart;          //   (bucket_words() entries each)
+    unsigned int* bcur;
+    unsigned long long* minmax;    // [0] smallest, [1] largest time key of the alive records
     unsigned int max_tiles;
     unsigned int capacity;
     unsigned int* order_t;         // event index in time order (first counters[1] entries alive)
     unsigned char* kill;           // per time-order position: 1 = removed by dead time
     unsigned int* coinc_cnt;       // per single: coincidences it opens
     // [0] n_in [1] after thresholder [2] after deadtime [3] singles [4] coincidences [6],[7] tile tickets of the two
-    // compactions [8] photons on a panel [9] adder drops; [16..20] queue 0, queue 1, hits, events, singles counts
+    // compactions [8] photons on a panel [9] adder drops [10],[11] photon tickets of k_detector / k_front [12] time sort
+    // fell back to LSD radix; [16..19] queue 0, queue 1, hits, events counts, [21] queue 2
     unsigned int* counters;
     unsigned long long* spectrum; int spectrum_bins; float spec_emin, spec_emax;
 };
@@ -33,11 +39,10 @@ struct DigitizerWorkspace {
 size_t sort_state_bytes();
 size_t sort_lookback_words(size_t capacity);   // status words one radix pass needs for `capacity` keys
 unsigned scan_tiles(size_t capacity);          // status words of the compaction scans
+unsigned bucket_words();                       // slice counters of the bucket sort
 
 // ---- digitizer (digitizer.cu) --------------------------------------------------------------------------
-int launch_events_aos_to_soa(const void* aos, EventSoA ev, unsigned int n, cudaStream_t s);
-int launch_events_soa_to_aos(EventSoA ev, void* aos, cudaStream_t s);
-int launch_digitize(EventSoA ev, EventSoA singles, void* singles_aos, void* coinc_aos, unsigned int coinc_cap,
+int launch_digitize(EventBuf ev, void* singles_aos, unsigned int singles_cap, void* coinc_aos, unsigned int coinc_cap,
                     const DigitizerDev& p, DigitizerWorkspace& ws, uint64_t seed, int num_sms, cudaStream_t s);
 
 // ---- transport (transport.cu) ----------------------------------------------------------------------------
@@ -53,7 +58,7 @@ int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQu
                  PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, unsigned int* counters, uint64_t seed, int num_sms,
                  cudaStream_t s);
 int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
-                    int record_hits, HitBuffer hits, EventSoA ev, unsigned int* counters, uint64_t seed,
+                    int record_hits, HitBuffer hits, EventBuf ev, unsigned int* counters, uint64_t seed,
                     int num_sms, cudaStream_t s);
 int launch_photons_aos_to_queue(const void* aos, PhotonQueue q, unsigned int n, cudaStream_t s);
 int launch_queue_to_photons_aos(PhotonQueue q, void* aos, cudaStream_t s);

@@ -1,14 +1,15 @@
-// Stable LSD radix sort of (key, value) pairs with 8-bit digits, one kernel per digit ("onesweep": chained scan with
-// decoupled look-back), hand-written for sm_100a.
+// Stable LSD radix sort of (key, value) pairs with 8-bit digits ("onesweep": one sweep per digit, chained scan with
+// decoupled look-back), hand-written for sm_100a, as DEVICE functions: the digitizer's two fallback kernels
+// (digitizer.cu: k_lsd_time_sort, k_dead_sorted) are persistent cooperative kernels that run all passes of a sort
+// with a grid barrier in between, so a sort that is not needed costs one empty launch.
 //
 // Replaces the reference's D2H -> std::sort -> H2D round trips (quicksort_h / orderevents, detector.cu:354-385).
 // Everything the sort needs to know at run time lives on the device: the element count, which of the two ping-pong
-// buffers currently holds the data (derived from the per-digit histograms).  The launch sequence is therefore
-// static and can sit inside a CUDA graph:
+// buffers currently holds the data (derived from the per-digit histograms).
 //
-//   producer kernel    writes keys/vals into buffer 0, accumulates the histograms of ALL digits (hist_accumulate) and
-//                      clears look-back array 0 (clear_lookback)
-//   k_onesweep x P     pass p: skip if one digit value holds every key (high bytes of fp64 times inside a short frame,
+//   producer step      writes keys/vals into buffer 0, accumulates the histograms of ALL digits (hist_add / hist_flush)
+//                      and clears look-back array 0 (clear_lookback)
+//   onesweep_pass x P  pass p: skip if one digit value holds every key (high bytes of fp64 times inside a short frame,
 //                      high bytes of site numbers); else tiles are claimed in order from a device counter, ranked
 //                      inside the tile (warp ballots => stable), chained to their predecessors through a per-digit
 //                      status word (aggregate / inclusive-prefix flags) and scattered.  Every pass clears the look-back
@@ -116,19 +117,45 @@ __device__ __forceinline__ unsigned current_buffer(const SortState* st, int npas
     return (unsigned)(npasses_before - __popc(m)) & 1u;
 }
 
+// ---- grid barrier of a cooperative launch (all blocks resident) ---------------------------------------------------
+// bar[0]: arrivals of the current generation, bar[1]: generation.  Zeroed once at allocation; self-resetting.
+__device__ __forceinline__ void grid_barrier(unsigned* bar) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned gen = ld_volatile(bar + 1);
+        __threadfence();
+        if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+            st_volatile(bar, 0u);
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (ld_volatile(bar + 1) == gen) {}
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 // ---- one pass -----------------------------------------------------------------------------------------------
+// Shared memory of a pass; one instance per kernel, handed to every call.
+struct PassSmem {
+    unsigned whist[kWarps][kBins];  // per-warp digit counters -> exclusive warp offsets
+    unsigned gbase[kBins];
+    unsigned wsum[kWarps];
+    unsigned s_tile;
+};
+
 template <typename KeyT>
-__global__ void __launch_bounds__(kThreads) k_onesweep(KeyT* keys0, KeyT* keys1, unsigned* vals0, unsigned* vals1,
-                                                       const unsigned* __restrict__ n_ptr, SortState* st,
-                                                       unsigned* lookback0, unsigned* lookback1, int pass) {
-    __shared__ unsigned whist[kWarps][kBins];  // per-warp digit counters -> exclusive warp offsets
-    __shared__ unsigned gbase[kBins];
-    __shared__ unsigned wsum[kWarps];
-    __shared__ unsigned s_tile;
+__device__ __forceinline__ void onesweep_pass(PassSmem& sm, KeyT* keys0, KeyT* keys1, unsigned* vals0, unsigned* vals1,
+                                              unsigned n, SortState* st, unsigned* lookback0, unsigned* lookback1, int pass) {
+    auto& whist = sm.whist;
+    auto& gbase = sm.gbase;
+    auto& wsum = sm.wsum;
+    unsigned& s_tile = sm.s_tile;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();  // the previous pass may still be reading the shared arrays
     // the tile ticket is requested first: its round trip overlaps the loads below (a skipped pass wastes it, harmlessly)
     if (tid == 0) s_tile = atomicAdd(&st->tile_counter[pass], 1u);
-    const unsigned n = *n_ptr;
     const unsigned ntiles = (n + kTile - 1) / kTile;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int shift = 8 * pass;
@@ -239,17 +266,28 @@ __global__ void __launch_bounds__(kThreads) k_onesweep(KeyT* keys0, KeyT* keys1,
     for (unsigned i = blockIdx.x * kThreads + tid; i < ntiles * kBins; i += gridDim.x * kThreads) lb_next[i] = 0u;
 }
 
+// one pass as a kernel of its own; `only_if` (may be null) points at a device word: the pass returns at once when it is 0
+template <typename KeyT>
+__global__ void __launch_bounds__(kThreads) k_onesweep(KeyT* keys0, KeyT* keys1, unsigned* vals0, unsigned* vals1,
+                                                       const unsigned* __restrict__ n_ptr, SortState* st,
+                                                       unsigned* lookback0, unsigned* lookback1, int pass,
+                                                       const unsigned* __restrict__ only_if) {
+    __shared__ PassSmem sm;
+    if (only_if && *only_if == 0u) return;
+    onesweep_pass<KeyT>(sm, keys0, keys1, vals0, vals1, *n_ptr, st, lookback0, lookback1, pass);
+}
+
 }  // namespace rsort
 
 // Issues the passes of a sort whose producer has already filled buffer 0, the histograms and look-back array 0.
-// Returns the number of launches.  The result is in buffer st->cur (device side).
+// Returns the number of launches.  Which buffer holds the result follows from the histograms (rsort::current_buffer).
 template <typename KeyT>
 inline int radix_sort_passes(KeyT* keys[2], unsigned* vals[2], const unsigned* n_dev, rsort::SortState* st,
-                             unsigned* lookback[2], int npasses, int grid, cudaStream_t s) {
+                             unsigned* lookback[2], int npasses, int grid, cudaStream_t s, const unsigned* only_if = nullptr) {
     for (int p = 0; p < npasses; p++)
         GPET_LAUNCH(sizeof(KeyT) == 8 ? "k_onesweep<u64>" : "k_onesweep<u32>", s,
                     rsort::k_onesweep<KeyT><<<grid, rsort::kThreads, 0, s>>>(keys[0], keys[1], vals[0], vals[1], n_dev, st,
-                                                                             lookback[0], lookback[1], p));
+                                                                             lookback[0], lookback[1], p, only_if));
     return npasses;
 }
 

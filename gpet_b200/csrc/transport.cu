@@ -651,7 +651,7 @@ __device__ __forceinline__ unsigned readout_merge(SlotsSmem& sl, int nslot, int 
 // refill_min: idle lanes that trigger a refill (amortises the ticket atomic and the queue loads)
 
 __global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs,
-                                                          int rdepth, int rpolicy, int record_hits, HitBuffer hits, EventSoA ev,
+                                                          int rdepth, int rpolicy, int record_hits, HitBuffer hits, EventBuf ev,
                                                           unsigned* __restrict__ counters, uint64_t seed, int refill_min) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     SlotsSmem& sl = *reinterpret_cast<SlotsSmem*>(s_raw);
@@ -794,13 +794,14 @@ __global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, Detect
                     if (deadmask >> k & 1u) continue;
                     if (slot < ev.capacity) {
                         const int key = sl.key[k][tid];
-                        const int mod = key >> 16, cry = key & 0xffff;
-                        ev.parn[slot] = parn; ev.pann[slot] = panel_id; ev.modn[slot] = mod; ev.cryn[slot] = cry;
-                        ev.siten[slot] = depth == 0 ? 0 : depth == 1 ? panel_id : depth == 2 ? panel_id * det.moduleN + mod
-                                                                                            : (panel_id * det.moduleN + mod) * det.crystalN + cry;
-                        ev.eventid[slot] = eid;
-                        ev.t[slot] = sl.t[k][tid]; ev.E[slot] = sl.E[k][tid];
-                        ev.x[slot] = sl.x[k][tid]; ev.y[slot] = sl.y[k][tid]; ev.z[slot] = sl.z[k][tid];
+                        EventRec r;
+                        r.parn = parn; r.pann = panel_id; r.modn = key >> 16; r.cryn = key & 0xffff;
+                        r.siten = depth == 0 ? 0 : depth == 1 ? panel_id : depth == 2 ? panel_id * det.moduleN + r.modn
+                                                                                     : (panel_id * det.moduleN + r.modn) * det.crystalN + r.cryn;
+                        r.eventid = eid;
+                        r.t = sl.t[k][tid]; r.E = sl.E[k][tid];
+                        r.x = sl.x[k][tid]; r.y = sl.y[k][tid]; r.z = sl.z[k][tid];
+                        store_event_rec(ev.rec + slot, r);
                     }
                     slot++;
                 }
@@ -972,7 +973,7 @@ int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQu
 }
 
 int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
-                    int record_hits, HitBuffer hits, EventSoA ev, unsigned int* counters, uint64_t seed, int num_sms,
+                    int record_hits, HitBuffer hits, EventBuf ev, unsigned int* counters, uint64_t seed, int num_sms,
                     cudaStream_t s) {
     const size_t smem = sizeof(SlotsSmem) + (size_t)det.npanels * sizeof(PanelDev);
     static int grid = 0;

@@ -70,6 +70,20 @@ def test_digitizer_bit_exact_late_times(ctx):
         assert list(counts) == list(wcounts) and parity.events_equal(got, want)
 
 
+@pytest.mark.parametrize("dead_type", [0, 1])
+def test_digitizer_clustered_times_take_the_lsd_fallback(ctx, dead_type):
+    """Times clustered far below the key range overfill one slice of the bucket sort: the device switches to the LSD radix
+    passes (counters[12]) and the result is still the oracle's, bit for bit."""
+    rng = np.random.default_rng(77)
+    ev = parity.random_events(50000, rng, tmax=1.0, nsites=936, tie_fraction=0.05)
+    ev["t"] += 1.0e6                       # 50 000 events inside one microsecond ...
+    ev["t"][:3] = [2.0, 7.5e11, 3.0]      # ... and three outliers that stretch the range by 18 orders of magnitude
+    got, counts, co, want, wcounts, wco = run_both(ctx, ev, dead_type=dead_type, dead_time_us=1e-4, coinc_window_us=1e-5)
+    assert list(counts) == list(wcounts)
+    assert parity.events_equal(got, want)
+    assert co.tobytes() == wco.tobytes()
+
+
 def test_digitizer_negative_site_and_unsorted_input(ctx):
     rng = np.random.default_rng(11)
     ev = parity.random_events(5000, rng, tmax=500.0, nsites=64)
