@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import shutil
 import statistics
@@ -200,15 +201,16 @@ ALG_BYTES = {
     "k_phantom": lambda c: 48 * c["photons"] + 48 * c["q1"],
     "k_panel_entry": lambda c: 48 * c["q1"] + 48 * c["on_panel"],
     "k_detector": lambda c: 48 * c["on_panel"] + 48 * c["hits"] + 44 * c["events"],
-    "k_prep": lambda c: 12 * c["events"] + 12 * c["events"],
-    "k_onesweep<u64>": lambda c: 24 * c["events"],
-    "k_site_keys": lambda c: 16 * c["alive"] + 12 * c["alive"],
-    "k_onesweep<u32>": lambda c: 16 * c["alive"],
-    "k_deadtime": lambda c: 20 * c["alive"] + c["alive"],
-    "k_emit_singles": lambda c: 9 * c["alive"] + (44 + 44 + 48) * c["singles"],
+    # digitizer: 48-byte records in, per-event side arrays (u64 time key, site, arrival rank | window flag)
+    "k_prep": lambda c: 48 * c["events"] + 8 * c["events"] + 8 * c["alive"],
+    "k_bucket_scan": lambda c: 8 * 2 ** max(6, math.ceil(math.log2(max(c["events"], 2))) - 3),
+    "k_bucket_scatter": lambda c: 8 * c["events"] + 8 * c["alive"] + 16 * c["alive"],
+    "k_bucket_rank": lambda c: 16 * c["alive"] + 16 * c["alive"],
+    "k_deadtime_chain": lambda c: 12 * c["alive"] + c["alive"],
+    "k_emit_singles": lambda c: 16 * c["alive"] + 48 * c["singles"] + (48 + 12) * c["singles"],
     "k_coinc_count": lambda c: 12 * c["singles"] + 4 * c["singles"],
-    "k_coinc_emit": lambda c: 4 * c["singles"] + 192 * c["coinc"],
-    "k_begin": lambda c: 20000,
+    "k_coinc_emit": lambda c: 4 * c["singles"] + 8 * c["coinc"],
+    "k_begin": lambda c: 4 * 2 ** 19,
 }
 
 
@@ -262,6 +264,8 @@ def main():
         ctx.set_seed(0x67504554 + 1000003 * rank)   # disjoint Philox keys per rank: independent decay histories
         ctx.load_config_file(ex / "input_PET.in", base_dir=ex)
         ctx.set_digitizer(coinc_window_us=0.01)
+        # coincidences reach the host as index pairs into the singles list (8 B each instead of two copied records)
+        ctx.set_coincidence_format(api.Context.COINC_PAIRS)
         ctx.set_spectrum(128, 0.0, 1.0e6)
         ctx.plan_frames(0)
         return ex, ctx
@@ -339,7 +343,7 @@ def main():
     st = m["e2e_stats"][-1]
     nframes = int(st.frames)
     h2d = nframes * 4096 + 64
-    d2h = int(st.singles * 48 + st.coincidences * 96 + 32 * 4 * st.frames)
+    d2h = int(st.singles * 48 + st.coincidences * 8 + 32 * 4 * st.frames)
 
     extra = None
     if not args.no_extra and world == 1 and args.source == DEFAULT_SOURCE:
@@ -408,7 +412,7 @@ def main():
                            "time_path": "fp64", "multi_gpu": "independent decay histories per rank (disjoint Philox keys), tallies all-reduced over NCCL"},
                 "clocks": clocks,
                 "e2e": {"value": m["e2e_pairs"] / (m["e2e_ms"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "timing": "wall clock around gpet_plan_frames + gpet_run (singles and coincidences delivered to pinned host memory), max over ranks"},
+                        "timing": "wall clock around gpet_plan_frames + gpet_run (singles as 48-byte records and coincidences as index pairs into them, delivered to pinned host memory), max over ranks"},
                 "gpu_launches": int(sum(s.kernel_launches for s in m["stats"])),
                 "roofline": roofline, "cpu_baseline": base,
                 "counters": {"pairs": int(s0.pairs), "hits": int(s0.hits), "events_adder": int(s0.events_adder),

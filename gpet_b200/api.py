@@ -126,6 +126,8 @@ _SIGS = {
     "gpet_run_resident": (C.c_int, [_P, C.POINTER(Stats)]),
     "gpet_result_singles": (C.c_int64, [_P, C.POINTER(_P)]),
     "gpet_result_coincidences": (C.c_int64, [_P, C.POINTER(_P)]),
+    "gpet_set_coincidence_format": (C.c_int, [_P, C.c_int]),
+    "gpet_result_coincidence_pairs": (C.c_int64, [_P, C.POINTER(_P)]),
     "gpet_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "gpet_get_spectrum": (C.c_int, [_P, _P, C.c_int]),
     "gpet_set_spectrum": (C.c_int, [_P, C.c_int, C.c_float, C.c_float]),
@@ -457,6 +459,20 @@ class Context:
             return np.zeros(0, COINC_DTYPE)
         buf = (C.c_char * (n * COINC_DTYPE.itemsize)).from_address(p.value)
         return np.frombuffer(buf, COINC_DTYPE, n).copy()
+
+    COINC_RECORDS, COINC_PAIRS = 0, 1
+
+    def set_coincidence_format(self, fmt):
+        self._ck(self._l.gpet_set_coincidence_format(self._h, int(fmt)))
+
+    def result_coincidence_pairs(self):
+        """(n, 2) uint32 indices into result_singles() (COINC_PAIRS mode)."""
+        p = C.c_void_p()
+        n = self._ck(self._l.gpet_result_coincidence_pairs(self._h, C.byref(p)))
+        if n == 0:
+            return np.zeros((0, 2), np.uint32)
+        buf = (C.c_char * (n * 8)).from_address(p.value)
+        return np.frombuffer(buf, np.uint32, 2 * n).reshape(n, 2).copy()
 
     def stats(self):
         st = Stats()

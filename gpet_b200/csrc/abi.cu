@@ -81,9 +81,13 @@ int ensure_buffers(gpet_ctx* c) {
     for (int k = 0; k < 2; k++) {
         if ((r = dev_alloc(c, &w.tkeys[k], ce))) return r;
         if ((r = dev_alloc(c, &w.tvals[k], ce))) return r;
-        if ((r = dev_alloc(c, &w.skeys[k], ce))) return r;
-        if ((r = dev_alloc(c, &w.svals[k], ce))) return r;
     }
+    if ((r = dev_alloc(c, &w.site_of, ce))) return r;
+    if ((r = dev_alloc(c, &w.aux, ce))) return r;
+    if ((r = dev_alloc(c, &w.bpay, ce))) return r;
+    if ((r = dev_alloc(c, &w.site_t, ce))) return r;
+    if ((r = dev_alloc(c, &w.stime, ce))) return r;
+    if ((r = dev_alloc(c, &w.span, ce))) return r;
     w.capacity = (unsigned)ce;
     w.max_tiles = scan_tiles(ce);
     for (int k = 0; k < 2; k++) {
@@ -94,14 +98,16 @@ int ensure_buffers(gpet_ctx* c) {
     if ((r = dev_alloc(c, &w.scan_status[2], (size_t)bucket_words() / 2048 + 1))) return r;
     if ((r = dev_alloc(c, &w.bcount, (size_t)bucket_words()))) return r;
     if ((r = dev_alloc(c, &w.bstart, (size_t)bucket_words()))) return r;
-    if ((r = dev_alloc(c, &w.bcur, (size_t)bucket_words()))) return r;
     if ((r = dev_alloc(c, &w.minmax, 2))) return r;
+    if ((r = dev_alloc(c, &w.grid_bar, 4))) return r;
+    CK(cudaMemset(w.grid_bar, 0, 4 * sizeof(unsigned)));
+    if ((r = dev_alloc(c, &c->d_pair_base, 2))) return r;
+    CK(cudaMemset(c->d_pair_base, 0, 2 * sizeof(unsigned)));
     {
         unsigned char* p = nullptr;
-        if ((r = dev_alloc(c, &p, 2 * sort_state_bytes()))) return r;
-        CK(cudaMemset(p, 0, 2 * sort_state_bytes()));
+        if ((r = dev_alloc(c, &p, sort_state_bytes()))) return r;
+        CK(cudaMemset(p, 0, sort_state_bytes()));
         w.st_time = reinterpret_cast<rsort::SortState*>(p);
-        w.st_site = reinterpret_cast<rsort::SortState*>(p + sort_state_bytes());
     }
     if ((r = dev_alloc(c, &w.order_t, ce))) return r;
     if ((r = dev_alloc(c, &w.kill, ce))) return r;
@@ -120,6 +126,9 @@ int ensure_buffers(gpet_ctx* c) {
             CK(cudaMalloc(&p, (size_t)c->coinc_cap * sizeof(gpet_coincidence)));
             c->allocs.push_back(p);
             c->coinc_slot[k] = p;
+            CK(cudaMalloc(&p, (size_t)c->coinc_cap * sizeof(uint2)));
+            c->allocs.push_back(p);
+            c->pairs_slot[k] = p;
             CK(cudaMallocHost((void**)&c->h_slot_counters[k], 32 * sizeof(unsigned)));
             CK(cudaEventCreateWithFlags(&c->ev_counters[k], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
@@ -373,6 +382,7 @@ void gpet_destroy(gpet_ctx* c) {
         }
         if (c->res_singles.p) cudaFreeHost(c->res_singles.p);
         if (c->res_coinc.p) cudaFreeHost(c->res_coinc.p);
+        if (c->res_pairs.p) cudaFreeHost(c->res_pairs.p);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         if (c->own_stream) cudaStreamDestroy(c->own_stream);
     }
@@ -810,7 +820,19 @@ int gpet_stage_digitize(gpet_ctx* c) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     DigitizerDev d = digitizer_dev(c);
-    c->stats.kernel_launches += launch_digitize(c->ev, c->singles_aos, (unsigned)c->cap_events, c->coinc_aos, c->coinc_cap, d, c->ws, c->seed, c->num_sms, c->stream);
+    DigitizerOut out{};
+    out.singles = c->singles_aos;
+    out.singles_cap = (unsigned)c->cap_events;
+    out.coinc_cap = c->coinc_cap;
+    if (c->in_run && c->coinc_format == GPET_COINC_PAIRS) {
+        // index pairs into the run's singles list: the base (singles of the earlier frames) travels on the device
+        out.pairs = c->pairs_slot[c->out_slot];
+        out.pair_base_in = c->d_pair_base + (c->run_frame & 1);
+        out.pair_base_out = c->d_pair_base + ((c->run_frame + 1) & 1);
+    } else {
+        out.coinc = c->coinc_aos;
+    }
+    c->stats.kernel_launches += launch_digitize(c->ev, out, d, c->ws, c->have_range ? &c->range : nullptr, c->seed, c->num_sms, c->stream);
     CK(cudaGetLastError());
     return GPET_OK;
 }
@@ -1016,16 +1038,21 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
     if (rs.resident) return GPET_OK;
     const size_t ns = std::min<size_t>(h[3], (size_t)c->cap_events), nc = std::min<size_t>(h[4], c->coinc_cap);
     const bool want_coinc = c->dig.coinc_window_us > 0.f;
+    const bool as_pairs = c->coinc_format == GPET_COINC_PAIRS;
+    PinnedArena& arena_c = as_pairs ? c->res_pairs : c->res_coinc;
+    const size_t rec_c = as_pairs ? 2 * sizeof(uint32_t) : sizeof(gpet_coincidence);
     if ((r = arena_reserve(c, c->res_singles, ns * sizeof(gpet_event)))) return r;
-    if (want_coinc && (r = arena_reserve(c, c->res_coinc, nc * sizeof(gpet_coincidence)))) return r;
+    if (want_coinc && (r = arena_reserve(c, arena_c, nc * rec_c))) return r;
     char* dst_s = c->res_singles.p + c->res_singles.size;
-    char* dst_c = want_coinc ? c->res_coinc.p + c->res_coinc.size : nullptr;
+    char* dst_c = want_coinc ? arena_c.p + arena_c.size : nullptr;
+    const size_t first_single = c->res_singles.size / sizeof(gpet_event);
     if (ns) CK(cudaMemcpyAsync(dst_s, c->singles_slot[slot], ns * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->copy_stream));
     if (want_coinc && nc)
-        CK(cudaMemcpyAsync(dst_c, c->coinc_slot[slot], nc * sizeof(gpet_coincidence), cudaMemcpyDeviceToHost, c->copy_stream));
+        CK(cudaMemcpyAsync(dst_c, as_pairs ? c->pairs_slot[slot] : c->coinc_slot[slot], nc * rec_c, cudaMemcpyDeviceToHost,
+                           c->copy_stream));
     CK(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
     c->res_singles.size += ns * sizeof(gpet_event);
-    if (want_coinc) c->res_coinc.size += nc * sizeof(gpet_coincidence);
+    if (want_coinc) arena_c.size += nc * rec_c;
     if (!rs.od.empty()) {
         // file dumps with the reference layouts (gPET.cu:367-383, 424): this path runs frame by frame (no pipelining)
         CK(cudaStreamSynchronize(c->copy_stream));
@@ -1044,7 +1071,17 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
         if (want_coinc) {
             FILE* fc = fopen(join_path(rs.od, "coincidences.dat").c_str(), "ab");
             if (!fc) return fail(c, GPET_ERR_IO, "cannot open coincidences.dat for appending");
-            if (nc) fwrite(dst_c, sizeof(gpet_coincidence), nc, fc);
+            if (nc && !as_pairs) fwrite(dst_c, sizeof(gpet_coincidence), nc, fc);
+            if (nc && as_pairs) {   // same file either way: gather the two singles of every pair
+                const gpet_event* sg = reinterpret_cast<const gpet_event*>(c->res_singles.p);
+                const uint32_t* pr = reinterpret_cast<const uint32_t*>(dst_c);
+                const size_t n_all = c->res_singles.size / sizeof(gpet_event);
+                for (size_t k = 0; k < nc; k++) {
+                    if (pr[2 * k] < first_single || pr[2 * k + 1] >= n_all) { fclose(fc); return fail(c, GPET_ERR_ARG, "coincidence pair out of range"); }
+                    fwrite(sg + pr[2 * k], sizeof(gpet_event), 1, fc);
+                    fwrite(sg + pr[2 * k + 1], sizeof(gpet_event), 1, fc);
+                }
+            }
             fclose(fc);
         }
     }
@@ -1068,6 +1105,14 @@ int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* sta
     CK(cudaStreamSynchronize(c->copy_stream));
     c->res_singles.size = 0;
     c->res_coinc.size = 0;
+    c->res_pairs.size = 0;
+    c->coinc_expanded.clear();
+    CK(cudaMemsetAsync(c->d_pair_base, 0, 2 * sizeof(unsigned), c->stream));
+    struct InRun {   // gpet_stage_digitize reads these while the run is in flight
+        gpet_ctx* c;
+        explicit InRun(gpet_ctx* c_) : c(c_) { c->in_run = true; c->run_frame = 0; }
+        ~InRun() { c->in_run = false; c->have_range = false; }
+    } in_run(c);
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -1097,7 +1142,16 @@ int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* sta
             st.pairs += c->frames[(size_t)f].npairs;
         }
         if ((rc = gpet_stage_panel_transport(c))) break;
-        if ((rc = gpet_stage_digitize(c))) break;
+        // source mode: event times lie in the frame's slice (plus a flight time far below a slice of the sort)
+        c->have_range = !psf_mode;
+        if (!psf_mode) {
+            const FramePlan& fp = c->frames[(size_t)f];
+            c->range = time_range_us(fp.t0_s * 1e6, (fp.t0_s + fp.dt_s) * 1e6);
+        }
+        c->run_frame = k;
+        rc = gpet_stage_digitize(c);
+        c->have_range = false;
+        if (rc) break;
         CK(cudaMemcpyAsync(c->h_slot_counters[slot], c->ws.counters, 32 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaEventRecord(c->ev_counters[slot], c->stream));
         k++;
@@ -1152,8 +1206,36 @@ int64_t gpet_result_singles(gpet_ctx* c, const gpet_event** ptr) {
 
 int64_t gpet_result_coincidences(gpet_ctx* c, const gpet_coincidence** ptr) {
     if (!c || !ptr) return GPET_ERR_ARG;
+    if (c->coinc_format == GPET_COINC_PAIRS) {   // records on demand: gather from the singles list
+        const size_t np = c->res_pairs.size / (2 * sizeof(uint32_t)), ns = c->res_singles.size / sizeof(gpet_event);
+        if (c->coinc_expanded.size() != np * sizeof(gpet_coincidence)) {
+            c->coinc_expanded.resize(np * sizeof(gpet_coincidence));
+            const uint32_t* pr = reinterpret_cast<const uint32_t*>(c->res_pairs.p);
+            const gpet_event* sg = reinterpret_cast<const gpet_event*>(c->res_singles.p);
+            gpet_coincidence* out = reinterpret_cast<gpet_coincidence*>(c->coinc_expanded.data());
+            for (size_t k = 0; k < np; k++) {
+                if (pr[2 * k] >= ns || pr[2 * k + 1] >= ns) return fail(c, GPET_ERR_ARG, "coincidence pair out of range");
+                out[k].a = sg[pr[2 * k]];
+                out[k].b = sg[pr[2 * k + 1]];
+            }
+        }
+        *ptr = reinterpret_cast<const gpet_coincidence*>(c->coinc_expanded.data());
+        return (int64_t)np;
+    }
     *ptr = reinterpret_cast<const gpet_coincidence*>(c->res_coinc.p);
     return (int64_t)(c->res_coinc.size / sizeof(gpet_coincidence));
+}
+
+int gpet_set_coincidence_format(gpet_ctx* c, int format) {
+    if (!c || (format != GPET_COINC_RECORDS && format != GPET_COINC_PAIRS)) return GPET_ERR_ARG;
+    c->coinc_format = format;
+    return GPET_OK;
+}
+
+int64_t gpet_result_coincidence_pairs(gpet_ctx* c, const uint32_t** ptr) {
+    if (!c || !ptr) return GPET_ERR_ARG;
+    *ptr = reinterpret_cast<const uint32_t*>(c->res_pairs.p);
+    return (int64_t)(c->res_pairs.size / (2 * sizeof(uint32_t)));
 }
 
 int gpet_get_stats(const gpet_ctx* c, gpet_stats* s) {

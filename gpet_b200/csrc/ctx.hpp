@@ -62,6 +62,13 @@ struct gpet_ctx {
     // gpet_run pipelines frames: frame k computes into slot k&1 while the host copies frame k-1 out of the other slot
     void* singles_slot[2] = {nullptr, nullptr};
     void* coinc_slot[2] = {nullptr, nullptr};
+    void* pairs_slot[2] = {nullptr, nullptr};            // uint2 index pairs (GPET_COINC_PAIRS)
+    unsigned* d_pair_base = nullptr;                     // [2]: singles of the run's earlier frames, alternating by frame
+    int coinc_format = 0;                                // GPET_COINC_RECORDS / GPET_COINC_PAIRS (gpet_run only)
+    bool in_run = false;
+    int64_t run_frame = 0;                               // owned frames launched so far in this run
+    bool have_range = false;                             // the time slice of the frame being digitized is known
+    gpet::TimeRange range{};
     unsigned* h_slot_counters[2] = {nullptr, nullptr};   // pinned, 32 words each
     cudaEvent_t ev_counters[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;
@@ -83,6 +90,8 @@ struct gpet_ctx {
     std::vector<FramePlan> frames;
     bool planned = false;
     PinnedArena res_singles, res_coinc;   // gpet_event / gpet_coincidence records of the last gpet_run
+    PinnedArena res_pairs;                // uint32 index pairs of the last gpet_run (GPET_COINC_PAIRS)
+    std::vector<char> coinc_expanded;     // records built on demand from res_pairs + res_singles
     gpet_stats stats{};
     uint64_t last_counts[4] = {0, 0, 0, 0};
     gpet::KernelTimer ktimer;   // per-kernel CUDA-event times (gpet_profile_enable)

@@ -1,24 +1,31 @@
-// Digitizer chain on the device: blur -> thresholder -> time sort -> site order -> dead time -> energy window
-// -> singles (time sorted) [-> coincidence sorter].  Reference: blur/energywindow/setSitenum/deadtime kernels
-// (gPET_kernals.cu:607-698, 814-837) and the host orchestration with three CPU sorts (gPET.cu:385-424,
-// detector.cu:354-385).  Here nothing leaves the device between stages: counts stay in `counters`, events are 48-byte
-// records in the file layout, and the final singles list is produced by one fused flag + scan + compaction of the
-// time order (no re-sort after dead time / energy window, since killing keeps the order).  The launch sequence is
-// static: all sizes and decisions live on the device.
+// Digitizer chain on the device: blur -> thresholder -> time sort -> dead time -> energy window -> singles (time
+// sorted) [-> coincidence sorter].  Reference: blur/energywindow/setSitenum/deadtime kernels (gPET_kernals.cu:607-698,
+// 814-837) and the host orchestration with three CPU sorts + orderevents (gPET.cu:385-424, detector.cu:354-385).
+// Here nothing leaves the device between stages: counts stay in `counters`, events are 48-byte records in the file
+// layout, and the launch sequence is static (all sizes and decisions live on the device).
 //
-// Time sort (D5).  The keys are the order-preserving u64 images of the fp64 times.  Decay times inside a frame are
-// spread over the frame, so the sort is a bucket sort: k_prep finds the key range, k_bucket_count/_scan/_scatter
-// distribute the events over 2^ceil(log2(n/8)) equal slices of that range (about 8 events each), k_bucket_sort ranks
-// every event inside its slice by (key, event index) -- four short kernels without ping-pong passes or chained scans,
-// and the result is the unique stable order whatever the scatter order was.  If some slice holds more than
-// kBucketLimit events (times clustered on a scale far below the key range: never the case for decay data, but legal
-// input of the replay entry point), k_bucket_scan raises counters[12] and the stable LSD radix sort of radix_sort.cuh
-// runs instead; its kernels are always enqueued and return at once when the flag is clear.
+// Time sort (D5).  Keys are the order-preserving u64 images of the fp64 times.  Times inside a frame are spread over
+// the frame, so the sort is a bucket sort over equal slices of the time range (about 8 events per slice): k_prep takes
+// each event's arrival rank in its slice with one atomic, k_bucket_scan turns the slice counts into starts,
+// k_bucket_scatter places (key, index, site) at start + arrival rank, k_bucket_rank orders every slice in shared
+// memory by (key, event index) -- the unique stable order whatever the arrival order was.  The key range comes from the
+// caller (the frame's time slice) or from k_range (replay entry); keys outside it are clamped into the end slices, so
+// the range only shapes the load, never the result.  If a slice holds more than kBucketLimit events (times clustered
+// far below the range: never the case for decay data, but legal input of the replay entry point) k_bucket_scan raises
+// counters[12] and ONE persistent cooperative kernel, k_lsd_fallback, runs the stable LSD radix sort of radix_sort.cuh
+// (all passes, grid barriers in between); it is always enqueued and returns at once when the flag is clear.
 //
-// Launches per frame: k_begin, k_prep, k_bucket_count, k_bucket_scan, k_bucket_scatter, k_bucket_sort, [k_lsd_hist,
-// 8 x k_onesweep<u64>: fallback, normally empty], k_site_keys, 4 x k_onesweep<u32> (passes whose digit is constant
-// return at once), k_deadtime, k_emit_singles [, k_coinc_count, k_coinc_emit].
+// Dead time (D6, D7) needs no sort by site: in the reference's (site, t) order the predecessor of an event is the
+// nearest earlier event of the same site in the time order, and it can only matter while t < (float)t_prev + tau, a
+// condition that is monotone in t_prev.  So every event walks back through the time order while that holds and stops
+// at the first event of its own site (paralyzable: that event kills it) -- O(events inside one dead time) per event.
+// The non-paralyzable chain is cut at the events their predecessor cannot kill (k_deadtime_chain).
+//
+// Launches per frame: k_begin, [k_range], k_prep, k_bucket_scan, k_bucket_scatter, k_bucket_rank, k_lsd_fallback
+// (normally empty), [k_deadtime_chain: non-paralyzable only], k_emit_singles [, k_coinc_count, k_coinc_emit].
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include "kernels.hpp"
 #include "philox.cuh"
 #include "ktimer.hpp"
@@ -31,10 +38,13 @@ namespace gpet {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kMaxLogBuckets = 17;
+constexpr int kMaxLogBuckets = 19;
 constexpr unsigned kMaxBuckets = 1u << kMaxLogBuckets;
 constexpr unsigned kBucketLimit = 1024;   // a fuller slice sends the time sort to the LSD fallback
 constexpr int kFlagLsd = 12;              // counters[kFlagLsd] != 0: time sort by LSD radix passes
+constexpr int kGroup = 256;               // slices ranked by one block at a time
+constexpr int kRankCap = 3840;            // events of a slice group that are ranked out of shared memory
+constexpr unsigned kEwinBit = 0x80000000u;  // payload bit: the record is inside the final energy window
 
 __device__ __forceinline__ unsigned long long time_key(double t) {
     unsigned long long b = (unsigned long long)__double_as_longlong(t);
@@ -52,34 +62,37 @@ __device__ __forceinline__ unsigned warp_sum(unsigned v) {
     return v;
 }
 
-// Equal slices of the key range [kmin, kmax] of the alive events: slice = (key - kmin) >> shift.
+// Equal slices of the TIME range [lo, hi] (not of the key range: the u64 image of a double is logarithmic in t):
+// slice = clamp((long long)((t - lo) * inv), 0, nb - 1), monotone in t, which is all the sort needs.
 struct BucketMap {
-    unsigned long long kmin;
-    int shift;
+    double lo, inv;
     unsigned nb;
 };
 
-__device__ __forceinline__ BucketMap bucket_map(const unsigned long long* __restrict__ minmax, unsigned n_alive) {
+__device__ __forceinline__ BucketMap bucket_map(const TimeRange& r, unsigned n) {
     BucketMap m;
-    const unsigned long long kmin = minmax[0], kmax = minmax[1];
-    m.kmin = kmin;
-    const unsigned long long range = (n_alive && kmax >= kmin) ? kmax - kmin : 0ull;
-    const int bits = range ? 64 - __clzll((long long)range) : 0;
-    int lognb = (n_alive > 1 ? 32 - __clz((int)(n_alive - 1)) : 0) - 3;   // ceil(log2 n) - 3: about 8 events per slice
+    const double lo = r.dev ? key_time(r.dev[0]) : r.lo, hi = r.dev ? key_time(r.dev[1]) : r.hi;
+    int lognb = (n > 1 ? 32 - __clz((int)(n - 1)) : 0) - 3;   // ceil(log2 n) - 3: about 8 events per slice
     lognb = min(max(lognb, 6), kMaxLogBuckets);
-    m.shift = max(bits - lognb, 0);
     m.nb = 1u << lognb;
+    m.lo = lo;
+    m.inv = (hi > lo && (hi - lo) < 1e300) ? (double)m.nb / (hi - lo) : 0.0;
     return m;
 }
 
 __device__ __forceinline__ unsigned bucket_of(const BucketMap& m, unsigned long long key) {
-    return (unsigned)((key - m.kmin) >> m.shift);
+    const double x = (key_time(key) - m.lo) * m.inv;
+    if (!(x > 0.0)) return 0u;
+    return x < (double)m.nb ? (unsigned)x : m.nb - 1u;
 }
 
+// (double)((float)t_prev + tau): the end of the dead time an event at t_prev opens, with the reference's fp32 `tdead`
+// and fp32 sum (gPET_kernals.cu:670-676); monotone in t_prev
+__device__ __forceinline__ double dead_until(double t_prev, float tau) { return (double)__fadd_rn((float)t_prev, tau); }
+
 // ------------------------------------------------------------------------------------------- stage 0: reset
-// counters[0..7] and the fallback flag, both LSD sort states, the scan status words, the slice counters, the key range.
-__global__ void __launch_bounds__(kThreads) k_begin(unsigned* __restrict__ counters, rsort::SortState* st_time,
-                                                    rsort::SortState* st_site, unsigned* __restrict__ scan_status0,
+// counters[0..7] and the fallback flag, the scan status words, the slice counters, the key range.
+__global__ void __launch_bounds__(kThreads) k_begin(unsigned* __restrict__ counters, unsigned* __restrict__ scan_status0,
                                                     unsigned* __restrict__ scan_status1, unsigned* __restrict__ scan_status2,
                                                     unsigned max_tiles, unsigned* __restrict__ bcount,
                                                     unsigned long long* __restrict__ minmax) {
@@ -87,27 +100,49 @@ __global__ void __launch_bounds__(kThreads) k_begin(unsigned* __restrict__ count
     if (tid < 8) counters[tid] = 0;
     if (tid == 8) counters[kFlagLsd] = 0;
     if (tid == 9) { minmax[0] = ~0ull; minmax[1] = 0ull; }
-    constexpr unsigned kWords = sizeof(rsort::SortState) / 4;
-    unsigned* a = reinterpret_cast<unsigned*>(st_time);
-    unsigned* b = reinterpret_cast<unsigned*>(st_site);
-    for (unsigned i = tid; i < kWords; i += nth) { a[i] = 0; b[i] = 0; }
     for (unsigned i = tid; i < max_tiles; i += nth) { scan_status0[i] = 0; scan_status1[i] = 0; }
     for (unsigned i = tid; i < kMaxBuckets / 2048u; i += nth) scan_status2[i] = 0;
-    for (unsigned i = tid; i < kMaxBuckets; i += nth) bcount[i] = 0;
+    uint4* b4 = reinterpret_cast<uint4*>(bcount);
+    for (unsigned i = tid; i < kMaxBuckets / 4u; i += nth) b4[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// ------------------------------------------------------------------------------------------- stage 1: blur + thresholder + time keys
-// blur (gPET_kernals.cu:814-837) + energywindow(Eth, 2e6) (gPET.cu:393) fused; writes the time key of every record
-// (all ones for a dead one) and the key range of the alive ones.
-__global__ void __launch_bounds__(kThreads) k_prep(EventBuf ev, DigitizerDev p, uint64_t seed,
-                                                   unsigned long long* __restrict__ keys, unsigned* __restrict__ counters,
-                                                   unsigned long long* __restrict__ minmax) {
+// replay entry only: key range of the records that are not dead on arrival
+__global__ void __launch_bounds__(kThreads) k_range(EventBuf ev, unsigned long long* __restrict__ minmax) {
     const unsigned n = min(*ev.count, ev.capacity);
-    if (blockIdx.x == 0 && threadIdx.x == 0) counters[0] = n;
-    unsigned alive_cnt = 0;
     unsigned long long kmin = ~0ull, kmax = 0ull;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double t = ev.rec[i].t;
+        if (t < kMaxT * 0.1) {
+            const unsigned long long key = time_key(t);
+            kmin = min(kmin, key);
+            kmax = max(kmax, key);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && kmin <= kmax) {
+        atomicMin(&minmax[0], kmin);
+        atomicMax(&minmax[1], kmax);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- stage 1: blur + thresholder + site + slice
+// blur (gPET_kernals.cu:814-837) + energywindow(Eth, 2e6) (gPET.cu:393) + setSitenum (gPET_kernals.cu:607-640) fused.
+// Per record: time key (all ones for a dead one), site number, arrival rank in its time slice | final-window flag.
+__global__ void __launch_bounds__(kThreads) k_prep(EventBuf ev, DigitizerDev p, uint64_t seed, TimeRange range,
+                                                   unsigned long long* __restrict__ keys, int* __restrict__ site_of,
+                                                   unsigned* __restrict__ aux, unsigned* __restrict__ bcount,
+                                                   unsigned* __restrict__ counters) {
+    const unsigned n = min(*ev.count, ev.capacity);
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[0] = n;
+    const BucketMap m = bucket_map(range, n);
+    unsigned alive_cnt = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         EventRec* rec = ev.rec + i;
+        const int4 a4 = reinterpret_cast<const int4*>(rec)[0];   // parn, pann, modn, cryn
         const int4 b4 = reinterpret_cast<const int4*>(rec)[1];   // siten, eventid, t
         float4 c4 = reinterpret_cast<const float4*>(rec)[2];     // E, x, y, z
         float E = c4.x;
@@ -120,8 +155,7 @@ __global__ void __launch_bounds__(kThreads) k_prep(EventBuf ev, DigitizerDev p, 
         if (!(R > 0.f)) R = 0.f;
         // R == 0 leaves E bit-identical (E + 0), so the draw is skipped: this is the deterministic replay mode
         if (R > 0.f || p.sblur > 0.f || p.tblur > 0.f) {
-            const int parn = reinterpret_cast<const int*>(rec)[0];
-            Philox rng(seed, (uint64_t)(uint32_t)parn, ((uint32_t)kStageBlur << 24) | ((uint32_t)b4.x & 0xFFFFFFu));
+            Philox rng(seed, (uint64_t)(uint32_t)a4.x, ((uint32_t)kStageBlur << 24) | ((uint32_t)b4.x & 0xFFFFFFu));
             uint4 r = rng.next();
             float rad = sqrtf(-2.0f * logf(u01(r.x)));
             float g0 = rad * cosf(kTwoPi * u01(r.y));
@@ -149,22 +183,20 @@ __global__ void __launch_bounds__(kThreads) k_prep(EventBuf ev, DigitizerDev p, 
         const unsigned long long key = alive ? time_key(t) : ~0ull;
         keys[i] = key;
         if (alive) {
+            // setSitenum at the dead-time level; dlevel == 3 keeps what readout left (gPET.cu:402-407)
+            int site = b4.x;
+            if (p.dlevel == 0) site = 0;
+            else if (p.dlevel == 1) site = a4.y;
+            else if (p.dlevel == 2) site = a4.y * p.moduleN + a4.z;
+            if (site != b4.x) rec->siten = site;
+            site_of[i] = site;
+            const unsigned arrival = atomicAdd(&bcount[bucket_of(m, key)], 1u);
+            aux[i] = arrival | (!(E < p.Ewinmin || E > p.Ewinmax) ? kEwinBit : 0u);
             alive_cnt++;
-            kmin = min(kmin, key);
-            kmax = max(kmax, key);
         }
     }
     alive_cnt = warp_sum(alive_cnt);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-    }
-    if ((threadIdx.x & 31) == 0 && alive_cnt) {
-        atomicAdd(&counters[1], alive_cnt);
-        atomicMin(&minmax[0], kmin);
-        atomicMax(&minmax[1], kmax);
-    }
+    if ((threadIdx.x & 31) == 0 && alive_cnt) atomicAdd(&counters[1], alive_cnt);
 }
 
 // ------------------------------------------------------------------------------------------- single-pass exclusive scan
@@ -225,206 +257,206 @@ __device__ __forceinline__ TileScan tile_exclusive_scan(const unsigned v[8], uns
 }
 
 // ------------------------------------------------------------------------------------------- stage 2: time sort (bucket sort)
-__global__ void __launch_bounds__(kThreads) k_bucket_count(const unsigned long long* __restrict__ keys,
-                                                           const unsigned* __restrict__ counters,
-                                                           const unsigned long long* __restrict__ minmax,
-                                                           unsigned* __restrict__ bcount) {
-    const unsigned n = counters[0];
-    const BucketMap m = bucket_map(minmax, counters[1]);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned long long key = keys[i];
-        if (key != ~0ull) atomicAdd(&bcount[bucket_of(m, key)], 1u);
-    }
-}
-
 // exclusive scan of the slice counters (one tile of 2048 per block, all blocks resident: tile = blockIdx);
 // raises the LSD-fallback flag when a slice is overfull
 __global__ void __launch_bounds__(kThreads) k_bucket_scan(const unsigned* __restrict__ bcount, unsigned* __restrict__ bstart,
-                                                          unsigned* __restrict__ bcur, unsigned* __restrict__ status,
-                                                          unsigned* __restrict__ counters,
-                                                          const unsigned long long* __restrict__ minmax) {
-    const BucketMap m = bucket_map(minmax, counters[1]);
+                                                          unsigned* __restrict__ status, unsigned* __restrict__ counters,
+                                                          TimeRange range) {
+    const BucketMap m = bucket_map(range, counters[0]);
     const unsigned tile = blockIdx.x;
     if (tile * kScanTile >= m.nb) return;
     const unsigned b0 = tile * kScanTile + threadIdx.x * 8;
     unsigned c[8];
     bool over = false;
+    {
+        const uint4 lo = reinterpret_cast<const uint4*>(bcount + b0)[0], hi = reinterpret_cast<const uint4*>(bcount + b0)[1];
+        c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w; c[4] = hi.x; c[5] = hi.y; c[6] = hi.z; c[7] = hi.w;
+    }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        c[k] = (b0 + k < m.nb) ? bcount[b0 + k] : 0u;
+        if (b0 + k >= m.nb) c[k] = 0u;
         over |= c[k] > kBucketLimit;
     }
     if (over) counters[kFlagLsd] = 1u;
     TileScan sc = tile_exclusive_scan(c, tile, status);
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-        if (b0 + k < m.nb) { bstart[b0 + k] = sc.excl[k]; bcur[b0 + k] = sc.excl[k]; }
+    if (b0 < m.nb) {   // nb is a multiple of 8
+        reinterpret_cast<uint4*>(bstart + b0)[0] = make_uint4(sc.excl[0], sc.excl[1], sc.excl[2], sc.excl[3]);
+        reinterpret_cast<uint4*>(bstart + b0)[1] = make_uint4(sc.excl[4], sc.excl[5], sc.excl[6], sc.excl[7]);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) k_bucket_scatter(const unsigned long long* __restrict__ keys,
-                                                             const unsigned* __restrict__ counters,
-                                                             const unsigned long long* __restrict__ minmax,
-                                                             unsigned* __restrict__ bcur, unsigned long long* __restrict__ bkeys,
-                                                             unsigned* __restrict__ bidx) {
+                                                             const int* __restrict__ site_of, const unsigned* __restrict__ aux,
+                                                             const unsigned* __restrict__ counters, TimeRange range,
+                                                             const unsigned* __restrict__ bstart,
+                                                             unsigned long long* __restrict__ bkeys, uint2* __restrict__ bpay) {
     if (counters[kFlagLsd]) return;
     const unsigned n = counters[0];
-    const BucketMap m = bucket_map(minmax, counters[1]);
+    const BucketMap m = bucket_map(range, n);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned long long key = keys[i];
         if (key == ~0ull) continue;
-        const unsigned pos = atomicAdd(&bcur[bucket_of(m, key)], 1u);
+        const unsigned a = aux[i];
+        const unsigned pos = __ldg(&bstart[bucket_of(m, key)]) + (a & ~kEwinBit);
         bkeys[pos] = key;
-        bidx[pos] = i;
+        bpay[pos] = make_uint2(i | (a & kEwinBit), (unsigned)site_of[i]);
     }
 }
 
-// rank of every event inside its slice by (key, event index): the stable time order
-__global__ void __launch_bounds__(kThreads) k_bucket_sort(const unsigned long long* __restrict__ bkeys,
-                                                          const unsigned* __restrict__ bidx, const unsigned* __restrict__ bstart,
-                                                          const unsigned* __restrict__ bend, const unsigned* __restrict__ counters,
-                                                          const unsigned long long* __restrict__ minmax,
-                                                          unsigned* __restrict__ order_t, unsigned long long* __restrict__ tsort) {
+// rank of every event inside its slice by (key, event index): the stable time order.  A block takes kGroup
+// consecutive slices at a time, stages their events in shared memory (they are contiguous) and ranks out of it.
+__global__ void __launch_bounds__(kThreads) k_bucket_rank(const unsigned long long* __restrict__ bkeys,
+                                                          const uint2* __restrict__ bpay, const unsigned* __restrict__ bstart,
+                                                          const unsigned* __restrict__ counters, TimeRange range,
+                                                          unsigned long long* __restrict__ tsort, unsigned* __restrict__ order_t,
+                                                          int* __restrict__ site_t) {
+    __shared__ unsigned long long sm_key[kRankCap];
+    __shared__ unsigned sm_idx[kRankCap];
+    __shared__ unsigned sm_start[kGroup + 1];
     if (counters[kFlagLsd]) return;
     const unsigned n1 = counters[1];
-    const BucketMap m = bucket_map(minmax, n1);
-    for (unsigned pos = blockIdx.x * blockDim.x + threadIdx.x; pos < n1; pos += gridDim.x * blockDim.x) {
-        const unsigned long long key = bkeys[pos];
-        const unsigned i = bidx[pos];
-        const unsigned b = bucket_of(m, key);
-        const unsigned s = bstart[b], e = bend[b];
-        unsigned rank = 0;
-        for (unsigned q = s; q < e; q++) {
-            const unsigned long long kq = bkeys[q];
-            if (kq < key || (kq == key && bidx[q] < i)) rank++;
+    const BucketMap m = bucket_map(range, counters[0]);
+    const unsigned ngroups = (m.nb + kGroup - 1) / kGroup;
+    for (unsigned g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const unsigned b0 = g * kGroup;
+        for (unsigned k = threadIdx.x; k <= (unsigned)kGroup; k += kThreads) sm_start[k] = (b0 + k < m.nb) ? bstart[b0 + k] : n1;
+        __syncthreads();
+        const unsigned base = sm_start[0], cnt = sm_start[kGroup] - base;
+        const bool staged = cnt <= (unsigned)kRankCap;
+        if (staged) {
+            for (unsigned e = threadIdx.x; e < cnt; e += kThreads) {
+                sm_key[e] = bkeys[base + e];
+                sm_idx[e] = bpay[base + e].x & ~kEwinBit;
+            }
+            __syncthreads();
         }
-        order_t[s + rank] = i;
-        tsort[s + rank] = key;
+        for (unsigned e = threadIdx.x; e < cnt; e += kThreads) {
+            const uint2 pay = bpay[base + e];
+            const unsigned long long key = staged ? sm_key[e] : bkeys[base + e];
+            const unsigned idx = pay.x & ~kEwinBit;
+            const unsigned b = bucket_of(m, key) - b0;
+            const unsigned s = sm_start[b] - base, en = sm_start[b + 1] - base;
+            unsigned rank = 0;
+            if (staged) {
+                for (unsigned q = s; q < en; q++) {
+                    const unsigned long long kq = sm_key[q];
+                    rank += (kq < key || (kq == key && sm_idx[q] < idx)) ? 1u : 0u;
+                }
+            } else {
+                for (unsigned q = s; q < en; q++) {
+                    const unsigned long long kq = bkeys[base + q];
+                    rank += (kq < key || (kq == key && (bpay[base + q].x & ~kEwinBit) < idx)) ? 1u : 0u;
+                }
+            }
+            const unsigned pos = base + s + rank;
+            tsort[pos] = key;
+            order_t[pos] = pay.x;
+            site_t[pos] = (int)pay.y;
+        }
+        __syncthreads();
     }
 }
 
-// fallback only: digit histograms of all 8 passes + identity payload for the LSD radix sort of the time keys
-__global__ void __launch_bounds__(kThreads) k_lsd_hist(const unsigned long long* __restrict__ keys, unsigned* __restrict__ vals,
-                                                       const unsigned* __restrict__ counters, rsort::SortState* st_time,
-                                                       unsigned* __restrict__ lookback0) {
-    if (counters[kFlagLsd] == 0u) return;
+// Fallback time sort: stable LSD radix sort of (key, index | window flag), all 8 passes in one persistent cooperative
+// kernel (grid barriers between the phases), then the same three output arrays as k_bucket_rank.  Returns at once when
+// the bucket sort did the job.
+__global__ void __launch_bounds__(rsort::kThreads) k_lsd_fallback(unsigned long long* keys0, unsigned long long* keys1,
+                                                                  unsigned* vals0, unsigned* vals1,
+                                                                  const unsigned* __restrict__ aux, const int* __restrict__ site_of,
+                                                                  const unsigned* __restrict__ counters, rsort::SortState* st,
+                                                                  unsigned* lookback0, unsigned* lookback1, unsigned* bar,
+                                                                  unsigned* __restrict__ order_t, int* __restrict__ site_t) {
+    __shared__ rsort::PassSmem sm;
     __shared__ unsigned sh_hist[8 * rsort::kBins];
-    const unsigned n = counters[0];
+    if (counters[kFlagLsd] == 0u) return;
+    const unsigned n = counters[0], n1 = counters[1];
+    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    {   // phase 0: clean sort state
+        constexpr unsigned kWords = sizeof(rsort::SortState) / 4;
+        unsigned* w = reinterpret_cast<unsigned*>(st);
+        for (unsigned i = gtid; i < kWords; i += nth) w[i] = 0u;
+        rsort::clear_lookback(lookback0, n);
+    }
+    rsort::grid_barrier(bar);
+    // phase 1: payload + digit histograms of all passes
     for (int i = threadIdx.x; i < 8 * rsort::kBins; i += blockDim.x) sh_hist[i] = 0;
     __syncthreads();
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        vals[i] = i;
-        rsort::hist_add<unsigned long long, 8>(sh_hist, keys[i]);
+    for (unsigned i = gtid; i < n; i += nth) {
+        const unsigned long long key = keys0[i];
+        vals0[i] = key != ~0ull ? (i | (aux[i] & kEwinBit)) : i;
+        rsort::hist_add<unsigned long long, 8>(sh_hist, key);
     }
     __syncthreads();
-    rsort::hist_flush<8>(sh_hist, st_time);
-    rsort::clear_lookback(lookback0, n);
-}
-
-// ------------------------------------------------------------------------------------------- stage 3: site keys
-// setSitenum (gPET_kernals.cu:607-640) fused with building the (site) sort keys over the time order.  After this
-// kernel the time order is in order_t / tsort whichever sort produced it.
-__global__ void __launch_bounds__(kThreads) k_site_keys(EventBuf ev, DigitizerDev p, unsigned long long* __restrict__ tkeys0,
-                                                        const unsigned long long* __restrict__ tkeys1,
-                                                        const unsigned* __restrict__ tvals0, const unsigned* __restrict__ tvals1,
-                                                        const rsort::SortState* st_time, unsigned* __restrict__ order_t,
-                                                        unsigned* __restrict__ keys, unsigned* __restrict__ vals,
-                                                        const unsigned* __restrict__ counters, rsort::SortState* st_site,
-                                                        unsigned* __restrict__ lookback0) {
-    __shared__ unsigned sh_hist[4 * rsort::kBins];
-    const unsigned n1 = counters[1];
-    const bool lsd = counters[kFlagLsd] != 0u;
-    const unsigned cur = rsort::current_buffer(st_time, 8, counters[0]);
-    const unsigned* __restrict__ t_sorted_vals = cur ? tvals1 : tvals0;
-    for (int i = threadIdx.x; i < 4 * rsort::kBins; i += blockDim.x) sh_hist[i] = 0;
-    __syncthreads();
-    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n1; j += gridDim.x * blockDim.x) {
-        unsigned i;
-        if (lsd) {
-            i = t_sorted_vals[j];
-            order_t[j] = i;
-            if (cur) tkeys0[j] = tkeys1[j];
-        } else {
-            i = order_t[j];
-        }
-        EventRec* rec = ev.rec + i;
-        int site;
-        switch (p.dlevel) {
-            case 0: site = 0; break;
-            case 1: site = rec->pann; break;
-            case 2: site = rec->pann * p.moduleN + rec->modn; break;
-            default: site = rec->siten; break;  // dlevel == 3: keep what readout left (gPET.cu:402-407)
-        }
-        if (p.dlevel >= 0 && p.dlevel <= 2) rec->siten = site;
-        // flip the sign bit: std::sort compares siten as signed int (gPET.h:101-106)
-        const unsigned key = (unsigned)site ^ 0x80000000u;
-        keys[j] = key;
-        vals[j] = j;
-        rsort::hist_add<unsigned, 4>(sh_hist, key);
+    rsort::hist_flush<8>(sh_hist, st);
+    rsort::grid_barrier(bar);
+    for (int pass = 0; pass < 8; pass++) {
+        rsort::onesweep_pass<unsigned long long>(sm, keys0, keys1, vals0, vals1, n, st, lookback0, lookback1, pass);
+        rsort::grid_barrier(bar);
     }
-    __syncthreads();
-    rsort::hist_flush<4>(sh_hist, st_site);
-    rsort::clear_lookback(lookback0, n1);
+    // the alive records come first (dead keys are all ones); outputs in the layout of k_bucket_rank (tsort = keys0)
+    const unsigned cur = rsort::current_buffer(st, 8, n);
+    const unsigned* __restrict__ v = cur ? vals1 : vals0;
+    for (unsigned j = gtid; j < n1; j += nth) {
+        const unsigned pv = v[j];
+        order_t[j] = pv;
+        site_t[j] = site_of[pv & ~kEwinBit];
+        if (cur) keys0[j] = keys1[j];
+    }
 }
 
-// ------------------------------------------------------------------------------------------- stage 4: dead time
+// ------------------------------------------------------------------------------------------- stage 3: dead time
 // deadtime (gPET_kernals.cu:657-698) with the snapshot-start semantics of SURVEY 8(a) D7: every decision uses the
-// original times; `tdead` is fp32 and `tdead + interval` is an fp32 sum, as in the reference.  q runs over the
-// (site, t) order; kill flags are stored by position in the time order.
-__global__ void __launch_bounds__(kThreads) k_deadtime(DigitizerDev p, const unsigned long long* __restrict__ tsort,
-                                                       const unsigned* __restrict__ skeys0, const unsigned* __restrict__ skeys1,
-                                                       const unsigned* __restrict__ svals0, const unsigned* __restrict__ svals1,
-                                                       const rsort::SortState* st_site, unsigned char* __restrict__ kill,
-                                                       const unsigned* __restrict__ counters) {
+// original times.  Paralyzable: is event j inside the dead time of the nearest earlier event of its site?
+__device__ __forceinline__ bool killed_by_predecessor(const unsigned long long* __restrict__ tsort, const int* __restrict__ site_t,
+                                                      unsigned j, double t, int site, float tau) {
+    for (unsigned q = j; q > 0;) {
+        q--;
+        if (!(t < dead_until(key_time(__ldg(&tsort[q])), tau))) return false;   // and so for every earlier event
+        if (__ldg(&site_t[q]) == site) return true;
+    }
+    return false;
+}
+
+// Non-paralyzable: sequential anchor chain per site.  An event its predecessor cannot kill survives any earlier anchor
+// as well (fp32 rounding and the fp32 sum are monotone), so it is a guaranteed anchor and the chain can be cut there:
+// one thread per such run start walks forward through the time order while the next event of its site is inside the
+// dead time of the previous one.
+__global__ void __launch_bounds__(kThreads) k_deadtime_chain(DigitizerDev p, const unsigned long long* __restrict__ tsort,
+                                                             const int* __restrict__ site_t, unsigned char* __restrict__ kill,
+                                                             const unsigned* __restrict__ counters) {
     const unsigned n1 = counters[1];
     const float tau = p.dtime;
-    const unsigned cur = rsort::current_buffer(st_site, 4, n1);
-    const unsigned* __restrict__ site_keys = cur ? skeys1 : skeys0;
-    const unsigned* __restrict__ order_s = cur ? svals1 : svals0;
-    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n1; q += gridDim.x * blockDim.x) {
-        const unsigned j = order_s[q];
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n1; j += gridDim.x * blockDim.x) {
         const double t = key_time(tsort[j]);
-        bool same_prev = false;
-        double tprev = 0.0;
-        if (q > 0 && site_keys[q] == site_keys[q - 1]) {
-            same_prev = true;
-            tprev = key_time(tsort[order_s[q - 1]]);
-        }
-        // "killable by its predecessor": t < (float)t_prev + tau with the fp32 sum of the reference (tdead is float)
-        const bool killable = same_prev && t < (double)__fadd_rn((float)tprev, tau);
-        if (p.dtype == 0) {
-            // paralyzable: tdead follows every event, so the predicate is predecessor-local
-            kill[j] = killable ? 1 : 0;
-        } else {
-            // non-paralyzable: sequential anchor chain per site.  An event its predecessor cannot kill survives any
-            // earlier anchor as well (fp32 rounding and the fp32 sum are monotone), so it is a guaranteed anchor and
-            // the chain can be cut there: one thread per such run start, runs are short at realistic rates.
-            if (killable) continue;
-            kill[j] = 0;
-            float tdead = (float)t;
-            unsigned r = q + 1;
-            while (r < n1 && site_keys[r] == site_keys[q]) {
-                const unsigned jr = order_s[r];
-                const double tr = key_time(tsort[jr]);
-                const double tr_prev = key_time(tsort[order_s[r - 1]]);
-                if (!(tr < (double)__fadd_rn((float)tr_prev, tau))) break;  // next run start
-                if (tr < (double)__fadd_rn(tdead, tau)) {
-                    kill[jr] = 1;
-                } else {
-                    kill[jr] = 0;
-                    tdead = (float)tr;
-                }
-                r++;
+        const int site = site_t[j];
+        if (killed_by_predecessor(tsort, site_t, j, t, site, tau)) continue;   // member of an earlier start's chain
+        kill[j] = 0;
+        float tdead = (float)t;
+        double until = dead_until(t, tau);   // dead time of the latest event of this site seen so far
+        for (unsigned r = j + 1; r < n1; r++) {
+            const double tr = key_time(tsort[r]);
+            if (!(tr < until)) break;        // the next event of this site, if any, starts its own chain
+            if (site_t[r] != site) continue;
+            if (tr < (double)__fadd_rn(tdead, tau)) {
+                kill[r] = 1;
+            } else {
+                kill[r] = 0;
+                tdead = (float)tr;
             }
+            until = dead_until(tr, tau);
         }
     }
 }
 
-// ------------------------------------------------------------------------------------------- stage 5: energy window + compaction -> singles
-// energywindow(Ewinmin, Ewinmax) (gPET.cu:418) over the survivors of the dead time, in time order.
+// ------------------------------------------------------------------------------------------- stage 4: energy window + compaction -> singles
+// dead time (paralyzable: decided here) + energywindow(Ewinmin, Ewinmax) (gPET.cu:418) over the time order; survivors are
+// compacted into the singles list, their times and panels into two side arrays for the coincidence sorter.
 __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, DigitizerDev p, EventRec* __restrict__ singles,
-                                                           unsigned singles_cap, const unsigned* __restrict__ order_t,
+                                                           unsigned singles_cap, const unsigned long long* __restrict__ tsort,
+                                                           const unsigned* __restrict__ order_t, const int* __restrict__ site_t,
                                                            const unsigned char* __restrict__ kill, unsigned* __restrict__ counters,
-                                                           unsigned* __restrict__ status, unsigned long long* __restrict__ spectrum,
+                                                           unsigned* __restrict__ status, double* __restrict__ stime,
+                                                           int* __restrict__ span, unsigned long long* __restrict__ spectrum,
                                                            int nbins, float emin, float emax) {
     __shared__ unsigned s_tile;
     __shared__ unsigned s_idx[kScanTile];
@@ -447,12 +479,13 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, Digitize
             const unsigned j = j0 + k;
             flag[k] = 0; idx[k] = 0;
             if (j < n1) {
-                const unsigned i = order_t[j];
-                idx[k] = i;
-                const bool a2 = kill[j] == 0;
-                const float E = ev.rec[i].E;
-                flag[k] = (a2 && !(E < p.Ewinmin || E > p.Ewinmax)) ? 1u : 0u;
-                c2 += a2 ? 1u : 0u;
+                const unsigned pv = order_t[j];
+                idx[k] = pv & ~kEwinBit;
+                bool dead;
+                if (p.dtype == 0) dead = killed_by_predecessor(tsort, site_t, j, key_time(tsort[j]), site_t[j], p.dtime);
+                else dead = kill[j] != 0;
+                flag[k] = (!dead && (pv & kEwinBit)) ? 1u : 0u;
+                c2 += dead ? 0u : 1u;
             }
         }
         TileScan sc = tile_exclusive_scan(flag, tile, status);
@@ -470,8 +503,8 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, Digitize
             const EventRec a = load_event_rec(ev.rec + s_idx[r]);
             EventRec b = a;
             if (two) b = load_event_rec(ev.rec + s_idx[r2]);
-            if (o < singles_cap) store_event_rec(singles + o, a);
-            if (two && o2 < singles_cap) store_event_rec(singles + o2, b);
+            if (o < singles_cap) { store_event_rec(singles + o, a); stime[o] = a.t; span[o] = a.pann; }
+            if (two && o2 < singles_cap) { store_event_rec(singles + o2, b); stime[o2] = b.t; span[o2] = b.pann; }
             if (spectrum && nbins > 0) {
                 float f = (a.E - emin) / (emax - emin) * nbins;
                 if (f >= 0.f && f < (float)nbins) {
@@ -495,29 +528,30 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, Digitize
     if ((threadIdx.x & 31) == 0 && c2) atomicAdd(&counters[2], c2);
 }
 
-// ------------------------------------------------------------------------------------------- stage 6: coincidence sorter (extension)
+// ------------------------------------------------------------------------------------------- stage 5: coincidence sorter (extension)
 // Windows are opened by the first single that is not inside an earlier window and last cwin us; a thread owns the
-// run of windows starting at a single whose predecessor is at least cwin earlier (guaranteed opener).
-__device__ __forceinline__ bool pair_ok(const EventRec* __restrict__ s, unsigned a, unsigned b, const DigitizerDev& p) {
+// run of windows starting at a single whose predecessor is at least cwin earlier (guaranteed opener).  Works on the
+// side arrays of the singles list (time, panel).
+__device__ __forceinline__ bool pair_ok(const int* __restrict__ span, unsigned a, unsigned b, const DigitizerDev& p) {
     if (p.cmindiff <= 0) return true;
-    int d = abs(s[a].pann - s[b].pann);
+    int d = abs(span[a] - span[b]);
     if (p.npanels > 0) d = min(d, p.npanels - d);
     return d >= p.cmindiff;
 }
 
-__global__ void __launch_bounds__(kThreads) k_coinc_count(const EventRec* __restrict__ s, DigitizerDev p,
-                                                          const unsigned* __restrict__ counters, unsigned singles_cap,
-                                                          unsigned* __restrict__ cnt) {
+__global__ void __launch_bounds__(kThreads) k_coinc_count(const double* __restrict__ stime, const int* __restrict__ span,
+                                                          DigitizerDev p, const unsigned* __restrict__ counters,
+                                                          unsigned singles_cap, unsigned* __restrict__ cnt) {
     const unsigned n = min(counters[3], singles_cap);
     const double W = (double)p.cwin;
     for (unsigned a0 = blockIdx.x * blockDim.x + threadIdx.x; a0 < n; a0 += gridDim.x * blockDim.x) {
-        if (a0 > 0 && !(s[a0].t >= s[a0 - 1].t + W)) continue;
+        if (a0 > 0 && !(stime[a0] >= stime[a0 - 1] + W)) continue;
         unsigned a = a0;
         while (true) {
-            const double tend = s[a].t + W;
+            const double tend = stime[a] + W;
             unsigned m = 0, valid = 0;
-            while (a + 1 + m < n && s[a + 1 + m].t < tend) {
-                if (pair_ok(s, a, a + 1 + m, p)) valid++;
+            while (a + 1 + m < n && stime[a + 1 + m] < tend) {
+                if (pair_ok(span, a, a + 1 + m, p)) valid++;
                 cnt[a + 1 + m] = 0;
                 m++;
             }
@@ -527,19 +561,25 @@ __global__ void __launch_bounds__(kThreads) k_coinc_count(const EventRec* __rest
             cnt[a] = c;
             a += m + 1;
             if (a >= n) break;
-            if (s[a].t >= s[a - 1].t + W) break;  // next guaranteed opener: owned by another thread
+            if (stime[a] >= stime[a - 1] + W) break;  // next guaranteed opener: owned by another thread
         }
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_coinc_emit(const EventRec* __restrict__ s, DigitizerDev p,
+// Compaction of the coincidences: index pairs into the run's singles list (pair_base = singles of the run's earlier
+// frames, kept on the device) and, when `out` is given, the two 48-byte records side by side.
+__global__ void __launch_bounds__(kThreads) k_coinc_emit(const EventRec* __restrict__ s, const double* __restrict__ stime,
+                                                         const int* __restrict__ span, DigitizerDev p,
                                                          const unsigned* __restrict__ cnt, unsigned* __restrict__ counters,
                                                          unsigned singles_cap, unsigned* __restrict__ status,
-                                                         gpet_coincidence* __restrict__ out, unsigned cap) {
+                                                         gpet_coincidence* __restrict__ out, uint2* __restrict__ pairs, unsigned cap,
+                                                         const unsigned* __restrict__ base_in, unsigned* __restrict__ base_out) {
     __shared__ unsigned s_tile;
     const unsigned n = min(counters[3], singles_cap);
     const unsigned ntiles = (n + kScanTile - 1) / kScanTile;
     const double W = (double)p.cwin;
+    const unsigned pair_base = base_in ? *base_in : 0u;
+    if (base_out && blockIdx.x == 0 && threadIdx.x == 0) *base_out = pair_base + n;
     while (true) {
         if (threadIdx.x == 0) s_tile = atomicAdd(&counters[7], 1u);
         __syncthreads();
@@ -556,16 +596,19 @@ __global__ void __launch_bounds__(kThreads) k_coinc_emit(const EventRec* __restr
             if (c[k] == 0) continue;
             const unsigned a = a0 + k;
             unsigned o = sc.excl[k];
-            const double tend = s[a].t + W;
-            for (unsigned b = a + 1; b < n && s[b].t < tend; b++) {
-                if (!pair_ok(s, a, b, p)) continue;
-                if (o < cap) {  // 2 x 48-byte records copied as 6 x 16 B from the singles list
-                    const int4* pa = reinterpret_cast<const int4*>(s + a);
-                    const int4* pb = reinterpret_cast<const int4*>(s + b);
-                    const int4 a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
-                    const int4 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
-                    int4* po = reinterpret_cast<int4*>(out + o);
-                    po[0] = a0; po[1] = a1; po[2] = a2; po[3] = b0; po[4] = b1; po[5] = b2;
+            const double tend = stime[a] + W;
+            for (unsigned b = a + 1; b < n && stime[b] < tend; b++) {
+                if (!pair_ok(span, a, b, p)) continue;
+                if (o < cap) {
+                    if (pairs) pairs[o] = make_uint2(pair_base + a, pair_base + b);
+                    if (out) {   // 2 x 48-byte records copied as 6 x 16 B from the singles list
+                        const int4* pa = reinterpret_cast<const int4*>(s + a);
+                        const int4* pb = reinterpret_cast<const int4*>(s + b);
+                        const int4 a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
+                        const int4 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
+                        int4* po = reinterpret_cast<int4*>(out + o);
+                        po[0] = a0; po[1] = a1; po[2] = a2; po[3] = b0; po[4] = b1; po[5] = b2;
+                    }
                 }
                 o++;
             }
@@ -576,49 +619,74 @@ __global__ void __launch_bounds__(kThreads) k_coinc_emit(const EventRec* __restr
 }  // namespace
 
 // ================================================================================================ launchers
-static inline int grid_for(int num_sms) { return num_sms * 2; }
-
 size_t sort_state_bytes() { return sizeof(rsort::SortState); }
 size_t sort_lookback_words(size_t capacity) { return ((capacity + rsort::kTile - 1) / rsort::kTile) * (size_t)rsort::kBins; }
 unsigned scan_tiles(size_t capacity) { return (unsigned)((capacity + kScanTile - 1) / kScanTile); }
 unsigned bucket_words() { return kMaxBuckets; }
 
-int launch_digitize(EventBuf ev, void* singles_aos, unsigned int singles_cap, void* coinc_aos, unsigned int coinc_cap,
-                    const DigitizerDev& p, DigitizerWorkspace& ws, uint64_t seed, int num_sms, cudaStream_t s) {
-    const int grid = grid_for(num_sms);
+TimeRange time_range_us(double t_lo_us, double t_hi_us) {
+    TimeRange r;
+    r.lo = t_lo_us;
+    r.hi = t_hi_us;
+    r.dev = nullptr;
+    return r;
+}
+
+int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p, DigitizerWorkspace& ws, const TimeRange* range,
+                    uint64_t seed, int num_sms, cudaStream_t s) {
+    const int grid = num_sms * 4;
     int launches = 0;
-    EventRec* singles = static_cast<EventRec*>(singles_aos);
-    unsigned long long* bkeys = ws.tkeys[1];   // the LSD ping-pong buffers double as the scatter target: the two sorts
-    unsigned* bidx = ws.tvals[1];              // never run in the same frame
-    const unsigned* lsd = &ws.counters[kFlagLsd];
-    GPET_LAUNCH("k_begin", s, k_begin<<<32, kThreads, 0, s>>>(ws.counters, ws.st_time, ws.st_site, ws.scan_status[0], ws.scan_status[1],
-                                                             ws.scan_status[2], ws.max_tiles, ws.bcount, ws.minmax));
-    GPET_LAUNCH("k_prep", s, k_prep<<<grid, kThreads, 0, s>>>(ev, p, seed, ws.tkeys[0], ws.counters, ws.minmax));
-    // time sort of the alive records (dead ones are left out: they would sink to the tail, like MAXT does)
-    GPET_LAUNCH("k_bucket_count", s, k_bucket_count<<<grid, kThreads, 0, s>>>(ws.tkeys[0], ws.counters, ws.minmax, ws.bcount));
-    GPET_LAUNCH("k_bucket_scan", s, k_bucket_scan<<<kMaxBuckets / kScanTile, kThreads, 0, s>>>(ws.bcount, ws.bstart, ws.bcur, ws.scan_status[2],
-                                                                                           ws.counters, ws.minmax));
-    GPET_LAUNCH("k_bucket_scatter", s, k_bucket_scatter<<<grid, kThreads, 0, s>>>(ws.tkeys[0], ws.counters, ws.minmax, ws.bcur, bkeys, bidx));
-    GPET_LAUNCH("k_bucket_sort", s, k_bucket_sort<<<2 * grid, kThreads, 0, s>>>(bkeys, bidx, ws.bstart, ws.bcur, ws.counters, ws.minmax, ws.order_t,
-                                                                             ws.tkeys[0]));
-    GPET_LAUNCH("k_lsd_hist", s, k_lsd_hist<<<grid, kThreads, 0, s>>>(ws.tkeys[0], ws.tvals[0], ws.counters, ws.st_time, ws.lookback[0]));
-    launches += 7;
-    launches += radix_sort_passes<unsigned long long>(ws.tkeys, ws.tvals, &ws.counters[0], ws.st_time, ws.lookback, 8, grid, s, lsd);
-    // site keys + site sort (stable => (site, t) order == orderevents, detector.cu:369-385)
-    GPET_LAUNCH("k_site_keys", s, k_site_keys<<<grid, kThreads, 0, s>>>(ev, p, ws.tkeys[0], ws.tkeys[1], ws.tvals[0], ws.tvals[1], ws.st_time,
-                                                                      ws.order_t, ws.skeys[0], ws.svals[0], ws.counters, ws.st_site, ws.lookback[0]));
-    launches += 1;
-    launches += radix_sort_passes<unsigned>(ws.skeys, ws.svals, &ws.counters[1], ws.st_site, ws.lookback, 4, grid, s);
-    GPET_LAUNCH("k_deadtime", s, k_deadtime<<<grid, kThreads, 0, s>>>(p, ws.tkeys[0], ws.skeys[0], ws.skeys[1], ws.svals[0], ws.svals[1], ws.st_site,
-                                                                    ws.kill, ws.counters));
-    GPET_LAUNCH("k_emit_singles", s, k_emit_singles<<<grid, kThreads, 0, s>>>(ev, p, singles, singles_cap, ws.order_t, ws.kill, ws.counters,
-                                                                            ws.scan_status[0], ws.spectrum, ws.spectrum_bins, ws.spec_emin,
-                                                                            ws.spec_emax));
-    launches += 2;
-    if (p.cwin > 0.f && coinc_aos) {
-        GPET_LAUNCH("k_coinc_count", s, k_coinc_count<<<grid, kThreads, 0, s>>>(singles, p, ws.counters, singles_cap, ws.coinc_cnt));
-        GPET_LAUNCH("k_coinc_emit", s, k_coinc_emit<<<grid, kThreads, 0, s>>>(singles, p, ws.coinc_cnt, ws.counters, singles_cap, ws.scan_status[1],
-                                                                            static_cast<gpet_coincidence*>(coinc_aos), coinc_cap));
+    EventRec* singles = static_cast<EventRec*>(out.singles);
+    unsigned long long* keys = ws.tkeys[0];    // by event index; after the sort: the sorted keys (tsort)
+    unsigned long long* bkeys = ws.tkeys[1];   // scatter target; ping-pong partner of the LSD fallback (the two sorts
+                                               // never run in the same frame)
+    GPET_LAUNCH("k_begin", s, k_begin<<<64, kThreads, 0, s>>>(ws.counters, ws.scan_status[0], ws.scan_status[1], ws.scan_status[2],
+                                                             ws.max_tiles, ws.bcount, ws.minmax));
+    launches++;
+    TimeRange tr;
+    if (range) {
+        tr = *range;
+    } else {
+        GPET_LAUNCH("k_range", s, k_range<<<grid, kThreads, 0, s>>>(ev, ws.minmax));
+        launches++;
+        tr.lo = 0.0; tr.hi = 0.0; tr.dev = ws.minmax;
+    }
+    GPET_LAUNCH("k_prep", s, k_prep<<<grid, kThreads, 0, s>>>(ev, p, seed, tr, keys, ws.site_of, ws.aux, ws.bcount, ws.counters));
+    GPET_LAUNCH("k_bucket_scan", s, k_bucket_scan<<<kMaxBuckets / kScanTile, kThreads, 0, s>>>(ws.bcount, ws.bstart, ws.scan_status[2],
+                                                                                           ws.counters, tr));
+    GPET_LAUNCH("k_bucket_scatter", s, k_bucket_scatter<<<grid, kThreads, 0, s>>>(keys, ws.site_of, ws.aux, ws.counters, tr, ws.bstart,
+                                                                                 bkeys, ws.bpay));
+    GPET_LAUNCH("k_bucket_rank", s, k_bucket_rank<<<grid, kThreads, 0, s>>>(bkeys, ws.bpay, ws.bstart, ws.counters, tr, keys, ws.order_t,
+                                                                           ws.site_t));
+    launches += 4;
+    {
+        static int coop_grid = 0;
+        if (!coop_grid) {
+            int per_sm = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lsd_fallback, rsort::kThreads, 0);
+            coop_grid = num_sms * std::max(1, std::min(per_sm, 2));
+        }
+        void* args[] = {&ws.tkeys[0], &ws.tkeys[1], &ws.tvals[0], &ws.tvals[1], &ws.aux, &ws.site_of, &ws.counters, &ws.st_time,
+                        &ws.lookback[0], &ws.lookback[1], &ws.grid_bar, &ws.order_t, &ws.site_t};
+        GPET_LAUNCH("k_lsd_fallback", s,
+                    cudaLaunchCooperativeKernel((const void*)k_lsd_fallback, dim3(coop_grid), dim3(rsort::kThreads), args, 0, s));
+        launches++;
+    }
+    if (p.dtype != 0) {
+        GPET_LAUNCH("k_deadtime_chain", s, k_deadtime_chain<<<grid, kThreads, 0, s>>>(p, keys, ws.site_t, ws.kill, ws.counters));
+        launches++;
+    }
+    GPET_LAUNCH("k_emit_singles", s, k_emit_singles<<<grid, kThreads, 0, s>>>(ev, p, singles, out.singles_cap, keys, ws.order_t, ws.site_t,
+                                                                            ws.kill, ws.counters, ws.scan_status[0], ws.stime, ws.span,
+                                                                            ws.spectrum, ws.spectrum_bins, ws.spec_emin, ws.spec_emax));
+    launches++;
+    if (p.cwin > 0.f && (out.coinc || out.pairs)) {
+        GPET_LAUNCH("k_coinc_count", s, k_coinc_count<<<grid, kThreads, 0, s>>>(ws.stime, ws.span, p, ws.counters, out.singles_cap, ws.coinc_cnt));
+        GPET_LAUNCH("k_coinc_emit", s, k_coinc_emit<<<grid, kThreads, 0, s>>>(singles, ws.stime, ws.span, p, ws.coinc_cnt, ws.counters,
+                                                                            out.singles_cap, ws.scan_status[1],
+                                                                            static_cast<gpet_coincidence*>(out.coinc),
+                                                                            static_cast<uint2*>(out.pairs), out.coinc_cap,
+                                                                            out.pair_base_in, out.pair_base_out));
         launches += 2;
     }
     return launches;

@@ -10,24 +10,35 @@ namespace gpet {
 
 namespace rsort { struct SortState; }
 
+// Time range (us) the time sort slices.  `dev` != nullptr: the range is read from device memory instead, as the u64
+// key images of its ends (dev[0], dev[1]).  The range only shapes the load of the sort, never its result.
+struct TimeRange {
+    double lo, hi;
+    const unsigned long long* dev;
+};
+TimeRange time_range_us(double t_lo_us, double t_hi_us);
+
 struct DigitizerWorkspace {
-    unsigned long long* tkeys[2];  // time sort ping-pong: order-preserving u64 image of the fp64 time
-    unsigned int* tvals[2];        //   payload: event index
-    unsigned int* skeys[2];        // site sort ping-pong: site number with the sign bit flipped
-    unsigned int* svals[2];        //   payload: position in the time order
+    unsigned long long* tkeys[2];  // [0] time keys by event index, then the sorted keys; [1] scatter target / LSD ping-pong
+    unsigned int* tvals[2];        // LSD fallback payload ping-pong (event index | window flag)
+    int* site_of;                  // dead-time site number by event index
+    unsigned int* aux;             // by event index: arrival rank in its time slice | window flag (bit 31)
+    uint2* bpay;                   // scatter target: (event index | window flag, site)
     unsigned int* lookback[2];     // sort_lookback_words(capacity) status words each (radix passes alternate between them)
-    rsort::SortState* st_time;     // device-resident sort bookkeeping (histograms, tile counters, current buffer)
-    rsort::SortState* st_site;
+    rsort::SortState* st_time;     // LSD fallback bookkeeping (histograms, tile counters)
+    unsigned int* grid_bar;        // grid barrier of the cooperative fallback kernel (2 words, zeroed once)
     unsigned int* scan_status[3];  // status words of the chained scans: singles compaction, coincidence compaction (max_tiles
                                    // each), slice counters of the bucket sort (bucket_words() / 2048)
-    unsigned int* bcount;          // bucket sort of the time keys: events per slice, slice starts, scatter cursors
-    unsigned int* bstart;          //   (bucket_words() entries each)
-    unsigned int* bcur;
-    unsigned long long* minmax;    // [0] smallest, [1] largest time key of the alive records
+    unsigned int* bcount;          // bucket sort of the time keys: events per slice, slice starts (bucket_words() entries each)
+    unsigned int* bstart;
+    unsigned long long* minmax;    // [0] smallest, [1] largest time key (k_range, replay entry)
     unsigned int max_tiles;
     unsigned int capacity;
-    unsigned int* order_t;         // event index in time order (first counters[1] entries alive)
-    unsigned char* kill;           // per time-order position: 1 = removed by dead time
+    unsigned int* order_t;         // event index | window flag, in time order (first counters[1] entries)
+    int* site_t;                   // site number in time order
+    unsigned char* kill;           // per time-order position: 1 = removed by dead time (non-paralyzable chain)
+    double* stime;                 // per single: time, panel (what the coincidence sorter reads)
+    int* span;
     unsigned int* coinc_cnt;       // per single: coincidences it opens
     // [0] n_in [1] after thresholder [2] after deadtime [3] singles [4] coincidences [6],[7] tile tickets of the two
     // compactions [8] photons on a panel [9] adder drops [10],[11] photon tickets of k_detector / k_front [12] time sort
@@ -36,14 +47,26 @@ struct DigitizerWorkspace {
     unsigned long long* spectrum; int spectrum_bins; float spec_emin, spec_emax;
 };
 
+// Where one frame's results go (device memory).
+struct DigitizerOut {
+    void* singles;                 // 48-byte records, time sorted
+    unsigned int singles_cap;
+    void* coinc;                   // 96-byte coincidence records, or nullptr
+    void* pairs;                   // uint2 index pairs into the run's singles list, or nullptr
+    unsigned int coinc_cap;
+    const unsigned int* pair_base_in;   // singles of the run's earlier frames (device word), nullptr = 0
+    unsigned int* pair_base_out;        // receives *pair_base_in + this frame's singles, or nullptr
+};
+
 size_t sort_state_bytes();
 size_t sort_lookback_words(size_t capacity);   // status words one radix pass needs for `capacity` keys
 unsigned scan_tiles(size_t capacity);          // status words of the compaction scans
 unsigned bucket_words();                       // slice counters of the bucket sort
 
 // ---- digitizer (digitizer.cu) --------------------------------------------------------------------------
-int launch_digitize(EventBuf ev, void* singles_aos, unsigned int singles_cap, void* coinc_aos, unsigned int coinc_cap,
-                    const DigitizerDev& p, DigitizerWorkspace& ws, uint64_t seed, int num_sms, cudaStream_t s);
+// range == nullptr: the key range is measured on the device first (replay entry)
+int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p, DigitizerWorkspace& ws, const TimeRange* range,
+                    uint64_t seed, int num_sms, cudaStream_t s);
 
 // ---- transport (transport.cu) ----------------------------------------------------------------------------
 int launch_source(const SourceDev* frame_dev, unsigned long long npairs, PhantomDev ph, PhotonQueue q0,

@@ -262,6 +262,15 @@ int gpet_run(gpet_ctx* ctx, const char* output_dir, gpet_stats* stats);
 int gpet_run_resident(gpet_ctx* ctx, gpet_stats* stats);
 int64_t gpet_result_singles(gpet_ctx* ctx, const gpet_event** ptr);
 int64_t gpet_result_coincidences(gpet_ctx* ctx, const gpet_coincidence** ptr);
+/* How gpet_run brings coincidences to the host (extension, like the sorter itself).  GPET_COINC_RECORDS (default): the
+ * two 48-byte singles side by side, 96 B per coincidence.  GPET_COINC_PAIRS: two uint32 indices into the run's singles
+ * list (gpet_result_singles), 8 B per coincidence -- the records are a gather the host can do when it needs them:
+ * gpet_result_coincidences builds them on demand, and coincidences.dat is written from them, so both formats give
+ * the same files and the same records. */
+enum { GPET_COINC_RECORDS = 0, GPET_COINC_PAIRS = 1 };
+int gpet_set_coincidence_format(gpet_ctx* ctx, int format);
+/* *ptr = pairs (2 x uint32 each: earlier single, later single); returns their number (0 in GPET_COINC_RECORDS mode). */
+int64_t gpet_result_coincidence_pairs(gpet_ctx* ctx, const uint32_t** ptr);
 int gpet_get_stats(const gpet_ctx* ctx, gpet_stats* stats);
 /* Energy spectrum tally of the accumulated singles (nbins over [emin, emax)), kept on device during the run;
  * this is what multi-GPU runs all-reduce. */

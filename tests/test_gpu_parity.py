@@ -381,6 +381,35 @@ def test_run_is_reproducible_and_shards_by_frame(tmp_path):
     assert s_c.tobytes() != s_a.tobytes()
 
 
+@needs_tables
+def test_coincidence_pairs_equal_coincidence_records(tmp_path):
+    """GPET_COINC_PAIRS (8-byte index pairs into the singles list, base carried on the device from frame to frame) is the
+    same answer as GPET_COINC_RECORDS: same records on demand, same coincidences.dat."""
+    ex = make_example_dir(tmp_path, source="source.txt", window="0 20")
+    out = {}
+    for fmt in (api.Context.COINC_RECORDS, api.Context.COINC_PAIRS):
+        od = tmp_path / f"out{fmt}"
+        od.mkdir()
+        with api.Context(0) as c:
+            c.set_seed(5)
+            c.set_capacity(1 << 17, 1 << 19, 1 << 18)
+            c.load_config_file(ex / "input_PET.in", base_dir=ex)
+            c.set_digitizer(coinc_window_us=0.01)
+            c.set_coincidence_format(fmt)
+            st = c.run(None)
+            out[fmt] = (st, c.result_singles(), c.result_coincidences(), c.result_coincidence_pairs())
+            st2 = c.run(od)      # file path (frame by frame)
+            assert st2.coincidences == st.coincidences
+            out[fmt] += (refio.read_coincidences(od / "coincidences.dat"),)
+    (st_r, s_r, co_r, p_r, f_r), (st_p, s_p, co_p, p_p, f_p) = out[0], out[1]
+    assert st_r.frames >= 3 and st_r.coincidences == st_p.coincidences > 100
+    assert s_r.tobytes() == s_p.tobytes()
+    assert p_r.shape[0] == 0 and p_p.shape[0] == st_p.coincidences
+    assert co_r.tobytes() == co_p.tobytes() == f_r.tobytes() == f_p.tobytes()
+    assert np.all(p_p[:, 0] < p_p[:, 1]) and p_p.max() < s_p.size
+    assert s_p[p_p[:, 0]].tobytes() == co_p["a"].tobytes() and s_p[p_p[:, 1]].tobytes() == co_p["b"].tobytes()
+
+
 # ------------------------------------------------------------------------------------------------ positron range / positron PSF
 def water_box(n=40, size=2.0):
     mat = np.ones((n, n, n), np.int32); den = np.ones((n, n, n), np.float32)

@@ -41,9 +41,9 @@ def main():
         def frame():
             if a.staged:
                 c.stage_source(0); c.stage_phantom(); c.stage_detector()
+                c.stage_digitize()
             else:
-                c.stage_front(0); c.stage_panel_transport()
-            c.stage_digitize()
+                c.run_resident()   # the product path: fused front end, digitizer sliced by the frame's time range
 
         for _ in range(3):
             frame()
