@@ -208,9 +208,7 @@ ALG_BYTES = {
     "k_bucket_rank": lambda c: 16 * c["alive"] + 16 * c["alive"],
     "k_deadtime_chain": lambda c: 12 * c["alive"] + c["alive"],
     "k_emit_singles": lambda c: 16 * c["alive"] + 48 * c["singles"] + (48 + 12) * c["singles"],
-    "k_coinc_count": lambda c: 12 * c["singles"] + 4 * c["singles"],
-    "k_coinc_emit": lambda c: 4 * c["singles"] + 8 * c["coinc"],
-    "k_begin": lambda c: 4 * 2 ** 19,
+    "k_coinc": lambda c: 12 * c["singles"] + 8 * c["coinc"],
 }
 
 

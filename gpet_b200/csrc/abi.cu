@@ -64,9 +64,26 @@ int ensure_buffers(gpet_ctx* c) {
     int r;
     const size_t cp = c->cap_photons, ch = c->cap_hits, ce = c->cap_events;
     DigitizerWorkspace& w = c->ws;
-    // every device-side counter lives in one 64-word block, so one small D2H brings all of them back
-    if ((r = dev_alloc(c, &w.counters, 64))) return r;
-    CK(cudaMemset(w.counters, 0, 64 * sizeof(unsigned)));
+    // Per-frame device state in ONE block, cleared by one memset per frame: the 64-word counter block (every device-side
+    // counter, so one small D2H brings all of them back), the status words of the three scans, the key range, the slice
+    // counters of the time sort.
+    w.capacity = (unsigned)ce;
+    w.max_tiles = scan_tiles(ce);
+    {
+        const size_t mt4 = ((size_t)w.max_tiles + 3) & ~(size_t)3, st2 = (size_t)bucket_words() / 2048 + 4;   // 16-byte segments
+        const size_t words = 64 + 2 * mt4 + st2 + 4 + (size_t)bucket_words();
+        unsigned* p = nullptr;
+        if ((r = dev_alloc(c, &p, words))) return r;
+        CK(cudaMemset(p, 0, words * sizeof(unsigned)));
+        w.frame_state = p;
+        w.frame_state_bytes = words * sizeof(unsigned);
+        w.counters = p; p += 64;
+        w.scan_status[0] = p; p += mt4;
+        w.scan_status[1] = p; p += mt4;
+        w.scan_status[2] = p; p += st2;
+        w.minmax = reinterpret_cast<unsigned long long*>(p); p += 4;
+        w.bcount = p;
+    }
     if ((r = alloc_queue(c, c->q[0], cp, w.counters + 16))) return r;
     if ((r = alloc_queue(c, c->q[1], cp, w.counters + 17))) return r;
     if ((r = alloc_queue(c, c->q[2], cp, w.counters + 21))) return r;   // photons that entered a panel (panel-local frame)
@@ -88,17 +105,11 @@ int ensure_buffers(gpet_ctx* c) {
     if ((r = dev_alloc(c, &w.site_t, ce))) return r;
     if ((r = dev_alloc(c, &w.stime, ce))) return r;
     if ((r = dev_alloc(c, &w.span, ce))) return r;
-    w.capacity = (unsigned)ce;
-    w.max_tiles = scan_tiles(ce);
     for (int k = 0; k < 2; k++) {
         if ((r = dev_alloc(c, &w.lookback[k], sort_lookback_words(ce)))) return r;
         CK(cudaMemset(w.lookback[k], 0, sort_lookback_words(ce) * sizeof(unsigned)));
-        if ((r = dev_alloc(c, &w.scan_status[k], (size_t)w.max_tiles))) return r;
     }
-    if ((r = dev_alloc(c, &w.scan_status[2], (size_t)bucket_words() / 2048 + 1))) return r;
-    if ((r = dev_alloc(c, &w.bcount, (size_t)bucket_words()))) return r;
     if ((r = dev_alloc(c, &w.bstart, (size_t)bucket_words()))) return r;
-    if ((r = dev_alloc(c, &w.minmax, 2))) return r;
     if ((r = dev_alloc(c, &w.grid_bar, 4))) return r;
     CK(cudaMemset(w.grid_bar, 0, 4 * sizeof(unsigned)));
     if ((r = dev_alloc(c, &c->d_pair_base, 2))) return r;
@@ -378,6 +389,7 @@ void gpet_destroy(gpet_ctx* c) {
         for (int k = 0; k < 2; k++) {
             if (c->h_slot_counters[k]) cudaFreeHost(c->h_slot_counters[k]);
             if (c->ev_counters[k]) cudaEventDestroy(c->ev_counters[k]);
+            if (c->ev_run[k]) cudaEventDestroy(c->ev_run[k]);
             if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
         }
         if (c->res_singles.p) cudaFreeHost(c->res_singles.p);
@@ -773,7 +785,7 @@ int gpet_stage_detector(gpet_ctx* c) {
     c->stats.kernel_launches += launch_panel_entry(c->q[1], c->q[2], detector_dev(c), c->ws.counters, c->num_sms, c->stream);
     c->stats.kernel_launches += launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth,
                                                 c->dig.readout_policy, c->tr.record_hits, c->hits, c->ev, c->ws.counters,
-                                                c->seed, c->num_sms, c->stream);
+                                                c->seed, c->num_sms, c->stream, !c->in_run);
     CK(cudaGetLastError());
     return GPET_OK;
 }
@@ -796,7 +808,7 @@ int gpet_stage_front(gpet_ctx* c, int64_t f) {
         npairs = fp.npairs;
     }
     c->stats.kernel_launches += launch_front(fr, npairs, c->q[0], c->q[1], c->q[2], phantom_dev(c), tables_dev(c), detector_dev(c),
-                                             c->tr.eabs_eV, c->ws.counters, c->seed, c->num_sms, c->stream);
+                                             c->tr.eabs_eV, c->ws.counters, c->seed, c->num_sms, c->stream, !c->in_run);
     CK(cudaGetLastError());
     return GPET_OK;
 }
@@ -809,7 +821,7 @@ int gpet_stage_panel_transport(gpet_ctx* c) {
     if ((r = upload_geometry(c))) return r;
     c->stats.kernel_launches += launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth,
                                                 c->dig.readout_policy, c->tr.record_hits, c->hits, c->ev, c->ws.counters,
-                                                c->seed, c->num_sms, c->stream);
+                                                c->seed, c->num_sms, c->stream, !c->in_run);
     CK(cudaGetLastError());
     return GPET_OK;
 }
@@ -832,7 +844,7 @@ int gpet_stage_digitize(gpet_ctx* c) {
     } else {
         out.coinc = c->coinc_aos;
     }
-    c->stats.kernel_launches += launch_digitize(c->ev, out, d, c->ws, c->have_range ? &c->range : nullptr, c->seed, c->num_sms, c->stream);
+    c->stats.kernel_launches += launch_digitize(c->ev, out, d, c->ws, c->have_range ? &c->range : nullptr, c->seed, c->num_sms, c->stream, !c->in_run);
     CK(cudaGetLastError());
     return GPET_OK;
 }
@@ -1113,9 +1125,11 @@ int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* sta
         explicit InRun(gpet_ctx* c_) : c(c_) { c->in_run = true; c->run_frame = 0; }
         ~InRun() { c->in_run = false; c->have_range = false; }
     } in_run(c);
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
+    if (!c->ev_run[0]) {
+        CK(cudaEventCreate(&c->ev_run[0]));
+        CK(cudaEventCreate(&c->ev_run[1]));
+    }
+    cudaEvent_t e0 = c->ev_run[0], e1 = c->ev_run[1];
     CK(cudaEventRecord(e0, c->stream));
     // simulateParticle batches: NPART photons, or NPART/2 positrons that become NPART photons (gPET.cu:33-44)
     const int64_t psf_batch = (psf_mode && c->psf.ptype == 0) ? (int64_t)(c->cap_photons / 2) : (int64_t)c->cap_photons;
@@ -1131,6 +1145,8 @@ int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* sta
         c->singles_aos = c->singles_slot[slot];
         c->coinc_aos = c->coinc_slot[slot];
         if (k >= 2 && !resident) CK(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
+        // one memset clears every counter, ticket, status word and slice counter of the frame
+        CK(cudaMemsetAsync(c->ws.frame_state, 0, c->ws.frame_state_bytes, c->stream));
         // fused front end: photons stay in registers from birth (or from queue 0 in PSF mode) to the panel face
         if (psf_mode) {
             int64_t first = f * psf_batch, n = std::min<int64_t>(psf_batch, (int64_t)c->psf.p.size() - first);
@@ -1162,8 +1178,6 @@ int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* sta
     if (rc != GPET_OK) {
         cudaStreamSynchronize(c->stream);
         cudaStreamSynchronize(c->copy_stream);
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
         return rc;
     }
     CK(cudaEventRecord(e1, c->stream));
@@ -1171,8 +1185,6 @@ int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* sta
     CK(cudaStreamSynchronize(c->copy_stream));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     st.ms_total = ms;
     st.kernel_launches = c->stats.kernel_launches - launches0;
     const uint64_t keep = c->stats.kernel_launches;

@@ -71,6 +71,7 @@ struct gpet_ctx {
     gpet::TimeRange range{};
     unsigned* h_slot_counters[2] = {nullptr, nullptr};   // pinned, 32 words each
     cudaEvent_t ev_counters[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_run[2] = {nullptr, nullptr};          // start / end of the last run (gpet_stats.ms_total)
     cudaStream_t copy_stream = nullptr;
     int out_slot = 0;
     void* stage_aos = nullptr;       // cap * 48 B staging for AoS <-> SoA conversion

@@ -12,7 +12,7 @@
 // caller (the frame's time slice) or from k_range (replay entry); keys outside it are clamped into the end slices, so
 // the range only shapes the load, never the result.  If a slice holds more than kBucketLimit events (times clustered
 // far below the range: never the case for decay data, but legal input of the replay entry point) k_bucket_scan raises
-// counters[12] and ONE persistent cooperative kernel, k_lsd_fallback, runs the stable LSD radix sort of radix_sort.cuh
+// counters[5] and ONE persistent cooperative kernel, k_lsd_fallback, runs the stable LSD radix sort of radix_sort.cuh
 // (all passes, grid barriers in between); it is always enqueued and returns at once when the flag is clear.
 //
 // Dead time (D6, D7) needs no sort by site: in the reference's (site, t) order the predecessor of an event is the
@@ -21,8 +21,8 @@
 // at the first event of its own site (paralyzable: that event kills it) -- O(events inside one dead time) per event.
 // The non-paralyzable chain is cut at the events their predecessor cannot kill (k_deadtime_chain).
 //
-// Launches per frame: k_begin, [k_range], k_prep, k_bucket_scan, k_bucket_scatter, k_bucket_rank, k_lsd_fallback
-// (normally empty), [k_deadtime_chain: non-paralyzable only], k_emit_singles [, k_coinc_count, k_coinc_emit].
+// Launches per frame: [k_range], k_prep, k_bucket_scan, k_bucket_scatter, k_bucket_rank, k_lsd_fallback
+// (normally empty), [k_deadtime_chain: non-paralyzable only], k_emit_singles [, k_coinc].
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -41,7 +41,7 @@ constexpr int kThreads = 256;
 constexpr int kMaxLogBuckets = 19;
 constexpr unsigned kMaxBuckets = 1u << kMaxLogBuckets;
 constexpr unsigned kBucketLimit = 1024;   // a fuller slice sends the time sort to the LSD fallback
-constexpr int kFlagLsd = 12;              // counters[kFlagLsd] != 0: time sort by LSD radix passes
+constexpr int kFlagLsd = 5;               // counters[kFlagLsd] != 0: time sort by LSD radix passes
 constexpr int kGroup = 256;               // slices ranked by one block at a time
 constexpr int kRankCap = 3840;            // events of a slice group that are ranked out of shared memory
 constexpr unsigned kEwinBit = 0x80000000u;  // payload bit: the record is inside the final energy window
@@ -71,7 +71,7 @@ struct BucketMap {
 
 __device__ __forceinline__ BucketMap bucket_map(const TimeRange& r, unsigned n) {
     BucketMap m;
-    const double lo = r.dev ? key_time(r.dev[0]) : r.lo, hi = r.dev ? key_time(r.dev[1]) : r.hi;
+    const double lo = r.dev ? key_time(~r.dev[0]) : r.lo, hi = r.dev ? key_time(r.dev[1]) : r.hi;
     int lognb = (n > 1 ? 32 - __clz((int)(n - 1)) : 0) - 3;   // ceil(log2 n) - 3: about 8 events per slice
     lognb = min(max(lognb, 6), kMaxLogBuckets);
     m.nb = 1u << lognb;
@@ -90,22 +90,6 @@ __device__ __forceinline__ unsigned bucket_of(const BucketMap& m, unsigned long 
 // and fp32 sum (gPET_kernals.cu:670-676); monotone in t_prev
 __device__ __forceinline__ double dead_until(double t_prev, float tau) { return (double)__fadd_rn((float)t_prev, tau); }
 
-// ------------------------------------------------------------------------------------------- stage 0: reset
-// counters[0..7] and the fallback flag, the scan status words, the slice counters, the key range.
-__global__ void __launch_bounds__(kThreads) k_begin(unsigned* __restrict__ counters, unsigned* __restrict__ scan_status0,
-                                                    unsigned* __restrict__ scan_status1, unsigned* __restrict__ scan_status2,
-                                                    unsigned max_tiles, unsigned* __restrict__ bcount,
-                                                    unsigned long long* __restrict__ minmax) {
-    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    if (tid < 8) counters[tid] = 0;
-    if (tid == 8) counters[kFlagLsd] = 0;
-    if (tid == 9) { minmax[0] = ~0ull; minmax[1] = 0ull; }
-    for (unsigned i = tid; i < max_tiles; i += nth) { scan_status0[i] = 0; scan_status1[i] = 0; }
-    for (unsigned i = tid; i < kMaxBuckets / 2048u; i += nth) scan_status2[i] = 0;
-    uint4* b4 = reinterpret_cast<uint4*>(bcount);
-    for (unsigned i = tid; i < kMaxBuckets / 4u; i += nth) b4[i] = make_uint4(0u, 0u, 0u, 0u);
-}
-
 // replay entry only: key range of the records that are not dead on arrival
 __global__ void __launch_bounds__(kThreads) k_range(EventBuf ev, unsigned long long* __restrict__ minmax) {
     const unsigned n = min(*ev.count, ev.capacity);
@@ -123,8 +107,8 @@ __global__ void __launch_bounds__(kThreads) k_range(EventBuf ev, unsigned long l
         kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
         kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
     }
-    if ((threadIdx.x & 31) == 0 && kmin <= kmax) {
-        atomicMin(&minmax[0], kmin);
+    if ((threadIdx.x & 31) == 0 && kmin <= kmax) {   // the smallest key is kept inverted, so that all zeros means "empty"
+        atomicMax(&minmax[0], ~kmin);
         atomicMax(&minmax[1], kmax);
     }
 }
@@ -150,8 +134,12 @@ __global__ void __launch_bounds__(kThreads) k_prep(EventBuf ev, DigitizerDev p, 
         float R = 0.f;
         // float / double mix exactly as the reference expression is typed
         if (p.blur_policy == 0) R = __fmul_rn(__fsqrt_rn(__fdiv_rn(p.Eref, E)), p.Rref);
-        if (p.blur_policy == 1)
-            R = (float)__dadd_rn((double)p.Rref, __ddiv_rn((double)__fmul_rn(p.slope, __fsub_rn(E, p.Eref)), 1e6));
+        if (p.blur_policy == 1) {
+            // slope == 0 (the shipped setting): the quotient is +-0 and Rref + (+-0) = Rref, without the fp64 divide
+            const float dE = __fsub_rn(E, p.Eref);
+            if (p.slope == 0.f && fabsf(dE) <= 3.0e38f) R = p.Rref;
+            else R = (float)__dadd_rn((double)p.Rref, __ddiv_rn((double)__fmul_rn(p.slope, dE), 1e6));
+        }
         if (!(R > 0.f)) R = 0.f;
         // R == 0 leaves E bit-identical (E + 0), so the draw is skipped: this is the deterministic replay mode
         if (R > 0.f || p.sblur > 0.f || p.tblur > 0.f) {
@@ -200,11 +188,15 @@ __global__ void __launch_bounds__(kThreads) k_prep(EventBuf ev, DigitizerDev p, 
 }
 
 // ------------------------------------------------------------------------------------------- single-pass exclusive scan
-// Tiles of 2048 elements (thread = 8 consecutive elements) claimed in order from a device counter; the running
-// total travels from tile to tile through one status word per tile (aggregate / inclusive-prefix flags, 30-bit
-// values), so flagging, scanning and compacting happen in ONE kernel.
+// Tiles of 2048 elements (thread = 8 consecutive elements), claimed in order (ticket or block index with all blocks
+// resident), so every earlier tile belongs to a running or finished block.  A tile publishes its total in one status
+// word and then adds up the words of ALL earlier tiles, one word per thread and round: at frame sizes (<= a few
+// thousand tiles) that is one L2 round trip, where a chained look-back walks ~40 ns per tile (measured:
+// tools/microbench/latency.cu, 23 us for 343 tiles) because all tiles of these short kernels start at the same time
+// and find no finished prefix to stop at.  So flagging, scanning and compacting happen in ONE kernel.
 constexpr int kScanTile = 2048;
 constexpr int kSpecSmemBins = 1024;
+constexpr unsigned kPublished = 1u << 31;
 
 struct TileScan {
     unsigned excl[8];    // exclusive prefix of each of the thread's 8 elements (global)
@@ -212,9 +204,18 @@ struct TileScan {
     unsigned tile_excl;  // sum over all earlier tiles
 };
 
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ TileScan tile_exclusive_scan(const unsigned v[8], unsigned tile, unsigned* __restrict__ status) {
     __shared__ unsigned ws[kThreads / 32];
-    __shared__ unsigned s_excl;
+    __shared__ unsigned wx[kThreads / 32];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned s = 0;
 #pragma unroll
@@ -234,25 +235,28 @@ __device__ __forceinline__ TileScan tile_exclusive_scan(const unsigned v[8], uns
         if (w < warp) wprefix += c;
         total += c;
     }
-    if (threadIdx.x == 0) {
-        unsigned excl = 0;
-        if (tile == 0) {
-            rsort::st_volatile(&status[0], rsort::kFlagPrefix | total);
-        } else {
-            rsort::st_volatile(&status[tile], rsort::kFlagAggregate | total);
-            excl = rsort::lookback_sum(status, 1, tile);
-            rsort::st_volatile(&status[tile], rsort::kFlagPrefix | (excl + total));
-        }
-        s_excl = excl;
+    if (threadIdx.x == 0) st_relaxed(&status[tile], kPublished | total);
+    // totals of all earlier tiles (a word that is not published yet is read again)
+    unsigned before = 0;
+    for (unsigned i = threadIdx.x; i < tile; i += kThreads) {
+        unsigned w;
+        do { w = ld_relaxed(&status[i]); } while (!(w & kPublished));
+        before += w & ~kPublished;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0) wx[warp] = before;
     __syncthreads();
+    unsigned excl_tile = 0;
+#pragma unroll
+    for (unsigned w = 0; w < kThreads / 32; w++) excl_tile += wx[w];
     TileScan r;
     r.tile_total = total;
-    r.tile_excl = s_excl;
-    unsigned e = s_excl + wprefix + (x - s);
+    r.tile_excl = excl_tile;
+    unsigned e = excl_tile + wprefix + (x - s);
 #pragma unroll
     for (int k = 0; k < 8; k++) { r.excl[k] = e; e += v[k]; }
-    __syncthreads();  // ws / s_excl are reused by the next tile
+    __syncthreads();  // ws / wx are reused by the next tile
     return r;
 }
 
@@ -262,16 +266,16 @@ __device__ __forceinline__ TileScan tile_exclusive_scan(const unsigned v[8], uns
 __global__ void __launch_bounds__(kThreads) k_bucket_scan(const unsigned* __restrict__ bcount, unsigned* __restrict__ bstart,
                                                           unsigned* __restrict__ status, unsigned* __restrict__ counters,
                                                           TimeRange range) {
-    const BucketMap m = bucket_map(range, counters[0]);
     const unsigned tile = blockIdx.x;
-    if (tile * kScanTile >= m.nb) return;
     const unsigned b0 = tile * kScanTile + threadIdx.x * 8;
     unsigned c[8];
     bool over = false;
-    {
+    {   // issued before the slice count is known (it hangs on a load of its own)
         const uint4 lo = reinterpret_cast<const uint4*>(bcount + b0)[0], hi = reinterpret_cast<const uint4*>(bcount + b0)[1];
         c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w; c[4] = hi.x; c[5] = hi.y; c[6] = hi.z; c[7] = hi.w;
     }
+    const BucketMap m = bucket_map(range, counters[0]);
+    if (tile * kScanTile >= m.nb) return;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         if (b0 + k >= m.nb) c[k] = 0u;
@@ -293,13 +297,29 @@ __global__ void __launch_bounds__(kThreads) k_bucket_scatter(const unsigned long
     if (counters[kFlagLsd]) return;
     const unsigned n = counters[0];
     const BucketMap m = bucket_map(range, n);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned long long key = keys[i];
-        if (key == ~0ull) continue;
-        const unsigned a = aux[i];
-        const unsigned pos = __ldg(&bstart[bucket_of(m, key)]) + (a & ~kEwinBit);
-        bkeys[pos] = key;
-        bpay[pos] = make_uint2(i | (a & kEwinBit), (unsigned)site_of[i]);
+    const unsigned nth = gridDim.x * blockDim.x;
+    // four independent elements per thread and round: the dependent gather of the slice start is the latency to hide
+    for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * nth) {
+        unsigned long long key[4];
+        unsigned a[4], pos[4];
+        int site[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned i = i0 + u * nth;
+            key[u] = i < n ? keys[i] : ~0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned i = i0 + u * nth;
+            if (key[u] != ~0ull) { a[u] = aux[i]; site[u] = site_of[i]; pos[u] = __ldg(&bstart[bucket_of(m, key[u])]); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (key[u] == ~0ull) continue;
+            const unsigned i = i0 + u * nth, o = pos[u] + (a[u] & ~kEwinBit);
+            bkeys[o] = key[u];
+            bpay[o] = make_uint2(i | (a[u] & kEwinBit), (unsigned)site[u]);
+        }
     }
 }
 
@@ -451,6 +471,11 @@ __global__ void __launch_bounds__(kThreads) k_deadtime_chain(DigitizerDev p, con
 // ------------------------------------------------------------------------------------------- stage 4: energy window + compaction -> singles
 // dead time (paralyzable: decided here) + energywindow(Ewinmin, Ewinmax) (gPET.cu:418) over the time order; survivors are
 // compacted into the singles list, their times and panels into two side arrays for the coincidence sorter.
+// A tile's times and sites are staged in shared memory with a halo of earlier events, so the backward walks of the
+// dead time run out of shared memory; the survivors' records are gathered as 16-byte pieces, eight independent loads
+// per thread in flight, and leave as consecutive 16-byte stores.
+constexpr int kHalo = 64;
+
 __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, DigitizerDev p, EventRec* __restrict__ singles,
                                                            unsigned singles_cap, const unsigned long long* __restrict__ tsort,
                                                            const unsigned* __restrict__ order_t, const int* __restrict__ site_t,
@@ -459,11 +484,15 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, Digitize
                                                            int* __restrict__ span, unsigned long long* __restrict__ spectrum,
                                                            int nbins, float emin, float emax) {
     __shared__ unsigned s_tile;
+    __shared__ double s_t[kHalo + kScanTile];
+    __shared__ int s_site[kHalo + kScanTile];
     __shared__ unsigned s_idx[kScanTile];
+    __shared__ __align__(16) unsigned char s_flag[kScanTile];
     __shared__ unsigned s_spec[kSpecSmemBins];   // block-private energy histogram (flushed once per block)
     const unsigned n1 = counters[1];
     const unsigned ntiles = (n1 + kScanTile - 1) / kScanTile;
     const bool spec_smem = spectrum && nbins > 0 && nbins <= kSpecSmemBins;
+    const float tau = p.dtime;
     if (spec_smem)
         for (int b = threadIdx.x; b < nbins; b += blockDim.x) s_spec[b] = 0;
     unsigned c2 = 0;
@@ -472,52 +501,101 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, Digitize
         __syncthreads();
         const unsigned tile = s_tile;
         if (tile >= ntiles) break;
-        const unsigned j0 = tile * kScanTile + threadIdx.x * 8;
-        unsigned idx[8], flag[8];
+        const unsigned jt = tile * kScanTile;                 // first position of the tile
+        const unsigned j0 = jt + threadIdx.x * 8;
+        // this thread's 8 consecutive payloads (scan layout); issued first, used after the flags are known
+        unsigned pv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) pv[k] = (j0 + k < n1) ? order_t[j0 + k] : 0u;
+        // stage [jt - kHalo, jt + kScanTile)
+        for (int e = threadIdx.x; e < kHalo + kScanTile; e += kThreads) {
+            const long long j = (long long)jt - kHalo + e;
+            if (j >= 0 && j < (long long)n1) {
+                s_t[e] = key_time(tsort[j]);
+                s_site[e] = site_t[j];
+            }
+        }
+        __syncthreads();
+        // flags, one element per thread and round (conflict-free shared-memory walks)
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const unsigned j = j0 + k;
-            flag[k] = 0; idx[k] = 0;
+            const int e = kHalo + k * kThreads + threadIdx.x;
+            const unsigned j = jt + k * kThreads + threadIdx.x;
+            unsigned char f = 2;   // 2: beyond the list, 1: removed by dead time, 0: survives it
             if (j < n1) {
-                const unsigned pv = order_t[j];
-                idx[k] = pv & ~kEwinBit;
                 bool dead;
-                if (p.dtype == 0) dead = killed_by_predecessor(tsort, site_t, j, key_time(tsort[j]), site_t[j], p.dtime);
-                else dead = kill[j] != 0;
-                flag[k] = (!dead && (pv & kEwinBit)) ? 1u : 0u;
+                if (p.dtype == 0) {
+                    const double t = s_t[e];
+                    const int site = s_site[e];
+                    dead = false;
+                    int q = e - 1;
+                    const int qmin = jt >= (unsigned)kHalo ? 0 : kHalo - (int)jt;   // first staged entry
+                    for (; q >= qmin; q--) {
+                        if (!(t < dead_until(s_t[q], tau))) break;
+                        if (s_site[q] == site) { dead = true; break; }
+                    }
+                    if (q < qmin && qmin == 0 && jt > (unsigned)kHalo)   // the walk left the halo: go on in global memory
+                        dead = killed_by_predecessor(tsort, site_t, jt - kHalo, t, site, tau);
+                } else {
+                    dead = kill[j] != 0;
+                }
+                f = dead ? 1 : 0;
                 c2 += dead ? 0u : 1u;
+            }
+            s_flag[k * kThreads + threadIdx.x] = f;
+        }
+        __syncthreads();
+        unsigned flag[8];
+        {
+            const uint2 f8 = reinterpret_cast<const uint2*>(s_flag)[threadIdx.x];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const unsigned f = ((k < 4 ? f8.x : f8.y) >> (8 * (k & 3))) & 0xffu;
+                flag[k] = (f == 0u && (pv[k] & kEwinBit)) ? 1u : 0u;
             }
         }
         TileScan sc = tile_exclusive_scan(flag, tile, status);
         if (tile == ntiles - 1 && threadIdx.x == 0) counters[3] = sc.tile_excl + sc.tile_total;
-        // survivors of this tile, in order, through shared memory: the emission below is then one record per thread
-        // and iteration, written as three 16-byte vectors to consecutive addresses
 #pragma unroll
         for (int k = 0; k < 8; k++)
-            if (flag[k]) s_idx[sc.excl[k] - sc.tile_excl] = idx[k];
+            if (flag[k]) s_idx[sc.excl[k] - sc.tile_excl] = pv[k] & ~kEwinBit;
         __syncthreads();
-        for (unsigned r = threadIdx.x; r < sc.tile_total; r += 2 * kThreads) {
-            const unsigned r2 = r + kThreads;
-            const bool two = r2 < sc.tile_total;
-            const unsigned o = sc.tile_excl + r, o2 = sc.tile_excl + r2;
-            const EventRec a = load_event_rec(ev.rec + s_idx[r]);
-            EventRec b = a;
-            if (two) b = load_event_rec(ev.rec + s_idx[r2]);
-            if (o < singles_cap) { store_event_rec(singles + o, a); stime[o] = a.t; span[o] = a.pann; }
-            if (two && o2 < singles_cap) { store_event_rec(singles + o2, b); stime[o2] = b.t; span[o2] = b.pann; }
-            if (spectrum && nbins > 0) {
-                float f = (a.E - emin) / (emax - emin) * nbins;
-                if (f >= 0.f && f < (float)nbins) {
-                    if (spec_smem) atomicAdd(&s_spec[(int)f], 1u);
-                    else atomicAdd(&spectrum[(int)f], 1ull);
+        // gather: piece l = 3 * r + part of the r-th survivor of the tile
+        const unsigned npieces = 3u * sc.tile_total;
+        const int4* __restrict__ src = reinterpret_cast<const int4*>(ev.rec);
+        int4* __restrict__ dst = reinterpret_cast<int4*>(singles);
+        for (unsigned l0 = 0; l0 < npieces; l0 += 8 * kThreads) {
+            int4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const unsigned l = l0 + u * kThreads + threadIdx.x;
+                if (l < npieces) {
+                    const unsigned r = l / 3u, part = l - 3u * r;
+                    v[u] = __ldg(src + 3ull * s_idx[r] + part);
                 }
-                f = (b.E - emin) / (emax - emin) * nbins;
-                if (two && f >= 0.f && f < (float)nbins) {
-                    if (spec_smem) atomicAdd(&s_spec[(int)f], 1u);
-                    else atomicAdd(&spectrum[(int)f], 1ull);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const unsigned l = l0 + u * kThreads + threadIdx.x;
+                if (l >= npieces) continue;
+                const unsigned r = l / 3u, part = l - 3u * r;
+                const unsigned o = sc.tile_excl + r;
+                if (o >= singles_cap) continue;
+                dst[3ull * o + part] = v[u];
+                if (part == 0) {
+                    span[o] = v[u].y;
+                } else if (part == 1) {
+                    stime[o] = __longlong_as_double((long long)(((unsigned long long)(unsigned)v[u].w << 32) | (unsigned)v[u].z));
+                } else if (spectrum && nbins > 0) {
+                    const float f = (__int_as_float(v[u].x) - emin) / (emax - emin) * nbins;
+                    if (f >= 0.f && f < (float)nbins) {
+                        if (spec_smem) atomicAdd(&s_spec[(int)f], 1u);
+                        else atomicAdd(&spectrum[(int)f], 1ull);
+                    }
                 }
             }
         }
+        __syncthreads();   // shared arrays are reused by the next tile
     }
     if (spec_smem) {
         __syncthreads();
@@ -529,52 +607,55 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, Digitize
 }
 
 // ------------------------------------------------------------------------------------------- stage 5: coincidence sorter (extension)
-// Windows are opened by the first single that is not inside an earlier window and last cwin us; a thread owns the
-// run of windows starting at a single whose predecessor is at least cwin earlier (guaranteed opener).  Works on the
-// side arrays of the singles list (time, panel).
-__device__ __forceinline__ bool pair_ok(const int* __restrict__ span, unsigned a, unsigned b, const DigitizerDev& p) {
+// Windows are opened by the first single that is not inside an earlier window and last cwin us.  A single whose
+// predecessor is at least cwin earlier is a guaranteed opener, so every single finds its own role by replaying the
+// windows from the nearest guaranteed opener at or before it (a few steps at realistic rates): no cross-thread state,
+// so counting, scanning and emitting are ONE kernel.  Works on the side arrays of the singles list (time, panel),
+// staged in shared memory with a halo on both sides.
+struct SinglesView {
+    const double* __restrict__ gt; const int* __restrict__ gp;   // global arrays
+    const double* st; const int* sp;                             // staged copy of [lo, hi)
+    unsigned lo, hi;
+    __device__ __forceinline__ double t(unsigned i) const { return (i >= lo && i < hi) ? st[i - lo] : gt[i]; }
+    __device__ __forceinline__ int pan(unsigned i) const { return (i >= lo && i < hi) ? sp[i - lo] : gp[i]; }
+};
+
+__device__ __forceinline__ bool pair_ok(const SinglesView& v, unsigned a, unsigned b, const DigitizerDev& p) {
     if (p.cmindiff <= 0) return true;
-    int d = abs(span[a] - span[b]);
+    int d = abs(v.pan(a) - v.pan(b));
     if (p.npanels > 0) d = min(d, p.npanels - d);
     return d >= p.cmindiff;
 }
 
-__global__ void __launch_bounds__(kThreads) k_coinc_count(const double* __restrict__ stime, const int* __restrict__ span,
-                                                          DigitizerDev p, const unsigned* __restrict__ counters,
-                                                          unsigned singles_cap, unsigned* __restrict__ cnt) {
-    const unsigned n = min(counters[3], singles_cap);
-    const double W = (double)p.cwin;
-    for (unsigned a0 = blockIdx.x * blockDim.x + threadIdx.x; a0 < n; a0 += gridDim.x * blockDim.x) {
-        if (a0 > 0 && !(stime[a0] >= stime[a0 - 1] + W)) continue;
-        unsigned a = a0;
-        while (true) {
-            const double tend = stime[a] + W;
-            unsigned m = 0, valid = 0;
-            while (a + 1 + m < n && stime[a + 1 + m] < tend) {
-                if (pair_ok(span, a, a + 1 + m, p)) valid++;
-                cnt[a + 1 + m] = 0;
-                m++;
-            }
-            unsigned c;
-            if (p.cpolicy == 0) c = (m == 1 && valid == 1) ? 1u : 0u;
-            else c = valid;
-            cnt[a] = c;
-            a += m + 1;
-            if (a >= n) break;
-            if (stime[a] >= stime[a - 1] + W) break;  // next guaranteed opener: owned by another thread
+// coincidences opened by single a (0 when it sits inside an earlier window)
+__device__ __forceinline__ unsigned coincidences_of(const SinglesView& v, unsigned a, unsigned n, double W, const DigitizerDev& p) {
+    unsigned w = a;
+    while (w > 0 && !(v.t(w) >= v.t(w - 1) + W)) w--;   // nearest guaranteed opener
+    while (true) {
+        const double tend = v.t(w) + W;
+        unsigned m = 0;
+        while (w + 1 + m < n && v.t(w + 1 + m) < tend) m++;
+        if (w == a) {
+            unsigned valid = 0;
+            for (unsigned b = a + 1; b <= a + m; b++) valid += pair_ok(v, a, b, p) ? 1u : 0u;
+            return p.cpolicy == 0 ? ((m == 1 && valid == 1) ? 1u : 0u) : valid;
         }
+        if (a <= w + m) return 0u;   // inside w's window
+        w += m + 1;
     }
 }
 
-// Compaction of the coincidences: index pairs into the run's singles list (pair_base = singles of the run's earlier
-// frames, kept on the device) and, when `out` is given, the two 48-byte records side by side.
-__global__ void __launch_bounds__(kThreads) k_coinc_emit(const EventRec* __restrict__ s, const double* __restrict__ stime,
-                                                         const int* __restrict__ span, DigitizerDev p,
-                                                         const unsigned* __restrict__ cnt, unsigned* __restrict__ counters,
-                                                         unsigned singles_cap, unsigned* __restrict__ status,
-                                                         gpet_coincidence* __restrict__ out, uint2* __restrict__ pairs, unsigned cap,
-                                                         const unsigned* __restrict__ base_in, unsigned* __restrict__ base_out) {
+// Index pairs into the run's singles list (pair_base = singles of the run's earlier frames, kept on the device) and,
+// when `out` is given, the two 48-byte records side by side.
+__global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__ s, const double* __restrict__ stime,
+                                                    const int* __restrict__ span, DigitizerDev p, unsigned* __restrict__ counters,
+                                                    unsigned singles_cap, unsigned* __restrict__ status,
+                                                    gpet_coincidence* __restrict__ out, uint2* __restrict__ pairs, unsigned cap,
+                                                    const unsigned* __restrict__ base_in, unsigned* __restrict__ base_out) {
     __shared__ unsigned s_tile;
+    __shared__ double s_t[kScanTile + 2 * kHalo];
+    __shared__ int s_p[kScanTile + 2 * kHalo];
+    __shared__ __align__(16) unsigned short s_cnt[kScanTile];
     const unsigned n = min(counters[3], singles_cap);
     const unsigned ntiles = (n + kScanTile - 1) / kScanTile;
     const double W = (double)p.cwin;
@@ -585,20 +666,41 @@ __global__ void __launch_bounds__(kThreads) k_coinc_emit(const EventRec* __restr
         __syncthreads();
         const unsigned tile = s_tile;
         if (tile >= ntiles) break;
-        const unsigned a0 = tile * kScanTile + threadIdx.x * 8;
-        unsigned c[8];
+        const unsigned at = tile * kScanTile;
+        SinglesView v;
+        v.gt = stime; v.gp = span; v.st = s_t; v.sp = s_p;
+        v.lo = at >= (unsigned)kHalo ? at - kHalo : 0u;
+        v.hi = min(at + kScanTile + kHalo, n);
+        for (unsigned i = v.lo + threadIdx.x; i < v.hi; i += kThreads) {
+            s_t[i - v.lo] = stime[i];
+            s_p[i - v.lo] = span[i];
+        }
+        __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 8; k++) c[k] = (a0 + k < n) ? cnt[a0 + k] : 0u;
+        for (int k = 0; k < 8; k++) {
+            const unsigned a = at + k * kThreads + threadIdx.x;
+            const unsigned c = a < n ? coincidences_of(v, a, n, W, p) : 0u;
+            s_cnt[k * kThreads + threadIdx.x] = (unsigned short)min(c, 0xffffu);
+        }
+        __syncthreads();
+        const unsigned a0 = at + threadIdx.x * 8;
+        unsigned c[8];
+        {
+            const uint4 c8 = reinterpret_cast<const uint4*>(s_cnt)[threadIdx.x];
+            c[0] = c8.x & 0xffffu; c[1] = c8.x >> 16; c[2] = c8.y & 0xffffu; c[3] = c8.y >> 16;
+            c[4] = c8.z & 0xffffu; c[5] = c8.z >> 16; c[6] = c8.w & 0xffffu; c[7] = c8.w >> 16;
+        }
         TileScan sc = tile_exclusive_scan(c, tile, status);
         if (tile == ntiles - 1 && threadIdx.x == 0) counters[4] = sc.tile_excl + sc.tile_total;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             if (c[k] == 0) continue;
             const unsigned a = a0 + k;
-            unsigned o = sc.excl[k];
-            const double tend = stime[a] + W;
-            for (unsigned b = a + 1; b < n && stime[b] < tend; b++) {
-                if (!pair_ok(span, a, b, p)) continue;
+            unsigned o = sc.excl[k], left = c[k];
+            const double tend = v.t(a) + W;
+            for (unsigned b = a + 1; left && b < n && v.t(b) < tend; b++) {
+                if (!pair_ok(v, a, b, p)) continue;
+                left--;
                 if (o < cap) {
                     if (pairs) pairs[o] = make_uint2(pair_base + a, pair_base + b);
                     if (out) {   // 2 x 48-byte records copied as 6 x 16 B from the singles list
@@ -613,6 +715,7 @@ __global__ void __launch_bounds__(kThreads) k_coinc_emit(const EventRec* __restr
                 o++;
             }
         }
+        __syncthreads();   // shared arrays are reused by the next tile
     }
 }
 
@@ -633,16 +736,18 @@ TimeRange time_range_us(double t_lo_us, double t_hi_us) {
 }
 
 int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p, DigitizerWorkspace& ws, const TimeRange* range,
-                    uint64_t seed, int num_sms, cudaStream_t s) {
-    const int grid = num_sms * 4;
+                    uint64_t seed, int num_sms, cudaStream_t s, bool reset) {
+    static const int grid_mult = [] { const char* v = getenv("GPET_DIGI_GRID"); return v && *v ? atoi(v) : 4; }();
+    const int grid = num_sms * grid_mult;
     int launches = 0;
     EventRec* singles = static_cast<EventRec*>(out.singles);
     unsigned long long* keys = ws.tkeys[0];    // by event index; after the sort: the sorted keys (tsort)
     unsigned long long* bkeys = ws.tkeys[1];   // scatter target; ping-pong partner of the LSD fallback (the two sorts
                                                // never run in the same frame)
-    GPET_LAUNCH("k_begin", s, k_begin<<<64, kThreads, 0, s>>>(ws.counters, ws.scan_status[0], ws.scan_status[1], ws.scan_status[2],
-                                                             ws.max_tiles, ws.bcount, ws.minmax));
-    launches++;
+    if (reset) {   // the digitizer's share of the frame state: counters[0..7], then everything behind the counter block
+        cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned), s);
+        cudaMemsetAsync(ws.counters + 64, 0, ws.frame_state_bytes - 64 * sizeof(unsigned), s);
+    }
     TimeRange tr;
     if (range) {
         tr = *range;
@@ -681,13 +786,10 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
                                                                             ws.spectrum, ws.spectrum_bins, ws.spec_emin, ws.spec_emax));
     launches++;
     if (p.cwin > 0.f && (out.coinc || out.pairs)) {
-        GPET_LAUNCH("k_coinc_count", s, k_coinc_count<<<grid, kThreads, 0, s>>>(ws.stime, ws.span, p, ws.counters, out.singles_cap, ws.coinc_cnt));
-        GPET_LAUNCH("k_coinc_emit", s, k_coinc_emit<<<grid, kThreads, 0, s>>>(singles, ws.stime, ws.span, p, ws.coinc_cnt, ws.counters,
-                                                                            out.singles_cap, ws.scan_status[1],
-                                                                            static_cast<gpet_coincidence*>(out.coinc),
-                                                                            static_cast<uint2*>(out.pairs), out.coinc_cap,
-                                                                            out.pair_base_in, out.pair_base_out));
-        launches += 2;
+        GPET_LAUNCH("k_coinc", s, k_coinc<<<grid, kThreads, 0, s>>>(singles, ws.stime, ws.span, p, ws.counters, out.singles_cap, ws.scan_status[1],
+                                                                  static_cast<gpet_coincidence*>(out.coinc), static_cast<uint2*>(out.pairs),
+                                                                  out.coinc_cap, out.pair_base_in, out.pair_base_out));
+        launches++;
     }
     return launches;
 }

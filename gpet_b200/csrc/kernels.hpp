@@ -31,7 +31,9 @@ struct DigitizerWorkspace {
                                    // each), slice counters of the bucket sort (bucket_words() / 2048)
     unsigned int* bcount;          // bucket sort of the time keys: events per slice, slice starts (bucket_words() entries each)
     unsigned int* bstart;
-    unsigned long long* minmax;    // [0] smallest, [1] largest time key (k_range, replay entry)
+    unsigned long long* minmax;    // [0] ~(smallest), [1] largest time key (k_range, replay entry); zero = empty
+    unsigned int* frame_state;     // counters | scan_status[0..2] | minmax | bcount as ONE block: a frame starts by zeroing it
+    size_t frame_state_bytes;
     unsigned int max_tiles;
     unsigned int capacity;
     unsigned int* order_t;         // event index | window flag, in time order (first counters[1] entries)
@@ -41,8 +43,8 @@ struct DigitizerWorkspace {
     int* span;
     unsigned int* coinc_cnt;       // per single: coincidences it opens
     // [0] n_in [1] after thresholder [2] after deadtime [3] singles [4] coincidences [6],[7] tile tickets of the two
-    // compactions [8] photons on a panel [9] adder drops [10],[11] photon tickets of k_detector / k_front [12] time sort
-    // fell back to LSD radix; [16..19] queue 0, queue 1, hits, events counts, [21] queue 2
+    // compactions [5] time sort fell back to LSD radix [8] photons on a panel [9] adder drops [10],[11] photon tickets of
+    // k_detector / k_front; [16..19] queue 0, queue 1, hits, events counts, [21] queue 2
     unsigned int* counters;
     unsigned long long* spectrum; int spectrum_bins; float spec_emin, spec_emax;
 };
@@ -65,8 +67,9 @@ unsigned bucket_words();                       // slice counters of the bucket s
 
 // ---- digitizer (digitizer.cu) --------------------------------------------------------------------------
 // range == nullptr: the key range is measured on the device first (replay entry)
+// reset: clear the stage's share of the frame state first (false inside gpet_run, where one memset per frame clears all)
 int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p, DigitizerWorkspace& ws, const TimeRange* range,
-                    uint64_t seed, int num_sms, cudaStream_t s);
+                    uint64_t seed, int num_sms, cudaStream_t s, bool reset);
 
 // ---- transport (transport.cu) ----------------------------------------------------------------------------
 int launch_source(const SourceDev* frame_dev, unsigned long long npairs, PhantomDev ph, PhotonQueue q0,
@@ -79,10 +82,10 @@ int launch_panel_entry(PhotonQueue q1, PhotonQueue q2, DetectorDev det, unsigned
 // fused source (frame_dev != nullptr) or queue q0 (frame_dev == nullptr) -> phantom -> panel entry -> q2; q1 only counts
 int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQueue q0, PhotonQueue q1, PhotonQueue q2,
                  PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, unsigned int* counters, uint64_t seed, int num_sms,
-                 cudaStream_t s);
+                 cudaStream_t s, bool reset);
 int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
                     int record_hits, HitBuffer hits, EventBuf ev, unsigned int* counters, uint64_t seed,
-                    int num_sms, cudaStream_t s);
+                    int num_sms, cudaStream_t s, bool reset);
 int launch_photons_aos_to_queue(const void* aos, PhotonQueue q, unsigned int n, cudaStream_t s);
 int launch_queue_to_photons_aos(PhotonQueue q, void* aos, cudaStream_t s);
 

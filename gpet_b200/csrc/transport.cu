@@ -944,7 +944,7 @@ int launch_panel_entry(PhotonQueue q1, PhotonQueue q2, DetectorDev det, unsigned
 
 int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQueue q0, PhotonQueue q1, PhotonQueue q2,
                  PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, unsigned int* counters, uint64_t seed, int num_sms,
-                 cudaStream_t s) {
+                 cudaStream_t s, bool reset) {
     const size_t smem_panels = (size_t)det.npanels * sizeof(PanelDev);
     static int grid[2] = {0, 0};
     static size_t grid_smem = 0;
@@ -958,10 +958,12 @@ int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQu
         grid_smem = smem_panels;
     }
     const int gen_min = tune("GPET_GEN_MIN", 12), entry_min = tune("GPET_ENTRY_MIN", 12);
-    cudaMemsetAsync(q1.count, 0, sizeof(unsigned), s);       // photons that left the phantom (tally only: q1 is not filled)
-    cudaMemsetAsync(q2.count, 0, sizeof(unsigned), s);
-    cudaMemsetAsync(counters + 8, 0, sizeof(unsigned), s);   // photons on a panel
-    cudaMemsetAsync(counters + 11, 0, sizeof(unsigned), s);  // k_front's ticket
+    if (reset) {
+        cudaMemsetAsync(q1.count, 0, sizeof(unsigned), s);       // photons that left the phantom (tally only: q1 is not filled)
+        cudaMemsetAsync(q2.count, 0, sizeof(unsigned), s);
+        cudaMemsetAsync(counters + 8, 0, sizeof(unsigned), s);   // photons on a panel
+        cudaMemsetAsync(counters + 11, 0, sizeof(unsigned), s);  // k_front's ticket
+    }
     if (frame_dev) {
         GPET_LAUNCH("k_front", s, k_front<false><<<grid[0], kThreads, smem_panels, s>>>(frame_dev, npairs, q0, ph, tb, det, eabs, seed, q2,
                                                                                       q1.count, counters, gen_min, entry_min));
@@ -974,7 +976,7 @@ int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQu
 
 int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
                     int record_hits, HitBuffer hits, EventBuf ev, unsigned int* counters, uint64_t seed, int num_sms,
-                    cudaStream_t s) {
+                    cudaStream_t s, bool reset) {
     const size_t smem = sizeof(SlotsSmem) + (size_t)det.npanels * sizeof(PanelDev);
     static int grid = 0;
     static size_t grid_smem = 0;
@@ -983,8 +985,10 @@ int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, i
         grid = persistent_grid(k_detector, num_sms, smem);
         grid_smem = smem;
     }
-    cudaMemsetAsync(hits.count, 0, 2 * sizeof(unsigned), s);   // hits.count, ev.count (adjacent words of the counter block)
-    cudaMemsetAsync(counters + 9, 0, 2 * sizeof(unsigned), s);   // adder drops, k_detector's ticket
+    if (reset) {
+        cudaMemsetAsync(hits.count, 0, 2 * sizeof(unsigned), s);     // hits.count, ev.count (adjacent words of the counter block)
+        cudaMemsetAsync(counters + 9, 0, 2 * sizeof(unsigned), s);   // adder drops, k_detector's ticket
+    }
     GPET_LAUNCH("k_detector", s, k_detector<<<grid, kThreads, smem, s>>>(q2, det, tb, eabs, readout_depth, readout_policy, record_hits, hits, ev,
                                                                        counters, seed, tune("GPET_REFILL_MIN", 4)));
     return 1;

@@ -73,7 +73,7 @@ def test_digitizer_bit_exact_late_times(ctx):
 @pytest.mark.parametrize("dead_type", [0, 1])
 def test_digitizer_clustered_times_take_the_lsd_fallback(ctx, dead_type):
     """Times clustered far below the key range overfill one slice of the bucket sort: the device switches to the LSD radix
-    passes (counters[12]) and the result is still the oracle's, bit for bit."""
+    passes (counters[5]) and the result is still the oracle's, bit for bit."""
     rng = np.random.default_rng(77)
     ev = parity.random_events(50000, rng, tmax=1.0, nsites=936, tie_fraction=0.05)
     ev["t"] += 1.0e6                       # 50 000 events inside one microsecond ...

@@ -30,6 +30,7 @@ def main():
         c.set_stream(stream.cuda_stream)
         c.load_config_file(ex / "input_PET.in", base_dir=ex)
         c.set_digitizer(coinc_window_us=0.01)
+        c.set_coincidence_format(api.Context.COINC_PAIRS)   # as bench.py does
         if a.scale != 1.0:
             src = c.sources()
             for i, s in enumerate(src):
