@@ -47,13 +47,15 @@ class DigitizerParams(C.Structure):
                 ("dead_level", C.c_int32), ("dead_type", C.c_int32), ("dead_time_us", C.c_float),
                 ("ewin_min", C.c_float), ("ewin_max", C.c_float),
                 ("time_blur_sigma_us", C.c_float), ("coinc_window_us", C.c_float),
-                ("coinc_policy", C.c_int32), ("coinc_min_panel_diff", C.c_int32)]
+                ("coinc_policy", C.c_int32), ("coinc_min_panel_diff", C.c_int32),
+                ("noise_mean_gap_us", C.c_float), ("noise_Emean_eV", C.c_float), ("noise_sigma_eV", C.c_float),
+                ("noise_interval_us", C.c_float)]
 
 
 class TransportParams(C.Structure):
     _fields_ = [("noncollinearity_rad", C.c_float), ("use_positron_range", C.c_int32), ("eabs_eV", C.c_float),
                 ("nsurface", C.c_int32), ("surface", C.c_float * (10 * GPET_MAX_SURFACES)),
-                ("record_hits", C.c_int32)]
+                ("record_hits", C.c_int32), ("record_psf", C.c_int32), ("record_sphere", C.c_float * 4)]
 
 
 class Stats(C.Structure):
@@ -107,11 +109,13 @@ _SIGS = {
     "gpet_get_frame": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
     "gpet_stage_source": (C.c_int, [_P, C.c_int64]),
     "gpet_stage_psf": (C.c_int, [_P, C.c_int64, C.c_int64]),
+    "gpet_set_psf_output": (C.c_int, [_P, C.c_int]),
     "gpet_stage_phantom": (C.c_int, [_P]),
     "gpet_stage_detector": (C.c_int, [_P]),
     "gpet_stage_front": (C.c_int, [_P, C.c_int64]),
     "gpet_stage_panel_transport": (C.c_int, [_P]),
     "gpet_stage_digitize": (C.c_int, [_P]),
+    "gpet_stage_noise": (C.c_int, [_P, C.c_double, C.c_double]),
     "gpet_queue_size": (C.c_int64, [_P, C.c_int]),
     "gpet_put_photons": (C.c_int, [_P, C.c_int, _P, C.c_int64]),
     "gpet_fetch_photons": (C.c_int64, [_P, C.c_int, _P, C.c_int64]),
@@ -262,12 +266,16 @@ class Context:
         if p is None:
             p = self.get_transport()
         for k, v in kw.items():
-            if k == "surface":
+            if k in ("surface", "record_sphere"):
                 for i, x in enumerate(v):
-                    p.surface[i] = x
+                    getattr(p, k)[i] = x
             else:
                 setattr(p, k, v)
         self._ck(self._l.gpet_set_transport(self._h, C.byref(p)))
+
+    def set_psf_output(self, mode):
+        """OUTPUTPSF of the reference (constants.h:5): 0 none, 1 source photons in PSF mode, 2 source + phantom dumps."""
+        self._ck(self._l.gpet_set_psf_output(self._h, mode))
 
     def set_time_window(self, t0, t1):
         self._ck(self._l.gpet_set_time_window(self._h, t0, t1))
@@ -373,6 +381,9 @@ class Context:
 
     def stage_detector(self):
         self._ck(self._l.gpet_stage_detector(self._h))
+
+    def stage_noise(self, t_lo_us, t_hi_us):
+        self._ck(self._l.gpet_stage_noise(self._h, t_lo_us, t_hi_us))
 
     def stage_front(self, f=-1):
         """Fused source (frame f >= 0) or queue 0 (f = -1) -> phantom -> panel entry -> queue 2."""

@@ -243,6 +243,8 @@ PhantomDev phantom_dev(const gpet_ctx* c) {
     d.ox = ph.offset[0]; d.oy = ph.offset[1]; d.oz = ph.offset[2];
     d.idx = 1.0f / ph.d[0]; d.idy = 1.0f / ph.d[1]; d.idz = 1.0f / ph.d[2];  // initialize.cu:846-851
     d.dx = ph.d[0]; d.dy = ph.d[1]; d.dz = ph.d[2];
+    d.rec_on = c->tr.record_psf != 0;
+    for (int i = 0; i < 4; i++) d.rec[i] = c->tr.record_sphere[i];
     return d;
 }
 
@@ -298,6 +300,8 @@ DigitizerDev digitizer_dev(const gpet_ctx* c) {
     d.tblur = p.time_blur_sigma_us; d.cwin = p.coinc_window_us; d.cpolicy = p.coinc_policy; d.cmindiff = p.coinc_min_panel_diff;
     d.npanels = (int)c->geo.panels.size();
     d.moduleN = c->geo.moduleN; d.crystalN = c->geo.crystalN;
+    d.noise_gap = p.noise_mean_gap_us; d.noise_Emean = p.noise_Emean_eV; d.noise_sigma = p.noise_sigma_eV;
+    d.noise_interval = p.noise_interval_us;
     return d;
 }
 
@@ -581,6 +585,8 @@ int gpet_load_config_file(gpet_ctx* c, const char* input_file, const char* base_
     tr.nsurface = cfg.nsurface;
     for (int i = 0; i < 10 * cfg.nsurface; i++) tr.surface[i] = cfg.surface[i];
     tr.record_hits = 1;
+    tr.record_psf = 0;   // RECORDPSF = 1 in the shipped constants.h: the sphere of field 14 is parsed but unused
+    for (int i = 0; i < 4; i++) tr.record_sphere[i] = cfg.recordsphere[i];
     if ((r = gpet_set_transport(c, &tr))) return r;
     gpet_digitizer_params d = c->dig;
     d.readout_depth = cfg.rdepth; d.readout_policy = cfg.rpolicy;
@@ -849,6 +855,19 @@ int gpet_stage_digitize(gpet_ctx* c) {
     return GPET_OK;
 }
 
+int gpet_stage_noise(gpet_ctx* c, double t_lo_us, double t_hi_us) {
+    NEED_DEVICE();
+    ProfScope prof(c);
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if (!c->have_geo) return fail(c, GPET_ERR_ARG, "noise singles need the detector geometry (panel / module / crystal counts)");
+    const DigitizerDev d = digitizer_dev(c);
+    if (d.noise_gap > 0.f && !(d.noise_interval > 0.f)) return fail(c, GPET_ERR_ARG, "noise_interval_us must be positive");
+    c->stats.kernel_launches += launch_noise(c->ev, d, t_lo_us, t_hi_us, c->seed, c->num_sms, c->stream);
+    CK(cudaGetLastError());
+    return GPET_OK;
+}
+
 // =================================================================================================== buffer access
 int64_t gpet_queue_size(gpet_ctx* c, int which) {
     NEED_DEVICE();
@@ -1003,6 +1022,44 @@ int append_device(gpet_ctx* c, const std::string& path, const void* dptr, size_t
     return GPET_OK;
 }
 
+// PSF triplet of one stage queue (gPET.cu:63-88, 296-351): per live photon 7 x float32 into out<tag>.dat, the event id into
+// id<tag>.dat and the fp64 time into time<tag>.dat, appended (readOutput.m:36-54)
+int dump_psf_queue(gpet_ctx* c, const std::string& od, int which, const char* tag, std::vector<gpet_photon>& buf) {
+    int64_t n = gpet_queue_size(c, which);
+    if (n < 0) return (int)n;
+    buf.resize((size_t)n);
+    if (n) {
+        n = gpet_fetch_photons(c, which, buf.data(), n);
+        if (n < 0) return (int)n;
+    }
+    FILE* fo = fopen(join_path(od, std::string("out") + tag + ".dat").c_str(), "ab");
+    FILE* fi = fopen(join_path(od, std::string("id") + tag + ".dat").c_str(), "ab");
+    FILE* ft = fopen(join_path(od, std::string("time") + tag + ".dat").c_str(), "ab");
+    if (!fo || !fi || !ft) {
+        if (fo) fclose(fo);
+        if (fi) fclose(fi);
+        if (ft) fclose(ft);
+        return fail(c, GPET_ERR_IO, std::string("cannot open the PSF dump files of stage ") + tag);
+    }
+    std::vector<float> f7;
+    std::vector<int32_t> id;
+    std::vector<double> tt;
+    f7.reserve((size_t)n * 7); id.reserve((size_t)n); tt.reserve((size_t)n);
+    for (int64_t k = 0; k < n; k++) {
+        const gpet_photon& p = buf[(size_t)k];
+        if (!(p.t > 0)) continue;   // gPET.cu:76
+        const float row[7] = {p.x, p.y, p.z, p.vx, p.vy, p.vz, p.E};
+        f7.insert(f7.end(), row, row + 7);
+        id.push_back(p.eventid);
+        tt.push_back(p.t);
+    }
+    fwrite(f7.data(), sizeof(float), f7.size(), fo);
+    fwrite(id.data(), sizeof(int32_t), id.size(), fi);
+    fwrite(tt.data(), sizeof(double), tt.size(), ft);
+    fclose(fo); fclose(fi); fclose(ft);
+    return GPET_OK;
+}
+
 // grow a pinned arena so that `extra` more bytes fit (contents kept); in-flight copies into it must have completed
 int arena_reserve(gpet_ctx* c, PinnedArena& a, size_t extra) {
     if (a.size + extra <= a.cap) return GPET_OK;
@@ -1135,6 +1192,8 @@ int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* sta
     const int64_t psf_batch = (psf_mode && c->psf.ptype == 0) ? (int64_t)(c->cap_photons / 2) : (int64_t)c->cap_photons;
     const int64_t nframes = psf_mode ? ((int64_t)c->psf.p.size() + psf_batch - 1) / psf_batch : (int64_t)c->frames.size();
     const bool pipelined = rs.od.empty();   // file dumps read the (single-buffered) hit and event buffers frame by frame
+    const int psf_out = rs.od.empty() ? 0 : c->psf_output;
+    std::vector<gpet_photon> psf_buf;
     int64_t k = 0;                           // owned frames launched so far
     int rc = GPET_OK;
     for (int64_t f = 0; f < nframes && rc == GPET_OK; f++) {
@@ -1152,17 +1211,43 @@ int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* sta
             int64_t first = f * psf_batch, n = std::min<int64_t>(psf_batch, (int64_t)c->psf.p.size() - first);
             if ((rc = gpet_stage_psf(c, first, n))) break;
             st.pairs += c->psf.ptype == 0 ? (uint64_t)n : (uint64_t)n / 2;
-            if ((rc = gpet_stage_front(c, -1))) break;
         } else {
-            if ((rc = gpet_stage_front(c, f))) break;
             st.pairs += c->frames[(size_t)f].npairs;
         }
-        if ((rc = gpet_stage_panel_transport(c))) break;
+        if (psf_out) {
+            // phase-space dumps need the stage queues in memory: staged kernels (same photons as the fused front end)
+            if (!psf_mode && (rc = gpet_stage_source(c, f))) break;
+            if ((psf_mode && psf_out == 1) || (!psf_mode && psf_out == 2))
+                if ((rc = dump_psf_queue(c, rs.od, 0, "source", psf_buf))) break;
+            if ((rc = gpet_stage_phantom(c))) break;
+            if (psf_out == 2 && (rc = dump_psf_queue(c, rs.od, 1, "phantom", psf_buf))) break;
+            if ((rc = gpet_stage_detector(c))) break;
+        } else {
+            if ((rc = gpet_stage_front(c, psf_mode ? -1 : f))) break;
+            if ((rc = gpet_stage_panel_transport(c))) break;
+        }
         // source mode: event times lie in the frame's slice (plus a flight time far below a slice of the sort)
         c->have_range = !psf_mode;
         if (!psf_mode) {
             const FramePlan& fp = c->frames[(size_t)f];
             c->range = time_range_us(fp.t0_s * 1e6, (fp.t0_s + fp.dt_s) * 1e6);
+        }
+        if (c->dig.noise_mean_gap_us > 0.f) {
+            // addnoise over the time the frame covers (PSF mode: the span of the batch's own times)
+            double lo = 0.0, hi = 0.0;
+            if (!psf_mode) {
+                lo = c->frames[(size_t)f].t0_s * 1e6;
+                hi = (c->frames[(size_t)f].t0_s + c->frames[(size_t)f].dt_s) * 1e6;
+            } else {
+                const int64_t first = f * psf_batch, n = std::min<int64_t>(psf_batch, (int64_t)c->psf.p.size() - first);
+                lo = 1e300; hi = -1e300;
+                for (int64_t k = first; k < first + n; k++) {
+                    const double t = c->psf.p[(size_t)k].t;
+                    if (t > 0) { lo = std::min(lo, t); hi = std::max(hi, t); }
+                }
+                hi = std::nextafter(hi, 1e300);
+            }
+            if (hi > lo && (rc = gpet_stage_noise(c, lo, hi))) break;
         }
         c->run_frame = k;
         rc = gpet_stage_digitize(c);
@@ -1241,6 +1326,12 @@ int64_t gpet_result_coincidences(gpet_ctx* c, const gpet_coincidence** ptr) {
 int gpet_set_coincidence_format(gpet_ctx* c, int format) {
     if (!c || (format != GPET_COINC_RECORDS && format != GPET_COINC_PAIRS)) return GPET_ERR_ARG;
     c->coinc_format = format;
+    return GPET_OK;
+}
+
+int gpet_set_psf_output(gpet_ctx* c, int mode) {
+    if (!c || mode < 0 || mode > 2) return GPET_ERR_ARG;
+    c->psf_output = mode;
     return GPET_OK;
 }
 

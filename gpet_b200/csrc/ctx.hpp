@@ -64,6 +64,7 @@ struct gpet_ctx {
     void* coinc_slot[2] = {nullptr, nullptr};
     void* pairs_slot[2] = {nullptr, nullptr};            // uint2 index pairs (GPET_COINC_PAIRS)
     unsigned* d_pair_base = nullptr;                     // [2]: singles of the run's earlier frames, alternating by frame
+    int psf_output = 0;                                  // OUTPUTPSF of the reference (gpet_set_psf_output)
     int coinc_format = 0;                                // GPET_COINC_RECORDS / GPET_COINC_PAIRS (gpet_run only)
     bool in_run = false;
     int64_t run_frame = 0;                               // owned frames launched so far in this run

@@ -14,7 +14,7 @@ constexpr double kMaxT = 1e20;                        // constants.h:18 MAXT
 
 // Philox stream ids (counter word 2, high byte)
 enum Stage : uint32_t {
-    kStageSource = 1, kStagePhantom = 2, kStageDetector = 3, kStageBlur = 4, kStagePlan = 5, kStagePsfPositron = 6
+    kStageSource = 1, kStagePhantom = 2, kStageDetector = 3, kStageBlur = 4, kStagePlan = 5, kStagePsfPositron = 6, kStageNoise = 7
 };
 
 // Photon phase-space queue: 48 B per photon, 16-byte vector accesses.
@@ -102,6 +102,8 @@ struct PhantomDev {
     float ox, oy, oz;      // offset
     float idx, idy, idz;   // 1/voxel size
     float dx, dy, dz;      // voxel size
+    int rec_on;            // 1: photons leaving the phantom are moved onto the PSF-recording sphere (RECORDPSF == -1, gPET_kernals.cu:288-294)
+    float rec[4];          // sphere centre x, y, z and radius (input_PET.in field 14)
 };
 
 struct TablesDev {
@@ -138,6 +140,7 @@ struct DigitizerDev {
     int dlevel, dtype; float dtime;
     float Ewinmin, Ewinmax;
     float tblur; float cwin; int cpolicy; int cmindiff;
+    float noise_gap, noise_Emean, noise_sigma, noise_interval;   // addnoise (gPET_kernals.cu:699-735); gap <= 0: off
     int npanels;
     int moduleN, crystalN;
 };

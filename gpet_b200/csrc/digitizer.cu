@@ -113,6 +113,47 @@ __global__ void __launch_bounds__(kThreads) k_range(EventBuf ev, unsigned long l
     }
 }
 
+// ------------------------------------------------------------------------------------------- noise singles
+// addnoise (gPET_kernals.cu:699-735): thread `id` owns the time slice [id, id+1) * interval and walks a Poisson process
+// of mean gap `lambda` through it; every arrival is an event with E = Emean + sigma * N(0,1), uniform position numbers in
+// (0,1] and a uniformly drawn panel / module / crystal, parn = -1, crystal-level siten.  The reference never launches
+// this kernel; what is specified here (and mirrored by the oracle): times accumulate in fp64 (the reference's fp32 `t`
+// stops advancing once its ulp exceeds the gaps, i.e. after ~17 s of acquisition at us gaps), int(N * u) is clamped to
+// N - 1 (u = 1 is possible), eventid = 0x80000000 | (slice << 10 | ordinal in the slice) so that noise events can be
+// told apart, one Philox stream per slice, three blocks per arrival, and only arrivals inside [t_lo, t_hi) are kept
+// (the frame being digitized).  Logarithm and Box-Muller in fp64, rounded once: the oracle's libm agrees.
+__global__ void __launch_bounds__(kThreads) k_noise(EventBuf ev, DigitizerDev p, uint64_t seed, double t_lo, double t_hi,
+                                                    long long id0, long long nslices) {
+    const double interval = (double)p.noise_interval, lambda = (double)p.noise_gap;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < nslices; k += (long long)gridDim.x * blockDim.x) {
+        const long long id = id0 + k;
+        double t = (double)id * interval;
+        const double tend = (double)(id + 1) * interval;
+        Philox rng(seed, (uint64_t)id, (uint32_t)kStageNoise << 24);
+        for (unsigned ord = 0; ord < (1u << 20); ord++) {
+            const uint4 r = rng.next();
+            t = __dadd_rn(t, __dmul_rn(-log((double)u01(r.x)), lambda));   // no contraction: the oracle's arithmetic
+            if (!(t < tend)) break;
+            const uint4 q = rng.next();
+            const uint4 w = rng.next();
+            if (t < t_lo || !(t < t_hi)) continue;
+            EventRec e;
+            const double g = sqrt(-2.0 * log((double)u01(r.y))) * cos(6.283185307179586 * (double)u01(r.z));
+            e.E = (float)__dadd_rn((double)p.noise_Emean, __dmul_rn((double)p.noise_sigma, g));
+            e.x = u01(r.w); e.y = u01(q.x); e.z = u01(q.y);
+            e.parn = -1;
+            e.pann = min((int)((float)p.npanels * u01(q.z)), p.npanels - 1);
+            e.modn = min((int)((float)p.moduleN * u01(q.w)), p.moduleN - 1);
+            e.cryn = min((int)((float)p.crystalN * u01(w.x)), p.crystalN - 1);
+            e.siten = e.pann * p.moduleN * p.crystalN + e.modn * p.crystalN + e.cryn;
+            e.eventid = (int)(0x80000000u | ((((unsigned)id << 10) | (ord & 1023u)) & 0x7fffffffu));
+            e.t = t;
+            const unsigned slot = atomicAdd(ev.count, 1u);
+            if (slot < ev.capacity) store_event_rec(ev.rec + slot, e);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------- stage 1: blur + thresholder + site + slice
 // blur (gPET_kernals.cu:814-837) + energywindow(Eth, 2e6) (gPET.cu:393) + setSitenum (gPET_kernals.cu:607-640) fused.
 // Per record: time key (all ones for a dead one), site number, arrival rank in its time slice | final-window flag.
@@ -143,7 +184,9 @@ __global__ void __launch_bounds__(kThreads) k_prep(EventBuf ev, DigitizerDev p, 
         if (!(R > 0.f)) R = 0.f;
         // R == 0 leaves E bit-identical (E + 0), so the draw is skipped: this is the deterministic replay mode
         if (R > 0.f || p.sblur > 0.f || p.tblur > 0.f) {
-            Philox rng(seed, (uint64_t)(uint32_t)a4.x, ((uint32_t)kStageBlur << 24) | ((uint32_t)b4.x & 0xFFFFFFu));
+            // stream = the photon; noise events (parn == -1, k_noise) are told apart by their event id
+            const uint64_t who = a4.x == -1 ? ((1ull << 32) | (uint32_t)b4.y) : (uint64_t)(uint32_t)a4.x;
+            Philox rng(seed, who, ((uint32_t)kStageBlur << 24) | ((uint32_t)b4.x & 0xFFFFFFu));
             uint4 r = rng.next();
             float rad = sqrtf(-2.0f * logf(u01(r.x)));
             float g0 = rad * cosf(kTwoPi * u01(r.y));
@@ -733,6 +776,16 @@ TimeRange time_range_us(double t_lo_us, double t_hi_us) {
     r.hi = t_hi_us;
     r.dev = nullptr;
     return r;
+}
+
+int launch_noise(EventBuf ev, const DigitizerDev& p, double t_lo_us, double t_hi_us, uint64_t seed, int num_sms, cudaStream_t s) {
+    if (!(p.noise_gap > 0.f) || !(p.noise_interval > 0.f) || !(t_hi_us > t_lo_us)) return 0;
+    const double iv = (double)p.noise_interval;
+    const long long id0 = (long long)floor(t_lo_us / iv), id1 = (long long)ceil(t_hi_us / iv);
+    const long long n = std::max<long long>(id1 - id0, 1);
+    const int grid = (int)std::min<long long>((n + kThreads - 1) / kThreads, (long long)num_sms * 8);
+    GPET_LAUNCH("k_noise", s, k_noise<<<grid, kThreads, 0, s>>>(ev, p, seed, t_lo_us, t_hi_us, id0, n));
+    return 1;
 }
 
 int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p, DigitizerWorkspace& ws, const TimeRange* range,

@@ -71,6 +71,9 @@ unsigned bucket_words();                       // slice counters of the bucket s
 int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p, DigitizerWorkspace& ws, const TimeRange* range,
                     uint64_t seed, int num_sms, cudaStream_t s, bool reset);
 
+// addnoise: events of the noise process with t_lo <= t < t_hi appended to ev (digitizer.cu)
+int launch_noise(EventBuf ev, const DigitizerDev& p, double t_lo_us, double t_hi_us, uint64_t seed, int num_sms, cudaStream_t s);
+
 // ---- transport (transport.cu) ----------------------------------------------------------------------------
 int launch_source(const SourceDev* frame_dev, unsigned long long npairs, PhantomDev ph, PhotonQueue q0,
                   uint64_t seed, int num_sms, cudaStream_t s);

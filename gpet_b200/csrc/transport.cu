@@ -277,6 +277,20 @@ __global__ void __launch_bounds__(kThreads) k_source(const SourceDev* __restrict
 }
 
 // ------------------------------------------------------------------------------------------- P1: phantom transport
+// getDistance (gPET_kernals.cu:148-171): flight length along the direction to the PSF-recording sphere; 0 when the line
+// misses it.  Statement by statement, IEEE divide and square root (this file is compiled without FMA contraction).
+__device__ __forceinline__ float record_distance(const PhantomDev& ph, const Photon& p) {
+    const float cx = p.x - ph.rec[0], cy = p.y - ph.rec[1], cz = p.z - ph.rec[2];
+    const float a = p.vx * p.vx + p.vy * p.vy + p.vz * p.vz;
+    const float b = 2.0f * (p.vx * cx + p.vy * cy + p.vz * cz);
+    const float c = (cx * cx + cy * cy + cz * cz) - ph.rec[3] * ph.rec[3];
+    const float disc = b * b - 4 * a * c;
+    if (disc < 0) return 0.f;
+    if (c < 0) return (-b + sqrtf(disc)) / (2 * a);
+    if (b < 0) return (-b - sqrtf(disc)) / (2 * a);
+    return (-b + sqrtf(disc)) / (2 * a);
+}
+
 // One Woodcock flight (gPET_kernals.cu:277-335).  Returns 0: still inside, 1: the photon leaves the stage alive (escaped,
 // keeping the overshoot position -- SURVEY quirk 2 -- or below the absorption energy after a Compton, which the reference
 // still hands to the detector stage -- quirk 3), 2: photo-absorbed (tof = -0.5 in the reference).
@@ -289,7 +303,14 @@ __device__ __forceinline__ int phantom_flight(Photon& p, Philox& rng, const Phan
     p.x = fmaf(s, p.vx, p.x); p.y = fmaf(s, p.vy, p.y); p.z = fmaf(s, p.vz, p.z);
     p.t += (double)s * kInvSpeedOfLight;
     int ix = (int)((p.x - ph.ox) * ph.idx), iy = (int)((p.y - ph.oy) * ph.idy), iz = (int)((p.z - ph.oz) * ph.idz);
-    if (ix <= 0 || ix >= ph.nx || iy <= 0 || iy >= ph.ny || iz <= 0 || iz >= ph.nz) return 1;
+    if (ix <= 0 || ix >= ph.nx || iy <= 0 || iy >= ph.ny || iz <= 0 || iz >= ph.nz) {
+        if (ph.rec_on) {   // RECORDPSF == -1 branch (gPET_kernals.cu:288-294)
+            const float rr = record_distance(ph, p);
+            p.x = fmaf(rr, p.vx, p.x); p.y = fmaf(rr, p.vy, p.y); p.z = fmaf(rr, p.vz, p.z);
+            p.t += (double)rr * kInvSpeedOfLight;
+        }
+        return 1;
+    }
     uint32_t vw = __ldg(ph.vox + ((size_t)iz * ph.ny + iy) * ph.nx + ix);
     int mat = (int)(vw & 15u);
     float rho = __uint_as_float(vw & ~15u);

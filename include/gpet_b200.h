@@ -109,6 +109,11 @@ typedef struct gpet_digitizer_params {
     float   coinc_window_us;     /* coincidence window; 0 = no coincidence sorting */
     int32_t coinc_policy;        /* 0 drop multiples (window with != 2 singles), 1 all pairs with the window opener */
     int32_t coinc_min_panel_diff;/* minimum |panel difference| (cyclic) for a valid pair; 0 = any two distinct sites */
+    /* noise singles = the reference's addnoise kernel (gPET_kernals.cu:699-735; declared in gPET.h:191, never launched
+     * there, so its four arguments have no input_PET.in field): a Poisson process of mean gap noise_mean_gap_us over the
+     * whole detector, drawn per time slice of noise_interval_us, E ~ N(noise_Emean, noise_sigma), uniform crystal.
+     * noise_mean_gap_us <= 0 disables it. */
+    float   noise_mean_gap_us, noise_Emean_eV, noise_sigma_eV, noise_interval_us;
 } gpet_digitizer_params;
 
 /* Transport parameters = input_PET.in fields 2, 12, 15, 17 (main.cu:57-60, 117-120, 135-147). */
@@ -119,6 +124,9 @@ typedef struct gpet_transport_params {
     int32_t nsurface;
     float   surface[10 * GPET_MAX_SURFACES];
     int32_t record_hits;         /* OUTPUTHIT (constants.h:6): keep Hits/HitsID rows */
+    int32_t record_psf;          /* 1 = the RECORDPSF == -1 branch of photon() (gPET_kernals.cu:288-294, getDistance :148-171):
+                                    a photon that leaves the phantom is moved onto the recording sphere */
+    float   record_sphere[4];    /* centre x y z and radius, cm (input_PET.in field 14, main.cu:127-133) */
 } gpet_transport_params;
 
 /* Run counters (the numbers the reference prints per epoch, gPET.cu:293,364,382,398,415,423). */
@@ -234,6 +242,9 @@ int gpet_stage_panel_transport(gpet_ctx* ctx);
 /* D3-D7 blur, energywindow, sort by t, setSitenum, orderevents, deadtime, energywindow (gPET.cu:385-424)
  * + the coincidence sorter extension: events -> singles (time sorted) [+ coincidences]. */
 int gpet_stage_digitize(gpet_ctx* ctx);
+/* addnoise (gPET_kernals.cu:699-735): append the noise events with t_lo_us <= t < t_hi_us to the event buffer (after the
+ * detector stage, before gpet_stage_digitize).  gpet_run does this per frame when noise is enabled. */
+int gpet_stage_noise(gpet_ctx* ctx, double t_lo_us, double t_hi_us);
 
 /* Host <-> device access to the stage buffers. which_queue: 0 after source, 1 after phantom, 2 entered a panel. */
 int64_t gpet_queue_size(gpet_ctx* ctx, int which_queue);
@@ -269,6 +280,13 @@ int64_t gpet_result_coincidences(gpet_ctx* ctx, const gpet_coincidence** ptr);
  * the same files and the same records. */
 enum { GPET_COINC_RECORDS = 0, GPET_COINC_PAIRS = 1 };
 int gpet_set_coincidence_format(gpet_ctx* ctx, int format);
+/* Phase-space dumps of gpet_run(output_dir) = the reference's OUTPUTPSF switch (constants.h:5; gPET.cu:63-114, 296-351):
+ * 0 none; 1 PSF-input mode: the photons entering the phantom -> outsource.dat / idsource.dat / timesource.dat;
+ * 2 source mode: those three after source sampling, and in both modes outphantom.dat / idphantom.dat / timephantom.dat
+ * after the phantom.  Per live photon (t > 0): 7 x float32 (x y z vx vy vz E), int32 eventid, float64 t -- the layout
+ * output/readOutput.m:36-54 reads.  With dumps on, gpet_run materialises the stage queues (staged kernels instead of the
+ * fused front end); the photons are the same. */
+int gpet_set_psf_output(gpet_ctx* ctx, int mode);
 /* *ptr = pairs (2 x uint32 each: earlier single, later single); returns their number (0 in GPET_COINC_RECORDS mode). */
 int64_t gpet_result_coincidence_pairs(gpet_ctx* ctx, const uint32_t** ptr);
 int gpet_get_stats(const gpet_ctx* ctx, gpet_stats* stats);

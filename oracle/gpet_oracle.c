@@ -62,7 +62,7 @@ static double u01d(uint32_t a, uint32_t b) {
     return (double)k * 1.1102230246251565e-16 + 5.551115123125783e-17;
 }
 
-enum { ST_SOURCE = 1, ST_PHANTOM = 2, ST_DETECTOR = 3, ST_BLUR = 4, ST_PLAN = 5, ST_PSF_POSITRON = 6 };
+enum { ST_SOURCE = 1, ST_PHANTOM = 2, ST_DETECTOR = 3, ST_BLUR = 4, ST_PLAN = 5, ST_PSF_POSITRON = 6, ST_NOISE = 7 };
 
 /* ------------------------------------------------------------------------------------------------ records */
 typedef struct { int32_t parn, pann, modn, cryn, siten, eventid; double t; float E, x, y, z; } orc_event; /* gPET.h:87-92 */
@@ -363,9 +363,29 @@ void orc_source_ex(int nsource, const uint64_t* cum_pairs, const int32_t* shape,
 }
 
 /* ------------------------------------------------------------------------------------------------ phantom (P1) */
-/* photon() (gPET_kernals.cu:256-345), in place: t = -0.5 marks a photo-absorbed photon. */
+/* getDistance (gPET_kernals.cu:148-171): distance along the direction to the PSF-recording sphere rec = (x, y, z, r) */
+static float record_distance(const float rec[4], const orc_photon* p) {
+    float cx = p->x - rec[0], cy = p->y - rec[1], cz = p->z - rec[2];
+    float a = p->vx * p->vx + p->vy * p->vy + p->vz * p->vz;
+    float b = 2.0f * (p->vx * cx + p->vy * cy + p->vz * cz);
+    float c = (cx * cx + cy * cy + cz * cz) - rec[3] * rec[3];
+    float disc = b * b - 4 * a * c;
+    if (disc < 0) return 0.f;
+    if (c < 0) return (-b + sqrtf(disc)) / (2 * a);
+    if (b < 0) return (-b - sqrtf(disc)) / (2 * a);
+    return (-b + sqrtf(disc)) / (2 * a);
+}
+
+/* photon() (gPET_kernals.cu:256-345), in place: t = -0.5 marks a photo-absorbed photon.  rec != NULL switches on the
+ * RECORDPSF == -1 branch (:288-294): a photon that leaves the phantom is moved onto the recording sphere. */
+void orc_phantom_ex(orc_photon* ph, int64_t n, const int32_t* mat, const float* dens, const int32_t dim[3],
+                    const float offset[3], const float size[3], const orc_tables* tb, float eabs, uint64_t seed, const float* rec);
 void orc_phantom(orc_photon* ph, int64_t n, const int32_t* mat, const float* dens, const int32_t dim[3],
                  const float offset[3], const float size[3], const orc_tables* tb, float eabs, uint64_t seed) {
+    orc_phantom_ex(ph, n, mat, dens, dim, offset, size, tb, eabs, seed, NULL);
+}
+void orc_phantom_ex(orc_photon* ph, int64_t n, const int32_t* mat, const float* dens, const int32_t dim[3],
+                    const float offset[3], const float size[3], const orc_tables* tb, float eabs, uint64_t seed, const float* rec) {
     float idx = 1.0f / (size[0] / dim[0]), idy = 1.0f / (size[1] / dim[1]), idz = 1.0f / (size[2] / dim[2]);
     for (int64_t id = 0; id < n; id++) {
         orc_photon* p = ph + id;
@@ -383,7 +403,14 @@ void orc_phantom(orc_photon* ph, int64_t n, const int32_t* mat, const float* den
             p->t += (double)s / ORC_SPE;
             /* getAbsVox (:19-29): truncation, voxel layer 0 counts as outside */
             int ix = (int)((p->x - offset[0]) * idx), iy = (int)((p->y - offset[1]) * idy), iz = (int)((p->z - offset[2]) * idz);
-            if (ix <= 0 || ix >= dim[0] || iy <= 0 || iy >= dim[1] || iz <= 0 || iz >= dim[2]) break;
+            if (ix <= 0 || ix >= dim[0] || iy <= 0 || iy >= dim[1] || iz <= 0 || iz >= dim[2]) {
+                if (rec) {
+                    float rr = record_distance(rec, p);
+                    p->x = fmaf(rr, p->vx, p->x); p->y = fmaf(rr, p->vy, p->y); p->z = fmaf(rr, p->vz, p->z);
+                    p->t += (double)rr / ORC_SPE;
+                }
+                break;
+            }
             size_t v = ((size_t)iz * dim[1] + iy) * dim[0] + ix;
             float rho = dens[v];
             int m = mat[v];
@@ -634,6 +661,49 @@ int64_t orc_detector(const orc_photon* ph, int64_t n, const orc_panel* panels, i
     return entered;
 }
 
+/* ------------------------------------------------------------------------------------------------ noise singles */
+/* addnoise (gPET_kernals.cu:699-735): thread `id` walks a Poisson process of mean gap `lambda` through its time slice
+ * [id, id+1) * interval; every arrival is an event with E = Emean + sigma * N(0,1), position numbers uniform in (0,1],
+ * uniformly drawn panel / module / crystal, parn = -1, crystal-level siten.  The reference never launches it.  Fixed
+ * here on purpose (and documented in DESIGN.md): fp64 time accumulation (the reference's fp32 `t` stalls once its ulp
+ * exceeds the gaps), int(N * u) clamped to N - 1, eventid = 0x80000000 | (slice << 10 | ordinal), arrivals kept only
+ * inside [t_lo, t_hi).  Returns the number of events (written while < cap), in slice order. */
+int64_t orc_noise(double t_lo, double t_hi, float lambda_us, float Emean, float sigma, float interval_us, int32_t npanels,
+                  int32_t moduleN, int32_t crystalN, uint64_t seed, orc_event* out, int64_t cap) {
+    if (!(lambda_us > 0.f) || !(interval_us > 0.f) || !(t_hi > t_lo)) return 0;
+    double iv = (double)interval_us, lam = (double)lambda_us;
+    int64_t id0 = (int64_t)floor(t_lo / iv), id1 = (int64_t)ceil(t_hi / iv), n = 0;
+    if (id1 <= id0) id1 = id0 + 1;
+    for (int64_t id = id0; id < id1; id++) {
+        double t = (double)id * iv, tend = (double)(id + 1) * iv;
+        orc_rng g;
+        rng_init(&g, seed, (uint64_t)id, (uint32_t)ST_NOISE << 24);
+        for (uint32_t ord = 0; ord < (1u << 20); ord++) {
+            uint32_t r[4], q[4], w[4];
+            rng_next(&g, r);
+            t = t + (-log((double)u01(r[0]))) * lam;
+            if (!(t < tend)) break;
+            rng_next(&g, q);
+            rng_next(&g, w);
+            if (t < t_lo || !(t < t_hi)) continue;
+            orc_event e;
+            double gs = sqrt(-2.0 * log((double)u01(r[1]))) * cos(6.283185307179586 * (double)u01(r[2]));
+            e.E = (float)((double)Emean + (double)sigma * gs);
+            e.x = u01(r[3]); e.y = u01(q[0]); e.z = u01(q[1]);
+            e.parn = -1;
+            e.pann = (int32_t)((float)npanels * u01(q[2])); if (e.pann > npanels - 1) e.pann = npanels - 1;
+            e.modn = (int32_t)((float)moduleN * u01(q[3])); if (e.modn > moduleN - 1) e.modn = moduleN - 1;
+            e.cryn = (int32_t)((float)crystalN * u01(w[0])); if (e.cryn > crystalN - 1) e.cryn = crystalN - 1;
+            e.siten = e.pann * moduleN * crystalN + e.modn * crystalN + e.cryn;
+            e.eventid = (int32_t)(0x80000000u | ((((uint32_t)id << 10) | (ord & 1023u)) & 0x7fffffffu));
+            e.t = t;
+            if (n < cap) out[n] = e;
+            n++;
+        }
+    }
+    return n;
+}
+
 /* ------------------------------------------------------------------------------------------------ digitizer (D3-D7) */
 static void merge_sort_idx(int64_t* idx, int64_t* tmp, int64_t n, int (*less)(int64_t, int64_t, const void*), const void* ctx) {
     /* bottom-up stable merge sort of an index array */
@@ -697,7 +767,9 @@ int64_t orc_digitize(const orc_event* in, int64_t n, const orc_digi_params* p, o
         if (!(R > 0.f)) R = 0.f;
         if (R > 0.f || p->blur_space > 0.f || p->time_blur_sigma_us > 0.f) {
             orc_rng g;
-            rng_init(&g, p->seed, (uint64_t)(uint32_t)e->parn, ((uint32_t)ST_BLUR << 24) | ((uint32_t)e->siten & 0xFFFFFFu));
+            /* stream = the photon; noise events (parn == -1, orc_noise) are told apart by their event id */
+            uint64_t who = e->parn == -1 ? ((1ull << 32) | (uint32_t)e->eventid) : (uint64_t)(uint32_t)e->parn;
+            rng_init(&g, p->seed, who, ((uint32_t)ST_BLUR << 24) | ((uint32_t)e->siten & 0xFFFFFFu));
             uint32_t r[4];
             rng_next(&g, r);
             float rad = sqrtf(-2.0f * logf(u01(r[0])));

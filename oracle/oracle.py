@@ -135,14 +135,27 @@ def psf_positron(positrons, first, dens, offset, size, nonangle, use_prange, see
     return out
 
 
-def phantom(photons, mat, dens, offset, size, tables: TableSet, eabs, seed):
+def phantom(photons, mat, dens, offset, size, tables: TableSet, eabs, seed, record_sphere=None):
+    """photon() (gPET_kernals.cu:256-345); record_sphere = (x, y, z, r) switches on the RECORDPSF == -1 branch."""
     ph = np.ascontiguousarray(photons, PHOTON_DTYPE).copy()
     mat = np.ascontiguousarray(mat, np.int32); dens = np.ascontiguousarray(dens, np.float32)
     nz, ny, nx = mat.shape
     dim = np.array([nx, ny, nz], np.int32); off = np.asarray(offset, np.float32); sz = np.asarray(size, np.float32)
-    lib().orc_phantom(_p(ph), C.c_int64(ph.size), _p(mat), _p(dens), _p(dim), _p(off), _p(sz), C.byref(tables.c),
-                      C.c_float(eabs), C.c_uint64(seed))
+    rec = None if record_sphere is None else np.ascontiguousarray(record_sphere, np.float32)
+    lib().orc_phantom_ex(_p(ph), C.c_int64(ph.size), _p(mat), _p(dens), _p(dim), _p(off), _p(sz), C.byref(tables.c),
+                         C.c_float(eabs), C.c_uint64(seed), _p(rec) if rec is not None else None)
     return ph
+
+
+def noise(t_lo_us, t_hi_us, mean_gap_us, Emean, sigma, interval_us, npanels, moduleN, crystalN, seed, cap=1 << 22):
+    """addnoise (gPET_kernals.cu:699-735) restated: the noise events with t_lo <= t < t_hi, in slice order."""
+    out = np.zeros(cap, EVENT_DTYPE)
+    lib().orc_noise.restype = C.c_int64
+    n = lib().orc_noise(C.c_double(t_lo_us), C.c_double(t_hi_us), C.c_float(mean_gap_us), C.c_float(Emean), C.c_float(sigma),
+                        C.c_float(interval_us), C.c_int32(npanels), C.c_int32(moduleN), C.c_int32(crystalN), C.c_uint64(seed),
+                        _p(out), C.c_int64(cap))
+    assert n <= cap, "noise event buffer too small"
+    return out[:n]
 
 
 def detector(photons, panels, counts4, pmat, pdens, surfaces, tables: TableSet, eabs, rdepth, rpolicy, seed,

@@ -195,6 +195,38 @@ def test_phantom_transport_matches_oracle_per_photon():
 
 
 @needs_tables
+def test_phantom_recording_sphere_matches_oracle():
+    # RECORDPSF == -1 branch of photon() (gPET_kernals.cu:288-294, getDistance :148-171): escaped photons end on the sphere
+    n = 32
+    mat = np.ones((n, n, n), np.int32); den = np.ones((n, n, n), np.float32)
+    s = parity.Setup(0, phantom=(mat, den), size=4.0)
+    sphere = (0.1, -0.2, 0.05, 12.0)
+    s.ctx.set_transport(record_psf=1, record_sphere=sphere)
+    rng = np.random.default_rng(23)
+    ph = parity.isotropic_photons(100000, rng, pos_sigma=0.5)
+    s.ctx.put_photons(0, ph)
+    s.ctx.stage_phantom()
+    got = s.ctx.fetch_photons(1)
+    want = orc.phantom(ph, s.mat, s.den, s.offset, s.size, s.tab_ph, s.eabs, s.seed, record_sphere=sphere)
+    want = want[want["t"] > 0]
+    ncommon, nmatch, only_g, only_o = parity.compare_photons(got, want)
+    assert only_g + only_o <= 0.004 * want.size and nmatch >= 0.995 * ncommon
+    # every photon that left the grid alive (not those stopped below the absorption energy inside) sits on the sphere
+    r = np.sqrt((got["x"] - sphere[0]) ** 2 + (got["y"] - sphere[1]) ** 2 + (got["z"] - sphere[2]) ** 2)
+    assert (np.abs(r - sphere[3]) < 1e-3).mean() > 0.99
+    # and the fused front end takes the same branch: same photons reach the panels as through the staged kernels
+    s.ctx.put_photons(0, ph)
+    s.ctx.stage_phantom(); s.ctx.stage_detector()
+    ev_staged = s.ctx.fetch_events()
+    s.ctx.put_photons(0, ph)
+    s.ctx.stage_front(-1); s.ctx.stage_panel_transport()
+    ev_fused = s.ctx.fetch_events()
+    assert ev_staged.size == ev_fused.size > 0
+    assert np.array_equal(np.sort(ev_staged, order=["parn", "t", "cryn"]), np.sort(ev_fused, order=["parn", "t", "cryn"]))
+    s.close()
+
+
+@needs_tables
 def test_detector_transport_matches_oracle_per_photon():
     s = parity.Setup(0, phantom="air", n=16)
     rng = np.random.default_rng(22)
@@ -355,6 +387,95 @@ def test_run_shipped_example_writes_reference_layouts(tmp_path):
         c2.set_digitizer(blur_Rref=0.0)
         again, _ = c2.digitize(adder)
     assert again.tobytes() == sing.tobytes()
+
+
+@needs_tables
+def test_run_writes_phase_space_dumps_like_outputpsf(tmp_path):
+    # OUTPUTPSF == 2 (gPET.cu:296-351): outsource/idsource/timesource after source sampling, out/id/timephantom after the
+    # phantom; layouts of readOutput.m:36-54.  The dumps force the staged kernels: the singles must not change.
+    ex = make_example_dir(tmp_path, source="source.txt", window="0 10")
+    od = ex / "output"
+    with api.Context(0) as c:
+        c.set_capacity(1 << 17, 1 << 19, 1 << 18)
+        c.load_config_file(ex / "input_PET.in", base_dir=ex)
+        st0 = c.run(None)
+        s0 = c.result_singles().copy()
+        c.set_psf_output(2)
+        st = c.run(od)
+        s1 = c.result_singles().copy()
+    assert st.frames >= 2 and st.pairs == st0.pairs
+    assert s0.tobytes() == s1.tobytes()
+    src, sid, stime = refio.read_psf_triplet(od / "outsource.dat", od / "idsource.dat", od / "timesource.dat")
+    assert src.shape == (2 * st.pairs, 7) and sid.size == stime.size == 2 * st.pairs
+    assert np.array_equal(sid[0::2], sid[1::2]) and np.array_equal(stime[0::2], stime[1::2])    # the two photons of a pair
+    assert np.array_equal(src[0::2, :3], src[1::2, :3])
+    assert np.allclose(np.linalg.norm(src[:, 3:6], axis=1), 1.0, atol=1e-4)
+    assert np.all(np.abs(src[:, 6] - 510999.1) < 30e3) and stime.min() > 0 and stime.max() <= 10e6
+    # back to back up to the acollinearity (sigma 0.0037 rad)
+    assert np.all(np.einsum("ij,ij->i", src[0::2, 3:6], src[1::2, 3:6]) < -0.999)
+    ph, pid, ptime = refio.read_psf_triplet(od / "outphantom.dat", od / "idphantom.dat", od / "timephantom.dat")
+    assert ph.shape == (st.photons_phantom_out, 7) and pid.size == ptime.size == st.photons_phantom_out
+    assert 0.8 * 2 * st.pairs < pid.size <= 2 * st.pairs and np.all(np.isin(pid, sid))
+    assert np.all(ph[:, 6] <= src[:, 6].max()) and ptime.min() > 0
+    # PSF-input mode, OUTPUTPSF == 1 (gPET.cu:63-88): the uploaded photons come back as the source triplet
+    rng = np.random.default_rng(5)
+    n = 20000
+    v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1)[:, None]
+    t = np.repeat(np.arange(1, n + 1, dtype=np.float64), 2)
+    vv = np.empty((2 * n, 3)); vv[0::2] = v; vv[1::2] = -v
+    refio.write_psf(ex / "input" / "psf.dat", np.zeros(2 * n), np.zeros(2 * n), np.zeros(2 * n), t, vv[:, 0], vv[:, 1], vv[:, 2],
+                    np.full(2 * n, 511000.0))
+    od2 = tmp_path / "out_psf"; od2.mkdir()
+    with api.Context(0) as c:
+        c.load_config_file(ex / "input_PET.in", base_dir=ex)
+        c.load_psf(ex / "input" / "psf.dat", 0, 1)
+        c.set_psf_output(1)
+        st = c.run(od2)
+    src, sid, stime = refio.read_psf_triplet(od2 / "outsource.dat", od2 / "idsource.dat", od2 / "timesource.dat")
+    assert src.shape == (2 * n, 7) and np.array_equal(sid, np.arange(2 * n)) and np.array_equal(stime, t)
+    assert np.array_equal(src[:, 3:6], vv.astype(np.float32)) and not (od2 / "outphantom.dat").exists()
+    assert st.singles > 0
+
+
+@needs_tables
+def test_noise_singles_match_oracle_and_enter_the_digitizer(tmp_path):
+    # addnoise (gPET_kernals.cu:699-735): same Philox streams on both sides; fp64 log / cos may differ in the last bit
+    s = parity.Setup(0, phantom="air", n=16)
+    c = s.ctx
+    lo, hi = 2.5e5, 7.5e5
+    p, d = parity.make_digi_params(seed=s.seed, dead_level=2, ewin_min=350000.0, ewin_max=650000.0, coinc_window_us=0.0)
+    parity.apply_digi_params(c, d)
+    c.set_digitizer(noise_mean_gap_us=1.5, noise_Emean_eV=4.0e5, noise_sigma_eV=3.0e4, noise_interval_us=500.0)
+    c.put_events(np.zeros(0, api.EVENT_DTYPE))
+    c.stage_noise(lo, hi)
+    got = c.fetch_events()
+    want = orc.noise(lo, hi, 1.5, 4.0e5, 3.0e4, 500.0, 8, 117, 64, s.seed).astype(api.EVENT_DTYPE)
+    assert abs(want.size - (hi - lo) / 1.5) < 5 * np.sqrt((hi - lo) / 1.5)
+    assert got.size == want.size
+    got = got[np.argsort(got["eventid"].view(np.uint32), kind="stable")]
+    want = want[np.argsort(want["eventid"].view(np.uint32), kind="stable")]
+    for k in ("parn", "pann", "modn", "cryn", "siten", "eventid", "x", "y", "z"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.allclose(got["t"], want["t"], rtol=1e-13, atol=0) and np.allclose(got["E"], want["E"], rtol=1e-6)
+    # noise + digitizer: the GPU's own noise list through the oracle digitizer gives the GPU's singles bit for bit
+    c.stage_digitize()
+    singles = c.fetch_singles()
+    osingles, _, _ = orc.digitize(got, p)
+    assert 0.5 * got.size < singles.size < got.size and singles.tobytes() == osingles.astype(api.EVENT_DTYPE).tobytes()
+    s.close()
+    # gpet_run injects the noise per frame: more singles than without, all noise singles inside the acquisition window
+    ex = make_example_dir(tmp_path, source="source.txt", window="0 10")
+    with api.Context(0) as c:
+        c.set_capacity(1 << 17, 1 << 19, 1 << 18)
+        c.load_config_file(ex / "input_PET.in", base_dir=ex)
+        st0 = c.run(None)
+        c.set_digitizer(noise_mean_gap_us=100.0, noise_Emean_eV=4.5e5, noise_sigma_eV=1.0e4, noise_interval_us=1.0e4)
+        st1 = c.run(None)
+        sg = c.result_singles().copy()
+    nz = sg[sg["parn"] == -1]
+    assert st1.frames >= 2 and st1.events_adder - st0.events_adder == pytest.approx(1e7 / 100.0, abs=5 * np.sqrt(1e5))
+    assert 0.5 * 1e5 < nz.size <= st1.events_adder - st0.events_adder
+    assert nz["t"].min() >= 0 and nz["t"].max() < 1e7 and np.all(np.diff(sg["t"][np.argsort(sg["t"], kind="stable")]) >= 0)
 
 
 @needs_tables

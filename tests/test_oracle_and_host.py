@@ -55,6 +55,26 @@ def test_digitizer_oracle_invariants():
 
 
 # ------------------------------------------------------------------------------------------------ C ABI surface
+def test_noise_oracle_is_a_poisson_process_over_the_detector():
+    # addnoise (gPET_kernals.cu:699-735): mean gap 2 us over 0.1 s -> 50 000 +- 224 arrivals, uniform sites, E ~ N(300 keV, 20 keV)
+    ev = orc.noise(5.0e4, 1.5e5, 2.0, 3.0e5, 2.0e4, 1000.0, 8, 117, 64, 99)
+    assert abs(ev.size - 50000) < 5 * np.sqrt(50000)
+    assert ev["t"].min() >= 5.0e4 and ev["t"].max() < 1.5e5 and np.all(np.diff(ev["t"]) > 0)
+    gaps = np.diff(ev["t"])
+    assert abs(gaps.mean() - 2.0) < 0.05 and abs(gaps.std() - 2.0) < 0.1          # exponential gaps
+    assert abs(ev["E"].mean() - 3.0e5) < 5 * 2.0e4 / np.sqrt(ev.size) and abs(ev["E"].std() - 2.0e4) < 500
+    assert np.all(ev["parn"] == -1) and np.all(ev["eventid"] < 0) and np.unique(ev["eventid"]).size == ev.size
+    assert ev["pann"].min() == 0 and ev["pann"].max() == 7 and ev["modn"].max() == 116 and ev["cryn"].max() == 63
+    assert np.array_equal(ev["siten"], (ev["pann"] * 117 + ev["modn"]) * 64 + ev["cryn"])
+    assert abs(np.bincount(ev["pann"], minlength=8) - ev.size / 8).max() < 5 * np.sqrt(ev.size / 8)
+    assert ev["x"].min() > 0 and ev["x"].max() <= 1
+    # windows tile: the events of [a, c) are those of [a, b) followed by those of [b, c)
+    a = orc.noise(5.0e4, 9.99e4, 2.0, 3.0e5, 2.0e4, 1000.0, 8, 117, 64, 99)
+    b = orc.noise(9.99e4, 1.5e5, 2.0, 3.0e5, 2.0e4, 1000.0, 8, 117, 64, 99)
+    assert np.concatenate([a, b]).tobytes() == ev.tobytes()
+    assert orc.noise(0, 1e5, 0.0, 3e5, 2e4, 1000.0, 8, 117, 64, 99).size == 0      # disabled
+
+
 def test_library_exports_every_declared_symbol():
     header = (parity.ROOT / "include" / "gpet_b200.h").read_text()
     declared = set(re.findall(r"\b(gpet_[a-z_0-9]+)\s*\(", header))
