@@ -268,24 +268,57 @@ def main():
         ctx.plan_frames(0)
         return ex, ctx
 
-    # Tally reduction over NCCL is part of the multi-GPU step (gpet_b200/multi.py).  It is issued asynchronously on a
-    # device tensor; the NEXT step's kernels are ordered behind it on the GPU (work.wait() is a stream dependency, not a
-    # host block), so every reduction runs inside a timed region without a host round trip per step.
-    pending = []
-    tally_host = torch.zeros(len(multi.TALLY_FIELDS), dtype=torch.int64).pin_memory() if world > 1 else None
-    tally_dev = torch.zeros(len(multi.TALLY_FIELDS), dtype=torch.int64, device=dev) if world > 1 else None
+    # Tally reduction over NCCL is part of the multi-GPU step (gpet_b200/multi.py).  Nothing in a step depends on the
+    # tallies, so the reduction of step k-1 is issued at the top of step k (after the step's start event) by a helper
+    # thread -- its host-side cost (~60 us of tensor copies and NCCL enqueue) and its NCCL kernel both overlap step k's
+    # own launches and kernels (gpet_run* is a foreign call: the GIL is free) -- and is waited for before the step's end
+    # event; the last step of a timed region also reduces its own tallies.  Every reduction therefore starts and
+    # completes inside a timed step.
+    import queue
+    nt = len(multi.TALLY_FIELDS)
+    no_tally = os.environ.get("GPET_BENCH_NO_TALLY") == "1"   # diagnostic only: what the per-step collective costs
+    carried = [None]                            # stats of the previous step, not reduced yet
+    jobs, done = queue.SimpleQueue(), queue.SimpleQueue()
+
+    def reducer():
+        torch.cuda.set_device(local)
+        side = torch.cuda.Stream(device=dev)
+        tally_host = torch.zeros(nt, dtype=torch.int64).pin_memory()
+        tally_dev = torch.zeros(nt, dtype=torch.int64, device=dev)
+        with torch.cuda.stream(side):
+            while True:
+                st = jobs.get()
+                if st is None:
+                    return
+                tally_host.copy_(torch.from_numpy(multi.stats_vector(st)))
+                tally_dev.copy_(tally_host, non_blocking=True)
+                done.put(dist.all_reduce(tally_dev, async_op=True))
+
+    if world > 1 and not no_tally:
+        threading.Thread(target=reducer, daemon=True).start()
+    inflight = [0]
+
+    def issue_reduce(st):
+        if world > 1 and not no_tally:
+            jobs.put(st)
+            inflight[0] += 1
 
     def drain():
-        while pending:
-            pending.pop().wait()
+        while inflight[0]:
+            done.get().wait()                   # stream dependency of this step's stream on the reduction
+            inflight[0] -= 1
 
-    def one_step(ctx, resident=True):
-        drain()
+    def one_step(ctx, resident=True, last=False):
+        if carried[0] is not None:
+            issue_reduce(carried[0])
         st = ctx.run_resident() if resident else ctx.run(None)
         if world > 1:
-            tally_host.copy_(torch.from_numpy(multi.stats_vector(st)))
-            tally_dev.copy_(tally_host, non_blocking=True)
-            pending.append(dist.all_reduce(tally_dev, async_op=True))
+            drain()
+            carried[0] = st
+            if last:
+                issue_reduce(st)
+                drain()
+                carried[0] = None
         return st
 
     def timed(ctx, nsteps, resident=True):
@@ -298,9 +331,7 @@ def main():
             w0 = time.perf_counter()
             if not resident:
                 ctx.plan_frames(0)              # e2e: planning + descriptor upload are part of the user's call
-            st = one_step(ctx, resident)
-            if _ == nsteps - 1:
-                drain()                         # the last reduction belongs to this timed region
+            st = one_step(ctx, resident, last=_ == nsteps - 1)
             e1.record(stream)
             torch.cuda.synchronize()
             w1 = time.perf_counter()
@@ -418,6 +449,7 @@ def main():
                              "coincidences_per_s": float(m["coinc"] / (m["total_ms"] * 1e-3))},
                 "extra": extra}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
+    jobs.put(None)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
