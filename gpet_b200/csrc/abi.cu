@@ -71,7 +71,7 @@ int ensure_buffers(gpet_ctx* c) {
     w.max_tiles = scan_tiles(ce);
     {
         const size_t mt4 = ((size_t)w.max_tiles + 3) & ~(size_t)3, st2 = (size_t)bucket_words() / 2048 + 4;   // 16-byte segments
-        const size_t words = 64 + 2 * mt4 + st2 + 4 + (size_t)bucket_words();
+        const size_t words = 64 + 2 * mt4 + st2 + 4 + (size_t)bucket_words() + kHotWords + 32;
         unsigned* p = nullptr;
         if ((r = dev_alloc(c, &p, words))) return r;
         CK(cudaMemset(p, 0, words * sizeof(unsigned)));
@@ -82,18 +82,20 @@ int ensure_buffers(gpet_ctx* c) {
         w.scan_status[1] = p; p += mt4;
         w.scan_status[2] = p; p += st2;
         w.minmax = reinterpret_cast<unsigned long long*>(p); p += 4;
-        w.bcount = p;
+        w.bcount = p; p += bucket_words();
+        // hot counters on lines of their own, 128-byte aligned (kernels.hpp HotWord)
+        w.hot = reinterpret_cast<unsigned*>((reinterpret_cast<uintptr_t>(p) + 127) & ~(uintptr_t)127);
     }
     if ((r = alloc_queue(c, c->q[0], cp, w.counters + 16))) return r;
     if ((r = alloc_queue(c, c->q[1], cp, w.counters + 17))) return r;
-    if ((r = alloc_queue(c, c->q[2], cp, w.counters + 21))) return r;   // photons that entered a panel (panel-local frame)
+    if ((r = alloc_queue(c, c->q[2], cp, w.hot + kHotQ2))) return r;   // photons that entered a panel (panel-local frame)
     if ((r = dev_alloc(c, &c->hits.id, 5 * ch))) return r;
     if ((r = dev_alloc(c, &c->hits.f, 5 * ch))) return r;
     if ((r = dev_alloc(c, &c->hits.t, ch))) return r;
-    c->hits.count = w.counters + 18;
+    c->hits.count = w.hot + kHotHitsEvents;
     c->hits.capacity = (unsigned)ch;
     if ((r = dev_alloc(c, &c->ev.rec, ce))) return r;
-    c->ev.count = w.counters + 19;
+    c->ev.count = w.hot + kHotHitsEvents + 1;
     c->ev.capacity = (unsigned)ce;
     for (int k = 0; k < 2; k++) {
         if ((r = dev_alloc(c, &w.tkeys[k], ce))) return r;
@@ -140,7 +142,7 @@ int ensure_buffers(gpet_ctx* c) {
             CK(cudaMalloc(&p, (size_t)c->coinc_cap * sizeof(uint2)));
             c->allocs.push_back(p);
             c->pairs_slot[k] = p;
-            CK(cudaMallocHost((void**)&c->h_slot_counters[k], 32 * sizeof(unsigned)));
+            CK(cudaMallocHost((void**)&c->h_slot_counters[k], 64 * sizeof(unsigned)));
             CK(cudaEventCreateWithFlags(&c->ev_counters[k], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
         }
@@ -268,6 +270,7 @@ int upload_geometry(gpet_ctx* c) {
         d.mody = p.MODy; d.modz = p.MODz; d.mspy = p.Mspacey; d.mspz = p.Mspacez;
         d.lsoy = p.LSOy; d.lsoz = p.LSOz; d.spy = p.spacey; d.spz = p.spacez;
         d.id = p.panel;
+        d.r2 = 0.25f * (p.lengthy * p.lengthy + p.lengthz * p.lengthz);
     }
     if ((r = dev_alloc(c, &c->d_panels, pd.size()))) return r;
     CK(cudaMemcpy(c->d_panels, pd.data(), pd.size() * sizeof(PanelDev), cudaMemcpyHostToDevice));
@@ -286,6 +289,16 @@ DetectorDev detector_dev(const gpet_ctx* c) {
     d.dens[0] = g.dens[0]; d.dens[1] = g.dens[1];
     d.nsurface = c->tr.nsurface;
     memcpy(d.surface, c->tr.surface, sizeof(float) * 10 * GPET_MAX_SURFACES);
+    // the bounding-sphere rejection in panel_entry needs Euclidean local coordinates: orthonormal axes on every panel
+    d.prefilter = g.panels.size() <= 32;
+    for (const gpet_panel& p : g.panels) {
+        const double u[3][3] = {{p.UniXx, p.UniXy, p.UniXz}, {p.UniYx, p.UniYy, p.UniYz}, {p.UniZx, p.UniZy, p.UniZz}};
+        for (int a = 0; a < 3; a++)
+            for (int b = a; b < 3; b++) {
+                const double dot = u[a][0] * u[b][0] + u[a][1] * u[b][1] + u[a][2] * u[b][2];
+                if (std::fabs(dot - (a == b ? 1.0 : 0.0)) > 1e-4) d.prefilter = 0;
+            }
+    }
     return d;
 }
 
@@ -343,9 +356,26 @@ int validate_materials(gpet_ctx* c) {
     return GPET_OK;
 }
 
+// One frame's counters to the host: the 32-word block plus the hot counters (gathered by one strided copy into words
+// 32..), asynchronously.  patch_counters() then puts the hot values where the host code reads them.
+int fetch_counters_async(gpet_ctx* c, unsigned* h) {
+    CK(cudaMemcpyAsync(h, c->ws.counters, 32 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpy2DAsync(h + 32, 2 * sizeof(unsigned), c->ws.hot, kHotStride * sizeof(unsigned), 2 * sizeof(unsigned), 4,
+                         cudaMemcpyDeviceToHost, c->stream));
+    return GPET_OK;
+}
+
+void patch_counters(unsigned* h) {
+    h[21] = h[32 + 2 * (kHotQ2 / kHotStride)];                 // photons on a panel
+    h[18] = h[32 + 2 * (kHotHitsEvents / kHotStride)];         // hits
+    h[19] = h[32 + 2 * (kHotHitsEvents / kHotStride) + 1];     // events
+}
+
 int read_counters(gpet_ctx* c) {  // synchronises the stream
-    CK(cudaMemcpyAsync(c->h_counters, c->ws.counters, 32 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    int r;
+    if ((r = fetch_counters_async(c, c->h_counters))) return r;
     CK(cudaStreamSynchronize(c->stream));
+    patch_counters(c->h_counters);
     return GPET_OK;
 }
 
@@ -790,7 +820,7 @@ int gpet_stage_detector(gpet_ctx* c) {
     if ((r = upload_geometry(c))) return r;
     c->stats.kernel_launches += launch_panel_entry(c->q[1], c->q[2], detector_dev(c), c->ws.counters, c->num_sms, c->stream);
     c->stats.kernel_launches += launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth,
-                                                c->dig.readout_policy, c->tr.record_hits, c->hits, c->ev, c->ws.counters,
+                                                c->dig.readout_policy, c->tr.record_hits, c->hits, c->ev, c->ws.counters, c->ws.hot,
                                                 c->seed, c->num_sms, c->stream, !c->in_run);
     CK(cudaGetLastError());
     return GPET_OK;
@@ -814,7 +844,7 @@ int gpet_stage_front(gpet_ctx* c, int64_t f) {
         npairs = fp.npairs;
     }
     c->stats.kernel_launches += launch_front(fr, npairs, c->q[0], c->q[1], c->q[2], phantom_dev(c), tables_dev(c), detector_dev(c),
-                                             c->tr.eabs_eV, c->ws.counters, c->seed, c->num_sms, c->stream, !c->in_run);
+                                             c->tr.eabs_eV, c->ws.counters, c->ws.hot, c->seed, c->num_sms, c->stream, !c->in_run);
     CK(cudaGetLastError());
     return GPET_OK;
 }
@@ -826,7 +856,7 @@ int gpet_stage_panel_transport(gpet_ctx* c) {
     if ((r = ensure_buffers(c))) return r;
     if ((r = upload_geometry(c))) return r;
     c->stats.kernel_launches += launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth,
-                                                c->dig.readout_policy, c->tr.record_hits, c->hits, c->ev, c->ws.counters,
+                                                c->dig.readout_policy, c->tr.record_hits, c->hits, c->ev, c->ws.counters, c->ws.hot,
                                                 c->seed, c->num_sms, c->stream, !c->in_run);
     CK(cudaGetLastError());
     return GPET_OK;
@@ -1085,6 +1115,7 @@ struct RunState {
 int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
     int r;
     CK(cudaEventSynchronize(c->ev_counters[slot]));
+    patch_counters(c->h_slot_counters[slot]);
     const unsigned* h = c->h_slot_counters[slot];
     gpet_stats& st = rs.st;
     const uint64_t n_ev = h[19], n_hits = h[18], n_q1 = h[17];
@@ -1253,7 +1284,7 @@ int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* sta
         rc = gpet_stage_digitize(c);
         c->have_range = false;
         if (rc) break;
-        CK(cudaMemcpyAsync(c->h_slot_counters[slot], c->ws.counters, 32 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+        if ((rc = fetch_counters_async(c, c->h_slot_counters[slot]))) break;
         CK(cudaEventRecord(c->ev_counters[slot], c->stream));
         k++;
         if (!pipelined) rc = retire_frame(c, slot, rs);

@@ -82,7 +82,8 @@ struct PanelDev {  // one panel, 128 B
     float lsoy, lsoz;          // crystal size
     float spy, spz;            // crystal gap
     int id;
-    float pad[7];
+    float r2;                  // (ly/2)^2 + (lz/2)^2: squared radius of the sphere around the face centre that holds the face
+    float pad[6];
 };
 static_assert(sizeof(PanelDev) == 128, "PanelDev must be 128 B");
 
@@ -94,6 +95,7 @@ struct DetectorDev {
     float dens[2];
     int nsurface;
     float surface[50];
+    int prefilter;             // 1: every panel's local axes are orthonormal, so the bounding-sphere rejection of panel_entry is valid
 };
 
 struct PhantomDev {

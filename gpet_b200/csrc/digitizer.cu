@@ -799,7 +799,7 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
                                                // never run in the same frame)
     if (reset) {   // the digitizer's share of the frame state: counters[0..7], then everything behind the counter block
         cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned), s);
-        cudaMemsetAsync(ws.counters + 64, 0, ws.frame_state_bytes - 64 * sizeof(unsigned), s);
+        cudaMemsetAsync(ws.counters + 64, 0, (size_t)(ws.hot - (ws.counters + 64)) * sizeof(unsigned), s);   // not the hot block: it holds the event count
     }
     TimeRange tr;
     if (range) {

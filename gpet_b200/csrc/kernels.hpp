@@ -46,6 +46,10 @@ struct DigitizerWorkspace {
     // compactions [5] time sort fell back to LSD radix [8] photons on a panel [9] adder drops [10],[11] photon tickets of
     // k_detector / k_front; [16..19] queue 0, queue 1, hits, events counts, [21] queue 2
     unsigned int* counters;
+    // Hot counters, one per 4 KB of their own: warp-aggregated atomics on ONE 128-byte line serialise at 0.67 ns each
+    // whatever word they hit (tools/microbench/latency.cu), which bounded k_front and k_detector while tickets and queue
+    // counts shared the counter block.  Word offsets below; part of frame_state (zeroed by the frame's memset).
+    unsigned int* hot;
     unsigned long long* spectrum; int spectrum_bins; float spec_emin, spec_emax;
 };
 
@@ -58,6 +62,15 @@ struct DigitizerOut {
     unsigned int coinc_cap;
     const unsigned int* pair_base_in;   // singles of the run's earlier frames (device word), nullptr = 0
     unsigned int* pair_base_out;        // receives *pair_base_in + this frame's singles, or nullptr
+};
+
+enum HotWord : unsigned {
+    kHotStride = 1024,                 // words between hot counters
+    kHotTicketFront = 0 * kHotStride,  // k_front's pair / photon ticket
+    kHotQ2 = 1 * kHotStride,           // photons on a panel (queue 2 count)
+    kHotTicketDet = 2 * kHotStride,    // k_detector's photon ticket
+    kHotHitsEvents = 3 * kHotStride,   // hits count, events count: adjacent words, reserved together by one 64-bit atomic
+    kHotWords = 4 * kHotStride
 };
 
 size_t sort_state_bytes();
@@ -84,10 +97,11 @@ int launch_phantom(PhotonQueue q0, PhotonQueue q1, PhantomDev ph, TablesDev tb, 
 int launch_panel_entry(PhotonQueue q1, PhotonQueue q2, DetectorDev det, unsigned int* counters, int num_sms, cudaStream_t s);
 // fused source (frame_dev != nullptr) or queue q0 (frame_dev == nullptr) -> phantom -> panel entry -> q2; q1 only counts
 int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQueue q0, PhotonQueue q1, PhotonQueue q2,
-                 PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, unsigned int* counters, uint64_t seed, int num_sms,
-                 cudaStream_t s, bool reset);
+                 PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, unsigned int* counters, unsigned int* hot, uint64_t seed,
+                 int num_sms, cudaStream_t s, bool reset);
+// hits.count and ev.count must be adjacent words (hits first, 8-byte aligned): one 64-bit atomic reserves both
 int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
-                    int record_hits, HitBuffer hits, EventBuf ev, unsigned int* counters, uint64_t seed,
+                    int record_hits, HitBuffer hits, EventBuf ev, unsigned int* counters, unsigned int* hot, uint64_t seed,
                     int num_sms, cudaStream_t s, bool reset);
 int launch_photons_aos_to_queue(const void* aos, PhotonQueue q, unsigned int n, cudaStream_t s);
 int launch_queue_to_photons_aos(PhotonQueue q, void* aos, cudaStream_t s);

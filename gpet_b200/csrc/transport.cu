@@ -434,28 +434,57 @@ __device__ __forceinline__ void compton_kn(float E, Philox& rng, float& efrac, f
 // Panel entry (gPET_kernals.cu:963-1009): the first panel (in index order) whose front face the photon's straight line
 // crosses while moving along the panel's growth direction.  On success the photon is returned in that panel's local
 // frame with the time of flight to the face added; ov.w carries the panel index.
-__device__ __forceinline__ bool panel_entry(const PanelDev* __restrict__ s_panels, int npanels, const Photon& p,
+// The exact test of one panel, statement by statement (gPET_kernals.cu:966-1007).
+__device__ __forceinline__ bool panel_entry_one(const PanelDev& pd, int i, const Photon& p, float4& pe, float4& ov, double& t) {
+    const float lvx = fmaf(p.vz, pd.uxz, fmaf(p.vy, pd.uxy, p.vx * pd.uxx));
+    if (!(lvx * pd.dirx >= 0.f)) return false;
+    const float rx = p.x - pd.ox, ry = p.y - pd.oy, rz = p.z - pd.oz;
+    const float lx = fmaf(rz, pd.uxz, fmaf(ry, pd.uxy, rx * pd.uxx));
+    const float q = __fdiv_rn(lx, lvx);
+    const float ly = fmaf(rz, pd.uyz, fmaf(ry, pd.uyy, rx * pd.uyx));
+    const float lvy = fmaf(p.vz, pd.uyz, fmaf(p.vy, pd.uyy, p.vx * pd.uyx));
+    const float y2 = fmaf(-q, lvy, ly);
+    if (!(fabsf(y2) < pd.ly / 2)) return false;
+    const float lz = fmaf(rz, pd.uzz, fmaf(ry, pd.uzy, rx * pd.uzx));
+    const float lvz = fmaf(p.vz, pd.uzz, fmaf(p.vy, pd.uzy, p.vx * pd.uzx));
+    const float z2 = fmaf(-q, lvz, lz);
+    if (!(fabsf(z2) < pd.lz / 2)) return false;
+    pe = make_float4(0.f, y2, z2, p.E);
+    ov = make_float4(lvx, lvy, lvz, __int_as_float(i));
+    t = p.t + (-(double)lx / (kSpeedOfLight * (double)lvx));
+    return true;
+}
+
+__device__ __forceinline__ bool panel_entry(const PanelDev* __restrict__ s_panels, const DetectorDev& det, const Photon& p,
                                             float4& pe, float4& ov, double& t) {
-    for (int i = 0; i < npanels; i++) {
-        const PanelDev& pd = s_panels[i];
-        const float lvx = fmaf(p.vz, pd.uxz, fmaf(p.vy, pd.uxy, p.vx * pd.uxx));
-        if (!(lvx * pd.dirx >= 0.f)) continue;
-        const float rx = p.x - pd.ox, ry = p.y - pd.oy, rz = p.z - pd.oz;
-        const float lx = fmaf(rz, pd.uxz, fmaf(ry, pd.uxy, rx * pd.uxx));
-        const float q = __fdiv_rn(lx, lvx);
-        const float ly = fmaf(rz, pd.uyz, fmaf(ry, pd.uyy, rx * pd.uyx));
-        const float lvy = fmaf(p.vz, pd.uyz, fmaf(p.vy, pd.uyy, p.vx * pd.uyx));
-        const float y2 = fmaf(-q, lvy, ly);
-        if (!(fabsf(y2) < pd.ly / 2)) continue;
-        const float lz = fmaf(rz, pd.uzz, fmaf(ry, pd.uzy, rx * pd.uzx));
-        const float lvz = fmaf(p.vz, pd.uzz, fmaf(p.vy, pd.uzy, p.vx * pd.uzx));
-        const float z2 = fmaf(-q, lvz, lz);
-        if (!(fabsf(z2) < pd.lz / 2)) continue;
-        pe = make_float4(0.f, y2, z2, p.E);
-        ov = make_float4(lvx, lvy, lvz, __int_as_float(i));
-        t = p.t + (-(double)lx / (kSpeedOfLight * (double)lvx));
-        return true;
+    const int npanels = det.npanels;
+    if (det.prefilter) {
+        // Phase 1, the same instructions for every lane: panels that can possibly accept.  An accepted crossing point lies
+        // on the photon's line and on the face, i.e. inside the sphere of radius^2 r2 around the face centre, so a line
+        // that misses the sphere (with a margin far above the rounding of this test) cannot be accepted.  3 of 4 panels
+        // fall to the direction test or to this one before the divide of the exact test.
+        const float vv = fmaf(p.vz, p.vz, fmaf(p.vy, p.vy, p.vx * p.vx));
+        unsigned cand = 0;
+        for (int i = 0; i < npanels; i++) {
+            const PanelDev& pd = s_panels[i];
+            const float lvx = fmaf(p.vz, pd.uxz, fmaf(p.vy, pd.uxy, p.vx * pd.uxx));
+            const float rx = p.x - pd.ox, ry = p.y - pd.oy, rz = p.z - pd.oz;
+            const float dv = fmaf(rz, p.vz, fmaf(ry, p.vy, rx * p.vx));
+            const float dd = fmaf(rz, rz, fmaf(ry, ry, rx * rx));
+            const float miss2 = fmaf(dd, vv, -dv * dv);                      // |d x v|^2 = distance^2 * |v|^2
+            const bool far = miss2 > fmaf(1.0e-3f, dd, 1.01f * pd.r2) * vv;  // NaN compares false: the exact test decides
+            if (lvx * pd.dirx >= 0.f && !far) cand |= 1u << i;
+        }
+        // Phase 2: the exact test on the candidates, in panel order (first accepting panel wins, as in the reference)
+        while (cand) {
+            const int i = __ffs(cand) - 1;
+            cand &= cand - 1;
+            if (panel_entry_one(s_panels[i], i, p, pe, ov, t)) return true;
+        }
+        return false;
     }
+    for (int i = 0; i < npanels; i++)
+        if (panel_entry_one(s_panels[i], i, p, pe, ov, t)) return true;
     return false;
 }
 
@@ -484,7 +513,7 @@ __global__ void __launch_bounds__(kThreads) k_panel_entry(PhotonQueue q1, Detect
             p.x = a.x; p.y = a.y; p.z = a.z; p.E = a.w; p.vx = dn.x; p.vy = dn.y; p.vz = dn.z;
             p.t = q1.t[i];
             id = q1.ids[i];
-            if (p.t > 0.0) ok = panel_entry(s_panels, det.npanels, p, pe, ov, t);
+            if (p.t > 0.0) ok = panel_entry(s_panels, det, p, pe, ov, t);
         }
         unsigned slot = warp_reserve(q2.count, ok ? 1u : 0u);
         if (ok) {
@@ -509,23 +538,49 @@ __global__ void __launch_bounds__(kThreads) k_panel_entry(PhotonQueue q1, Detect
 // generation, panel search) are run when enough lanes wait for them so that they execute nearly convergent.
 // gen_min / entry_min: waiting lanes that trigger pair generation / the panel search
 
+// Entered photons are staged per warp in shared memory and appended 32 at a time: one atomic on the queue count per
+// flush (warp-aggregated atomics on one line serialise at 0.67 ns each, tools/microbench/latency.cu -- with an append
+// per panel search and the ticket on the same line that was 2/3 of this kernel's time) and full-line stores.
+struct FrontStage {
+    float4 pe[kThreads / 32][32];
+    float4 ov[kThreads / 32][32];
+    double t[kThreads / 32][32];
+    int2 id[kThreads / 32][32];
+};
+
+__device__ __forceinline__ void front_flush(FrontStage& st, unsigned warp, unsigned lane, unsigned n, const PhotonQueue& q2) {
+    __syncwarp();
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(q2.count, n);
+    base = __shfl_sync(kFull, base, 0);
+    if (lane < n && base + lane < q2.capacity) {
+        q2.pos_e[base + lane] = st.pe[warp][lane];
+        q2.dir_n[base + lane] = st.ov[warp][lane];
+        q2.t[base + lane] = st.t[warp][lane];
+        q2.ids[base + lane] = st.id[warp][lane];
+    }
+    __syncwarp();
+}
+
 template <bool kFromQueue>
-__global__ void __launch_bounds__(kThreads) k_front(const SourceDev* __restrict__ fr, unsigned long long npairs, PhotonQueue q0,
+__global__ void __launch_bounds__(kThreads, 4) k_front(const SourceDev* __restrict__ fr, unsigned long long npairs, PhotonQueue q0,
                                                     PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, uint64_t seed,
                                                     PhotonQueue q2, unsigned* __restrict__ q1_count,
-                                                    unsigned* __restrict__ counters, int gen_min, int entry_min) {
-    extern __shared__ PanelDev s_panels[];
+                                                    unsigned* __restrict__ counters, unsigned* __restrict__ ticket, int gen_min,
+                                                    int entry_min) {
+    extern __shared__ __align__(16) unsigned char s_front[];
+    FrontStage& stage = *reinterpret_cast<FrontStage*>(s_front);
+    PanelDev* s_panels = reinterpret_cast<PanelDev*>(s_front + sizeof(FrontStage));
     stage_panels(s_panels, det);
     enum { NEED = 0, FLY = 1, ESC = 2 };
-    const unsigned lane = lane_id();
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned nunits = kFromQueue ? min(*q0.count, q0.capacity) : (unsigned)min(npairs, (unsigned long long)(q2.capacity / 2));
-    unsigned* __restrict__ ticket = counters + 11;
     if (!kFromQueue && blockIdx.x == 0 && threadIdx.x == 0) *q0.count = 2u * nunits;
     int state = NEED;
     bool has_b = false, exhausted = false;
     Photon p{}, b{};
-    unsigned n_out = 0, n_on = 0;
+    unsigned n_out = 0, n_on = 0, staged = 0;
     Philox rng(seed, 0, 0);
     while (true) {
         if (!kFromQueue && state == NEED && has_b) {   // second photon of the pair
@@ -578,22 +633,28 @@ __global__ void __launch_bounds__(kThreads) k_front(const SourceDev* __restrict_
             double t = 0.0;
             if (state == ESC) {
                 n_out++;
-                ok = panel_entry(s_panels, det.npanels, p, pe, ov, t);
+                ok = panel_entry(s_panels, det, p, pe, ov, t);
                 state = NEED;
             }
-            const unsigned slot = warp_reserve(q2.count, ok ? 1u : 0u);
+            const unsigned okmask = __ballot_sync(kFull, ok);
+            const unsigned total = __popc(okmask);
+            if (staged + total > 32u) {
+                front_flush(stage, warp, lane, staged, q2);
+                staged = 0;
+            }
             if (ok) {
                 n_on++;
-                if (slot < q2.capacity) {
-                    q2.pos_e[slot] = pe;
-                    q2.dir_n[slot] = ov;
-                    q2.t[slot] = t;
-                    q2.ids[slot] = make_int2(p.eid, p.parn);
-                }
+                const unsigned pos = staged + __popc(okmask & lt_mask);
+                stage.pe[warp][pos] = pe;
+                stage.ov[warp][pos] = ov;
+                stage.t[warp][pos] = t;
+                stage.id[warp][pos] = make_int2(p.eid, p.parn);
             }
+            staged += total;
         }
         if (exhausted && __ballot_sync(kFull, state != NEED || has_b) == 0) break;
     }
+    if (staged) front_flush(stage, warp, lane, staged, q2);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         n_out += __shfl_xor_sync(kFull, n_out, o);
@@ -639,9 +700,13 @@ __device__ __forceinline__ bool adder(SlotsSmem& sl, int& n, int key, float E, f
 __device__ __forceinline__ unsigned readout_merge(SlotsSmem& sl, int nslot, int depth, int rpolicy) {
     const int tid = threadIdx.x;
     unsigned deadmask = 0;
+    // rolled loops on purpose: few lanes of a warp ever get here, and unrolled 6 x 6 this function was 24 KB of SASS --
+    // half the kernel -- pushing the hot loop out of the 32 KB instruction cache
+#pragma unroll 1
     for (int i = 0; i < nslot - 1; i++) {
         if (deadmask >> i & 1u) continue;
         const int ki = sl.key[i][tid];
+#pragma unroll 1
         for (int j = i + 1; j < nslot; j++) {
             if (deadmask >> j & 1u) continue;
             const int kj = sl.key[j][tid];
@@ -671,9 +736,12 @@ __device__ __forceinline__ unsigned readout_merge(SlotsSmem& sl, int nslot, int 
 // their histories.  Adder on the fly, readout (gPET_kernals.cu:756-813) when the photon is finished.
 // refill_min: idle lanes that trigger a refill (amortises the ticket atomic and the queue loads)
 
+constexpr unsigned kDetChunk = 32;   // photons a warp claims from the queue with one ticket atomic
+
 __global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs,
                                                           int rdepth, int rpolicy, int record_hits, HitBuffer hits, EventBuf ev,
-                                                          unsigned* __restrict__ counters, uint64_t seed, int refill_min) {
+                                                          unsigned* __restrict__ counters, unsigned* __restrict__ ticket, uint64_t seed,
+                                                          int refill_min) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     SlotsSmem& sl = *reinterpret_cast<SlotsSmem*>(s_raw);
     PanelDev* s_panels = reinterpret_cast<PanelDev*>(s_raw + sizeof(SlotsSmem));
@@ -683,39 +751,45 @@ __global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, Detect
     const unsigned lane = lane_id();
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned n = min(*q2.count, q2.capacity);
-    unsigned* __restrict__ ticket = counters + 10;
+    // hits.count and ev.count are adjacent words: one 64-bit atomic reserves the warp's hit rows and event records
+    unsigned long long* __restrict__ hits_events = reinterpret_cast<unsigned long long*>(hits.count);
     const int depth = (rdepth != 3 && rpolicy == 1) ? 2 : rdepth;
     bool active = false, exhausted = false;
+    unsigned chunk_pos = 0, chunk_end = 0;   // the warp's claimed share of the queue (warp-uniform)
     float x = 0, y = 0, z = 0, E = 0, vx = 0, vy = 0, vz = 0;
     double t = 0;
     int eid = 0, parn = 0, pa = 0, nslot = 0;
     unsigned n_drop_adder = 0;
     Philox rng(seed, 0, 0);
     while (true) {
-        // ---- refill idle lanes from the ticket counter
+        // ---- refill idle lanes from the warp's chunk of the queue; a new chunk costs one ticket atomic per kDetChunk photons
         unsigned amask = __ballot_sync(kFull, active);
         if (!exhausted && (__popc(~amask) >= refill_min || amask == 0)) {
-            const unsigned need = ~amask;
-            const unsigned cnt = __popc(need);
-            unsigned base = 0;
-            if (lane == 0) base = atomicAdd(ticket, cnt);
-            base = __shfl_sync(kFull, base, 0);
-            if (!active) {
-                const unsigned idx = base + __popc(need & lt_mask);
-                if (idx < n) {
-                    const float4 pe = __ldcs(q2.pos_e + idx);
-                    const float4 dn = __ldcs(q2.dir_n + idx);
-                    t = __ldcs(q2.t + idx);
-                    const int2 id = __ldcs(q2.ids + idx);
-                    x = pe.x; y = pe.y; z = pe.z; E = pe.w;
-                    vx = dn.x; vy = dn.y; vz = dn.z; pa = __float_as_int(dn.w);
-                    eid = id.x; parn = id.y;
-                    rng = Philox(seed, (uint64_t)(uint32_t)parn, (uint32_t)kStageDetector << 24);
-                    nslot = 0;
-                    active = true;
-                }
+            if (chunk_pos == chunk_end) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(ticket, kDetChunk);
+                base = __shfl_sync(kFull, base, 0);
+                chunk_pos = min(base, n);
+                chunk_end = min(base + kDetChunk, n);
+                if (base >= n) exhausted = true;
             }
-            if (base + cnt >= n) exhausted = true;
+            const unsigned need = ~amask;
+            const unsigned avail = chunk_end - chunk_pos;
+            const unsigned rank = __popc(need & lt_mask);
+            if (!active && rank < avail) {
+                const unsigned idx = chunk_pos + rank;
+                const float4 pe = __ldcs(q2.pos_e + idx);
+                const float4 dn = __ldcs(q2.dir_n + idx);
+                t = __ldcs(q2.t + idx);
+                const int2 id = __ldcs(q2.ids + idx);
+                x = pe.x; y = pe.y; z = pe.z; E = pe.w;
+                vx = dn.x; vy = dn.y; vz = dn.z; pa = __float_as_int(dn.w);
+                eid = id.x; parn = id.y;
+                rng = Philox(seed, (uint64_t)(uint32_t)parn, (uint32_t)kStageDetector << 24);
+                nslot = 0;
+                active = true;
+            }
+            chunk_pos += min((unsigned)__popc(need), avail);
             amask = __ballot_sync(kFull, active);
         }
         if (amask == 0) {
@@ -781,39 +855,50 @@ __global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, Detect
                 if (nh == 2 && !adder(sl, nslot, h_key, h_E1, x, y, z, t)) n_drop_adder++;
             }
         }
-        // ---- hits: rows in file layout, warp-aggregated
-        if (record_hits) {
-            unsigned hmask = __ballot_sync(kFull, nh > 0);
-            if (hmask) {
-                unsigned slot = warp_reserve(hits.count, (unsigned)nh);
-                if (nh > 0) {
-                    const int panel_id = s_panels[pa].id;
-                    for (int k = 0; k < nh; k++) {
-                        if (slot + k < hits.capacity) {
-                            int* hi = hits.id + 5ull * (slot + k);
-                            float* hf = hits.f + 5ull * (slot + k);
-                            hi[0] = parn; hi[1] = panel_id; hi[2] = h_key >> 16; hi[3] = h_key & 0xffff; hi[4] = k ? 2 : h_type0;
-                            hf[0] = k ? h_E1 : h_E0; hf[1] = (float)t; hf[2] = x; hf[3] = y; hf[4] = z;
-                            hits.t[slot + k] = t;
-                        }
+        // ---- photon finished: readout (gPET_kernals.cu:756-813)
+        if (finished) active = false;
+        const bool mine = finished && nslot > 0;
+        unsigned deadmask = 0;
+        if (mine && nslot > 1 && rdepth != 3) deadmask = readout_merge(sl, nslot, depth, rpolicy);
+        const unsigned ne = mine ? (unsigned)(nslot - __popc(deadmask)) : 0u;
+        const unsigned nhits = record_hits ? (unsigned)nh : 0u;
+        // ---- one reservation for the warp's hit rows and event records: packed prefix sums (hits <= 64, events <= 192
+        // per warp and iteration), one 64-bit atomic
+        const unsigned packed = nhits | (ne << 16);
+        if (__ballot_sync(kFull, packed != 0u)) {
+            unsigned incl = packed;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned yv = __shfl_up_sync(kFull, incl, o);
+                if (lane >= (unsigned)o) incl += yv;
+            }
+            const unsigned total = __shfl_sync(kFull, incl, 31);
+            unsigned long long base = 0;
+            if (lane == 31) base = atomicAdd(hits_events, (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 32));
+            base = __shfl_sync(kFull, base, 31);
+            const unsigned excl = incl - packed;
+            unsigned hslot = (unsigned)(base & 0xffffffffull) + (excl & 0xffffu);
+            unsigned eslot = (unsigned)(base >> 32) + (excl >> 16);
+            // hits: rows in file layout
+            if (nhits > 0) {
+                const int panel_id = s_panels[pa].id;
+                for (unsigned k = 0; k < nhits; k++) {
+                    if (hslot + k < hits.capacity) {
+                        int* hi = hits.id + 5ull * (hslot + k);
+                        float* hf = hits.f + 5ull * (hslot + k);
+                        hi[0] = parn; hi[1] = panel_id; hi[2] = h_key >> 16; hi[3] = h_key & 0xffff; hi[4] = k ? 2 : h_type0;
+                        hf[0] = k ? h_E1 : h_E0; hf[1] = (float)t; hf[2] = x; hf[3] = y; hf[4] = z;
+                        hits.t[hslot + k] = t;
                     }
                 }
             }
-        }
-        // ---- photon finished: readout (gPET_kernals.cu:756-813) and event append
-        if (finished) active = false;
-        const bool mine = finished && nslot > 0;
-        const unsigned fmask = __ballot_sync(kFull, mine);
-        if (fmask) {
-            unsigned deadmask = 0;
-            if (mine && nslot > 1 && rdepth != 3) deadmask = readout_merge(sl, nslot, depth, rpolicy);
-            const int cnt = mine ? nslot - __popc(deadmask) : 0;
-            unsigned slot = warp_reserve(ev.count, (unsigned)cnt);
+            // events of the finished photons
             if (mine) {
                 const int panel_id = s_panels[pa].id;
+#pragma unroll 1
                 for (int k = 0; k < nslot; k++) {
                     if (deadmask >> k & 1u) continue;
-                    if (slot < ev.capacity) {
+                    if (eslot < ev.capacity) {
                         const int key = sl.key[k][tid];
                         EventRec r;
                         r.parn = parn; r.pann = panel_id; r.modn = key >> 16; r.cryn = key & 0xffff;
@@ -822,13 +907,13 @@ __global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, Detect
                         r.eventid = eid;
                         r.t = sl.t[k][tid]; r.E = sl.E[k][tid];
                         r.x = sl.x[k][tid]; r.y = sl.y[k][tid]; r.z = sl.z[k][tid];
-                        store_event_rec(ev.rec + slot, r);
+                        store_event_rec(ev.rec + eslot, r);
                     }
-                    slot++;
+                    eslot++;
                 }
-                nslot = 0;
             }
         }
+        if (mine) nslot = 0;
     }
     // per-warp tallies
     unsigned b = n_drop_adder;
@@ -964,40 +1049,41 @@ int launch_panel_entry(PhotonQueue q1, PhotonQueue q2, DetectorDev det, unsigned
 }
 
 int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQueue q0, PhotonQueue q1, PhotonQueue q2,
-                 PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, unsigned int* counters, uint64_t seed, int num_sms,
-                 cudaStream_t s, bool reset) {
-    const size_t smem_panels = (size_t)det.npanels * sizeof(PanelDev);
+                 PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, unsigned int* counters, unsigned int* hot, uint64_t seed,
+                 int num_sms, cudaStream_t s, bool reset) {
+    const size_t smem = sizeof(FrontStage) + (size_t)det.npanels * sizeof(PanelDev);
     static int grid[2] = {0, 0};
     static size_t grid_smem = 0;
-    if (!grid[0] || grid_smem != smem_panels) {
-        if (smem_panels > 48 * 1024) {
-            cudaFuncSetAttribute(k_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panels);
-            cudaFuncSetAttribute(k_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panels);
+    if (!grid[0] || grid_smem != smem) {
+        if (smem > 48 * 1024) {
+            cudaFuncSetAttribute(k_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
-        grid[0] = persistent_grid(k_front<false>, num_sms, smem_panels);
-        grid[1] = persistent_grid(k_front<true>, num_sms, smem_panels);
-        grid_smem = smem_panels;
+        grid[0] = persistent_grid(k_front<false>, num_sms, smem);
+        grid[1] = persistent_grid(k_front<true>, num_sms, smem);
+        grid_smem = smem;
     }
     const int gen_min = tune("GPET_GEN_MIN", 12), entry_min = tune("GPET_ENTRY_MIN", 12);
+    unsigned* ticket = hot + kHotTicketFront;
     if (reset) {
         cudaMemsetAsync(q1.count, 0, sizeof(unsigned), s);       // photons that left the phantom (tally only: q1 is not filled)
         cudaMemsetAsync(q2.count, 0, sizeof(unsigned), s);
         cudaMemsetAsync(counters + 8, 0, sizeof(unsigned), s);   // photons on a panel
-        cudaMemsetAsync(counters + 11, 0, sizeof(unsigned), s);  // k_front's ticket
+        cudaMemsetAsync(ticket, 0, sizeof(unsigned), s);
     }
     if (frame_dev) {
-        GPET_LAUNCH("k_front", s, k_front<false><<<grid[0], kThreads, smem_panels, s>>>(frame_dev, npairs, q0, ph, tb, det, eabs, seed, q2,
-                                                                                      q1.count, counters, gen_min, entry_min));
+        GPET_LAUNCH("k_front", s, k_front<false><<<grid[0], kThreads, smem, s>>>(frame_dev, npairs, q0, ph, tb, det, eabs, seed, q2,
+                                                                               q1.count, counters, ticket, gen_min, entry_min));
     } else {
-        GPET_LAUNCH("k_front<queue>", s, k_front<true><<<grid[1], kThreads, smem_panels, s>>>(nullptr, 0ull, q0, ph, tb, det, eabs, seed, q2,
-                                                                                            q1.count, counters, gen_min, entry_min));
+        GPET_LAUNCH("k_front<queue>", s, k_front<true><<<grid[1], kThreads, smem, s>>>(nullptr, 0ull, q0, ph, tb, det, eabs, seed, q2,
+                                                                                     q1.count, counters, ticket, gen_min, entry_min));
     }
     return 1;
 }
 
 int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
-                    int record_hits, HitBuffer hits, EventBuf ev, unsigned int* counters, uint64_t seed, int num_sms,
-                    cudaStream_t s, bool reset) {
+                    int record_hits, HitBuffer hits, EventBuf ev, unsigned int* counters, unsigned int* hot, uint64_t seed,
+                    int num_sms, cudaStream_t s, bool reset) {
     const size_t smem = sizeof(SlotsSmem) + (size_t)det.npanels * sizeof(PanelDev);
     static int grid = 0;
     static size_t grid_smem = 0;
@@ -1006,12 +1092,15 @@ int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, i
         grid = persistent_grid(k_detector, num_sms, smem);
         grid_smem = smem;
     }
+    if (ev.count != hits.count + 1 || (reinterpret_cast<uintptr_t>(hits.count) & 7u)) return 0;   // see kernels.hpp
+    unsigned* ticket = hot + kHotTicketDet;
     if (reset) {
-        cudaMemsetAsync(hits.count, 0, 2 * sizeof(unsigned), s);     // hits.count, ev.count (adjacent words of the counter block)
-        cudaMemsetAsync(counters + 9, 0, 2 * sizeof(unsigned), s);   // adder drops, k_detector's ticket
+        cudaMemsetAsync(hits.count, 0, 2 * sizeof(unsigned), s);   // hits.count, ev.count
+        cudaMemsetAsync(counters + 9, 0, sizeof(unsigned), s);     // adder drops
+        cudaMemsetAsync(ticket, 0, sizeof(unsigned), s);
     }
     GPET_LAUNCH("k_detector", s, k_detector<<<grid, kThreads, smem, s>>>(q2, det, tb, eabs, readout_depth, readout_policy, record_hits, hits, ev,
-                                                                       counters, seed, tune("GPET_REFILL_MIN", 4)));
+                                                                       counters, ticket, seed, tune("GPET_REFILL_MIN", 4)));
     return 1;
 }
 

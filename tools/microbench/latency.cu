@@ -22,6 +22,19 @@ __global__ void k_atomic(unsigned* ctr, unsigned* out, int steps) {
     if (v == 0xffffffffu) out[0] = v;
 }
 
+// what the transport kernels do: ONE lane per warp adds to a shared counter and the warp waits for the old value.
+// words = number of distinct counters the warps spread over (stride words apart); 1 = every warp on the same address
+__global__ void __launch_bounds__(256) k_atomic_warp(unsigned* ctr, unsigned* out, int steps, int words, int stride) {
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned v = 0;
+    for (int s = 0; s < steps; s++) {
+        unsigned r = 0;
+        if ((threadIdx.x & 31) == 0) r = atomicAdd(ctr + ((warp + v) % words) * stride, 3u);
+        v += __shfl_sync(~0u, r, 0) & 1u;
+    }
+    if (v == 0xffffffffu) out[0] = v;
+}
+
 template <int MODE> __device__ __forceinline__ unsigned ld(const unsigned* p) {
     if (MODE == 0) return *reinterpret_cast<const volatile unsigned*>(p);
     unsigned v;
@@ -142,7 +155,15 @@ int main() {
     }
     {
         unsigned *c, *o;
-        CK(cudaMalloc(&c, 4096 * 4)); CK(cudaMalloc(&o, 4));
+        CK(cudaMalloc(&c, 32 * 1024 * 4 + 4096)); CK(cudaMalloc(&o, 4));
+        for (int words : {1, 2, 4, 32})
+            for (int stride : {1, 32, 1024}) {
+                if (words == 1 && stride > 1) continue;
+                const int steps = 40;
+                float us = time_us([&] { k_atomic_warp<<<592, 256>>>(c, o, steps, words, stride); }, 20);
+                printf("warp-aggregated atomicAdd with return: 4736 warps x %d dependent, %2d counters %4d words apart: %8.2f us = %.2f ns per atomic\n",
+                       steps, words, stride, us, us * 1e3 / (4736.0 * steps));
+            }
         for (int steps : {1, 9, 33}) printf("atomicAdd with return, %2d dependent, 148x256 threads on 32 words: %.2f us\n", steps, time_us([&] { k_atomic<<<148, 256>>>(c, o, steps); }, 50));
     }
     for (unsigned n : {131072u, 702464u, 2097152u}) {

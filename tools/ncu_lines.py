@@ -29,15 +29,19 @@ def sass_rows(rep, kernel):
     return out
 
 
-def line_table(kernel, cubin_sub):
+def line_table(kernel, cubin_sub, nsass):
     with tempfile.TemporaryDirectory() as td:
         subprocess.run(["cuobjdump", "-xelf", "all", str(ROOT / "gpet_b200" / "libgpet_b200.so")], cwd=td, capture_output=True)
         cub = [p for p in Path(td).glob("*.cubin") if cub_match(p.name, cubin_sub)][0]
         txt = subprocess.run(["nvdisasm", "-g", "-c", str(cub)], capture_output=True, text=True).stdout
-    lines, cur, infn = [], None, False
+    # one line list per function whose name contains `kernel` (template instances are separate functions)
+    fns, lines, cur, infn = [], None, None, False
     for ln in txt.splitlines():
         if ln.startswith(".text."):
             infn = kernel in ln
+            if infn:
+                lines = []
+                fns.append(lines)
             continue
         if not infn:
             continue
@@ -48,7 +52,9 @@ def line_table(kernel, cubin_sub):
             continue
         if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
             lines.append(cur)
-    return lines
+    if not fns:
+        raise SystemExit(f"no function matching {kernel} in the cubin")
+    return min(fns, key=lambda f: abs(len(f) - nsass))
 
 
 def cub_match(name, sub):
@@ -60,7 +66,7 @@ def main():
     cubin_sub = sys.argv[3] if len(sys.argv) > 3 else "transport"
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 45
     sass = sass_rows(rep, kernel)
-    lt = line_table(kernel, cubin_sub)
+    lt = line_table(kernel, cubin_sub, len(sass))
     if len(lt) != len(sass):
         print(f"# warning: {len(sass)} SASS rows in the report vs {len(lt)} in the cubin (rebuilt since the capture?)")
     n = min(len(lt), len(sass))
