@@ -1,7 +1,7 @@
 # Builds libgpet_b200.so (sm_100a only) and the gPET-compatible CLI.  `python -c "import __graft_entry__ as g; g.build()"` calls this.
 NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O2,-ffp-contract=off -Xptxas -v
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O2,-ffp-contract=off -Xptxas -v $(EXTRA)
 CSRC := gpet_b200/csrc
 OBJ := build/abi.o build/digitizer.o build/transport.o build/host_io.o build/planner.o
 LIB := gpet_b200/libgpet_b200.so

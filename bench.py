@@ -124,6 +124,28 @@ class ClockSampler:
                 "power_w_max": max(self.power) if self.power else None}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU (one process per GPU: the pinned result
+    arenas are then first-touched on that NUMA node and the D2H copies do not cross the socket interconnect)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = gpu_index
+        if vis and all(x.strip().isdigit() for x in vis.split(",")):
+            idx = int(vis.split(",")[gpu_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def cpu_baseline(ex, source=DEFAULT_SOURCE, npairs=6_000_000, chunk=1_000_000, seed=12345):
     """Oracle port on one host core over a bounded sample of the same workload: `npairs` pairs of the workload's source
     distribution through source -> phantom -> detector -> digitizer, in chunks of `chunk` pairs (one digitizer pass each)."""
@@ -241,6 +263,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)   # before any pinned allocation: result arenas land on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)

@@ -24,6 +24,7 @@
 // Launches per frame: [k_range], k_prep, k_bucket_scan, k_bucket_scatter, k_bucket_rank, k_lsd_fallback
 // (normally empty), [k_deadtime_chain: non-paralyzable only], k_emit_singles [, k_coinc].
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include "kernels.hpp"
@@ -42,8 +43,6 @@ constexpr int kMaxLogBuckets = 19;
 constexpr unsigned kMaxBuckets = 1u << kMaxLogBuckets;
 constexpr unsigned kBucketLimit = 1024;   // a fuller slice sends the time sort to the LSD fallback
 constexpr int kFlagLsd = 5;               // counters[kFlagLsd] != 0: time sort by LSD radix passes
-constexpr int kGroup = 256;               // slices ranked by one block at a time
-constexpr int kRankCap = 3840;            // events of a slice group that are ranked out of shared memory
 constexpr unsigned kEwinBit = 0x80000000u;  // payload bit: the record is inside the final energy window
 
 __device__ __forceinline__ unsigned long long time_key(double t) {
@@ -366,57 +365,54 @@ __global__ void __launch_bounds__(kThreads) k_bucket_scatter(const unsigned long
     }
 }
 
-// rank of every event inside its slice by (key, event index): the stable time order.  A block takes kGroup
-// consecutive slices at a time, stages their events in shared memory (they are contiguous) and ranks out of it.
+// rank of every event inside its slice by (key, event index): the stable time order.  One thread per event, four
+// independent events per thread and round with their loads issued together; the events of a slice are contiguous and a
+// few cache lines at most, so the walk over the slice runs out of L1 (the warp that ranks them has just loaded them).
+// No shared memory and no barrier: at frame sizes this kernel is a latency chain (load, slice bounds, walk, store), and a
+// block that staged 256 slices at a time spent 19 us on six dependent rounds whatever the frame size.
 __global__ void __launch_bounds__(kThreads) k_bucket_rank(const unsigned long long* __restrict__ bkeys,
                                                           const uint2* __restrict__ bpay, const unsigned* __restrict__ bstart,
                                                           const unsigned* __restrict__ counters, TimeRange range,
                                                           unsigned long long* __restrict__ tsort, unsigned* __restrict__ order_t,
                                                           int* __restrict__ site_t) {
-    __shared__ unsigned long long sm_key[kRankCap];
-    __shared__ unsigned sm_idx[kRankCap];
-    __shared__ unsigned sm_start[kGroup + 1];
     if (counters[kFlagLsd]) return;
     const unsigned n1 = counters[1];
     const BucketMap m = bucket_map(range, counters[0]);
-    const unsigned ngroups = (m.nb + kGroup - 1) / kGroup;
-    for (unsigned g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        const unsigned b0 = g * kGroup;
-        for (unsigned k = threadIdx.x; k <= (unsigned)kGroup; k += kThreads) sm_start[k] = (b0 + k < m.nb) ? bstart[b0 + k] : n1;
-        __syncthreads();
-        const unsigned base = sm_start[0], cnt = sm_start[kGroup] - base;
-        const bool staged = cnt <= (unsigned)kRankCap;
-        if (staged) {
-            for (unsigned e = threadIdx.x; e < cnt; e += kThreads) {
-                sm_key[e] = bkeys[base + e];
-                sm_idx[e] = bpay[base + e].x & ~kEwinBit;
-            }
-            __syncthreads();
+    const unsigned nth = gridDim.x * blockDim.x;
+    for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < n1; e0 += 4 * nth) {
+        unsigned long long key[4];
+        uint2 pay[4];
+        unsigned s[4], en[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned e = e0 + u * nth;
+            if (e < n1) { key[u] = bkeys[e]; pay[u] = bpay[e]; }
         }
-        for (unsigned e = threadIdx.x; e < cnt; e += kThreads) {
-            const uint2 pay = bpay[base + e];
-            const unsigned long long key = staged ? sm_key[e] : bkeys[base + e];
-            const unsigned idx = pay.x & ~kEwinBit;
-            const unsigned b = bucket_of(m, key) - b0;
-            const unsigned s = sm_start[b] - base, en = sm_start[b + 1] - base;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned e = e0 + u * nth;
+            if (e < n1) {
+                const unsigned b = bucket_of(m, key[u]);
+                s[u] = __ldg(&bstart[b]);
+                en[u] = b + 1 < m.nb ? __ldg(&bstart[b + 1]) : n1;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned e = e0 + u * nth;
+            if (e >= n1) continue;
+            const unsigned idx = pay[u].x & ~kEwinBit;
             unsigned rank = 0;
-            if (staged) {
-                for (unsigned q = s; q < en; q++) {
-                    const unsigned long long kq = sm_key[q];
-                    rank += (kq < key || (kq == key && sm_idx[q] < idx)) ? 1u : 0u;
-                }
-            } else {
-                for (unsigned q = s; q < en; q++) {
-                    const unsigned long long kq = bkeys[base + q];
-                    rank += (kq < key || (kq == key && (bpay[base + q].x & ~kEwinBit) < idx)) ? 1u : 0u;
-                }
+            for (unsigned q = s[u]; q < en[u]; q++) {
+                const unsigned long long kq = bkeys[q];
+                if (kq < key[u]) rank++;
+                else if (kq == key[u] && q != e && (bpay[q].x & ~kEwinBit) < idx) rank++;
             }
-            const unsigned pos = base + s + rank;
-            tsort[pos] = key;
-            order_t[pos] = pay.x;
-            site_t[pos] = (int)pay.y;
+            const unsigned pos = s[u] + rank;
+            tsort[pos] = key[u];
+            order_t[pos] = pay[u].x;
+            site_t[pos] = (int)pay[u].y;
         }
-        __syncthreads();
     }
 }
 
@@ -539,11 +535,19 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, Digitize
     if (spec_smem)
         for (int b = threadIdx.x; b < nbins; b += blockDim.x) s_spec[b] = 0;
     unsigned c2 = 0;
+#ifdef GPET_PHASE_TRACE
+    long long ph[8]; int nph = 0;
+#define PH() do { if (nph < 8) ph[nph++] = clock64(); } while (0)
+    PH();
+#else
+#define PH() do {} while (0)
+#endif
     while (true) {
         if (threadIdx.x == 0) s_tile = atomicAdd(&counters[6], 1u);
         __syncthreads();
         const unsigned tile = s_tile;
         if (tile >= ntiles) break;
+        PH();
         const unsigned jt = tile * kScanTile;                 // first position of the tile
         const unsigned j0 = jt + threadIdx.x * 8;
         // this thread's 8 consecutive payloads (scan layout); issued first, used after the flags are known
@@ -551,14 +555,29 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, Digitize
 #pragma unroll
         for (int k = 0; k < 8; k++) pv[k] = (j0 + k < n1) ? order_t[j0 + k] : 0u;
         // stage [jt - kHalo, jt + kScanTile)
-        for (int e = threadIdx.x; e < kHalo + kScanTile; e += kThreads) {
-            const long long j = (long long)jt - kHalo + e;
-            if (j >= 0 && j < (long long)n1) {
-                s_t[e] = key_time(tsort[j]);
-                s_site[e] = site_t[j];
+        {   // all loads first, then the shared-memory stores: one round trip instead of one per round of the loop
+            constexpr int kRounds = (kHalo + kScanTile + kThreads - 1) / kThreads;
+            unsigned long long kv[kRounds];
+            int sv[kRounds];
+#pragma unroll
+            for (int r = 0; r < kRounds; r++) {
+                const int e = r * kThreads + threadIdx.x;
+                const long long j = (long long)jt - kHalo + e;
+                const bool ok = e < kHalo + kScanTile && j >= 0 && j < (long long)n1;
+                kv[r] = ok ? tsort[j] : 0ull;
+                sv[r] = ok ? site_t[j] : 0;
+            }
+#pragma unroll
+            for (int r = 0; r < kRounds; r++) {
+                const int e = r * kThreads + threadIdx.x;
+                if (e < kHalo + kScanTile) {
+                    s_t[e] = key_time(kv[r]);
+                    s_site[e] = sv[r];
+                }
             }
         }
         __syncthreads();
+        PH();
         // flags, one element per thread and round (conflict-free shared-memory walks)
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -588,6 +607,7 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, Digitize
             s_flag[k * kThreads + threadIdx.x] = f;
         }
         __syncthreads();
+        PH();
         unsigned flag[8];
         {
             const uint2 f8 = reinterpret_cast<const uint2*>(s_flag)[threadIdx.x];
@@ -598,6 +618,7 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, Digitize
             }
         }
         TileScan sc = tile_exclusive_scan(flag, tile, status);
+        PH();
         if (tile == ntiles - 1 && threadIdx.x == 0) counters[3] = sc.tile_excl + sc.tile_total;
 #pragma unroll
         for (int k = 0; k < 8; k++)
@@ -639,7 +660,13 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, Digitize
             }
         }
         __syncthreads();   // shared arrays are reused by the next tile
+        PH();
     }
+#ifdef GPET_PHASE_TRACE
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 170 || blockIdx.x == 340) && nph >= 6)
+        printf("emit block %d: ticket %lld stage %lld flags %lld scan %lld gather %lld cycles\n", blockIdx.x, ph[1] - ph[0], ph[2] - ph[1],
+               ph[3] - ph[2], ph[4] - ph[3], ph[5] - ph[4]);
+#endif
     if (spec_smem) {
         __syncthreads();
         for (int b = threadIdx.x; b < nbins; b += blockDim.x)
@@ -714,9 +741,24 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
         v.gt = stime; v.gp = span; v.st = s_t; v.sp = s_p;
         v.lo = at >= (unsigned)kHalo ? at - kHalo : 0u;
         v.hi = min(at + kScanTile + kHalo, n);
-        for (unsigned i = v.lo + threadIdx.x; i < v.hi; i += kThreads) {
-            s_t[i - v.lo] = stime[i];
-            s_p[i - v.lo] = span[i];
+        {   // all loads first, then the shared-memory stores
+            constexpr int kRounds = (kScanTile + 2 * kHalo + kThreads - 1) / kThreads;
+            double tv[kRounds];
+            int pv[kRounds];
+#pragma unroll
+            for (int r = 0; r < kRounds; r++) {
+                const unsigned i = v.lo + r * kThreads + threadIdx.x;
+                tv[r] = i < v.hi ? stime[i] : 0.0;
+                pv[r] = i < v.hi ? span[i] : 0;
+            }
+#pragma unroll
+            for (int r = 0; r < kRounds; r++) {
+                const unsigned i = v.lo + r * kThreads + threadIdx.x;
+                if (i < v.hi) {
+                    s_t[i - v.lo] = tv[r];
+                    s_p[i - v.lo] = pv[r];
+                }
+            }
         }
         __syncthreads();
 #pragma unroll

@@ -756,6 +756,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, Detect
     const int depth = (rdepth != 3 && rpolicy == 1) ? 2 : rdepth;
     bool active = false, exhausted = false;
     unsigned chunk_pos = 0, chunk_end = 0;   // the warp's claimed share of the queue (warp-uniform)
+    unsigned seen = 0;                       // ticket value after this warp's last claim
+    const unsigned nwarps = gridDim.x * (kThreads / 32);
     float x = 0, y = 0, z = 0, E = 0, vx = 0, vy = 0, vz = 0;
     double t = 0;
     int eid = 0, parn = 0, pa = 0, nslot = 0;
@@ -766,11 +768,17 @@ __global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, Detect
         unsigned amask = __ballot_sync(kFull, active);
         if (!exhausted && (__popc(~amask) >= refill_min || amask == 0)) {
             if (chunk_pos == chunk_end) {
+                // guided self-scheduling: full chunks while the queue is long, smaller ones as it drains (remaining /
+                // 2 x warps, from the ticket value this warp saw last), so that the warps run dry together instead of
+                // one of them starting 32 fresh histories when the others are done
+                const unsigned left = n > seen ? n - seen : 0u;
+                const unsigned want = max(2u, min(kDetChunk, left / (2u * nwarps)));
                 unsigned base = 0;
-                if (lane == 0) base = atomicAdd(ticket, kDetChunk);
+                if (lane == 0) base = atomicAdd(ticket, want);
                 base = __shfl_sync(kFull, base, 0);
+                seen = base + want;
                 chunk_pos = min(base, n);
-                chunk_end = min(base + kDetChunk, n);
+                chunk_end = min(base + want, n);
                 if (base >= n) exhausted = true;
             }
             const unsigned need = ~amask;
