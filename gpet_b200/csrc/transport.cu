@@ -107,6 +107,13 @@ __device__ __forceinline__ unsigned warp_reserve(unsigned* counter, unsigned min
 }
 
 // ------------------------------------------------------------------------------------------- S2/S3: source sampling
+// Angles that only place a point or a direction uniformly use the SFU sine / cosine (absolute error 4e-7 on [0, 2 pi],
+// i.e. 2e-7 cm on a 0.5 cm source radius): two instructions instead of the ~150 of a full-precision sincosf, in a kernel
+// that is bound by instruction issue.  The reference calls cosf / sinf here (gPET_kernals.cu:465-477, 536-540); the
+// oracle keeps libm, and the parity test of this stage holds both to 2e-5.  NOT used where a result is close to +-1 and
+// its distance from 1 matters (cosf(delta) of the acollinearity, rotate_dir keeps the reference's own intrinsics).
+__device__ __forceinline__ void fast_sincos(float a, float& sn, float& cs) { sn = __sinf(a); cs = __cosf(a); }
+
 __device__ __forceinline__ void sample_shape(int shape, const float* __restrict__ c, uint4 r, float& x, float& y, float& z) {
     float u0 = u01(r.x), u1 = u01(r.y), u2 = u01(r.z);
     if (shape < 0 || shape > 2) shape = 0;
@@ -115,18 +122,20 @@ __device__ __forceinline__ void sample_shape(int shape, const float* __restrict_
         y = c[1] + c[4] * (-1.f + 2.f * u1) * 0.5f;
         z = c[2] + c[5] * (-1.f + 2.f * u2) * 0.5f;
     } else if (shape == 1) {  // cylinder along z: radius c3, height c4
-        float phi = kTwoPi * u0;
+        float sn, cs;
+        fast_sincos(kTwoPi * u0, sn, cs);
         float rr = c[3] * sqrtf(u1);
-        x = c[0] + rr * cosf(phi);
-        y = c[1] + rr * sinf(phi);
+        x = c[0] + rr * cs;
+        y = c[1] + rr * sn;
         z = c[2] + c[4] * (-1.f + 2.f * u2) * 0.5f;
     } else {  // sphere radius c3
-        float phi = kTwoPi * u0;
+        float sn, cs;
+        fast_sincos(kTwoPi * u0, sn, cs);
         float ct = -1.f + 2.f * u1;
         float rr = c[3] * cbrtf(u2);
         float st = sqrtf(1.f - ct * ct);
-        x = c[0] + rr * st * cosf(phi);
-        y = c[1] + rr * st * sinf(phi);
+        x = c[0] + rr * st * cs;
+        y = c[1] + rr * st * sn;
         z = c[2] + rr * ct;
     }
 }
@@ -239,11 +248,13 @@ __device__ __forceinline__ void source_pair(const SourceDev* __restrict__ fr, co
     float ct = -1.f + 2.f * u01(r0.z);
     float phi = kTwoPi * u01(r0.w);
     float st = sqrtf(1.f - ct * ct);
-    float vx = st * cosf(phi), vy = st * sinf(phi), vz = ct;
+    float sphi, cphi;
+    fast_sincos(phi, sphi, cphi);
+    float vx = st * cphi, vy = st * sphi, vz = ct;
     // acollinearity: delta = N(0,1) * sigma (gPET_kernals.cu:549-555)
     uint4 r2 = rng.next();
     float phi2 = kTwoPi * u01(r2.x);
-    float g = sqrtf(-2.f * logf(u01(r2.y))) * cosf(kTwoPi * u01(r2.z));
+    float g = sqrtf(-2.f * __logf(u01(r2.y))) * __cosf(kTwoPi * u01(r2.z));
     float delta = g * fr->nonangle;
     if (fr->use_prange) {
         // S4 + S5: positron kinetic energy, then its range (gPET_kernals.cu:529-533); direction is sampled (usedirection 0)

@@ -158,8 +158,14 @@ def test_source_sampling_matches_oracle():
                       tau, frac, fr["t0_s"], fr["first_pair"], 0.0037056, int(fr["pairs"].sum()), s.seed)
     assert got.size == want.size == 2 * int(fr["pairs"].sum())
     assert np.array_equal(got["parn"], want["parn"]) and np.array_equal(got["eventid"], want["eventid"])
+    # the GPU places uniform angles with the SFU sine / cosine (4e-7 absolute): positions and the first photon's direction
+    # agree to 2e-5 everywhere.  The partner's direction goes through rotate(-cosf(delta)), and for |delta| < ~5e-4 rad
+    # fp32 cosf(delta) is within an ulp or two of 1: a last-bit change of delta then moves sin(theta) by ~1e-4 (in the
+    # reference as well), so a handful of partners per million may differ by a few 1e-4 -- far below the 3.7e-3 rad sigma
     for f_ in ("x", "y", "z", "vx", "vy", "vz"):
-        assert np.allclose(got[f_], want[f_], atol=2e-5), f_
+        d = np.abs(got[f_].astype(np.float64) - want[f_])
+        assert d[0::2].max() < 2e-5, f_
+        assert (d[1::2] > 2e-5).mean() < 1e-4 and d[1::2].max() < 1e-3, f_
     assert np.allclose(got["E"], want["E"], rtol=1e-6)
     assert np.allclose(got["t"], want["t"], rtol=1e-12, atol=1e-6)
     # physics: times inside the frame, pairs back to back within the acollinearity
@@ -564,8 +570,9 @@ def test_source_with_positron_range_matches_oracle():
     assert got.size == want.size > 20000
     d = np.sqrt((got["x"] - want["x"]) ** 2 + (got["y"] - want["y"]) ** 2 + (got["z"] - want["z"]) ** 2)
     assert (d < 2e-4).mean() > 0.995           # a few walks cross a voxel face differently (powf/logf last bits)
-    for f_ in ("vx", "vy", "vz"):
-        assert np.allclose(got[f_], want[f_], atol=2e-5)
+    for f_ in ("vx", "vy", "vz"):   # partners with |delta| < ~5e-4 rad: see test_source_sampling_matches_oracle
+        dv = np.abs(got[f_].astype(np.float64) - want[f_])
+        assert dv[0::2].max() < 2e-5 and (dv[1::2] > 2e-5).mean() < 1e-4 and dv[1::2].max() < 1e-3
     assert np.allclose(got["t"], want["t"], rtol=1e-12, atol=1e-6)
     # the range really moved the annihilation points: mm scale for O-15 in water, both photons of a pair share the point
     moved = np.sqrt((want["x"] - plain["x"]) ** 2 + (want["y"] - plain["y"]) ** 2 + (want["z"] - plain["z"]) ** 2)
