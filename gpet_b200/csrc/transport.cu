@@ -400,6 +400,10 @@ __global__ void __launch_bounds__(kThreads) k_phantom(PhotonQueue q0, PhotonQueu
 
 // ------------------------------------------------------------------------------------------- X1/X2/D1/D2: detector
 constexpr int kSlots = 6;  // distinct crystals per photon kept by the adder (reference: Event events[4], no bound check)
+// k_detector's block: 3 x 256 threads per SM at 72 registers without spills (132 us per source.txt frame); measured
+// alternatives: 4 x 256 at 64 registers with spills 147 us, 7 x 128 at 72 registers with spills 136 us
+constexpr int kDetThreads = 256;
+constexpr int kDetBlocksPerSm = 3;
 
 __device__ __forceinline__ void crystal_search(const PanelDev& pd, const DetectorDev& det, float px, float py, float pz,
                                                int& m_id, int& M_id, int& L_id) {
@@ -680,9 +684,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_front(const SourceDev* __restri
 // Per-thread adder slots in shared memory, [slot][thread] so that a warp's accesses are conflict free.  A slot is one
 // crystal of the photon's panel: key = (module << 16) | crystal-in-module (a photon never leaves its panel).
 struct SlotsSmem {
-    int key[kSlots][kThreads];
-    float E[kSlots][kThreads], x[kSlots][kThreads], y[kSlots][kThreads], z[kSlots][kThreads];
-    double t[kSlots][kThreads];
+    int key[kSlots][kDetThreads];
+    float E[kSlots][kDetThreads], x[kSlots][kDetThreads], y[kSlots][kDetThreads], z[kSlots][kDetThreads];
+    double t[kSlots][kDetThreads];
 };
 
 // D1 adder (gPET_kernals.cu:737-755): merge hits of the same crystal; energy-weighted centroid with the
@@ -749,7 +753,7 @@ __device__ __forceinline__ unsigned readout_merge(SlotsSmem& sl, int nslot, int 
 
 constexpr unsigned kDetChunk = 32;   // photons a warp claims from the queue with one ticket atomic
 
-__global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs,
+__global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs,
                                                           int rdepth, int rpolicy, int record_hits, HitBuffer hits, EventBuf ev,
                                                           unsigned* __restrict__ counters, unsigned* __restrict__ ticket, uint64_t seed,
                                                           int refill_min) {
@@ -768,7 +772,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_detector(PhotonQueue q2, Detect
     bool active = false, exhausted = false;
     unsigned chunk_pos = 0, chunk_end = 0;   // the warp's claimed share of the queue (warp-uniform)
     unsigned seen = 0;                       // ticket value after this warp's last claim
-    const unsigned nwarps = gridDim.x * (kThreads / 32);
+    const unsigned nwarps = gridDim.x * (kDetThreads / 32);
     float x = 0, y = 0, z = 0, E = 0, vx = 0, vy = 0, vz = 0;
     double t = 0;
     int eid = 0, parn = 0, pa = 0, nslot = 0;
@@ -1013,9 +1017,9 @@ int tune(const char* name, int dflt) {
 }
 
 template <typename K>
-int persistent_grid(K kernel, int num_sms, size_t smem) {
+int persistent_grid(K kernel, int num_sms, size_t smem, int threads = kThreads) {
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
     if (per_sm < 1) per_sm = 1;
     return per_sm * num_sms;
 }
@@ -1108,7 +1112,7 @@ int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, i
     static size_t grid_smem = 0;
     if (!grid || grid_smem != smem) {
         cudaFuncSetAttribute(k_detector, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        grid = persistent_grid(k_detector, num_sms, smem);
+        grid = persistent_grid(k_detector, num_sms, smem, kDetThreads);
         grid_smem = smem;
     }
     if (ev.count != hits.count + 1 || (reinterpret_cast<uintptr_t>(hits.count) & 7u)) return 0;   // see kernels.hpp
@@ -1118,7 +1122,7 @@ int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, i
         cudaMemsetAsync(counters + 9, 0, sizeof(unsigned), s);     // adder drops
         cudaMemsetAsync(ticket, 0, sizeof(unsigned), s);
     }
-    GPET_LAUNCH("k_detector", s, k_detector<<<grid, kThreads, smem, s>>>(q2, det, tb, eabs, readout_depth, readout_policy, record_hits, hits, ev,
+    GPET_LAUNCH("k_detector", s, k_detector<<<grid, kDetThreads, smem, s>>>(q2, det, tb, eabs, readout_depth, readout_policy, record_hits, hits, ev,
                                                                        counters, ticket, seed, tune("GPET_REFILL_MIN", 4)));
     return 1;
 }
