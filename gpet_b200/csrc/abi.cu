@@ -70,7 +70,8 @@ int ensure_buffers(gpet_ctx* c) {
     w.capacity = (unsigned)ce;
     w.max_tiles = scan_tiles(ce);
     {
-        const size_t mt4 = ((size_t)w.max_tiles + 3) & ~(size_t)3, st2 = (size_t)bucket_words() / 2048 + 4;   // 16-byte segments
+        const size_t mt4 = (((size_t)w.max_tiles + 3) & ~(size_t)3) * scan_status_stride();
+        const size_t st2 = ((size_t)bucket_words() / 2048 + 4) * scan_status_stride();
         const size_t words = 64 + 2 * mt4 + st2 + 4 + (size_t)bucket_words() + kHotWords + 32;
         unsigned* p = nullptr;
         if ((r = dev_alloc(c, &p, words))) return r;
@@ -126,8 +127,10 @@ int ensure_buffers(gpet_ctx* c) {
     if ((r = dev_alloc(c, &w.kill, ce))) return r;
     if ((r = dev_alloc(c, &w.coinc_cnt, ce))) return r;
     if (w.spectrum_bins > 0) {
-        if ((r = dev_alloc(c, &w.spectrum, (size_t)w.spectrum_bins))) return r;
-        CK(cudaMemset(w.spectrum, 0, sizeof(unsigned long long) * w.spectrum_bins));
+        w.spectrum_stride = w.spectrum_bins <= 1024 ? 16 : 1;
+        const size_t nw = (size_t)w.spectrum_bins * w.spectrum_stride;
+        if ((r = dev_alloc(c, &w.spectrum, nw))) return r;
+        CK(cudaMemset(w.spectrum, 0, sizeof(unsigned long long) * nw));
     }
     {
         void* p = nullptr;
@@ -1413,7 +1416,8 @@ int gpet_profile_get(gpet_ctx* c, int i, char* name, int name_cap, double* total
 int gpet_get_spectrum(gpet_ctx* c, uint64_t* bins, int nbins) {
     NEED_DEVICE();
     if (!bins || nbins != c->ws.spectrum_bins || !c->ws.spectrum) return fail(c, GPET_ERR_ARG, "spectrum not configured");
-    CK(cudaMemcpyAsync(bins, c->ws.spectrum, sizeof(uint64_t) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpy2DAsync(bins, sizeof(uint64_t), c->ws.spectrum, sizeof(uint64_t) * c->ws.spectrum_stride, sizeof(uint64_t), (size_t)nbins,
+                         cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return GPET_OK;
 }

@@ -61,6 +61,18 @@ __device__ __forceinline__ unsigned warp_sum(unsigned v) {
     return v;
 }
 
+// sum over the block, valid in thread 0 (all threads must call)
+__device__ __forceinline__ unsigned block_sum(unsigned v) {
+    __shared__ unsigned s_part[kThreads / 32];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned t = 0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < kThreads / 32; w++) t += s_part[w];
+    return t;
+}
+
 // Equal slices of the TIME range [lo, hi] (not of the key range: the u64 image of a double is logarithmic in t):
 // slice = clamp((long long)((t - lo) * inv), 0, nb - 1), monotone in t, which is all the sort needs.
 struct BucketMap {
@@ -156,7 +168,7 @@ __global__ void __launch_bounds__(kThreads) k_noise(EventBuf ev, DigitizerDev p,
 // ------------------------------------------------------------------------------------------- stage 1: blur + thresholder + site + slice
 // blur (gPET_kernals.cu:814-837) + energywindow(Eth, 2e6) (gPET.cu:393) + setSitenum (gPET_kernals.cu:607-640) fused.
 // Per record: time key (all ones for a dead one), site number, arrival rank in its time slice | final-window flag.
-__global__ void __launch_bounds__(kThreads) k_prep(EventBuf ev, DigitizerDev p, uint64_t seed, TimeRange range,
+__global__ void __launch_bounds__(kThreads, 4) k_prep(EventBuf ev, DigitizerDev p, uint64_t seed, TimeRange range,
                                                    unsigned long long* __restrict__ keys, int* __restrict__ site_of,
                                                    unsigned* __restrict__ aux, unsigned* __restrict__ bcount,
                                                    unsigned* __restrict__ counters) {
@@ -225,8 +237,8 @@ __global__ void __launch_bounds__(kThreads) k_prep(EventBuf ev, DigitizerDev p, 
             alive_cnt++;
         }
     }
-    alive_cnt = warp_sum(alive_cnt);
-    if ((threadIdx.x & 31) == 0 && alive_cnt) atomicAdd(&counters[1], alive_cnt);
+    alive_cnt = block_sum(alive_cnt);   // one add per block: tallies of a whole grid land on one line and serialise there
+    if (threadIdx.x == 0 && alive_cnt) atomicAdd(&counters[1], alive_cnt);
 }
 
 // ------------------------------------------------------------------------------------------- single-pass exclusive scan
@@ -239,6 +251,11 @@ __global__ void __launch_bounds__(kThreads) k_prep(EventBuf ev, DigitizerDev p, 
 constexpr int kScanTile = 2048;
 constexpr int kSpecSmemBins = 1024;
 constexpr unsigned kPublished = 1u << 31;
+// One status word per 128-byte line: every tile polls the words of all earlier tiles (343 tiles: 59 k loads per round),
+// and accesses to ONE line are served one after the other (0.67 ns each for atomics, tools/microbench/latency.cu) --
+// packed, the polling alone cost 10-15 us per scan (clock64 phase trace); on lines of their own the loads spread over
+// the L2 slices.
+constexpr unsigned kStatusStride = 32;
 
 struct TileScan {
     unsigned excl[8];    // exclusive prefix of each of the thread's 8 elements (global)
@@ -277,12 +294,12 @@ __device__ __forceinline__ TileScan tile_exclusive_scan(const unsigned v[8], uns
         if (w < warp) wprefix += c;
         total += c;
     }
-    if (threadIdx.x == 0) st_relaxed(&status[tile], kPublished | total);
+    if (threadIdx.x == 0) st_relaxed(&status[(size_t)tile * kStatusStride], kPublished | total);
     // totals of all earlier tiles (a word that is not published yet is read again)
     unsigned before = 0;
     for (unsigned i = threadIdx.x; i < tile; i += kThreads) {
         unsigned w;
-        do { w = ld_relaxed(&status[i]); } while (!(w & kPublished));
+        do { w = ld_relaxed(&status[(size_t)i * kStatusStride]); } while (!(w & kPublished));
         before += w & ~kPublished;
     }
 #pragma unroll
@@ -515,13 +532,13 @@ __global__ void __launch_bounds__(kThreads) k_deadtime_chain(DigitizerDev p, con
 // per thread in flight, and leave as consecutive 16-byte stores.
 constexpr int kHalo = 64;
 
-__global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, DigitizerDev p, EventRec* __restrict__ singles,
+__global__ void __launch_bounds__(kThreads, 3) k_emit_singles(EventBuf ev, DigitizerDev p, EventRec* __restrict__ singles,
                                                            unsigned singles_cap, const unsigned long long* __restrict__ tsort,
                                                            const unsigned* __restrict__ order_t, const int* __restrict__ site_t,
                                                            const unsigned char* __restrict__ kill, unsigned* __restrict__ counters,
                                                            unsigned* __restrict__ status, double* __restrict__ stime,
                                                            int* __restrict__ span, unsigned long long* __restrict__ spectrum,
-                                                           int nbins, float emin, float emax) {
+                                                           int nbins, int spec_stride, float emin, float emax) {
     __shared__ unsigned s_tile;
     __shared__ double s_t[kHalo + kScanTile];
     __shared__ int s_site[kHalo + kScanTile];
@@ -654,7 +671,7 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, Digitize
                     const float f = (__int_as_float(v[u].x) - emin) / (emax - emin) * nbins;
                     if (f >= 0.f && f < (float)nbins) {
                         if (spec_smem) atomicAdd(&s_spec[(int)f], 1u);
-                        else atomicAdd(&spectrum[(int)f], 1ull);
+                        else atomicAdd(&spectrum[(size_t)(int)f * spec_stride], 1ull);
                     }
                 }
             }
@@ -670,10 +687,10 @@ __global__ void __launch_bounds__(kThreads) k_emit_singles(EventBuf ev, Digitize
     if (spec_smem) {
         __syncthreads();
         for (int b = threadIdx.x; b < nbins; b += blockDim.x)
-            if (s_spec[b]) atomicAdd(&spectrum[b], (unsigned long long)s_spec[b]);
+            if (s_spec[b]) atomicAdd(&spectrum[(size_t)b * spec_stride], (unsigned long long)s_spec[b]);
     }
-    c2 = warp_sum(c2);
-    if ((threadIdx.x & 31) == 0 && c2) atomicAdd(&counters[2], c2);
+    c2 = block_sum(c2);
+    if (threadIdx.x == 0 && c2) atomicAdd(&counters[2], c2);
 }
 
 // ------------------------------------------------------------------------------------------- stage 5: coincidence sorter (extension)
@@ -731,11 +748,16 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
     const double W = (double)p.cwin;
     const unsigned pair_base = base_in ? *base_in : 0u;
     if (base_out && blockIdx.x == 0 && threadIdx.x == 0) *base_out = pair_base + n;
+#ifdef GPET_PHASE_TRACE
+    long long ph[8]; int nph = 0;
+    PH();
+#endif
     while (true) {
         if (threadIdx.x == 0) s_tile = atomicAdd(&counters[7], 1u);
         __syncthreads();
         const unsigned tile = s_tile;
         if (tile >= ntiles) break;
+        PH();
         const unsigned at = tile * kScanTile;
         SinglesView v;
         v.gt = stime; v.gp = span; v.st = s_t; v.sp = s_p;
@@ -761,6 +783,7 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
             }
         }
         __syncthreads();
+        PH();
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const unsigned a = at + k * kThreads + threadIdx.x;
@@ -768,6 +791,7 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
             s_cnt[k * kThreads + threadIdx.x] = (unsigned short)min(c, 0xffffu);
         }
         __syncthreads();
+        PH();
         const unsigned a0 = at + threadIdx.x * 8;
         unsigned c[8];
         {
@@ -776,6 +800,7 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
             c[4] = c8.z & 0xffffu; c[5] = c8.z >> 16; c[6] = c8.w & 0xffffu; c[7] = c8.w >> 16;
         }
         TileScan sc = tile_exclusive_scan(c, tile, status);
+        PH();
         if (tile == ntiles - 1 && threadIdx.x == 0) counters[4] = sc.tile_excl + sc.tile_total;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -801,7 +826,13 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
             }
         }
         __syncthreads();   // shared arrays are reused by the next tile
+        PH();
     }
+#ifdef GPET_PHASE_TRACE
+    if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 170 || blockIdx.x == 340) && nph >= 6)
+        printf("coinc block %d: ticket %lld stage %lld count %lld scan %lld emit %lld cycles\n", blockIdx.x, ph[1] - ph[0], ph[2] - ph[1],
+               ph[3] - ph[2], ph[4] - ph[3], ph[5] - ph[4]);
+#endif
 }
 
 }  // namespace
@@ -810,6 +841,7 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
 size_t sort_state_bytes() { return sizeof(rsort::SortState); }
 size_t sort_lookback_words(size_t capacity) { return ((capacity + rsort::kTile - 1) / rsort::kTile) * (size_t)rsort::kBins; }
 unsigned scan_tiles(size_t capacity) { return (unsigned)((capacity + kScanTile - 1) / kScanTile); }
+unsigned scan_status_stride() { return kStatusStride; }
 unsigned bucket_words() { return kMaxBuckets; }
 
 TimeRange time_range_us(double t_lo_us, double t_hi_us) {
@@ -832,8 +864,26 @@ int launch_noise(EventBuf ev, const DigitizerDev& p, double t_lo_us, double t_hi
 
 int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p, DigitizerWorkspace& ws, const TimeRange* range,
                     uint64_t seed, int num_sms, cudaStream_t s, bool reset) {
-    static const int grid_mult = [] { const char* v = getenv("GPET_DIGI_GRID"); return v && *v ? atoi(v) : 4; }();
-    const int grid = num_sms * grid_mult;
+    // One wave per kernel: a grid of exactly the resident blocks.  With 592 blocks everywhere, k_emit_singles (104
+    // registers, 2 blocks per SM) ran the last 47 of a frame's 343 tiles in a second wave, 28 + 15 us.  GPET_DIGI_GRID
+    // overrides the blocks per SM for tuning runs.
+    static const int grid_mult = [] { const char* v = getenv("GPET_DIGI_GRID"); return v && *v ? atoi(v) : 0; }();
+    auto resident = [&](const void* kernel, int dflt) {
+        if (grid_mult > 0) return num_sms * grid_mult;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = dflt;
+        return num_sms * per_sm;
+    };
+    static int g_prep = 0, g_scatter = 0, g_rank = 0, g_emit = 0, g_coinc = 0, g_chain = 0;
+    if (!g_prep) {
+        g_prep = resident((const void*)k_prep, 4);
+        g_scatter = resident((const void*)k_bucket_scatter, 4);
+        g_rank = resident((const void*)k_bucket_rank, 4);
+        g_emit = resident((const void*)k_emit_singles, 3);
+        g_coinc = resident((const void*)k_coinc, 4);
+        g_chain = resident((const void*)k_deadtime_chain, 4);
+    }
+    const int grid = num_sms * 4;   // k_range
     int launches = 0;
     EventRec* singles = static_cast<EventRec*>(out.singles);
     unsigned long long* keys = ws.tkeys[0];    // by event index; after the sort: the sorted keys (tsort)
@@ -851,12 +901,12 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
         launches++;
         tr.lo = 0.0; tr.hi = 0.0; tr.dev = ws.minmax;
     }
-    GPET_LAUNCH("k_prep", s, k_prep<<<grid, kThreads, 0, s>>>(ev, p, seed, tr, keys, ws.site_of, ws.aux, ws.bcount, ws.counters));
+    GPET_LAUNCH("k_prep", s, k_prep<<<g_prep, kThreads, 0, s>>>(ev, p, seed, tr, keys, ws.site_of, ws.aux, ws.bcount, ws.counters));
     GPET_LAUNCH("k_bucket_scan", s, k_bucket_scan<<<kMaxBuckets / kScanTile, kThreads, 0, s>>>(ws.bcount, ws.bstart, ws.scan_status[2],
                                                                                            ws.counters, tr));
-    GPET_LAUNCH("k_bucket_scatter", s, k_bucket_scatter<<<grid, kThreads, 0, s>>>(keys, ws.site_of, ws.aux, ws.counters, tr, ws.bstart,
+    GPET_LAUNCH("k_bucket_scatter", s, k_bucket_scatter<<<g_scatter, kThreads, 0, s>>>(keys, ws.site_of, ws.aux, ws.counters, tr, ws.bstart,
                                                                                  bkeys, ws.bpay));
-    GPET_LAUNCH("k_bucket_rank", s, k_bucket_rank<<<grid, kThreads, 0, s>>>(bkeys, ws.bpay, ws.bstart, ws.counters, tr, keys, ws.order_t,
+    GPET_LAUNCH("k_bucket_rank", s, k_bucket_rank<<<g_rank, kThreads, 0, s>>>(bkeys, ws.bpay, ws.bstart, ws.counters, tr, keys, ws.order_t,
                                                                            ws.site_t));
     launches += 4;
     {
@@ -873,15 +923,15 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
         launches++;
     }
     if (p.dtype != 0) {
-        GPET_LAUNCH("k_deadtime_chain", s, k_deadtime_chain<<<grid, kThreads, 0, s>>>(p, keys, ws.site_t, ws.kill, ws.counters));
+        GPET_LAUNCH("k_deadtime_chain", s, k_deadtime_chain<<<g_chain, kThreads, 0, s>>>(p, keys, ws.site_t, ws.kill, ws.counters));
         launches++;
     }
-    GPET_LAUNCH("k_emit_singles", s, k_emit_singles<<<grid, kThreads, 0, s>>>(ev, p, singles, out.singles_cap, keys, ws.order_t, ws.site_t,
+    GPET_LAUNCH("k_emit_singles", s, k_emit_singles<<<g_emit, kThreads, 0, s>>>(ev, p, singles, out.singles_cap, keys, ws.order_t, ws.site_t,
                                                                             ws.kill, ws.counters, ws.scan_status[0], ws.stime, ws.span,
-                                                                            ws.spectrum, ws.spectrum_bins, ws.spec_emin, ws.spec_emax));
+                                                                            ws.spectrum, ws.spectrum_bins, ws.spectrum_stride, ws.spec_emin, ws.spec_emax));
     launches++;
     if (p.cwin > 0.f && (out.coinc || out.pairs)) {
-        GPET_LAUNCH("k_coinc", s, k_coinc<<<grid, kThreads, 0, s>>>(singles, ws.stime, ws.span, p, ws.counters, out.singles_cap, ws.scan_status[1],
+        GPET_LAUNCH("k_coinc", s, k_coinc<<<g_coinc, kThreads, 0, s>>>(singles, ws.stime, ws.span, p, ws.counters, out.singles_cap, ws.scan_status[1],
                                                                   static_cast<gpet_coincidence*>(out.coinc), static_cast<uint2*>(out.pairs),
                                                                   out.coinc_cap, out.pair_base_in, out.pair_base_out));
         launches++;

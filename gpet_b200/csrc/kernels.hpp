@@ -50,7 +50,9 @@ struct DigitizerWorkspace {
     // whatever word they hit (tools/microbench/latency.cu), which bounded k_front and k_detector while tickets and queue
     // counts shared the counter block.  Word offsets below; part of frame_state (zeroed by the frame's memset).
     unsigned int* hot;
-    unsigned long long* spectrum; int spectrum_bins; float spec_emin, spec_emax;
+    // energy spectrum of the singles; bin b lives at spectrum[b * spectrum_stride] (one bin per 128-byte line for small
+    // histograms: every block adds its private histogram at the end, and atomics on one line serialise)
+    unsigned long long* spectrum; int spectrum_bins; int spectrum_stride; float spec_emin, spec_emax;
 };
 
 // Where one frame's results go (device memory).
@@ -75,7 +77,8 @@ enum HotWord : unsigned {
 
 size_t sort_state_bytes();
 size_t sort_lookback_words(size_t capacity);   // status words one radix pass needs for `capacity` keys
-unsigned scan_tiles(size_t capacity);          // status words of the compaction scans
+unsigned scan_tiles(size_t capacity);          // tiles of the compaction scans
+unsigned scan_status_stride();                 // words between the status words of two tiles (one per 128-byte line)
 unsigned bucket_words();                       // slice counters of the bucket sort
 
 // ---- digitizer (digitizer.cu) --------------------------------------------------------------------------

@@ -675,9 +675,18 @@ __global__ void __launch_bounds__(kThreads, 4) k_front(const SourceDev* __restri
         n_out += __shfl_xor_sync(kFull, n_out, o);
         n_on += __shfl_xor_sync(kFull, n_on, o);
     }
+    // one pair of tallies per block (per warp they were 9.5 k adds on one line at the tail of the kernel)
+    __shared__ unsigned s_tally[2];
+    if (threadIdx.x < 2) s_tally[threadIdx.x] = 0;
+    __syncthreads();
     if (lane == 0) {
-        if (n_out) atomicAdd(q1_count, n_out);
-        if (n_on) atomicAdd(&counters[8], n_on);
+        if (n_out) atomicAdd(&s_tally[0], n_out);
+        if (n_on) atomicAdd(&s_tally[1], n_on);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_tally[0]) atomicAdd(q1_count, s_tally[0]);
+        if (s_tally[1]) atomicAdd(&counters[8], s_tally[1]);
     }
 }
 
