@@ -883,7 +883,8 @@ int gpet_stage_digitize(gpet_ctx* c) {
     } else {
         out.coinc = c->coinc_aos;
     }
-    c->stats.kernel_launches += launch_digitize(c->ev, out, d, c->ws, c->have_range ? &c->range : nullptr, c->seed, c->num_sms, c->stream, !c->in_run);
+    c->stats.kernel_launches += launch_digitize(c->ev, out, d, c->ws, c->have_range ? &c->range : nullptr, c->seed, c->num_sms, c->stream, !c->in_run,
+                                                !(c->in_run && c->skip_fallback));
     CK(cudaGetLastError());
     return GPET_OK;
 }
@@ -1107,6 +1108,8 @@ int arena_reserve(gpet_ctx* c, PinnedArena& a, size_t extra) {
     return GPET_OK;
 }
 
+constexpr int kRetryWithFallback = 1;   // internal: run_attempt() asks run_impl() for a second attempt
+
 struct RunState {
     gpet_stats st{};
     bool resident = false;
@@ -1120,6 +1123,7 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
     CK(cudaEventSynchronize(c->ev_counters[slot]));
     patch_counters(c->h_slot_counters[slot]);
     const unsigned* h = c->h_slot_counters[slot];
+    if (c->skip_fallback && h[5]) return kRetryWithFallback;   // a slice of the time sort overflowed and no fallback was enqueued
     gpet_stats& st = rs.st;
     const uint64_t n_ev = h[19], n_hits = h[18], n_q1 = h[17];
     st.frames++;
@@ -1191,7 +1195,22 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
     return GPET_OK;
 }
 
+int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* stats_out);
+
+// Source-mode decay times are spread over the frame, so the bucket sort of the time keys never overflows a slice there
+// and the idle launch of its LSD fallback is skipped; should a frame raise the overflow flag after all (counter-based
+// RNG: every frame can be regenerated), the whole run is repeated with the fallback enqueued.  PSF mode and file dumps
+// keep the fallback (arbitrary input times; files are appended frame by frame).
 int run_impl(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* stats_out) {
+    const bool speculate = c->usepsf == 0 && !(output_dir && *output_dir);
+    c->skip_fallback = speculate;
+    int r = run_attempt(c, output_dir, resident, stats_out);
+    c->skip_fallback = false;
+    if (r == kRetryWithFallback) r = run_attempt(c, output_dir, resident, stats_out);
+    return r;
+}
+
+int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* stats_out) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     const bool psf_mode = c->usepsf != 0;

@@ -67,6 +67,7 @@ struct gpet_ctx {
     int psf_output = 0;                                  // OUTPUTPSF of the reference (gpet_set_psf_output)
     int coinc_format = 0;                                // GPET_COINC_RECORDS / GPET_COINC_PAIRS (gpet_run only)
     bool in_run = false;
+    bool skip_fallback = false;                          // gpet_run's first attempt: time sort without the LSD fallback kernel
     int64_t run_frame = 0;                               // owned frames launched so far in this run
     bool have_range = false;                             // the time slice of the frame being digitized is known
     gpet::TimeRange range{};

@@ -538,13 +538,16 @@ __global__ void __launch_bounds__(kThreads, 3) k_emit_singles(EventBuf ev, Digit
                                                            const unsigned char* __restrict__ kill, unsigned* __restrict__ counters,
                                                            unsigned* __restrict__ status, double* __restrict__ stime,
                                                            int* __restrict__ span, unsigned long long* __restrict__ spectrum,
-                                                           int nbins, int spec_stride, float emin, float emax) {
+                                                           int nbins, int spec_stride, float emin, float emax, int fallback_skipped) {
     __shared__ unsigned s_tile;
     __shared__ double s_t[kHalo + kScanTile];
     __shared__ int s_site[kHalo + kScanTile];
     __shared__ unsigned s_idx[kScanTile];
     __shared__ __align__(16) unsigned char s_flag[kScanTile];
     __shared__ unsigned s_spec[kSpecSmemBins];   // block-private energy histogram (flushed once per block)
+    // the caller did not enqueue the LSD fallback and a slice overflowed: there is no time order; leave no singles (the
+    // host sees counters[kFlagLsd] and runs again with the fallback)
+    if (fallback_skipped && counters[kFlagLsd]) return;
     const unsigned n1 = counters[1];
     const unsigned ntiles = (n1 + kScanTile - 1) / kScanTile;
     const bool spec_smem = spectrum && nbins > 0 && nbins <= kSpecSmemBins;
@@ -863,7 +866,7 @@ int launch_noise(EventBuf ev, const DigitizerDev& p, double t_lo_us, double t_hi
 }
 
 int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p, DigitizerWorkspace& ws, const TimeRange* range,
-                    uint64_t seed, int num_sms, cudaStream_t s, bool reset) {
+                    uint64_t seed, int num_sms, cudaStream_t s, bool reset, bool with_fallback) {
     // One wave per kernel: a grid of exactly the resident blocks.  With 592 blocks everywhere, k_emit_singles (104
     // registers, 2 blocks per SM) ran the last 47 of a frame's 343 tiles in a second wave, 28 + 15 us.  GPET_DIGI_GRID
     // overrides the blocks per SM for tuning runs.
@@ -909,7 +912,7 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
     GPET_LAUNCH("k_bucket_rank", s, k_bucket_rank<<<g_rank, kThreads, 0, s>>>(bkeys, ws.bpay, ws.bstart, ws.counters, tr, keys, ws.order_t,
                                                                            ws.site_t));
     launches += 4;
-    {
+    if (with_fallback) {
         static int coop_grid = 0;
         if (!coop_grid) {
             int per_sm = 1;
@@ -928,7 +931,8 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
     }
     GPET_LAUNCH("k_emit_singles", s, k_emit_singles<<<g_emit, kThreads, 0, s>>>(ev, p, singles, out.singles_cap, keys, ws.order_t, ws.site_t,
                                                                             ws.kill, ws.counters, ws.scan_status[0], ws.stime, ws.span,
-                                                                            ws.spectrum, ws.spectrum_bins, ws.spectrum_stride, ws.spec_emin, ws.spec_emax));
+                                                                            ws.spectrum, ws.spectrum_bins, ws.spectrum_stride, ws.spec_emin, ws.spec_emax,
+                                                                            with_fallback ? 0 : 1));
     launches++;
     if (p.cwin > 0.f && (out.coinc || out.pairs)) {
         GPET_LAUNCH("k_coinc", s, k_coinc<<<g_coinc, kThreads, 0, s>>>(singles, ws.stime, ws.span, p, ws.counters, out.singles_cap, ws.scan_status[1],

@@ -84,8 +84,10 @@ unsigned bucket_words();                       // slice counters of the bucket s
 // ---- digitizer (digitizer.cu) --------------------------------------------------------------------------
 // range == nullptr: the key range is measured on the device first (replay entry)
 // reset: clear the stage's share of the frame state first (false inside gpet_run, where one memset per frame clears all)
+// with_fallback == false: the LSD fallback kernel is not enqueued (6.6 us of idle cooperative launch per frame); if a
+// slice of the bucket sort overflows, counters[5] is raised, no singles are produced and the caller must run again
 int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p, DigitizerWorkspace& ws, const TimeRange* range,
-                    uint64_t seed, int num_sms, cudaStream_t s, bool reset);
+                    uint64_t seed, int num_sms, cudaStream_t s, bool reset, bool with_fallback);
 
 // addnoise: events of the noise process with t_lo <= t < t_hi appended to ev (digitizer.cu)
 int launch_noise(EventBuf ev, const DigitizerDev& p, double t_lo_us, double t_hi_us, uint64_t seed, int num_sms, cudaStream_t s);

@@ -485,6 +485,41 @@ def test_noise_singles_match_oracle_and_enter_the_digitizer(tmp_path):
 
 
 @needs_tables
+def test_run_repeats_with_the_lsd_fallback_when_decay_times_cluster(tmp_path):
+    # gpet_run's first attempt skips the idle launch of the LSD fallback (source-mode times are spread over the frame).
+    # A half-life of 0.1 ms in a 10 s frame puts every decay into the first slices of the bucket sort: the overflow flag
+    # comes back with the frame's counters and the run is repeated with the fallback enqueued.
+    ex = make_example_dir(tmp_path, source="source.txt", window="0 10")
+    (ex / "data" / "isotopes.txt").write_text((parity.EXAMPLE / "data" / "isotopes.txt").read_text().replace("6586.26 0.97", "0.0001 0.97"))
+    (ex / "input" / "source.txt").write_text("1\natoms, isotope row, shape, centre x y z (cm), three shape parameters#\n"
+                                             "150000 0 1 0 0 0 0.3 0.5 0\n")
+    with api.Context(0) as c:
+        c.load_config_file(ex / "input_PET.in", base_dir=ex)
+        c.set_digitizer(coinc_window_us=0.01, blur_Rref=0.0)
+        c.profile(True)
+        st = c.run(None)
+        kt = c.kernel_times()
+        c.profile(False)
+        sg = c.result_singles().copy()
+        st2 = c.run_resident()
+    assert st.frames == 1 and abs(st.pairs - 150000 * 0.97) < 6 * np.sqrt(150000 * 0.03 * 0.97) + 1
+    assert "k_lsd_fallback" in kt and kt["k_bucket_scan"][1] == 2      # two attempts, the second with the fallback
+    assert sg.size == st.singles > 20000 and np.all(np.diff(sg["t"]) >= 0) and sg["t"].max() < 5e3
+    assert st2.singles == st.singles and st2.coincidences == st.coincidences
+    # the same events through the replay entry (which always carries the fallback) give the same singles
+    with api.Context(0) as c:
+        c.load_config_file(ex / "input_PET.in", base_dir=ex)
+        c.set_digitizer(coinc_window_us=0.01, blur_Rref=0.0)
+        c.plan_frames(0)
+        c.stage_front(0); c.stage_panel_transport()
+        ev = c.fetch_events()
+        again, _ = c.digitize(ev)
+    assert again.size == sg.size
+    k = lambda e: np.sort(e, order=["t", "parn", "siten"]).tobytes()
+    assert k(again) == k(sg)
+
+
+@needs_tables
 def test_run_is_reproducible_and_shards_by_frame(tmp_path):
     ex = make_example_dir(tmp_path, source="source.txt", window="0 20")
     def run(rank, world, seed=77):
