@@ -906,8 +906,12 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
             }
             const unsigned total = __shfl_sync(kFull, incl, 31);
             unsigned long long base = 0;
+#ifdef GPET_EXP_NOATOMIC   // timing experiment only: no reservation round trip (output positions are wrong)
+            base = ((unsigned long long)((blockIdx.x * 8u + (threadIdx.x >> 5)) * 200u + (chunk_pos & 127u))) * 0x100000001ull;
+#else
             if (lane == 31) base = atomicAdd(hits_events, (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 32));
             base = __shfl_sync(kFull, base, 31);
+#endif
             const unsigned excl = incl - packed;
             unsigned hslot = (unsigned)(base & 0xffffffffull) + (excl & 0xffffu);
             unsigned eslot = (unsigned)(base >> 32) + (excl >> 16);
