@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -293,6 +294,7 @@ DetectorDev detector_dev(const gpet_ctx* c) {
     d.nsurface = c->tr.nsurface;
     memcpy(d.surface, c->tr.surface, sizeof(float) * 10 * GPET_MAX_SURFACES);
     // the bounding-sphere rejection in panel_entry needs Euclidean local coordinates: orthonormal axes on every panel
+    d.dirmask = (c->in_run && c->dirmask_on) ? c->d_dirmask : nullptr;
     d.prefilter = g.panels.size() <= 32;
     for (const gpet_panel& p : g.panels) {
         const double u[3][3] = {{p.UniXx, p.UniXy, p.UniXz}, {p.UniYx, p.UniYy, p.UniYz}, {p.UniZx, p.UniZy, p.UniZz}};
@@ -517,6 +519,7 @@ int gpet_load_geometry(gpet_ctx* c, const char* geo_file) {
     std::string e = parse_geometry(geo_file, g);
     if (!e.empty()) return fail(c, GPET_ERR_IO, e);
     c->geo = g;
+    c->geo_version++;
     c->have_geo = true;
     rebuild_majorants(c);
     return validate_materials(c);
@@ -1197,6 +1200,81 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
 
 int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* stats_out);
 
+// Direction table of the panel search (DetectorDev::dirmask): for every cell of the direction cube the panels a photon
+// flying in such a direction can possibly enter, given that its line passes within `rref` of `o` -- true inside
+// gpet_run, where a photon's line goes through its birth point (inside a source shape / a PSF record) or through its
+// last interaction (inside the phantom box).  A panel is dropped from a cell only if, for every direction of the cell,
+// (a) the photon moves against the panel's growth direction or (b) the line misses the bounding sphere of the face by
+// a margin -- both with the cell's half diagonal and rounding slack on the safe side.  Off with positron range (the
+// reference's range walk can displace the annihilation point without bound).
+int prepare_dirmask(gpet_ctx* c) {
+    c->dirmask_on = false;
+    const Geometry& g = c->geo;
+    if (!c->have_geo || !c->have_ph || g.panels.empty() || g.panels.size() > 32 || c->tr.use_positron_range) return GPET_OK;
+    if (getenv("GPET_NO_DIRMASK")) return GPET_OK;
+    double o[3], rref = 0.0;
+    for (int k = 0; k < 3; k++) o[k] = (double)c->ph.offset[k] + 0.5 * (double)c->ph.size[k];
+    rref = 0.5 * std::sqrt((double)c->ph.size[0] * c->ph.size[0] + (double)c->ph.size[1] * c->ph.size[1] + (double)c->ph.size[2] * c->ph.size[2]);
+    auto reach = [&](double x, double y, double z, double ext) {
+        const double dx = x - o[0], dy = y - o[1], dz = z - o[2];
+        rref = std::max(rref, std::sqrt(dx * dx + dy * dy + dz * dz) + ext);
+    };
+    if (c->usepsf) {
+        for (const gpet_photon& p : c->psf.p) reach(p.x, p.y, p.z, 0.0);
+    } else {
+        for (int i = 0; i < c->src.n(); i++) {
+            const float* q = c->src.coeff.data() + 6 * i;
+            const int shape = c->src.shape[(size_t)i];
+            double ext;
+            if (shape == 1) ext = std::sqrt((double)q[3] * q[3] + 0.25 * (double)q[4] * q[4]);        // cylinder: radius, height
+            else if (shape == 2) ext = std::fabs((double)q[3]);                                         // sphere
+            else ext = 0.5 * std::sqrt((double)q[3] * q[3] + (double)q[4] * q[4] + (double)q[5] * q[5]);   // box: full lengths
+            reach(q[0], q[1], q[2], ext);
+        }
+    }
+    if (!std::isfinite(rref)) return GPET_OK;
+    rref = rref * 1.001 + 1e-3;
+    const double key[5] = {o[0], o[1], o[2], rref, (double)c->geo_version};
+    bool same = c->d_dirmask != nullptr;
+    for (int k = 0; k < 5; k++) same = same && key[k] == c->dirmask_key[k];
+    if (!same) {
+        const int nb = gpet::kDirBins;
+        const double hd = std::sqrt(3.0) / nb + 2e-5;
+        const unsigned all = g.panels.size() >= 32 ? ~0u : ((1u << g.panels.size()) - 1u);
+        std::vector<unsigned> tab((size_t)nb * nb * nb, all);
+        // a photon whose line misses every face leaves the mask empty; orthonormal axes are checked by detector_dev
+        for (int iz = 0; iz < nb; iz++)
+            for (int iy = 0; iy < nb; iy++)
+                for (int ix = 0; ix < nb; ix++) {
+                    const double cx = -1.0 + (ix + 0.5) * 2.0 / nb, cy = -1.0 + (iy + 0.5) * 2.0 / nb, cz = -1.0 + (iz + 0.5) * 2.0 / nb;
+                    const double cn = std::sqrt(cx * cx + cy * cy + cz * cz);
+                    if (std::fabs(cn - 1.0) > hd + 2e-4) continue;   // no direction of (nearly) unit length falls here
+                    unsigned m = 0;
+                    for (size_t i = 0; i < g.panels.size(); i++) {
+                        const gpet_panel& p = g.panels[i];
+                        const double un = std::sqrt((double)p.UniXx * p.UniXx + (double)p.UniXy * p.UniXy + (double)p.UniXz * p.UniXz);
+                        const double lvx = cx * p.UniXx + cy * p.UniXy + cz * p.UniXz;
+                        const bool dir_ok = p.directionx == 0 ? true : p.directionx > 0 ? lvx >= -(hd * un + 1e-3) : lvx <= hd * un + 1e-3;
+                        const double dx = p.offsetx - o[0], dy = p.offsety - o[1], dz = p.offsetz - o[2];
+                        const double dn = std::sqrt(dx * dx + dy * dy + dz * dz);
+                        const double kx = dy * cz - dz * cy, ky = dz * cx - dx * cz, kz = dx * cy - dy * cx;
+                        const double miss = (std::sqrt(kx * kx + ky * ky + kz * kz) - dn * hd) / 1.0002 - rref;
+                        const double rp = 0.5 * std::sqrt((double)p.lengthy * p.lengthy + (double)p.lengthz * p.lengthz);
+                        const bool near = miss <= 1.006 * rp + 0.01;
+                        if (dir_ok && near) m |= 1u << i;
+                    }
+                    tab[((size_t)iz * nb + iy) * nb + ix] = m;
+                }
+        int r;
+        if (!c->d_dirmask && (r = dev_alloc(c, &c->d_dirmask, tab.size()))) return r;
+        CK(cudaMemcpyAsync(c->d_dirmask, tab.data(), tab.size() * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));   // `tab` is a local
+        for (int k = 0; k < 5; k++) c->dirmask_key[k] = key[k];
+    }
+    c->dirmask_on = true;
+    return GPET_OK;
+}
+
 // Source-mode decay times are spread over the frame, so the bucket sort of the time keys never overflows a slice there
 // and the idle launch of its LSD fallback is skipped; should a frame raise the overflow flag after all (counter-based
 // RNG: every frame can be regenerated), the whole run is repeated with the fallback enqueued.  PSF mode and file dumps
@@ -1219,6 +1297,7 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
         if (nf < 0) return (int)nf;
     }
     if (psf_mode && !c->have_psf) return fail(c, GPET_ERR_ARG, "no PSF loaded");
+    if ((r = prepare_dirmask(c))) return r;
     RunState rs;
     rs.resident = resident;
     rs.od = output_dir ? output_dir : "";

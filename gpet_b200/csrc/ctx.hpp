@@ -79,6 +79,10 @@ struct gpet_ctx {
     void* stage_aos = nullptr;       // cap * 48 B staging for AoS <-> SoA conversion
     size_t stage_bytes = 0;
     gpet::PanelDev* d_panels = nullptr;
+    unsigned* d_dirmask = nullptr;          // direction table of the panel search (gpet_run only), kDirBins^3 words
+    bool dirmask_on = false;                // valid for the run in flight
+    double dirmask_key[5] = {0, 0, 0, -1, -1};   // reference point, reference radius, geometry version it was built for
+    int geo_version = 0;
     uint32_t* d_vox = nullptr;
     float4* d_xs = nullptr;
     float *d_maj_ph = nullptr, *d_maj_det = nullptr, *d_cmpsf = nullptr, *d_rayff = nullptr;

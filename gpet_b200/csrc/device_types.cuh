@@ -96,7 +96,12 @@ struct DetectorDev {
     int nsurface;
     float surface[50];
     int prefilter;             // 1: every panel's local axes are orthonormal, so the bounding-sphere rejection of panel_entry is valid
+    // Direction table (gpet_run only, nullptr otherwise): kDirBins^3 cells over the direction cube [-1,1]^3, one bit per
+    // panel that a photon flying in a direction of that cell can possibly enter, GIVEN that its line passes the
+    // reference sphere the table was built for (phantom box + source shapes / PSF points).  Conservative.
+    const unsigned* dirmask;
 };
+constexpr int kDirBins = 32;
 
 struct PhantomDev {
     const uint32_t* vox;   // packed: fp32 density with the material id in the 4 low mantissa bits

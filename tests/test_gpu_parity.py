@@ -520,6 +520,51 @@ def test_run_repeats_with_the_lsd_fallback_when_decay_times_cluster(tmp_path):
 
 
 @needs_tables
+@pytest.mark.parametrize("case", ["ring8_small_phantom", "ring32_offset_sources", "psf_input"])
+def test_direction_table_of_the_panel_search_changes_nothing(tmp_path, monkeypatch, case):
+    # gpet_run narrows the panel search with a direction table built for the run's phantom, sources and geometry
+    # (conservative by construction); GPET_NO_DIRMASK=1 runs the plain search.  Same singles, byte for byte.
+    import os
+    if case == "ring8_small_phantom":
+        ex = make_example_dir(tmp_path, source="source.txt", window="0 12")
+    elif case == "ring32_offset_sources":
+        # 32 panels at 30 cm, sources far off centre (8 cm) and a big phantom: wide candidate sets
+        ex = make_example_dir(tmp_path, n=40, source="source.txt", window="0 12")
+        (ex / "input" / "config8.geo").write_text(parity.gen_inputs.ring_geo(32, 30.0))
+        text = (ex / "input_PET.in").read_text().replace("-0.5 -0.5 -0.5", "-10 -10 -10").replace("1 1 1\n", "20 20 20\n")
+        (ex / "input_PET.in").write_text(text)
+        mat, den = parity.gen_inputs.water_cylinder_phantom(40, 0.5, 16.0, 16.0)
+        parity.gen_inputs.write_phantom(mat, den, ex / "input" / "cylinder_phantom_mat.dat", ex / "input" / "cylinder_phantom_den.dat")
+        (ex / "input" / "source.txt").write_text("3\natoms, isotope row, shape, centre x y z (cm), three shape parameters#\n"
+                                                 "4000000 0 1 6 5 -4 1.0 4 0\n3000000 0 2 -7 3 6 1.5 0 0\n3000000 0 0 0 -8 0 2 2 6\n")
+    else:
+        ex = make_example_dir(tmp_path, window="0 12")
+        rng = np.random.default_rng(11)
+        n = 60000
+        v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1)[:, None]
+        pos = rng.uniform(-3, 3, size=(n, 3))
+        refio.write_psf(ex / "input" / "psf.dat", pos[:, 0], pos[:, 1], pos[:, 2], np.arange(1, n + 1, dtype=np.float64), v[:, 0], v[:, 1], v[:, 2],
+                        np.full(n, 511000.0))
+    def run(no_table):
+        if no_table:
+            monkeypatch.setenv("GPET_NO_DIRMASK", "1")
+        else:
+            monkeypatch.delenv("GPET_NO_DIRMASK", raising=False)
+        with api.Context(0) as c:
+            c.set_capacity(1 << 18, 1 << 20, 1 << 19)
+            c.load_config_file(ex / "input_PET.in", base_dir=ex)
+            if case == "psf_input":
+                c.load_psf(ex / "input" / "psf.dat", 0, 1)
+            c.set_digitizer(coinc_window_us=0.01)
+            st = c.run(None)
+            return st, c.result_singles().copy()
+    st_a, s_a = run(False)
+    st_b, s_b = run(True)
+    assert st_a.singles == st_b.singles > 5000 and st_a.photons_on_panel == st_b.photons_on_panel and st_a.hits == st_b.hits
+    assert s_a.tobytes() == s_b.tobytes()
+
+
+@needs_tables
 def test_run_is_reproducible_and_shards_by_frame(tmp_path):
     ex = make_example_dir(tmp_path, source="source.txt", window="0 20")
     def run(rank, world, seed=77):
