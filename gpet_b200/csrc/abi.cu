@@ -825,9 +825,12 @@ int gpet_stage_detector(gpet_ctx* c) {
     if ((r = ensure_buffers(c))) return r;
     if ((r = upload_geometry(c))) return r;
     c->stats.kernel_launches += launch_panel_entry(c->q[1], c->q[2], detector_dev(c), c->ws.counters, c->num_sms, c->stream);
-    c->stats.kernel_launches += launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth,
-                                                c->dig.readout_policy, c->tr.record_hits, c->hits, c->ev, c->ws.counters, c->ws.hot,
-                                                c->seed, c->num_sms, c->stream, !c->in_run);
+    {
+        const int nl = launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth, c->dig.readout_policy,
+                                       c->tr.record_hits, c->hits, c->ev, c->ws.counters, c->ws.hot, c->seed, c->num_sms, c->stream, !c->in_run);
+        if (nl < 0) return fail(c, GPET_ERR_ARG, "hit and event counters must be adjacent words (internal layout error)");
+        c->stats.kernel_launches += nl;
+    }
     CK(cudaGetLastError());
     return GPET_OK;
 }
@@ -861,9 +864,12 @@ int gpet_stage_panel_transport(gpet_ctx* c) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((r = upload_geometry(c))) return r;
-    c->stats.kernel_launches += launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth,
-                                                c->dig.readout_policy, c->tr.record_hits, c->hits, c->ev, c->ws.counters, c->ws.hot,
-                                                c->seed, c->num_sms, c->stream, !c->in_run);
+    {
+        const int nl = launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth, c->dig.readout_policy,
+                                       c->tr.record_hits, c->hits, c->ev, c->ws.counters, c->ws.hot, c->seed, c->num_sms, c->stream, !c->in_run);
+        if (nl < 0) return fail(c, GPET_ERR_ARG, "hit and event counters must be adjacent words (internal layout error)");
+        c->stats.kernel_launches += nl;
+    }
     CK(cudaGetLastError());
     return GPET_OK;
 }

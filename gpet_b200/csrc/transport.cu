@@ -1166,7 +1166,7 @@ int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, i
         grid = persistent_grid(k_detector, num_sms, smem, kDetThreads);
         grid_smem = smem;
     }
-    if (ev.count != hits.count + 1 || (reinterpret_cast<uintptr_t>(hits.count) & 7u)) return 0;   // see kernels.hpp
+    if (ev.count != hits.count + 1 || (reinterpret_cast<uintptr_t>(hits.count) & 7u)) return -1;   // see kernels.hpp: caller reports it
     unsigned* ticket = hot + kHotTicketDet;
     if (reset) {
         cudaMemsetAsync(hits.count, 0, 2 * sizeof(unsigned), s);   // hits.count, ev.count

@@ -15,6 +15,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--decays", type=int, default=4_000_000)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--case", default="", help="substring of the case name (config4 | config5)")
     a = ap.parse_args()
     import torch
     import test_configs as tc
@@ -35,6 +36,8 @@ def main():
                                    den="input/phantom_den.dat", source="input/src.txt", geo="input/ring.geo", blur=(1, 662000, 0.05, 0, 0)),
         src=[(natom, 0, 1, 0, 0, 0, 0.5, 18.0, 0)], dig=dict(coinc_min_panel_diff=4))
     for name, cs in cases.items():
+        if a.case and a.case not in name:
+            continue
         with tempfile.TemporaryDirectory() as tmp:
             ex = tc.workdir(Path(tmp), cs["text"], phantom=cs["phantom"], geo_text=cs["geo_text"],
                             extra={"src.txt": gen_inputs.source_file(cs["src"])})
