@@ -565,6 +565,39 @@ def test_direction_table_of_the_panel_search_changes_nothing(tmp_path, monkeypat
 
 
 @needs_tables
+def test_run_edge_cases_empty_acquisition_and_overflow(tmp_path):
+    ex = make_example_dir(tmp_path, source="source.txt", window="0 4")
+    # (1) no atoms: every frame is empty; the run succeeds with empty results
+    (ex / "input" / "source.txt").write_text("1\natoms, isotope row, shape, centre x y z (cm), three shape parameters#\n0 0 1 0 0 0 0.3 0.5 0\n")
+    with api.Context(0) as c:
+        c.load_config_file(ex / "input_PET.in", base_dir=ex)
+        c.set_digitizer(coinc_window_us=0.01)
+        st = c.run(None)
+        assert st.pairs == 0 and st.singles == 0 and st.coincidences == 0 and c.result_singles().size == 0
+        assert c.run_resident().singles == 0
+    # (2) an event buffer far too small for the frame: the run reports GPET_ERR_CAPACITY, it does not drop records silently
+    (ex / "input" / "source.txt").write_text((parity.EXAMPLE / "input" / "source.txt").read_text())
+    with api.Context(0) as c:
+        c.set_capacity(1 << 18, 1 << 12, 1 << 11)      # 2048 events, 4096 hits for ~37 k pairs
+        c.load_config_file(ex / "input_PET.in", base_dir=ex)
+        with pytest.raises(api.GpetError) as e:
+            c.run(None)
+        assert e.value.code == -5
+        # and the context is still usable afterwards with sane capacities? (a new context: capacities are fixed at first use)
+    with api.Context(0) as c:
+        c.load_config_file(ex / "input_PET.in", base_dir=ex)
+        st = c.run(None)
+        assert st.singles > 10000 and st.overflow_events == 0 and st.overflow_hits == 0
+    # (3) a frame larger than the photon queue cannot be planned around: frames are cut to the capacity instead
+    with api.Context(0) as c:
+        c.set_capacity(1 << 12, 1 << 16, 1 << 15)      # 2048 pairs per frame
+        c.load_config_file(ex / "input_PET.in", base_dir=ex)
+        st2 = c.run(None)
+        # (the planner draws the decays per frame: another frame plan is another, statistically equal, acquisition)
+        assert st2.frames > 10 and abs(st2.pairs - st.pairs) < 6 * np.sqrt(st.pairs) and abs(st2.singles - st.singles) < 0.03 * st.singles
+
+
+@needs_tables
 def test_run_is_reproducible_and_shards_by_frame(tmp_path):
     ex = make_example_dir(tmp_path, source="source.txt", window="0 20")
     def run(rank, world, seed=77):
