@@ -597,6 +597,25 @@ def test_run_edge_cases_empty_acquisition_and_overflow(tmp_path):
         assert st2.frames > 10 and abs(st2.pairs - st.pairs) < 6 * np.sqrt(st.pairs) and abs(st2.singles - st.singles) < 0.03 * st.singles
 
 
+def test_c_example_replays_adder_dat_like_the_oracle(tmp_path):
+    # examples/c/digitize_replay.c: adder.dat -> singles.dat through the C ABI from plain C, against the oracle
+    import subprocess
+    exe = tmp_path / "digitize_replay"
+    libdir = parity.ROOT / "gpet_b200"
+    subprocess.run(["gcc", "-std=c99", f"-I{parity.ROOT / 'include'}", str(parity.ROOT / "examples" / "c" / "digitize_replay.c"),
+                    f"-L{libdir}", "-lgpet_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    ev = parity.random_events(30000, np.random.default_rng(4), tmax=2.0e5)
+    ev.tofile(tmp_path / "adder.dat")
+    r = subprocess.run([str(exe), str(parity.EXAMPLE / "input" / "config8.geo"), str(tmp_path / "adder.dat"), str(tmp_path / "singles.dat"), "0"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    p, _ = parity.make_digi_params(ewin_min=350000.0, ewin_max=650000.0)
+    want, counts, _ = orc.digitize(ev, p, want_coinc=False)
+    got = refio.read_events(tmp_path / "singles.dat")
+    assert got.size == want.size > 5000 and got.tobytes() == want.astype(api.EVENT_DTYPE).tobytes()
+    assert f"singles {want.size}" in r.stdout
+
+
 @needs_tables
 def test_run_is_reproducible_and_shards_by_frame(tmp_path):
     ex = make_example_dir(tmp_path, source="source.txt", window="0 20")

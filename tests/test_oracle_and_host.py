@@ -265,6 +265,19 @@ def test_frame_planner_statistics_and_invariance():
         assert [c.frame_pairs(f) for f in range(nf)] != pairs
 
 
+def test_c_example_compiles_as_c99_and_refuses_to_compute_without_a_device(tmp_path):
+    # the header is plain C (no C++/torch types in the signatures): examples/c/digitize_replay.c builds with gcc -std=c99
+    exe = tmp_path / "digitize_replay"
+    libdir = parity.ROOT / "gpet_b200"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{parity.ROOT / 'include'}",
+                    str(parity.ROOT / "examples" / "c" / "digitize_replay.c"), f"-L{libdir}", "-lgpet_b200", f"-Wl,-rpath,{libdir}",
+                    "-o", str(exe)], check=True)
+    parity.random_events(500, np.random.default_rng(3)).tofile(tmp_path / "adder.dat")
+    r = subprocess.run([str(exe), str(parity.EXAMPLE / "input" / "config8.geo"), str(tmp_path / "adder.dat"), str(tmp_path / "singles.dat"), "-1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr and not (tmp_path / "singles.dat").exists()
+
+
 def test_cli_rejects_missing_argument():
     exe = parity.ROOT / "bin" / "gpet_b200"
     if not exe.exists():
