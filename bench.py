@@ -241,6 +241,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--source", default=DEFAULT_SOURCE, help="source file of the example (source.txt | pointsource.txt)")
+    ap.add_argument("--e2e-frame-pairs", type=int, default=700000,
+                    help="frame size (pairs) of the end-to-end runs: two frames, so that the D2H copy of frame 0 overlaps frame 1 "
+                         "(tools/frames_sweep.py); 0 = one frame as in the resident runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
@@ -353,7 +356,7 @@ def main():
             e0.record(stream)
             w0 = time.perf_counter()
             if not resident:
-                ctx.plan_frames(0)              # e2e: planning + descriptor upload are part of the user's call
+                ctx.plan_frames(args.e2e_frame_pairs)   # e2e: planning + descriptor upload are part of the user's call
             st = one_step(ctx, resident, last=_ == nsteps - 1)
             e1.record(stream)
             torch.cuda.synchronize()
@@ -381,6 +384,7 @@ def main():
         # e2e through gpet_run: host results in pinned memory, wall clock around planning + run
         timed(ctx, 2, resident=False)
         e_times, e_stats = timed(ctx, max(3, min(steps, 20)), resident=False)
+        ctx.plan_frames(0)                      # back to the resident plan (per-kernel profile below)
         e_ms = torch.tensor([sum(e_times)], dtype=torch.float64, device=dev)
         e_pairs = torch.tensor([sum(s.pairs for s in e_stats)], dtype=torch.int64, device=dev)
         if world > 1:
@@ -458,13 +462,13 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": m["total_ms"] / nsteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(args.source), "pairs_per_step_per_gpu": m["pairs"] / nsteps / world,
-                           "frames_per_step": nframes, "l2": "flushed between timed steps (256 MiB write)",
+"config": {"workload": workload_name(args.source), "pairs_per_step_per_gpu": m["pairs"] / nsteps / world,
+                           "frames_per_step": int(m["stats"][-1].frames), "e2e_frames_per_step": nframes, "l2": "flushed between timed steps (256 MiB write)",
                            "coincidence_window_us": 0.01, "rng": "Philox4x32-10, key = 0x67504554 + 1000003*rank",
                            "time_path": "fp64", "multi_gpu": "independent decay histories per rank (disjoint Philox keys), tallies all-reduced over NCCL"},
                 "clocks": clocks,
                 "e2e": {"value": m["e2e_pairs"] / (m["e2e_ms"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "timing": "wall clock around gpet_plan_frames + gpet_run (singles as 48-byte records and coincidences as index pairs into them, delivered to pinned host memory), max over ranks"},
+                        "timing": "wall clock around gpet_plan_frames + gpet_run (singles as 48-byte records and coincidences as index pairs into them, delivered to pinned host memory; the acquisition is planned as e2e_frames_per_step frames so that the copy of a frame overlaps the next frame's kernels), max over ranks"},
                 "gpu_launches": int(sum(s.kernel_launches for s in m["stats"])),
                 "roofline": roofline, "cpu_baseline": base,
                 "counters": {"pairs": int(s0.pairs), "hits": int(s0.hits), "events_adder": int(s0.events_adder),

@@ -149,6 +149,7 @@ int ensure_buffers(gpet_ctx* c) {
             CK(cudaMallocHost((void**)&c->h_slot_counters[k], 64 * sizeof(unsigned)));
             CK(cudaEventCreateWithFlags(&c->ev_counters[k], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_emit[k], cudaEventDisableTiming));
         }
         CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         c->out_slot = 0;
@@ -428,6 +429,7 @@ void gpet_destroy(gpet_ctx* c) {
         for (int k = 0; k < 2; k++) {
             if (c->h_slot_counters[k]) cudaFreeHost(c->h_slot_counters[k]);
             if (c->ev_counters[k]) cudaEventDestroy(c->ev_counters[k]);
+            if (c->ev_emit[k]) cudaEventDestroy(c->ev_emit[k]);
             if (c->ev_run[k]) cudaEventDestroy(c->ev_run[k]);
             if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]);
         }
@@ -884,6 +886,10 @@ int gpet_stage_digitize(gpet_ctx* c) {
     out.singles = c->singles_aos;
     out.singles_cap = (unsigned)c->cap_events;
     out.coinc_cap = c->coinc_cap;
+    if (c->in_run && c->early_copy) {
+        out.h_singles_count = c->h_slot_counters[c->out_slot] + 48;   // a spare word of the slot's pinned block
+        out.ev_after_emit = c->ev_emit[c->out_slot];
+    }
     if (c->in_run && c->coinc_format == GPET_COINC_PAIRS) {
         // index pairs into the run's singles list: the base (singles of the earlier frames) travels on the device
         out.pairs = c->pairs_slot[c->out_slot];
@@ -1129,6 +1135,17 @@ struct RunState {
 // Take frame results out of slot `slot`: wait for its counters, account, start the D2H copies of the records.
 int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
     int r;
+    size_t ns_early = 0;
+    char* dst_early = nullptr;
+    if (c->early_copy) {
+        // the singles are final once k_emit_singles is done: their copy starts now and overlaps the coincidence sorter
+        CK(cudaEventSynchronize(c->ev_emit[slot]));
+        ns_early = std::min<size_t>(c->h_slot_counters[slot][48], (size_t)c->cap_events);
+        if ((r = arena_reserve(c, c->res_singles, ns_early * sizeof(gpet_event)))) return r;
+        dst_early = c->res_singles.p + c->res_singles.size;
+        if (ns_early)
+            CK(cudaMemcpyAsync(dst_early, c->singles_slot[slot], ns_early * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->copy_stream));
+    }
     CK(cudaEventSynchronize(c->ev_counters[slot]));
     patch_counters(c->h_slot_counters[slot]);
     const unsigned* h = c->h_slot_counters[slot];
@@ -1157,12 +1174,14 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
     const bool as_pairs = c->coinc_format == GPET_COINC_PAIRS;
     PinnedArena& arena_c = as_pairs ? c->res_pairs : c->res_coinc;
     const size_t rec_c = as_pairs ? 2 * sizeof(uint32_t) : sizeof(gpet_coincidence);
-    if ((r = arena_reserve(c, c->res_singles, ns * sizeof(gpet_event)))) return r;
+    if (!c->early_copy && (r = arena_reserve(c, c->res_singles, ns * sizeof(gpet_event)))) return r;
     if (want_coinc && (r = arena_reserve(c, arena_c, nc * rec_c))) return r;
-    char* dst_s = c->res_singles.p + c->res_singles.size;
+    char* dst_s = c->early_copy ? dst_early : c->res_singles.p + c->res_singles.size;
     char* dst_c = want_coinc ? arena_c.p + arena_c.size : nullptr;
     const size_t first_single = c->res_singles.size / sizeof(gpet_event);
-    if (ns) CK(cudaMemcpyAsync(dst_s, c->singles_slot[slot], ns * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (c->early_copy && ns_early != ns) return fail(c, GPET_ERR_CUDA, "singles count changed after the emit kernel (internal error)");
+    if (ns && !c->early_copy)
+        CK(cudaMemcpyAsync(dst_s, c->singles_slot[slot], ns * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->copy_stream));
     if (want_coinc && nc)
         CK(cudaMemcpyAsync(dst_c, as_pairs ? c->pairs_slot[slot] : c->coinc_slot[slot], nc * rec_c, cudaMemcpyDeviceToHost,
                            c->copy_stream));
@@ -1318,7 +1337,7 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
     struct InRun {   // gpet_stage_digitize reads these while the run is in flight
         gpet_ctx* c;
         explicit InRun(gpet_ctx* c_) : c(c_) { c->in_run = true; c->run_frame = 0; }
-        ~InRun() { c->in_run = false; c->have_range = false; }
+        ~InRun() { c->in_run = false; c->have_range = false; c->early_copy = false; }
     } in_run(c);
     if (!c->ev_run[0]) {
         CK(cudaEventCreate(&c->ev_run[0]));
@@ -1330,6 +1349,7 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
     const int64_t psf_batch = (psf_mode && c->psf.ptype == 0) ? (int64_t)(c->cap_photons / 2) : (int64_t)c->cap_photons;
     const int64_t nframes = psf_mode ? ((int64_t)c->psf.p.size() + psf_batch - 1) / psf_batch : (int64_t)c->frames.size();
     const bool pipelined = rs.od.empty();   // file dumps read the (single-buffered) hit and event buffers frame by frame
+    c->early_copy = pipelined && !resident;
     const int psf_out = rs.od.empty() ? 0 : c->psf_output;
     std::vector<gpet_photon> psf_buf;
     int64_t k = 0;                           // owned frames launched so far
@@ -1391,7 +1411,7 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
         rc = gpet_stage_digitize(c);
         c->have_range = false;
         if (rc) break;
-        if ((rc = fetch_counters_async(c, c->h_slot_counters[slot]))) break;
+        c->stats.kernel_launches += launch_publish_counters(c->ws.counters, c->ws.hot, c->h_slot_counters[slot], c->stream);
         CK(cudaEventRecord(c->ev_counters[slot], c->stream));
         k++;
         if (!pipelined) rc = retire_frame(c, slot, rs);

@@ -73,6 +73,8 @@ struct gpet_ctx {
     gpet::TimeRange range{};
     unsigned* h_slot_counters[2] = {nullptr, nullptr};   // pinned, 32 words each
     cudaEvent_t ev_counters[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_emit[2] = {nullptr, nullptr};         // singles of the slot's frame are final (recorded before the coincidence sorter)
+    bool early_copy = false;                             // this run starts the singles D2H at ev_emit instead of at the frame's end
     cudaEvent_t ev_run[2] = {nullptr, nullptr};          // start / end of the last run (gpet_stats.ms_total)
     cudaStream_t copy_stream = nullptr;
     int out_slot = 0;

@@ -538,7 +538,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_emit_singles(EventBuf ev, Digit
                                                            const unsigned char* __restrict__ kill, unsigned* __restrict__ counters,
                                                            unsigned* __restrict__ status, double* __restrict__ stime,
                                                            int* __restrict__ span, unsigned long long* __restrict__ spectrum,
-                                                           int nbins, int spec_stride, float emin, float emax, int fallback_skipped) {
+                                                           int nbins, int spec_stride, float emin, float emax, int fallback_skipped,
+                                                           unsigned* __restrict__ h_singles_count) {
     __shared__ unsigned s_tile;
     __shared__ double s_t[kHalo + kScanTile];
     __shared__ int s_site[kHalo + kScanTile];
@@ -547,8 +548,12 @@ __global__ void __launch_bounds__(kThreads, 3) k_emit_singles(EventBuf ev, Digit
     __shared__ unsigned s_spec[kSpecSmemBins];   // block-private energy histogram (flushed once per block)
     // the caller did not enqueue the LSD fallback and a slice overflowed: there is no time order; leave no singles (the
     // host sees counters[kFlagLsd] and runs again with the fallback)
-    if (fallback_skipped && counters[kFlagLsd]) return;
+    if (fallback_skipped && counters[kFlagLsd]) {
+        if (h_singles_count && blockIdx.x == 0 && threadIdx.x == 0) *h_singles_count = 0u;
+        return;
+    }
     const unsigned n1 = counters[1];
+    if (h_singles_count && n1 == 0u && blockIdx.x == 0 && threadIdx.x == 0) *h_singles_count = 0u;   // no tile will report
     const unsigned ntiles = (n1 + kScanTile - 1) / kScanTile;
     const bool spec_smem = spectrum && nbins > 0 && nbins <= kSpecSmemBins;
     const float tau = p.dtime;
@@ -639,7 +644,12 @@ __global__ void __launch_bounds__(kThreads, 3) k_emit_singles(EventBuf ev, Digit
         }
         TileScan sc = tile_exclusive_scan(flag, tile, status);
         PH();
-        if (tile == ntiles - 1 && threadIdx.x == 0) counters[3] = sc.tile_excl + sc.tile_total;
+        if (tile == ntiles - 1 && threadIdx.x == 0) {
+            counters[3] = sc.tile_excl + sc.tile_total;
+            // pinned host word (zero-copy store): the host starts the D2H copy of the singles from it without a
+            // memcpy of its own on this stream, which would queue behind the previous frame's copy on the D2H engine
+            if (h_singles_count) *h_singles_count = sc.tile_excl + sc.tile_total;
+        }
 #pragma unroll
         for (int k = 0; k < 8; k++)
             if (flag[k]) s_idx[sc.excl[k] - sc.tile_excl] = pv[k] & ~kEwinBit;
@@ -855,6 +865,20 @@ TimeRange time_range_us(double t_lo_us, double t_hi_us) {
     return r;
 }
 
+// The frame's counters to a pinned host block by zero-copy stores: 32 counter words, then the hot counters two by two
+// (same layout as fetch_counters_async in abi.cu).  A cudaMemcpyAsync on the compute stream would wait for the D2H
+// copy engine, which the previous frame's singles keep busy for hundreds of microseconds.
+__global__ void k_publish_counters(const unsigned* __restrict__ counters, const unsigned* __restrict__ hot, unsigned* __restrict__ h_dst) {
+    const unsigned i = threadIdx.x;
+    if (i < 32) h_dst[i] = counters[i];
+    else if (i < 40) h_dst[i] = hot[((i - 32) >> 1) * kHotStride + ((i - 32) & 1)];
+}
+
+int launch_publish_counters(const unsigned* counters, const unsigned* hot, unsigned* h_dst, cudaStream_t s) {
+    GPET_LAUNCH("k_publish_counters", s, k_publish_counters<<<1, 64, 0, s>>>(counters, hot, h_dst));
+    return 1;
+}
+
 int launch_noise(EventBuf ev, const DigitizerDev& p, double t_lo_us, double t_hi_us, uint64_t seed, int num_sms, cudaStream_t s) {
     if (!(p.noise_gap > 0.f) || !(p.noise_interval > 0.f) || !(t_hi_us > t_lo_us)) return 0;
     const double iv = (double)p.noise_interval;
@@ -932,8 +956,9 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
     GPET_LAUNCH("k_emit_singles", s, k_emit_singles<<<g_emit, kThreads, 0, s>>>(ev, p, singles, out.singles_cap, keys, ws.order_t, ws.site_t,
                                                                             ws.kill, ws.counters, ws.scan_status[0], ws.stime, ws.span,
                                                                             ws.spectrum, ws.spectrum_bins, ws.spectrum_stride, ws.spec_emin, ws.spec_emax,
-                                                                            with_fallback ? 0 : 1));
+                                                                            with_fallback ? 0 : 1, out.ev_after_emit ? out.h_singles_count : nullptr));
     launches++;
+    if (out.ev_after_emit && out.h_singles_count) cudaEventRecord(out.ev_after_emit, s);
     if (p.cwin > 0.f && (out.coinc || out.pairs)) {
         GPET_LAUNCH("k_coinc", s, k_coinc<<<g_coinc, kThreads, 0, s>>>(singles, ws.stime, ws.span, p, ws.counters, out.singles_cap, ws.scan_status[1],
                                                                   static_cast<gpet_coincidence*>(out.coinc), static_cast<uint2*>(out.pairs),

@@ -64,6 +64,10 @@ struct DigitizerOut {
     unsigned int coinc_cap;
     const unsigned int* pair_base_in;   // singles of the run's earlier frames (device word), nullptr = 0
     unsigned int* pair_base_out;        // receives *pair_base_in + this frame's singles, or nullptr
+    // optional: right after k_emit_singles the singles count is copied to this pinned host word and the event is
+    // recorded, so that the host can start the D2H copy of the singles while the coincidence sorter still runs
+    unsigned int* h_singles_count;
+    cudaEvent_t ev_after_emit;
 };
 
 enum HotWord : unsigned {
@@ -89,6 +93,8 @@ unsigned bucket_words();                       // slice counters of the bucket s
 int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p, DigitizerWorkspace& ws, const TimeRange* range,
                     uint64_t seed, int num_sms, cudaStream_t s, bool reset, bool with_fallback);
 
+// the frame's counter block (32 words) and hot counters (4 x 2 words) to pinned host memory by zero-copy stores
+int launch_publish_counters(const unsigned* counters, const unsigned* hot, unsigned* h_dst, cudaStream_t s);
 // addnoise: events of the noise process with t_lo <= t < t_hi appended to ev (digitizer.cu)
 int launch_noise(EventBuf ev, const DigitizerDev& p, double t_lo_us, double t_hi_us, uint64_t seed, int num_sms, cudaStream_t s);
 

@@ -24,7 +24,7 @@ def main():
         c.set_digitizer(coinc_window_us=0.01)
         c.set_coincidence_format(api.Context.COINC_PAIRS)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-        for mp in (0, 600000, 400000, 300000, 150000):
+        for mp in (0, 1200000, 900000, 800000, 700000, 620000, 590000, 560000, 500000, 450000, 400000):
             nf = c.plan_frames(mp)
             res = {}
             for mode in ("resident", "e2e"):
