@@ -292,8 +292,16 @@ DetectorDev detector_dev(const gpet_ctx* c) {
     d.moduleNy = g.moduleNy; d.crystalNy = g.crystalNy; d.moduleN = g.moduleN; d.crystalN = g.crystalN;
     d.mat[0] = g.mat[0]; d.mat[1] = g.mat[1];
     d.dens[0] = g.dens[0]; d.dens[1] = g.dens[1];
-    d.nsurface = c->tr.nsurface;
-    memcpy(d.surface, c->tr.surface, sizeof(float) * 10 * GPET_MAX_SURFACES);
+    // quadric surfaces that can never exclude a point (all coefficients zero, constant term >= 0: the shipped
+    // "0 0 0 0 0 0 0 0 0 1") are dropped here instead of being evaluated at every step of every photon
+    // (crystalSearch, gPET_kernals.cu:1241-1245, returns when the quadric is < 0)
+    d.nsurface = 0;
+    for (int k = 0; k < c->tr.nsurface && k < GPET_MAX_SURFACES; k++) {
+        const float* q = c->tr.surface + 10 * k;
+        bool inert = q[9] >= 0.f;
+        for (int j = 0; j < 9; j++) inert = inert && q[j] == 0.f;
+        if (!inert) memcpy(d.surface + 10 * d.nsurface++, q, sizeof(float) * 10);
+    }
     // the bounding-sphere rejection in panel_entry needs Euclidean local coordinates: orthonormal axes on every panel
     d.dirmask = (c->in_run && c->dirmask_on) ? c->d_dirmask : nullptr;
     d.prefilter = g.panels.size() <= 32;

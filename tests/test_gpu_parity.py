@@ -278,6 +278,34 @@ def test_detector_transport_matches_oracle_per_photon():
 
 
 @needs_tables
+def test_detector_quadric_surfaces_exclude_hits_like_the_oracle():
+    # crystalSearch (gPET_kernals.cu:1241-1245): a point where a quadric is < 0 is not in a crystal (no hit, gap material).
+    # Two surfaces: the shipped inert one (dropped on the host) and a real one, x + 1 < 0: the rear half of the 2 cm panels.
+    s = parity.Setup(0, phantom="air", n=16)
+    surfaces = np.array([0, 0, 0, 0, 0, 0, 0, 0, 0, 1,   0, 0, 0, 0, 0, 0, 1, 0, 0, 1], np.float32)
+    s.ctx.set_transport(nsurface=2, surface=list(surfaces))
+    rng = np.random.default_rng(24)
+    ph = parity.isotropic_photons(150000, rng)
+    s.ctx.put_photons(1, ph)
+    s.ctx.stage_detector()
+    hits = s.ctx.fetch_hits(); ev = s.ctx.fetch_events()
+    res = orc.detector(ph, s.panels, s.counts4, s.pmat, s.pdens, surfaces, s.tab_det, s.eabs, 2, 1, s.seed)
+    assert hits.size > 10000 and abs(hits.size - res["hits"].size) <= 0.003 * res["hits"].size
+    assert abs(ev.size - res["events"].size) <= 0.003 * res["events"].size
+    assert hits["x"].min() >= -1.0 - 1e-5 and res["hits"]["x"].min() >= -1.0 - 1e-5      # nothing recorded behind the surface
+    a = {(int(r["parn"]), int(r["siten"])): float(r["E"]) for r in ev}
+    b = {(int(r["parn"]), int(r["siten"])): float(r["E"]) for r in res["events"]}
+    common = set(a) & set(b)
+    assert len(common) >= 0.99 * len(b) and sum(abs(a[k] - b[k]) <= 2e-3 * b[k] for k in common) >= 0.99 * len(common)
+    # with the inert surface alone the rear half records hits again
+    s.ctx.set_transport(nsurface=1, surface=list(surfaces[:10]))
+    s.ctx.put_photons(1, ph)
+    s.ctx.stage_detector()
+    assert s.ctx.fetch_hits()["x"].min() < -1.5
+    s.close()
+
+
+@needs_tables
 def test_pipeline_spectra_agree_statistically_with_independent_seeds():
     # statistical parity: GPU run with one seed vs oracle run with another on the same inputs; chi-square / ndf
     s = parity.Setup(0, phantom="cylinder", n=32, size=2.0, seed=1111)
