@@ -890,33 +890,36 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
                 float lamden = lammin * rho;
                 float prob = fmaxf(1.0f - lamden * xs.tot, 0.f);
                 float u = u01(r.y);
+                bool turn = false;   // Compton and Rayleigh lanes rotate together below (one copy of the code, more lanes on it)
+                float costh = 1.f, phi = 0.f;
                 if (u >= prob) {
                     prob += lamden * xs.compt;
                     if (u < prob) {
-                        float efrac, costh;
+                        float efrac;
                         compton_kn(E, rng, efrac, costh);
                         float de = E * (1.0f - efrac);
-                        float phi = kTwoPi * u01(r.z);
+                        phi = kTwoPi * u01(r.z);
                         if (m_id == 0) { h_type0 = 1; h_E0 = de; nh = 1; }
                         E -= de;
                         if (E < eabs) {
                             if (m_id == 0) { h_E1 = E; nh = 2; }  // type 2: remainder absorbed on the spot
                             finished = true;
                         } else {
-                            rotate_dir(vx, vy, vz, costh, phi);
+                            turn = true;
                         }
                     } else {
                         prob += lamden * xs.rayl;
                         if (u < prob) {
-                            float costh = surface_lookup(tb.rayff, mat, tb.rl_ncp, tb.rl_ne, E * tb.rl_ide, u01(r.z) * tb.rl_idcp);
-                            float phi = kTwoPi * u01(r.w);
-                            rotate_dir(vx, vy, vz, costh, phi);
+                            costh = surface_lookup(tb.rayff, mat, tb.rl_ncp, tb.rl_ne, E * tb.rl_ide, u01(r.z) * tb.rl_idcp);
+                            phi = kTwoPi * u01(r.w);
+                            turn = true;
                         } else {
                             if (m_id == 0) { h_type0 = 4; h_E0 = E; nh = 1; }
                             finished = true;
                         }
                     }
                 }
+                if (turn) rotate_dir(vx, vy, vz, costh, phi);
                 h_key = (M_id << 16) | (L_id & 0xffff);
             }
             // adder on the fly
