@@ -74,6 +74,7 @@ def bench_reference(ex: Path, steps=3, warmup=1, binname="gPET_nodump", metric="
     sim = med["sim_wall_s"] * len(runs)
     v = med["pairs"] / med["sim_wall_s"]
     ncores = os.cpu_count()
+    coinc = reference_coincidences(ex, med)
     return {"metric": metric, "value": v, "unit": unit, "n_gpus": 1, "steps": steps, "warmup": warmup,
             "ms_per_step": 1e3 * sim / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": workload, "binary": binname,
@@ -82,8 +83,35 @@ def bench_reference(ex: Path, steps=3, warmup=1, binname="gPET_nodump", metric="
                              "sample": f"{steps} full runs of the shipped example by the reference's own CUDA build (texture-object patch only) on the same GPU; its host side (3 std::sort + orderevents per epoch, file appends) is single-threaded; node has {ncores} cores"},
             "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "reference_counters": {k: runs[-1][k] for k in ("pairs", "epochs", "hits", "events_adder", "events_threshold", "events_deadtime", "singles")},
+            "reference_coincidences": coinc,
             "reference_times": {"sim_wall_s": [r["sim_wall_s"] for r in runs], "total_wall_s": [r["total_wall_s"] for r in runs],
                                 "process_wall_s": [r["process_wall_s"] for r in runs]}}
+
+
+def reference_coincidences(ex: Path, run, window_us=0.01):
+    """The reference has no coincidence sorter: its singles.dat of the last run goes through the oracle's
+    sorter (thresholds and dead time switched off, so that the singles pass unchanged), timed separately."""
+    try:
+        import numpy as np
+        from oracle import oracle as orc
+        sing = np.fromfile(Path(ex) / "output" / "singles.dat", dtype=orc.EVENT_DTYPE)
+        if sing.size == 0:
+            return None
+        p = orc.DigiParams()
+        for k, v in dict(readout_depth=2, readout_policy=1, threshold_eV=0.0, blur_policy=1, blur_Eref=662000.0, blur_Rref=0.0, blur_slope=0.0,
+                         blur_space=0.0, dead_level=3, dead_type=0, dead_time_us=0.0, ewin_min=0.0, ewin_max=2.0e6, time_blur_sigma_us=0.0,
+                         coinc_window_us=window_us, coinc_policy=0, coinc_min_panel_diff=0, npanels=8, moduleN=117, crystalN=64, seed=1).items():
+            setattr(p, k, v)
+        t0 = time.perf_counter()
+        out, counts, co = orc.digitize(sing, p)
+        dt = time.perf_counter() - t0
+        if out.size != sing.size:
+            return {"note": f"pass-through changed the singles ({sing.size} -> {out.size})"}
+        return {"singles_in_file": int(sing.size), "coincidences": int(co.size), "window_us": window_us,
+                "per_s_of_simulation_region": co.size / run["sim_wall_s"], "oracle_sorter_s": dt,
+                "note": "output/ is cleaned before every run: singles.dat holds the last run only"}
+    except Exception as e:  # noqa: BLE001
+        return {"note": f"unavailable: {type(e).__name__}: {e}"}
 
 
 if __name__ == "__main__":
