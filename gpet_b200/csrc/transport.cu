@@ -231,8 +231,10 @@ __device__ __forceinline__ void store_photon(const PhotonQueue& q, unsigned slot
 // sampled direction, photon b is the acollinear partner; they share the point and the time.
 __device__ __forceinline__ void source_pair(const SourceDev* __restrict__ fr, const PhantomDev& ph, uint64_t seed,
                                             unsigned long long k, Photon& a, Photon& b) {
+    // source of pair k = number of inclusive prefix sums at or below k (monotone table): independent loads, no
+    // dependent chain through up to nsource iterations
     int s = 0;
-    while (s < fr->nsource - 1 && k >= fr->cum_pairs[s]) s++;
+    for (int i = 0; i < fr->nsource - 1; i++) s += k >= fr->cum_pairs[i] ? 1 : 0;
     const unsigned long long gk = fr->first_pair + k;
     Philox rng(seed, gk, (uint32_t)kStageSource << 24);
     uint4 r0 = rng.next();
