@@ -144,6 +144,9 @@ _SIGS = {
 _lib = None
 
 
+ABI_VERSION = 2   # GPET_ABI_VERSION of include/gpet_b200.h
+
+
 def lib():
     """Load libgpet_b200.so (built in-tree by `make` / __graft_entry__.build()).  Raises if it is missing."""
     global _lib
@@ -156,6 +159,8 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
+        if l.gpet_abi_version() != ABI_VERSION:   # the ctypes structures below mirror the header of exactly this version
+            raise RuntimeError(f"{LIB_PATH} has ABI version {l.gpet_abi_version()}, this module expects {ABI_VERSION}: rebuild (`make`)")
         _lib = l
     return _lib
 

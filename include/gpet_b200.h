@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GPET_ABI_VERSION 1
+#define GPET_ABI_VERSION 2  /* 2: gpet_transport_params + record_psf / record_sphere, gpet_digitizer_params + noise_*, gpet_set_psf_output, gpet_stage_noise */
 
 typedef enum gpet_status {
     GPET_OK = 0,

@@ -84,7 +84,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(l, name), f"{name} declared in gpet_b200.h but not exported"
     assert set(api._SIGS) == declared, declared ^ set(api._SIGS)
-    assert api.lib().gpet_abi_version() == 1
+    assert api.lib().gpet_abi_version() == 2
 
 
 def test_record_layouts():
