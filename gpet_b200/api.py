@@ -136,6 +136,7 @@ _SIGS = {
     "gpet_get_spectrum": (C.c_int, [_P, _P, C.c_int]),
     "gpet_set_spectrum": (C.c_int, [_P, C.c_int, C.c_float, C.c_float]),
     "gpet_set_shard": (C.c_int, [_P, C.c_int, C.c_int]),
+    "gpet_get_direction_table": (C.c_int64, [_P, _P, C.c_int64, _P]),
     "gpet_profile_enable": (C.c_int, [_P, C.c_int]),
     "gpet_profile_count": (C.c_int, [_P]),
     "gpet_profile_get": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
@@ -277,6 +278,17 @@ class Context:
             else:
                 setattr(p, k, v)
         self._ck(self._l.gpet_set_transport(self._h, C.byref(p)))
+
+    def direction_table(self):
+        """(table[32, 32, 32] indexed [iz, iy, ix], reference sphere (x, y, z, r)) or (None, None) when it does not apply."""
+        ref = np.zeros(4, np.float64)
+        n = self._ck(self._l.gpet_get_direction_table(self._h, None, 0, _ptr(ref)))
+        if n == 0:
+            return None, None
+        tab = np.zeros(n, np.uint32)
+        self._ck(self._l.gpet_get_direction_table(self._h, _ptr(tab), n, _ptr(ref)))
+        nb = round(n ** (1 / 3))
+        return tab.reshape(nb, nb, nb), ref
 
     def set_psf_output(self, mode):
         """OUTPUTPSF of the reference (constants.h:5): 0 none, 1 source photons in PSF mode, 2 source + phantom dumps."""

@@ -1240,12 +1240,10 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
 // (a) the photon moves against the panel's growth direction or (b) the line misses the bounding sphere of the face by
 // a margin -- both with the cell's half diagonal and rounding slack on the safe side.  Off with positron range (the
 // reference's range walk can displace the annihilation point without bound).
-int prepare_dirmask(gpet_ctx* c) {
-    c->dirmask_on = false;
+// host part: reference sphere (o, rref) and the table; false when the table does not apply to the loaded inputs
+bool build_dirmask(const gpet_ctx* c, double o[3], double& rref, std::vector<unsigned>& tab) {
     const Geometry& g = c->geo;
-    if (!c->have_geo || !c->have_ph || g.panels.empty() || g.panels.size() > 32 || c->tr.use_positron_range) return GPET_OK;
-    if (getenv("GPET_NO_DIRMASK")) return GPET_OK;
-    double o[3], rref = 0.0;
+    if (!c->have_geo || !c->have_ph || g.panels.empty() || g.panels.size() > 32 || c->tr.use_positron_range) return false;
     for (int k = 0; k < 3; k++) o[k] = (double)c->ph.offset[k] + 0.5 * (double)c->ph.size[k];
     rref = 0.5 * std::sqrt((double)c->ph.size[0] * c->ph.size[0] + (double)c->ph.size[1] * c->ph.size[1] + (double)c->ph.size[2] * c->ph.size[2]);
     auto reach = [&](double x, double y, double z, double ext) {
@@ -1265,39 +1263,48 @@ int prepare_dirmask(gpet_ctx* c) {
             reach(q[0], q[1], q[2], ext);
         }
     }
-    if (!std::isfinite(rref)) return GPET_OK;
+    if (!std::isfinite(rref)) return false;
     rref = rref * 1.001 + 1e-3;
+    const int nb = gpet::kDirBins;
+    const double hd = std::sqrt(3.0) / nb + 2e-5;
+    const unsigned all = g.panels.size() >= 32 ? ~0u : ((1u << g.panels.size()) - 1u);
+    tab.assign((size_t)nb * nb * nb, all);
+    for (int iz = 0; iz < nb; iz++)
+        for (int iy = 0; iy < nb; iy++)
+            for (int ix = 0; ix < nb; ix++) {
+                const double cx = -1.0 + (ix + 0.5) * 2.0 / nb, cy = -1.0 + (iy + 0.5) * 2.0 / nb, cz = -1.0 + (iz + 0.5) * 2.0 / nb;
+                const double cn = std::sqrt(cx * cx + cy * cy + cz * cz);
+                if (std::fabs(cn - 1.0) > hd + 2e-4) continue;   // no direction of (nearly) unit length falls here
+                unsigned m = 0;
+                for (size_t i = 0; i < g.panels.size(); i++) {
+                    const gpet_panel& p = g.panels[i];
+                    const double un = std::sqrt((double)p.UniXx * p.UniXx + (double)p.UniXy * p.UniXy + (double)p.UniXz * p.UniXz);
+                    const double lvx = cx * p.UniXx + cy * p.UniXy + cz * p.UniXz;
+                    const bool dir_ok = p.directionx == 0 ? true : p.directionx > 0 ? lvx >= -(hd * un + 1e-3) : lvx <= hd * un + 1e-3;
+                    const double dx = p.offsetx - o[0], dy = p.offsety - o[1], dz = p.offsetz - o[2];
+                    const double dn = std::sqrt(dx * dx + dy * dy + dz * dz);
+                    const double kx = dy * cz - dz * cy, ky = dz * cx - dx * cz, kz = dx * cy - dy * cx;
+                    const double miss = (std::sqrt(kx * kx + ky * ky + kz * kz) - dn * hd) / 1.0002 - rref;
+                    const double rp = 0.5 * std::sqrt((double)p.lengthy * p.lengthy + (double)p.lengthz * p.lengthz);
+                    const bool near = miss <= 1.006 * rp + 0.01;
+                    if (dir_ok && near) m |= 1u << i;
+                }
+                tab[((size_t)iz * nb + iy) * nb + ix] = m;
+            }
+    return true;
+}
+
+int prepare_dirmask(gpet_ctx* c) {
+    c->dirmask_on = false;
+    if (getenv("GPET_NO_DIRMASK")) return GPET_OK;
+    double o[3], rref = 0.0;
+    std::vector<unsigned> tab;
+    // cheap key first: reference sphere and geometry version
+    if (!build_dirmask(c, o, rref, tab)) return GPET_OK;
     const double key[5] = {o[0], o[1], o[2], rref, (double)c->geo_version};
     bool same = c->d_dirmask != nullptr;
     for (int k = 0; k < 5; k++) same = same && key[k] == c->dirmask_key[k];
     if (!same) {
-        const int nb = gpet::kDirBins;
-        const double hd = std::sqrt(3.0) / nb + 2e-5;
-        const unsigned all = g.panels.size() >= 32 ? ~0u : ((1u << g.panels.size()) - 1u);
-        std::vector<unsigned> tab((size_t)nb * nb * nb, all);
-        // a photon whose line misses every face leaves the mask empty; orthonormal axes are checked by detector_dev
-        for (int iz = 0; iz < nb; iz++)
-            for (int iy = 0; iy < nb; iy++)
-                for (int ix = 0; ix < nb; ix++) {
-                    const double cx = -1.0 + (ix + 0.5) * 2.0 / nb, cy = -1.0 + (iy + 0.5) * 2.0 / nb, cz = -1.0 + (iz + 0.5) * 2.0 / nb;
-                    const double cn = std::sqrt(cx * cx + cy * cy + cz * cz);
-                    if (std::fabs(cn - 1.0) > hd + 2e-4) continue;   // no direction of (nearly) unit length falls here
-                    unsigned m = 0;
-                    for (size_t i = 0; i < g.panels.size(); i++) {
-                        const gpet_panel& p = g.panels[i];
-                        const double un = std::sqrt((double)p.UniXx * p.UniXx + (double)p.UniXy * p.UniXy + (double)p.UniXz * p.UniXz);
-                        const double lvx = cx * p.UniXx + cy * p.UniXy + cz * p.UniXz;
-                        const bool dir_ok = p.directionx == 0 ? true : p.directionx > 0 ? lvx >= -(hd * un + 1e-3) : lvx <= hd * un + 1e-3;
-                        const double dx = p.offsetx - o[0], dy = p.offsety - o[1], dz = p.offsetz - o[2];
-                        const double dn = std::sqrt(dx * dx + dy * dy + dz * dz);
-                        const double kx = dy * cz - dz * cy, ky = dz * cx - dx * cz, kz = dx * cy - dy * cx;
-                        const double miss = (std::sqrt(kx * kx + ky * ky + kz * kz) - dn * hd) / 1.0002 - rref;
-                        const double rp = 0.5 * std::sqrt((double)p.lengthy * p.lengthy + (double)p.lengthz * p.lengthz);
-                        const bool near = miss <= 1.006 * rp + 0.01;
-                        if (dir_ok && near) m |= 1u << i;
-                    }
-                    tab[((size_t)iz * nb + iy) * nb + ix] = m;
-                }
         int r;
         if (!c->d_dirmask && (r = dev_alloc(c, &c->d_dirmask, tab.size()))) return r;
         CK(cudaMemcpyAsync(c->d_dirmask, tab.data(), tab.size() * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
@@ -1493,6 +1500,19 @@ int gpet_set_coincidence_format(gpet_ctx* c, int format) {
     if (!c || (format != GPET_COINC_RECORDS && format != GPET_COINC_PAIRS)) return GPET_ERR_ARG;
     c->coinc_format = format;
     return GPET_OK;
+}
+
+int64_t gpet_get_direction_table(const gpet_ctx* c, uint32_t* out, int64_t cap, double ref_sphere[4]) {
+    if (!c) return GPET_ERR_ARG;
+    double o[3], rref = 0.0;
+    std::vector<unsigned> tab;
+    if (!build_dirmask(c, o, rref, tab)) return 0;
+    if (ref_sphere) { ref_sphere[0] = o[0]; ref_sphere[1] = o[1]; ref_sphere[2] = o[2]; ref_sphere[3] = rref; }
+    if (out) {
+        if (cap < (int64_t)tab.size()) return GPET_ERR_CAPACITY;
+        for (size_t k = 0; k < tab.size(); k++) out[k] = tab[k];
+    }
+    return (int64_t)tab.size();
 }
 
 int gpet_set_psf_output(gpet_ctx* c, int mode) {

@@ -302,6 +302,12 @@ int gpet_profile_count(gpet_ctx* ctx);
 int gpet_profile_get(gpet_ctx* ctx, int i, char* name, int name_cap, double* total_ms, uint64_t* launches);
 /* Shard the planned frames: this context only runs frames f with f % world == rank. */
 int gpet_set_shard(gpet_ctx* ctx, int rank, int world);
+/* The direction table gpet_run narrows the panel search with: 32^3 words over the direction cube
+ * [-1,1]^3, cell = floor((v + 1) * 16) per axis, x fastest; bit i set = a photon flying in a direction of that cell whose
+ * line passes the reference sphere (centre x y z, radius -> ref_sphere) can enter panel i.  Returns the number of words
+ * (0: the table does not apply to the loaded inputs -- no phantom/geometry, more than 32 panels, positron range on).
+ * Works on a host-only context; exists so that its conservativeness can be tested without a GPU. */
+int64_t gpet_get_direction_table(const gpet_ctx* ctx, uint32_t* out, int64_t cap, double ref_sphere[4]);
 
 #ifdef __cplusplus
 }

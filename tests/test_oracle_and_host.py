@@ -265,6 +265,61 @@ def test_frame_planner_statistics_and_invariance():
         assert [c.frame_pairs(f) for f in range(nf)] != pairs
 
 
+@pytest.mark.parametrize("geo,phantom_half,sources", [
+    ("config8", 0.5, [(0, 0, 0.0, 1.5)]),                                   # shipped ring, 1 cm phantom, sources inside 1.5 cm
+    ("ring32", 10.0, [(6, 5, -4.0, 4.2), (-7, 3, 6.0, 1.5), (0, -8, 0.0, 3.4)]),   # 32 panels at 30 cm, big phantom, off-centre sources
+])
+def test_direction_table_never_drops_a_panel_the_exact_test_accepts(tmp_path, geo, phantom_half, sources):
+    """gpet_run narrows the panel search with a direction table.  Brute force on the CPU: random
+    lines through the reference sphere, the reference's acceptance test (gPET_kernals.cu:966-1007) in float64 for every
+    panel, and the accepting panel must be in the table cell of the line's direction."""
+    from tools import gen_inputs
+    geo_path = parity.EXAMPLE / "input" / "config8.geo"
+    if geo == "ring32":
+        geo_path = tmp_path / "ring.geo"
+        geo_path.write_text(gen_inputs.ring_geo(32, 30.0))
+    n = 8
+    mat = np.zeros((n, n, n), np.int32); den = np.ones((n, n, n), np.float32)
+    src = tmp_path / "src.txt"
+    src.write_text(f"{len(sources)}\nheader#\n" + "".join(f"1000 0 2 {x} {y} {z} {r} 0 0\n" for x, y, z, r in sources))
+    with api.Context(-1) as c:
+        c.load_geometry(geo_path)
+        c.set_phantom(mat, den, np.full(3, -phantom_half, np.float32), np.full(3, 2 * phantom_half, np.float32))
+        c.load_isotopes(parity.EXAMPLE / "data" / "isotopes.txt")
+        c.load_source(src)
+        tab, ref = c.direction_table()
+        panels = c.panels()
+    assert tab is not None and tab.shape == (32, 32, 32)
+    assert ref[3] >= np.sqrt(3) * phantom_half and all(np.hypot(np.hypot(x, y), z) + r <= ref[3] for x, y, z, r in sources)
+    rng = np.random.default_rng(7)
+    m = 400000
+    q = rng.normal(size=(m, 3)); q *= (ref[3] * rng.random(m) ** (1 / 3) / np.linalg.norm(q, axis=1))[:, None]; q += ref[:3]   # in the sphere
+    v = rng.normal(size=(m, 3)); v /= np.linalg.norm(v, axis=1)[:, None]
+    v32 = v.astype(np.float32)
+    # the photon may sit anywhere on its line when the search runs (overshoot position): slide it along v
+    pos = q + v * rng.uniform(-40, 40, m)[:, None]
+    cell = np.clip(np.floor((v32.astype(np.float64) + 1.0) * 16.0).astype(int), 0, 31)
+    mask = tab[cell[:, 2], cell[:, 1], cell[:, 0]]
+    accepted_any = np.zeros(m, bool)
+    for i, p in enumerate(panels):
+        ux = np.array([p["UniXx"], p["UniXy"], p["UniXz"]], np.float64); uy = np.array([p["UniYx"], p["UniYy"], p["UniYz"]], np.float64)
+        uz = np.array([p["UniZx"], p["UniZy"], p["UniZz"]], np.float64); o = np.array([p["offsetx"], p["offsety"], p["offsetz"]], np.float64)
+        lvx = v @ ux
+        r = pos - o
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = (r @ ux) / lvx
+            y2 = r @ uy - t * (v @ uy); z2 = r @ uz - t * (v @ uz)
+        ok = (lvx * p["directionx"] >= 0) & (np.abs(y2) < p["lengthy"] / 2) & (np.abs(z2) < p["lengthz"] / 2)
+        dropped = ok & ((mask >> np.uint32(i)) & 1 == 0)
+        assert not dropped.any(), (geo, i, int(dropped.sum()))
+        accepted_any |= ok
+    assert accepted_any.mean() > 0.1                       # the test really exercised accepting panels
+    uniq, inv = np.unique(mask, return_inverse=True)
+    pop = np.array([bin(int(x)).count("1") for x in uniq])[inv]
+    # and the table really narrows the search (directions along the ring axis see every panel of the 32-panel ring)
+    assert (pop.max() <= 4 and np.median(pop) <= 3) if geo == "config8" else np.median(pop) <= 18
+
+
 def test_c_example_compiles_as_c99_and_refuses_to_compute_without_a_device(tmp_path):
     # the header is plain C (no C++/torch types in the signatures): examples/c/digitize_replay.c builds with gcc -std=c99
     exe = tmp_path / "digitize_replay"
