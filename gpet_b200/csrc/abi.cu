@@ -559,6 +559,7 @@ int gpet_load_psf(gpet_ctx* c, const char* f, int64_t max_particles, int ptype) 
     if (ptype != 0 && ptype != 1) return fail(c, GPET_ERR_ARG, "psf particle type must be 0 (positron) or 1 (photon)");
     std::string e = load_psf(f, max_particles, ptype, c->psf);
     if (!e.empty()) { c->have_psf = false; return fail(c, GPET_ERR_IO, e); }
+    c->psf_version++;
     c->have_psf = true;
     c->usepsf = 1;
     return GPET_OK;
@@ -1240,8 +1241,8 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
 // (a) the photon moves against the panel's growth direction or (b) the line misses the bounding sphere of the face by
 // a margin -- both with the cell's half diagonal and rounding slack on the safe side.  Off with positron range (the
 // reference's range walk can displace the annihilation point without bound).
-// host part: reference sphere (o, rref) and the table; false when the table does not apply to the loaded inputs
-bool build_dirmask(const gpet_ctx* c, double o[3], double& rref, std::vector<unsigned>& tab) {
+// reference sphere (o, rref) of the direction table; false when the table does not apply to the loaded inputs
+bool dirmask_reference(const gpet_ctx* c, double o[3], double& rref) {
     const Geometry& g = c->geo;
     if (!c->have_geo || !c->have_ph || g.panels.empty() || g.panels.size() > 32 || c->tr.use_positron_range) return false;
     for (int k = 0; k < 3; k++) o[k] = (double)c->ph.offset[k] + 0.5 * (double)c->ph.size[k];
@@ -1251,7 +1252,17 @@ bool build_dirmask(const gpet_ctx* c, double o[3], double& rref, std::vector<uns
         rref = std::max(rref, std::sqrt(dx * dx + dy * dy + dz * dz) + ext);
     };
     if (c->usepsf) {
-        for (const gpet_photon& p : c->psf.p) reach(p.x, p.y, p.z, 0.0);
+        // millions of records: once per (PSF file, phantom position), not once per run
+        if (c->psf_reach_key[0] != o[0] || c->psf_reach_key[1] != o[1] || c->psf_reach_key[2] != o[2] || c->psf_reach_key[3] != (double)c->psf_version) {
+            double far2 = 0.0;
+            for (const gpet_photon& p : c->psf.p) {
+                const double dx = p.x - o[0], dy = p.y - o[1], dz = p.z - o[2];
+                far2 = std::max(far2, dx * dx + dy * dy + dz * dz);
+            }
+            c->psf_reach = std::sqrt(far2);
+            c->psf_reach_key[0] = o[0]; c->psf_reach_key[1] = o[1]; c->psf_reach_key[2] = o[2]; c->psf_reach_key[3] = (double)c->psf_version;
+        }
+        rref = std::max(rref, c->psf_reach);
     } else {
         for (int i = 0; i < c->src.n(); i++) {
             const float* q = c->src.coeff.data() + 6 * i;
@@ -1265,6 +1276,13 @@ bool build_dirmask(const gpet_ctx* c, double o[3], double& rref, std::vector<uns
     }
     if (!std::isfinite(rref)) return false;
     rref = rref * 1.001 + 1e-3;
+    return true;
+}
+
+// the table itself (32 k cells x panels: ~0.4 ms of host time, so only when the reference sphere or the geometry changed)
+bool build_dirmask(const gpet_ctx* c, double o[3], double& rref, std::vector<unsigned>& tab) {
+    if (!dirmask_reference(c, o, rref)) return false;
+    const Geometry& g = c->geo;
     const int nb = gpet::kDirBins;
     const double hd = std::sqrt(3.0) / nb + 2e-5;
     const unsigned all = g.panels.size() >= 32 ? ~0u : ((1u << g.panels.size()) - 1u);
@@ -1298,13 +1316,14 @@ int prepare_dirmask(gpet_ctx* c) {
     c->dirmask_on = false;
     if (getenv("GPET_NO_DIRMASK")) return GPET_OK;
     double o[3], rref = 0.0;
-    std::vector<unsigned> tab;
     // cheap key first: reference sphere and geometry version
-    if (!build_dirmask(c, o, rref, tab)) return GPET_OK;
+    if (!dirmask_reference(c, o, rref)) return GPET_OK;
     const double key[5] = {o[0], o[1], o[2], rref, (double)c->geo_version};
     bool same = c->d_dirmask != nullptr;
     for (int k = 0; k < 5; k++) same = same && key[k] == c->dirmask_key[k];
     if (!same) {
+        std::vector<unsigned> tab;
+        if (!build_dirmask(c, o, rref, tab)) return GPET_OK;
         int r;
         if (!c->d_dirmask && (r = dev_alloc(c, &c->d_dirmask, tab.size()))) return r;
         CK(cudaMemcpyAsync(c->d_dirmask, tab.data(), tab.size() * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));

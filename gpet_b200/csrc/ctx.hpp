@@ -85,6 +85,9 @@ struct gpet_ctx {
     bool dirmask_on = false;                // valid for the run in flight
     double dirmask_key[5] = {0, 0, 0, -1, -1};   // reference point, reference radius, geometry version it was built for
     int geo_version = 0;
+    int psf_version = 0;                    // bumped by gpet_load_psf
+    mutable double psf_reach_key[4] = {0, 0, 0, -1};   // (o, psf_version) the cached reach below belongs to
+    mutable double psf_reach = 0.0;         // largest distance of a PSF record from o
     uint32_t* d_vox = nullptr;
     float4* d_xs = nullptr;
     float *d_maj_ph = nullptr, *d_maj_det = nullptr, *d_cmpsf = nullptr, *d_rayff = nullptr;
