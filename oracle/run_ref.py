@@ -75,6 +75,16 @@ def bench_reference(ex: Path, steps=3, warmup=1, binname="gPET_nodump", metric="
     v = med["pairs"] / med["sim_wall_s"]
     ncores = os.cpu_count()
     coinc = reference_coincidences(ex, med)
+    # one run of the binary as shipped (OUTPUTHIT = 1: Hits.dat / HitsID.dat written per epoch), so that the comparison
+    # above is visibly not an I/O contest
+    dumps = None
+    if (REFDIR / "gPET").exists():
+        try:
+            r = run_once(ex, "gPET")
+            if r["returncode"] == 0 and r["sim_wall_s"]:
+                dumps = {"binary": "gPET", "sim_wall_s": r["sim_wall_s"], "pairs": r["pairs"], "value": r["pairs"] / r["sim_wall_s"]}
+        except Exception as e:  # noqa: BLE001
+            dumps = {"note": f"unavailable: {type(e).__name__}: {e}"}
     return {"metric": metric, "value": v, "unit": unit, "n_gpus": 1, "steps": steps, "warmup": warmup,
             "ms_per_step": 1e3 * sim / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": workload, "binary": binname,
@@ -83,7 +93,7 @@ def bench_reference(ex: Path, steps=3, warmup=1, binname="gPET_nodump", metric="
                              "sample": f"{steps} full runs of the shipped example by the reference's own CUDA build (texture-object patch only) on the same GPU; its host side (3 std::sort + orderevents per epoch, file appends) is single-threaded; node has {ncores} cores"},
             "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "reference_counters": {k: runs[-1][k] for k in ("pairs", "epochs", "hits", "events_adder", "events_threshold", "events_deadtime", "singles")},
-            "reference_coincidences": coinc,
+            "reference_coincidences": coinc, "reference_with_dumps": dumps,
             "reference_times": {"sim_wall_s": [r["sim_wall_s"] for r in runs], "total_wall_s": [r["total_wall_s"] for r in runs],
                                 "process_wall_s": [r["process_wall_s"] for r in runs]}}
 
