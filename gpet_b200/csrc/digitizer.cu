@@ -61,6 +61,8 @@ __device__ __forceinline__ unsigned warp_sum(unsigned v) {
     return v;
 }
 
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // sum over the block, valid in thread 0 (all threads must call)
 __device__ __forceinline__ unsigned block_sum(unsigned v) {
     __shared__ unsigned s_part[kThreads / 32];
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_prep(EventBuf ev, DigitizerDev 
                                                    unsigned long long* __restrict__ keys, int* __restrict__ site_of,
                                                    unsigned* __restrict__ aux, unsigned* __restrict__ bcount,
                                                    unsigned* __restrict__ counters) {
+    pdl_wait();
     const unsigned n = min(*ev.count, ev.capacity);
     if (blockIdx.x == 0 && threadIdx.x == 0) counters[0] = n;
     const BucketMap m = bucket_map(range, n);
@@ -325,6 +328,7 @@ __device__ __forceinline__ TileScan tile_exclusive_scan(const unsigned v[8], uns
 __global__ void __launch_bounds__(kThreads) k_bucket_scan(const unsigned* __restrict__ bcount, unsigned* __restrict__ bstart,
                                                           unsigned* __restrict__ status, unsigned* __restrict__ counters,
                                                           TimeRange range) {
+    pdl_wait();
     const unsigned tile = blockIdx.x;
     const unsigned b0 = tile * kScanTile + threadIdx.x * 8;
     unsigned c[8];
@@ -353,6 +357,7 @@ __global__ void __launch_bounds__(kThreads) k_bucket_scatter(const unsigned long
                                                              const unsigned* __restrict__ counters, TimeRange range,
                                                              const unsigned* __restrict__ bstart,
                                                              unsigned long long* __restrict__ bkeys, uint2* __restrict__ bpay) {
+    pdl_wait();
     if (counters[kFlagLsd]) return;
     const unsigned n = counters[0];
     const BucketMap m = bucket_map(range, n);
@@ -392,6 +397,7 @@ __global__ void __launch_bounds__(kThreads) k_bucket_rank(const unsigned long lo
                                                           const unsigned* __restrict__ counters, TimeRange range,
                                                           unsigned long long* __restrict__ tsort, unsigned* __restrict__ order_t,
                                                           int* __restrict__ site_t) {
+    pdl_wait();
     if (counters[kFlagLsd]) return;
     const unsigned n1 = counters[1];
     const BucketMap m = bucket_map(range, counters[0]);
@@ -540,6 +546,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_emit_singles(EventBuf ev, Digit
                                                            int* __restrict__ span, unsigned long long* __restrict__ spectrum,
                                                            int nbins, int spec_stride, float emin, float emax, int fallback_skipped,
                                                            unsigned* __restrict__ h_singles_count) {
+    pdl_wait();
     __shared__ unsigned s_tile;
     __shared__ double s_t[kHalo + kScanTile];
     __shared__ int s_site[kHalo + kScanTile];
@@ -752,6 +759,7 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
                                                     unsigned singles_cap, unsigned* __restrict__ status,
                                                     gpet_coincidence* __restrict__ out, uint2* __restrict__ pairs, unsigned cap,
                                                     const unsigned* __restrict__ base_in, unsigned* __restrict__ base_out) {
+    pdl_wait();
     __shared__ unsigned s_tile;
     __shared__ double s_t[kScanTile + 2 * kHalo];
     __shared__ int s_p[kScanTile + 2 * kHalo];
@@ -857,6 +865,21 @@ unsigned scan_tiles(size_t capacity) { return (unsigned)((capacity + kScanTile -
 unsigned scan_status_stride() { return kStatusStride; }
 unsigned bucket_words() { return kMaxBuckets; }
 
+// Programmatic dependent launch: the kernel may be set up and its blocks made resident while its predecessor in the
+// stream is still draining; every kernel launched this way starts with pdl_wait() (griddepcontrol.wait), which returns
+// when the predecessor has completed and its writes are visible.  Saves the launch latency at each of the digitizer's
+// kernel boundaries (short, latency-bound kernels).
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 TimeRange time_range_us(double t_lo_us, double t_hi_us) {
     TimeRange r;
     r.lo = t_lo_us;
@@ -869,13 +892,14 @@ TimeRange time_range_us(double t_lo_us, double t_hi_us) {
 // (same layout as fetch_counters_async in abi.cu).  A cudaMemcpyAsync on the compute stream would wait for the D2H
 // copy engine, which the previous frame's singles keep busy for hundreds of microseconds.
 __global__ void k_publish_counters(const unsigned* __restrict__ counters, const unsigned* __restrict__ hot, unsigned* __restrict__ h_dst) {
+    pdl_wait();
     const unsigned i = threadIdx.x;
     if (i < 32) h_dst[i] = counters[i];
     else if (i < 40) h_dst[i] = hot[((i - 32) >> 1) * kHotStride + ((i - 32) & 1)];
 }
 
 int launch_publish_counters(const unsigned* counters, const unsigned* hot, unsigned* h_dst, cudaStream_t s) {
-    GPET_LAUNCH("k_publish_counters", s, k_publish_counters<<<1, 64, 0, s>>>(counters, hot, h_dst));
+    GPET_LAUNCH("k_publish_counters", s, launch_pdl(k_publish_counters, 1, 64, s, counters, hot, h_dst));
     return 1;
 }
 
@@ -928,13 +952,13 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
         launches++;
         tr.lo = 0.0; tr.hi = 0.0; tr.dev = ws.minmax;
     }
-    GPET_LAUNCH("k_prep", s, k_prep<<<g_prep, kThreads, 0, s>>>(ev, p, seed, tr, keys, ws.site_of, ws.aux, ws.bcount, ws.counters));
-    GPET_LAUNCH("k_bucket_scan", s, k_bucket_scan<<<kMaxBuckets / kScanTile, kThreads, 0, s>>>(ws.bcount, ws.bstart, ws.scan_status[2],
-                                                                                           ws.counters, tr));
-    GPET_LAUNCH("k_bucket_scatter", s, k_bucket_scatter<<<g_scatter, kThreads, 0, s>>>(keys, ws.site_of, ws.aux, ws.counters, tr, ws.bstart,
-                                                                                 bkeys, ws.bpay));
-    GPET_LAUNCH("k_bucket_rank", s, k_bucket_rank<<<g_rank, kThreads, 0, s>>>(bkeys, ws.bpay, ws.bstart, ws.counters, tr, keys, ws.order_t,
-                                                                           ws.site_t));
+    GPET_LAUNCH("k_prep", s, launch_pdl(k_prep, g_prep, kThreads, s, ev, p, seed, tr, keys, ws.site_of, ws.aux, ws.bcount, ws.counters));
+    GPET_LAUNCH("k_bucket_scan", s, launch_pdl(k_bucket_scan, (int)(kMaxBuckets / kScanTile), kThreads, s, ws.bcount, ws.bstart, ws.scan_status[2],
+                                                ws.counters, tr));
+    GPET_LAUNCH("k_bucket_scatter", s, launch_pdl(k_bucket_scatter, g_scatter, kThreads, s, keys, ws.site_of, ws.aux, ws.counters, tr, ws.bstart,
+                                                   bkeys, ws.bpay));
+    GPET_LAUNCH("k_bucket_rank", s, launch_pdl(k_bucket_rank, g_rank, kThreads, s, bkeys, ws.bpay, ws.bstart, ws.counters, tr, keys, ws.order_t,
+                                                ws.site_t));
     launches += 4;
     if (with_fallback) {
         static int coop_grid = 0;
@@ -953,14 +977,14 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
         GPET_LAUNCH("k_deadtime_chain", s, k_deadtime_chain<<<g_chain, kThreads, 0, s>>>(p, keys, ws.site_t, ws.kill, ws.counters));
         launches++;
     }
-    GPET_LAUNCH("k_emit_singles", s, k_emit_singles<<<g_emit, kThreads, 0, s>>>(ev, p, singles, out.singles_cap, keys, ws.order_t, ws.site_t,
-                                                                            ws.kill, ws.counters, ws.scan_status[0], ws.stime, ws.span,
-                                                                            ws.spectrum, ws.spectrum_bins, ws.spectrum_stride, ws.spec_emin, ws.spec_emax,
-                                                                            with_fallback ? 0 : 1, out.ev_after_emit ? out.h_singles_count : nullptr));
+    GPET_LAUNCH("k_emit_singles", s, launch_pdl(k_emit_singles, g_emit, kThreads, s, ev, p, singles, out.singles_cap, keys, ws.order_t, ws.site_t,
+                                                ws.kill, ws.counters, ws.scan_status[0], ws.stime, ws.span, ws.spectrum, ws.spectrum_bins,
+                                                ws.spectrum_stride, ws.spec_emin, ws.spec_emax, with_fallback ? 0 : 1,
+                                                out.ev_after_emit ? out.h_singles_count : (unsigned*)nullptr));
     launches++;
     if (out.ev_after_emit && out.h_singles_count) cudaEventRecord(out.ev_after_emit, s);
     if (p.cwin > 0.f && (out.coinc || out.pairs)) {
-        GPET_LAUNCH("k_coinc", s, k_coinc<<<g_coinc, kThreads, 0, s>>>(singles, ws.stime, ws.span, p, ws.counters, out.singles_cap, ws.scan_status[1],
+        GPET_LAUNCH("k_coinc", s, launch_pdl(k_coinc, g_coinc, kThreads, s, singles, ws.stime, ws.span, p, ws.counters, out.singles_cap, ws.scan_status[1],
                                                                   static_cast<gpet_coincidence*>(out.coinc), static_cast<uint2*>(out.pairs),
                                                                   out.coinc_cap, out.pair_base_in, out.pair_base_out));
         launches++;

@@ -810,6 +810,8 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
     SlotsSmem& sl = *reinterpret_cast<SlotsSmem*>(s_raw);
     PanelDev* s_panels = reinterpret_cast<PanelDev*>(s_raw + sizeof(SlotsSmem));
     stage_panels(s_panels, det);
+    // programmatic dependent launch: everything above overlapped the tail of the front-end kernel; its queue is read below
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int tid = threadIdx.x;
     const unsigned lane = lane_id();
@@ -1178,8 +1180,17 @@ int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, i
         cudaMemsetAsync(counters + 9, 0, sizeof(unsigned), s);     // adder drops
         cudaMemsetAsync(ticket, 0, sizeof(unsigned), s);
     }
-    GPET_LAUNCH("k_detector", s, k_detector<<<grid, kDetThreads, smem, s>>>(q2, det, tb, eabs, readout_depth, readout_policy, record_hits, hits, ev,
-                                                                       counters, ticket, seed, tune("GPET_REFILL_MIN", 4)));
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)kDetThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const int refill_min = tune("GPET_REFILL_MIN", 4);
+        GPET_LAUNCH("k_detector", s, cudaLaunchKernelEx(&cfg, k_detector, q2, det, tb, eabs, readout_depth, readout_policy, record_hits, hits, ev,
+                                                        counters, ticket, seed, refill_min));
+    }
     return 1;
 }
 
