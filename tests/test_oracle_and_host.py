@@ -320,6 +320,40 @@ def test_direction_table_never_drops_a_panel_the_exact_test_accepts(tmp_path, ge
     assert (pop.max() <= 4 and np.median(pop) <= 3) if geo == "config8" else np.median(pop) <= 18
 
 
+def test_direction_table_reference_sphere_follows_the_inputs(tmp_path):
+    # the table is built for (phantom box + source shapes | PSF records); it must widen with them and switch off when a
+    # photon's line is not bounded (positron range) or the panels do not fit a 32-bit mask
+    n = 8
+    mat = np.zeros((n, n, n), np.int32); den = np.ones((n, n, n), np.float32)
+    src = tmp_path / "src.txt"
+    src.write_text("1\nheader#\n1000 0 1 3 0 0 0.5 2 0\n")          # cylinder r 0.5, h 2 at x = 3
+    with api.Context(-1) as c:
+        assert c.direction_table() == (None, None)                        # nothing loaded
+        c.load_geometry(parity.EXAMPLE / "input" / "config8.geo")
+        c.set_phantom(mat, den, np.full(3, -0.5, np.float32), np.full(3, 1.0, np.float32))
+        _, ref0 = c.direction_table()
+        assert abs(ref0[3] - (np.sqrt(3) / 2 * 1.001 + 1e-3)) < 1e-6 and np.allclose(ref0[:3], 0)
+        c.load_isotopes(parity.EXAMPLE / "data" / "isotopes.txt")
+        c.load_source(src)
+        _, ref1 = c.direction_table()
+        assert abs(ref1[3] - ((3 + np.sqrt(0.25 + 1.0)) * 1.001 + 1e-3)) < 1e-5
+        c.set_transport(use_positron_range=1)
+        assert c.direction_table() == (None, None)
+        c.set_transport(use_positron_range=0)
+        refio.write_psf(tmp_path / "psf.dat", np.array([0.0, 7.0]), np.array([0.0, 0.0]), np.array([0.0, -2.0]), np.array([1.0, 2.0]),
+                        np.array([1.0, 0.0]), np.array([0.0, 1.0]), np.array([0.0, 0.0]), np.array([511e3, 511e3]))
+        c.load_psf(tmp_path / "psf.dat", 0, 1)
+        _, ref2 = c.direction_table()
+        assert abs(ref2[3] - (np.sqrt(49 + 4) * 1.001 + 1e-3)) < 1e-5      # PSF mode: the records, not the sources
+    from tools import gen_inputs
+    big = tmp_path / "ring40.geo"
+    big.write_text(gen_inputs.ring_geo(40, 50.0))
+    with api.Context(-1) as c:
+        c.load_geometry(big)
+        c.set_phantom(mat, den, np.full(3, -0.5, np.float32), np.full(3, 1.0, np.float32))
+        assert c.direction_table() == (None, None)                        # 40 panels do not fit the mask
+
+
 def test_c_example_compiles_as_c99_and_refuses_to_compute_without_a_device(tmp_path):
     # the header is plain C (no C++/torch types in the signatures): examples/c/digitize_replay.c builds with gcc -std=c99
     exe = tmp_path / "digitize_replay"
