@@ -180,6 +180,42 @@ def test_loader_errors_are_reported_not_fatal(tmp_path):
             c.load_tables(tmp_path / "nothing")
 
 
+def test_parsers_survive_truncated_and_corrupted_files(tmp_path):
+    # the reference exits (or reads garbage) on malformed input (CUDA_CALL / FILEEXIST macros, unchecked fscanf); the
+    # loaders here must report an error or accept the file -- never crash
+    rng = np.random.default_rng(0)
+    texts = {"in": (parity.EXAMPLE / "input_PET.in").read_text(), "geo": (parity.EXAMPLE / "input" / "config8.geo").read_text(),
+             "src": (parity.EXAMPLE / "input" / "source.txt").read_text(), "iso": (parity.EXAMPLE / "data" / "isotopes.txt").read_text()}
+    outcomes = {k: [0, 0] for k in texts}
+    for kind, text in texts.items():
+        for trial in range(120):
+            data = bytearray(text.encode())
+            if trial % 2 == 0:
+                data = data[: int(rng.integers(0, len(data)))]
+            else:
+                for _ in range(int(rng.integers(1, 12))):
+                    data[int(rng.integers(0, len(data)))] = int(rng.integers(0, 256))
+            f = tmp_path / f"{kind}.txt"
+            f.write_bytes(bytes(data))
+            with api.Context(-1) as c:
+                try:
+                    if kind == "in":
+                        c.load_config_file(f, base_dir=parity.EXAMPLE)
+                    elif kind == "geo":
+                        c.load_geometry(f)
+                        assert 0 <= c.panels().size <= 100000
+                    elif kind == "iso":
+                        c.load_isotopes(f)
+                    else:
+                        c.load_isotopes(parity.EXAMPLE / "data" / "isotopes.txt")
+                        c.load_source(f)
+                    outcomes[kind][0] += 1
+                except api.GpetError as e:
+                    assert e.code in (-1, -2, -6) and str(e)
+                    outcomes[kind][1] += 1
+    assert all(err > 0 for _, err in outcomes.values()), outcomes
+
+
 def test_psf_loader(tmp_path):
     rec = parity.gen_inputs.back_to_back_psf(1000)
     rec.tofile(tmp_path / "psf.dat")
