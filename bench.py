@@ -399,7 +399,7 @@ def main():
     st = m["e2e_stats"][-1]
     nframes = int(st.frames)
     h2d = nframes * 4096 + 64
-    d2h = int(st.singles * 48 + st.coincidences * 8 + 32 * 4 * st.frames)
+    d2h = int(st.singles * 48 + st.coincidences * (8 + 1) + 32 * 4 * st.frames)   # records, index pairs + class bytes, counters
 
     extra = None
     if not args.no_extra and world == 1 and args.source == DEFAULT_SOURCE:
@@ -468,11 +468,12 @@ def main():
                            "time_path": "fp64", "multi_gpu": "independent decay histories per rank (disjoint Philox keys), tallies all-reduced over NCCL"},
                 "clocks": clocks,
                 "e2e": {"value": m["e2e_pairs"] / (m["e2e_ms"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "timing": "wall clock around gpet_plan_frames + gpet_run (singles as 48-byte records and coincidences as index pairs into them, delivered to pinned host memory; the acquisition is planned as e2e_frames_per_step frames so that the copy of a frame overlaps the next frame's kernels), max over ranks"},
+                        "timing": "wall clock around gpet_plan_frames + gpet_run (singles as 48-byte records, coincidences as index pairs into them plus one class byte each, delivered to pinned host memory; the acquisition is planned as e2e_frames_per_step frames so that the copy of a frame overlaps the next frame's kernels), max over ranks"},
                 "gpu_launches": int(sum(s.kernel_launches for s in m["stats"])),
                 "roofline": roofline, "cpu_baseline": base,
                 "counters": {"pairs": int(s0.pairs), "hits": int(s0.hits), "events_adder": int(s0.events_adder),
                              "singles": int(s0.singles), "coincidences": int(s0.coincidences),
+                             "trues": int(s0.trues), "scatters": int(s0.scatters), "randoms": int(s0.randoms),
                              "coincidences_per_s": float(m["coinc"] / (m["total_ms"] * 1e-3))},
                 "extra": extra}
         os.write(json_fd, (json.dumps(line) + "\n").encode())

@@ -49,7 +49,7 @@ class DigitizerParams(C.Structure):
                 ("time_blur_sigma_us", C.c_float), ("coinc_window_us", C.c_float),
                 ("coinc_policy", C.c_int32), ("coinc_min_panel_diff", C.c_int32),
                 ("noise_mean_gap_us", C.c_float), ("noise_Emean_eV", C.c_float), ("noise_sigma_eV", C.c_float),
-                ("noise_interval_us", C.c_float)]
+                ("noise_interval_us", C.c_float), ("coinc_pair_shift", C.c_int32)]
 
 
 class TransportParams(C.Structure):
@@ -63,7 +63,8 @@ class Stats(C.Structure):
                 ("pairs", "photons_phantom_out", "photons_on_panel", "hits", "events_adder", "events_threshold",
                  "events_deadtime", "singles", "coincidences", "overflow_hits", "overflow_events", "overflow_adder",
                  "frames", "kernel_launches")] + \
-               [(n, C.c_double) for n in ("ms_source", "ms_phantom", "ms_detector", "ms_digitizer", "ms_total")]
+               [(n, C.c_double) for n in ("ms_source", "ms_phantom", "ms_detector", "ms_digitizer", "ms_total")] + \
+               [(n, C.c_uint64) for n in ("trues", "scatters", "randoms")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -124,6 +125,8 @@ _SIGS = {
     "gpet_fetch_hits": (C.c_int64, [_P, _P, C.c_int64]),
     "gpet_fetch_singles": (C.c_int64, [_P, _P, C.c_int64]),
     "gpet_fetch_coincidences": (C.c_int64, [_P, _P, C.c_int64]),
+    "gpet_fetch_coincidence_classes": (C.c_int64, [_P, _P, C.c_int64, _P]),
+    "gpet_mark_scattered": (C.c_int, [_P, _P, C.c_int64]),
     "gpet_last_counts": (C.c_int, [_P, _P]),
     "gpet_digitize": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
     "gpet_run": (C.c_int, [_P, C.c_char_p, C.POINTER(Stats)]),
@@ -132,6 +135,7 @@ _SIGS = {
     "gpet_result_coincidences": (C.c_int64, [_P, C.POINTER(_P)]),
     "gpet_set_coincidence_format": (C.c_int, [_P, C.c_int]),
     "gpet_result_coincidence_pairs": (C.c_int64, [_P, C.POINTER(_P)]),
+    "gpet_result_coincidence_classes": (C.c_int64, [_P, C.POINTER(_P)]),
     "gpet_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "gpet_get_spectrum": (C.c_int, [_P, _P, C.c_int]),
     "gpet_set_spectrum": (C.c_int, [_P, C.c_int, C.c_float, C.c_float]),
@@ -145,7 +149,7 @@ _SIGS = {
 _lib = None
 
 
-ABI_VERSION = 2   # GPET_ABI_VERSION of include/gpet_b200.h
+ABI_VERSION = 3   # GPET_ABI_VERSION of include/gpet_b200.h
 
 
 def lib():
@@ -446,6 +450,20 @@ class Context:
     def fetch_coincidences(self, cap=1 << 21):
         return self._fetch(self._l.gpet_fetch_coincidences, COINC_DTYPE, cap)
 
+    TRUE, SCATTER, RANDOM = 0, 1, 2   # coincidence classes
+
+    def fetch_coincidence_classes(self, cap=1 << 21):
+        """(classes uint8[n], totals uint64[3] = trues, scatters, randoms) of the last frame's coincidences."""
+        out = np.zeros(cap, np.uint8)
+        totals = np.zeros(3, np.uint64)
+        n = self._ck(self._l.gpet_fetch_coincidence_classes(self._h, _ptr(out), out.size, _ptr(totals)))
+        return out[:n], totals
+
+    def mark_scattered(self, parn):
+        """Replay only: photons (by gpet_event.parn) that scattered in the phantom; call after put_events."""
+        parn = np.ascontiguousarray(parn, np.int32)
+        self._ck(self._l.gpet_mark_scattered(self._h, _ptr(parn), parn.size))
+
     def last_counts(self):
         c = np.zeros(4, np.uint64)
         self._ck(self._l.gpet_last_counts(self._h, _ptr(c)))
@@ -501,6 +519,15 @@ class Context:
             return np.zeros((0, 2), np.uint32)
         buf = (C.c_char * (n * 8)).from_address(p.value)
         return np.frombuffer(buf, np.uint32, 2 * n).reshape(n, 2).copy()
+
+    def result_coincidence_classes(self):
+        """uint8 class per coincidence of the last run (0 true, 1 scatter, 2 random)."""
+        p = C.c_void_p()
+        n = self._ck(self._l.gpet_result_coincidence_classes(self._h, C.byref(p)))
+        if n == 0:
+            return np.zeros(0, np.uint8)
+        buf = (C.c_char * n).from_address(p.value)
+        return np.frombuffer(buf, np.uint8, n).copy()
 
     def stats(self):
         st = Stats()

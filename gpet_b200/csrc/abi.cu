@@ -146,6 +146,9 @@ int ensure_buffers(gpet_ctx* c) {
             CK(cudaMalloc(&p, (size_t)c->coinc_cap * sizeof(uint2)));
             c->allocs.push_back(p);
             c->pairs_slot[k] = p;
+            CK(cudaMalloc(&p, (size_t)c->coinc_cap));
+            c->allocs.push_back(p);
+            c->cls_slot[k] = p;
             CK(cudaMallocHost((void**)&c->h_slot_counters[k], 64 * sizeof(unsigned)));
             CK(cudaEventCreateWithFlags(&c->ev_counters[k], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c->ev_copied[k], cudaEventDisableTiming));
@@ -155,10 +158,19 @@ int ensure_buffers(gpet_ctx* c) {
         c->out_slot = 0;
         c->singles_aos = c->singles_slot[0];
         c->coinc_aos = c->coinc_slot[0];
+        c->cls_aos = c->cls_slot[0];
         c->stage_bytes = std::max(std::max(ce * sizeof(gpet_event), cp * sizeof(gpet_photon)), ch * sizeof(gpet_hit));
         CK(cudaMalloc(&p, c->stage_bytes));
         c->allocs.push_back(p);
         c->stage_aos = p;
+    }
+    {   // scatter tags: zeroed once, never cleared again (serial 0 is never used)
+        size_t nt = 1024;
+        while (nt < cp) nt <<= 1;
+        if ((r = dev_alloc(c, &c->d_scat_tag, nt))) return r;
+        CK(cudaMemset(c->d_scat_tag, 0, nt * sizeof(unsigned)));
+        c->scat_mask = (unsigned)(nt - 1);
+        c->scat_serial = 0;
     }
     if ((r = dev_alloc(c, &c->d_totals, 32))) return r;
     CK(cudaMemset(c->d_totals, 0, 32 * sizeof(unsigned long long)));
@@ -304,6 +316,7 @@ DetectorDev detector_dev(const gpet_ctx* c) {
     }
     // the bounding-sphere rejection in panel_entry needs Euclidean local coordinates: orthonormal axes on every panel
     d.dirmask = (c->in_run && c->dirmask_on) ? c->d_dirmask : nullptr;
+    d.scat_tag = c->d_scat_tag; d.scat_mask = c->scat_mask; d.scat_serial = c->scat_serial;
     d.prefilter = g.panels.size() <= 32;
     for (const gpet_panel& p : g.panels) {
         const double u[3][3] = {{p.UniXx, p.UniXy, p.UniXz}, {p.UniYx, p.UniYy, p.UniYz}, {p.UniZx, p.UniZy, p.UniZz}};
@@ -329,7 +342,17 @@ DigitizerDev digitizer_dev(const gpet_ctx* c) {
     d.moduleN = c->geo.moduleN; d.crystalN = c->geo.crystalN;
     d.noise_gap = p.noise_mean_gap_us; d.noise_Emean = p.noise_Emean_eV; d.noise_sigma = p.noise_sigma_eV;
     d.noise_interval = p.noise_interval_us;
+    d.pair_shift = std::min(std::max(p.coinc_pair_shift, 0), 31);
+    d.scat_tag = c->d_scat_tag; d.scat_mask = c->scat_mask; d.scat_serial = c->scat_serial;
     return d;
+}
+
+// New photons are about to reach the panel faces, or new events are put: tags of anything earlier must not match.
+void new_scatter_serial(gpet_ctx* c) {
+    if (++c->scat_serial == 0u) {   // wrapped after 2^32 frames: the one time the table is cleared
+        if (c->d_scat_tag) cudaMemsetAsync(c->d_scat_tag, 0, ((size_t)c->scat_mask + 1) * sizeof(unsigned), c->stream);
+        c->scat_serial = 1u;
+    }
 }
 
 void rebuild_majorants(gpet_ctx* c) {
@@ -444,6 +467,7 @@ void gpet_destroy(gpet_ctx* c) {
         if (c->res_singles.p) cudaFreeHost(c->res_singles.p);
         if (c->res_coinc.p) cudaFreeHost(c->res_coinc.p);
         if (c->res_pairs.p) cudaFreeHost(c->res_pairs.p);
+        if (c->res_cls.p) cudaFreeHost(c->res_cls.p);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         if (c->own_stream) cudaStreamDestroy(c->own_stream);
     }
@@ -835,6 +859,7 @@ int gpet_stage_detector(gpet_ctx* c) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((r = upload_geometry(c))) return r;
+    new_scatter_serial(c);
     c->stats.kernel_launches += launch_panel_entry(c->q[1], c->q[2], detector_dev(c), c->ws.counters, c->num_sms, c->stream);
     {
         const int nl = launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth, c->dig.readout_policy,
@@ -863,7 +888,10 @@ int gpet_stage_front(gpet_ctx* c, int64_t f) {
         fr = c->d_frames + f;
         npairs = fp.npairs;
     }
-    c->stats.kernel_launches += launch_front(fr, npairs, c->q[0], c->q[1], c->q[2], phantom_dev(c), tables_dev(c), detector_dev(c),
+    new_scatter_serial(c);
+    PhantomDev ph = phantom_dev(c);   // the fused front end tags a photon the moment it scatters (transport.cu mark_scattered)
+    ph.scat_tag = c->d_scat_tag; ph.scat_mask = c->scat_mask; ph.scat_serial = c->scat_serial;
+    c->stats.kernel_launches += launch_front(fr, npairs, c->q[0], c->q[1], c->q[2], ph, tables_dev(c), detector_dev(c),
                                              c->tr.eabs_eV, c->ws.counters, c->ws.hot, c->seed, c->num_sms, c->stream, !c->in_run);
     CK(cudaGetLastError());
     return GPET_OK;
@@ -895,6 +923,7 @@ int gpet_stage_digitize(gpet_ctx* c) {
     out.singles = c->singles_aos;
     out.singles_cap = (unsigned)c->cap_events;
     out.coinc_cap = c->coinc_cap;
+    out.cls = c->cls_aos;
     if (c->in_run && c->early_copy) {
         out.h_singles_count = c->h_slot_counters[c->out_slot] + 48;   // a spare word of the slot's pinned block
         out.ev_after_emit = c->ev_emit[c->out_slot];
@@ -944,6 +973,7 @@ int gpet_put_photons(gpet_ctx* c, int which, const gpet_photon* in, int64_t n) {
     if ((r = ensure_buffers(c))) return r;
     if ((uint64_t)n > c->cap_photons) return fail(c, GPET_ERR_CAPACITY, "photon batch exceeds capacity");
     if (n) CK(cudaMemcpyAsync(c->stage_aos, in, (size_t)n * sizeof(gpet_photon), cudaMemcpyHostToDevice, c->stream));
+    if (which == 2) new_scatter_serial(c);   // photons put on the panel faces directly carry no scatter tags
     c->stats.kernel_launches += launch_photons_aos_to_queue(c->stage_aos, c->q[which], (unsigned)n, c->stream);
     CK(cudaGetLastError());
     return GPET_OK;
@@ -968,6 +998,7 @@ int gpet_put_events(gpet_ctx* c, const gpet_event* in, int64_t n) {
     if ((r = ensure_buffers(c))) return r;
     if ((uint64_t)n > c->cap_events) return fail(c, GPET_ERR_CAPACITY, "event list exceeds capacity");
     // the device buffer holds the records in the file layout: a plain copy
+    new_scatter_serial(c);   // replayed events: no photon is tagged as scattered unless gpet_mark_scattered says so
     const unsigned n32 = (unsigned)n;
     if (n) CK(cudaMemcpyAsync(c->ev.rec, in, (size_t)n * sizeof(gpet_event), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->ev.count, &n32, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
@@ -1032,6 +1063,37 @@ int64_t gpet_fetch_coincidences(gpet_ctx* c, gpet_coincidence* out, int64_t cap)
     CK(cudaMemcpyAsync(out, c->coinc_aos, (size_t)n * sizeof(gpet_coincidence), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return n;
+}
+
+int64_t gpet_fetch_coincidence_classes(gpet_ctx* c, uint8_t* out, int64_t cap, uint64_t totals[3]) {
+    NEED_DEVICE();
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((r = read_counters(c))) return r;
+    if (totals)
+        for (int k = 0; k < 3; k++) totals[k] = c->h_counters[12 + k];
+    int64_t n = std::min<int64_t>(std::min<unsigned>(c->h_counters[4], c->coinc_cap), cap);
+    if (n <= 0 || !out) return 0;
+    CK(cudaMemcpyAsync(out, c->cls_aos, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return n;
+}
+
+int gpet_mark_scattered(gpet_ctx* c, const int32_t* parn, int64_t n) {
+    NEED_DEVICE();
+    ProfScope prof(c);
+    if (n < 0 || (n > 0 && !parn)) return GPET_ERR_ARG;
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((uint64_t)n * sizeof(int32_t) > c->stage_bytes) return fail(c, GPET_ERR_CAPACITY, "scatter list exceeds the staging buffer");
+    if (n == 0) return GPET_OK;
+    if (c->scat_serial == 0u) new_scatter_serial(c);
+    CK(cudaMemcpyAsync(c->stage_aos, parn, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    c->stats.kernel_launches += launch_mark_scattered(static_cast<const int*>(c->stage_aos), (unsigned)n, c->d_scat_tag, c->scat_mask,
+                                                      c->scat_serial, c->stream);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));   // the caller's list may go away
+    return GPET_OK;
 }
 
 int gpet_last_counts(gpet_ctx* c, uint64_t counts[4]) {
@@ -1170,6 +1232,9 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
     st.events_deadtime += h[2];
     st.singles += h[3];
     st.coincidences += h[4];
+    st.trues += h[12];
+    st.scatters += h[13];
+    st.randoms += h[14];
     st.overflow_adder += h[9];
     if (n_hits > c->hits.capacity) st.overflow_hits += n_hits - c->hits.capacity;
     if (n_ev > c->ev.capacity) st.overflow_events += n_ev - c->ev.capacity;
@@ -1185,18 +1250,25 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
     const size_t rec_c = as_pairs ? 2 * sizeof(uint32_t) : sizeof(gpet_coincidence);
     if (!c->early_copy && (r = arena_reserve(c, c->res_singles, ns * sizeof(gpet_event)))) return r;
     if (want_coinc && (r = arena_reserve(c, arena_c, nc * rec_c))) return r;
+    if (want_coinc && (r = arena_reserve(c, c->res_cls, nc))) return r;
     char* dst_s = c->early_copy ? dst_early : c->res_singles.p + c->res_singles.size;
     char* dst_c = want_coinc ? arena_c.p + arena_c.size : nullptr;
+    char* dst_k = want_coinc ? c->res_cls.p + c->res_cls.size : nullptr;
     const size_t first_single = c->res_singles.size / sizeof(gpet_event);
     if (c->early_copy && ns_early != ns) return fail(c, GPET_ERR_CUDA, "singles count changed after the emit kernel (internal error)");
     if (ns && !c->early_copy)
         CK(cudaMemcpyAsync(dst_s, c->singles_slot[slot], ns * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->copy_stream));
-    if (want_coinc && nc)
+    if (want_coinc && nc) {
         CK(cudaMemcpyAsync(dst_c, as_pairs ? c->pairs_slot[slot] : c->coinc_slot[slot], nc * rec_c, cudaMemcpyDeviceToHost,
                            c->copy_stream));
+        CK(cudaMemcpyAsync(dst_k, c->cls_slot[slot], nc, cudaMemcpyDeviceToHost, c->copy_stream));
+    }
     CK(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
     c->res_singles.size += ns * sizeof(gpet_event);
-    if (want_coinc) arena_c.size += nc * rec_c;
+    if (want_coinc) {
+        arena_c.size += nc * rec_c;
+        c->res_cls.size += nc;
+    }
     if (!rs.od.empty()) {
         // file dumps with the reference layouts (gPET.cu:367-383, 424): this path runs frame by frame (no pipelining)
         CK(cudaStreamSynchronize(c->copy_stream));
@@ -1227,6 +1299,11 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
                 }
             }
             fclose(fc);
+            // one class byte per record of coincidences.dat (0 true, 1 scatter, 2 random)
+            FILE* fk = fopen(join_path(rs.od, "coincidences_class.dat").c_str(), "ab");
+            if (!fk) return fail(c, GPET_ERR_IO, "cannot open coincidences_class.dat for appending");
+            if (nc) fwrite(dst_k, 1, nc, fk);
+            fclose(fk);
         }
     }
     return GPET_OK;
@@ -1366,6 +1443,7 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
     c->res_singles.size = 0;
     c->res_coinc.size = 0;
     c->res_pairs.size = 0;
+    c->res_cls.size = 0;
     c->coinc_expanded.clear();
     CK(cudaMemsetAsync(c->d_pair_base, 0, 2 * sizeof(unsigned), c->stream));
     struct InRun {   // gpet_stage_digitize reads these while the run is in flight
@@ -1395,6 +1473,7 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
         c->out_slot = slot;
         c->singles_aos = c->singles_slot[slot];
         c->coinc_aos = c->coinc_slot[slot];
+        c->cls_aos = c->cls_slot[slot];
         if (k >= 2 && !resident) CK(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
         // one memset clears every counter, ticket, status word and slice counter of the frame
         CK(cudaMemsetAsync(c->ws.frame_state, 0, c->ws.frame_state_bytes, c->stream));
@@ -1538,6 +1617,12 @@ int gpet_set_psf_output(gpet_ctx* c, int mode) {
     if (!c || mode < 0 || mode > 2) return GPET_ERR_ARG;
     c->psf_output = mode;
     return GPET_OK;
+}
+
+int64_t gpet_result_coincidence_classes(gpet_ctx* c, const uint8_t** ptr) {
+    if (!c || !ptr) return GPET_ERR_ARG;
+    *ptr = reinterpret_cast<const uint8_t*>(c->res_cls.p);
+    return (int64_t)c->res_cls.size;
 }
 
 int64_t gpet_result_coincidence_pairs(gpet_ctx* c, const uint32_t** ptr) {

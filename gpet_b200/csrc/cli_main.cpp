@@ -48,7 +48,9 @@ int main(int argc, char** argv) {
            "counts of events after thresholder is %llu\ncounts of events after deadtime is %llu\ncounts of singles is %llu\n",
            (unsigned long long)st.pairs, (unsigned long long)st.hits, (unsigned long long)st.events_adder,
            (unsigned long long)st.events_threshold, (unsigned long long)st.events_deadtime, (unsigned long long)st.singles);
-    if (cwin > 0.f) printf("counts of coincidences is %llu\n", (unsigned long long)st.coincidences);
+    if (cwin > 0.f)
+        printf("counts of coincidences is %llu (trues %llu, scatters %llu, randoms %llu)\n", (unsigned long long)st.coincidences,
+               (unsigned long long)st.trues, (unsigned long long)st.scatters, (unsigned long long)st.randoms);
     printf("Simulation time: %f s. (device %f ms, %llu frames, %llu kernel launches)\n",
            std::chrono::duration<double>(t2 - t1).count(), st.ms_total, (unsigned long long)st.frames,
            (unsigned long long)st.kernel_launches);

@@ -63,6 +63,12 @@ struct gpet_ctx {
     void* singles_slot[2] = {nullptr, nullptr};
     void* coinc_slot[2] = {nullptr, nullptr};
     void* pairs_slot[2] = {nullptr, nullptr};            // uint2 index pairs (GPET_COINC_PAIRS)
+    void* cls_slot[2] = {nullptr, nullptr};              // one class byte per coincidence (0 true, 1 scatter, 2 random)
+    void* cls_aos = nullptr;                             // = cls_slot[out_slot]
+    // scatter tags (DetectorDev::scat_tag): table of a power of two >= cap_photons words; the serial is bumped whenever
+    // new photons reach the panel faces or new events are put, so stale tags never match
+    unsigned* d_scat_tag = nullptr;
+    unsigned scat_mask = 0, scat_serial = 0;
     unsigned* d_pair_base = nullptr;                     // [2]: singles of the run's earlier frames, alternating by frame
     int psf_output = 0;                                  // OUTPUTPSF of the reference (gpet_set_psf_output)
     int coinc_format = 0;                                // GPET_COINC_RECORDS / GPET_COINC_PAIRS (gpet_run only)
@@ -103,6 +109,7 @@ struct gpet_ctx {
     bool planned = false;
     PinnedArena res_singles, res_coinc;   // gpet_event / gpet_coincidence records of the last gpet_run
     PinnedArena res_pairs;                // uint32 index pairs of the last gpet_run (GPET_COINC_PAIRS)
+    PinnedArena res_cls;                  // class bytes of the last gpet_run's coincidences
     std::vector<char> coinc_expanded;     // records built on demand from res_pairs + res_singles
     gpet_stats stats{};
     uint64_t last_counts[4] = {0, 0, 0, 0};

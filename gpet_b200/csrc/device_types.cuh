@@ -100,6 +100,13 @@ struct DetectorDev {
     // panel that a photon flying in a direction of that cell can possibly enter, GIVEN that its line passes the
     // reference sphere the table was built for (phantom box + source shapes / PSF points).  Conservative.
     const unsigned* dirmask;
+    // Scatter tags (coincidence classification): a photon that enters a panel after at least one
+    // Compton or Rayleigh interaction in the phantom stores the serial number of its frame at scat_tag[parn & scat_mask];
+    // the coincidence sorter finds it there by the single's parn.  A frame's photon numbers are contiguous and the table
+    // holds at least a frame's photons, so slots are unique within a frame; the serial changes with every frame, so the
+    // table is never cleared.  nullptr: off.
+    unsigned* scat_tag;
+    unsigned scat_mask, scat_serial;
 };
 constexpr int kDirBins = 32;
 
@@ -111,6 +118,9 @@ struct PhantomDev {
     float dx, dy, dz;      // voxel size
     int rec_on;            // 1: photons leaving the phantom are moved onto the PSF-recording sphere (RECORDPSF == -1, gPET_kernals.cu:288-294)
     float rec[4];          // sphere centre x, y, z and radius (input_PET.in field 14)
+    // scatter tags, set for the fused front end only (see DetectorDev::scat_tag; the staged path tags at panel entry)
+    unsigned* scat_tag;
+    unsigned scat_mask, scat_serial;
 };
 
 struct TablesDev {
@@ -150,6 +160,10 @@ struct DigitizerDev {
     float noise_gap, noise_Emean, noise_sigma, noise_interval;   // addnoise (gPET_kernals.cu:699-735); gap <= 0: off
     int npanels;
     int moduleN, crystalN;
+    // coincidence classes (k_coinc): same annihilation iff eventid >> pair_shift agree; scatter tags as in DetectorDev
+    int pair_shift;
+    const unsigned* scat_tag;
+    unsigned scat_mask, scat_serial;
 };
 
 }  // namespace gpet

@@ -752,15 +752,33 @@ __device__ __forceinline__ unsigned coincidences_of(const SinglesView& v, unsign
     }
 }
 
+// Coincidence classes (the reference has neither a sorter nor a scatter flag, F2 / F11):
+//   2 random  -- the two singles come from different annihilations (eventid >> pair_shift differ), or one of them is a
+//                noise single (parn == -1, k_noise)
+//   1 scatter -- same annihilation, and at least one of the two photons interacted in the phantom (its scatter tag,
+//                DetectorDev::scat_tag, carries this frame's serial)
+//   0 true    -- same annihilation, both photons unscattered in the phantom
+__device__ __forceinline__ bool photon_scattered(const DigitizerDev& p, int parn) {
+    return p.scat_tag != nullptr && parn != -1 && __ldg(p.scat_tag + ((unsigned)parn & p.scat_mask)) == p.scat_serial;
+}
+__device__ __forceinline__ unsigned coincidence_class(const DigitizerDev& p, int parn_a, int eid_a, bool a_scat, int parn_b, int eid_b) {
+    if (parn_a == -1 || parn_b == -1 || (eid_a >> p.pair_shift) != (eid_b >> p.pair_shift)) return 2u;
+    return (a_scat || photon_scattered(p, parn_b)) ? 1u : 0u;
+}
+
 // Index pairs into the run's singles list (pair_base = singles of the run's earlier frames, kept on the device) and,
-// when `out` is given, the two 48-byte records side by side.
+// when `out` is given, the two 48-byte records side by side; `cls` (optional) receives one class byte per coincidence.
 __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__ s, const double* __restrict__ stime,
                                                     const int* __restrict__ span, DigitizerDev p, unsigned* __restrict__ counters,
                                                     unsigned singles_cap, unsigned* __restrict__ status,
                                                     gpet_coincidence* __restrict__ out, uint2* __restrict__ pairs, unsigned cap,
-                                                    const unsigned* __restrict__ base_in, unsigned* __restrict__ base_out) {
+                                                    const unsigned* __restrict__ base_in, unsigned* __restrict__ base_out,
+                                                    unsigned char* __restrict__ cls) {
     pdl_wait();
     __shared__ unsigned s_tile;
+    __shared__ unsigned s_cls[3];
+    unsigned n_cls[3] = {0u, 0u, 0u};   // this thread's true / scatter / random coincidences
+    if (threadIdx.x < 3) s_cls[threadIdx.x] = 0u;   // ordered before its use by the barriers of the tile loop and of the tally
     __shared__ double s_t[kScanTile + 2 * kHalo];
     __shared__ int s_p[kScanTile + 2 * kHalo];
     __shared__ __align__(16) unsigned short s_cnt[kScanTile];
@@ -829,18 +847,24 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
             const unsigned a = a0 + k;
             unsigned o = sc.excl[k], left = c[k];
             const double tend = v.t(a) + W;
+            // the opener's photon number and annihilation number (words 0 and 5 of its record), its scatter tag
+            const int4* pa = reinterpret_cast<const int4*>(s + a);
+            const int4 ra0 = __ldg(pa), ra1 = __ldg(pa + 1);
+            const bool a_scat = photon_scattered(p, ra0.x);
             for (unsigned b = a + 1; left && b < n && v.t(b) < tend; b++) {
                 if (!pair_ok(v, a, b, p)) continue;
                 left--;
+                const int4* pb = reinterpret_cast<const int4*>(s + b);
+                const int4 rb0 = __ldg(pb), rb1 = __ldg(pb + 1);
+                const unsigned cl = coincidence_class(p, ra0.x, ra1.y, a_scat, rb0.x, rb1.y);
+                n_cls[0] += cl == 0u ? 1u : 0u; n_cls[1] += cl == 1u ? 1u : 0u; n_cls[2] += cl == 2u ? 1u : 0u;
                 if (o < cap) {
                     if (pairs) pairs[o] = make_uint2(pair_base + a, pair_base + b);
+                    if (cls) cls[o] = (unsigned char)cl;
                     if (out) {   // 2 x 48-byte records copied as 6 x 16 B from the singles list
-                        const int4* pa = reinterpret_cast<const int4*>(s + a);
-                        const int4* pb = reinterpret_cast<const int4*>(s + b);
-                        const int4 a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
-                        const int4 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
+                        const int4 ra2 = __ldg(pa + 2), rb2 = __ldg(pb + 2);
                         int4* po = reinterpret_cast<int4*>(out + o);
-                        po[0] = a0; po[1] = a1; po[2] = a2; po[3] = b0; po[4] = b1; po[5] = b2;
+                        po[0] = ra0; po[1] = ra1; po[2] = ra2; po[3] = rb0; po[4] = rb1; po[5] = rb2;
                     }
                 }
                 o++;
@@ -854,6 +878,14 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
         printf("coinc block %d: ticket %lld stage %lld count %lld scan %lld emit %lld cycles\n", blockIdx.x, ph[1] - ph[0], ph[2] - ph[1],
                ph[3] - ph[2], ph[4] - ph[3], ph[5] - ph[4]);
 #endif
+    // class tallies: one add per block and class (counters[12..14] = trues, scatters, randoms)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const unsigned w = warp_sum(n_cls[k]);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cls[k], w);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3 && s_cls[threadIdx.x]) atomicAdd(&counters[12 + threadIdx.x], s_cls[threadIdx.x]);
 }
 
 }  // namespace
@@ -903,6 +935,19 @@ int launch_publish_counters(const unsigned* counters, const unsigned* hot, unsig
     return 1;
 }
 
+// gpet_mark_scattered: scatter tags for a caller's list of photon numbers (replayed events carry no transport history)
+__global__ void k_mark_scattered(const int* __restrict__ parn, unsigned n, unsigned* __restrict__ tag, unsigned mask, unsigned serial) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (parn[i] != -1) tag[(unsigned)parn[i] & mask] = serial;
+}
+
+int launch_mark_scattered(const int* parn, unsigned n, unsigned* tag, unsigned mask, unsigned serial, cudaStream_t s) {
+    if (n == 0 || tag == nullptr) return 0;
+    const int grid = (int)std::min<unsigned>((n + kThreads - 1) / kThreads, 1024u);
+    GPET_LAUNCH("k_mark_scattered", s, k_mark_scattered<<<grid, kThreads, 0, s>>>(parn, n, tag, mask, serial));
+    return 1;
+}
+
 int launch_noise(EventBuf ev, const DigitizerDev& p, double t_lo_us, double t_hi_us, uint64_t seed, int num_sms, cudaStream_t s) {
     if (!(p.noise_gap > 0.f) || !(p.noise_interval > 0.f) || !(t_hi_us > t_lo_us)) return 0;
     const double iv = (double)p.noise_interval;
@@ -942,6 +987,7 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
                                                // never run in the same frame)
     if (reset) {   // the digitizer's share of the frame state: counters[0..7], then everything behind the counter block
         cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned), s);
+        cudaMemsetAsync(ws.counters + 12, 0, 3 * sizeof(unsigned), s);   // coincidence class tallies
         cudaMemsetAsync(ws.counters + 64, 0, (size_t)(ws.hot - (ws.counters + 64)) * sizeof(unsigned), s);   // not the hot block: it holds the event count
     }
     TimeRange tr;
@@ -986,7 +1032,8 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
     if (p.cwin > 0.f && (out.coinc || out.pairs)) {
         GPET_LAUNCH("k_coinc", s, launch_pdl(k_coinc, g_coinc, kThreads, s, singles, ws.stime, ws.span, p, ws.counters, out.singles_cap, ws.scan_status[1],
                                                                   static_cast<gpet_coincidence*>(out.coinc), static_cast<uint2*>(out.pairs),
-                                                                  out.coinc_cap, out.pair_base_in, out.pair_base_out));
+                                                                  out.coinc_cap, out.pair_base_in, out.pair_base_out,
+                                                                  static_cast<unsigned char*>(out.cls)));
         launches++;
     }
     return launches;

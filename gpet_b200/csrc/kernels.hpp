@@ -43,8 +43,8 @@ struct DigitizerWorkspace {
     int* span;
     unsigned int* coinc_cnt;       // per single: coincidences it opens
     // [0] n_in [1] after thresholder [2] after deadtime [3] singles [4] coincidences [6],[7] tile tickets of the two
-    // compactions [5] time sort fell back to LSD radix [8] photons on a panel [9] adder drops [10],[11] photon tickets of
-    // k_detector / k_front; [16..19] queue 0, queue 1, hits, events counts, [21] queue 2
+    // compactions [5] time sort fell back to LSD radix [8] photons on a panel [9] adder drops [12..14] true / scatter /
+    // random coincidences; [16..19] queue 0, queue 1, hits, events counts, [21] queue 2
     unsigned int* counters;
     // Hot counters, one per 4 KB of their own: warp-aggregated atomics on ONE 128-byte line serialise at 0.67 ns each
     // whatever word they hit (tools/microbench/latency.cu), which bounded k_front and k_detector while tickets and queue
@@ -62,6 +62,7 @@ struct DigitizerOut {
     void* coinc;                   // 96-byte coincidence records, or nullptr
     void* pairs;                   // uint2 index pairs into the run's singles list, or nullptr
     unsigned int coinc_cap;
+    void* cls;                     // one class byte per coincidence (0 true, 1 scatter, 2 random), or nullptr
     const unsigned int* pair_base_in;   // singles of the run's earlier frames (device word), nullptr = 0
     unsigned int* pair_base_out;        // receives *pair_base_in + this frame's singles, or nullptr
     // optional: right after k_emit_singles the singles count is copied to this pinned host word and the event is
@@ -97,6 +98,9 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
 int launch_publish_counters(const unsigned* counters, const unsigned* hot, unsigned* h_dst, cudaStream_t s);
 // addnoise: events of the noise process with t_lo <= t < t_hi appended to ev (digitizer.cu)
 int launch_noise(EventBuf ev, const DigitizerDev& p, double t_lo_us, double t_hi_us, uint64_t seed, int num_sms, cudaStream_t s);
+
+// scatter tags of a host-supplied list of photon numbers (gpet_mark_scattered)
+int launch_mark_scattered(const int* parn, unsigned n, unsigned* tag, unsigned mask, unsigned serial, cudaStream_t s);
 
 // ---- transport (transport.cu) ----------------------------------------------------------------------------
 int launch_source(const SourceDev* frame_dev, unsigned long long npairs, PhantomDev ph, PhotonQueue q0,

@@ -304,6 +304,17 @@ __device__ __forceinline__ float record_distance(const PhantomDev& ph, const Pho
     return (-b + sqrtf(disc)) / (2 * a);
 }
 
+// Scatter tags (DetectorDev::scat_tag): read back by the coincidence sorter through the single's parn.  Plain stores: the
+// slot belongs to this photon alone within its frame.  The fused front end tags a photon when it scatters (its nscat
+// then never has to stay in a register up to the panel search); the staged path carries nscat through queue 1 and tags
+// at panel entry.
+__device__ __forceinline__ void mark_scattered(const PhantomDev& ph, int parn) {
+    if (ph.scat_tag != nullptr) ph.scat_tag[(unsigned)parn & ph.scat_mask] = ph.scat_serial;
+}
+__device__ __forceinline__ void mark_scattered(const DetectorDev& det, int parn, int nscat) {
+    if (nscat > 0 && det.scat_tag != nullptr) det.scat_tag[(unsigned)parn & det.scat_mask] = det.scat_serial;
+}
+
 // One Woodcock flight (gPET_kernals.cu:277-335).  Returns 0: still inside, 1: the photon leaves the stage alive (escaped,
 // keeping the overshoot position -- SURVEY quirk 2 -- or below the absorption energy after a Compton, which the reference
 // still hands to the detector stage -- quirk 3), 2: photo-absorbed (tof = -0.5 in the reference).
@@ -340,6 +351,7 @@ __device__ __forceinline__ int phantom_flight(Photon& p, Philox& rng, const Phan
         float phi = kTwoPi * u01(r.w);
         p.E *= efrac;
         p.nscat++;
+        mark_scattered(ph, p.parn);
         if (p.E < eabs) return 1;
         rotate_dir(p.vx, p.vy, p.vz, costh, phi);
         return 0;
@@ -349,6 +361,7 @@ __device__ __forceinline__ int phantom_flight(Photon& p, Philox& rng, const Phan
         float costh = surface_lookup(tb.rayff, mat, tb.rl_ncp, tb.rl_ne, p.E * tb.rl_ide, u01(r.z) * tb.rl_idcp);
         float phi = kTwoPi * u01(r.w);
         p.nscat++;
+        mark_scattered(ph, p.parn);
         rotate_dir(p.vx, p.vy, p.vz, costh, phi);
         return 0;
     }
@@ -562,10 +575,12 @@ __global__ void __launch_bounds__(kThreads) k_panel_entry(PhotonQueue q1, Detect
         float4 pe = make_float4(0, 0, 0, 0), ov = make_float4(0, 0, 0, 0);
         double t = 0.0;
         int2 id = make_int2(0, 0);
+        int nscat = 0;
         if (i < n) {
             Photon p;
             const float4 a = q1.pos_e[i], dn = q1.dir_n[i];
             p.x = a.x; p.y = a.y; p.z = a.z; p.E = a.w; p.vx = dn.x; p.vy = dn.y; p.vz = dn.z;
+            nscat = __float_as_int(dn.w);
             p.t = q1.t[i];
             id = q1.ids[i];
             if (p.t > 0.0) ok = panel_entry(s_panels, det, p, pe, ov, t);
@@ -573,6 +588,7 @@ __global__ void __launch_bounds__(kThreads) k_panel_entry(PhotonQueue q1, Detect
         unsigned slot = warp_reserve(q2.count, ok ? 1u : 0u);
         if (ok) {
             n_on_panel++;
+            mark_scattered(det, id.y, nscat);
             if (slot < q2.capacity) {
                 q2.pos_e[slot] = pe;
                 q2.dir_n[slot] = ov;

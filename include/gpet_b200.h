@@ -25,7 +25,9 @@
 extern "C" {
 #endif
 
-#define GPET_ABI_VERSION 2  /* 2: gpet_transport_params + record_psf / record_sphere, gpet_digitizer_params + noise_*, gpet_set_psf_output, gpet_stage_noise */
+#define GPET_ABI_VERSION 3  /* 2: gpet_transport_params + record_psf / record_sphere, gpet_digitizer_params + noise_*, gpet_set_psf_output, gpet_stage_noise
+                             * 3: coincidence classes: gpet_digitizer_params + coinc_pair_shift, gpet_stats + trues / scatters / randoms,
+                             *    gpet_fetch_coincidence_classes, gpet_result_coincidence_classes, gpet_mark_scattered */
 
 typedef enum gpet_status {
     GPET_OK = 0,
@@ -114,6 +116,10 @@ typedef struct gpet_digitizer_params {
      * whole detector, drawn per time slice of noise_interval_us, E ~ N(noise_Emean, noise_sigma), uniform crystal.
      * noise_mean_gap_us <= 0 disables it. */
     float   noise_mean_gap_us, noise_Emean_eV, noise_sigma_eV, noise_interval_us;
+    /* coincidence classes: two singles belong to the same annihilation iff eventid >> coinc_pair_shift agree.  0 for the
+     * isotope source and the positron PSF (both photons carry the pair's eventid, gPET_kernals.cu:546-547, 590-591);
+     * 1 for a photon PSF whose records 2k, 2k+1 are the two photons of pair k (eventid = record index, initialize.cu:103). */
+    int32_t coinc_pair_shift;
 } gpet_digitizer_params;
 
 /* Transport parameters = input_PET.in fields 2, 12, 15, 17 (main.cu:57-60, 117-120, 135-147). */
@@ -144,6 +150,10 @@ typedef struct gpet_stats {
     uint64_t frames;
     uint64_t kernel_launches;  /* launches of this library's own kernels */
     double   ms_source, ms_phantom, ms_detector, ms_digitizer, ms_total; /* CUDA-event times */
+    /* coincidence classes (extension): trues + scatters + randoms == coincidences */
+    uint64_t trues;            /* same annihilation, neither photon interacted in the phantom */
+    uint64_t scatters;         /* same annihilation, at least one photon Compton- or Rayleigh-scattered in the phantom */
+    uint64_t randoms;          /* different annihilations, or a noise single */
 } gpet_stats;
 
 /* ---- lifecycle ---------------------------------------------------------------------------------------- */
@@ -255,6 +265,18 @@ int64_t gpet_fetch_events(gpet_ctx* ctx, gpet_event* out, int64_t cap);    /* po
 int64_t gpet_fetch_hits(gpet_ctx* ctx, gpet_hit* out, int64_t cap);
 int64_t gpet_fetch_singles(gpet_ctx* ctx, gpet_event* out, int64_t cap);   /* "singles.dat" of the last frame */
 int64_t gpet_fetch_coincidences(gpet_ctx* ctx, gpet_coincidence* out, int64_t cap);
+/* Coincidence classes of the last frame (extension; the reference has no sorter, F2, and no scatter flag,
+ * F11): one byte per record of gpet_fetch_coincidences, 0 true / 1 scatter / 2 random.  Random = the two singles stem
+ * from different annihilations (eventid >> coinc_pair_shift differ) or one is a noise single (parn == -1); scatter =
+ * same annihilation and at least one of the two photons had a Compton or Rayleigh interaction in the phantom
+ * (gPET_kernals.cu:304-334) before it entered its panel; true = the rest.  totals (may be NULL) = {trues, scatters,
+ * randoms} of the frame, counted over all coincidences even when the record buffer overflowed; out may be NULL. */
+int64_t gpet_fetch_coincidence_classes(gpet_ctx* ctx, uint8_t* out, int64_t cap, uint64_t totals[3]);
+/* Replay (gpet_put_events -> gpet_stage_digitize) has no transport history: this marks the photons with the given
+ * photon numbers (gpet_event.parn) as scattered in the phantom.  Call after gpet_put_events, which forgets all marks;
+ * the photon numbers of one event list must be distinct modulo the photon capacity rounded up to a power of two (true
+ * for the contiguous numbers the source and PSF stages assign). */
+int gpet_mark_scattered(gpet_ctx* ctx, const int32_t* parn, int64_t n);
 /* counts[0..3] = events in, after thresholder, after deadtime, singles (gPET.cu:382,398,415,423). */
 int gpet_last_counts(gpet_ctx* ctx, uint64_t counts[4]);
 
@@ -289,6 +311,10 @@ int gpet_set_coincidence_format(gpet_ctx* ctx, int format);
 int gpet_set_psf_output(gpet_ctx* ctx, int mode);
 /* *ptr = pairs (2 x uint32 each: earlier single, later single); returns their number (0 in GPET_COINC_RECORDS mode). */
 int64_t gpet_result_coincidence_pairs(gpet_ctx* ctx, const uint32_t** ptr);
+/* *ptr = one class byte per coincidence of the run, in the order of gpet_result_coincidences / _pairs (0 true,
+ * 1 scatter, 2 random; see gpet_fetch_coincidence_classes); returns their number.  gpet_run(output_dir) also appends
+ * them to coincidences_class.dat.  The totals are the trues, scatters and randoms fields of gpet_stats. */
+int64_t gpet_result_coincidence_classes(gpet_ctx* ctx, const uint8_t** ptr);
 int gpet_get_stats(const gpet_ctx* ctx, gpet_stats* stats);
 /* Energy spectrum tally of the accumulated singles (nbins over [emin, emax)), kept on device during the run;
  * this is what multi-GPU runs all-reduce. */

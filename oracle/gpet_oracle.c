@@ -876,3 +876,34 @@ int64_t orc_digitize(const orc_event* in, int64_t n, const orc_digi_params* p, o
     return cnt;
 }
 
+
+/* Coincidence classes (extension; the reference has neither a coincidence sorter, SURVEY F2, nor a scatter flag, F11 --
+ * parity for this function is against this specification only).  One byte per coincidence record:
+ *   2 random  : the singles stem from different annihilations (eventid >> pair_shift differ) or one is a noise single
+ *               (parn == -1, addnoise gPET_kernals.cu:699-735 has no particle)
+ *   1 scatter : same annihilation and at least one of the two photons is in `scattered` (photon numbers with a Compton
+ *               or Rayleigh interaction in the phantom, the nscat > 0 photons of orc_phantom; gPET_kernals.cu:304-334)
+ *   0 true    : the rest
+ * totals[0..2] = trues, scatters, randoms. */
+static int cmp_i32(const void* a, const void* b) {
+    const int32_t x = *(const int32_t*)a, y = *(const int32_t*)b;
+    return x < y ? -1 : x > y;
+}
+void orc_classify(const orc_coinc* co, int64_t n, const int32_t* scattered, int64_t nscat, int32_t pair_shift, uint8_t* cls,
+                  uint64_t totals[3]) {
+    int32_t* sorted = (int32_t*)malloc(sizeof(int32_t) * (size_t)(nscat > 0 ? nscat : 1));
+    if (nscat > 0) memcpy(sorted, scattered, sizeof(int32_t) * (size_t)nscat);
+    qsort(sorted, (size_t)(nscat > 0 ? nscat : 0), sizeof(int32_t), cmp_i32);
+    totals[0] = totals[1] = totals[2] = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const orc_event *a = &co[i].a, *b = &co[i].b;
+        uint8_t c;
+        if (a->parn == -1 || b->parn == -1 || (a->eventid >> pair_shift) != (b->eventid >> pair_shift)) c = 2;
+        else if (nscat > 0 && (bsearch(&a->parn, sorted, (size_t)nscat, sizeof(int32_t), cmp_i32) ||
+                               bsearch(&b->parn, sorted, (size_t)nscat, sizeof(int32_t), cmp_i32))) c = 1;
+        else c = 0;
+        if (cls) cls[i] = c;
+        totals[c]++;
+    }
+    free(sorted);
+}

@@ -190,3 +190,13 @@ def digitize(events, params: DigiParams, want_coinc=True):
                             C.byref(nc))
     assert nc.value <= ccap
     return out[:ns], counts, co[:nc.value]
+
+
+def classify(coincidences, scattered_parn, pair_shift=0):
+    """(classes uint8[n], totals uint64[3]): 0 true, 1 scatter, 2 random (orc_classify)."""
+    co = np.ascontiguousarray(coincidences, COINC_DTYPE)
+    sc = np.ascontiguousarray(scattered_parn, np.int32)
+    cls = np.zeros(max(co.size, 1), np.uint8)
+    totals = np.zeros(3, np.uint64)
+    lib().orc_classify(_p(co), C.c_int64(co.size), _p(sc), C.c_int64(sc.size), C.c_int32(pair_shift), _p(cls), _p(totals))
+    return cls[:co.size], totals

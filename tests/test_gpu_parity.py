@@ -719,6 +719,95 @@ def test_coincidence_pairs_equal_coincidence_records(tmp_path):
     assert s_p[p_p[:, 0]].tobytes() == co_p["a"].tobytes() and s_p[p_p[:, 1]].tobytes() == co_p["b"].tobytes()
 
 
+# ------------------------------------------------------------------------------------------------ coincidence classes
+def paired_events(npairs, rng, tmax, nnoise=0, pair_shift=0):
+    """Two events per annihilation a few ns apart (photon numbers 2k, 2k+1), dense enough in time for randoms and
+    multiples, plus noise-like events (parn = -1)."""
+    n = 2 * npairs
+    ev = parity.random_events(n + nnoise, rng, tmax=tmax, nsites=936)
+    ev["parn"][:n] = np.arange(n, dtype=np.int32)
+    ev["eventid"][:n] = ev["parn"][:n] >> 1 if pair_shift == 0 else ev["parn"][:n]
+    ev["t"][1:n:2] = ev["t"][0:n:2] + rng.uniform(0.0, 0.008, npairs)
+    ev["E"][:n] = rng.uniform(200e3, 600e3, n).astype(np.float32)
+    ev["parn"][n:] = -1
+    ev["eventid"][n:] = (0x80000000 | np.arange(nnoise, dtype=np.int64)).astype(np.uint32).view(np.int32)
+    return ev[rng.permutation(ev.size)]
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+@pytest.mark.parametrize("pair_shift", [0, 1])
+def test_coincidence_classes_of_replayed_events_match_oracle(ctx, policy, pair_shift):
+    rng = np.random.default_rng(40 + 2 * policy + pair_shift)
+    ev = paired_events(60_000, rng, tmax=1.0e4, nnoise=500, pair_shift=pair_shift)
+    p, d = parity.make_digi_params(coinc_window_us=0.01, coinc_policy=policy, ewin_min=100e3)
+    parity.apply_digi_params(ctx, d)
+    ctx.set_digitizer(coinc_pair_shift=pair_shift)
+    want_s, _, want_co = orc.digitize(ev, p)
+    for frac in (0.15, 0.0, 0.4):   # marks of an earlier list must not survive put_events
+        scattered = rng.choice(ev["parn"][ev["parn"] >= 0], int(frac * ev.size), replace=False).astype(np.int32)
+        ctx.put_events(ev)
+        ctx.mark_scattered(scattered)
+        ctx.stage_digitize()
+        co = ctx.fetch_coincidences()
+        cls, totals = ctx.fetch_coincidence_classes()
+        assert co.tobytes() == want_co.astype(api.COINC_DTYPE).tobytes() and co.size > 5000
+        want_cls, want_totals = orc.classify(want_co, scattered, pair_shift)
+        assert np.array_equal(cls, want_cls) and list(totals) == list(want_totals)
+        assert int(totals.sum()) == co.size and totals[2] > 20 and totals[0] > 1000
+        assert (totals[1] > 100) == (frac > 0)
+    ctx.set_digitizer(coinc_pair_shift=0)
+    # the replay entry itself forgets the marks as well
+    ctx.digitize(ev)
+    cls, totals = ctx.fetch_coincidence_classes()
+    assert totals[1] == 0 and np.all(cls != 1)
+
+
+@needs_tables
+def test_run_classifies_coincidences_like_the_staged_scatter_counts(tmp_path):
+    """gpet_run's classes (scatter tags written by the fused front end, or at panel entry by the staged kernels when
+    phase-space dumps are on) against the nscat of the same photons fetched after the staged phantom kernel."""
+    ex = make_example_dir(tmp_path, source="source.txt", window="0 20")
+    def setup(c):
+        c.set_seed(11)
+        c.set_capacity(1 << 17, 1 << 19, 1 << 18)
+        c.load_config_file(ex / "input_PET.in", base_dir=ex)
+        c.set_digitizer(coinc_window_us=0.2, coinc_policy=1)
+    scattered = []
+    with api.Context(0) as c:
+        setup(c)
+        nf = c.plan_frames()
+        for f in range(nf):
+            c.stage_source(f)
+            c.stage_phantom()
+            ph = c.fetch_photons(1)
+            scattered.append(ph["parn"][ph["nscat"] > 0])
+    scattered = np.concatenate(scattered).astype(np.int32)
+    od = tmp_path / "out"; od.mkdir()
+    od2 = tmp_path / "out2"; od2.mkdir()
+    with api.Context(0) as c:
+        setup(c)
+        st = c.run(None)
+        co, cls = c.result_coincidences(), c.result_coincidence_classes()
+        c.set_coincidence_format(api.Context.COINC_PAIRS)
+        st_p = c.run(None)
+        cls_p = c.result_coincidence_classes()
+        st_r = c.run_resident()
+        st_f = c.run(od)             # frame by frame, fused front end
+        c.set_psf_output(2)
+        st_s = c.run(od2)            # staged kernels: tags written at panel entry
+    assert st.frames >= 3 and st.coincidences == co.size == cls.size > 300
+    want_cls, want_totals = orc.classify(co, scattered, 0)
+    assert np.array_equal(cls, want_cls)
+    assert [st.trues, st.scatters, st.randoms] == [int(v) for v in want_totals]
+    assert st.trues > 100 and st.scatters > 10 and st.randoms > 10
+    assert np.array_equal(cls_p, cls)
+    for other in (st_p, st_r, st_f, st_s):
+        assert [other.trues, other.scatters, other.randoms] == [st.trues, st.scatters, st.randoms]
+    assert np.fromfile(od / "coincidences_class.dat", np.uint8).tobytes() == cls.tobytes()
+    assert np.fromfile(od2 / "coincidences_class.dat", np.uint8).tobytes() == cls.tobytes()
+    assert refio.read_coincidences(od / "coincidences.dat").tobytes() == co.tobytes()
+
+
 # ------------------------------------------------------------------------------------------------ positron range / positron PSF
 def water_box(n=40, size=2.0):
     mat = np.ones((n, n, n), np.int32); den = np.ones((n, n, n), np.float32)

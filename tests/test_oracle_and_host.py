@@ -75,6 +75,38 @@ def test_noise_oracle_is_a_poisson_process_over_the_detector():
     assert orc.noise(0, 1e5, 0.0, 3e5, 2e4, 1000.0, 8, 117, 64, 99).size == 0      # disabled
 
 
+def test_coincidence_class_oracle_known_answers():
+    """orc_classify by hand: random = different annihilation or a noise single, scatter = same annihilation with a
+    photon of the scattered list, true = the rest; the pair shift groups a photon PSF's records 2k, 2k+1."""
+    def co(rows):
+        c = np.zeros(len(rows), orc.COINC_DTYPE)
+        for i, (pa, ea, pb, eb) in enumerate(rows):
+            c[i]["a"]["parn"], c[i]["a"]["eventid"], c[i]["b"]["parn"], c[i]["b"]["eventid"] = pa, ea, pb, eb
+        return c
+    rows = [(10, 5, 11, 5), (10, 5, 13, 6), (20, 10, 21, 10), (21, 10, 20, 10), (-1, -5, 30, 15), (30, 15, 31, 15),
+            (40, 20, -1, 20), (-2147483648, 7, 2147483647, 7)]
+    cls, tot = orc.classify(co(rows), [21, 99, -2147483648], 0)
+    assert cls.tolist() == [0, 2, 1, 1, 2, 0, 2, 1] and tot.tolist() == [2, 3, 3]
+    cls, tot = orc.classify(co(rows), [], 0)
+    assert cls.tolist() == [0, 2, 0, 0, 2, 0, 2, 0] and tot.tolist() == [5, 0, 3]
+    # photon PSF: eventid = record index, records 2k and 2k+1 are one pair
+    rows = [(4, 4, 5, 5), (5, 5, 6, 6), (6, 6, 7, 7)]
+    cls, tot = orc.classify(co(rows), [7], 1)
+    assert cls.tolist() == [0, 2, 1] and tot.tolist() == [1, 1, 1]
+    assert orc.classify(co([]), [1, 2], 0)[1].tolist() == [0, 0, 0]
+    # against plain numpy on a random list
+    rng = np.random.default_rng(3)
+    c = np.zeros(5000, orc.COINC_DTYPE)
+    for side in "ab":
+        c[side]["parn"] = rng.integers(-1, 400, c.size)
+        c[side]["eventid"] = c[side]["parn"] >> 1
+    scattered = rng.choice(400, 60, replace=False)
+    cls, tot = orc.classify(c, scattered, 0)
+    rnd = (c["a"]["parn"] == -1) | (c["b"]["parn"] == -1) | (c["a"]["eventid"] != c["b"]["eventid"])
+    sc = np.isin(c["a"]["parn"], scattered) | np.isin(c["b"]["parn"], scattered)
+    assert np.array_equal(cls, np.where(rnd, 2, np.where(sc, 1, 0))) and tot.tolist() == np.bincount(cls, minlength=3).tolist()
+
+
 def test_library_exports_every_declared_symbol():
     header = (parity.ROOT / "include" / "gpet_b200.h").read_text()
     declared = set(re.findall(r"\b(gpet_[a-z_0-9]+)\s*\(", header))
@@ -84,7 +116,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(l, name), f"{name} declared in gpet_b200.h but not exported"
     assert set(api._SIGS) == declared, declared ^ set(api._SIGS)
-    assert api.lib().gpet_abi_version() == 2
+    assert api.lib().gpet_abi_version() == 3
 
 
 def test_record_layouts():
