@@ -126,7 +126,8 @@ int ensure_buffers(gpet_ctx* c) {
     }
     if ((r = dev_alloc(c, &w.order_t, ce))) return r;
     if ((r = dev_alloc(c, &w.kill, ce))) return r;
-    if ((r = dev_alloc(c, &w.coinc_cnt, ce))) return r;
+    if ((r = dev_alloc(c, &w.spar, ce))) return r;
+    if ((r = dev_alloc(c, &w.seid, ce))) return r;
     if (w.spectrum_bins > 0) {
         w.spectrum_stride = w.spectrum_bins <= 1024 ? 16 : 1;
         const size_t nw = (size_t)w.spectrum_bins * w.spectrum_stride;

@@ -543,7 +543,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_emit_singles(EventBuf ev, Digit
                                                            const unsigned* __restrict__ order_t, const int* __restrict__ site_t,
                                                            const unsigned char* __restrict__ kill, unsigned* __restrict__ counters,
                                                            unsigned* __restrict__ status, double* __restrict__ stime,
-                                                           int* __restrict__ span, unsigned long long* __restrict__ spectrum,
+                                                           int* __restrict__ span, int* __restrict__ spar, int* __restrict__ seid,
+                                                           unsigned long long* __restrict__ spectrum,
                                                            int nbins, int spec_stride, float emin, float emax, int fallback_skipped,
                                                            unsigned* __restrict__ h_singles_count) {
     pdl_wait();
@@ -685,8 +686,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_emit_singles(EventBuf ev, Digit
                 dst[3ull * o + part] = v[u];
                 if (part == 0) {
                     span[o] = v[u].y;
+                    spar[o] = v[u].x;
                 } else if (part == 1) {
                     stime[o] = __longlong_as_double((long long)(((unsigned long long)(unsigned)v[u].w << 32) | (unsigned)v[u].z));
+                    seid[o] = v[u].y;
                 } else if (spectrum && nbins > 0) {
                     const float f = (__int_as_float(v[u].x) - emin) / (emax - emin) * nbins;
                     if (f >= 0.f && f < (float)nbins) {
@@ -727,6 +730,23 @@ struct SinglesView {
     __device__ __forceinline__ int pan(unsigned i) const { return (i >= lo && i < hi) ? sp[i - lo] : gp[i]; }
 };
 
+// Coincidence classes (SURVEY 8f-1; the reference has neither a sorter nor a scatter flag, F2 / F11):
+//   2 random  -- the two singles come from different annihilations (eventid >> pair_shift differ), or one of them is a
+//                noise single (parn == -1, k_noise)
+//   1 scatter -- same annihilation, and at least one of the two photons interacted in the phantom (its scatter tag,
+//                DetectorDev::scat_tag, carries this frame's serial)
+//   0 true    -- same annihilation, both photons unscattered in the phantom
+// Per single: bit 0 = its photon scattered in the phantom, bit 1 = noise single.
+constexpr unsigned kCfScattered = 1u, kCfNoise = 2u;
+__device__ __forceinline__ unsigned class_flags(const DigitizerDev& p, int parn) {
+    if (parn == -1) return kCfNoise;
+    return (p.scat_tag != nullptr && __ldg(p.scat_tag + ((unsigned)parn & p.scat_mask)) == p.scat_serial) ? kCfScattered : 0u;
+}
+__device__ __forceinline__ unsigned coincidence_class(const DigitizerDev& p, int eid_a, unsigned cf_a, int eid_b, unsigned cf_b) {
+    if (((cf_a | cf_b) & kCfNoise) || (eid_a >> p.pair_shift) != (eid_b >> p.pair_shift)) return 2u;
+    return ((cf_a | cf_b) & kCfScattered) ? 1u : 0u;
+}
+
 __device__ __forceinline__ bool pair_ok(const SinglesView& v, unsigned a, unsigned b, const DigitizerDev& p) {
     if (p.cmindiff <= 0) return true;
     int d = abs(v.pan(a) - v.pan(b));
@@ -752,24 +772,15 @@ __device__ __forceinline__ unsigned coincidences_of(const SinglesView& v, unsign
     }
 }
 
-// Coincidence classes (SURVEY 8f-1; the reference has neither a sorter nor a scatter flag, F2 / F11):
-//   2 random  -- the two singles come from different annihilations (eventid >> pair_shift differ), or one of them is a
-//                noise single (parn == -1, k_noise)
-//   1 scatter -- same annihilation, and at least one of the two photons interacted in the phantom (its scatter tag,
-//                DetectorDev::scat_tag, carries this frame's serial)
-//   0 true    -- same annihilation, both photons unscattered in the phantom
-__device__ __forceinline__ bool photon_scattered(const DigitizerDev& p, int parn) {
-    return p.scat_tag != nullptr && parn != -1 && __ldg(p.scat_tag + ((unsigned)parn & p.scat_mask)) == p.scat_serial;
-}
-__device__ __forceinline__ unsigned coincidence_class(const DigitizerDev& p, int parn_a, int eid_a, bool a_scat, int parn_b, int eid_b) {
-    if (parn_a == -1 || parn_b == -1 || (eid_a >> p.pair_shift) != (eid_b >> p.pair_shift)) return 2u;
-    return (a_scat || photon_scattered(p, parn_b)) ? 1u : 0u;
-}
-
 // Index pairs into the run's singles list (pair_base = singles of the run's earlier frames, kept on the device) and,
 // when `out` is given, the two 48-byte records side by side; `cls` (optional) receives one class byte per coincidence.
+// The photon number and annihilation number of every single come from the side arrays k_emit_singles wrote (spar, seid);
+// the scatter tags of the staged singles are looked up during staging -- one more round trip there, all lookups of a
+// tile in flight together -- so that the emission loop works from shared memory alone (looked up per coincidence inside
+// that loop, two dependent round trips per pair and thread, the kernel took 37 instead of 27 us).
 __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__ s, const double* __restrict__ stime,
-                                                    const int* __restrict__ span, DigitizerDev p, unsigned* __restrict__ counters,
+                                                    const int* __restrict__ span, const int* __restrict__ spar,
+                                                    const int* __restrict__ seid, DigitizerDev p, unsigned* __restrict__ counters,
                                                     unsigned singles_cap, unsigned* __restrict__ status,
                                                     gpet_coincidence* __restrict__ out, uint2* __restrict__ pairs, unsigned cap,
                                                     const unsigned* __restrict__ base_in, unsigned* __restrict__ base_out,
@@ -781,6 +792,8 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
     if (threadIdx.x < 3) s_cls[threadIdx.x] = 0u;   // ordered before its use by the barriers of the tile loop and of the tally
     __shared__ double s_t[kScanTile + 2 * kHalo];
     __shared__ int s_p[kScanTile + 2 * kHalo];
+    __shared__ int s_eid[kScanTile + 2 * kHalo];
+    __shared__ unsigned char s_cf[kScanTile + 2 * kHalo];
     __shared__ __align__(16) unsigned short s_cnt[kScanTile];
     const unsigned n = min(counters[3], singles_cap);
     const unsigned ntiles = (n + kScanTile - 1) / kScanTile;
@@ -805,12 +818,14 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
         {   // all loads first, then the shared-memory stores
             constexpr int kRounds = (kScanTile + 2 * kHalo + kThreads - 1) / kThreads;
             double tv[kRounds];
-            int pv[kRounds];
+            int pv[kRounds], ev[kRounds], pn[kRounds];
 #pragma unroll
             for (int r = 0; r < kRounds; r++) {
                 const unsigned i = v.lo + r * kThreads + threadIdx.x;
                 tv[r] = i < v.hi ? stime[i] : 0.0;
                 pv[r] = i < v.hi ? span[i] : 0;
+                ev[r] = i < v.hi ? seid[i] : 0;
+                pn[r] = i < v.hi ? spar[i] : -1;
             }
 #pragma unroll
             for (int r = 0; r < kRounds; r++) {
@@ -818,7 +833,18 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
                 if (i < v.hi) {
                     s_t[i - v.lo] = tv[r];
                     s_p[i - v.lo] = pv[r];
+                    s_eid[i - v.lo] = ev[r];
                 }
+            }
+            // second round trip: the scatter tags of all staged singles.  (Looking up only the singles with a neighbour
+            // closer than the window -- half of them on the shipped example -- was measured: no difference, 33.1 us.)
+            unsigned cf[kRounds];
+#pragma unroll
+            for (int r = 0; r < kRounds; r++) cf[r] = class_flags(p, pn[r]);
+#pragma unroll
+            for (int r = 0; r < kRounds; r++) {
+                const unsigned i = v.lo + r * kThreads + threadIdx.x;
+                if (i < v.hi) s_cf[i - v.lo] = (unsigned char)cf[r];
             }
         }
         __syncthreads();
@@ -847,24 +873,30 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
             const unsigned a = a0 + k;
             unsigned o = sc.excl[k], left = c[k];
             const double tend = v.t(a) + W;
-            // the opener's photon number and annihilation number (words 0 and 5 of its record), its scatter tag
-            const int4* pa = reinterpret_cast<const int4*>(s + a);
-            const int4 ra0 = __ldg(pa), ra1 = __ldg(pa + 1);
-            const bool a_scat = photon_scattered(p, ra0.x);
+            // annihilation number and class flags of a single: staged, or (window beyond the halo) from global memory
+            auto info = [&](unsigned i, int& eid, unsigned& cf) {
+                if (i >= v.lo && i < v.hi) { eid = s_eid[i - v.lo]; cf = s_cf[i - v.lo]; }
+                else { eid = seid[i]; cf = class_flags(p, spar[i]); }
+            };
+            int eid_a; unsigned cf_a;
+            info(a, eid_a, cf_a);
             for (unsigned b = a + 1; left && b < n && v.t(b) < tend; b++) {
                 if (!pair_ok(v, a, b, p)) continue;
                 left--;
-                const int4* pb = reinterpret_cast<const int4*>(s + b);
-                const int4 rb0 = __ldg(pb), rb1 = __ldg(pb + 1);
-                const unsigned cl = coincidence_class(p, ra0.x, ra1.y, a_scat, rb0.x, rb1.y);
+                int eid_b; unsigned cf_b;
+                info(b, eid_b, cf_b);
+                const unsigned cl = coincidence_class(p, eid_a, cf_a, eid_b, cf_b);
                 n_cls[0] += cl == 0u ? 1u : 0u; n_cls[1] += cl == 1u ? 1u : 0u; n_cls[2] += cl == 2u ? 1u : 0u;
                 if (o < cap) {
                     if (pairs) pairs[o] = make_uint2(pair_base + a, pair_base + b);
                     if (cls) cls[o] = (unsigned char)cl;
                     if (out) {   // 2 x 48-byte records copied as 6 x 16 B from the singles list
-                        const int4 ra2 = __ldg(pa + 2), rb2 = __ldg(pb + 2);
+                        const int4* pa = reinterpret_cast<const int4*>(s + a);
+                        const int4* pb = reinterpret_cast<const int4*>(s + b);
+                        const int4 a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
+                        const int4 b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
                         int4* po = reinterpret_cast<int4*>(out + o);
-                        po[0] = ra0; po[1] = ra1; po[2] = ra2; po[3] = rb0; po[4] = rb1; po[5] = rb2;
+                        po[0] = a0; po[1] = a1; po[2] = a2; po[3] = b0; po[4] = b1; po[5] = b2;
                     }
                 }
                 o++;
@@ -1024,13 +1056,13 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
         launches++;
     }
     GPET_LAUNCH("k_emit_singles", s, launch_pdl(k_emit_singles, g_emit, kThreads, s, ev, p, singles, out.singles_cap, keys, ws.order_t, ws.site_t,
-                                                ws.kill, ws.counters, ws.scan_status[0], ws.stime, ws.span, ws.spectrum, ws.spectrum_bins,
+                                                ws.kill, ws.counters, ws.scan_status[0], ws.stime, ws.span, ws.spar, ws.seid, ws.spectrum, ws.spectrum_bins,
                                                 ws.spectrum_stride, ws.spec_emin, ws.spec_emax, with_fallback ? 0 : 1,
                                                 out.ev_after_emit ? out.h_singles_count : (unsigned*)nullptr));
     launches++;
     if (out.ev_after_emit && out.h_singles_count) cudaEventRecord(out.ev_after_emit, s);
     if (p.cwin > 0.f && (out.coinc || out.pairs)) {
-        GPET_LAUNCH("k_coinc", s, launch_pdl(k_coinc, g_coinc, kThreads, s, singles, ws.stime, ws.span, p, ws.counters, out.singles_cap, ws.scan_status[1],
+        GPET_LAUNCH("k_coinc", s, launch_pdl(k_coinc, g_coinc, kThreads, s, singles, ws.stime, ws.span, ws.spar, ws.seid, p, ws.counters, out.singles_cap, ws.scan_status[1],
                                                                   static_cast<gpet_coincidence*>(out.coinc), static_cast<uint2*>(out.pairs),
                                                                   out.coinc_cap, out.pair_base_in, out.pair_base_out,
                                                                   static_cast<unsigned char*>(out.cls)));

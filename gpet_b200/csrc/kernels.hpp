@@ -41,7 +41,8 @@ struct DigitizerWorkspace {
     unsigned char* kill;           // per time-order position: 1 = removed by dead time (non-paralyzable chain)
     double* stime;                 // per single: time, panel (what the coincidence sorter reads)
     int* span;
-    unsigned int* coinc_cnt;       // per single: coincidences it opens
+    int* spar;                     // per single: photon number and annihilation number (coincidence classes)
+    int* seid;
     // [0] n_in [1] after thresholder [2] after deadtime [3] singles [4] coincidences [6],[7] tile tickets of the two
     // compactions [5] time sort fell back to LSD radix [8] photons on a panel [9] adder drops [12..14] true / scatter /
     // random coincidences; [16..19] queue 0, queue 1, hits, events counts, [21] queue 2
