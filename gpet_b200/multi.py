@@ -9,7 +9,8 @@ from __future__ import annotations
 import numpy as np
 
 TALLY_FIELDS = ("pairs", "photons_phantom_out", "photons_on_panel", "hits", "events_adder", "events_threshold",
-                "events_deadtime", "singles", "coincidences", "overflow_hits", "overflow_events", "overflow_adder", "frames")
+                "events_deadtime", "singles", "coincidences", "trues", "scatters", "randoms", "overflow_hits", "overflow_events",
+                "overflow_adder", "frames")
 
 
 def owned_frames(nframes: int, rank: int, world: int):

@@ -127,6 +127,9 @@ def test_config3_point_source_sensitivity_sweep(tmp_path):
             assert st.events_adder == ref_events          # same seed: transport identical, only the window changes
             assert abs(st.pairs - decays) < 6 * np.sqrt(decays)
             sens.append(st.singles / st.pairs); coin.append(st.coincidences / st.pairs)
+            # coincidence classes: nothing to scatter in (air, 6e-5 interactions per photon), ~1700 singles/s -> no randoms to speak of
+            assert st.trues + st.scatters + st.randoms == st.coincidences
+            assert st.scatters <= 0.01 * st.coincidences and st.randoms <= 0.01 * st.coincidences
     assert all(a > b for a, b in zip(sens, sens[1:])) and all(a > b for a, b in zip(coin, coin[1:]))
     assert 0.05 < coin[0] < 0.2 and 0.2 < sens[0] < 0.7
     # oracle at a matched count with another seed: fraction of post-readout events inside each window
@@ -161,12 +164,17 @@ def test_config4_mouse_phantom_256(tmp_path):
         c.set_digitizer(coinc_window_us=0.01)
         c.plan_frames(1 << 20)                # ~1 Mi pairs per frame: 3 frames
         st = c.run(None)
-        singles = c.result_singles(); co = c.result_coincidences()
+        singles = c.result_singles(); co = c.result_coincidences(); cls = c.result_coincidence_classes()
         # one frame staged by hand for the comparison below
         c.stage_source(0)
         q0 = c.fetch_photons(0)[:300000]
     assert st.frames >= 3 and abs(st.pairs - decays) < 6 * np.sqrt(decays)
     assert st.singles == singles.size and st.coincidences == co.size > 0
+    # coincidence classes: ~13 % of the photons scatter in the mouse (checked per photon below), so roughly a fifth of the
+    # same-annihilation coincidences hold a scattered photon, less what the energy window removes
+    assert st.trues + st.scatters + st.randoms == st.coincidences and np.array_equal(np.bincount(cls, minlength=3), [st.trues, st.scatters, st.randoms])
+    assert np.array_equal(cls == 2, co["a"]["eventid"] != co["b"]["eventid"])
+    assert 0.03 < st.scatters / (st.trues + st.scatters) < 0.45
     assert st.events_adder >= st.events_threshold >= st.events_deadtime >= st.singles
     # frames are consecutive time slices: the concatenated singles are globally time ordered
     assert np.all(np.diff(singles["t"]) >= 0)
@@ -225,6 +233,11 @@ def test_config5_ring_of_32_panels_with_20cm_water(tmp_path):
     assert 0.9 < out_frac < 0.999
     d = np.abs(co["a"]["pann"] - co["b"]["pann"]); d = np.minimum(d, 32 - d)
     assert co.size > 0 and d.min() >= 4
+    # scatter fraction of the coincidences from the class tallies: most photons scatter in 20 cm of
+    # water, the energy window removes the large angles
+    assert st.trues + st.scatters + st.randoms == st.coincidences
+    if st.trues + st.scatters > 500:
+        assert 0.05 < st.scatters / (st.trues + st.scatters) < 0.9
     # per-photon parity in the big phantom (multi-step Woodcock, several Comptons per history) and in the ring
     s = parity.Setup(0, phantom=(mat, den), size=size, geo=ex / "input" / "ring.geo")
     s.ctx.put_photons(0, q0); s.ctx.stage_phantom()
