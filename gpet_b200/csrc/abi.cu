@@ -165,11 +165,11 @@ int ensure_buffers(gpet_ctx* c) {
         c->allocs.push_back(p);
         c->stage_aos = p;
     }
-    {   // scatter tags: zeroed once, never cleared again (serial 0 is never used)
+    {   // scatter tags, one byte per photon slot: zeroed here and whenever the serial wraps (serial 0 is never used)
         size_t nt = 1024;
         while (nt < cp) nt <<= 1;
         if ((r = dev_alloc(c, &c->d_scat_tag, nt))) return r;
-        CK(cudaMemset(c->d_scat_tag, 0, nt * sizeof(unsigned)));
+        CK(cudaMemset(c->d_scat_tag, 0, nt));
         c->scat_mask = (unsigned)(nt - 1);
         c->scat_serial = 0;
     }
@@ -350,8 +350,8 @@ DigitizerDev digitizer_dev(const gpet_ctx* c) {
 
 // New photons are about to reach the panel faces, or new events are put: tags of anything earlier must not match.
 void new_scatter_serial(gpet_ctx* c) {
-    if (++c->scat_serial == 0u) {   // wrapped after 2^32 frames: the one time the table is cleared
-        if (c->d_scat_tag) cudaMemsetAsync(c->d_scat_tag, 0, ((size_t)c->scat_mask + 1) * sizeof(unsigned), c->stream);
+    if (++c->scat_serial > 255u) {   // one-byte tags: every 255 serials the table is cleared (4 MB, stream ordered) and the count restarts
+        if (c->d_scat_tag) cudaMemsetAsync(c->d_scat_tag, 0, (size_t)c->scat_mask + 1, c->stream);
         c->scat_serial = 1u;
     }
 }

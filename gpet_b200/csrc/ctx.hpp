@@ -65,9 +65,9 @@ struct gpet_ctx {
     void* pairs_slot[2] = {nullptr, nullptr};            // uint2 index pairs (GPET_COINC_PAIRS)
     void* cls_slot[2] = {nullptr, nullptr};              // one class byte per coincidence (0 true, 1 scatter, 2 random)
     void* cls_aos = nullptr;                             // = cls_slot[out_slot]
-    // scatter tags (DetectorDev::scat_tag): table of a power of two >= cap_photons words; the serial is bumped whenever
+    // scatter tags (DetectorDev::scat_tag): table of a power of two >= cap_photons bytes; the serial (1..255) is bumped whenever
     // new photons reach the panel faces or new events are put, so stale tags never match
-    unsigned* d_scat_tag = nullptr;
+    unsigned char* d_scat_tag = nullptr;
     unsigned scat_mask = 0, scat_serial = 0;
     unsigned* d_pair_base = nullptr;                     // [2]: singles of the run's earlier frames, alternating by frame
     int psf_output = 0;                                  // OUTPUTPSF of the reference (gpet_set_psf_output)

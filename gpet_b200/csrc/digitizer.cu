@@ -740,7 +740,7 @@ struct SinglesView {
 constexpr unsigned kCfScattered = 1u, kCfNoise = 2u;
 __device__ __forceinline__ unsigned class_flags(const DigitizerDev& p, int parn) {
     if (parn == -1) return kCfNoise;
-    return (p.scat_tag != nullptr && __ldg(p.scat_tag + ((unsigned)parn & p.scat_mask)) == p.scat_serial) ? kCfScattered : 0u;
+    return (p.scat_tag != nullptr && (unsigned)__ldg(p.scat_tag + ((unsigned)parn & p.scat_mask)) == p.scat_serial) ? kCfScattered : 0u;
 }
 __device__ __forceinline__ unsigned coincidence_class(const DigitizerDev& p, int eid_a, unsigned cf_a, int eid_b, unsigned cf_b) {
     if (((cf_a | cf_b) & kCfNoise) || (eid_a >> p.pair_shift) != (eid_b >> p.pair_shift)) return 2u;
@@ -968,12 +968,12 @@ int launch_publish_counters(const unsigned* counters, const unsigned* hot, unsig
 }
 
 // gpet_mark_scattered: scatter tags for a caller's list of photon numbers (replayed events carry no transport history)
-__global__ void k_mark_scattered(const int* __restrict__ parn, unsigned n, unsigned* __restrict__ tag, unsigned mask, unsigned serial) {
+__global__ void k_mark_scattered(const int* __restrict__ parn, unsigned n, unsigned char* __restrict__ tag, unsigned mask, unsigned serial) {
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        if (parn[i] != -1) tag[(unsigned)parn[i] & mask] = serial;
+        if (parn[i] != -1) tag[(unsigned)parn[i] & mask] = (unsigned char)serial;
 }
 
-int launch_mark_scattered(const int* parn, unsigned n, unsigned* tag, unsigned mask, unsigned serial, cudaStream_t s) {
+int launch_mark_scattered(const int* parn, unsigned n, unsigned char* tag, unsigned mask, unsigned serial, cudaStream_t s) {
     if (n == 0 || tag == nullptr) return 0;
     const int grid = (int)std::min<unsigned>((n + kThreads - 1) / kThreads, 1024u);
     GPET_LAUNCH("k_mark_scattered", s, k_mark_scattered<<<grid, kThreads, 0, s>>>(parn, n, tag, mask, serial));

@@ -101,7 +101,7 @@ int launch_publish_counters(const unsigned* counters, const unsigned* hot, unsig
 int launch_noise(EventBuf ev, const DigitizerDev& p, double t_lo_us, double t_hi_us, uint64_t seed, int num_sms, cudaStream_t s);
 
 // scatter tags of a host-supplied list of photon numbers (gpet_mark_scattered)
-int launch_mark_scattered(const int* parn, unsigned n, unsigned* tag, unsigned mask, unsigned serial, cudaStream_t s);
+int launch_mark_scattered(const int* parn, unsigned n, unsigned char* tag, unsigned mask, unsigned serial, cudaStream_t s);
 
 // ---- transport (transport.cu) ----------------------------------------------------------------------------
 int launch_source(const SourceDev* frame_dev, unsigned long long npairs, PhantomDev ph, PhotonQueue q0,

@@ -309,10 +309,10 @@ __device__ __forceinline__ float record_distance(const PhantomDev& ph, const Pho
 // then never has to stay in a register up to the panel search); the staged path carries nscat through queue 1 and tags
 // at panel entry.
 __device__ __forceinline__ void mark_scattered(const PhantomDev& ph, int parn) {
-    if (ph.scat_tag != nullptr) ph.scat_tag[(unsigned)parn & ph.scat_mask] = ph.scat_serial;
+    if (ph.scat_tag != nullptr) ph.scat_tag[(unsigned)parn & ph.scat_mask] = (unsigned char)ph.scat_serial;
 }
 __device__ __forceinline__ void mark_scattered(const DetectorDev& det, int parn, int nscat) {
-    if (nscat > 0 && det.scat_tag != nullptr) det.scat_tag[(unsigned)parn & det.scat_mask] = det.scat_serial;
+    if (nscat > 0 && det.scat_tag != nullptr) det.scat_tag[(unsigned)parn & det.scat_mask] = (unsigned char)det.scat_serial;
 }
 
 // One Woodcock flight (gPET_kernals.cu:277-335).  Returns 0: still inside, 1: the photon leaves the stage alive (escaped,

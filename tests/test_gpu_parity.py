@@ -755,6 +755,19 @@ def test_coincidence_classes_of_replayed_events_match_oracle(ctx, policy, pair_s
         assert np.array_equal(cls, want_cls) and list(totals) == list(want_totals)
         assert int(totals.sum()) == co.size and totals[2] > 20 and totals[0] > 1000
         assert (totals[1] > 100) == (frac > 0)
+    # one-byte tags: the serial wraps every 255 event lists / frames and the table is cleared then; marks set before the
+    # wrap must be gone after it, marks set after it must work
+    ctx.put_events(ev)
+    ctx.mark_scattered(ev["parn"][ev["parn"] >= 0])
+    for _ in range(254):          # + the put below = 255 serials later: the same serial value again
+        ctx.put_events(ev[:1])
+    scattered = rng.choice(ev["parn"][ev["parn"] >= 0], ev.size // 5, replace=False).astype(np.int32)
+    ctx.put_events(ev)
+    ctx.mark_scattered(scattered)
+    ctx.stage_digitize()
+    cls, totals = ctx.fetch_coincidence_classes()
+    want_cls, want_totals = orc.classify(want_co, scattered, pair_shift)
+    assert np.array_equal(cls, want_cls) and list(totals) == list(want_totals)
     ctx.set_digitizer(coinc_pair_shift=0)
     # the replay entry itself forgets the marks as well
     ctx.digitize(ev)
