@@ -54,6 +54,39 @@ def test_digitizer_oracle_invariants():
         assert parity.events_equal(s, s2)
 
 
+@pytest.mark.parametrize("dead_type", [0, 1])
+@pytest.mark.parametrize("dead_level", [0, 1, 2, 3])
+def test_digitizer_oracle_equals_a_literal_walk_of_the_reference_kernels(dead_level, dead_type):
+    """The C oracle (closed-form dead time of SURVEY 8a D7, merge sorts) against tests/pyref_digitizer.py: the reference's
+    host sequence and kernels followed statement by statement in plain Python, dead-time chains walked literally (every
+    walker on the list as it was before any kill -- at early times the reference's own outcome does not depend on how its
+    threads interleave; the last case is at t = 1e8 us, where `tdead` in fp32 is coarser than the dead time)."""
+    import pyref_digitizer as pyref
+    rng = np.random.default_rng(100 + 2 * dead_level + dead_type)
+    kills, npairs = 0, [0, 0]
+    for n, nsites, tmax, tau, policy, mindiff in [(0, 8, 1e3, 2.2, 0, 0), (1, 8, 1e3, 2.2, 0, 0), (2, 1, 3.0, 2.2, 1, 0),
+                                                  (60, 3, 100.0, 2.2, 0, 0), (1200, 40, 900.0, 2.2, 0, 2),
+                                                  (1200, 936, 300.0, 0.9, 1, 0), (1200, 936, 400.0, 0.9, 0, 2),
+                                                  (1500, 12, 4000.0, 7.5, 1, 3), (1501, 30, 300.0, 2.2, 1, 0)]:
+        ev = parity.random_events(n, rng, tmax=tmax, nsites=nsites, tie_fraction=0.05 if n > 10 else 0.0)
+        if n == 1501:
+            ev["t"] += 1.0e8      # late times: the fp32 `tdead` of the kernel is 8 us coarse, wider than the dead time
+        p, d = parity.make_digi_params(dead_level=dead_level, dead_type=dead_type, dead_time_us=tau, coinc_window_us=0.3,
+                                       coinc_policy=policy, coinc_min_panel_diff=mindiff)
+        s, counts, co = orc.digitize(ev, p)
+        ws, wcounts, wpairs = pyref.digitize(ev, d)
+        assert [int(c) for c in counts] == wcounts, (n, nsites, counts, wcounts)
+        assert s.tobytes() == ws.astype(orc.EVENT_DTYPE).tobytes()
+        assert co.size == len(wpairs)
+        if wpairs:
+            ia, ib = np.array(wpairs).T
+            assert co["a"].tobytes() == s[ia].tobytes() and co["b"].tobytes() == s[ib].tobytes()
+        kills += wcounts[1] - wcounts[2]
+        npairs[policy] += len(wpairs)
+    # dead time and both sorter policies had work to do (one site for the whole detector leaves no two singles in a window)
+    assert kills > 100 and (dead_level == 0 or (npairs[0] > 30 and npairs[1] > 80))
+
+
 # ------------------------------------------------------------------------------------------------ C ABI surface
 def test_noise_oracle_is_a_poisson_process_over_the_detector():
     # addnoise (gPET_kernals.cu:699-735): mean gap 2 us over 0.1 s -> 50 000 +- 224 arrivals, uniform sites, E ~ N(300 keV, 20 keV)
