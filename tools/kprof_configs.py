@@ -58,7 +58,8 @@ def main():
             tot = sum(v[0] for v in kt.values()) / a.reps
             print(f"# {name}: {st.pairs} pairs in {nf} frames, {tot * 1e3:.1f} us of kernel time per run = {st.pairs / tot / 1e6:.2f} G pairs/s; "
                   f"phantom out {st.photons_phantom_out / (2 * st.pairs):.3f}, on panel {st.photons_on_panel / (2 * st.pairs):.3f}, "
-                  f"singles {st.singles}, coincidences {st.coincidences}")
+                  f"singles {st.singles}, coincidences {st.coincidences} (trues {st.trues}, scatters {st.scatters}, randoms {st.randoms}; "
+                  f"scatter fraction {st.scatters / max(st.trues + st.scatters, 1):.3f})")
             for k, (ms, nl) in kt.items():
                 print(f"{ms / a.reps * 1e3:9.2f} us/run  {nl // a.reps:3d} launches  {ms / nl * 1e3:8.2f} us each  {k}")
             c.close()

@@ -57,7 +57,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
             print(json.dumps({"n_gpus": world, "frames": int(tot["frames"]), "pairs": int(tot["pairs"]), "singles": int(tot["singles"]),
-                              "coincidences": int(tot["coincidences"]), "seconds": float(t.item()),
+                              "coincidences": int(tot["coincidences"]), "trues": int(tot["trues"]), "scatters": int(tot["scatters"]),
+                              "randoms": int(tot["randoms"]), "seconds": float(t.item()),
                               "pairs_per_s": tot["pairs"] / float(t.item()), "scaling": "strong (one acquisition, frames sharded)"}))
         c.close()
     if world > 1:
