@@ -29,6 +29,11 @@ def read_coincidences(path):
     return np.fromfile(path, COINC_DTYPE)
 
 
+def read_coincidence_classes(path):
+    """coincidences_class.dat: one uint8 per record of coincidences.dat (0 true, 1 scatter, 2 random)."""
+    return np.fromfile(path, np.uint8)
+
+
 def read_hits(hits_id_path, hits_path):
     """HitsID.dat (5 x int32 per hit) + Hits.dat (5 x float32 per hit) (readOutput.m:3-16).
     Columns: particle id, panel, module, crystal, type | E, t, local x, y, z."""
