@@ -166,6 +166,22 @@ def test_host_only_context_refuses_compute():
             c.digitize(np.zeros(4, api.EVENT_DTYPE))
         with pytest.raises(api.GpetError):
             c.run()
+        # every compute entry point, not only the big ones: no CPU fallback anywhere
+        calls = [lambda: c.stage_source(0), lambda: c.stage_psf(0, 0), lambda: c.stage_phantom(), lambda: c.stage_detector(),
+                 lambda: c.stage_front(-1), lambda: c.stage_panel_transport(), lambda: c.stage_noise(0.0, 1.0),
+                 lambda: c.put_photons(0, np.zeros(1, api.PHOTON_DTYPE)), lambda: c.fetch_photons(0), lambda: c.put_events(np.zeros(1, api.EVENT_DTYPE)),
+                 lambda: c.fetch_events(4), lambda: c.fetch_hits(4), lambda: c.fetch_singles(4), lambda: c.fetch_coincidences(4),
+                 lambda: c.fetch_coincidence_classes(4), lambda: c.mark_scattered([1, 2]), lambda: c.last_counts(), lambda: c.run_resident(),
+                 lambda: c.queue_size(0)]
+        for k, f in enumerate(calls):
+            with pytest.raises(api.GpetError) as e:
+                f()
+            assert e.value.code == -4, k
+        # results of a run that never happened are empty, not an error
+        assert c.result_singles().size == 0 and c.result_coincidences().size == 0 and c.result_coincidence_classes().size == 0
+        assert c.get_digitizer().coinc_pair_shift == 0
+        c.set_digitizer(coinc_pair_shift=1)
+        assert c.get_digitizer().coinc_pair_shift == 1
 
 
 # ------------------------------------------------------------------------------------------------ loaders
