@@ -1,0 +1,244 @@
+"""Unit tests of the CPU oracle's file-local functions, reached through tests/c/oracle_units.c: against physics where a
+closed form exists (Klein-Nishina, rotation geometry) and against plain-Python restatements of the reference lines
+(crystalSearch, adder, readout).  CPU only; the oracle is the thing under test here."""
+import ctypes as C
+import subprocess
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+import parity
+from gpet_b200 import refio
+from oracle import oracle as orc
+
+f32 = np.float32
+MC2 = 510.9991e3
+MAXT = 1e20
+
+
+@pytest.fixture(scope="module")
+def units(tmp_path_factory):
+    so = tmp_path_factory.mktemp("units") / "liborc_units.so"
+    subprocess.run(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-Wno-unused-function",
+                    "-o", str(so), str(parity.ROOT / "tests" / "c" / "oracle_units.c"), "-lm"], check=True)
+    return C.CDLL(str(so))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ------------------------------------------------------------------------------------------------ P6 rotate
+def test_rotate_turns_by_the_polar_angle_and_keeps_the_norm(units):
+    """rotate (gPET_kernals.cu:172-254): the new direction has unit length and makes the angle theta with the old one;
+    for a fixed direction, phi sweeps the cone uniformly (the azimuth of the new direction around the old one equals phi
+    up to a constant)."""
+    rng = np.random.default_rng(1)
+    n = 20000
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:200] *= rng.uniform(0.5, 2.0, (200, 1))            # not normalised on input: renormalised (lines 205-212)
+    d[200:210] = [0, 0, 1]; d[210:220] = [0, 0, -1]       # rho = 0: the two special cases (lines 236-252)
+    d = d.astype(f32)
+    costh = rng.uniform(-1, 1, n).astype(f32)
+    costh[:5] = [1, -1, 0, 1, -1]
+    phi = rng.uniform(0, 2 * np.pi, n).astype(f32)
+    out = d.copy()
+    units.u_rotate(_p(out), C.c_int64(n), _p(costh), _p(phi))
+    d0 = d.astype(np.float64)
+    d0 /= np.linalg.norm(d0, axis=1, keepdims=True)
+    o = out.astype(np.float64)
+    unit = np.ones(n, bool); unit[:200] = False
+    assert np.abs(np.linalg.norm(o[unit], axis=1) - 1).max() < 2e-4   # the reference itself tolerates 1e-4 before it renormalises
+    assert np.abs((o[unit] * d0[unit]).sum(1) - costh[unit]).max() < 2e-4
+    # Not normalised on input: the reference renormalises (u, v, w) but goes on with the rho2 of the vector as it came in
+    # (gPET_kernals.cu:203-212 vs 222), so the result is NOT a unit vector, whatever the header comment says.  Transport
+    # never gets there (directions stay within 1e-4 of unit length); the oracle keeps the statement order all the same.
+    u, v, w = d[:200, 0].copy(), d[:200, 1].copy(), d[:200, 2].copy()
+    rho2 = u * u + v * v
+    norm = f32(1) / np.sqrt(rho2 + w * w)
+    u, v, w = u * norm, v * norm, w * norm
+    sp, cp = np.sin(phi[:200]), np.cos(phi[:200])
+    c2 = costh[:200] * costh[:200]
+    sthrho = np.where(c2 < 1, np.sqrt(np.maximum(f32(1) - c2, 0) / rho2), f32(0)).astype(f32)
+    urho, vrho = u * sthrho, v * sthrho
+    lit = np.stack([u * costh[:200] - vrho * sp + w * urho * cp, v * costh[:200] + urho * sp + w * vrho * cp,
+                    w * costh[:200] - rho2 * sthrho * cp], 1)
+    assert np.abs(out[:200] - lit).max() < 2e-6 and np.abs(np.linalg.norm(o[:200], axis=1) - 1).max() > 0.05
+    # azimuth: same direction and polar angle, phi and phi + pi/2 -> the two results are perpendicular around the axis
+    k = 5000
+    a = np.repeat(d[1000:1001], k, 0).copy(); b = a.copy()
+    ct = np.full(k, 0.3, f32); ph = rng.uniform(0, 2 * np.pi, k).astype(f32)
+    units.u_rotate(_p(a), C.c_int64(k), _p(ct), _p(ph))
+    units.u_rotate(_p(b), C.c_int64(k), _p(ct), _p((ph + f32(np.pi / 2)).astype(f32)))
+    axis = d0[1000]
+    pa = a - np.outer(a @ axis, axis); pb = b - np.outer(b @ axis, axis)
+    assert np.abs((pa * pb).sum(1)).max() < 1e-4 * (1 - 0.09)       # perpendicular transverse parts
+    assert np.abs(np.einsum("ij,ij->i", np.cross(pa, pb), np.tile(axis, (k, 1))) - (1 - 0.09)).max() < 1e-3   # right-handed, |.| = sin^2
+
+
+# ------------------------------------------------------------------------------------------------ X3 Klein-Nishina
+@pytest.mark.parametrize("E", [60e3, 140e3, 511e3, 1.0e6])
+def test_compton_sampler_follows_klein_nishina(units, E):
+    """comsam, free electron (gPET_kernals.cu:90-126): the sampled energy fraction follows
+    dsigma/d(eps) ~ (1/eps + eps) (1 - eps sin^2(theta) / (1 + eps^2)) on [1/(1+2k), 1], and cos(theta) is Compton's
+    relation for that fraction."""
+    n = 400000
+    ef = np.zeros(n, f32); ct = np.zeros(n, f32)
+    units.u_compton_kn(C.c_float(E), C.c_uint64(77), C.c_int64(n), _p(ef), _p(ct))
+    k = E / MC2
+    emin = 1.0 / (1.0 + 2.0 * k)
+    assert ef.min() >= emin * (1 - 1e-5) and ef.max() <= 1.0
+    assert np.abs(ct - (1.0 - (1.0 - ef.astype(np.float64)) / (ef.astype(np.float64) * k))).max() < 2e-4
+    edges = np.linspace(emin, 1.0, 41)
+    xs = np.linspace(emin, 1.0, 40 * 400 + 1)
+    c = 1.0 - (1.0 - xs) / (xs * k)
+    pdf = (1.0 / xs + xs) * (1.0 - xs * (1.0 - c * c) / (1.0 + xs * xs))
+    cdf = np.concatenate([[0.0], np.cumsum(0.5 * (pdf[1:] + pdf[:-1]) * np.diff(xs))])
+    expect = np.diff(cdf[::400]) / cdf[-1] * n
+    got, _ = np.histogram(ef, edges)
+    chi2 = ((got - expect) ** 2 / expect).sum()
+    assert chi2 / 39 < 1.8, (E, chi2)
+
+
+# ------------------------------------------------------------------------------------------------ X2 crystalSearch
+def crystal_search_literal(p, moduleNy, crystalNy, surfaces, x, y, z):
+    """gPET_kernals.cu:1236-1279 in float32, statement by statement.  Returns (m_id, M_id, L_id), -1 = not reached."""
+    x, y, z = f32(x), f32(y), f32(z)
+    for s in surfaces:
+        s = [f32(v) for v in s]
+        q = (s[0] * x * x + s[1] * y * y + s[2] * z * z + s[3] * x * y + s[4] * x * z + s[5] * y * z + s[6] * x + s[7] * y + s[8] * z + s[9])
+        if q < 0:
+            return 1, -1, -1
+    y = f32(p["lengthy"] / f32(2)) + y
+    z = f32(p["lengthz"] / f32(2)) + z
+    py, pz = f32(p["MODy"] + p["Mspacey"]), f32(p["MODz"] + p["Mspacez"])
+    My = int(f32(y / py)) if np.floor(f32(y / py)) > 0 else 0
+    Mz = int(f32(z / pz)) if np.floor(f32(z / pz)) > 0 else 0
+    M = Mz * moduleNy + My
+    y = f32(y - f32(f32(My) * py)); z = f32(z - f32(f32(Mz) * pz))
+    if y > p["MODy"] or z > p["MODz"]:
+        return 1, M, -1
+    cy, cz = f32(p["LSOy"] + p["spacey"]), f32(p["LSOz"] + p["spacez"])
+    Ly = int(f32(y / cy)) if np.floor(f32(y / cy)) > 0 else 0
+    Lz = int(f32(z / cz)) if np.floor(f32(z / cz)) > 0 else 0
+    L = Lz * crystalNy + Ly
+    y = f32(y - f32(f32(Ly) * cy)); z = f32(z - f32(f32(Lz) * cz))
+    if y > p["LSOy"] or z > p["LSOz"]:
+        return 1, M, L
+    return 0, M, L
+
+
+def test_crystal_search_equals_a_literal_walk_of_the_reference(units):
+    panels, mat, dens, counts = refio.parse_geometry(parity.EXAMPLE / "input" / "config8.geo")
+    moduleNy, crystalNy, moduleN, crystalN = counts
+    p = panels[0]
+    rng = np.random.default_rng(2)
+    n = 4000
+    xyz = np.stack([rng.uniform(-p["lengthx"], 0, n), rng.uniform(-p["lengthy"] / 2, p["lengthy"] / 2, n),
+                    rng.uniform(-p["lengthz"] / 2, p["lengthz"] / 2, n)], 1).astype(f32)
+    # points on and next to module / crystal borders
+    pitch = f32(p["MODy"] + p["Mspacey"])
+    xyz[:200, 1] = (-p["lengthy"] / 2 + pitch * rng.integers(0, moduleNy, 200) + rng.choice([0.0, 1e-6, -1e-6, float(p["MODy"])], 200)).astype(f32)
+    excluded = []
+    for surfaces in ([], [[0, 0, 0, 0, 0, 0, 0, 0, 0, 1]], [[0, 1, 1, 0, 0, 0, 0, 0, 0, -4.0]]):
+        sf = np.asarray(surfaces, f32).ravel() if surfaces else np.zeros(10, f32)
+        ids = np.zeros((n, 3), np.int32)
+        pc = np.ascontiguousarray(panels[:1])
+        units.u_crystal_search(_p(pc), C.c_int(moduleNy), C.c_int(crystalNy), C.c_int(len(surfaces)), _p(sf), C.c_int64(n), _p(xyz), _p(ids))
+        want = np.array([crystal_search_literal(p, moduleNy, crystalNy, surfaces, *xyz[i]) for i in range(n)], np.int32)
+        # the ids the reference leaves unset on an early return are the caller's previous values: compare what is defined
+        assert np.array_equal(ids[:, 0], want[:, 0])
+        reached_M = want[:, 1] >= 0
+        assert np.array_equal(ids[reached_M, 1], want[reached_M, 1])
+        reached_L = want[:, 2] >= 0
+        assert np.array_equal(ids[reached_L, 2], want[reached_L, 2])
+        assert (want[:, 0] == 0).sum() > 0.3 * n and ids[:, 1].max() < moduleN and ids[:, 2].max() < crystalN
+        excluded.append(int((want[:, 0] == 1).sum()))
+    # the inert surface of the shipped input changes nothing; y^2 + z^2 - 4 < 0 takes the crystals within 2 cm of the x axis out
+    assert excluded[0] == excluded[1] < excluded[2] and excluded[2] - excluded[0] > 50
+
+
+# ------------------------------------------------------------------------------------------------ D1 adder, D2 readout
+def _fma32(a, b, c):
+    """float32 fma(a, b, c): exact product and sum, one rounding (the contraction is spelled out)."""
+    return f32(float(Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c))))
+
+
+def _centroid(x0, e0, x1, e1):
+    return f32(_fma32(x0, e0, f32(x1 * e1)) / f32(e0 + e1))
+
+
+def adder_readout_literal(hits, depth, policy, moduleN, cap=6):
+    """adder (gPET_kernals.cu:737-755) over the hits of one photon, then readout (:756-813)."""
+    ev = []
+    for h in hits:
+        h = h.copy()
+        for e in ev:
+            if e["siten"] == h["siten"]:
+                for ax in "xyz":
+                    e[ax] = _centroid(e[ax], e["E"], h[ax], h["E"])
+                e["E"] = f32(e["E"] + h["E"])
+                break
+        else:
+            if len(ev) < cap:
+                ev.append(h)
+    if depth == 3 or not ev:
+        return ev
+    if policy == 1:
+        depth = 2
+    for e in ev:
+        e["siten"] = 0 if depth == 0 else e["pann"] if depth == 1 else e["pann"] * moduleN + e["modn"]
+    out = []
+    for i in range(len(ev)):
+        e0 = ev[i].copy()
+        if e0["t"] > MAXT * 0.1:
+            continue
+        for j in range(i + 1, len(ev)):
+            e = ev[j]
+            if e["t"] > MAXT * 0.1:
+                continue
+            if e["parn"] == e0["parn"] and e["siten"] == e0["siten"]:
+                if policy == 1:
+                    for ax in "xyz":
+                        e0[ax] = _centroid(e0[ax], e0["E"], e[ax], e["E"])
+                    e0["E"] = f32(e0["E"] + e["E"])
+                    e["t"] = MAXT
+                    continue
+                e0 = e0 if e0["E"] > e["E"] else e.copy()
+                e["t"] = MAXT
+        out.append(e0)
+    return out
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+@pytest.mark.parametrize("depth", [0, 1, 2, 3])
+def test_adder_and_readout_equal_a_literal_walk_of_the_reference(units, depth, policy):
+    rng = np.random.default_rng(10 + 2 * depth + policy)
+    moduleN, crystalN = 117, 64
+    nout_seen = set()
+    for trial in range(300):
+        n = int(rng.integers(1, 9))
+        hits = np.zeros(n, orc.EVENT_DTYPE)
+        hits["parn"] = 4242
+        hits["pann"] = 3
+        hits["modn"] = rng.choice([5, 6, 7], n)                     # few modules / crystals: merges at every level
+        hits["cryn"] = rng.choice([1, 2, 3], n)
+        hits["siten"] = (hits["pann"] * moduleN + hits["modn"]) * crystalN + hits["cryn"]
+        hits["eventid"] = 2121
+        hits["t"] = 100.0 + np.sort(rng.uniform(0, 1e-3, n))
+        hits["E"] = rng.choice([30e3, 120e3, 120e3, 341e3], n).astype(f32) * rng.choice([1.0, 1.0, 0.7], n).astype(f32)
+        for ax in "xyz":
+            hits[ax] = rng.uniform(-2, 2, n)
+        out = np.zeros(8, orc.EVENT_DTYPE)
+        ovf = C.c_int()
+        nout = units.u_adder_readout(_p(hits), C.c_int(n), C.c_int(depth), C.c_int(policy), C.c_int(moduleN), _p(out), C.byref(ovf))
+        want = adder_readout_literal([dict(zip(hits.dtype.names, h)) for h in hits.tolist()], depth, policy, moduleN)
+        assert nout == len(want), (trial, nout, len(want))
+        for k, w in enumerate(want):
+            got = dict(zip(out.dtype.names, out[k].tolist()))
+            for name in out.dtype.names:
+                assert got[name] == (float(w[name]) if name in "Exyzt" else w[name]), (trial, k, name, got[name], w[name])
+        nout_seen.add(nout)
+    assert len(nout_seen) >= 3 or (depth <= 1 and policy == 0)      # one panel: world and panel level leave one event
