@@ -242,3 +242,70 @@ def test_adder_and_readout_equal_a_literal_walk_of_the_reference(units, depth, p
                 assert got[name] == (float(w[name]) if name in "Exyzt" else w[name]), (trial, k, name, got[name], w[name])
         nout_seen.add(nout)
     assert len(nout_seen) >= 3 or (depth <= 1 and policy == 0)      # one panel: world and panel level leave one event
+
+
+# ------------------------------------------------------------------------------------------------ S2, S3 source sampling
+def _chi2_uniform(u, bins=40):
+    got, _ = np.histogram(u, bins, (0.0, 1.0))
+    e = u.size / bins
+    return ((got - e) ** 2 / e).sum() / (bins - 1)
+
+
+def test_source_oracle_samples_what_setposition_specifies():
+    """orc_source against the physics setPosition / getPositionFromShape state (gPET_kernals.cu:445-561): positions
+    uniform in box / cylinder / sphere, decay times from the exponential truncated to the frame, photon 1 isotropic,
+    photon 2 turned by a Gaussian acollinearity with E = mc2 -+ delta mc2 / 2, ids and times shared as the reference does."""
+    n = 300000
+    shapes = [0, 1, 2]
+    coeff = np.array([[1.0, -2.0, 0.5, 0.4, 0.6, 0.8], [-3.0, 1.0, 2.0, 0.7, 1.5, 0.0], [4.0, 4.0, -1.0, 0.9, 0.0, 0.0]], np.float32)
+    cum = np.array([n // 3, 2 * n // 3, n], np.uint64)
+    tau = np.array([6586.26 * 1.442695, 122.24 * 1.442695, 1223.4 * 1.442695])   # F-18, O-15, C-11 mean lives (s)
+    dt = 90.0
+    frac = 1.0 - np.exp(-dt / tau)
+    sigma = 0.0037056
+    first = 5_000_000_000                                                        # photon numbers wrap modulo 2^32
+    ph = orc.source(cum, shapes, coeff.ravel(), tau, frac, 30.0, first, sigma, n, 99)
+    a, b = ph[0::2], ph[1::2]
+    assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["t"], b["t"]) and np.array_equal(a["eventid"], b["eventid"])
+    k = np.arange(n, dtype=np.uint64)
+    assert np.array_equal(a["eventid"].view(np.uint32), ((first + k) & 0xFFFFFFFF).astype(np.uint32))
+    assert np.array_equal(a["parn"].view(np.uint32), ((2 * (first + k)) & 0xFFFFFFFF).astype(np.uint32))
+    assert np.array_equal(b["parn"].view(np.uint32), ((2 * (first + k) + 1) & 0xFFFFFFFF).astype(np.uint32))
+    assert np.all(a["nscat"] == 0)
+    lo = 0
+    for s, hi in enumerate(cum.astype(int)):
+        q = a[lo:hi]
+        c = coeff[s]
+        dx, dy, dz = q["x"] - c[0], q["y"] - c[1], q["z"] - c[2]
+        if shapes[s] == 0:       # box: centre and full lengths
+            for d, full in ((dx, c[3]), (dy, c[4]), (dz, c[5])):
+                assert np.abs(d).max() <= full / 2 * (1 + 1e-6) and _chi2_uniform(d / full + 0.5) < 1.7
+        elif shapes[s] == 1:     # cylinder along z: radius, height
+            r2 = (dx * dx + dy * dy) / c[3] ** 2
+            assert r2.max() <= 1 + 1e-5 and _chi2_uniform(r2) < 1.7 and _chi2_uniform(dz / c[4] + 0.5) < 1.7
+            assert _chi2_uniform(np.arctan2(dy, dx) / (2 * np.pi) + 0.5) < 1.7
+        else:                    # sphere: radius (cbrtf of a uniform)
+            r3 = (dx * dx + dy * dy + dz * dz) ** 1.5 / c[3] ** 3
+            assert r3.max() <= 1 + 1e-5 and _chi2_uniform(r3) < 1.7
+            assert _chi2_uniform(dz / np.sqrt(dx * dx + dy * dy + dz * dz) / 2 + 0.5) < 1.7
+        # decay time: inverse transform of the exponential truncated to [0, dt)
+        p = q["t"] * 1e-6 - 30.0
+        assert p.min() >= 0 and p.max() < dt
+        assert _chi2_uniform((1.0 - np.exp(-p / tau[s])) / frac[s]) < 1.7
+        lo = hi
+    # photon 1 isotropic
+    assert np.abs(np.sqrt(a["vx"] ** 2 + a["vy"] ** 2 + a["vz"] ** 2) - 1).max() < 1e-5
+    assert _chi2_uniform(a["vz"] / 2 + 0.5) < 1.7 and _chi2_uniform(np.arctan2(a["vy"], a["vx"]) / (2 * np.pi) + 0.5) < 1.7
+    # photon 2: angle pi - |delta| to photon 1, delta ~ N(0, sigma); energies mc2 +- delta mc2 / 2
+    da = (a["E"].astype(np.float64) - MC2) / (MC2 / 2)
+    db = (b["E"].astype(np.float64) - MC2) / (MC2 / 2)
+    assert np.abs(da + db).max() < 1e-6 * 4 and abs(da.mean()) < 4 * sigma / np.sqrt(n)
+    assert abs(da.std() / sigma - 1) < 0.01
+    cosang = (a["vx"].astype(np.float64) * b["vx"] + a["vy"].astype(np.float64) * b["vy"] + a["vz"].astype(np.float64) * b["vz"])
+    cross = np.linalg.norm(np.cross(np.stack([a["vx"], a["vy"], a["vz"]], 1).astype(np.float64),
+                                    np.stack([b["vx"], b["vy"], b["vz"]], 1).astype(np.float64)), axis=1)
+    assert cosang.max() < -0.999                                   # back to back
+    assert abs(np.sqrt((cross ** 2).mean()) / sigma - 1) < 0.01    # sin|delta| ~ |delta|
+    # the same delta turns the photon and splits the energy -- up to the reference's fp32 rotate(-cos(delta)): cos(delta)
+    # is 1 - delta^2/2 rounded to a float, which resolves angles only to sqrt(2 * 2^-24) = 3.5e-4 rad near zero
+    assert np.abs(cross - np.abs(da)).max() < 4e-4 and (cross == 0).mean() > 0.02
