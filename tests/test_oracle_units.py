@@ -309,3 +309,43 @@ def test_source_oracle_samples_what_setposition_specifies():
     # the same delta turns the photon and splits the energy -- up to the reference's fp32 rotate(-cos(delta)): cos(delta)
     # is 1 - delta^2/2 rounded to a float, which resolves angles only to sqrt(2 * 2^-24) = 3.5e-4 rad near zero
     assert np.abs(cross - np.abs(da)).max() < 4e-4 and (cross == 0).mean() > 0.02
+
+
+# ------------------------------------------------------------------------------------------------ P1 Woodcock tracking
+@pytest.mark.skipif(not parity.have_tables(), reason="packed tables not built")
+@pytest.mark.parametrize("E", [511e3, 140e3])
+def test_phantom_oracle_attenuates_like_beer_lambert_through_layers(E):
+    """photon() (gPET_kernals.cu:256-345) is Woodcock tracking: whatever the majorant, the photons that cross water,
+    bone and air without a real interaction must be exp(-sum mu_i L_i) of the beam, mu_i = Sigma_tot(E) rho_i from the
+    same tables.  Host-only context: tables and majorants come from the product's loaders, the walk is the oracle's."""
+    n = 64
+    mat = np.zeros((n, n, n), np.int32); den = np.full((n, n, n), 1.2048e-3, np.float32)      # air, x fastest
+    mat[:, :, :22] = 1; den[:, :, :22] = 1.0                                                  # water   x < -1.0
+    mat[:, :, 22:37] = 3; den[:, :, 22:37] = 1.85                                             # bone    -1.0 <= x < 0.5
+    s = parity.Setup(-1, phantom=(mat, den), size=6.4)
+    nph = 400000
+    ph = np.zeros(nph, orc.PHOTON_DTYPE)
+    ph["x"] = -3.0; ph["y"] = 0.05; ph["z"] = 0.05
+    ph["vx"] = 1.0
+    ph["E"] = E
+    ph["t"] = 1.0 + np.arange(nph)
+    ph["parn"] = np.arange(nph); ph["eventid"] = np.arange(nph) // 2
+    out = orc.phantom(ph, s.mat, s.den, s.offset, s.size, s.tab_ph, s.eabs, 4321)
+    alive = out["t"] > 0
+    straight = alive & (out["nscat"] == 0)
+    assert np.all(out["E"][straight] == np.float32(E)) and np.all(out["vx"][straight] == 1.0)
+    assert np.all(out["x"][straight] > 3.1)                     # they left through the far face (overshoot kept, quirk 2)
+    # time of flight of the straight ones: path / c
+    path = out["x"][straight].astype(np.float64) + 3.0
+    assert np.abs(out["t"][straight] - ph["t"][straight] - path / 29979.2458).max() < 1e-6
+    energy = s.energy.astype(np.float64)
+    dims = s.ctx.table_dims()
+    lam = np.array([np.interp(E, energy, row.astype(np.float64)) for row in s.ctx.table(0).reshape(dims["nmat"], dims["nen"])])
+    mu = lam[1] * 1.0 * 2.0 + lam[3] * 1.85 * 1.5 + lam[0] * 1.2048e-3 * 2.7
+    want = np.exp(-mu)
+    got = straight.mean()
+    assert abs(got - want) < 4 * np.sqrt(want * (1 - want) / nph) + 2e-4, (E, got, want)
+    # the interacting rest: scattered (alive, nscat > 0) or photo-absorbed (dead); at 511 keV in water and bone nearly all scatter
+    absorbed = (~alive).mean()
+    assert (absorbed < 0.02) if E > 300e3 else (0.01 < absorbed < 0.2)
+    s.close()
