@@ -349,3 +349,57 @@ def test_phantom_oracle_attenuates_like_beer_lambert_through_layers(E):
     absorbed = (~alive).mean()
     assert (absorbed < 0.02) if E > 300e3 else (0.01 < absorbed < 0.2)
     s.close()
+
+
+# ------------------------------------------------------------------------------------------------ X1 detector transport
+@pytest.mark.skipif(not parity.have_tables(), reason="packed tables not built")
+def test_detector_oracle_stops_photons_like_beer_lambert_in_one_crystal():
+    """photonde (gPET_kernals.cu:839-1233): a beam down the axis of one crystal stays in crystal material over the panel's
+    whole depth.  Compton and photoelectric interactions are recorded as hits, Rayleigh ones only turn the photon, so the
+    first hits that still lie ON the beam axis are the photons whose first interaction of any kind was a recorded one:
+    (1 - f_Rayleigh) (1 - exp(-mu L)) of the beam, at depths distributed as exp(-mu x), Compton : photoelectric as the
+    partial cross sections; the deposited energies of a photon never add up to more than it brought."""
+    s = parity.Setup(-1, phantom="air", n=8)
+    p = s.panels[0]
+    moduleNy, crystalNy = int(s.counts4[0]), int(s.counts4[1])
+    ly = -p["lengthy"] / 2 + 4 * (p["MODy"] + p["Mspacey"]) + 3 * (p["LSOy"] + p["spacey"]) + p["LSOy"] / 2     # centre of a crystal
+    lz = -p["lengthz"] / 2 + 6 * (p["MODz"] + p["Mspacez"]) + 2 * (p["LSOz"] + p["spacez"]) + p["LSOz"] / 2
+    ux = np.array([p["UniXx"], p["UniXy"], p["UniXz"]], np.float64); uy = np.array([p["UniYx"], p["UniYy"], p["UniYz"]], np.float64)
+    uz = np.array([p["UniZx"], p["UniZy"], p["UniZz"]], np.float64)
+    o = np.array([p["offsetx"], p["offsety"], p["offsetz"]], np.float64)
+    depth_dir = ux * float(p["directionx"])
+    start = o - 0.05 * depth_dir + ly * uy + lz * uz
+    nph = 200000
+    ph = np.zeros(nph, orc.PHOTON_DTYPE)
+    ph["x"], ph["y"], ph["z"] = start
+    ph["vx"], ph["vy"], ph["vz"] = depth_dir
+    ph["E"] = 511e3
+    ph["t"] = 1.0 + np.arange(nph)
+    ph["parn"] = np.arange(nph); ph["eventid"] = np.arange(nph) // 2
+    res = orc.detector(ph, s.panels, s.counts4, s.pmat, s.pdens, s.surfaces, s.tab_det, s.eabs, 2, 1, 2468)
+    assert res["entered"] == nph
+    hits = res["hits"]
+    assert np.all(hits["pann"] == p["panel"])
+    assert np.all(np.diff(hits["parn"]) >= 0)                            # hits are appended in photon order
+    first = hits[np.r_[True, hits["parn"][1:] != hits["parn"][:-1]]]
+    on_axis = first[(np.abs(first["y"] - ly) < 1e-5) & (np.abs(first["z"] - lz) < 1e-5)]
+    assert on_axis.size > 0.9 * first.size
+    assert np.all(on_axis["modn"] == 6 * moduleNy + 4) and np.all(on_axis["cryn"] == 2 * crystalNy + 3)
+    dims = s.ctx.table_dims()
+    xs = {k: np.interp(511e3, s.energy.astype(np.float64), s.ctx.table(k).reshape(dims["nmat"], dims["nen"])[s.pmat[0]].astype(np.float64))
+          for k in (0, 1, 3)}                                               # total, Compton, Rayleigh (cm^2/g)
+    mu = xs[0] * float(s.pdens[0])
+    L = float(p["lengthx"])
+    f_c, f_r = xs[1] / xs[0], xs[3] / xs[0]
+    want = (1 - f_r) * (1 - np.exp(-mu * L))
+    got = on_axis.size / nph
+    assert abs(got - want) < 4 * np.sqrt(want * (1 - want) / nph) + 2e-4, (got, want)
+    depth = np.abs(on_axis["x"].astype(np.float64))
+    assert depth.max() <= L * (1 + 1e-6)
+    assert _chi2_uniform((1 - np.exp(-mu * depth)) / (1 - np.exp(-mu * L))) < 1.7
+    share_c = f_c / (1 - f_r)
+    assert abs(np.isin(on_axis["type"], (1, 2)).mean() - share_c) < 4 * np.sqrt(share_c * (1 - share_c) / on_axis.size) + 1e-3
+    assert np.all(np.isin(hits["type"], (1, 2, 4)))                          # Rayleigh leaves no hit
+    dep = np.bincount(hits["parn"], weights=hits["E"].astype(np.float64), minlength=nph)
+    assert dep.max() <= 511e3 * (1 + 1e-6) and (np.abs(dep - 511e3) < 1.0).mean() > 0.3      # full absorption is common in LSO
+    s.close()
