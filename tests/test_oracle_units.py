@@ -403,3 +403,39 @@ def test_detector_oracle_stops_photons_like_beer_lambert_in_one_crystal():
     dep = np.bincount(hits["parn"], weights=hits["E"].astype(np.float64), minlength=nph)
     assert dep.max() <= 511e3 * (1 + 1e-6) and (np.abs(dep - 511e3) < 1.0).mean() > 0.3      # full absorption is common in LSO
     s.close()
+
+
+# ------------------------------------------------------------------------------------------------ D3 blur
+@pytest.mark.parametrize("policy", [0, 1])
+def test_blur_oracle_has_the_specified_resolution(policy):
+    """blur (gPET_kernals.cu:814-837): E' = E + N(0,1) R E / 2.35482 with R = sqrt(Eref/E) Rref (policy 0) or
+    Rref + slope (E - Eref) / 1e6 (policy 1); spatial blur N(0, Sblur) per axis; time blur (extension) N(0, sigma_t)."""
+    n = 200000
+    rng = np.random.default_rng(3)
+    ev = np.zeros(n, orc.EVENT_DTYPE)
+    ev["parn"] = np.arange(n); ev["eventid"] = np.arange(n) // 2
+    ev["siten"] = np.arange(n)                       # one event per site: dead time has nothing to do
+    ev["pann"] = 0; ev["modn"] = np.arange(n) % 117; ev["cryn"] = np.arange(n) % 64
+    ev["t"] = 10.0 + 5.0 * np.arange(n)
+    ev["E"] = np.where(np.arange(n) % 2 == 0, 511e3, 300e3).astype(np.float32)
+    Eref, Rref, slope, sblur, tblur = 511e3, 0.12, 0.2, 0.07, 0.3
+    p, d = parity.make_digi_params(dead_level=3, threshold_eV=0.0, ewin_min=0.0, ewin_max=2e6, blur_policy=policy, blur_Eref=Eref,
+                                   blur_Rref=Rref, blur_slope=slope, blur_space=sblur, time_blur_sigma_us=tblur)
+    s, counts, _ = orc.digitize(ev, p)
+    assert s.size == n
+    s = s[np.argsort(s["parn"])]
+    for E0 in (511e3, 300e3):
+        m = ev["E"] == np.float32(E0)
+        R = np.sqrt(Eref / E0) * Rref if policy == 0 else Rref + slope * (E0 - Eref) / 1e6
+        sig = R * E0 / 2.35482
+        z = (s["E"][m].astype(np.float64) - E0) / sig
+        assert abs(z.mean()) < 4 / np.sqrt(m.sum()) and abs(z.std() - 1) < 0.01
+        from math import erf
+        u = 0.5 * (1 + np.vectorize(erf)(z / np.sqrt(2)))
+        assert _chi2_uniform(u) < 1.7                                   # Gaussian, not just the right width
+    for ax in "xyz":
+        dxyz = s[ax].astype(np.float64) - ev[ax]
+        assert abs(dxyz.mean()) < 4 * sblur / np.sqrt(n) and abs(dxyz.std() / sblur - 1) < 0.01
+    dt = s["t"] - ev["t"]
+    assert abs(dt.mean()) < 4 * tblur / np.sqrt(n) and abs(dt.std() / tblur - 1) < 0.01
+    assert abs(np.corrcoef(dt, s["E"].astype(np.float64) - ev["E"])[0, 1]) < 0.01     # independent draws (Box-Muller sine / cosine)
