@@ -36,3 +36,11 @@ int u_adder_readout(const orc_event* hits, int n, int depth, int policy, int mod
     for (int k = 0; k < nout; k++) out[k] = evs[k];
     return nout;
 }
+
+void u_sample_ek_positron(const float* coef8, uint64_t seed, int64_t n, float* ek_eV) {
+    for (int64_t i = 0; i < n; i++) {
+        orc_rng g;
+        rng_init(&g, seed, (uint64_t)i, 0u);
+        ek_eV[i] = sample_ek_positron(coef8, &g);
+    }
+}

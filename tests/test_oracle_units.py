@@ -439,3 +439,27 @@ def test_blur_oracle_has_the_specified_resolution(policy):
     dt = s["t"] - ev["t"]
     assert abs(dt.mean()) < 4 * tblur / np.sqrt(n) and abs(dt.std() / tblur - 1) < 0.01
     assert abs(np.corrcoef(dt, s["E"].astype(np.float64) - ev["E"])[0, 1]) < 0.01     # independent draws (Box-Muller sine / cosine)
+
+
+# ------------------------------------------------------------------------------------------------ S4 positron energy
+@pytest.mark.parametrize("row", [0, 1, 2])
+def test_positron_energy_oracle_follows_the_fitted_spectrum(units, row):
+    """sampleEkPositron (gPET_kernals.cu:420-443): rejection sampling of the total energy under the six-coefficient
+    polynomial of data/isotopes.txt (cut at zero and at the stated pdf maximum), returned as kinetic energy in eV."""
+    lines = (parity.EXAMPLE / "data" / "isotopes.txt").read_text().splitlines()
+    vals = np.array(lines[2 + row].split(), np.float64)
+    coef8 = vals[2:10].astype(f32)                     # Emax (MeV, total), pdf maximum, six coefficients
+    n = 300000
+    ek = np.zeros(n, f32)
+    units.u_sample_ek_positron(_p(coef8), C.c_uint64(5), C.c_int64(n), _p(ek))
+    emax = float(coef8[0])
+    E = ek.astype(np.float64) * 1e-6 + 0.511
+    assert E.min() >= 0.511 and E.max() <= emax * (1 + 1e-6)
+    xs = np.linspace(0.511, emax, 40 * 200 + 1)
+    pdf = np.clip(sum(float(coef8[2 + i]) * xs ** (5 - i) for i in range(6)), 0.0, float(coef8[1]))
+    cdf = np.concatenate([[0.0], np.cumsum(0.5 * (pdf[1:] + pdf[:-1]) * np.diff(xs))])
+    expect = np.diff(cdf[::200]) / cdf[-1] * n
+    got, _ = np.histogram(E, np.linspace(0.511, emax, 41))
+    m = expect > 20
+    assert m.sum() > 30 and (((got - expect) ** 2 / np.maximum(expect, 1e-9))[m]).sum() / (m.sum() - 1) < 1.8
+    assert 0.2 * (emax - 0.511) < E.mean() - 0.511 < 0.5 * (emax - 0.511)      # a beta spectrum: mean near a third of the end point
