@@ -44,3 +44,7 @@ void u_sample_ek_positron(const float* coef8, uint64_t seed, int64_t n, float* e
         ek_eV[i] = sample_ek_positron(coef8, &g);
     }
 }
+
+void u_surface_lookup(const float* surf, int mat, int ncp, int ne, int64_t n, const float* xe, const float* xcp, float* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = surface_lookup(surf, mat, ncp, ne, xe[i], xcp[i]);
+}

@@ -517,3 +517,52 @@ def test_positron_range_oracle_walks_a_water_equivalent_gaussian_path():
     assert 0.15 < in_water < 0.25 and 0.02 < crossed.mean() < 0.5 * in_water
     assert np.abs(weq[~away] - r[~away]).max() < 0.1 * np.sqrt(3) * 3.0 + 1e-3
     assert np.all(weq[~away] <= r[~away] + 2e-4)                                                # the habit only ever shortens the walk
+
+
+# ------------------------------------------------------------------------------------------------ P4, P5 surface reads
+def test_surface_lookup_is_the_linear_texture_fetch_of_the_reference(units):
+    """comsam (table) / rylsam read cos(theta) with tex3D(E idE + 0.5, U idCP + 0.5, mat + 0.5) from a linear-filter,
+    clamp-addressed texture (gPET_kernals.cu:80-85, 140-145; initialize.cu:552-565): texel centres sit at i + 0.5, so this
+    is the bilinear interpolation of the table at (E / dE, U / dCP), held at the borders."""
+    from scipy.interpolate import RegularGridInterpolator
+    rng = np.random.default_rng(4)
+    nmat, ncp, ne = 3, 31, 17
+    surf = np.sort(rng.uniform(-1, 1, (nmat, ncp, ne)).astype(f32), axis=1)        # an inverse CDF grows with U
+    n = 50000
+    xe = rng.uniform(-1.5, ne + 0.5, n).astype(f32)
+    xcp = rng.uniform(-1.5, ncp + 0.5, n).astype(f32)
+    xe[:100] = rng.integers(0, ne, 100); xcp[:100] = rng.integers(0, ncp, 100)      # exactly on the nodes
+    for mat in range(nmat):
+        out = np.zeros(n, f32)
+        units.u_surface_lookup(_p(surf), C.c_int(mat), C.c_int(ncp), C.c_int(ne), C.c_int64(n), _p(xe), _p(xcp), _p(out))
+        interp = RegularGridInterpolator((np.arange(ncp), np.arange(ne)), surf[mat].astype(np.float64))
+        want = interp(np.stack([np.clip(xcp, 0, ncp - 1), np.clip(xe, 0, ne - 1)], 1))
+        assert np.abs(out - want).max() < 3e-7 * 4
+        # on a node the table value itself (to an ulp at the last row / column, where the fetch is p0 + 1 * (p1 - p0))
+        assert np.abs(out[:100] - surf[mat][xcp[:100].astype(int), xe[:100].astype(int)]).max() < 1.5e-7
+
+
+# ------------------------------------------------------------------------------------------------ getDistance
+@pytest.mark.skipif(not parity.have_tables(), reason="packed tables not built")
+def test_recording_sphere_oracle_puts_escaped_photons_on_the_sphere():
+    """getDistance + the RECORDPSF == -1 branch of photon() (gPET_kernals.cu:148-171, 288-294): a photon that leaves the
+    phantom is moved along its direction onto the recording sphere, its clock changed by the path."""
+    s = parity.Setup(-1, phantom="cylinder", n=32)
+    rng = np.random.default_rng(6)
+    ph = parity.isotropic_photons(50000, rng, pos_sigma=0.1)
+    sphere = (0.1, -0.2, 0.05, 5.0)
+    plain = orc.phantom(ph, s.mat, s.den, s.offset, s.size, s.tab_ph, s.eabs, s.seed)
+    rec = orc.phantom(ph, s.mat, s.den, s.offset, s.size, s.tab_ph, s.eabs, s.seed, record_sphere=sphere)
+    alive = plain["t"] > 0
+    assert np.array_equal(alive, rec["t"] > 0) and alive.mean() > 0.9
+    a, b = plain[alive], rec[alive]
+    pa = np.stack([a["x"], a["y"], a["z"]], 1).astype(np.float64); pb = np.stack([b["x"], b["y"], b["z"]], 1).astype(np.float64)
+    v = np.stack([a["vx"], a["vy"], a["vz"]], 1).astype(np.float64)
+    assert np.array_equal(a["vx"], b["vx"]) and np.array_equal(a["E"], b["E"]) and np.array_equal(a["nscat"], b["nscat"])
+    assert np.abs(np.linalg.norm(pb - np.array(sphere[:3]), axis=1) - sphere[3]).max() < 5e-4      # fp32 quadratic formula
+    step = ((pb - pa) * v).sum(1)
+    # along the direction -- forwards, or BACKWARDS for the photons whose last free flight (mean free path ~10 cm against a
+    # 1 cm phantom) carried them beyond the sphere: getDistance then returns the negative root and the clock runs back
+    assert np.abs(np.cross(pb - pa, v)).max() < 5e-4 and (step > 0).mean() > 0.2 and (step < 0).mean() > 0.2
+    assert np.abs((b["t"] - a["t"]) - step / 29979.2458).max() < 1e-7
+    s.close()
