@@ -566,3 +566,67 @@ def test_recording_sphere_oracle_puts_escaped_photons_on_the_sphere():
     assert np.abs(np.cross(pb - pa, v)).max() < 5e-4 and (step > 0).mean() > 0.2 and (step < 0).mean() > 0.2
     assert np.abs((b["t"] - a["t"]) - step / 29979.2458).max() < 1e-7
     s.close()
+
+
+# ------------------------------------------------------------------------------------------------ X1 panel entry, P7 majorants
+@pytest.mark.skipif(not parity.have_tables(), reason="packed tables not built")
+def test_detector_oracle_enters_the_panel_the_ray_hits(tmp_path):
+    """photonde prologue (gPET_kernals.cu:963-1009): the panel a photon enters and the local frame its hits are written
+    in, against a plain ray / rectangle intersection in numpy -- every first hit that has not been turned before lies on
+    the photon's ray when mapped back with the panel's axes, in the panel the ray meets, and the photons the oracle lets
+    in are the ones whose ray meets a front face."""
+    s = parity.Setup(-1, phantom="air", n=8)
+    rng = np.random.default_rng(12)
+    nph = 60000
+    ph = parity.isotropic_photons(nph, rng, pos_sigma=0.5)
+    res = orc.detector(ph, s.panels, s.counts4, s.pmat, s.pdens, s.surfaces, s.tab_det, s.eabs, 2, 1, 99)
+    o0 = np.stack([ph["x"], ph["y"], ph["z"]], 1).astype(np.float64); v = np.stack([ph["vx"], ph["vy"], ph["vz"]], 1).astype(np.float64)
+    # independent: first front face (plane through the offset, normal = local x) the ray meets inside its rectangle, moving inwards
+    best_t = np.full(nph, np.inf); best_p = np.full(nph, -1)
+    for k, p in enumerate(s.panels):
+        o = np.array([p["offsetx"], p["offsety"], p["offsetz"]], np.float64)
+        ux, uy, uz = (np.array([p[a + "x"], p[a + "y"], p[a + "z"]], np.float64) for a in ("UniX", "UniY", "UniZ"))
+        vn = v @ ux
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = ((o - o0) @ ux) / vn
+        hit = o0 + t[:, None] * v - o
+        ok = (t > 0) & (vn * float(p["directionx"]) > 0) & (np.abs(hit @ uy) < p["lengthy"] / 2) & (np.abs(hit @ uz) < p["lengthz"] / 2)
+        better = ok & (t < best_t)
+        best_t[better] = t[better]; best_p[better] = k
+    assert abs(res["entered"] - (best_p >= 0).sum()) <= 3                      # rays through the very edge of a face may round either way
+    hits = res["hits"]
+    first = hits[np.r_[True, hits["parn"][1:] != hits["parn"][:-1]]]
+    assert np.all(best_p[first["parn"]] >= 0)                                  # no hit without an entry
+    pan = s.panels[first["pann"]]
+    g = (np.stack([pan["offsetx"], pan["offsety"], pan["offsetz"]], 1).astype(np.float64)
+         + first["x"][:, None].astype(np.float64) * np.stack([pan["UniXx"], pan["UniXy"], pan["UniXz"]], 1)
+         + first["y"][:, None].astype(np.float64) * np.stack([pan["UniYx"], pan["UniYy"], pan["UniYz"]], 1)
+         + first["z"][:, None].astype(np.float64) * np.stack([pan["UniZx"], pan["UniZy"], pan["UniZz"]], 1))
+    off_ray = np.linalg.norm(np.cross(g - o0[first["parn"]], v[first["parn"]]), axis=1)
+    straight = off_ray < 2e-3
+    assert straight.mean() > 0.9                                               # the rest was Rayleigh-scattered before its first hit
+    assert np.array_equal(first["pann"][straight], best_p[first["parn"]][straight])
+    depth = ((g - o0[first["parn"]]) * v[first["parn"]]).sum(1) - best_t[first["parn"]]
+    assert depth[straight].min() > -1e-3                                       # behind the front face
+    # flight time of the straight ones: path / c
+    path = ((g - o0[first["parn"]]) * v[first["parn"]]).sum(1)
+    assert np.abs(first["t"][straight] - ph["t"][first["parn"]][straight] - path[straight] / 29979.2458).max() < 1e-6
+    s.close()
+
+
+@pytest.mark.skipif(not parity.have_tables(), reason="packed tables not built")
+def test_majorants_bound_every_material_at_every_energy():
+    """iniwck (initialize.cu:773-829, 919-966): Woodcock tracking is unbiased only if 1 / lambda_min(E) >= Sigma_tot(E) rho for
+    every material at its largest density -- for the oracle's majorant and for the product's (host side of libgpet_b200)."""
+    s = parity.Setup(-1, phantom="cylinder", n=32)
+    dims = s.ctx.table_dims()
+    lamph = s.ctx.table(0).reshape(dims["nmat"], dims["nen"]).astype(np.float64)
+    maxden = np.zeros(dims["nmat"])
+    for m in np.unique(s.mat):
+        maxden[m] = s.den[s.mat == m].max()
+    need = (lamph * maxden[:, None]).max(0)
+    maj_oracle = orc.build_majorant(lamph.astype(f32), maxden.astype(f32)).astype(np.float64)
+    assert np.all(maj_oracle >= need * (1 - 1e-6)) and np.all(maj_oracle <= need * (1 + 1e-5))       # tight: the maximum itself
+    maj_product = s.ctx.table(6).astype(np.float64)
+    assert maj_product.size == dims["nen"] and np.all(maj_product >= need * (1 - 1e-6)) and np.all(maj_product <= need * (1 + 1e-5))
+    s.close()
