@@ -630,3 +630,43 @@ def test_majorants_bound_every_material_at_every_energy():
     maj_product = s.ctx.table(6).astype(np.float64)
     assert maj_product.size == dims["nen"] and np.all(maj_product >= need * (1 - 1e-6)) and np.all(maj_product <= need * (1 + 1e-5))
     s.close()
+
+
+# ------------------------------------------------------------------------------------------------ whole transport vs the REAL reference
+@pytest.mark.skipif(not parity.have_tables(), reason="packed tables not built")
+@pytest.mark.parametrize("case", [0, 1])
+def test_oracle_transport_reproduces_the_reference_binarys_rates(case):
+    """Known answers from the reference itself: tests/golden/reference_transport_rates.json holds the per-pair counters the
+    reference's own CUDA build printed on the shipped example (tools/ref_pin.py on a B200, tools/make_reference_rates_fixture.py).
+    The CPU oracle -- source, phantom, detector, adder / readout, thresholder, dead time, energy window -- on the same
+    inputs must give the same hits, events and singles per annihilation pair within BASELINE.json's 1 % (plus 3 sigma of
+    both samples)."""
+    import json
+    ref = json.loads((parity.GOLDEN / "reference_transport_rates.json").read_text())["cases"][case]
+    window = float(ref["window_s"].split()[1])
+    s = parity.Setup(device=-1, phantom=parity.gen_inputs.cylinder_phantom(n=200), size=1.0)
+    src = refio.parse_sources(parity.EXAMPLE / "input" / ref["source"])
+    iso = refio.parse_isotopes(parity.EXAMPLE / "data" / "isotopes.txt")
+    tau = np.array([np.float64(iso[x["type"]]["halftime"]) * 1.442695 for x in src])
+    frac = -np.expm1(-window / tau)
+    weight = np.array([x["natom"] * frac[i] * iso[x["type"]]["ratio"] for i, x in enumerate(src)], np.float64)
+    n = 300000
+    per_src = np.floor(weight / weight.sum() * n).astype(np.uint64)
+    per_src[-1] += np.uint64(n - int(per_src.sum()))
+    ph = orc.source(np.cumsum(per_src), [x["shape"] for x in src], np.concatenate([x["coeff"] for x in src]), tau, frac, 0.0, 0,
+                    0.0037056, n, 2024)
+    ph = orc.phantom(ph, s.mat, s.den, s.offset, s.size, s.tab_ph, s.eabs, 2024)
+    res = orc.detector(ph, s.panels, s.counts4, s.pmat, s.pdens, s.surfaces, s.tab_det, s.eabs, 2, 1, 2024)
+    cfg = refio.parse_config(parity.EXAMPLE / "input_PET.in")
+    p, _ = parity.make_digi_params(readout_depth=cfg["rdepth"], readout_policy=cfg["rpolicy"], threshold_eV=float(cfg["Eth"]),
+                                   blur_policy=1, blur_Rref=0.0, blur_slope=0.0, blur_space=0.0, dead_level=cfg["dlevel"],
+                                   dead_type=cfg["dtype"], dead_time_us=float(cfg["dtime"]), ewin_min=float(cfg["Ewinmin"]),
+                                   ewin_max=float(cfg["Ewinmax"]))
+    singles, counts, _ = orc.digitize(res["events"], p)
+    got = {"hits": res["hits"].size / n, "events_adder": res["events"].size / n, "events_threshold": int(counts[1]) / n,
+           "singles": singles.size / n}
+    for k, g in got.items():
+        want = ref[k + "_per_pair"]
+        sig = np.sqrt(want / n + want / ref["reference_pairs"])                 # Poisson on both counts
+        assert abs(g - want) < 0.01 * want + 3 * sig, (ref["source"], k, g, want)
+    s.close()
