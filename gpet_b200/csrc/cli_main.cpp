@@ -1,4 +1,5 @@
-// gPET-compatible command line: `gpet_b200 input_PET.in [--data DIR] [--out DIR] [--seed N] [--coinc-window US]`.
+// gPET-compatible command line: `gpet_b200 input_PET.in [--data DIR] [--out DIR] [--seed N] [--device N] [--coinc-window US
+// [--coinc-policy 0|1] [--min-panel-diff N] [--pair-shift 0|1]]`.
 // Mirrors main() of the reference (main.cu:26-276): one positional input file, paths relative to the working
 // directory, outputs appended under ./output/ with the layouts output/readOutput.m reads.
 #include <chrono>
@@ -17,13 +18,16 @@ int main(int argc, char** argv) {
     std::string input = argv[1], data, out = "output";
     unsigned long long seed = 0x67504554ull;
     float cwin = 0.f;
-    int device = 0;
+    int device = 0, cpolicy = -1, cmindiff = -1, pair_shift = -1;
     for (int i = 2; i + 1 < argc; i += 2) {
         if (!strcmp(argv[i], "--data")) data = argv[i + 1];
         else if (!strcmp(argv[i], "--out")) out = argv[i + 1];
         else if (!strcmp(argv[i], "--seed")) seed = strtoull(argv[i + 1], nullptr, 0);
         else if (!strcmp(argv[i], "--coinc-window")) cwin = (float)atof(argv[i + 1]);
         else if (!strcmp(argv[i], "--device")) device = atoi(argv[i + 1]);
+        else if (!strcmp(argv[i], "--coinc-policy")) cpolicy = atoi(argv[i + 1]);      // 0 drop multiples, 1 all pairs with the opener
+        else if (!strcmp(argv[i], "--min-panel-diff")) cmindiff = atoi(argv[i + 1]);   // cyclic panel distance a pair needs
+        else if (!strcmp(argv[i], "--pair-shift")) pair_shift = atoi(argv[i + 1]);     // 1: photon PSF with records 2k, 2k+1 = one pair
         else { fprintf(stderr, "unknown option %s\n", argv[i]); return 1; }
     }
     auto t0 = std::chrono::steady_clock::now();
@@ -36,6 +40,9 @@ int main(int argc, char** argv) {
         gpet_digitizer_params d;
         gpet_get_digitizer(ctx, &d);
         d.coinc_window_us = cwin;
+        if (cpolicy >= 0) d.coinc_policy = cpolicy;
+        if (cmindiff >= 0) d.coinc_min_panel_diff = cmindiff;
+        if (pair_shift >= 0) d.coinc_pair_shift = pair_shift;
         gpet_set_digitizer(ctx, &d);
     }
     auto t1 = std::chrono::steady_clock::now();
