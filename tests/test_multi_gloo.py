@@ -22,6 +22,12 @@ def _free_port():
     return p
 
 
+def stats_ok(tot, world, fields):
+    tri = world * (world + 1) // 2
+    return (all(tot[name] == tri * (k + 1) for k, name in enumerate(fields))
+            and {"trues", "scatters", "randoms", "coincidences", "singles", "pairs"} <= set(fields))
+
+
 def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
@@ -44,9 +50,14 @@ def _worker(rank, world, port, q):
             except api.GpetError as e:
                 refused = e.code == -4                   # GPET_ERR_NO_DEVICE: no CPU fallback
         tot = multi.allreduce_tallies([my_pairs, len(mine), 1])
+        # the whole tally vector of a run (gpet_stats), coincidence classes included
+        st = api.Stats()
+        for k, name in enumerate(multi.TALLY_FIELDS):
+            setattr(st, name, (rank + 1) * (k + 1))
+        stats_tot = dict(zip(multi.TALLY_FIELDS, multi.allreduce_tallies(multi.stats_vector(st)).tolist()))
         gathered = [None] * world
         dist.all_gather_object(gathered, (mine, frames))
-        q.put((rank, mine, my_pairs, all_pairs, tot.tolist(), gathered, refused))
+        q.put((rank, mine, my_pairs, all_pairs, tot.tolist(), gathered, refused and stats_ok(stats_tot, world, multi.TALLY_FIELDS)))
     finally:
         dist.destroy_process_group()
 
