@@ -83,6 +83,21 @@ def test_digitizer_oracle_equals_a_literal_walk_of_the_reference_kernels(dead_le
             assert co["a"].tobytes() == s[ia].tobytes() and co["b"].tobytes() == s[ib].tobytes()
         kills += wcounts[1] - wcounts[2]
         npairs[policy] += len(wpairs)
+    # times on a grid of exactly the window and half the dead time: every comparison of the chain sits on its boundary
+    # (t < tdead + tau, t > t_prev + tau, t_b < t_a + W are all strict) and ties abound
+    ev = parity.random_events(900, rng, tmax=100.0, nsites=936)
+    ev["t"] = 10.0 + 0.25 * rng.integers(0, 500, ev.size)
+    ev["E"] = rng.uniform(100e3, 600e3, ev.size).astype(np.float32)
+    ev["siten"] = rng.integers(0, 6, ev.size); ev["pann"] = ev["siten"]; ev["modn"] = 0
+    for policy in (0, 1):
+        p, d = parity.make_digi_params(dead_level=dead_level, dead_type=dead_type, dead_time_us=0.5, coinc_window_us=0.25, coinc_policy=policy)
+        s, counts, co = orc.digitize(ev, p)
+        ws, wcounts, wpairs = pyref.digitize(ev, d)
+        assert [int(c) for c in counts] == wcounts and s.tobytes() == ws.astype(orc.EVENT_DTYPE).tobytes() and co.size == len(wpairs)
+        if wpairs:
+            ia, ib = np.array(wpairs).T
+            assert co["a"].tobytes() == s[ia].tobytes() and co["b"].tobytes() == s[ib].tobytes()
+        assert wcounts[1] - wcounts[2] > 50
     # dead time and both sorter policies had work to do (one site for the whole detector leaves no two singles in a window)
     assert kills > 100 and (dead_level == 0 or (npairs[0] > 30 and npairs[1] > 80))
 
