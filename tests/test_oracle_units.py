@@ -670,3 +670,41 @@ def test_oracle_transport_reproduces_the_reference_binarys_rates(case):
         sig = np.sqrt(want / n + want / ref["reference_pairs"])                 # Poisson on both counts
         assert abs(g - want) < 0.01 * want + 3 * sig, (ref["source"], k, g, want)
     s.close()
+
+
+# ------------------------------------------------------------------------------------------------ P4, P5, P6 in the phantom walk
+@pytest.mark.skipif(not parity.have_tables(), reason="packed tables not built")
+def test_phantom_oracle_single_scatters_obey_compton_kinematics():
+    """photon() (gPET_kernals.cu:304-334): a photon that interacted once leaves either with its energy untouched (Rayleigh)
+    or with E' = E / (1 + E / mc2 (1 - cos theta)) for the angle it was turned by (Compton with the cmpsf angle, the
+    energy from the free-electron relation, :66-88), and the shares follow the partial cross sections of water."""
+    n = 64
+    mat = np.ones((n, n, n), np.int32); den = np.ones((n, n, n), np.float32)                      # water
+    s = parity.Setup(-1, phantom=(mat, den), size=6.4)
+    nph = 300000
+    ph = np.zeros(nph, orc.PHOTON_DTYPE)
+    ph["x"] = -3.0; ph["y"] = 0.05; ph["z"] = 0.05
+    ph["vx"] = 1.0
+    ph["E"] = 511e3
+    ph["t"] = 1.0 + np.arange(nph)
+    ph["parn"] = np.arange(nph); ph["eventid"] = np.arange(nph) // 2
+    out = orc.phantom(ph, s.mat, s.den, s.offset, s.size, s.tab_ph, s.eabs, 555)
+    once = out[(out["t"] > 0) & (out["nscat"] == 1)]
+    assert once.size > 0.2 * nph
+    norm = np.sqrt(once["vx"].astype(np.float64) ** 2 + once["vy"].astype(np.float64) ** 2 + once["vz"].astype(np.float64) ** 2)
+    assert np.abs(norm - 1).max() < 1e-5
+    cos_t = once["vx"].astype(np.float64) / norm                                                   # the beam flew along +x
+    rayleigh = once["E"] == np.float32(511e3)
+    kappa = 511e3 / MC2
+    expect = 511e3 / (1.0 + kappa * (1.0 - cos_t[~rayleigh]))
+    assert np.abs(once["E"][~rayleigh] / expect - 1).max() < 2e-5
+    assert cos_t[rayleigh].mean() > 0.98                                                           # coherent scattering is forward peaked at 511 keV
+    dims = s.ctx.table_dims()
+    xs = {k: np.interp(511e3, s.energy.astype(np.float64), s.ctx.table(k).reshape(dims["nmat"], dims["nen"])[1].astype(np.float64)) for k in (1, 3)}
+    share = xs[3] / (xs[1] + xs[3])                                                                # Rayleigh among the scatters
+    # the once-scattered sample is biased by what happens afterwards (a Compton photon has less energy and a longer way out),
+    # so only the order of magnitude is an invariant here
+    assert 0.3 * share < rayleigh.mean() < 3 * share
+    # energy spectrum of the Compton ones stays inside the kinematic limits
+    assert once["E"][~rayleigh].min() >= 511e3 / (1 + 2 * kappa) * (1 - 1e-5)
+    s.close()
