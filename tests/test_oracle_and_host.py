@@ -167,6 +167,46 @@ def test_library_exports_every_declared_symbol():
     assert api.lib().gpet_abi_version() == 3
 
 
+def test_missing_or_stale_library_fails_loudly(monkeypatch, tmp_path):
+    """No CUDA library, no product: the Python mirror raises instead of computing anything itself, and refuses a library
+    built from another header version."""
+    monkeypatch.setattr(api, "_lib", None)
+    monkeypatch.setattr(api, "LIB_PATH", tmp_path / "libgpet_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        api.Context(0)
+    monkeypatch.undo()
+    monkeypatch.setattr(api, "_lib", None)
+    monkeypatch.setattr(api, "ABI_VERSION", api.ABI_VERSION + 1)
+    with pytest.raises(RuntimeError, match="ABI version"):
+        api.lib()
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under gpet_b200/ (Python or C++/CUDA) names it, the library does not link
+    it, and bench.py reaches it only inside its baseline legs."""
+    import ast
+    for f in (parity.ROOT / "gpet_b200" / "csrc").glob("*"):
+        includes = [l for l in f.read_text().splitlines() if l.lstrip().startswith("#include")]
+        assert not any("oracle" in l for l in includes), f
+    rules = [l for l in (parity.ROOT / "Makefile").read_text().splitlines() if not l.lstrip().startswith("#")]
+    assert not any("oracle" in l for l in rules)                      # the product's build never reaches into oracle/
+    for f in (parity.ROOT / "gpet_b200").glob("*.py"):
+        for node in ast.walk(ast.parse(f.read_text())):
+            names = [a.name for a in node.names] if isinstance(node, ast.Import) else [node.module or ""] if isinstance(node, ast.ImportFrom) else []
+            assert not any(n.split(".")[0] == "oracle" for n in names), f
+    deps = subprocess.run(["ldd", str(api.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "oracle" not in deps
+    tree = ast.parse((parity.ROOT / "bench.py").read_text())
+    importing = set()
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
+                importing.add(fn.name)
+    top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+    assert not any((getattr(n, "module", "") or "").startswith("oracle") for n in top)
+    assert importing <= {"cpu_baseline", "reference_line"}, importing
+
+
 def test_record_layouts():
     assert api.EVENT_DTYPE.itemsize == 48 and api.EVENT_DTYPE.fields["t"][1] == 24 and api.EVENT_DTYPE.fields["E"][1] == 32
     assert api.COINC_DTYPE.itemsize == 96 and api.HIT_DTYPE.itemsize == 48 and api.PHOTON_DTYPE.itemsize == 48
