@@ -708,3 +708,34 @@ def test_phantom_oracle_single_scatters_obey_compton_kinematics():
     # energy spectrum of the Compton ones stays inside the kinematic limits
     assert once["E"][~rayleigh].min() >= 511e3 / (1 + 2 * kappa) * (1 - 1e-5)
     s.close()
+
+
+# ------------------------------------------------------------------------------------------------ S6 positron PSF
+def test_positron_psf_oracle_makes_back_to_back_pairs_at_the_positrons_time():
+    """setPositionForPhoton (gPET_kernals.cu:563-604) without positron range: both photons start at the positron's
+    position AND time (the reference forgets the second photon's time and thereby loses it -- fixed),
+    photon 1 isotropic and independent of the positron's own direction, photon 2 back to back up to the acollinearity,
+    ids 2i / 2i+1 counted from the batch offset."""
+    n = 200000
+    rng = np.random.default_rng(21)
+    pos = np.zeros(n, orc.PHOTON_DTYPE)
+    pos["x"], pos["y"], pos["z"] = rng.uniform(-1, 1, (3, n)).astype(f32)
+    pos["vx"] = 1.0                                   # every positron flies along +x: must not show in the photons
+    pos["E"] = 0.3e6
+    pos["t"] = rng.uniform(1.0, 1e6, n)
+    first = 7_000_000
+    sigma = 0.0037056
+    out = orc.psf_positron(pos, first, np.ones((4, 4, 4), f32), (-1, -1, -1), (2, 2, 2), sigma, False, 31)
+    a, b = out[0::2], out[1::2]
+    for q in (a, b):
+        assert np.array_equal(q["x"], pos["x"]) and np.array_equal(q["y"], pos["y"]) and np.array_equal(q["z"], pos["z"])
+        assert np.array_equal(q["t"], pos["t"])
+        assert np.array_equal(q["eventid"], first + np.arange(n))
+    assert np.array_equal(a["parn"], 2 * (first + np.arange(n))) and np.array_equal(b["parn"], a["parn"] + 1)
+    assert _chi2_uniform(a["vz"] / 2 + 0.5) < 1.7 and _chi2_uniform(a["vx"] / 2 + 0.5) < 1.7
+    assert _chi2_uniform(np.arctan2(a["vy"], a["vx"]) / (2 * np.pi) + 0.5) < 1.7
+    va = np.stack([a["vx"], a["vy"], a["vz"]], 1).astype(np.float64); vb = np.stack([b["vx"], b["vy"], b["vz"]], 1).astype(np.float64)
+    assert (va * vb).sum(1).max() < -0.999
+    delta = (a["E"].astype(np.float64) - MC2) / (MC2 / 2)
+    assert abs(delta.std() / sigma - 1) < 0.01 and np.abs(delta + (b["E"].astype(np.float64) - MC2) / (MC2 / 2)).max() < 4e-6
+    assert abs(np.sqrt((np.linalg.norm(np.cross(va, vb), axis=1) ** 2).mean()) / sigma - 1) < 0.01
