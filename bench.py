@@ -229,8 +229,10 @@ ALG_BYTES = {
     "k_bucket_scatter": lambda c: 8 * c["events"] + 8 * c["alive"] + 16 * c["alive"],
     "k_bucket_rank": lambda c: 16 * c["alive"] + 16 * c["alive"],
     "k_deadtime_chain": lambda c: 12 * c["alive"] + c["alive"],
-    "k_emit_singles": lambda c: 16 * c["alive"] + 48 * c["singles"] + (48 + 12) * c["singles"],
-    "k_coinc": lambda c: 12 * c["singles"] + 8 * c["coinc"],
+    # singles: 48-byte record gathered and written, side arrays time (8) + panel, photon number, annihilation number (4 each)
+    "k_emit_singles": lambda c: 16 * c["alive"] + 48 * c["singles"] + (48 + 20) * c["singles"],
+    # the side arrays of every single, its scatter tag (1 byte), index pair + class byte per coincidence
+    "k_coinc": lambda c: (20 + 1) * c["singles"] + (8 + 1) * c["coinc"],
 }
 
 
