@@ -102,6 +102,35 @@ def test_digitizer_oracle_equals_a_literal_walk_of_the_reference_kernels(dead_le
     assert kills > 100 and (dead_level == 0 or (npairs[0] > 30 and npairs[1] > 80))
 
 
+def test_digitizer_oracle_equals_the_literal_walk_on_small_adversarial_lists():
+    """Differential fuzz of the same two restatements on thousands of tiny lists built to sit on every edge at once: times
+    on a half-microsecond grid (ties, exact window and dead-time boundaries, tau = 0), early and at 1e8 us, energies on the
+    window bounds, negative and repeated site numbers, every dead-time level and type, both sorter policies, panel distance."""
+    import pyref_digitizer as pyref
+    rng = np.random.default_rng(0)
+    with_pairs = with_kills = 0
+    for trial in range(1500):
+        n = int(rng.integers(0, 14))
+        ev = np.zeros(n, orc.EVENT_DTYPE)
+        ev["parn"] = rng.permutation(n); ev["eventid"] = ev["parn"] // 2
+        ev["pann"] = rng.integers(0, 3, n); ev["modn"] = rng.integers(0, 2, n); ev["cryn"] = rng.integers(0, 2, n)
+        ev["siten"] = rng.integers(-1, 3, n)
+        ev["t"] = rng.integers(0, 12, n) * 0.5 + (1e8 if trial % 5 == 0 else 1.0)
+        ev["E"] = rng.choice([40e3, 50e3, 60e3, 300e3, 700e3, 700e3 + 1, 2e6, 2.1e6], n)
+        p, d = parity.make_digi_params(dead_level=int(rng.integers(0, 4)), dead_type=int(rng.integers(0, 2)),
+                                       dead_time_us=float(rng.choice([0.0, 0.5, 1.0, 2.2])), coinc_window_us=float(rng.choice([0.25, 0.5, 1.0])),
+                                       coinc_policy=int(rng.integers(0, 2)), coinc_min_panel_diff=int(rng.integers(0, 3)), npanels=3,
+                                       moduleN=2, crystalN=2, threshold_eV=50e3, ewin_min=55e3, ewin_max=700e3)
+        s, counts, co = orc.digitize(ev, p)
+        ws, wcounts, wpairs = pyref.digitize(ev, d)
+        assert [int(c) for c in counts] == wcounts and s.tobytes() == ws.astype(orc.EVENT_DTYPE).tobytes() and co.size == len(wpairs), (trial, d)
+        if wpairs:
+            ia, ib = np.array(wpairs).T
+            assert co["a"].tobytes() == s[ia].tobytes() and co["b"].tobytes() == s[ib].tobytes(), (trial, d)
+        with_pairs += bool(wpairs); with_kills += wcounts[1] > wcounts[2]
+    assert with_pairs > 100 and with_kills > 100
+
+
 # ------------------------------------------------------------------------------------------------ C ABI surface
 def test_noise_oracle_is_a_poisson_process_over_the_detector():
     # addnoise (gPET_kernals.cu:699-735): mean gap 2 us over 0.1 s -> 50 000 +- 224 arrivals, uniform sites, E ~ N(300 keV, 20 keV)
