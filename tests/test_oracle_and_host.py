@@ -568,6 +568,30 @@ def test_c_example_compiles_as_c99_and_refuses_to_compute_without_a_device(tmp_p
     assert r.returncode == 3 and "no CPU fallback" in r.stderr and not (tmp_path / "singles.dat").exists()
 
 
+def test_c_run_example_compiles_as_c99_and_refuses_to_compute_without_a_device(tmp_path):
+    # examples/c/run_classify.c: the whole-run entry points and the coincidence classes from plain C; on a host-only
+    # context the loaders work (the shipped example parses) and gpet_run refuses
+    exe = tmp_path / "run_classify"
+    libdir = parity.ROOT / "gpet_b200"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{parity.ROOT / 'include'}",
+                    str(parity.ROOT / "examples" / "c" / "run_classify.c"), f"-L{libdir}", "-lgpet_b200", f"-Wl,-rpath,{libdir}",
+                    "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)], capture_output=True).returncode == 2
+    if not parity.have_tables():
+        pytest.skip("packed tables not built")
+    ex = tmp_path / "ex"
+    (ex / "input").mkdir(parents=True); (ex / "data").mkdir()
+    (ex / "input_PET.in").write_text((parity.EXAMPLE / "input_PET.in").read_text().replace("200 200 200", "16 16 16"))
+    for f in ("config8.geo", "pointsource.txt"):
+        (ex / "input" / f).write_text((parity.EXAMPLE / "input" / f).read_text())
+    (ex / "data" / "isotopes.txt").write_text((parity.EXAMPLE / "data" / "isotopes.txt").read_text())
+    (ex / "data" / "input4gPET.gpettab").write_bytes(parity.PACKED.read_bytes())
+    mat, den = parity.gen_inputs.cylinder_phantom(n=16)
+    parity.gen_inputs.write_phantom(mat, den, ex / "input" / "cylinder_phantom_mat.dat", ex / "input" / "cylinder_phantom_den.dat")
+    r = subprocess.run([str(exe), "input_PET.in", "0.01", "-1"], cwd=ex, capture_output=True, text=True)
+    assert r.returncode == 3 and "gpet_run failed" in r.stderr and "no CPU fallback" in r.stderr, r.stderr
+
+
 def test_cli_rejects_missing_argument():
     exe = parity.ROOT / "bin" / "gpet_b200"
     if not exe.exists():
