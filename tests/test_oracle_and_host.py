@@ -241,6 +241,43 @@ def test_record_layouts():
     assert api.COINC_DTYPE.itemsize == 96 and api.HIT_DTYPE.itemsize == 48 and api.PHOTON_DTYPE.itemsize == 48
 
 
+def test_ctypes_mirror_has_the_headers_struct_layouts(tmp_path):
+    """Every struct that crosses the boundary, field by field: sizeof / offsetof from the C header (a C99 program built here)
+    against the ctypes structures and numpy record types of gpet_b200/api.py."""
+    structs = {"gpet_digitizer_params": api.DigitizerParams, "gpet_transport_params": api.TransportParams, "gpet_stats": api.Stats}
+    records = {"gpet_event": api.EVENT_DTYPE, "gpet_coincidence": api.COINC_DTYPE, "gpet_hit": api.HIT_DTYPE,
+               "gpet_photon": api.PHOTON_DTYPE, "gpet_panel": api.PANEL_DTYPE}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "gpet_b200.h"', "int main(void) {"]
+    for name, st in structs.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        lines += [f'printf("{name}.{f} %zu\\n", offsetof({name}, {f}));' for f, _ in st._fields_]
+    for name, dt in records.items():
+        lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        lines += [f'printf("{name}.{f} %zu\\n", offsetof({name}, {f}));' for f in dt.names]
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", f"-I{parity.ROOT / 'include'}", str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, st in structs.items():
+        assert int(got[name]) == ctypes.sizeof(st), name
+        for f, _ in st._fields_:
+            assert int(got[f"{name}.{f}"]) == getattr(st, f).offset, (name, f)
+    for name, dt in records.items():
+        assert int(got[name]) == dt.itemsize, name
+        for f in dt.names:
+            assert int(got[f"{name}.{f}"]) == dt.fields[f][1], (name, f)
+    # and nothing in the header's structs is missing from the mirror
+    header = (parity.ROOT / "include" / "gpet_b200.h").read_text()
+    for name, st in structs.items():
+        body = re.search(r"typedef struct " + name + r" \{(.*?)\} " + name + ";", header, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        declared = [re.sub(r"\[.*", "", t).strip() for decl in body.split(";") for t in decl.split(",") if decl.strip()]
+        declared = [d.split()[-1] for d in declared if d]
+        assert declared == [f for f, _ in st._fields_], (name, declared)
+
+
 def test_host_only_context_refuses_compute():
     with api.Context(device=-1) as c:
         with pytest.raises(api.GpetError) as e:
