@@ -140,6 +140,8 @@ _SIGS = {
     "gpet_get_spectrum": (C.c_int, [_P, _P, C.c_int]),
     "gpet_set_spectrum": (C.c_int, [_P, C.c_int, C.c_float, C.c_float]),
     "gpet_set_shard": (C.c_int, [_P, C.c_int, C.c_int]),
+    "gpet_set_first_pair": (C.c_int, [_P, C.c_uint64]),
+    "gpet_peek_config_device": (C.c_int, [C.c_char_p]),
     "gpet_get_direction_table": (C.c_int64, [_P, _P, C.c_int64, _P]),
     "gpet_profile_enable": (C.c_int, [_P, C.c_int]),
     "gpet_profile_count": (C.c_int, [_P]),
@@ -149,7 +151,7 @@ _SIGS = {
 _lib = None
 
 
-ABI_VERSION = 3   # GPET_ABI_VERSION of include/gpet_b200.h
+ABI_VERSION = 4   # GPET_ABI_VERSION of include/gpet_b200.h
 
 
 def lib():
@@ -323,6 +325,10 @@ class Context:
 
     def set_shard(self, rank, world):
         self._ck(self._l.gpet_set_shard(self._h, rank, world))
+
+    def set_first_pair(self, first_pair):
+        """global 64-bit index of the acquisition's first annihilation pair (gpet_set_first_pair)"""
+        self._ck(self._l.gpet_set_first_pair(self._h, int(first_pair)))
 
     def set_spectrum(self, nbins, emin, emax):
         self._ck(self._l.gpet_set_spectrum(self._h, nbins, emin, emax))

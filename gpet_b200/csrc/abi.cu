@@ -91,9 +91,10 @@ int ensure_buffers(gpet_ctx* c) {
     if ((r = alloc_queue(c, c->q[0], cp, w.counters + 16))) return r;
     if ((r = alloc_queue(c, c->q[1], cp, w.counters + 17))) return r;
     if ((r = alloc_queue(c, c->q[2], cp, w.hot + kHotQ2))) return r;   // photons that entered a panel (panel-local frame)
-    if ((r = dev_alloc(c, &c->hits.id, 5 * ch))) return r;
-    if ((r = dev_alloc(c, &c->hits.f, 5 * ch))) return r;
+    if ((r = dev_alloc(c, &c->hits.id4, ch))) return r;
+    if ((r = dev_alloc(c, &c->hits.f4, ch))) return r;
     if ((r = dev_alloc(c, &c->hits.t, ch))) return r;
+    if ((r = dev_alloc(c, &c->hits.type, ch))) return r;
     c->hits.count = w.hot + kHotHitsEvents;
     c->hits.capacity = (unsigned)ch;
     if ((r = dev_alloc(c, &c->ev.rec, ce))) return r;
@@ -218,6 +219,28 @@ TablesDev tables_dev(const gpet_ctx* c) {
     return d;
 }
 
+// Keep the voxel grid resident in L2: a persisting access-policy window on the stream the kernels are launched on, when the
+// driver's persisting carve-out allows it (cudaDevAttrMaxPersistingL2CacheSize).  Re-applied whenever the stream changes
+// (gpet_set_stream); GPET_NO_L2_WINDOW=1 leaves it off (A/B measurements, profiles/).
+void apply_l2_window(gpet_ctx* c) {
+    if (!c->has_device || !c->d_vox || !c->vox_bytes || !c->stream) return;
+    if (getenv("GPET_NO_L2_WINDOW")) return;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+    if (max_persist <= 0 || max_window <= 0) return;
+    const size_t bytes = std::min<size_t>(c->vox_bytes, (size_t)max_window);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)max_persist));
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = c->d_vox;
+    attr.accessPolicyWindow.num_bytes = bytes;
+    attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)max_persist / (float)bytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();
+}
+
 int upload_phantom(gpet_ctx* c) {
     if (c->dev_phantom) return GPET_OK;
     if (!c->have_ph) return fail(c, GPET_ERR_ARG, "phantom not loaded");
@@ -235,22 +258,8 @@ int upload_phantom(gpet_ctx* c) {
     if ((r = dev_alloc(c, &c->d_vox, n))) return r;
     CK(cudaMemcpy(c->d_vox, vox.data(), n * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_maj_ph, c->maj_ph.data(), c->maj_ph.size() * 4, cudaMemcpyHostToDevice));
-    // keep the voxel grid resident in L2 (persisting access-policy window) when the carve-out allows it
-    int max_persist = 0, max_window = 0;
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
-    if (max_persist > 0 && max_window > 0) {
-        size_t bytes = std::min<size_t>(n * 4, (size_t)max_window);
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)max_persist));
-        cudaStreamAttrValue attr{};
-        attr.accessPolicyWindow.base_ptr = c->d_vox;
-        attr.accessPolicyWindow.num_bytes = bytes;
-        attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)max_persist / (float)bytes);
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-        cudaGetLastError();
-    }
+    c->vox_bytes = n * 4;
+    apply_l2_window(c);
     c->dev_phantom = true;
     return GPET_OK;
 }
@@ -343,6 +352,7 @@ DigitizerDev digitizer_dev(const gpet_ctx* c) {
     d.moduleN = c->geo.moduleN; d.crystalN = c->geo.crystalN;
     d.noise_gap = p.noise_mean_gap_us; d.noise_Emean = p.noise_Emean_eV; d.noise_sigma = p.noise_sigma_eV;
     d.noise_interval = p.noise_interval_us;
+    d.id_base = c->id_base;
     d.pair_shift = std::min(std::max(p.coinc_pair_shift, 0), 31);
     d.scat_tag = c->d_scat_tag; d.scat_mask = c->scat_mask; d.scat_serial = c->scat_serial;
     return d;
@@ -480,6 +490,10 @@ const char* gpet_last_error(const gpet_ctx* c) { return c ? c->err.c_str() : "nu
 int gpet_set_stream(gpet_ctx* c, void* s) {
     if (!c) return GPET_ERR_ARG;
     c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+    if (c->has_device) {
+        cudaSetDevice(c->device);
+        apply_l2_window(c);   // the access-policy window is a stream attribute: it follows the stream the kernels run on
+    }
     return GPET_OK;
 }
 
@@ -636,6 +650,21 @@ int gpet_set_source_atoms(gpet_ctx* c, int i, uint64_t natom) {
     return GPET_OK;
 }
 
+int gpet_set_first_pair(gpet_ctx* c, uint64_t first_pair) {
+    if (!c) return GPET_ERR_ARG;
+    if (first_pair > (1ull << 62)) return fail(c, GPET_ERR_ARG, "first pair index out of range");
+    c->first_pair = first_pair;
+    c->planned = false;
+    return GPET_OK;
+}
+
+int gpet_peek_config_device(const char* input_file) {
+    if (!input_file) return GPET_ERR_ARG;
+    Config cfg;
+    if (!parse_config(input_file, cfg).empty()) return GPET_ERR_IO;
+    return cfg.device >= 0 ? cfg.device : GPET_ERR_FORMAT;
+}
+
 int gpet_set_shard(gpet_ctx* c, int rank, int world) {
     if (!c || world < 1 || rank < 0 || rank >= world) return GPET_ERR_ARG;
     c->rank = rank; c->world = world;
@@ -768,7 +797,7 @@ int64_t gpet_plan_frames(gpet_ctx* c, uint64_t max_pairs) {
     uint64_t cap_pairs = c->cap_photons / 2;
     if (max_pairs == 0 || max_pairs > cap_pairs) max_pairs = cap_pairs;
     c->max_pairs_per_frame = max_pairs;
-    std::string e = plan_frames(c->src, c->iso, c->tstart, c->tend, max_pairs, c->seed, c->frames);
+    std::string e = plan_frames(c->src, c->iso, c->tstart, c->tend, max_pairs, c->seed, c->first_pair, c->frames);
     if (!e.empty()) return fail(c, GPET_ERR_ARG, e);
     c->planned = true;
     if (c->has_device) {
@@ -816,6 +845,7 @@ int gpet_stage_source(gpet_ctx* c, int64_t f) {
         if ((r = upload_phantom(c))) return r;
         ph = phantom_dev(c);
     }
+    c->id_base = 2ull * fp.first_pair;   // the queues now hold this frame's photons
     c->stats.kernel_launches += launch_source(c->d_frames + f, fp.npairs, ph, c->q[0], c->seed, c->num_sms, c->stream);
     CK(cudaGetLastError());
     return GPET_OK;
@@ -831,6 +861,7 @@ int gpet_stage_psf(gpet_ctx* c, int64_t first, int64_t n) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((uint64_t)(2 * n) > c->cap_photons) return fail(c, GPET_ERR_CAPACITY, "positron batch exceeds half the photon capacity");
+    c->id_base = 0;
     PhantomDev ph{};
     if (c->tr.use_positron_range) {
         if ((r = upload_phantom(c))) return r;
@@ -849,7 +880,7 @@ int gpet_stage_phantom(gpet_ctx* c) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((r = upload_phantom(c))) return r;
-    c->stats.kernel_launches += launch_phantom(c->q[0], c->q[1], phantom_dev(c), tables_dev(c), c->tr.eabs_eV, c->seed, c->num_sms, c->stream);
+    c->stats.kernel_launches += launch_phantom(c->q[0], c->q[1], phantom_dev(c), tables_dev(c), c->tr.eabs_eV, c->seed, c->id_base, c->num_sms, c->stream);
     CK(cudaGetLastError());
     return GPET_OK;
 }
@@ -864,7 +895,7 @@ int gpet_stage_detector(gpet_ctx* c) {
     c->stats.kernel_launches += launch_panel_entry(c->q[1], c->q[2], detector_dev(c), c->ws.counters, c->num_sms, c->stream);
     {
         const int nl = launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth, c->dig.readout_policy,
-                                       c->tr.record_hits, c->hits, c->ev, c->ws.counters, c->ws.hot, c->seed, c->num_sms, c->stream, !c->in_run);
+                                       c->tr.record_hits, c->hits, c->ev, c->ws.counters, c->ws.hot, c->seed, c->id_base, c->num_sms, c->stream, !c->in_run);
         if (nl < 0) return fail(c, GPET_ERR_ARG, "hit and event counters must be adjacent words (internal layout error)");
         c->stats.kernel_launches += nl;
     }
@@ -888,12 +919,13 @@ int gpet_stage_front(gpet_ctx* c, int64_t f) {
         if (2 * fp.npairs > c->cap_photons) return fail(c, GPET_ERR_CAPACITY, "frame exceeds the photon capacity");
         fr = c->d_frames + f;
         npairs = fp.npairs;
+        c->id_base = 2ull * fp.first_pair;
     }
     new_scatter_serial(c);
     PhantomDev ph = phantom_dev(c);   // the fused front end tags a photon the moment it scatters (transport.cu mark_scattered)
     ph.scat_tag = c->d_scat_tag; ph.scat_mask = c->scat_mask; ph.scat_serial = c->scat_serial;
     c->stats.kernel_launches += launch_front(fr, npairs, c->q[0], c->q[1], c->q[2], ph, tables_dev(c), detector_dev(c),
-                                             c->tr.eabs_eV, c->ws.counters, c->ws.hot, c->seed, c->num_sms, c->stream, !c->in_run);
+                                             c->tr.eabs_eV, c->ws.counters, c->ws.hot, c->seed, c->id_base, c->num_sms, c->stream, !c->in_run);
     CK(cudaGetLastError());
     return GPET_OK;
 }
@@ -906,7 +938,7 @@ int gpet_stage_panel_transport(gpet_ctx* c) {
     if ((r = upload_geometry(c))) return r;
     {
         const int nl = launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth, c->dig.readout_policy,
-                                       c->tr.record_hits, c->hits, c->ev, c->ws.counters, c->ws.hot, c->seed, c->num_sms, c->stream, !c->in_run);
+                                       c->tr.record_hits, c->hits, c->ev, c->ws.counters, c->ws.hot, c->seed, c->id_base, c->num_sms, c->stream, !c->in_run);
         if (nl < 0) return fail(c, GPET_ERR_ARG, "hit and event counters must be adjacent words (internal layout error)");
         c->stats.kernel_launches += nl;
     }
@@ -973,6 +1005,7 @@ int gpet_put_photons(gpet_ctx* c, int which, const gpet_photon* in, int64_t n) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((uint64_t)n > c->cap_photons) return fail(c, GPET_ERR_CAPACITY, "photon batch exceeds capacity");
+    c->id_base = 0;   // the caller's ids as they are
     if (n) CK(cudaMemcpyAsync(c->stage_aos, in, (size_t)n * sizeof(gpet_photon), cudaMemcpyHostToDevice, c->stream));
     if (which == 2) new_scatter_serial(c);   // photons put on the panel faces directly carry no scatter tags
     c->stats.kernel_launches += launch_photons_aos_to_queue(c->stage_aos, c->q[which], (unsigned)n, c->stream);
@@ -998,6 +1031,7 @@ int gpet_put_events(gpet_ctx* c, const gpet_event* in, int64_t n) {
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((uint64_t)n > c->cap_events) return fail(c, GPET_ERR_CAPACITY, "event list exceeds capacity");
+    c->id_base = 0;
     // the device buffer holds the records in the file layout: a plain copy
     new_scatter_serial(c);   // replayed events: no photon is tagged as scattered unless gpet_mark_scattered says so
     const unsigned n32 = (unsigned)n;
@@ -1026,19 +1060,10 @@ int64_t gpet_fetch_hits(gpet_ctx* c, gpet_hit* out, int64_t cap) {
     if ((r = read_counters(c))) return r;
     int64_t n = std::min<int64_t>(std::min<unsigned>(c->h_counters[18], c->hits.capacity), cap);
     if (n <= 0) return 0;
-    std::vector<int32_t> id((size_t)5 * n);
-    std::vector<float> f((size_t)5 * n);
-    std::vector<double> t((size_t)n);
-    CK(cudaMemcpyAsync(id.data(), c->hits.id, id.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(f.data(), c->hits.f, f.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(t.data(), c->hits.t, t.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    if ((size_t)n * sizeof(gpet_hit) > c->stage_bytes) return fail(c, GPET_ERR_CAPACITY, "hit list exceeds the staging buffer");
+    c->stats.kernel_launches += launch_hits_to_aos(c->hits, (unsigned)n, c->stage_aos, c->stream);
+    CK(cudaMemcpyAsync(out, c->stage_aos, (size_t)n * sizeof(gpet_hit), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    for (int64_t k = 0; k < n; k++) {
-        gpet_hit& h = out[k];
-        h.parn = id[5 * k]; h.pann = id[5 * k + 1]; h.modn = id[5 * k + 2]; h.cryn = id[5 * k + 3]; h.type = id[5 * k + 4];
-        h.E = f[5 * k]; h.t32 = f[5 * k + 1]; h.x = f[5 * k + 2]; h.y = f[5 * k + 3]; h.z = f[5 * k + 4];
-        h.t = t[k];
-    }
     return n;
 }
 
@@ -1202,7 +1227,13 @@ struct RunState {
     bool resident = false;
     std::string od;
     std::vector<char> tmp;
+    // File runs keep their results in the pinned arenas only while these stay small: past kKeepBytes the arenas become
+    // per-frame scratch (what is in the files is dropped from memory), as the reference streams every epoch to disk
+    // (gPET.cu:383, 424).  `dropped` = singles of the run no longer in the arena (index pairs are run-global).
+    bool streaming = false;
+    size_t dropped = 0;
 };
+constexpr size_t kKeepBytes = 1ull << 30;
 
 // Take frame results out of slot `slot`: wait for its counters, account, start the D2H copies of the records.
 int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
@@ -1273,14 +1304,17 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
     if (!rs.od.empty()) {
         // file dumps with the reference layouts (gPET.cu:367-383, 424): this path runs frame by frame (no pipelining)
         CK(cudaStreamSynchronize(c->copy_stream));
-        const size_t nh = std::min<size_t>(n_hits, c->hits.capacity), ne = std::min<size_t>(n_ev, c->ev.capacity);
+        const size_t nh = std::min<size_t>(n_hits, c->hits.capacity);
         if (c->tr.record_hits) {
-            if ((r = append_device(c, join_path(rs.od, "HitsID.dat"), c->hits.id, nh * 5 * sizeof(int32_t), rs.tmp))) return r;
-            if ((r = append_device(c, join_path(rs.od, "Hits.dat"), c->hits.f, nh * 5 * sizeof(float), rs.tmp))) return r;
+            // the SoA hit buffer in the reference's row layout (gPET.cu:367-376), built in the staging buffer
+            int* id5 = static_cast<int*>(c->stage_aos);
+            float* f5 = reinterpret_cast<float*>(id5 + 5 * nh);
+            if (nh * 40 > c->stage_bytes) return fail(c, GPET_ERR_CAPACITY, "hit list exceeds the staging buffer");
+            c->stats.kernel_launches += launch_hits_to_rows(c->hits, (unsigned)nh, id5, f5, c->stream);
+            if ((r = append_device(c, join_path(rs.od, "HitsID.dat"), id5, nh * 5 * sizeof(int32_t), rs.tmp))) return r;
+            if ((r = append_device(c, join_path(rs.od, "Hits.dat"), f5, nh * 5 * sizeof(float), rs.tmp))) return r;
         }
-        // note: adder.dat of the reference is written before blur; blur runs in place, so with blur enabled the
-        // energies in this dump are the blurred ones
-        if ((r = append_device(c, join_path(rs.od, "adder.dat"), c->ev.rec, ne * sizeof(gpet_event), rs.tmp))) return r;
+        // adder.dat was appended by run_attempt before the digitizer ran (blur works in place; gPET.cu:383-388)
         FILE* fs = fopen(join_path(rs.od, "singles.dat").c_str(), "ab");
         if (!fs) return fail(c, GPET_ERR_IO, "cannot open singles.dat for appending");
         if (ns) fwrite(dst_s, sizeof(gpet_event), ns, fs);
@@ -1294,9 +1328,10 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
                 const uint32_t* pr = reinterpret_cast<const uint32_t*>(dst_c);
                 const size_t n_all = c->res_singles.size / sizeof(gpet_event);
                 for (size_t k = 0; k < nc; k++) {
-                    if (pr[2 * k] < first_single || pr[2 * k + 1] >= n_all) { fclose(fc); return fail(c, GPET_ERR_ARG, "coincidence pair out of range"); }
-                    fwrite(sg + pr[2 * k], sizeof(gpet_event), 1, fc);
-                    fwrite(sg + pr[2 * k + 1], sizeof(gpet_event), 1, fc);
+                    const size_t ia = (size_t)pr[2 * k] - rs.dropped, ib = (size_t)pr[2 * k + 1] - rs.dropped;   // run-global -> arena
+                    if (pr[2 * k] < rs.dropped || ia < first_single || ib >= n_all) { fclose(fc); return fail(c, GPET_ERR_ARG, "coincidence pair out of range"); }
+                    fwrite(sg + ia, sizeof(gpet_event), 1, fc);
+                    fwrite(sg + ib, sizeof(gpet_event), 1, fc);
                 }
             }
             fclose(fc);
@@ -1305,6 +1340,12 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
             if (!fk) return fail(c, GPET_ERR_IO, "cannot open coincidences_class.dat for appending");
             if (nc) fwrite(dst_k, 1, nc, fk);
             fclose(fk);
+        }
+        if (rs.streaming || c->res_singles.size + c->res_coinc.size + c->res_pairs.size + c->res_cls.size > kKeepBytes) {
+            rs.streaming = true;
+            c->results_streamed = true;
+            rs.dropped += c->res_singles.size / sizeof(gpet_event);
+            c->res_singles.size = 0; c->res_coinc.size = 0; c->res_pairs.size = 0; c->res_cls.size = 0;
         }
     }
     return GPET_OK;
@@ -1445,6 +1486,7 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
     c->res_coinc.size = 0;
     c->res_pairs.size = 0;
     c->res_cls.size = 0;
+    c->results_streamed = false;
     c->coinc_expanded.clear();
     CK(cudaMemsetAsync(c->d_pair_base, 0, 2 * sizeof(unsigned), c->stream));
     struct InRun {   // gpet_stage_digitize reads these while the run is in flight
@@ -1469,7 +1511,8 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
     int rc = GPET_OK;
     for (int64_t f = 0; f < nframes && rc == GPET_OK; f++) {
         if (f % c->world != c->rank) continue;
-        if (!psf_mode && c->frames[(size_t)f].npairs == 0) continue;
+        // an empty frame still has its noise singles (addnoise covers the frame's time slice, decays or not)
+        if (!psf_mode && c->frames[(size_t)f].npairs == 0 && !(c->dig.noise_mean_gap_us > 0.f)) continue;
         const int slot = (int)(k & 1);
         c->out_slot = slot;
         c->singles_aos = c->singles_slot[slot];
@@ -1521,6 +1564,13 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
             }
             if (hi > lo && (rc = gpet_stage_noise(c, lo, hi))) break;
         }
+        if (!pipelined) {
+            // adder.dat: the post-readout events as the reference writes them, BEFORE blur (gPET.cu:383-388); the digitizer
+            // blurs, relabels siten and kills in place
+            if ((rc = read_counters(c))) break;
+            const size_t ne = std::min<size_t>(c->h_counters[19], c->ev.capacity);
+            if ((rc = append_device(c, join_path(rs.od, "adder.dat"), c->ev.rec, ne * sizeof(gpet_event), rs.tmp))) break;
+        }
         c->run_frame = k;
         rc = gpet_stage_digitize(c);
         c->have_range = false;
@@ -1557,6 +1607,8 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
 
 extern "C" {
 
+static const char* const kStreamedMsg = "the run's results were streamed to the output files (more than 1 GiB): read them there";
+
 int gpet_run(gpet_ctx* c, const char* output_dir, gpet_stats* stats) {
     NEED_DEVICE();
     return run_impl(c, output_dir, false, stats);
@@ -1569,12 +1621,14 @@ int gpet_run_resident(gpet_ctx* c, gpet_stats* stats) {
 
 int64_t gpet_result_singles(gpet_ctx* c, const gpet_event** ptr) {
     if (!c || !ptr) return GPET_ERR_ARG;
+    if (c->results_streamed) return fail(c, GPET_ERR_CAPACITY, kStreamedMsg);
     *ptr = reinterpret_cast<const gpet_event*>(c->res_singles.p);
     return (int64_t)(c->res_singles.size / sizeof(gpet_event));
 }
 
 int64_t gpet_result_coincidences(gpet_ctx* c, const gpet_coincidence** ptr) {
     if (!c || !ptr) return GPET_ERR_ARG;
+    if (c->results_streamed) return fail(c, GPET_ERR_CAPACITY, kStreamedMsg);
     if (c->coinc_format == GPET_COINC_PAIRS) {   // records on demand: gather from the singles list
         const size_t np = c->res_pairs.size / (2 * sizeof(uint32_t)), ns = c->res_singles.size / sizeof(gpet_event);
         if (c->coinc_expanded.size() != np * sizeof(gpet_coincidence)) {
@@ -1622,12 +1676,14 @@ int gpet_set_psf_output(gpet_ctx* c, int mode) {
 
 int64_t gpet_result_coincidence_classes(gpet_ctx* c, const uint8_t** ptr) {
     if (!c || !ptr) return GPET_ERR_ARG;
+    if (c->results_streamed) return fail(c, GPET_ERR_CAPACITY, kStreamedMsg);
     *ptr = reinterpret_cast<const uint8_t*>(c->res_cls.p);
     return (int64_t)c->res_cls.size;
 }
 
 int64_t gpet_result_coincidence_pairs(gpet_ctx* c, const uint32_t** ptr) {
     if (!c || !ptr) return GPET_ERR_ARG;
+    if (c->results_streamed) return fail(c, GPET_ERR_CAPACITY, kStreamedMsg);
     *ptr = reinterpret_cast<const uint32_t*>(c->res_pairs.p);
     return (int64_t)(c->res_pairs.size / (2 * sizeof(uint32_t)));
 }

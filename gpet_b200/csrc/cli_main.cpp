@@ -18,7 +18,7 @@ int main(int argc, char** argv) {
     std::string input = argv[1], data, out = "output";
     unsigned long long seed = 0x67504554ull;
     float cwin = 0.f;
-    int device = 0, cpolicy = -1, cmindiff = -1, pair_shift = -1;
+    int device = -1, cpolicy = -1, cmindiff = -1, pair_shift = -1;   // device: --device, else the GPU index line of the input file
     for (int i = 2; i + 1 < argc; i += 2) {
         if (!strcmp(argv[i], "--data")) data = argv[i + 1];
         else if (!strcmp(argv[i], "--out")) out = argv[i + 1];
@@ -32,6 +32,11 @@ int main(int argc, char** argv) {
     }
     auto t0 = std::chrono::steady_clock::now();
     gpet_ctx* ctx = nullptr;
+    if (device < 0) {
+        // "GPU index" of input_PET.in, as the reference's main() uses it (main.cu:52-56, iniDevice)
+        device = gpet_peek_config_device(input.c_str());
+        if (device < 0) { fprintf(stderr, "gpet_b200: cannot read the GPU index from %s\n", input.c_str()); return 1; }
+    }
     if (gpet_create(device, &ctx) != GPET_OK) return 1;
     gpet_set_seed(ctx, seed);
     int r = gpet_load_config_file(ctx, input.c_str(), nullptr, data.empty() ? nullptr : data.c_str());

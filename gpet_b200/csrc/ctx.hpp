@@ -45,6 +45,8 @@ struct gpet_ctx {
     float tstart = 0.f, tend = 1.f;
     std::vector<float> maj_ph, maj_det;
     int rank = 0, world = 1;
+    uint64_t first_pair = 0;                // global index of the acquisition's first annihilation pair (gpet_set_first_pair)
+    uint64_t id_base = 0;                   // global index of the first photon of the frame now in the queues (photon_index)
 
     // ---- capacities
     uint64_t cap_photons = 1ull << 22, cap_hits = 1ull << 23, cap_events = 1ull << 22;
@@ -95,6 +97,7 @@ struct gpet_ctx {
     mutable double psf_reach_key[4] = {0, 0, 0, -1};   // (o, psf_version) the cached reach below belongs to
     mutable double psf_reach = 0.0;         // largest distance of a PSF record from o
     uint32_t* d_vox = nullptr;
+    size_t vox_bytes = 0;                   // size of the voxel grid (access-policy window)
     float4* d_xs = nullptr;
     float *d_maj_ph = nullptr, *d_maj_det = nullptr, *d_cmpsf = nullptr, *d_rayff = nullptr;
     gpet::SourceDev* d_frames = nullptr;
@@ -111,6 +114,7 @@ struct gpet_ctx {
     PinnedArena res_pairs;                // uint32 index pairs of the last gpet_run (GPET_COINC_PAIRS)
     PinnedArena res_cls;                  // class bytes of the last gpet_run's coincidences
     std::vector<char> coinc_expanded;     // records built on demand from res_pairs + res_singles
+    bool results_streamed = false;        // the last file run outgrew the arenas: its results are in the files only
     gpet_stats stats{};
     uint64_t last_counts[4] = {0, 0, 0, 0};
     gpet::KernelTimer ktimer;   // per-kernel CUDA-event times (gpet_profile_enable)

@@ -12,6 +12,18 @@ constexpr float kIMC2 = 1.95695060911e-6f;            // constants.h:34
 constexpr float kTwoPi = 6.2831853071795864769252867f;
 constexpr double kMaxT = 1e20;                        // constants.h:18 MAXT
 
+// History numbers.  The records of the reference carry 32-bit ids (gPET.h:50, 87-92); here the global photon index is
+// 64 bits wide (1e10 decays = 2e10 photons), the record keeps its low 31 bits (never negative: parn == -1 stays the mark of
+// a noise single, eventid's top bit the mark of a noise event) and every Philox stream is keyed by the full index,
+// rebuilt from the record and the index of the first photon of the frame (a frame holds far fewer than 2^31 photons):
+//   index = base + ((parn - base) mod 2^31).
+// base == 0 (stage-level entry points, replayed lists, the first 2^31 photons of a run): the 32-bit id as it is.
+constexpr unsigned kIdMask = 0x7fffffffu;
+__host__ __device__ __forceinline__ unsigned long long photon_index(int parn, unsigned long long base) {
+    if (base == 0ull) return (unsigned long long)(unsigned)parn;
+    return base + (unsigned long long)(((unsigned)parn - (unsigned)base) & kIdMask);
+}
+
 // Philox stream ids (counter word 2, high byte)
 enum Stage : uint32_t {
     kStageSource = 1, kStagePhantom = 2, kStageDetector = 3, kStageBlur = 4, kStagePlan = 5, kStagePsfPositron = 6, kStageNoise = 7
@@ -27,11 +39,15 @@ struct PhotonQueue {
     unsigned int capacity;
 };
 
-// Hits in file layout: row k occupies id[5k..5k+4] (HitsID.dat) and f[5k..5k+4] (Hits.dat).
+// Hits as structure-of-arrays of 16-byte vectors: a warp's staged hits leave the SM as full-line vector stores (one int4,
+// one float4, one double and one int per hit and lane, consecutive hits in consecutive lanes).  The file layout of the
+// reference (HitsID.dat: 5 x int32 rows, Hits.dat: 5 x float32 rows, gPET.cu:367-376) is produced from these on demand
+// by k_hits_to_rows / k_hits_to_aos (file dumps and gpet_fetch_hits), never on the transport path.
 struct HitBuffer {
-    int* id;              // parn, pann, modn, cryn, type
-    float* f;             // E, t(float32), x, y, z
-    double* t;            // fp64 time (extension)
+    int4* id4;            // parn, pann, modn, cryn
+    float4* f4;           // E, x, y, z (panel-local)
+    double* t;            // fp64 time (the file keeps its float32 image)
+    int* type;            // 1 Compton deposit, 2 absorbed remainder, 4 photoelectric
     unsigned int* count;
     unsigned int capacity;
 };
@@ -161,6 +177,7 @@ struct DigitizerDev {
     float noise_gap, noise_Emean, noise_sigma, noise_interval;   // addnoise (gPET_kernals.cu:699-735); gap <= 0: off
     int npanels;
     int moduleN, crystalN;
+    unsigned long long id_base;   // global index of the frame's first photon (photon_index); 0 for replayed lists
     // coincidence classes (k_coinc): same annihilation iff eventid >> pair_shift agree; scatter tags as in DetectorDev
     int pair_shift;
     const unsigned char* scat_tag;

@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_prep(EventBuf ev, DigitizerDev 
         // R == 0 leaves E bit-identical (E + 0), so the draw is skipped: this is the deterministic replay mode
         if (R > 0.f || p.sblur > 0.f || p.tblur > 0.f) {
             // stream = the photon; noise events (parn == -1, k_noise) are told apart by their event id
-            const uint64_t who = a4.x == -1 ? ((1ull << 32) | (uint32_t)b4.y) : (uint64_t)(uint32_t)a4.x;
+            // (the full 64-bit photon index: with 1e10 decays the 31-bit number of the record repeats every 2^30 pairs)
+            const uint64_t who = a4.x == -1 ? ((1ull << 63) | (uint32_t)b4.y) : photon_index(a4.x, p.id_base);
             Philox rng(seed, who, ((uint32_t)kStageBlur << 24) | ((uint32_t)b4.x & 0xFFFFFFu));
             uint4 r = rng.next();
             float rad = sqrtf(-2.0f * logf(u01(r.x)));

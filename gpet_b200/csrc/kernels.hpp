@@ -108,17 +108,21 @@ int launch_source(const SourceDev* frame_dev, unsigned long long npairs, Phantom
                   uint64_t seed, int num_sms, cudaStream_t s);
 int launch_psf_positron(const void* positrons_aos, PhotonQueue q0, unsigned int n_positrons, unsigned long long first,
                         PhantomDev ph, float nonangle, int use_prange, uint64_t seed, int num_sms, cudaStream_t s);
-int launch_phantom(PhotonQueue q0, PhotonQueue q1, PhantomDev ph, TablesDev tb, float eabs, uint64_t seed,
+// id_base: global index of the first photon of the frame in the queue (device_types.cuh photon_index); 0 = ids as they are
+int launch_phantom(PhotonQueue q0, PhotonQueue q1, PhantomDev ph, TablesDev tb, float eabs, uint64_t seed, unsigned long long id_base,
                    int num_sms, cudaStream_t s);
 int launch_panel_entry(PhotonQueue q1, PhotonQueue q2, DetectorDev det, unsigned int* counters, int num_sms, cudaStream_t s);
 // fused source (frame_dev != nullptr) or queue q0 (frame_dev == nullptr) -> phantom -> panel entry -> q2; q1 only counts
 int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQueue q0, PhotonQueue q1, PhotonQueue q2,
                  PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, unsigned int* counters, unsigned int* hot, uint64_t seed,
-                 int num_sms, cudaStream_t s, bool reset);
+                 unsigned long long id_base, int num_sms, cudaStream_t s, bool reset);
 // hits.count and ev.count must be adjacent words (hits first, 8-byte aligned): one 64-bit atomic reserves both
 int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
                     int record_hits, HitBuffer hits, EventBuf ev, unsigned int* counters, unsigned int* hot, uint64_t seed,
-                    int num_sms, cudaStream_t s, bool reset);
+                    unsigned long long id_base, int num_sms, cudaStream_t s, bool reset);
+// the SoA hit buffer in the reference's file layout (HitsID.dat / Hits.dat rows) or as gpet_hit records
+int launch_hits_to_rows(HitBuffer hits, unsigned int n, int* id5, float* f5, cudaStream_t s);
+int launch_hits_to_aos(HitBuffer hits, unsigned int n, void* aos, cudaStream_t s);
 int launch_photons_aos_to_queue(const void* aos, PhotonQueue q, unsigned int n, cudaStream_t s);
 int launch_queue_to_photons_aos(PhotonQueue q, void* aos, cudaStream_t s);
 

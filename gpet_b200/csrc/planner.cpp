@@ -68,7 +68,7 @@ uint64_t sample_binomial(uint64_t n, double p, uint64_t seed, uint64_t stream, u
 }
 
 std::string plan_frames(const Sources& src, const Isotopes& iso, float tstart_s, float tend_s, uint64_t max_pairs,
-                        uint64_t seed, std::vector<FramePlan>& out) {
+                        uint64_t seed, uint64_t first_pair0, std::vector<FramePlan>& out) {
     out.clear();
     const int ns = src.n();
     if (ns < 1) return "no sources";
@@ -82,7 +82,7 @@ std::string plan_frames(const Sources& src, const Isotopes& iso, float tstart_s,
     }
     double t = tstart_s;
     const double tend = tend_s;
-    uint64_t first_pair = 0;
+    uint64_t first_pair = first_pair0;
     auto expected_pairs = [&](double dt) {
         double e = 0.0;
         for (int i = 0; i < ns; i++) e += natom[i] * (1.0 - std::exp2(-dt / thalf[i])) * ratio[i];

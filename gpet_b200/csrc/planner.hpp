@@ -11,8 +11,10 @@
 
 namespace gpet {
 
+// first_pair0: global index of the first pair of the acquisition (64-bit history numbers; 0 unless the caller continues or
+// shards a longer history sequence, gpet_set_first_pair)
 std::string plan_frames(const Sources& src, const Isotopes& iso, float tstart_s, float tend_s, uint64_t max_pairs,
-                        uint64_t seed, std::vector<FramePlan>& out);
+                        uint64_t seed, uint64_t first_pair0, std::vector<FramePlan>& out);
 void fill_source_dev(const Sources& src, const Isotopes& iso, const FramePlan& fp, float nonangle, int use_prange,
                      SourceDev& d);
 

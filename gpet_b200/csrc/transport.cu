@@ -9,6 +9,7 @@
 //   * stage boundaries are compact SoA queues filled with warp-aggregated appends (one atomic per warp);
 //   * the per-photon adder/readout runs in registers (no local-memory Event[4]); hits leave the SM as contiguous
 //     rows already in the HitsID.dat / Hits.dat layout.
+#include <algorithm>
 #include <cstdlib>
 
 #include "kernels.hpp"
@@ -265,9 +266,10 @@ __device__ __forceinline__ void source_pair(const SourceDev* __restrict__ fr, co
     }
     a.x = b.x = x; a.y = b.y = y; a.z = b.z = z;
     a.t = b.t = t_us;
-    a.eid = b.eid = (int)(unsigned)gk;
+    // records keep the low 31 bits of the 64-bit history numbers (device_types.cuh photon_index)
+    a.eid = b.eid = (int)((unsigned)gk & kIdMask);
     a.nscat = b.nscat = 0;
-    a.parn = (int)(unsigned)(2ull * gk); b.parn = (int)(unsigned)(2ull * gk + 1ull);
+    a.parn = (int)((unsigned)(2ull * gk) & kIdMask); b.parn = (int)((unsigned)(2ull * gk + 1ull) & kIdMask);
     a.vx = vx; a.vy = vy; a.vz = vz;
     a.E = kMC2 + delta * kMC2 * 0.5f;
     rotate_dir(vx, vy, vz, -cosf(delta), phi2);
@@ -369,7 +371,7 @@ __device__ __forceinline__ int phantom_flight(Photon& p, Philox& rng, const Phan
 }
 
 __global__ void __launch_bounds__(kThreads) k_phantom(PhotonQueue q0, PhotonQueue q1, PhantomDev ph, TablesDev tb,
-                                                      float eabs, uint64_t seed) {
+                                                      float eabs, uint64_t seed, unsigned long long id_base) {
     const unsigned n = min(*q0.count, q0.capacity);
     const unsigned stride = gridDim.x * blockDim.x;
     unsigned next = blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(kThreads) k_phantom(PhotonQueue q0, PhotonQueu
                 p.x = pe.x; p.y = pe.y; p.z = pe.z; p.E = pe.w;
                 p.vx = dn.x; p.vy = dn.y; p.vz = dn.z; p.nscat = __float_as_int(dn.w);
                 p.t = tt; p.eid = id.x; p.parn = id.y;
-                rng = Philox(seed, (uint64_t)(uint32_t)p.parn, (uint32_t)kStagePhantom << 24);
+                rng = Philox(seed, photon_index(p.parn, id_base), (uint32_t)kStagePhantom << 24);
                 active = true;
             }
             amask = __ballot_sync(kFull, active);
@@ -638,7 +640,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_front(const SourceDev* __restri
                                                     PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, uint64_t seed,
                                                     PhotonQueue q2, unsigned* __restrict__ q1_count,
                                                     unsigned* __restrict__ counters, unsigned* __restrict__ ticket, int gen_min,
-                                                    int entry_min) {
+                                                    int entry_min, unsigned long long id_base_q) {
     extern __shared__ __align__(16) unsigned char s_front[];
     FrontStage& stage = *reinterpret_cast<FrontStage*>(s_front);
     PanelSm* s_panels = reinterpret_cast<PanelSm*>(s_front + sizeof(FrontStage));
@@ -647,6 +649,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_front(const SourceDev* __restri
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned nunits = kFromQueue ? min(*q0.count, q0.capacity) : (unsigned)min(npairs, (unsigned long long)(q2.capacity / 2));
+    // index of the frame's first photon; re-read where a photon starts instead of living in two registers
+    auto id_base_of_frame = [&]() -> unsigned long long { return kFromQueue ? id_base_q : 2ull * __ldg(&fr->first_pair); };
     if (!kFromQueue && blockIdx.x == 0 && threadIdx.x == 0) *q0.count = 2u * nunits;
     int state = NEED;
     bool has_b = false, exhausted = false;
@@ -657,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_front(const SourceDev* __restri
         if (!kFromQueue && state == NEED && has_b) {   // second photon of the pair
             p = b;
             has_b = false;
-            rng = Philox(seed, (uint64_t)(uint32_t)p.parn, (uint32_t)kStagePhantom << 24);
+            rng = Philox(seed, photon_index(p.parn, id_base_of_frame()), (uint32_t)kStagePhantom << 24);
             state = FLY;
         }
         unsigned need = __ballot_sync(kFull, state == NEED);
@@ -684,7 +688,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_front(const SourceDev* __restri
                         has_b = true;
                     }
                     if (live) {
-                        rng = Philox(seed, (uint64_t)(uint32_t)p.parn, (uint32_t)kStagePhantom << 24);
+                        rng = Philox(seed, photon_index(p.parn, id_base_of_frame()), (uint32_t)kStagePhantom << 24);
                         state = FLY;
                     }
                 }
@@ -746,8 +750,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_front(const SourceDev* __restri
     }
 }
 
-// Per-thread adder slots in shared memory, [slot][thread] so that a warp's accesses are conflict free.  A slot is one
-// crystal of the photon's panel: key = (module << 16) | crystal-in-module (a photon never leaves its panel).
+// Adder slots ("columns") in shared memory.  A slot is one crystal of the photon's panel: key = (module << 16) |
+// crystal-in-module (a photon never leaves its panel).  k_detector_v1 gives every thread its own column [slot][thread];
+// k_detector gives every WARP a pool of 32 + kSpare columns (below).
 struct SlotsSmem {
     int key[kSlots][kDetThreads];
     float E[kSlots][kDetThreads], x[kSlots][kDetThreads], y[kSlots][kDetThreads], z[kSlots][kDetThreads];
@@ -756,53 +761,53 @@ struct SlotsSmem {
 
 // D1 adder (gPET_kernals.cu:737-755): merge hits of the same crystal; energy-weighted centroid with the
 // contraction spelled out: (x_i*E_i + x*E)/(E_i+E) = fma(x_i, E_i, x*E) / (E_i + E)
-__device__ __forceinline__ bool adder(SlotsSmem& sl, int& n, int key, float E, float x, float y, float z, double t) {
-    const int tid = threadIdx.x;
+template <class S>
+__device__ __forceinline__ bool adder(S& sl, int col, int& n, int key, float E, float x, float y, float z, double t) {
     for (int k = 0; k < n; k++) {
-        if (sl.key[k][tid] == key) {
-            const float ek = sl.E[k][tid];
+        if (sl.key[k][col] == key) {
+            const float ek = sl.E[k][col];
             const float es = __fadd_rn(ek, E);
-            sl.x[k][tid] = __fdiv_rn(__fmaf_rn(sl.x[k][tid], ek, __fmul_rn(x, E)), es);
-            sl.y[k][tid] = __fdiv_rn(__fmaf_rn(sl.y[k][tid], ek, __fmul_rn(y, E)), es);
-            sl.z[k][tid] = __fdiv_rn(__fmaf_rn(sl.z[k][tid], ek, __fmul_rn(z, E)), es);
-            sl.E[k][tid] = es;
+            sl.x[k][col] = __fdiv_rn(__fmaf_rn(sl.x[k][col], ek, __fmul_rn(x, E)), es);
+            sl.y[k][col] = __fdiv_rn(__fmaf_rn(sl.y[k][col], ek, __fmul_rn(y, E)), es);
+            sl.z[k][col] = __fdiv_rn(__fmaf_rn(sl.z[k][col], ek, __fmul_rn(z, E)), es);
+            sl.E[k][col] = es;
             return true;
         }
     }
     if (n >= kSlots) return false;
-    sl.key[n][tid] = key; sl.E[n][tid] = E; sl.x[n][tid] = x; sl.y[n][tid] = y; sl.z[n][tid] = z; sl.t[n][tid] = t;
+    sl.key[n][col] = key; sl.E[n][col] = E; sl.x[n][col] = x; sl.y[n][col] = y; sl.z[n][col] = z; sl.t[n][col] = t;
     n++;
     return true;
 }
 
 // D2 readout (gPET_kernals.cu:756-813) of one finished photon: merges the slots whose key agrees at the readout level
 // (depth 0/1: the whole panel, 2: module, else crystal); returns the bit mask of the slots merged away.
-__device__ __forceinline__ unsigned readout_merge(SlotsSmem& sl, int nslot, int depth, int rpolicy) {
-    const int tid = threadIdx.x;
+template <class S>
+__device__ __forceinline__ unsigned readout_merge(S& sl, int col, int nslot, int depth, int rpolicy) {
     unsigned deadmask = 0;
-    // rolled loops on purpose: few lanes of a warp ever get here, and unrolled 6 x 6 this function was 24 KB of SASS --
-    // half the kernel -- pushing the hot loop out of the 32 KB instruction cache
+    // rolled loops on purpose: unrolled 6 x 6 this function was 24 KB of SASS -- half the kernel -- pushing the hot loop
+    // out of the 32 KB instruction cache
 #pragma unroll 1
     for (int i = 0; i < nslot - 1; i++) {
         if (deadmask >> i & 1u) continue;
-        const int ki = sl.key[i][tid];
+        const int ki = sl.key[i][col];
 #pragma unroll 1
         for (int j = i + 1; j < nslot; j++) {
             if (deadmask >> j & 1u) continue;
-            const int kj = sl.key[j][tid];
+            const int kj = sl.key[j][col];
             const bool same = depth <= 1 ? true : depth == 2 ? (ki >> 16) == (kj >> 16) : ki == kj;
             if (!same) continue;
-            const float Ei = sl.E[i][tid], Ej = sl.E[j][tid];
+            const float Ei = sl.E[i][col], Ej = sl.E[j][col];
             if (rpolicy == 1) {
                 const float es = __fadd_rn(Ei, Ej);
-                sl.x[i][tid] = __fdiv_rn(__fmaf_rn(sl.x[i][tid], Ei, __fmul_rn(sl.x[j][tid], Ej)), es);
-                sl.y[i][tid] = __fdiv_rn(__fmaf_rn(sl.y[i][tid], Ei, __fmul_rn(sl.y[j][tid], Ej)), es);
-                sl.z[i][tid] = __fdiv_rn(__fmaf_rn(sl.z[i][tid], Ei, __fmul_rn(sl.z[j][tid], Ej)), es);
-                sl.E[i][tid] = es;
+                sl.x[i][col] = __fdiv_rn(__fmaf_rn(sl.x[i][col], Ei, __fmul_rn(sl.x[j][col], Ej)), es);
+                sl.y[i][col] = __fdiv_rn(__fmaf_rn(sl.y[i][col], Ei, __fmul_rn(sl.y[j][col], Ej)), es);
+                sl.z[i][col] = __fdiv_rn(__fmaf_rn(sl.z[i][col], Ei, __fmul_rn(sl.z[j][col], Ej)), es);
+                sl.E[i][col] = es;
             } else if (!(Ei > Ej)) {
                 // winner-take-all: the larger energy wins the whole record (ties -> the later one)
-                sl.key[i][tid] = kj; sl.E[i][tid] = Ej; sl.x[i][tid] = sl.x[j][tid];
-                sl.y[i][tid] = sl.y[j][tid]; sl.z[i][tid] = sl.z[j][tid]; sl.t[i][tid] = sl.t[j][tid];
+                sl.key[i][col] = kj; sl.E[i][col] = Ej; sl.x[i][col] = sl.x[j][col];
+                sl.y[i][col] = sl.y[j][col]; sl.z[i][col] = sl.z[j][col]; sl.t[i][col] = sl.t[j][col];
             }
             deadmask |= 1u << j;
         }
@@ -810,35 +815,35 @@ __device__ __forceinline__ unsigned readout_merge(SlotsSmem& sl, int nslot, int 
     return deadmask;
 }
 
-// Photon transport inside a panel (gPET_kernals.cu:1018-1192) over the compact panel-entry queue.  Persistent warps;
-// a lane whose photon is finished reads it out (adder slots -> events) and pulls the next photon from a global ticket
-// counter (one atomic per warp and refill), so that lanes stay busy until the queue is empty whatever the lengths of
-// their histories.  Adder on the fly, readout (gPET_kernals.cu:756-813) when the photon is finished.
-// refill_min: idle lanes that trigger a refill (amortises the ticket atomic and the queue loads)
+__device__ __forceinline__ int event_siten(int depth, int panel_id, int modn, int cryn, const DetectorDev& det) {
+    return depth == 0 ? 0 : depth == 1 ? panel_id : depth == 2 ? panel_id * det.moduleN + modn
+                                                             : (panel_id * det.moduleN + modn) * det.crystalN + cryn;
+}
 
 constexpr unsigned kDetChunk = 32;   // photons a warp claims from the queue with one ticket atomic
 
-__global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs,
+// ---- k_detector_v1: round 1's kernel, kept selectable (GPET_DET_V=1) as the A/B partner of the kernel below --------
+// One lane = one photon from entry to readout; the Klein-Nishina rejection loop, the adder / readout merges and the event
+// emission run nested inside the flight loop with whatever lanes need them (12 of 32 lanes per instruction).
+__global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector_v1(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs,
                                                           int rdepth, int rpolicy, int record_hits, HitBuffer hits, EventBuf ev,
                                                           unsigned* __restrict__ counters, unsigned* __restrict__ ticket, uint64_t seed,
-                                                          int refill_min) {
+                                                          int refill_min, unsigned long long id_base) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     SlotsSmem& sl = *reinterpret_cast<SlotsSmem*>(s_raw);
     PanelDev* s_panels = reinterpret_cast<PanelDev*>(s_raw + sizeof(SlotsSmem));
     stage_panels(s_panels, det);
-    // programmatic dependent launch: everything above overlapped the tail of the front-end kernel; its queue is read below
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int tid = threadIdx.x;
     const unsigned lane = lane_id();
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned n = min(*q2.count, q2.capacity);
-    // hits.count and ev.count are adjacent words: one 64-bit atomic reserves the warp's hit rows and event records
     unsigned long long* __restrict__ hits_events = reinterpret_cast<unsigned long long*>(hits.count);
     const int depth = (rdepth != 3 && rpolicy == 1) ? 2 : rdepth;
     bool active = false, exhausted = false;
-    unsigned chunk_pos = 0, chunk_end = 0;   // the warp's claimed share of the queue (warp-uniform)
-    unsigned seen = 0;                       // ticket value after this warp's last claim
+    unsigned chunk_pos = 0, chunk_end = 0;
+    unsigned seen = 0;
     const unsigned nwarps = gridDim.x * (kDetThreads / 32);
     float x = 0, y = 0, z = 0, E = 0, vx = 0, vy = 0, vz = 0;
     double t = 0;
@@ -846,13 +851,9 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
     unsigned n_drop_adder = 0;
     Philox rng(seed, 0, 0);
     while (true) {
-        // ---- refill idle lanes from the warp's chunk of the queue; a new chunk costs one ticket atomic per kDetChunk photons
         unsigned amask = __ballot_sync(kFull, active);
         if (!exhausted && (__popc(~amask) >= refill_min || amask == 0)) {
             if (chunk_pos == chunk_end) {
-                // guided self-scheduling: full chunks while the queue is long, smaller ones as it drains (remaining /
-                // 2 x warps, from the ticket value this warp saw last), so that the warps run dry together instead of
-                // one of them starting 32 fresh histories when the others are done
                 const unsigned left = n > seen ? n - seen : 0u;
                 const unsigned want = max(2u, min(kDetChunk, left / (2u * nwarps)));
                 unsigned base = 0;
@@ -875,7 +876,7 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
                 x = pe.x; y = pe.y; z = pe.z; E = pe.w;
                 vx = dn.x; vy = dn.y; vz = dn.z; pa = __float_as_int(dn.w);
                 eid = id.x; parn = id.y;
-                rng = Philox(seed, (uint64_t)(uint32_t)parn, (uint32_t)kStageDetector << 24);
+                rng = Philox(seed, photon_index(parn, id_base), (uint32_t)kStageDetector << 24);
                 nslot = 0;
                 active = true;
             }
@@ -886,7 +887,6 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
             if (exhausted) break;
             continue;
         }
-        // up to two hits per flight (Compton deposit + absorption of the remainder), both at the same point
         int nh = 0, h_key = 0, h_type0 = 0;
         float h_E0 = 0.f, h_E1 = 0.f;
         bool finished = false;
@@ -900,7 +900,7 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
             x = fmaf(s, vx, x); y = fmaf(s, vy, y); z = fmaf(s, vz, z);
             t += (double)s * kInvSpeedOfLight;
             if (fabsf(y) > pd.ly * 0.5f || fabsf(z) > pd.lz * 0.5f || x * pd.dirx < 0.f || x * pd.dirx > pd.lx) {
-                finished = true;  // left the panel
+                finished = true;
             } else {
                 int m_id, M_id, L_id;
                 crystal_search(pd, det, x, y, z, m_id, M_id, L_id);
@@ -910,7 +910,7 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
                 float lamden = lammin * rho;
                 float prob = fmaxf(1.0f - lamden * xs.tot, 0.f);
                 float u = u01(r.y);
-                bool turn = false;   // Compton and Rayleigh lanes rotate together below (one copy of the code, more lanes on it)
+                bool turn = false;
                 float costh = 1.f, phi = 0.f;
                 if (u >= prob) {
                     prob += lamden * xs.compt;
@@ -922,7 +922,7 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
                         if (m_id == 0) { h_type0 = 1; h_E0 = de; nh = 1; }
                         E -= de;
                         if (E < eabs) {
-                            if (m_id == 0) { h_E1 = E; nh = 2; }  // type 2: remainder absorbed on the spot
+                            if (m_id == 0) { h_E1 = E; nh = 2; }
                             finished = true;
                         } else {
                             turn = true;
@@ -942,21 +942,17 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
                 if (turn) rotate_dir(vx, vy, vz, costh, phi);
                 h_key = (M_id << 16) | (L_id & 0xffff);
             }
-            // adder on the fly
             if (nh >= 1) {
-                if (!adder(sl, nslot, h_key, h_E0, x, y, z, t)) n_drop_adder++;
-                if (nh == 2 && !adder(sl, nslot, h_key, h_E1, x, y, z, t)) n_drop_adder++;
+                if (!adder(sl, tid, nslot, h_key, h_E0, x, y, z, t)) n_drop_adder++;
+                if (nh == 2 && !adder(sl, tid, nslot, h_key, h_E1, x, y, z, t)) n_drop_adder++;
             }
         }
-        // ---- photon finished: readout (gPET_kernals.cu:756-813)
         if (finished) active = false;
         const bool mine = finished && nslot > 0;
         unsigned deadmask = 0;
-        if (mine && nslot > 1 && rdepth != 3) deadmask = readout_merge(sl, nslot, depth, rpolicy);
+        if (mine && nslot > 1 && rdepth != 3) deadmask = readout_merge(sl, tid, nslot, depth, rpolicy);
         const unsigned ne = mine ? (unsigned)(nslot - __popc(deadmask)) : 0u;
         const unsigned nhits = record_hits ? (unsigned)nh : 0u;
-        // ---- one reservation for the warp's hit rows and event records: packed prefix sums (hits <= 64, events <= 192
-        // per warp and iteration), one 64-bit atomic
         const unsigned packed = nhits | (ne << 16);
         if (__ballot_sync(kFull, packed != 0u)) {
             unsigned incl = packed;
@@ -967,29 +963,22 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
             }
             const unsigned total = __shfl_sync(kFull, incl, 31);
             unsigned long long base = 0;
-#ifdef GPET_EXP_NOATOMIC   // timing experiment only: no reservation round trip (output positions are wrong)
-            base = ((unsigned long long)((blockIdx.x * 8u + (threadIdx.x >> 5)) * 200u + (chunk_pos & 127u))) * 0x100000001ull;
-#else
             if (lane == 31) base = atomicAdd(hits_events, (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 32));
             base = __shfl_sync(kFull, base, 31);
-#endif
             const unsigned excl = incl - packed;
             unsigned hslot = (unsigned)(base & 0xffffffffull) + (excl & 0xffffu);
             unsigned eslot = (unsigned)(base >> 32) + (excl >> 16);
-            // hits: rows in file layout
             if (nhits > 0) {
                 const int panel_id = s_panels[pa].id;
                 for (unsigned k = 0; k < nhits; k++) {
                     if (hslot + k < hits.capacity) {
-                        int* hi = hits.id + 5ull * (hslot + k);
-                        float* hf = hits.f + 5ull * (hslot + k);
-                        hi[0] = parn; hi[1] = panel_id; hi[2] = h_key >> 16; hi[3] = h_key & 0xffff; hi[4] = k ? 2 : h_type0;
-                        hf[0] = k ? h_E1 : h_E0; hf[1] = (float)t; hf[2] = x; hf[3] = y; hf[4] = z;
+                        hits.id4[hslot + k] = make_int4(parn, panel_id, h_key >> 16, h_key & 0xffff);
+                        hits.f4[hslot + k] = make_float4(k ? h_E1 : h_E0, x, y, z);
                         hits.t[hslot + k] = t;
+                        hits.type[hslot + k] = k ? 2 : h_type0;
                     }
                 }
             }
-            // events of the finished photons
             if (mine) {
                 const int panel_id = s_panels[pa].id;
 #pragma unroll 1
@@ -999,8 +988,7 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
                         const int key = sl.key[k][tid];
                         EventRec r;
                         r.parn = parn; r.pann = panel_id; r.modn = key >> 16; r.cryn = key & 0xffff;
-                        r.siten = depth == 0 ? 0 : depth == 1 ? panel_id : depth == 2 ? panel_id * det.moduleN + r.modn
-                                                                                     : (panel_id * det.moduleN + r.modn) * det.crystalN + r.cryn;
+                        r.siten = event_siten(depth, panel_id, r.modn, r.cryn, det);
                         r.eventid = eid;
                         r.t = sl.t[k][tid]; r.E = sl.E[k][tid];
                         r.x = sl.x[k][tid]; r.y = sl.y[k][tid]; r.z = sl.z[k][tid];
@@ -1012,11 +1000,322 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
         }
         if (mine) nslot = 0;
     }
+    unsigned b = n_drop_adder;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(kFull, b, o);
+    if (lane == 0 && b) atomicAdd(&counters[9], b);
+}
+
+// ---- k_detector -----------------------------------------------------------------------------------------------------
+// Photon transport inside a panel (photonde, gPET_kernals.cu:1018-1192, with comsam :90-126, adder / readout :737-813) over
+// the compact panel-entry queue.  Persistent warps with lane refill as before; what changed against k_detector_v1 is
+// WHERE the divergent work runs (ncu of v1: 12.3 of 32 lanes per instruction, 49 % of the warp instructions with < 8):
+//
+//  * Interaction-type regrouping inside the warp.  A lane is in one of two states: FLY (next step = one Woodcock flight)
+//    or KN (its photon Compton-scattered; next step = one rejection round of the Klein-Nishina sampler).  Both steps start
+//    with one Philox block, drawn by all lanes together; then the FLY lanes do their flight and the KN lanes their round,
+//    and the lanes whose interaction is decided (Compton accepted, Rayleigh, photo-absorption) meet again in ONE copy of
+//    the rotation and of the adder.  In v1 the rejection loop ran nested inside the flight with the 2-5 lanes that had just
+//    scattered, Philox included; here rejected lanes pool with the lanes that scatter on the following flights.  The draws
+//    of a photon are the same blocks in the same order (flight, rounds, flight, ...), so results are unchanged.
+//  * Readout and event emission pooled across photons.  A warp owns 32 + kSpare adder columns.  A photon that finishes
+//    with deposits leaves its column behind (header: photon, event, panel, slot count) and its lane takes a spare one
+//    and goes on with the next photon; when the spares run out the warp reads out all pending columns at once, one lane
+//    per finished photon (readout merges with their IEEE divides, event records as 16-byte vector stores), with one
+//    atomic for the lot.  v1 did this per photon as it finished: 2-3 lanes on the merges, 5 on the emission.
+//  * Hits staged per warp in shared memory and flushed 32 at a time: one atomic per flush instead of one per loop
+//    iteration, and the rows leave as full-line vector stores into the SoA hit buffer (v1: 30 scalar STG.32 per hit pair).
+template <int NC>
+struct WarpPool {
+    int4 hid[32];            // staged hits: parn, pann, modn, cryn
+    float4 hf[32];           // E, x, y, z
+    double ht[32];
+    double t[kSlots][NC];    // adder columns, [slot][column]
+    int key[kSlots][NC];
+    float E[kSlots][NC], x[kSlots][NC], y[kSlots][NC], z[kSlots][NC];
+    int h_parn[NC], h_eid[NC], h_pan_ns[NC];   // header of a pending column: photon, event, panel index | slots << 8
+    int htype[32];
+    unsigned char free_col[NC], pend_col[NC];  // stack of free columns, list of pending ones
+};
+
+template <int NC, int BPS>
+__global__ void __launch_bounds__(kDetThreads, BPS) k_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs,
+                                                              int rdepth, int rpolicy, int record_hits, HitBuffer hits, EventBuf ev,
+                                                              unsigned* __restrict__ counters, unsigned* __restrict__ ticket, uint64_t seed,
+                                                              int refill_min, unsigned long long id_base) {
+    static_assert(NC > 32 && NC <= 64 && sizeof(WarpPool<NC>) % 16 == 0, "column pool shape");
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    WarpPool<NC>& wp = reinterpret_cast<WarpPool<NC>*>(s_raw)[warp];
+    PanelDev* s_panels = reinterpret_cast<PanelDev*>(s_raw + sizeof(WarpPool<NC>) * (kDetThreads / 32));
+    for (unsigned i = lane; i < (unsigned)(NC - 32); i += 32) wp.free_col[i] = (unsigned char)(32 + i);
+    stage_panels(s_panels, det);
+    // programmatic dependent launch: everything above overlapped the tail of the front-end kernel; its queue is read below
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned n = min(*q2.count, q2.capacity);
+    const int depth = (rdepth != 3 && rpolicy == 1) ? 2 : rdepth;
+    bool active = false, exhausted = false, kn = false;
+    unsigned chunk_pos = 0, chunk_end = 0;   // the warp's claimed share of the queue (warp-uniform)
+    unsigned seen = 0;                       // ticket value after this warp's last claim
+    unsigned nfree = NC - 32, npend = 0, hstaged = 0;   // warp-uniform: free columns, pending columns, staged hits
+    const unsigned nwarps = gridDim.x * (kDetThreads / 32);
+    float x = 0, y = 0, z = 0, E = 0, vx = 0, vy = 0, vz = 0, kn_phi = 0;
+    double t = 0;
+    int eid = 0, parn = 0, pa = 0, nslot = 0, col = (int)lane, h_key = 0, mid = 0;
+    unsigned n_drop_adder = 0;
+    Philox rng(seed, 0, 0);
+
+    // all pending columns -> events: one lane per finished photon
+    auto drain = [&]() {
+        __syncwarp();
+        unsigned ne = 0, deadmask = 0;
+        int c = 0, hp = 0, nsl = 0;
+        if (lane < npend) {
+            c = wp.pend_col[lane];
+            hp = wp.h_pan_ns[c];
+            nsl = hp >> 8;
+            if (nsl > 1 && rdepth != 3) deadmask = readout_merge(wp, c, nsl, depth, rpolicy);
+            ne = (unsigned)(nsl - __popc(deadmask));
+        }
+        unsigned incl = ne;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned yv = __shfl_up_sync(kFull, incl, o);
+            if (lane >= (unsigned)o) incl += yv;
+        }
+        const unsigned total = __shfl_sync(kFull, incl, 31);
+        unsigned base = 0;
+        if (lane == 31 && total) base = atomicAdd(ev.count, total);
+        base = __shfl_sync(kFull, base, 31);
+        unsigned eslot = base + incl - ne;
+        if (lane < npend) {
+            const int panel_id = s_panels[hp & 0xff].id, pn = wp.h_parn[c], ei = wp.h_eid[c];
+#pragma unroll 1
+            for (int k = 0; k < nsl; k++) {
+                if (deadmask >> k & 1u) continue;
+                if (eslot < ev.capacity) {
+                    const int key = wp.key[k][c];
+                    EventRec r;
+                    r.parn = pn; r.pann = panel_id; r.modn = key >> 16; r.cryn = key & 0xffff;
+                    r.siten = event_siten(depth, panel_id, r.modn, r.cryn, det);
+                    r.eventid = ei;
+                    r.t = wp.t[k][c]; r.E = wp.E[k][c];
+                    r.x = wp.x[k][c]; r.y = wp.y[k][c]; r.z = wp.z[k][c];
+                    store_event_rec(ev.rec + eslot, r);
+                }
+                eslot++;
+            }
+            wp.free_col[nfree + lane] = (unsigned char)c;
+        }
+        nfree += npend;
+        npend = 0;
+        __syncwarp();
+    };
+    // staged hits -> the SoA hit buffer: consecutive rows in consecutive lanes
+    auto flush_hits = [&]() {
+        __syncwarp();
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(hits.count, hstaged);
+        base = __shfl_sync(kFull, base, 0);
+        if (lane < hstaged && base + lane < hits.capacity) {
+            hits.id4[base + lane] = wp.hid[lane];
+            hits.f4[base + lane] = wp.hf[lane];
+            hits.t[base + lane] = wp.ht[lane];
+            hits.type[base + lane] = wp.htype[lane];
+        }
+        hstaged = 0;
+        __syncwarp();
+    };
+    auto stage_hit = [&](bool has, int type, float Eh) {
+        const unsigned m = __ballot_sync(kFull, has);
+        if (m == 0u) return;
+        const unsigned cnt = __popc(m);
+        if (hstaged + cnt > 32u) flush_hits();
+        if (has) {
+            const unsigned p = hstaged + __popc(m & lt_mask);
+            wp.hid[p] = make_int4(parn, s_panels[pa].id, h_key >> 16, h_key & 0xffff);
+            wp.hf[p] = make_float4(Eh, x, y, z);
+            wp.ht[p] = t;
+            wp.htype[p] = type;
+        }
+        hstaged += cnt;
+    };
+
+    while (true) {
+        // ---- refill idle lanes from the warp's chunk of the queue; a new chunk costs one ticket atomic per kDetChunk photons
+        unsigned amask = __ballot_sync(kFull, active);
+        if (!exhausted && (__popc(~amask) >= refill_min || amask == 0)) {
+            if (chunk_pos == chunk_end) {
+                // guided self-scheduling: full chunks while the queue is long, smaller ones as it drains (remaining /
+                // 2 x warps, from the ticket value this warp saw last), so that the warps run dry together
+                const unsigned left = n > seen ? n - seen : 0u;
+                const unsigned want = max(2u, min(kDetChunk, left / (2u * nwarps)));
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(ticket, want);
+                base = __shfl_sync(kFull, base, 0);
+                seen = base + want;
+                chunk_pos = min(base, n);
+                chunk_end = min(base + want, n);
+                if (base >= n) exhausted = true;
+            }
+            const unsigned need = ~amask;
+            const unsigned avail = chunk_end - chunk_pos;
+            const unsigned rank = __popc(need & lt_mask);
+            if (!active && rank < avail) {
+                const unsigned idx = chunk_pos + rank;
+                const float4 pe = __ldcs(q2.pos_e + idx);
+                const float4 dn = __ldcs(q2.dir_n + idx);
+                t = __ldcs(q2.t + idx);
+                const int2 id = __ldcs(q2.ids + idx);
+                x = pe.x; y = pe.y; z = pe.z; E = pe.w;
+                vx = dn.x; vy = dn.y; vz = dn.z; pa = __float_as_int(dn.w);
+                eid = id.x; parn = id.y;
+                rng = Philox(seed, photon_index(parn, id_base), (uint32_t)kStageDetector << 24);
+                nslot = 0;
+                kn = false;
+                active = true;
+            }
+            chunk_pos += min((unsigned)__popc(need), avail);
+            amask = __ballot_sync(kFull, active);
+        }
+        if (amask == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- one step per active lane.  Up to two hits per step (Compton deposit + absorption of the remainder), both at
+        // the lane's position
+        int nh = 0, h_type0 = 0;
+        float h_E0 = 0.f, h_E1 = 0.f;
+        bool finished = false, turn = false;
+        float costh = 1.f, phi = 0.f;
+        uint4 r = make_uint4(0u, 0u, 0u, 0u);
+        if (active) r = rng.next();
+        if (active && !kn) {
+            // FLY: one Woodcock flight (gPET_kernals.cu:1018-1050) and the choice of the interaction
+            const PanelDev& pd = s_panels[pa];
+            int ie; float fe;
+            energy_index(tb, E, ie, fe);
+            float lammin = __fdividef(1.0f, lerp_table(tb.maj_detector, ie, fe));
+            float s = -lammin * __logf(u01(r.x));
+            x = fmaf(s, vx, x); y = fmaf(s, vy, y); z = fmaf(s, vz, z);
+            t += (double)s * kInvSpeedOfLight;
+            if (fabsf(y) > pd.ly * 0.5f || fabsf(z) > pd.lz * 0.5f || x * pd.dirx < 0.f || x * pd.dirx > pd.lx) {
+                finished = true;  // left the panel
+            } else {
+                int M_id, L_id;
+                crystal_search(pd, det, x, y, z, mid, M_id, L_id);
+                h_key = (M_id << 16) | (L_id & 0xffff);
+                float rho = det.dens[mid];
+                int mat = det.mat[mid];
+                Xs3 xs = lerp_xs(tb, mat, ie, fe);
+                float lamden = lammin * rho;
+                float prob = fmaxf(1.0f - lamden * xs.tot, 0.f);
+                float u = u01(r.y);
+                if (u >= prob) {
+                    prob += lamden * xs.compt;
+                    if (u < prob) {
+                        kn = true;                       // Compton: the sampler's rounds are this lane's next steps
+                        kn_phi = kTwoPi * u01(r.z);
+                    } else {
+                        prob += lamden * xs.rayl;
+                        if (u < prob) {
+                            costh = surface_lookup(tb.rayff, mat, tb.rl_ncp, tb.rl_ne, E * tb.rl_ide, u01(r.z) * tb.rl_idcp);
+                            phi = kTwoPi * u01(r.w);
+                            turn = true;
+                        } else {
+                            if (mid == 0) { h_type0 = 4; h_E0 = E; nh = 1; }
+                            finished = true;
+                        }
+                    }
+                }
+            }
+        } else if (active) {
+            // KN: one rejection round of the Klein-Nishina sampler for free electrons at rest (compton_kn above,
+            // gPET_kernals.cu:90-126), on this step's Philox block
+            const float e0 = E * kIMC2;
+            const float twoe = 2.0f * e0;
+            const float kmin2 = 1.0f / ((1.0f + twoe) * (1.0f + twoe));
+            const float loge = __logf(1.0f + twoe);
+            float efrac;
+            if (u01(r.x) * (loge + twoe * (1.0f + e0) * kmin2) < loge) efrac = expf(-u01(r.y) * loge);
+            else efrac = sqrtf(kmin2 + u01(r.y) * (1.0f - kmin2));
+            const float mess = e0 * e0 * efrac * (1.0f + efrac * efrac);
+            if (u01(r.z) * mess <= mess - (1.0f - efrac) * ((1.0f + twoe) * efrac - 1.0f)) {
+                kn = false;
+                costh = 1.0f - (1.0f - efrac) / (efrac * e0);
+                const float de = E * (1.0f - efrac);
+                phi = kn_phi;
+                if (mid == 0) { h_type0 = 1; h_E0 = de; nh = 1; }
+                E -= de;
+                if (E < eabs) {
+                    if (mid == 0) { h_E1 = E; nh = 2; }  // type 2: remainder absorbed on the spot
+                    finished = true;
+                } else {
+                    turn = true;
+                }
+            }
+        }
+        // ---- decided interactions meet here: one rotation, one adder
+        if (turn) rotate_dir(vx, vy, vz, costh, phi);
+        if (nh >= 1) {
+            if (!adder(wp, col, nslot, h_key, h_E0, x, y, z, t)) n_drop_adder++;
+            if (nh == 2 && !adder(wp, col, nslot, h_key, h_E1, x, y, z, t)) n_drop_adder++;
+        }
+        if (record_hits) {
+            stage_hit(nh >= 1, h_type0, h_E0);
+            stage_hit(nh == 2, 2, h_E1);
+        }
+        // ---- finished photons with deposits park their column and take a spare one
+        if (finished) active = false;
+        unsigned fin = __ballot_sync(kFull, finished && nslot > 0);
+        while (fin) {
+            if (nfree == 0u) drain();
+            const unsigned take = min((unsigned)__popc(fin), nfree);
+            const bool in = (fin >> lane) & 1u;
+            const unsigned rank = __popc(fin & lt_mask);
+            if (in && rank < take) {
+                wp.h_parn[col] = parn; wp.h_eid[col] = eid; wp.h_pan_ns[col] = pa | (nslot << 8);
+                wp.pend_col[npend + rank] = (unsigned char)col;
+                col = wp.free_col[nfree - 1u - rank];
+                nslot = 0;
+            }
+            fin = __ballot_sync(kFull, in && rank >= take);
+            npend += take;
+            nfree -= take;
+        }
+    }
+    if (npend) drain();
+    if (hstaged) flush_hits();
     // per-warp tallies
     unsigned b = n_drop_adder;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(kFull, b, o);
     if (lane == 0 && b) atomicAdd(&counters[9], b);
+}
+
+// hits in the reference's file layout (gPET.cu:367-376; readOutput.m:3-16), for the dumps and gpet_fetch_hits only
+__global__ void k_hits_to_rows(HitBuffer h, unsigned n, int* __restrict__ id5, float* __restrict__ f5) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 a = h.id4[i];
+        const float4 f = h.f4[i];
+        int* hi = id5 + 5ull * i;
+        float* hf = f5 + 5ull * i;
+        hi[0] = a.x; hi[1] = a.y; hi[2] = a.z; hi[3] = a.w; hi[4] = h.type[i];
+        hf[0] = f.x; hf[1] = (float)h.t[i]; hf[2] = f.y; hf[3] = f.z; hf[4] = f.w;
+    }
+}
+
+__global__ void k_hits_to_aos(HitBuffer h, unsigned n, gpet_hit* __restrict__ out) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4 a = h.id4[i];
+        const float4 f = h.f4[i];
+        gpet_hit o;
+        o.parn = a.x; o.pann = a.y; o.modn = a.z; o.cryn = a.w; o.type = h.type[i];
+        o.E = f.x; o.t = h.t[i]; o.t32 = (float)o.t; o.x = f.y; o.y = f.z; o.z = f.w;
+        out[i] = o;
+    }
 }
 
 // ------------------------------------------------------------------------------------------- host AoS <-> queue
@@ -1080,7 +1379,7 @@ __global__ void __launch_bounds__(kThreads) k_psf_positron(const gpet_photon* __
         q0.pos_e[p] = make_float4(x, y, z, E);
         q0.dir_n[p] = make_float4(vx, vy, vz, __int_as_float(0));
         q0.t[p] = e.t;
-        q0.ids[p] = make_int2((int)(unsigned)gi, (int)(unsigned)(2ull * gi + which));
+        q0.ids[p] = make_int2((int)((unsigned)gi & kIdMask), (int)((unsigned)(2ull * gi + which) & kIdMask));
     }
 }
 
@@ -1096,6 +1395,20 @@ int persistent_grid(K kernel, int num_sms, size_t smem, int threads = kThreads) 
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
     if (per_sm < 1) per_sm = 1;
     return per_sm * num_sms;
+}
+
+// Launch shapes depend on the device (SM count, shared memory) and on the panel count: cached per device, so that
+// contexts on different GPUs of one process never share a stale grid (a persistent kernel sized for another device can
+// lose its one-wave property; a cooperative one can fail to launch).
+constexpr int kMaxDevices = 64;
+struct ShapeCache {
+    int grid[kMaxDevices][4];
+    size_t smem[kMaxDevices][4];
+};
+int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d >= 0 && d < kMaxDevices ? d : 0;
 }
 
 }  // namespace
@@ -1120,47 +1433,48 @@ int launch_psf_positron(const void* positrons_aos, PhotonQueue q0, unsigned int 
     return 1;
 }
 
-int launch_phantom(PhotonQueue q0, PhotonQueue q1, PhantomDev ph, TablesDev tb, float eabs, uint64_t seed, int num_sms,
-                   cudaStream_t s) {
-    static int grid = 0;
-    if (!grid) grid = persistent_grid(k_phantom, num_sms, 0);
+int launch_phantom(PhotonQueue q0, PhotonQueue q1, PhantomDev ph, TablesDev tb, float eabs, uint64_t seed, unsigned long long id_base,
+                   int num_sms, cudaStream_t s) {
+    static ShapeCache sc{};
+    const int dev = current_device();
+    if (!sc.grid[dev][0]) sc.grid[dev][0] = persistent_grid(k_phantom, num_sms, 0);
     cudaMemsetAsync(q1.count, 0, sizeof(unsigned), s);
-    GPET_LAUNCH("k_phantom", s, k_phantom<<<grid, kThreads, 0, s>>>(q0, q1, ph, tb, eabs, seed));
+    GPET_LAUNCH("k_phantom", s, k_phantom<<<sc.grid[dev][0], kThreads, 0, s>>>(q0, q1, ph, tb, eabs, seed, id_base));
     return 1;
 }
 
 int launch_panel_entry(PhotonQueue q1, PhotonQueue q2, DetectorDev det, unsigned int* counters, int num_sms, cudaStream_t s) {
     const size_t smem_panels = (size_t)det.npanels * sizeof(PanelSm);
-    static int grid = 0;
-    static size_t grid_smem = 0;
-    if (!grid || grid_smem != smem_panels) {
+    static ShapeCache sc{};
+    const int dev = current_device();
+    if (!sc.grid[dev][0] || sc.smem[dev][0] != smem_panels) {
         if (smem_panels > 48 * 1024)
             cudaFuncSetAttribute(k_panel_entry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panels);
-        grid = persistent_grid(k_panel_entry, num_sms, smem_panels);
-        grid_smem = smem_panels;
+        sc.grid[dev][0] = persistent_grid(k_panel_entry, num_sms, smem_panels);
+        sc.smem[dev][0] = smem_panels;
     }
     cudaMemsetAsync(q2.count, 0, sizeof(unsigned), s);
     cudaMemsetAsync(counters + 8, 0, sizeof(unsigned), s);   // photons on a panel
-    GPET_LAUNCH("k_panel_entry", s, k_panel_entry<<<grid, kThreads, smem_panels, s>>>(q1, det, q2, counters));
+    GPET_LAUNCH("k_panel_entry", s, k_panel_entry<<<sc.grid[dev][0], kThreads, smem_panels, s>>>(q1, det, q2, counters));
     return 1;
 }
 
 int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQueue q0, PhotonQueue q1, PhotonQueue q2,
                  PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, unsigned int* counters, unsigned int* hot, uint64_t seed,
-                 int num_sms, cudaStream_t s, bool reset) {
+                 unsigned long long id_base, int num_sms, cudaStream_t s, bool reset) {
     const size_t smem = sizeof(FrontStage) + (size_t)det.npanels * sizeof(PanelSm);
-    static int grid[2] = {0, 0};
-    static size_t grid_smem = 0;
-    if (!grid[0] || grid_smem != smem) {
+    static ShapeCache sc{};
+    const int dev = current_device();
+    if (!sc.grid[dev][0] || sc.smem[dev][0] != smem) {
         if (smem > 48 * 1024) {
             cudaFuncSetAttribute(k_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             cudaFuncSetAttribute(k_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
-        grid[0] = persistent_grid(k_front<false>, num_sms, smem);
-        grid[1] = persistent_grid(k_front<true>, num_sms, smem);
-        grid_smem = smem;
+        sc.grid[dev][0] = persistent_grid(k_front<false>, num_sms, smem);
+        sc.grid[dev][1] = persistent_grid(k_front<true>, num_sms, smem);
+        sc.smem[dev][0] = smem;
     }
-    const int gen_min = tune("GPET_GEN_MIN", 12), entry_min = tune("GPET_ENTRY_MIN", 12);
+    static const int gen_min = tune("GPET_GEN_MIN", 12), entry_min = tune("GPET_ENTRY_MIN", 12);
     unsigned* ticket = hot + kHotTicketFront;
     if (reset) {
         cudaMemsetAsync(q1.count, 0, sizeof(unsigned), s);       // photons that left the phantom (tally only: q1 is not filled)
@@ -1169,26 +1483,44 @@ int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQu
         cudaMemsetAsync(ticket, 0, sizeof(unsigned), s);
     }
     if (frame_dev) {
-        GPET_LAUNCH("k_front", s, k_front<false><<<grid[0], kThreads, smem, s>>>(frame_dev, npairs, q0, ph, tb, det, eabs, seed, q2,
-                                                                               q1.count, counters, ticket, gen_min, entry_min));
+        GPET_LAUNCH("k_front", s, k_front<false><<<sc.grid[dev][0], kThreads, smem, s>>>(frame_dev, npairs, q0, ph, tb, det, eabs, seed, q2,
+                                                                                       q1.count, counters, ticket, gen_min, entry_min, 0ull));
     } else {
-        GPET_LAUNCH("k_front<queue>", s, k_front<true><<<grid[1], kThreads, smem, s>>>(nullptr, 0ull, q0, ph, tb, det, eabs, seed, q2,
-                                                                                     q1.count, counters, ticket, gen_min, entry_min));
+        GPET_LAUNCH("k_front<queue>", s, k_front<true><<<sc.grid[dev][1], kThreads, smem, s>>>(nullptr, 0ull, q0, ph, tb, det, eabs, seed, q2,
+                                                                                             q1.count, counters, ticket, gen_min, entry_min, id_base));
     }
+    return 1;
+}
+
+// k_detector variants: GPET_DET_V=1 round 1's kernel, 2 (default) 8 spare columns per warp at 3 blocks per SM,
+// 3: 24 spare columns at 2 blocks per SM (A/B runs, tools/kprof.py)
+template <typename K>
+int launch_detector_variant(K kernel, int slot, size_t pool_bytes, PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth,
+                            int readout_policy, int record_hits, HitBuffer hits, EventBuf ev, unsigned int* counters, unsigned* ticket,
+                            uint64_t seed, unsigned long long id_base, int num_sms, cudaStream_t s) {
+    const size_t smem = pool_bytes + (size_t)det.npanels * sizeof(PanelDev);
+    static ShapeCache sc{};
+    const int dev = current_device();
+    if (!sc.grid[dev][slot] || sc.smem[dev][slot] != smem) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sc.grid[dev][slot] = persistent_grid(kernel, num_sms, smem, kDetThreads);
+        sc.smem[dev][slot] = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)sc.grid[dev][slot]); cfg.blockDim = dim3((unsigned)kDetThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    static const int refill_min = tune("GPET_REFILL_MIN", 4);
+    GPET_LAUNCH("k_detector", s, cudaLaunchKernelEx(&cfg, kernel, q2, det, tb, eabs, readout_depth, readout_policy, record_hits, hits, ev,
+                                                    counters, ticket, seed, refill_min, id_base));
     return 1;
 }
 
 int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
                     int record_hits, HitBuffer hits, EventBuf ev, unsigned int* counters, unsigned int* hot, uint64_t seed,
-                    int num_sms, cudaStream_t s, bool reset) {
-    const size_t smem = sizeof(SlotsSmem) + (size_t)det.npanels * sizeof(PanelDev);
-    static int grid = 0;
-    static size_t grid_smem = 0;
-    if (!grid || grid_smem != smem) {
-        cudaFuncSetAttribute(k_detector, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        grid = persistent_grid(k_detector, num_sms, smem, kDetThreads);
-        grid_smem = smem;
-    }
+                    unsigned long long id_base, int num_sms, cudaStream_t s, bool reset) {
     if (ev.count != hits.count + 1 || (reinterpret_cast<uintptr_t>(hits.count) & 7u)) return -1;   // see kernels.hpp: caller reports it
     unsigned* ticket = hot + kHotTicketDet;
     if (reset) {
@@ -1196,17 +1528,29 @@ int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, i
         cudaMemsetAsync(counters + 9, 0, sizeof(unsigned), s);     // adder drops
         cudaMemsetAsync(ticket, 0, sizeof(unsigned), s);
     }
-    {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)kDetThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        const int refill_min = tune("GPET_REFILL_MIN", 4);
-        GPET_LAUNCH("k_detector", s, cudaLaunchKernelEx(&cfg, k_detector, q2, det, tb, eabs, readout_depth, readout_policy, record_hits, hits, ev,
-                                                        counters, ticket, seed, refill_min));
-    }
+    static const int variant = tune("GPET_DET_V", 2);
+    constexpr size_t kWarps = kDetThreads / 32;
+    if (variant == 1)
+        return launch_detector_variant(k_detector_v1, 0, sizeof(SlotsSmem), q2, det, tb, eabs, readout_depth, readout_policy, record_hits, hits,
+                                       ev, counters, ticket, seed, id_base, num_sms, s);
+    if (variant == 3)
+        return launch_detector_variant(k_detector<56, 2>, 2, kWarps * sizeof(WarpPool<56>), q2, det, tb, eabs, readout_depth, readout_policy,
+                                       record_hits, hits, ev, counters, ticket, seed, id_base, num_sms, s);
+    return launch_detector_variant(k_detector<40, 3>, 1, kWarps * sizeof(WarpPool<40>), q2, det, tb, eabs, readout_depth, readout_policy,
+                                   record_hits, hits, ev, counters, ticket, seed, id_base, num_sms, s);
+}
+
+int launch_hits_to_rows(HitBuffer hits, unsigned int n, int* id5, float* f5, cudaStream_t s) {
+    if (n == 0) return 0;
+    const unsigned blocks = std::min((n + kThreads - 1) / kThreads, 4096u);
+    GPET_LAUNCH("k_hits_to_rows", s, k_hits_to_rows<<<blocks, kThreads, 0, s>>>(hits, n, id5, f5));
+    return 1;
+}
+
+int launch_hits_to_aos(HitBuffer hits, unsigned int n, void* aos, cudaStream_t s) {
+    if (n == 0) return 0;
+    const unsigned blocks = std::min((n + kThreads - 1) / kThreads, 4096u);
+    GPET_LAUNCH("k_hits_to_aos", s, k_hits_to_aos<<<blocks, kThreads, 0, s>>>(hits, n, static_cast<gpet_hit*>(aos)));
     return 1;
 }
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GPET_ABI_VERSION 3  /* 2: gpet_transport_params + record_psf / record_sphere, gpet_digitizer_params + noise_*, gpet_set_psf_output, gpet_stage_noise
+#define GPET_ABI_VERSION 4  /* 4: 64-bit history numbers (gpet_set_first_pair), gpet_peek_config_device, results of large file runs streamed; 3: see below; 2: gpet_transport_params + record_psf / record_sphere, gpet_digitizer_params + noise_*, gpet_set_psf_output, gpet_stage_noise
                              * 3: coincidence classes: gpet_digitizer_params + coinc_pair_shift, gpet_stats + trues / scatters / randoms,
                              *    gpet_fetch_coincidence_classes, gpet_result_coincidence_classes, gpet_mark_scattered */
 
@@ -328,6 +328,15 @@ int gpet_profile_count(gpet_ctx* ctx);
 int gpet_profile_get(gpet_ctx* ctx, int i, char* name, int name_cap, double* total_ms, uint64_t* launches);
 /* Shard the planned frames: this context only runs frames f with f % world == rank. */
 int gpet_set_shard(gpet_ctx* ctx, int rank, int world);
+/* 64-bit history numbers.  The reference indexes atoms and threads with 32-bit integers (gPET.h:50 `unsigned int natom`,
+ * gPET_kernals.cu:490-497), which caps an acquisition near 4e9 histories.  Here every pair has a 64-bit global index
+ * (pair k of the acquisition = first_pair + k; photons 2k, 2k+1) that keys all its Philox streams; the 32-bit
+ * eventid / parn fields of the output records keep the low 31 bits (parn == -1 stays the mark of a noise single).
+ * first_pair (default 0) lets a caller continue, or shard by decay index, a longer history sequence. */
+int gpet_set_first_pair(gpet_ctx* ctx, uint64_t first_pair);
+/* "GPU index" line of input_PET.in (main.cu:52-56) without creating a context: the device a CLI run should use.
+ * Returns the index (>= 0) or a negative gpet_status. */
+int gpet_peek_config_device(const char* input_file);
 /* The direction table gpet_run narrows the panel search with: 32^3 words over the direction cube
  * [-1,1]^3, cell = floor((v + 1) * 16) per axis, x fastest; bit i set = a photon flying in a direction of that cell whose
  * line passes the reference sphere (centre x y z, radius -> ref_sphere) can enter panel i.  Returns the number of words

@@ -62,6 +62,16 @@ static double u01d(uint32_t a, uint32_t b) {
     return (double)k * 1.1102230246251565e-16 + 5.551115123125783e-17;
 }
 
+/* 64-bit history numbers (gpet_b200.h gpet_set_first_pair; the reference stops at 32 bits, gPET.h:50): records keep the low
+ * 31 bits, Philox streams are keyed by the full index, rebuilt from the record and the index of the frame's first photon.
+ * id_base == 0: the 32-bit id as it is.  Set by orc_set_id_base() before a call (test infrastructure: one global). */
+static uint64_t g_id_base = 0;
+void orc_set_id_base(uint64_t base) { g_id_base = base; }
+static uint64_t photon_index(int32_t parn) {
+    if (g_id_base == 0) return (uint64_t)(uint32_t)parn;
+    return g_id_base + (uint64_t)(((uint32_t)parn - (uint32_t)g_id_base) & 0x7fffffffu);
+}
+
 enum { ST_SOURCE = 1, ST_PHANTOM = 2, ST_DETECTOR = 3, ST_BLUR = 4, ST_PLAN = 5, ST_PSF_POSITRON = 6, ST_NOISE = 7 };
 
 /* ------------------------------------------------------------------------------------------------ records */
@@ -282,7 +292,7 @@ void orc_psf_positron(const orc_photon* pos, int64_t n, uint64_t first, const fl
             if (which == 0) E = ORC_MC2 + delta * ORC_MC2 * 0.5f;
             else { rotate_dir(&ax, &ay, &az, -cosf(delta), phi2); E = ORC_MC2 - delta * ORC_MC2 * 0.5f; }
             p->x = x; p->y = y; p->z = z; p->E = E; p->vx = ax; p->vy = ay; p->vz = az; p->nscat = 0;
-            p->t = e->t; p->eventid = (int32_t)(uint32_t)gi; p->parn = (int32_t)(uint32_t)(2 * gi + which);
+            p->t = e->t; p->eventid = (int32_t)((uint32_t)gi & 0x7fffffffu); p->parn = (int32_t)((uint32_t)(2 * gi + which) & 0x7fffffffu);
         }
     }
 }
@@ -357,7 +367,7 @@ void orc_source_ex(int nsource, const uint64_t* cum_pairs, const int32_t* shape,
             if (which == 0) E = ORC_MC2 + delta * ORC_MC2 * 0.5f;
             else { rotate_dir(&ax, &ay, &az, -cosf(delta), phi2); E = ORC_MC2 - delta * ORC_MC2 * 0.5f; }
             p->x = x; p->y = y; p->z = z; p->E = E; p->vx = ax; p->vy = ay; p->vz = az; p->nscat = 0;
-            p->t = t_us; p->eventid = (int32_t)(uint32_t)gk; p->parn = (int32_t)(uint32_t)(2 * gk + which);
+            p->t = t_us; p->eventid = (int32_t)((uint32_t)gk & 0x7fffffffu); p->parn = (int32_t)((uint32_t)(2 * gk + which) & 0x7fffffffu);
         }
     }
 }
@@ -391,7 +401,7 @@ void orc_phantom_ex(orc_photon* ph, int64_t n, const int32_t* mat, const float* 
         orc_photon* p = ph + id;
         if (p->E < 0.f || p->t <= 0.0) continue;  /* :272 */
         orc_rng g;
-        rng_init(&g, seed, (uint64_t)(uint32_t)p->parn, (uint32_t)ST_PHANTOM << 24);
+        rng_init(&g, seed, photon_index(p->parn), (uint32_t)ST_PHANTOM << 24);
         for (;;) {
             uint32_t r[4];
             rng_next(&g, r);
@@ -580,7 +590,7 @@ int64_t orc_detector(const orc_photon* ph, int64_t n, const orc_panel* panels, i
         entered++;
         const orc_panel* pd = panels + pa;
         orc_rng g;
-        rng_init(&g, seed, (uint64_t)(uint32_t)p->parn, (uint32_t)ST_DETECTOR << 24);
+        rng_init(&g, seed, photon_index(p->parn), (uint32_t)ST_DETECTOR << 24);
         orc_event evs[ORC_MAXEV];
         int cnt = 0;
         for (;;) {
@@ -768,7 +778,7 @@ int64_t orc_digitize(const orc_event* in, int64_t n, const orc_digi_params* p, o
         if (R > 0.f || p->blur_space > 0.f || p->time_blur_sigma_us > 0.f) {
             orc_rng g;
             /* stream = the photon; noise events (parn == -1, orc_noise) are told apart by their event id */
-            uint64_t who = e->parn == -1 ? ((1ull << 32) | (uint32_t)e->eventid) : (uint64_t)(uint32_t)e->parn;
+            uint64_t who = e->parn == -1 ? ((1ull << 63) | (uint32_t)e->eventid) : photon_index(e->parn);
             rng_init(&g, p->seed, who, ((uint32_t)ST_BLUR << 24) | ((uint32_t)e->siten & 0xFFFFFFu));
             uint32_t r[4];
             rng_next(&g, r);

@@ -60,6 +60,11 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def set_id_base(base):
+    """global index of the first photon of the frame the following calls work on (64-bit history numbers); 0 = ids as they are"""
+    lib().orc_set_id_base(C.c_uint64(int(base)))
+
+
 def philox(ctr, key):
     c = np.asarray(ctr, np.uint32); k = np.asarray(key, np.uint32); o = np.zeros(4, np.uint32)
     lib().orc_philox4x32_10(_p(c), _p(k), _p(o))

@@ -414,12 +414,15 @@ def test_run_shipped_example_writes_reference_layouts(tmp_path):
     assert (co["a"]["eventid"] == co["b"]["eventid"]).mean() > 0.9
     # sensitivity: ~0.41 of the photons reach a panel
     assert 0.3 < st.photons_on_panel / (2 * st.pairs) < 0.5
-    # replay pin: adder.dat through the digitizer alone reproduces singles.dat bit for bit (blur is on in the shipped
-    # file, and already applied in this dump, so replay with R = 0)
+    # replay pin: adder.dat is written BEFORE blur, as the reference does (gPET.cu:383-388); through the digitizer alone, blur
+    # on as shipped and the same Philox key, it reproduces singles.dat bit for bit (the blur stream of an event is keyed by
+    # its photon and readout site, both in the record)
     with api.Context(0) as c2:
         c2.load_config_file(ex / "input_PET.in", base_dir=ex)
-        c2.set_digitizer(blur_Rref=0.0)
         again, _ = c2.digitize(adder)
+    # the dump really is the unblurred list: the 511 keV photopeak of the adder is a line, that of the singles is not
+    peak = adder["E"][(adder["E"] > 505e3) & (adder["E"] < 517e3)]
+    assert peak.size > 1000 and np.std(peak) < 600.0 < np.std(sing["E"][(sing["E"] > 450e3) & (sing["E"] < 570e3)])
     assert again.tobytes() == sing.tobytes()
 
 

@@ -193,7 +193,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(l, name), f"{name} declared in gpet_b200.h but not exported"
     assert set(api._SIGS) == declared, declared ^ set(api._SIGS)
-    assert api.lib().gpet_abi_version() == 3
+    assert api.lib().gpet_abi_version() == api.ABI_VERSION == 4
 
 
 def test_missing_or_stale_library_fails_loudly(monkeypatch, tmp_path):

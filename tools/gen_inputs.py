@@ -201,3 +201,65 @@ if __name__ == "__main__":
     write_phantom(m, d, out / "cylinder_phantom_mat.dat", out / "cylinder_phantom_den.dat")
     back_to_back_psf(a.psf_pairs).tofile(out / "psf.dat")
     print("wrote", out)
+
+
+# ------------------------------------------------------------------------------------------------ named configurations
+# The BASELINE.json configurations as files a gPET user would write, shared by tests/test_reference_stats.py,
+# tools/ref_stats.py (which runs the REFERENCE BINARY on them) and the scale runs.  `decays` = expected annihilation
+# pairs in the 0-120 s window (F-18 row 0 of isotopes.txt: T1/2 6586.26 s, branching 0.97).
+STATS_CONFIGS = ("config1_water10", "config2_psf", "config4_mouse", "config5_ring")
+
+
+def stats_config(name, decays, blur=(1, 662000, 0.05, 0, 0), deadtime=(3, 0, 2.2)):
+    """Returns dict(text, phantom=(mat, den) | None, geo_text | None, extra={file: text}, psf=records | None, npanels, moduleN)."""
+    natom = atoms_for_decays(decays, 6586.26, 120.0, 0.97)
+    if name == "config1_water10":
+        # shipped 8-panel geometry, but a phantom that scatters: 10 cm water cylinder (200^3 over 10 cm), F-18 rod r 0.5 x 8 cm
+        n = 200
+        mat, den = cylinder_phantom(n=n, size=10.0, radius=5.0)
+        text = input_file(dims=(n, n, n), offset=(-5.0,) * 3, extent=(10.0,) * 3, mat="input/phantom_mat.dat", den="input/phantom_den.dat",
+                          source="input/src.txt", blur=blur, deadtime=deadtime)
+        return dict(text=text, phantom=(mat, den), geo_text=None, extra={"src.txt": source_file([(natom, 0, 1, 0, 0, 0, 0.5, 8.0, 0)])},
+                    psf=None, npanels=8, moduleN=117)
+    if name == "config2_psf":
+        mat, den = air_phantom(32)
+        text = input_file(dims=(32, 32, 32), mat="input/phantom_mat.dat", den="input/phantom_den.dat", usepsf=1, source="input/psf.dat",
+                          ptype=1, nhist=2 * decays, blur=blur, deadtime=deadtime)
+        return dict(text=text, phantom=(mat, den), geo_text=None, extra={}, psf=back_to_back_psf(decays), npanels=8, moduleN=117)
+    if name == "config4_mouse":
+        n = 256
+        size = (3.2, 3.2, 6.4)
+        text = input_file(dims=(n, n, n), offset=tuple(-x / 2 for x in size), extent=size, mat="input/phantom_mat.dat",
+                          den="input/phantom_den.dat", source="input/src.txt", blur=blur, deadtime=deadtime)
+        return dict(text=text, phantom=mouse_phantom(n, size), geo_text=None,
+                    extra={"src.txt": source_file([(natom, 0, 1, 0, 0, 0, 1.2, 5.0, 0)])}, psf=None, npanels=8, moduleN=117)
+    if name == "config5_ring":
+        n = 256
+        text = input_file(dims=(n, n, n), offset=(-12.8,) * 3, extent=(25.6,) * 3, mat="input/phantom_mat.dat", den="input/phantom_den.dat",
+                          source="input/src.txt", geo="input/ring.geo", blur=blur, deadtime=deadtime)
+        return dict(text=text, phantom=water_cylinder_phantom(n, 0.1, 20.0, 20.0), geo_text=ring_geo(32, 40.0),
+                    extra={"src.txt": source_file([(natom, 0, 1, 0, 0, 0, 0.5, 18.0, 0)])}, psf=None, npanels=32, moduleN=52)
+    raise KeyError(name)
+
+
+def write_workdir(ex, cfg, example_dir, packed_tables=None):
+    """Lay `cfg` (stats_config) out under `ex` the way the reference expects: input_PET.in, input/, data/, output/."""
+    ex = Path(ex)
+    (ex / "input").mkdir(parents=True, exist_ok=True)
+    (ex / "data").mkdir(exist_ok=True)
+    (ex / "output").mkdir(exist_ok=True)
+    example_dir = Path(example_dir)
+    (ex / "input_PET.in").write_text(cfg["text"])
+    (ex / "input" / "config8.geo").write_text((example_dir / "input" / "config8.geo").read_text())
+    (ex / "data" / "isotopes.txt").write_text((example_dir / "data" / "isotopes.txt").read_text())
+    if packed_tables is not None and not (ex / "data" / "input4gPET.gpettab").exists():
+        (ex / "data" / "input4gPET.gpettab").symlink_to(packed_tables)
+    if cfg["phantom"] is not None:
+        write_phantom(cfg["phantom"][0], cfg["phantom"][1], ex / "input" / "phantom_mat.dat", ex / "input" / "phantom_den.dat")
+    if cfg["geo_text"] is not None:
+        (ex / "input" / "ring.geo").write_text(cfg["geo_text"])
+    for name, content in cfg["extra"].items():
+        (ex / "input" / name).write_text(content)
+    if cfg["psf"] is not None:
+        np.ascontiguousarray(cfg["psf"], "<f8").tofile(ex / "input" / "psf.dat")
+    return ex
