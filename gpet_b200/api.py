@@ -141,6 +141,11 @@ _SIGS = {
     "gpet_set_spectrum": (C.c_int, [_P, C.c_int, C.c_float, C.c_float]),
     "gpet_set_shard": (C.c_int, [_P, C.c_int, C.c_int]),
     "gpet_set_first_pair": (C.c_int, [_P, C.c_uint64]),
+    "gpet_set_emit_window": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),
+    "gpet_clear_emit_window": (C.c_int, [_P]),
+    "gpet_get_emit_counts": (C.c_int, [_P, _P]),
+    "gpet_copy_events_to_device": (C.c_int64, [_P, _P, C.c_int64]),
+    "gpet_put_events_device": (C.c_int, [_P, _P, C.c_int64]),
     "gpet_peek_config_device": (C.c_int, [C.c_char_p]),
     "gpet_get_direction_table": (C.c_int64, [_P, _P, C.c_int64, _P]),
     "gpet_profile_enable": (C.c_int, [_P, C.c_int]),
@@ -325,6 +330,25 @@ class Context:
 
     def set_shard(self, rank, world):
         self._ck(self._l.gpet_set_shard(self._h, rank, world))
+
+    def set_emit_window(self, lo_us, hi_us, halo_start_us=float("-inf")):
+        """digitize a time slice [lo, hi) given with its halo (gpet_set_emit_window); None clears"""
+        self._ck(self._l.gpet_set_emit_window(self._h, float(lo_us), float(hi_us), float(halo_start_us)))
+
+    def clear_emit_window(self):
+        self._ck(self._l.gpet_clear_emit_window(self._h))
+
+    def emit_counts(self):
+        """(singles before the window, singles inside it, halo-too-short flag) of the last digitizer pass"""
+        out = (C.c_uint64 * 3)()
+        self._ck(self._l.gpet_get_emit_counts(self._h, out))
+        return int(out[0]), int(out[1]), int(out[2])
+
+    def copy_events_to_device(self, dst_ptr, cap):
+        return self._ck(self._l.gpet_copy_events_to_device(self._h, C.c_void_p(dst_ptr), int(cap)))
+
+    def put_events_device(self, src_ptr, n):
+        self._ck(self._l.gpet_put_events_device(self._h, C.c_void_p(src_ptr), int(n)))
 
     def set_first_pair(self, first_pair):
         """global 64-bit index of the acquisition's first annihilation pair (gpet_set_first_pair)"""

@@ -1,6 +1,10 @@
 // extern "C" boundary of libgpet_b200.so (see include/gpet_b200.h for the reference call each entry replaces).
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -95,10 +99,10 @@ int ensure_buffers(gpet_ctx* c) {
     if ((r = dev_alloc(c, &c->hits.f4, ch))) return r;
     if ((r = dev_alloc(c, &c->hits.t, ch))) return r;
     if ((r = dev_alloc(c, &c->hits.type, ch))) return r;
-    c->hits.count = w.hot + kHotHitsEvents;
+    c->hits.count = w.hot + kHotHits;
     c->hits.capacity = (unsigned)ch;
     if ((r = dev_alloc(c, &c->ev.rec, ce))) return r;
-    c->ev.count = w.hot + kHotHitsEvents + 1;
+    c->ev.count = w.hot + kHotEvents;
     c->ev.capacity = (unsigned)ce;
     for (int k = 0; k < 2; k++) {
         if ((r = dev_alloc(c, &w.tkeys[k], ce))) return r;
@@ -298,6 +302,10 @@ int upload_geometry(gpet_ctx* c) {
         d.lsoy = p.LSOy; d.lsoz = p.LSOz; d.spy = p.spacey; d.spz = p.spacez;
         d.id = p.panel;
         d.r2 = 0.25f * (p.lengthy * p.lengthy + p.lengthz * p.lengthz);
+        // reciprocals of crystalSearch's divisors (the fp32 sums the kernel forms), rounded once from extended precision
+        auto rcp = [](float a, float b) { const float s = a + b; return (float)(1.0L / (long double)s); };
+        d.rcp_my = rcp(p.MODy, p.Mspacey); d.rcp_mz = rcp(p.MODz, p.Mspacez);
+        d.rcp_cy = rcp(p.LSOy, p.spacey); d.rcp_cz = rcp(p.LSOz, p.spacez);
     }
     if ((r = dev_alloc(c, &c->d_panels, pd.size()))) return r;
     CK(cudaMemcpy(c->d_panels, pd.data(), pd.size() * sizeof(PanelDev), cudaMemcpyHostToDevice));
@@ -353,6 +361,8 @@ DigitizerDev digitizer_dev(const gpet_ctx* c) {
     d.noise_gap = p.noise_mean_gap_us; d.noise_Emean = p.noise_Emean_eV; d.noise_sigma = p.noise_sigma_eV;
     d.noise_interval = p.noise_interval_us;
     d.id_base = c->id_base;
+    d.emit_on = c->emit_on ? 1 : 0;
+    d.emit_lo = c->emit_lo; d.emit_hi = c->emit_hi; d.trust_lo = c->emit_trust;
     d.pair_shift = std::min(std::max(p.coinc_pair_shift, 0), 31);
     d.scat_tag = c->d_scat_tag; d.scat_mask = c->scat_mask; d.scat_serial = c->scat_serial;
     return d;
@@ -408,15 +418,15 @@ int validate_materials(gpet_ctx* c) {
 // 32..), asynchronously.  patch_counters() then puts the hot values where the host code reads them.
 int fetch_counters_async(gpet_ctx* c, unsigned* h) {
     CK(cudaMemcpyAsync(h, c->ws.counters, 32 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpy2DAsync(h + 32, 2 * sizeof(unsigned), c->ws.hot, kHotStride * sizeof(unsigned), 2 * sizeof(unsigned), 4,
+    CK(cudaMemcpy2DAsync(h + 32, 2 * sizeof(unsigned), c->ws.hot, kHotStride * sizeof(unsigned), 2 * sizeof(unsigned), kHotLines,
                          cudaMemcpyDeviceToHost, c->stream));
     return GPET_OK;
 }
 
 void patch_counters(unsigned* h) {
     h[21] = h[32 + 2 * (kHotQ2 / kHotStride)];                 // photons on a panel
-    h[18] = h[32 + 2 * (kHotHitsEvents / kHotStride)];         // hits
-    h[19] = h[32 + 2 * (kHotHitsEvents / kHotStride) + 1];     // events
+    h[18] = h[32 + 2 * (kHotHits / kHotStride)];               // hits
+    h[19] = h[32 + 2 * (kHotEvents / kHotStride)];             // events
 }
 
 int read_counters(gpet_ctx* c) {  // synchronises the stream
@@ -479,6 +489,7 @@ void gpet_destroy(gpet_ctx* c) {
         if (c->res_coinc.p) cudaFreeHost(c->res_coinc.p);
         if (c->res_pairs.p) cudaFreeHost(c->res_pairs.p);
         if (c->res_cls.p) cudaFreeHost(c->res_cls.p);
+        if (c->res_adder.p) cudaFreeHost(c->res_adder.p);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         if (c->own_stream) cudaStreamDestroy(c->own_stream);
     }
@@ -647,6 +658,65 @@ int gpet_set_source_atoms(gpet_ctx* c, int i, uint64_t natom) {
     if (!c || !c->have_src || i < 0 || i >= c->src.n()) return GPET_ERR_ARG;
     c->src.natom[i] = natom;
     c->planned = false;
+    return GPET_OK;
+}
+
+int gpet_set_emit_window(gpet_ctx* c, double lo_us, double hi_us, double halo_start_us) {
+    if (!c) return GPET_ERR_ARG;
+    if (!(hi_us > lo_us) || halo_start_us > lo_us) return fail(c, GPET_ERR_ARG, "emit window must satisfy halo_start <= lo < hi");
+    c->emit_on = true;
+    c->emit_lo = lo_us; c->emit_hi = hi_us;
+    // decisions about events of the window may rest on events at least one dead time / one coincidence window after the cut
+    const double reach = std::max((double)c->dig.dead_time_us, (double)c->dig.coinc_window_us);
+    c->emit_trust = std::isfinite(halo_start_us) ? halo_start_us + reach * 1.0001 + 1e-6 : -HUGE_VAL;
+    if (c->emit_trust > lo_us) return fail(c, GPET_ERR_ARG, "halo shorter than the dead time / coincidence window");
+    return GPET_OK;
+}
+
+int gpet_clear_emit_window(gpet_ctx* c) {
+    if (!c) return GPET_ERR_ARG;
+    c->emit_on = false;
+    return GPET_OK;
+}
+
+int gpet_get_emit_counts(gpet_ctx* c, uint64_t out[3]) {
+    NEED_DEVICE();
+    if (!out) return GPET_ERR_ARG;
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((r = read_counters(c))) return r;
+    out[0] = c->h_counters[10]; out[1] = c->h_counters[11]; out[2] = c->h_counters[15];
+    return GPET_OK;
+}
+
+// events between the device event buffer and caller-owned DEVICE memory (the exchange of gpet_b200/multi.py moves them
+// between GPUs with NCCL; nothing goes through the host)
+int64_t gpet_copy_events_to_device(gpet_ctx* c, void* dst_device, int64_t cap) {
+    NEED_DEVICE();
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((r = read_counters(c))) return r;
+    const int64_t n = std::min<int64_t>(std::min<unsigned>(c->h_counters[19], c->ev.capacity), cap);
+    if (n > 0) {
+        if (!dst_device) return GPET_ERR_ARG;
+        CK(cudaMemcpyAsync(dst_device, c->ev.rec, (size_t)n * sizeof(gpet_event), cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return n;
+}
+
+int gpet_put_events_device(gpet_ctx* c, const void* src_device, int64_t n) {
+    NEED_DEVICE();
+    if (n < 0 || (n > 0 && !src_device)) return GPET_ERR_ARG;
+    int r;
+    if ((r = ensure_buffers(c))) return r;
+    if ((uint64_t)n > c->cap_events) return fail(c, GPET_ERR_CAPACITY, "event list exceeds capacity");
+    c->id_base = 0;
+    new_scatter_serial(c);
+    const unsigned n32 = (unsigned)n;
+    if (n) CK(cudaMemcpyAsync(c->ev.rec, src_device, (size_t)n * sizeof(gpet_event), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->ev.count, &n32, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return GPET_OK;
 }
 
@@ -896,7 +966,6 @@ int gpet_stage_detector(gpet_ctx* c) {
     {
         const int nl = launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth, c->dig.readout_policy,
                                        c->tr.record_hits, c->hits, c->ev, c->ws.counters, c->ws.hot, c->seed, c->id_base, c->num_sms, c->stream, !c->in_run);
-        if (nl < 0) return fail(c, GPET_ERR_ARG, "hit and event counters must be adjacent words (internal layout error)");
         c->stats.kernel_launches += nl;
     }
     CK(cudaGetLastError());
@@ -939,7 +1008,6 @@ int gpet_stage_panel_transport(gpet_ctx* c) {
     {
         const int nl = launch_detector(c->q[2], detector_dev(c), tables_dev(c), c->tr.eabs_eV, c->dig.readout_depth, c->dig.readout_policy,
                                        c->tr.record_hits, c->hits, c->ev, c->ws.counters, c->ws.hot, c->seed, c->id_base, c->num_sms, c->stream, !c->in_run);
-        if (nl < 0) return fail(c, GPET_ERR_ARG, "hit and event counters must be adjacent words (internal layout error)");
         c->stats.kernel_launches += nl;
     }
     CK(cudaGetLastError());
@@ -1206,10 +1274,16 @@ int dump_psf_queue(gpet_ctx* c, const std::string& od, int which, const char* ta
     return GPET_OK;
 }
 
+std::string writer_wait_idle(void* file_writer);   // FileWriter::wait_idle (defined below)
+
 // grow a pinned arena so that `extra` more bytes fit (contents kept); in-flight copies into it must have completed
 int arena_reserve(gpet_ctx* c, PinnedArena& a, size_t extra) {
     if (a.size + extra <= a.cap) return GPET_OK;
     CK(cudaStreamSynchronize(c->copy_stream));
+    if (c->file_writer) {   // the writer thread may still read from the block that is about to move
+        const std::string e = writer_wait_idle(c->file_writer);
+        if (!e.empty()) return fail(c, GPET_ERR_IO, e);
+    }
     size_t ncap = std::max<size_t>(std::max<size_t>(a.cap * 2, a.size + extra), 1u << 20);
     char* np = nullptr;
     CK(cudaMallocHost((void**)&np, ncap));
@@ -1222,6 +1296,85 @@ int arena_reserve(gpet_ctx* c, PinnedArena& a, size_t extra) {
 
 constexpr int kRetryWithFallback = 1;   // internal: run_attempt() asks run_impl() for a second attempt
 
+// File runs append every frame's records to the reference's output files (outevents, detector.cu:387-408; gPET.cu:383,
+// 424).  The records reach pinned host memory by asynchronous copies; ONE writer thread appends them to the files in the
+// order they were queued, so that a frame's file I/O (63 bytes per pair, the slowest stage of a file run by an order of
+// magnitude) overlaps the kernels and copies of the following frames.  A job whose data is still in flight carries the
+// event that marks the end of its copy.
+struct FileWriter {
+    struct Job { std::string path; const char* p; size_t n; cudaEvent_t ready; };
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv, cv_idle;
+    std::deque<Job> q;
+    bool stop = false, busy = false, started = false;
+    int device = -1;
+    std::string err;
+    void start() {
+        if (started) return;
+        started = true;
+        th = std::thread([this] {
+            if (device >= 0) cudaSetDevice(device);   // the jobs' events live in this device's context
+            for (;;) {
+                Job j;
+                {
+                    std::unique_lock<std::mutex> lk(m);
+                    cv.wait(lk, [this] { return stop || !q.empty(); });
+                    if (q.empty()) return;
+                    j = q.front();
+                    q.pop_front();
+                    busy = true;
+                }
+                std::string e;
+                if (j.ready) {
+                    if (cudaEventSynchronize(j.ready) != cudaSuccess) e = "copy of " + j.path + " failed";
+                    cudaEventDestroy(j.ready);
+                }
+                if (e.empty() && j.n) {
+                    FILE* f = fopen(j.path.c_str(), "ab");
+                    if (!f) e = "cannot open " + j.path + " for appending";
+                    else {
+                        if (fwrite(j.p, 1, j.n, f) != j.n) e = "short write to " + j.path;
+                        fclose(f);
+                    }
+                }
+                {
+                    std::lock_guard<std::mutex> lk(m);
+                    if (!e.empty() && err.empty()) err = e;
+                    busy = false;
+                }
+                cv_idle.notify_all();
+            }
+        });
+    }
+    void push(const std::string& path, const char* p, size_t n, cudaEvent_t ready = nullptr) {
+        start();
+        {
+            std::lock_guard<std::mutex> lk(m);
+            q.push_back(Job{path, p, n, ready});
+        }
+        cv.notify_one();
+    }
+    // all queued appends are on disk (or failed: the first error is returned)
+    std::string wait_idle() {
+        if (!started) return "";
+        std::unique_lock<std::mutex> lk(m);
+        cv_idle.wait(lk, [this] { return q.empty() && !busy; });
+        return err;
+    }
+    ~FileWriter() {
+        if (!started) return;
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+        }
+        cv.notify_one();
+        th.join();
+    }
+};
+
+std::string writer_wait_idle(void* file_writer) { return static_cast<FileWriter*>(file_writer)->wait_idle(); }
+
 struct RunState {
     gpet_stats st{};
     bool resident = false;
@@ -1232,6 +1385,7 @@ struct RunState {
     // (gPET.cu:383, 424).  `dropped` = singles of the run no longer in the arena (index pairs are run-global).
     bool streaming = false;
     size_t dropped = 0;
+    FileWriter writer;
 };
 constexpr size_t kKeepBytes = 1ull << 30;
 
@@ -1315,15 +1469,15 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
             if ((r = append_device(c, join_path(rs.od, "Hits.dat"), f5, nh * 5 * sizeof(float), rs.tmp))) return r;
         }
         // adder.dat was appended by run_attempt before the digitizer ran (blur works in place; gPET.cu:383-388)
-        FILE* fs = fopen(join_path(rs.od, "singles.dat").c_str(), "ab");
-        if (!fs) return fail(c, GPET_ERR_IO, "cannot open singles.dat for appending");
-        if (ns) fwrite(dst_s, sizeof(gpet_event), ns, fs);
-        fclose(fs);
+        rs.writer.push(join_path(rs.od, "singles.dat"), dst_s, ns * sizeof(gpet_event));
         if (want_coinc) {
-            FILE* fc = fopen(join_path(rs.od, "coincidences.dat").c_str(), "ab");
-            if (!fc) return fail(c, GPET_ERR_IO, "cannot open coincidences.dat for appending");
-            if (nc && !as_pairs) fwrite(dst_c, sizeof(gpet_coincidence), nc, fc);
-            if (nc && as_pairs) {   // same file either way: gather the two singles of every pair
+            if (!as_pairs) {
+                rs.writer.push(join_path(rs.od, "coincidences.dat"), dst_c, nc * sizeof(gpet_coincidence));
+            } else {   // same file either way: gather the two singles of every pair (synchronous: an extension format, not the hot path)
+                const std::string e = rs.writer.wait_idle();
+                if (!e.empty()) return fail(c, GPET_ERR_IO, e);
+                FILE* fc = fopen(join_path(rs.od, "coincidences.dat").c_str(), "ab");
+                if (!fc) return fail(c, GPET_ERR_IO, "cannot open coincidences.dat for appending");
                 const gpet_event* sg = reinterpret_cast<const gpet_event*>(c->res_singles.p);
                 const uint32_t* pr = reinterpret_cast<const uint32_t*>(dst_c);
                 const size_t n_all = c->res_singles.size / sizeof(gpet_event);
@@ -1333,15 +1487,15 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
                     fwrite(sg + ia, sizeof(gpet_event), 1, fc);
                     fwrite(sg + ib, sizeof(gpet_event), 1, fc);
                 }
+                fclose(fc);
             }
-            fclose(fc);
             // one class byte per record of coincidences.dat (0 true, 1 scatter, 2 random)
-            FILE* fk = fopen(join_path(rs.od, "coincidences_class.dat").c_str(), "ab");
-            if (!fk) return fail(c, GPET_ERR_IO, "cannot open coincidences_class.dat for appending");
-            if (nc) fwrite(dst_k, 1, nc, fk);
-            fclose(fk);
+            rs.writer.push(join_path(rs.od, "coincidences_class.dat"), dst_k, nc);
         }
-        if (rs.streaming || c->res_singles.size + c->res_coinc.size + c->res_pairs.size + c->res_cls.size > kKeepBytes) {
+        if (rs.streaming || c->res_singles.size + c->res_coinc.size + c->res_pairs.size + c->res_cls.size + c->res_adder.size > kKeepBytes) {
+            const std::string e = rs.writer.wait_idle();   // the arenas are about to be reused
+            if (!e.empty()) return fail(c, GPET_ERR_IO, e);
+            c->res_adder.size = 0;
             rs.streaming = true;
             c->results_streamed = true;
             rs.dropped += c->res_singles.size / sizeof(gpet_event);
@@ -1486,7 +1640,11 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
     c->res_coinc.size = 0;
     c->res_pairs.size = 0;
     c->res_cls.size = 0;
+    c->res_adder.size = 0;
     c->results_streamed = false;
+    c->file_writer = &rs.writer;
+    rs.writer.device = c->device;
+    struct ClearWriter { gpet_ctx* c; ~ClearWriter() { c->file_writer = nullptr; } } clear_writer{c};
     c->coinc_expanded.clear();
     CK(cudaMemsetAsync(c->d_pair_base, 0, 2 * sizeof(unsigned), c->stream));
     struct InRun {   // gpet_stage_digitize reads these while the run is in flight
@@ -1568,8 +1726,18 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
             // adder.dat: the post-readout events as the reference writes them, BEFORE blur (gPET.cu:383-388); the digitizer
             // blurs, relabels siten and kills in place
             if ((rc = read_counters(c))) break;
-            const size_t ne = std::min<size_t>(c->h_counters[19], c->ev.capacity);
-            if ((rc = append_device(c, join_path(rs.od, "adder.dat"), c->ev.rec, ne * sizeof(gpet_event), rs.tmp))) break;
+            const size_t nb = std::min<size_t>(c->h_counters[19], c->ev.capacity) * sizeof(gpet_event);
+            if ((rc = arena_reserve(c, c->res_adder, nb))) break;
+            char* dst = c->res_adder.p + c->res_adder.size;
+            c->res_adder.size += nb;
+            if (nb) {
+                // copied on the compute stream, i.e. before the digitizer touches the records; the writer waits for the event
+                cudaEvent_t done = nullptr;
+                if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaMemcpyAsync(dst, c->ev.rec, nb, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                    cudaEventRecord(done, c->stream) != cudaSuccess) { rc = fail(c, GPET_ERR_CUDA, "adder.dat copy failed"); break; }
+                rs.writer.push(join_path(rs.od, "adder.dat"), dst, nb, done);
+            }
         }
         c->run_frame = k;
         rc = gpet_stage_digitize(c);
@@ -1582,6 +1750,10 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
         else if (k >= 2) rc = retire_frame(c, slot ^ 1, rs);
     }
     if (rc == GPET_OK && pipelined && k >= 1) rc = retire_frame(c, (int)((k - 1) & 1), rs);
+    {   // the files are complete when the run returns
+        const std::string e = rs.writer.wait_idle();
+        if (!e.empty() && rc == GPET_OK) rc = fail(c, GPET_ERR_IO, e);
+    }
     if (rc != GPET_OK) {
         cudaStreamSynchronize(c->stream);
         cudaStreamSynchronize(c->copy_stream);

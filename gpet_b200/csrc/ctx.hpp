@@ -45,6 +45,8 @@ struct gpet_ctx {
     float tstart = 0.f, tend = 1.f;
     std::vector<float> maj_ph, maj_det;
     int rank = 0, world = 1;
+    bool emit_on = false;                   // gpet_set_emit_window: digitize a time slice with its halo
+    double emit_lo = 0.0, emit_hi = 0.0, emit_trust = 0.0;
     uint64_t first_pair = 0;                // global index of the acquisition's first annihilation pair (gpet_set_first_pair)
     uint64_t id_base = 0;                   // global index of the first photon of the frame now in the queues (photon_index)
 
@@ -113,6 +115,8 @@ struct gpet_ctx {
     PinnedArena res_singles, res_coinc;   // gpet_event / gpet_coincidence records of the last gpet_run
     PinnedArena res_pairs;                // uint32 index pairs of the last gpet_run (GPET_COINC_PAIRS)
     PinnedArena res_cls;                  // class bytes of the last gpet_run's coincidences
+    PinnedArena res_adder;                // file runs: post-readout events on their way to adder.dat
+    void* file_writer = nullptr;          // the running file run's writer thread (abi.cu FileWriter), else nullptr
     std::vector<char> coinc_expanded;     // records built on demand from res_pairs + res_singles
     bool results_streamed = false;        // the last file run outgrew the arenas: its results are in the files only
     gpet_stats stats{};

@@ -99,7 +99,9 @@ struct PanelDev {  // one panel, 128 B
     float spy, spz;            // crystal gap
     int id;
     float r2;                  // (ly/2)^2 + (lz/2)^2: squared radius of the sphere around the face centre that holds the face
-    float pad[6];
+    // correctly rounded reciprocals of the four divisors of crystalSearch: 1/(mody+mspy), 1/(modz+mspz), 1/(lsoy+spy), 1/(lsoz+spz)
+    float rcp_my, rcp_mz, rcp_cy, rcp_cz;
+    float pad[2];
 };
 static_assert(sizeof(PanelDev) == 128, "PanelDev must be 128 B");
 
@@ -178,6 +180,13 @@ struct DigitizerDev {
     int npanels;
     int moduleN, crystalN;
     unsigned long long id_base;   // global index of the frame's first photon (photon_index); 0 for replayed lists
+    // Emit window (gpet_set_emit_window; multi-GPU exchange by time slice): the list holds this rank's slice [emit_lo, emit_hi)
+    // plus a halo of the neighbouring slices.  Everything is digitized as one list; singles are all written (the sorter
+    // needs the halo), counters[10] / [11] count those before / inside the window, and only coincidences whose opening
+    // single lies inside the window are emitted.  trust_lo = start of the halo + max(dead time, coincidence window): a
+    // decision for an event of the window that depends on anything earlier raises counters[15] (halo too short).
+    int emit_on;
+    double emit_lo, emit_hi, trust_lo;
     // coincidence classes (k_coinc): same annihilation iff eventid >> pair_shift agree; scatter tags as in DetectorDev
     int pair_shift;
     const unsigned char* scat_tag;

@@ -504,9 +504,11 @@ __device__ __forceinline__ bool killed_by_predecessor(const unsigned long long* 
 // as well (fp32 rounding and the fp32 sum are monotone), so it is a guaranteed anchor and the chain can be cut there:
 // one thread per such run start walks forward through the time order while the next event of its site is inside the
 // dead time of the previous one.
+__device__ __forceinline__ void counters_flag_halo(unsigned* counters) { counters[15] = 1u; }
+
 __global__ void __launch_bounds__(kThreads) k_deadtime_chain(DigitizerDev p, const unsigned long long* __restrict__ tsort,
                                                              const int* __restrict__ site_t, unsigned char* __restrict__ kill,
-                                                             const unsigned* __restrict__ counters) {
+                                                             unsigned* __restrict__ counters) {
     const unsigned n1 = counters[1];
     const float tau = p.dtime;
     for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n1; j += gridDim.x * blockDim.x) {
@@ -516,10 +518,13 @@ __global__ void __launch_bounds__(kThreads) k_deadtime_chain(DigitizerDev p, con
         kill[j] = 0;
         float tdead = (float)t;
         double until = dead_until(t, tau);   // dead time of the latest event of this site seen so far
+        // a chain that starts inside the first dead time of the list may have lost its real start to the cut of the halo
+        const bool suspect = p.emit_on && t < p.trust_lo;
         for (unsigned r = j + 1; r < n1; r++) {
             const double tr = key_time(tsort[r]);
             if (!(tr < until)) break;        // the next event of this site, if any, starts its own chain
             if (site_t[r] != site) continue;
+            if (suspect && tr >= p.emit_lo) counters_flag_halo(counters);
             if (tr < (double)__fadd_rn(tdead, tau)) {
                 kill[r] = 1;
             } else {
@@ -568,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_emit_singles(EventBuf ev, Digit
     const float tau = p.dtime;
     if (spec_smem)
         for (int b = threadIdx.x; b < nbins; b += blockDim.x) s_spec[b] = 0;
-    unsigned c2 = 0;
+    unsigned c2 = 0, n_before = 0, n_inside = 0;   // n_*: singles before / inside the emit window
 #ifdef GPET_PHASE_TRACE
     long long ph[8]; int nph = 0;
 #define PH() do { if (nph < 8) ph[nph++] = clock64(); } while (0)
@@ -689,8 +694,13 @@ __global__ void __launch_bounds__(kThreads, 3) k_emit_singles(EventBuf ev, Digit
                     span[o] = v[u].y;
                     spar[o] = v[u].x;
                 } else if (part == 1) {
-                    stime[o] = __longlong_as_double((long long)(((unsigned long long)(unsigned)v[u].w << 32) | (unsigned)v[u].z));
+                    const double ts = __longlong_as_double((long long)(((unsigned long long)(unsigned)v[u].w << 32) | (unsigned)v[u].z));
+                    stime[o] = ts;
                     seid[o] = v[u].y;
+                    if (p.emit_on) {
+                        if (ts < p.emit_lo) n_before++;
+                        else if (ts < p.emit_hi) n_inside++;
+                    }
                 } else if (spectrum && nbins > 0) {
                     const float f = (__int_as_float(v[u].x) - emin) / (emax - emin) * nbins;
                     if (f >= 0.f && f < (float)nbins) {
@@ -715,6 +725,14 @@ __global__ void __launch_bounds__(kThreads, 3) k_emit_singles(EventBuf ev, Digit
     }
     c2 = block_sum(c2);
     if (threadIdx.x == 0 && c2) atomicAdd(&counters[2], c2);
+    if (p.emit_on) {
+        __syncthreads();
+        n_before = block_sum(n_before);
+        if (threadIdx.x == 0 && n_before) atomicAdd(&counters[10], n_before);
+        __syncthreads();
+        n_inside = block_sum(n_inside);
+        if (threadIdx.x == 0 && n_inside) atomicAdd(&counters[11], n_inside);
+    }
 }
 
 // ------------------------------------------------------------------------------------------- stage 5: coincidence sorter (extension)
@@ -756,9 +774,13 @@ __device__ __forceinline__ bool pair_ok(const SinglesView& v, unsigned a, unsign
 }
 
 // coincidences opened by single a (0 when it sits inside an earlier window)
-__device__ __forceinline__ unsigned coincidences_of(const SinglesView& v, unsigned a, unsigned n, double W, const DigitizerDev& p) {
+__device__ __forceinline__ unsigned coincidences_of(const SinglesView& v, unsigned a, unsigned n, double W, const DigitizerDev& p,
+                                                    unsigned* __restrict__ counters) {
+    if (p.emit_on && !(v.t(a) >= p.emit_lo && v.t(a) < p.emit_hi)) return 0u;   // opened in a neighbour's slice: theirs
     unsigned w = a;
     while (w > 0 && !(v.t(w) >= v.t(w - 1) + W)) w--;   // nearest guaranteed opener
+    // the replay must start from a single whose own status does not depend on what the halo cut off
+    if (p.emit_on && v.t(w) < p.trust_lo) counters[15] = 1u;
     while (true) {
         const double tend = v.t(w) + W;
         unsigned m = 0;
@@ -853,7 +875,7 @@ __global__ void __launch_bounds__(kThreads) k_coinc(const EventRec* __restrict__
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const unsigned a = at + k * kThreads + threadIdx.x;
-            const unsigned c = a < n ? coincidences_of(v, a, n, W, p) : 0u;
+            const unsigned c = a < n ? coincidences_of(v, a, n, W, p, counters) : 0u;
             s_cnt[k * kThreads + threadIdx.x] = (unsigned short)min(c, 0xffffu);
         }
         __syncthreads();
@@ -960,7 +982,7 @@ __global__ void k_publish_counters(const unsigned* __restrict__ counters, const 
     pdl_wait();
     const unsigned i = threadIdx.x;
     if (i < 32) h_dst[i] = counters[i];
-    else if (i < 40) h_dst[i] = hot[((i - 32) >> 1) * kHotStride + ((i - 32) & 1)];
+    else if (i < 32 + 2 * kHotLines) h_dst[i] = hot[((i - 32) >> 1) * kHotStride + ((i - 32) & 1)];
 }
 
 int launch_publish_counters(const unsigned* counters, const unsigned* hot, unsigned* h_dst, cudaStream_t s) {
@@ -1020,7 +1042,7 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
                                                // never run in the same frame)
     if (reset) {   // the digitizer's share of the frame state: counters[0..7], then everything behind the counter block
         cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned), s);
-        cudaMemsetAsync(ws.counters + 12, 0, 3 * sizeof(unsigned), s);   // coincidence class tallies
+        cudaMemsetAsync(ws.counters + 10, 0, 6 * sizeof(unsigned), s);   // emit-window counts, coincidence class tallies, halo flag
         cudaMemsetAsync(ws.counters + 64, 0, (size_t)(ws.hot - (ws.counters + 64)) * sizeof(unsigned), s);   // not the hot block: it holds the event count
     }
     TimeRange tr;

@@ -77,8 +77,10 @@ enum HotWord : unsigned {
     kHotTicketFront = 0 * kHotStride,  // k_front's pair / photon ticket
     kHotQ2 = 1 * kHotStride,           // photons on a panel (queue 2 count)
     kHotTicketDet = 2 * kHotStride,    // k_detector's photon ticket
-    kHotHitsEvents = 3 * kHotStride,   // hits count, events count: adjacent words, reserved together by one 64-bit atomic
-    kHotWords = 4 * kHotStride
+    kHotHits = 3 * kHotStride,         // hits count
+    kHotEvents = 4 * kHotStride,       // post-readout events count (a line of its own: both are bumped by every warp's flushes)
+    kHotLines = 5,
+    kHotWords = 5 * kHotStride
 };
 
 size_t sort_state_bytes();
@@ -95,7 +97,7 @@ unsigned bucket_words();                       // slice counters of the bucket s
 int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p, DigitizerWorkspace& ws, const TimeRange* range,
                     uint64_t seed, int num_sms, cudaStream_t s, bool reset, bool with_fallback);
 
-// the frame's counter block (32 words) and hot counters (4 x 2 words) to pinned host memory by zero-copy stores
+// the frame's counter block (32 words) and hot counters (kHotLines x 2 words) to pinned host memory by zero-copy stores
 int launch_publish_counters(const unsigned* counters, const unsigned* hot, unsigned* h_dst, cudaStream_t s);
 // addnoise: events of the noise process with t_lo <= t < t_hi appended to ev (digitizer.cu)
 int launch_noise(EventBuf ev, const DigitizerDev& p, double t_lo_us, double t_hi_us, uint64_t seed, int num_sms, cudaStream_t s);
@@ -116,7 +118,6 @@ int launch_panel_entry(PhotonQueue q1, PhotonQueue q2, DetectorDev det, unsigned
 int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQueue q0, PhotonQueue q1, PhotonQueue q2,
                  PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, unsigned int* counters, unsigned int* hot, uint64_t seed,
                  unsigned long long id_base, int num_sms, cudaStream_t s, bool reset);
-// hits.count and ev.count must be adjacent words (hits first, 8-byte aligned): one 64-bit atomic reserves both
 int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
                     int record_hits, HitBuffer hits, EventBuf ev, unsigned int* counters, unsigned int* hot, uint64_t seed,
                     unsigned long long id_base, int num_sms, cudaStream_t s, bool reset);

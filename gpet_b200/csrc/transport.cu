@@ -759,18 +759,72 @@ struct SlotsSmem {
     double t[kSlots][kDetThreads];
 };
 
-// D1 adder (gPET_kernals.cu:737-755): merge hits of the same crystal; energy-weighted centroid with the
-// contraction spelled out: (x_i*E_i + x*E)/(E_i+E) = fma(x_i, E_i, x*E) / (E_i + E)
-template <class S>
-__device__ __forceinline__ bool adder(S& sl, int col, int& n, int key, float E, float x, float y, float z, double t) {
+__device__ __forceinline__ int event_siten(int depth, int panel_id, int modn, int cryn, const DetectorDev& det) {
+    return depth == 0 ? 0 : depth == 1 ? panel_id : depth == 2 ? panel_id * det.moduleN + modn
+                                                             : (panel_id * det.moduleN + modn) * det.crystalN + cryn;
+}
+
+constexpr unsigned kDetChunk = 32;   // photons a warp claims from the queue with one ticket atomic
+
+// ---- k_detector -----------------------------------------------------------------------------------------------------
+// Photon transport inside a panel (photonde, gPET_kernals.cu:1018-1192, with comsam :90-126, adder / readout :737-813) over
+// the compact panel-entry queue.  Persistent warps with lane refill, one lane = one photon from entry to readout.  Against
+// round 1's kernel ("v1" below; ncu: 12.3 of 32 lanes per instruction) the divergent parts run differently:
+//
+//  * Klein-Nishina rejection sampling by the WHOLE warp.  In v1 the 2-6 lanes whose flight ended in a Compton scatter ran
+//    the rejection loop nested in the flight loop -- a Philox block and the acceptance test per round, as many rounds as
+//    the unluckiest of them needed -- while the other lanes waited (19 % of the kernel's warp instructions at 4 lanes).
+//    Here the warp evaluates floor(32 / nC) consecutive rounds of each of the nC scattering photons AT ONCE, lane
+//    L = (photon L mod nC, round L div nC), every lane one Philox block and one acceptance test; each photon then takes
+//    its first accepted round.  Round k of a photon uses the Philox block it would have used sequentially (block counter
+//    + k) and the counter advances past the accepted round only, so the draws, and therefore the results, are those of the
+//    sequential loop bit for bit; the blocks of later rounds are simply never used.  One pass settles all photons in
+//    > 99 % of the cases (acceptance is ~2/3 per round); the pass repeats for the rest.
+//  * The three IEEE divides of an adder / readout centroid share one correctly rounded reciprocal (div3_rn below).
+//  * crystal_search divides by four constants of the panel: their reciprocals come with the panel record (div_rcp).
+//  * Hits and events are staged per warp in shared memory and leave 32 at a time: one atomic per flush instead of one per
+//    loop iteration (the reservation's round trip was 7 % of v1's stall samples), hit rows as full-line vector stores into
+//    the SoA hit buffer, events as 1.5 KB of consecutive 16-byte stores.
+//
+// A measured dead end, for the record (profiles/r02a_*): making the rejection rounds loop iterations of their own (a lane
+// state "KN" next to "FLY", both sharing the iteration's Philox block) and pooling readout over spare adder columns took
+// the kernel from 130 to 170 us: the scattering lanes no longer fly, the flight body -- the most expensive piece -- ran
+// with 15 instead of 24 lanes, and every per-iteration cost was paid 1.5 times as often.
+
+// a / b, b > 0 normal, with rcp = the correctly rounded 1 / b: one multiply and two FMAs give the correctly rounded quotient
+// (Markstein's correction: q = RN(a * rcp), r = a - b q exactly, RN(q + r * rcp)).  Checked against IEEE division on
+// 2e7 random operands of the magnitudes that occur here (tests/test_oracle_units.py) -- and the parity tests compare the
+// events of this kernel with the oracle's plain divisions.
+__device__ __forceinline__ float div_rcp(float a, float b, float rcp) {
+    const float q = __fmul_rn(a, rcp);
+    return __fmaf_rn(__fmaf_rn(-b, q, a), rcp, q);
+}
+
+// energy-weighted centroid of two deposits, as the reference forms it: fma(x_i, E_i, x E) / (E_i + E)
+struct Centroid { float x, y, z, E; };
+__device__ __forceinline__ Centroid merge_centroid(float xi, float yi, float zi, float Ei, float x, float y, float z, float E) {
+    Centroid c;
+    c.E = __fadd_rn(Ei, E);
+    const float rcp = __frcp_rn(c.E);
+    // energies are 1e3 .. 2e6 eV and coordinates a few cm: far inside the range where the correction is exact; anything
+    // else (a zero or non-finite sum) takes the plain divide
+    if (c.E > 1.0f && c.E < 1.0e30f) {
+        c.x = div_rcp(__fmaf_rn(xi, Ei, __fmul_rn(x, E)), c.E, rcp);
+        c.y = div_rcp(__fmaf_rn(yi, Ei, __fmul_rn(y, E)), c.E, rcp);
+        c.z = div_rcp(__fmaf_rn(zi, Ei, __fmul_rn(z, E)), c.E, rcp);
+    } else {
+        c.x = __fdiv_rn(__fmaf_rn(xi, Ei, __fmul_rn(x, E)), c.E);
+        c.y = __fdiv_rn(__fmaf_rn(yi, Ei, __fmul_rn(y, E)), c.E);
+        c.z = __fdiv_rn(__fmaf_rn(zi, Ei, __fmul_rn(z, E)), c.E);
+    }
+    return c;
+}
+
+__device__ __forceinline__ bool adder_fast(SlotsSmem& sl, int col, int& n, int key, float E, float x, float y, float z, double t) {
     for (int k = 0; k < n; k++) {
         if (sl.key[k][col] == key) {
-            const float ek = sl.E[k][col];
-            const float es = __fadd_rn(ek, E);
-            sl.x[k][col] = __fdiv_rn(__fmaf_rn(sl.x[k][col], ek, __fmul_rn(x, E)), es);
-            sl.y[k][col] = __fdiv_rn(__fmaf_rn(sl.y[k][col], ek, __fmul_rn(y, E)), es);
-            sl.z[k][col] = __fdiv_rn(__fmaf_rn(sl.z[k][col], ek, __fmul_rn(z, E)), es);
-            sl.E[k][col] = es;
+            const Centroid c = merge_centroid(sl.x[k][col], sl.y[k][col], sl.z[k][col], sl.E[k][col], x, y, z, E);
+            sl.x[k][col] = c.x; sl.y[k][col] = c.y; sl.z[k][col] = c.z; sl.E[k][col] = c.E;
             return true;
         }
     }
@@ -780,13 +834,8 @@ __device__ __forceinline__ bool adder(S& sl, int col, int& n, int key, float E, 
     return true;
 }
 
-// D2 readout (gPET_kernals.cu:756-813) of one finished photon: merges the slots whose key agrees at the readout level
-// (depth 0/1: the whole panel, 2: module, else crystal); returns the bit mask of the slots merged away.
-template <class S>
-__device__ __forceinline__ unsigned readout_merge(S& sl, int col, int nslot, int depth, int rpolicy) {
+__device__ __forceinline__ unsigned readout_merge_fast(SlotsSmem& sl, int col, int nslot, int depth, int rpolicy) {
     unsigned deadmask = 0;
-    // rolled loops on purpose: unrolled 6 x 6 this function was 24 KB of SASS -- half the kernel -- pushing the hot loop
-    // out of the 32 KB instruction cache
 #pragma unroll 1
     for (int i = 0; i < nslot - 1; i++) {
         if (deadmask >> i & 1u) continue;
@@ -799,13 +848,9 @@ __device__ __forceinline__ unsigned readout_merge(S& sl, int col, int nslot, int
             if (!same) continue;
             const float Ei = sl.E[i][col], Ej = sl.E[j][col];
             if (rpolicy == 1) {
-                const float es = __fadd_rn(Ei, Ej);
-                sl.x[i][col] = __fdiv_rn(__fmaf_rn(sl.x[i][col], Ei, __fmul_rn(sl.x[j][col], Ej)), es);
-                sl.y[i][col] = __fdiv_rn(__fmaf_rn(sl.y[i][col], Ei, __fmul_rn(sl.y[j][col], Ej)), es);
-                sl.z[i][col] = __fdiv_rn(__fmaf_rn(sl.z[i][col], Ei, __fmul_rn(sl.z[j][col], Ej)), es);
-                sl.E[i][col] = es;
+                const Centroid c = merge_centroid(sl.x[i][col], sl.y[i][col], sl.z[i][col], Ei, sl.x[j][col], sl.y[j][col], sl.z[j][col], Ej);
+                sl.x[i][col] = c.x; sl.y[i][col] = c.y; sl.z[i][col] = c.z; sl.E[i][col] = c.E;
             } else if (!(Ei > Ej)) {
-                // winner-take-all: the larger energy wins the whole record (ties -> the later one)
                 sl.key[i][col] = kj; sl.E[i][col] = Ej; sl.x[i][col] = sl.x[j][col];
                 sl.y[i][col] = sl.y[j][col]; sl.z[i][col] = sl.z[j][col]; sl.t[i][col] = sl.t[j][col];
             }
@@ -815,332 +860,110 @@ __device__ __forceinline__ unsigned readout_merge(S& sl, int col, int nslot, int
     return deadmask;
 }
 
-__device__ __forceinline__ int event_siten(int depth, int panel_id, int modn, int cryn, const DetectorDev& det) {
-    return depth == 0 ? 0 : depth == 1 ? panel_id : depth == 2 ? panel_id * det.moduleN + modn
-                                                             : (panel_id * det.moduleN + modn) * det.crystalN + cryn;
+// crystalSearch (gPET_kernals.cu:1236-1279) with the panel's four divisors replaced by their reciprocals (PanelDev::rcp*)
+__device__ __forceinline__ void crystal_search_rcp(const PanelDev& pd, const DetectorDev& det, float px, float py, float pz,
+                                                   int& m_id, int& M_id, int& L_id) {
+    m_id = 1; M_id = -1; L_id = -1;
+    for (int k = 0; k < det.nsurface; k++) {
+        const float* c = det.surface + 10 * k;
+        float q = c[0] * px * px + c[1] * py * py + c[2] * pz * pz + c[3] * px * py + c[4] * px * pz + c[5] * py * pz +
+                  c[6] * px + c[7] * py + c[8] * pz + c[9];
+        if (q < 0.f) return;
+    }
+    float y = pd.ly / 2 + py, z = pd.lz / 2 + pz;
+    const float dmy = pd.mody + pd.mspy, dmz = pd.modz + pd.mspz;
+    float my = div_rcp(y, dmy, pd.rcp_my), mz = div_rcp(z, dmz, pd.rcp_mz);
+    int My = floorf(my) > 0.f ? (int)my : 0, Mz = floorf(mz) > 0.f ? (int)mz : 0;
+    M_id = Mz * det.moduleNy + My;
+    y = y - My * dmy;
+    z = z - Mz * dmz;
+    if (y > pd.mody || z > pd.modz) return;
+    const float dcy = pd.lsoy + pd.spy, dcz = pd.lsoz + pd.spz;
+    float cy = div_rcp(y, dcy, pd.rcp_cy), cz = div_rcp(z, dcz, pd.rcp_cz);
+    int Ly = floorf(cy) > 0.f ? (int)cy : 0, Lz = floorf(cz) > 0.f ? (int)cz : 0;
+    L_id = Lz * det.crystalNy + Ly;
+    y = y - Ly * dcy;
+    z = z - Lz * dcz;
+    if (y > pd.lsoy || z > pd.lsoz) return;
+    m_id = 0;
 }
 
-constexpr unsigned kDetChunk = 32;   // photons a warp claims from the queue with one ticket atomic
+// per-warp staging of the rows that leave the SM: 32 hits (SoA pieces) and 32 events (48-byte records)
+struct WarpStage {
+    int4 hid[32];            // hits: parn, pann, modn, cryn
+    float4 hf[32];           // E, x, y, z
+    double ht[32];
+    int4 ev[32 * 3];         // events: record k = pieces 3k .. 3k+2
+    int htype[32];
+    int kn_src[32];          // lane of the j-th scattering photon (cooperative Klein-Nishina pass)
+};
 
-// ---- k_detector_v1: round 1's kernel, kept selectable (GPET_DET_V=1) as the A/B partner of the kernel below --------
-// One lane = one photon from entry to readout; the Klein-Nishina rejection loop, the adder / readout merges and the event
-// emission run nested inside the flight loop with whatever lanes need them (12 of 32 lanes per instruction).
-__global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector_v1(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs,
-                                                          int rdepth, int rpolicy, int record_hits, HitBuffer hits, EventBuf ev,
-                                                          unsigned* __restrict__ counters, unsigned* __restrict__ ticket, uint64_t seed,
-                                                          int refill_min, unsigned long long id_base) {
+constexpr int kKnMaxRounds = 8;   // rounds of one photon evaluated side by side at most (acceptance ~2/3: 8 rounds fail 2e-4 of the time)
+
+// lane -> (photon j = lane mod nC, round k = lane div nC) and the lanes that hold the rounds of photon 0 (bits 0, nC, 2 nC, ...
+// for the R = min(32 / nC, kKnMaxRounds) rounds of a pass), by nC = 1..32: tables instead of two integer divisions and a loop
+struct KnTables {
+    unsigned char jk[33][32];   // j | k << 5
+    unsigned rounds[33];        // stride mask
+};
+__device__ KnTables c_kn;   // read through the L1 (lanes read 32 consecutive bytes: one sector; a __constant__ table would serialise them)
+
+__global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs,
+                                                       int rdepth, int rpolicy, int record_hits, HitBuffer hits, EventBuf ev,
+                                                       unsigned* __restrict__ counters, unsigned* __restrict__ ticket, uint64_t seed,
+                                                       int refill_min, unsigned long long id_base) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     SlotsSmem& sl = *reinterpret_cast<SlotsSmem*>(s_raw);
-    PanelDev* s_panels = reinterpret_cast<PanelDev*>(s_raw + sizeof(SlotsSmem));
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    WarpStage& ws = reinterpret_cast<WarpStage*>(s_raw + sizeof(SlotsSmem))[warp];
+    PanelDev* s_panels = reinterpret_cast<PanelDev*>(s_raw + sizeof(SlotsSmem) + sizeof(WarpStage) * (kDetThreads / 32));
     stage_panels(s_panels, det);
+    // programmatic dependent launch: everything above overlapped the tail of the front-end kernel; its queue is read below
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int tid = threadIdx.x;
-    const unsigned lane = lane_id();
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned n = min(*q2.count, q2.capacity);
-    unsigned long long* __restrict__ hits_events = reinterpret_cast<unsigned long long*>(hits.count);
     const int depth = (rdepth != 3 && rpolicy == 1) ? 2 : rdepth;
     bool active = false, exhausted = false;
-    unsigned chunk_pos = 0, chunk_end = 0;
-    unsigned seen = 0;
+    unsigned chunk_pos = 0, chunk_end = 0;   // the warp's claimed share of the queue (warp-uniform)
+    unsigned seen = 0;                       // ticket value after this warp's last claim
+    unsigned hstaged = 0, estaged = 0;       // warp-uniform: staged hits, staged events
     const unsigned nwarps = gridDim.x * (kDetThreads / 32);
     float x = 0, y = 0, z = 0, E = 0, vx = 0, vy = 0, vz = 0;
     double t = 0;
     int eid = 0, parn = 0, pa = 0, nslot = 0;
     unsigned n_drop_adder = 0;
     Philox rng(seed, 0, 0);
-    while (true) {
-        unsigned amask = __ballot_sync(kFull, active);
-        if (!exhausted && (__popc(~amask) >= refill_min || amask == 0)) {
-            if (chunk_pos == chunk_end) {
-                const unsigned left = n > seen ? n - seen : 0u;
-                const unsigned want = max(2u, min(kDetChunk, left / (2u * nwarps)));
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(ticket, want);
-                base = __shfl_sync(kFull, base, 0);
-                seen = base + want;
-                chunk_pos = min(base, n);
-                chunk_end = min(base + want, n);
-                if (base >= n) exhausted = true;
-            }
-            const unsigned need = ~amask;
-            const unsigned avail = chunk_end - chunk_pos;
-            const unsigned rank = __popc(need & lt_mask);
-            if (!active && rank < avail) {
-                const unsigned idx = chunk_pos + rank;
-                const float4 pe = __ldcs(q2.pos_e + idx);
-                const float4 dn = __ldcs(q2.dir_n + idx);
-                t = __ldcs(q2.t + idx);
-                const int2 id = __ldcs(q2.ids + idx);
-                x = pe.x; y = pe.y; z = pe.z; E = pe.w;
-                vx = dn.x; vy = dn.y; vz = dn.z; pa = __float_as_int(dn.w);
-                eid = id.x; parn = id.y;
-                rng = Philox(seed, photon_index(parn, id_base), (uint32_t)kStageDetector << 24);
-                nslot = 0;
-                active = true;
-            }
-            chunk_pos += min((unsigned)__popc(need), avail);
-            amask = __ballot_sync(kFull, active);
-        }
-        if (amask == 0) {
-            if (exhausted) break;
-            continue;
-        }
-        int nh = 0, h_key = 0, h_type0 = 0;
-        float h_E0 = 0.f, h_E1 = 0.f;
-        bool finished = false;
-        if (active) {
-            const PanelDev& pd = s_panels[pa];
-            uint4 r = rng.next();
-            int ie; float fe;
-            energy_index(tb, E, ie, fe);
-            float lammin = __fdividef(1.0f, lerp_table(tb.maj_detector, ie, fe));
-            float s = -lammin * __logf(u01(r.x));
-            x = fmaf(s, vx, x); y = fmaf(s, vy, y); z = fmaf(s, vz, z);
-            t += (double)s * kInvSpeedOfLight;
-            if (fabsf(y) > pd.ly * 0.5f || fabsf(z) > pd.lz * 0.5f || x * pd.dirx < 0.f || x * pd.dirx > pd.lx) {
-                finished = true;
-            } else {
-                int m_id, M_id, L_id;
-                crystal_search(pd, det, x, y, z, m_id, M_id, L_id);
-                float rho = det.dens[m_id];
-                int mat = det.mat[m_id];
-                Xs3 xs = lerp_xs(tb, mat, ie, fe);
-                float lamden = lammin * rho;
-                float prob = fmaxf(1.0f - lamden * xs.tot, 0.f);
-                float u = u01(r.y);
-                bool turn = false;
-                float costh = 1.f, phi = 0.f;
-                if (u >= prob) {
-                    prob += lamden * xs.compt;
-                    if (u < prob) {
-                        float efrac;
-                        compton_kn(E, rng, efrac, costh);
-                        float de = E * (1.0f - efrac);
-                        phi = kTwoPi * u01(r.z);
-                        if (m_id == 0) { h_type0 = 1; h_E0 = de; nh = 1; }
-                        E -= de;
-                        if (E < eabs) {
-                            if (m_id == 0) { h_E1 = E; nh = 2; }
-                            finished = true;
-                        } else {
-                            turn = true;
-                        }
-                    } else {
-                        prob += lamden * xs.rayl;
-                        if (u < prob) {
-                            costh = surface_lookup(tb.rayff, mat, tb.rl_ncp, tb.rl_ne, E * tb.rl_ide, u01(r.z) * tb.rl_idcp);
-                            phi = kTwoPi * u01(r.w);
-                            turn = true;
-                        } else {
-                            if (m_id == 0) { h_type0 = 4; h_E0 = E; nh = 1; }
-                            finished = true;
-                        }
-                    }
-                }
-                if (turn) rotate_dir(vx, vy, vz, costh, phi);
-                h_key = (M_id << 16) | (L_id & 0xffff);
-            }
-            if (nh >= 1) {
-                if (!adder(sl, tid, nslot, h_key, h_E0, x, y, z, t)) n_drop_adder++;
-                if (nh == 2 && !adder(sl, tid, nslot, h_key, h_E1, x, y, z, t)) n_drop_adder++;
-            }
-        }
-        if (finished) active = false;
-        const bool mine = finished && nslot > 0;
-        unsigned deadmask = 0;
-        if (mine && nslot > 1 && rdepth != 3) deadmask = readout_merge(sl, tid, nslot, depth, rpolicy);
-        const unsigned ne = mine ? (unsigned)(nslot - __popc(deadmask)) : 0u;
-        const unsigned nhits = record_hits ? (unsigned)nh : 0u;
-        const unsigned packed = nhits | (ne << 16);
-        if (__ballot_sync(kFull, packed != 0u)) {
-            unsigned incl = packed;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned yv = __shfl_up_sync(kFull, incl, o);
-                if (lane >= (unsigned)o) incl += yv;
-            }
-            const unsigned total = __shfl_sync(kFull, incl, 31);
-            unsigned long long base = 0;
-            if (lane == 31) base = atomicAdd(hits_events, (unsigned long long)(total & 0xffffu) | ((unsigned long long)(total >> 16) << 32));
-            base = __shfl_sync(kFull, base, 31);
-            const unsigned excl = incl - packed;
-            unsigned hslot = (unsigned)(base & 0xffffffffull) + (excl & 0xffffu);
-            unsigned eslot = (unsigned)(base >> 32) + (excl >> 16);
-            if (nhits > 0) {
-                const int panel_id = s_panels[pa].id;
-                for (unsigned k = 0; k < nhits; k++) {
-                    if (hslot + k < hits.capacity) {
-                        hits.id4[hslot + k] = make_int4(parn, panel_id, h_key >> 16, h_key & 0xffff);
-                        hits.f4[hslot + k] = make_float4(k ? h_E1 : h_E0, x, y, z);
-                        hits.t[hslot + k] = t;
-                        hits.type[hslot + k] = k ? 2 : h_type0;
-                    }
-                }
-            }
-            if (mine) {
-                const int panel_id = s_panels[pa].id;
-#pragma unroll 1
-                for (int k = 0; k < nslot; k++) {
-                    if (deadmask >> k & 1u) continue;
-                    if (eslot < ev.capacity) {
-                        const int key = sl.key[k][tid];
-                        EventRec r;
-                        r.parn = parn; r.pann = panel_id; r.modn = key >> 16; r.cryn = key & 0xffff;
-                        r.siten = event_siten(depth, panel_id, r.modn, r.cryn, det);
-                        r.eventid = eid;
-                        r.t = sl.t[k][tid]; r.E = sl.E[k][tid];
-                        r.x = sl.x[k][tid]; r.y = sl.y[k][tid]; r.z = sl.z[k][tid];
-                        store_event_rec(ev.rec + eslot, r);
-                    }
-                    eslot++;
-                }
-            }
-        }
-        if (mine) nslot = 0;
-    }
-    unsigned b = n_drop_adder;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(kFull, b, o);
-    if (lane == 0 && b) atomicAdd(&counters[9], b);
-}
 
-// ---- k_detector -----------------------------------------------------------------------------------------------------
-// Photon transport inside a panel (photonde, gPET_kernals.cu:1018-1192, with comsam :90-126, adder / readout :737-813) over
-// the compact panel-entry queue.  Persistent warps with lane refill as before; what changed against k_detector_v1 is
-// WHERE the divergent work runs (ncu of v1: 12.3 of 32 lanes per instruction, 49 % of the warp instructions with < 8):
-//
-//  * Interaction-type regrouping inside the warp.  A lane is in one of two states: FLY (next step = one Woodcock flight)
-//    or KN (its photon Compton-scattered; next step = one rejection round of the Klein-Nishina sampler).  Both steps start
-//    with one Philox block, drawn by all lanes together; then the FLY lanes do their flight and the KN lanes their round,
-//    and the lanes whose interaction is decided (Compton accepted, Rayleigh, photo-absorption) meet again in ONE copy of
-//    the rotation and of the adder.  In v1 the rejection loop ran nested inside the flight with the 2-5 lanes that had just
-//    scattered, Philox included; here rejected lanes pool with the lanes that scatter on the following flights.  The draws
-//    of a photon are the same blocks in the same order (flight, rounds, flight, ...), so results are unchanged.
-//  * Readout and event emission pooled across photons.  A warp owns 32 + kSpare adder columns.  A photon that finishes
-//    with deposits leaves its column behind (header: photon, event, panel, slot count) and its lane takes a spare one
-//    and goes on with the next photon; when the spares run out the warp reads out all pending columns at once, one lane
-//    per finished photon (readout merges with their IEEE divides, event records as 16-byte vector stores), with one
-//    atomic for the lot.  v1 did this per photon as it finished: 2-3 lanes on the merges, 5 on the emission.
-//  * Hits staged per warp in shared memory and flushed 32 at a time: one atomic per flush instead of one per loop
-//    iteration, and the rows leave as full-line vector stores into the SoA hit buffer (v1: 30 scalar STG.32 per hit pair).
-template <int NC>
-struct WarpPool {
-    int4 hid[32];            // staged hits: parn, pann, modn, cryn
-    float4 hf[32];           // E, x, y, z
-    double ht[32];
-    double t[kSlots][NC];    // adder columns, [slot][column]
-    int key[kSlots][NC];
-    float E[kSlots][NC], x[kSlots][NC], y[kSlots][NC], z[kSlots][NC];
-    int h_parn[NC], h_eid[NC], h_pan_ns[NC];   // header of a pending column: photon, event, panel index | slots << 8
-    int htype[32];
-    unsigned char free_col[NC], pend_col[NC];  // stack of free columns, list of pending ones
-};
-
-template <int NC, int BPS>
-__global__ void __launch_bounds__(kDetThreads, BPS) k_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs,
-                                                              int rdepth, int rpolicy, int record_hits, HitBuffer hits, EventBuf ev,
-                                                              unsigned* __restrict__ counters, unsigned* __restrict__ ticket, uint64_t seed,
-                                                              int refill_min, unsigned long long id_base) {
-    static_assert(NC > 32 && NC <= 64 && sizeof(WarpPool<NC>) % 16 == 0, "column pool shape");
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    WarpPool<NC>& wp = reinterpret_cast<WarpPool<NC>*>(s_raw)[warp];
-    PanelDev* s_panels = reinterpret_cast<PanelDev*>(s_raw + sizeof(WarpPool<NC>) * (kDetThreads / 32));
-    for (unsigned i = lane; i < (unsigned)(NC - 32); i += 32) wp.free_col[i] = (unsigned char)(32 + i);
-    stage_panels(s_panels, det);
-    // programmatic dependent launch: everything above overlapped the tail of the front-end kernel; its queue is read below
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const unsigned n = min(*q2.count, q2.capacity);
-    const int depth = (rdepth != 3 && rpolicy == 1) ? 2 : rdepth;
-    bool active = false, exhausted = false, kn = false;
-    unsigned chunk_pos = 0, chunk_end = 0;   // the warp's claimed share of the queue (warp-uniform)
-    unsigned seen = 0;                       // ticket value after this warp's last claim
-    unsigned nfree = NC - 32, npend = 0, hstaged = 0;   // warp-uniform: free columns, pending columns, staged hits
-    const unsigned nwarps = gridDim.x * (kDetThreads / 32);
-    float x = 0, y = 0, z = 0, E = 0, vx = 0, vy = 0, vz = 0, kn_phi = 0;
-    double t = 0;
-    int eid = 0, parn = 0, pa = 0, nslot = 0, col = (int)lane, h_key = 0, mid = 0;
-    unsigned n_drop_adder = 0;
-    Philox rng(seed, 0, 0);
-
-    // all pending columns -> events: one lane per finished photon
-    auto drain = [&]() {
-        __syncwarp();
-        unsigned ne = 0, deadmask = 0;
-        int c = 0, hp = 0, nsl = 0;
-        if (lane < npend) {
-            c = wp.pend_col[lane];
-            hp = wp.h_pan_ns[c];
-            nsl = hp >> 8;
-            if (nsl > 1 && rdepth != 3) deadmask = readout_merge(wp, c, nsl, depth, rpolicy);
-            ne = (unsigned)(nsl - __popc(deadmask));
-        }
-        unsigned incl = ne;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned yv = __shfl_up_sync(kFull, incl, o);
-            if (lane >= (unsigned)o) incl += yv;
-        }
-        const unsigned total = __shfl_sync(kFull, incl, 31);
-        unsigned base = 0;
-        if (lane == 31 && total) base = atomicAdd(ev.count, total);
-        base = __shfl_sync(kFull, base, 31);
-        unsigned eslot = base + incl - ne;
-        if (lane < npend) {
-            const int panel_id = s_panels[hp & 0xff].id, pn = wp.h_parn[c], ei = wp.h_eid[c];
-#pragma unroll 1
-            for (int k = 0; k < nsl; k++) {
-                if (deadmask >> k & 1u) continue;
-                if (eslot < ev.capacity) {
-                    const int key = wp.key[k][c];
-                    EventRec r;
-                    r.parn = pn; r.pann = panel_id; r.modn = key >> 16; r.cryn = key & 0xffff;
-                    r.siten = event_siten(depth, panel_id, r.modn, r.cryn, det);
-                    r.eventid = ei;
-                    r.t = wp.t[k][c]; r.E = wp.E[k][c];
-                    r.x = wp.x[k][c]; r.y = wp.y[k][c]; r.z = wp.z[k][c];
-                    store_event_rec(ev.rec + eslot, r);
-                }
-                eslot++;
-            }
-            wp.free_col[nfree + lane] = (unsigned char)c;
-        }
-        nfree += npend;
-        npend = 0;
-        __syncwarp();
-    };
-    // staged hits -> the SoA hit buffer: consecutive rows in consecutive lanes
     auto flush_hits = [&]() {
         __syncwarp();
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(hits.count, hstaged);
         base = __shfl_sync(kFull, base, 0);
         if (lane < hstaged && base + lane < hits.capacity) {
-            hits.id4[base + lane] = wp.hid[lane];
-            hits.f4[base + lane] = wp.hf[lane];
-            hits.t[base + lane] = wp.ht[lane];
-            hits.type[base + lane] = wp.htype[lane];
+            hits.id4[base + lane] = ws.hid[lane];
+            hits.f4[base + lane] = ws.hf[lane];
+            hits.t[base + lane] = ws.ht[lane];
+            hits.type[base + lane] = ws.htype[lane];
         }
         hstaged = 0;
         __syncwarp();
     };
-    auto stage_hit = [&](bool has, int type, float Eh) {
-        const unsigned m = __ballot_sync(kFull, has);
-        if (m == 0u) return;
-        const unsigned cnt = __popc(m);
-        if (hstaged + cnt > 32u) flush_hits();
-        if (has) {
-            const unsigned p = hstaged + __popc(m & lt_mask);
-            wp.hid[p] = make_int4(parn, s_panels[pa].id, h_key >> 16, h_key & 0xffff);
-            wp.hf[p] = make_float4(Eh, x, y, z);
-            wp.ht[p] = t;
-            wp.htype[p] = type;
+    auto flush_events = [&]() {
+        __syncwarp();
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(ev.count, estaged);
+        base = __shfl_sync(kFull, base, 0);
+        const unsigned room = base < ev.capacity ? min(estaged, ev.capacity - base) : 0u;
+        int4* dst = reinterpret_cast<int4*>(ev.rec + base);
+#pragma unroll
+        for (unsigned p = 0; p < 3; p++) {
+            const unsigned piece = p * 32u + lane;
+            if (piece < 3u * room) dst[piece] = ws.ev[piece];
         }
-        hstaged += cnt;
+        estaged = 0;
+        __syncwarp();
     };
 
     while (true) {
@@ -1174,7 +997,6 @@ __global__ void __launch_bounds__(kDetThreads, BPS) k_detector(PhotonQueue q2, D
                 eid = id.x; parn = id.y;
                 rng = Philox(seed, photon_index(parn, id_base), (uint32_t)kStageDetector << 24);
                 nslot = 0;
-                kn = false;
                 active = true;
             }
             chunk_pos += min((unsigned)__popc(need), avail);
@@ -1184,17 +1006,15 @@ __global__ void __launch_bounds__(kDetThreads, BPS) k_detector(PhotonQueue q2, D
             if (exhausted) break;
             continue;
         }
-        // ---- one step per active lane.  Up to two hits per step (Compton deposit + absorption of the remainder), both at
-        // the lane's position
-        int nh = 0, h_type0 = 0;
+        // ---- one Woodcock flight per active lane (gPET_kernals.cu:1018-1050) and the choice of the interaction.  Up to two
+        // hits per flight (Compton deposit + absorption of the remainder), both at the same point
+        int nh = 0, h_key = 0, h_type0 = 0, mid = 1;
         float h_E0 = 0.f, h_E1 = 0.f;
-        bool finished = false, turn = false;
+        bool finished = false, turn = false, compton = false;
         float costh = 1.f, phi = 0.f;
-        uint4 r = make_uint4(0u, 0u, 0u, 0u);
-        if (active) r = rng.next();
-        if (active && !kn) {
-            // FLY: one Woodcock flight (gPET_kernals.cu:1018-1050) and the choice of the interaction
+        if (active) {
             const PanelDev& pd = s_panels[pa];
+            uint4 r = rng.next();
             int ie; float fe;
             energy_index(tb, E, ie, fe);
             float lammin = __fdividef(1.0f, lerp_table(tb.maj_detector, ie, fe));
@@ -1205,7 +1025,7 @@ __global__ void __launch_bounds__(kDetThreads, BPS) k_detector(PhotonQueue q2, D
                 finished = true;  // left the panel
             } else {
                 int M_id, L_id;
-                crystal_search(pd, det, x, y, z, mid, M_id, L_id);
+                crystal_search_rcp(pd, det, x, y, z, mid, M_id, L_id);
                 h_key = (M_id << 16) | (L_id & 0xffff);
                 float rho = det.dens[mid];
                 int mat = det.mat[mid];
@@ -1216,8 +1036,8 @@ __global__ void __launch_bounds__(kDetThreads, BPS) k_detector(PhotonQueue q2, D
                 if (u >= prob) {
                     prob += lamden * xs.compt;
                     if (u < prob) {
-                        kn = true;                       // Compton: the sampler's rounds are this lane's next steps
-                        kn_phi = kTwoPi * u01(r.z);
+                        compton = true;
+                        phi = kTwoPi * u01(r.z);
                     } else {
                         prob += lamden * xs.rayl;
                         if (u < prob) {
@@ -1231,63 +1051,130 @@ __global__ void __launch_bounds__(kDetThreads, BPS) k_detector(PhotonQueue q2, D
                     }
                 }
             }
-        } else if (active) {
-            // KN: one rejection round of the Klein-Nishina sampler for free electrons at rest (compton_kn above,
-            // gPET_kernals.cu:90-126), on this step's Philox block
-            const float e0 = E * kIMC2;
-            const float twoe = 2.0f * e0;
-            const float kmin2 = 1.0f / ((1.0f + twoe) * (1.0f + twoe));
-            const float loge = __logf(1.0f + twoe);
-            float efrac;
-            if (u01(r.x) * (loge + twoe * (1.0f + e0) * kmin2) < loge) efrac = expf(-u01(r.y) * loge);
-            else efrac = sqrtf(kmin2 + u01(r.y) * (1.0f - kmin2));
-            const float mess = e0 * e0 * efrac * (1.0f + efrac * efrac);
-            if (u01(r.z) * mess <= mess - (1.0f - efrac) * ((1.0f + twoe) * efrac - 1.0f)) {
-                kn = false;
-                costh = 1.0f - (1.0f - efrac) / (efrac * e0);
-                const float de = E * (1.0f - efrac);
-                phi = kn_phi;
-                if (mid == 0) { h_type0 = 1; h_E0 = de; nh = 1; }
-                E -= de;
-                if (E < eabs) {
-                    if (mid == 0) { h_E1 = E; nh = 2; }  // type 2: remainder absorbed on the spot
-                    finished = true;
+        }
+        // ---- Klein-Nishina sampling of the scattering photons (comsam, gPET_kernals.cu:90-126) by the whole warp
+        unsigned cmask = __ballot_sync(kFull, compton);
+        float efrac = 1.f;
+        bool pending = compton;
+        while (cmask) {
+            const unsigned nC = __popc(cmask);
+            const unsigned R = min(32u / nC, (unsigned)kKnMaxRounds);
+            const unsigned mine = __popc(cmask & lt_mask);          // this lane's number among the scattering photons
+            if (pending) ws.kn_src[mine] = (int)lane;
+            __syncwarp();
+            const unsigned jk = __ldg(&c_kn.jk[nC][lane]);
+            const unsigned j = jk & 31u, k = jk >> 5;               // this lane evaluates round k of photon j
+            const int src = ws.kn_src[j];
+            const float Ej = __shfl_sync(kFull, E, src);
+            const unsigned c0 = __shfl_sync(kFull, rng.c0, src), c1 = __shfl_sync(kFull, rng.c1, src), c3 = __shfl_sync(kFull, rng.c3, src);
+            bool acc = false;
+            float ef = 0.f;
+            if (k < R) {
+                Philox g(seed, 0, (uint32_t)kStageDetector << 24);
+                g.c0 = c0; g.c1 = c1; g.c3 = c3 + k;
+                const uint4 q = g.next();
+                const float e0 = Ej * kIMC2;
+                const float twoe = 2.0f * e0;
+                const float kmin2 = 1.0f / ((1.0f + twoe) * (1.0f + twoe));
+                const float loge = __logf(1.0f + twoe);
+                if (u01(q.x) * (loge + twoe * (1.0f + e0) * kmin2) < loge) ef = expf(-u01(q.y) * loge);
+                else ef = sqrtf(kmin2 + u01(q.y) * (1.0f - kmin2));
+                const float mess = e0 * e0 * ef * (1.0f + ef * ef);
+                acc = u01(q.z) * mess <= mess - (1.0f - ef) * ((1.0f + twoe) * ef - 1.0f);
+            }
+            const unsigned accmask = __ballot_sync(kFull, acc);
+            // the lanes that hold this photon's rounds: mine, mine + nC, ...; the first accepted one is the sampler's answer
+            const unsigned pat = __ldg(&c_kn.rounds[nC]) << mine;
+            const unsigned hit = pending ? (accmask & pat) : 0u;
+            const int win = hit ? __ffs(hit) - 1 : 0;
+            const float efw = __shfl_sync(kFull, ef, win);
+            if (pending) {
+                if (hit) {
+                    efrac = efw;
+                    rng.c3 += __popc(pat & ((1u << win) - 1u)) + 1u;   // rounds before the accepted one were rejections; its block is the last one consumed
+                    pending = false;
                 } else {
-                    turn = true;
+                    rng.c3 += R;                                  // R rejections
                 }
             }
+            __syncwarp();
+            cmask = __ballot_sync(kFull, pending);
         }
-        // ---- decided interactions meet here: one rotation, one adder
-        if (turn) rotate_dir(vx, vy, vz, costh, phi);
-        if (nh >= 1) {
-            if (!adder(wp, col, nslot, h_key, h_E0, x, y, z, t)) n_drop_adder++;
-            if (nh == 2 && !adder(wp, col, nslot, h_key, h_E1, x, y, z, t)) n_drop_adder++;
-        }
-        if (record_hits) {
-            stage_hit(nh >= 1, h_type0, h_E0);
-            stage_hit(nh == 2, 2, h_E1);
-        }
-        // ---- finished photons with deposits park their column and take a spare one
-        if (finished) active = false;
-        unsigned fin = __ballot_sync(kFull, finished && nslot > 0);
-        while (fin) {
-            if (nfree == 0u) drain();
-            const unsigned take = min((unsigned)__popc(fin), nfree);
-            const bool in = (fin >> lane) & 1u;
-            const unsigned rank = __popc(fin & lt_mask);
-            if (in && rank < take) {
-                wp.h_parn[col] = parn; wp.h_eid[col] = eid; wp.h_pan_ns[col] = pa | (nslot << 8);
-                wp.pend_col[npend + rank] = (unsigned char)col;
-                col = wp.free_col[nfree - 1u - rank];
-                nslot = 0;
+        if (compton) {
+            const float e0 = E * kIMC2;
+            costh = 1.0f - (1.0f - efrac) / (efrac * e0);
+            const float de = E * (1.0f - efrac);
+            if (mid == 0) { h_type0 = 1; h_E0 = de; nh = 1; }
+            E -= de;
+            if (E < eabs) {
+                if (mid == 0) { h_E1 = E; nh = 2; }  // type 2: remainder absorbed on the spot
+                finished = true;
+            } else {
+                turn = true;
             }
-            fin = __ballot_sync(kFull, in && rank >= take);
-            npend += take;
-            nfree -= take;
         }
+        if (turn) rotate_dir(vx, vy, vz, costh, phi);
+        // ---- adder on the fly
+        if (nh >= 1) {
+            if (!adder_fast(sl, tid, nslot, h_key, h_E0, x, y, z, t)) n_drop_adder++;
+            if (nh == 2 && !adder_fast(sl, tid, nslot, h_key, h_E1, x, y, z, t)) n_drop_adder++;
+        }
+        // ---- hits into the warp's staging rows
+        if (record_hits) {
+#pragma unroll
+            for (int pass = 0; pass < 2; pass++) {
+                const bool has = nh > pass;
+                const unsigned m = __ballot_sync(kFull, has);
+                if (m == 0u) break;
+                const unsigned cnt = __popc(m);
+                if (hstaged + cnt > 32u) flush_hits();
+                if (has) {
+                    const unsigned p = hstaged + __popc(m & lt_mask);
+                    ws.hid[p] = make_int4(parn, s_panels[pa].id, h_key >> 16, h_key & 0xffff);
+                    ws.hf[p] = make_float4(pass ? h_E1 : h_E0, x, y, z);
+                    ws.ht[p] = t;
+                    ws.htype[p] = pass ? 2 : h_type0;
+                }
+                hstaged += cnt;
+            }
+        }
+        // ---- photon finished: readout (gPET_kernals.cu:756-813), events into the warp's staging records
+        if (finished) active = false;
+        const bool mine_ev = finished && nslot > 0;
+        unsigned deadmask = 0;
+        if (mine_ev && nslot > 1 && rdepth != 3) deadmask = readout_merge_fast(sl, tid, nslot, depth, rpolicy);
+        unsigned ne = mine_ev ? (unsigned)(nslot - __popc(deadmask)) : 0u;
+        if (__ballot_sync(kFull, ne != 0u)) {
+            // at most kSlots events per lane: rounds of one event per lane, so that a round always fits the 32 records
+            int knext = 0;
+#pragma unroll 1
+            while (true) {
+                const bool has = ne != 0u;
+                const unsigned m = __ballot_sync(kFull, has);
+                if (m == 0u) break;
+                const unsigned cnt = __popc(m);
+                if (estaged + cnt > 32u) flush_events();
+                if (has) {
+                    while (deadmask >> knext & 1u) knext++;
+                    const int key = sl.key[knext][tid];
+                    const int panel_id = s_panels[pa].id;
+                    EventRec r;
+                    r.parn = parn; r.pann = panel_id; r.modn = key >> 16; r.cryn = key & 0xffff;
+                    r.siten = event_siten(depth, panel_id, r.modn, r.cryn, det);
+                    r.eventid = eid;
+                    r.t = sl.t[knext][tid]; r.E = sl.E[knext][tid];
+                    r.x = sl.x[knext][tid]; r.y = sl.y[knext][tid]; r.z = sl.z[knext][tid];
+                    store_event_rec(reinterpret_cast<EventRec*>(ws.ev) + (estaged + __popc(m & lt_mask)), r);
+                    knext++;
+                    ne--;
+                }
+                estaged += cnt;
+            }
+        }
+        if (mine_ev) nslot = 0;
     }
-    if (npend) drain();
     if (hstaged) flush_hits();
+    if (estaged) flush_events();
     // per-warp tallies
     unsigned b = n_drop_adder;
 #pragma unroll
@@ -1492,8 +1379,6 @@ int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQu
     return 1;
 }
 
-// k_detector variants: GPET_DET_V=1 round 1's kernel, 2 (default) 8 spare columns per warp at 3 blocks per SM,
-// 3: 24 spare columns at 2 blocks per SM (A/B runs, tools/kprof.py)
 template <typename K>
 int launch_detector_variant(K kernel, int slot, size_t pool_bytes, PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth,
                             int readout_policy, int record_hits, HitBuffer hits, EventBuf ev, unsigned int* counters, unsigned* ticket,
@@ -1521,22 +1406,29 @@ int launch_detector_variant(K kernel, int slot, size_t pool_bytes, PhotonQueue q
 int launch_detector(PhotonQueue q2, DetectorDev det, TablesDev tb, float eabs, int readout_depth, int readout_policy,
                     int record_hits, HitBuffer hits, EventBuf ev, unsigned int* counters, unsigned int* hot, uint64_t seed,
                     unsigned long long id_base, int num_sms, cudaStream_t s, bool reset) {
-    if (ev.count != hits.count + 1 || (reinterpret_cast<uintptr_t>(hits.count) & 7u)) return -1;   // see kernels.hpp: caller reports it
     unsigned* ticket = hot + kHotTicketDet;
     if (reset) {
-        cudaMemsetAsync(hits.count, 0, 2 * sizeof(unsigned), s);   // hits.count, ev.count
+        cudaMemsetAsync(hits.count, 0, sizeof(unsigned), s);
+        cudaMemsetAsync(ev.count, 0, sizeof(unsigned), s);
         cudaMemsetAsync(counters + 9, 0, sizeof(unsigned), s);     // adder drops
         cudaMemsetAsync(ticket, 0, sizeof(unsigned), s);
     }
-    static const int variant = tune("GPET_DET_V", 2);
+    static bool tables_ready[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!tables_ready[dev]) {
+        KnTables h{};
+        for (unsigned nC = 1; nC <= 32; nC++) {
+            const unsigned R = std::min(32u / nC, (unsigned)kKnMaxRounds);
+            for (unsigned l = 0; l < 32; l++) h.jk[nC][l] = (unsigned char)((l % nC) | (std::min(l / nC, 7u) << 5));
+            for (unsigned l = 0; l < 32; l++) if (l / nC >= R) h.jk[nC][l] = (unsigned char)((l % nC) | (7u << 5));
+            for (unsigned kk = 0; kk < R; kk++) h.rounds[nC] |= 1u << (kk * nC);
+        }
+        cudaMemcpyToSymbolAsync(c_kn, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
+        cudaStreamSynchronize(s);   // `h` is a local
+        tables_ready[dev] = true;
+    }
     constexpr size_t kWarps = kDetThreads / 32;
-    if (variant == 1)
-        return launch_detector_variant(k_detector_v1, 0, sizeof(SlotsSmem), q2, det, tb, eabs, readout_depth, readout_policy, record_hits, hits,
-                                       ev, counters, ticket, seed, id_base, num_sms, s);
-    if (variant == 3)
-        return launch_detector_variant(k_detector<56, 2>, 2, kWarps * sizeof(WarpPool<56>), q2, det, tb, eabs, readout_depth, readout_policy,
-                                       record_hits, hits, ev, counters, ticket, seed, id_base, num_sms, s);
-    return launch_detector_variant(k_detector<40, 3>, 1, kWarps * sizeof(WarpPool<40>), q2, det, tb, eabs, readout_depth, readout_policy,
+    return launch_detector_variant(k_detector, 1, sizeof(SlotsSmem) + kWarps * sizeof(WarpStage), q2, det, tb, eabs, readout_depth, readout_policy,
                                    record_hits, hits, ev, counters, ticket, seed, id_base, num_sms, s);
 }
 

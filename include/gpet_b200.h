@@ -328,6 +328,20 @@ int gpet_profile_count(gpet_ctx* ctx);
 int gpet_profile_get(gpet_ctx* ctx, int i, char* name, int name_cap, double* total_ms, uint64_t* launches);
 /* Shard the planned frames: this context only runs frames f with f % world == rank. */
 int gpet_set_shard(gpet_ctx* ctx, int rank, int world);
+/* Multi-GPU exchange by time slice (gpet_b200/multi.py).  Decay histories shard over the GPUs; what couples them
+ * again is the digitizer -- dead time per site and the coincidence sorter over the global time order (the reference
+ * digitizes each epoch = time slice as one list, gPET.cu:385-424).  Every rank therefore receives the post-readout events
+ * of ITS time slice [lo, hi) from all ranks plus a halo of the neighbouring slices, digitizes them as one list and keeps
+ * what belongs to the slice: the singles with lo <= t < hi (a contiguous range of the time-sorted list: counts[0] singles
+ * precede it, counts[1] are inside) and the coincidences whose opening single lies in the slice.  halo_start_us = time
+ * from which on the list is complete (-INFINITY: from the start of the acquisition); decisions that would need anything
+ * earlier raise counts[2] (halo too short) instead of being silently wrong. */
+int gpet_set_emit_window(gpet_ctx* ctx, double lo_us, double hi_us, double halo_start_us);
+int gpet_clear_emit_window(gpet_ctx* ctx);
+int gpet_get_emit_counts(gpet_ctx* ctx, uint64_t counts[3]);
+/* The event buffer <-> caller-owned DEVICE memory (48-byte records), for exchanges between GPUs that never touch the host. */
+int64_t gpet_copy_events_to_device(gpet_ctx* ctx, void* dst_device, int64_t cap);
+int gpet_put_events_device(gpet_ctx* ctx, const void* src_device, int64_t n);
 /* 64-bit history numbers.  The reference indexes atoms and threads with 32-bit integers (gPET.h:50 `unsigned int natom`,
  * gPET_kernals.cu:490-497), which caps an acquisition near 4e9 histories.  Here every pair has a 64-bit global index
  * (pair k of the acquisition = first_pair + k; photons 2k, 2k+1) that keys all its Philox streams; the 32-bit

@@ -420,9 +420,10 @@ def test_run_shipped_example_writes_reference_layouts(tmp_path):
     with api.Context(0) as c2:
         c2.load_config_file(ex / "input_PET.in", base_dir=ex)
         again, _ = c2.digitize(adder)
-    # the dump really is the unblurred list: the 511 keV photopeak of the adder is a line, that of the singles is not
+    # the dump really is the unblurred list: the photopeak of the adder is as narrow as the acollinearity leaves it
+    # (E = 511 keV (1 +- delta / 2), sigma 0.95 keV), that of the singles carries the 5 % energy blur (sigma 11 keV)
     peak = adder["E"][(adder["E"] > 505e3) & (adder["E"] < 517e3)]
-    assert peak.size > 1000 and np.std(peak) < 600.0 < np.std(sing["E"][(sing["E"] > 450e3) & (sing["E"] < 570e3)])
+    assert peak.size > 1000 and np.std(peak) < 1500.0 < 5000.0 < np.std(sing["E"][(sing["E"] > 450e3) & (sing["E"] < 570e3)])
     assert again.tobytes() == sing.tobytes()
 
 

@@ -11,7 +11,14 @@ COLS = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "rd_MB"), ("d
         ("smsp__thread_inst_executed_per_inst_executed.ratio", "thr/inst"), ("sm__issue_active.avg.pct_of_peak_sustained_elapsed", "issue%"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"), ("lts__t_sector_hit_rate.pct", "L2hit%"),
         ("l1tex__t_sector_hit_rate.pct", "L1hit%"), ("launch__registers_per_thread", "regs"),
-        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"), ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram%")]
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"), ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
+        # pipe utilisation: the double-precision time path (t += s / c, the fp64 divide of the panel entry, decay times) runs
+        # on the FP64 pipe; north_star asks for its utilisation by name
+        ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64%"),
+        ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%"),
+        ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu%"),
+        ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"),
+        ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%")]
 
 
 def short(name):

@@ -44,15 +44,16 @@ COINC_WINDOW_US = 0.01
 
 
 def reduce_events(adder, singles, npanels, moduleN):
-    """histograms of one run's post-readout events (adder.dat) and singles (singles.dat)"""
-    return {
-        "n_adder": int(adder.size), "n_singles": int(singles.size),
-        "hist_adder_E": np.histogram(adder["E"], E_BINS)[0].tolist(),
-        "hist_singles_E": np.histogram(singles["E"], E_BINS)[0].tolist(),
-        "adder_below_400keV": int((adder["E"] < 400000.0).sum()),
-        "panel_occupancy": np.bincount(adder["pann"], minlength=npanels)[:npanels].tolist(),
-        "module_occupancy": np.bincount(adder["modn"], minlength=moduleN)[:moduleN].tolist(),
-    }
+    """histograms of one run's post-readout events (adder.dat; None in PSF mode, where the reference does not write it,
+    gPET.cu:131) and singles (singles.dat); occupancies from the singles"""
+    out = {"n_singles": int(singles.size), "hist_singles_E": np.histogram(singles["E"], E_BINS)[0].tolist(),
+           "singles_below_400keV": int((singles["E"] < 400000.0).sum()),
+           "panel_occupancy": np.bincount(singles["pann"], minlength=npanels)[:npanels].tolist(),
+           "module_occupancy": np.bincount(singles["modn"], minlength=moduleN)[:moduleN].tolist()}
+    if adder is not None:
+        out.update({"n_adder": int(adder.size), "hist_adder_E": np.histogram(adder["E"], E_BINS)[0].tolist(),
+                    "adder_below_400keV": int((adder["E"] < 400000.0).sum())})
+    return out
 
 
 def reduce_hits(ids, f):
@@ -77,9 +78,12 @@ def run_reference(name, cfg, decays, hit_decays, tmp):
     ex = gen_inputs.write_workdir(Path(tmp) / f"{name}_ref", cfg, EXAMPLE)
     t0 = time.perf_counter()
     r = run_ref.run_once(ex, "gPET_nodump", timeout=1500)
-    if r["returncode"] != 0 or r["pairs"] <= 0:
+    if cfg["psf"] is not None:
+        r["pairs"] = cfg["psf"].shape[0] // 2   # simulateParticle prints no emission counts (gPET.cu:13-199); every record is run
+        r["epochs"] = -(-cfg["psf"].shape[0] // 524288)
+    if r["returncode"] != 0 or r["pairs"] <= 0 or not (ex / "output" / "singles.dat").exists():
         return {"error": (r["stdout_tail"][-600:] + r["stderr_tail"])}
-    adder = refio.read_events(ex / "output" / "adder.dat")
+    adder = refio.read_events(ex / "output" / "adder.dat") if (ex / "output" / "adder.dat").exists() else None
     singles = refio.read_events(ex / "output" / "singles.dat")
     rep = {"binary": "oracle/_ref/gPET_nodump", "pairs": r["pairs"], "epochs": r["epochs"], "sim_wall_s": r["sim_wall_s"],
            "process_wall_s": time.perf_counter() - t0,
@@ -137,17 +141,22 @@ def compare(ref, ours):
     """rates per pair (relative difference, statistical sigma of the difference) and shape chi-squares"""
     out = {"rates": {}, "chi2": {}}
     for k in ("hits", "events_adder", "events_threshold", "events_deadtime", "singles"):
+        if not ref["counters"][k]:
+            continue
         a, b = ref["counters"][k] / ref["pairs"], ours["counters"][k] / ours["pairs"]
         sig = np.sqrt(1.0 / max(ref["counters"][k], 1) + 1.0 / max(ours["counters"][k], 1))
         out["rates"][k] = {"reference": a, "ours": b, "rel_diff": (b - a) / a if a else None, "stat_sigma_rel": float(sig)}
     a, b = ref["coincidences"] / ref["pairs"], ours["coincidences"] / ours["pairs"]
     out["rates"]["coincidences"] = {"reference": a, "ours": b, "rel_diff": (b - a) / a if a else None,
                                     "stat_sigma_rel": float(np.sqrt(1.0 / max(ref["coincidences"], 1) + 1.0 / max(ours["coincidences"], 1)))}
-    a, b = ref["adder_below_400keV"] / ref["n_adder"], ours["adder_below_400keV"] / ours["n_adder"]
-    out["rates"]["adder_share_below_400keV"] = {"reference": a, "ours": b, "rel_diff": (b - a) / a}
+    for what in ("adder", "singles"):
+        if f"n_{what}" in ref and f"n_{what}" in ours:
+            a, b = ref[f"{what}_below_400keV"] / ref[f"n_{what}"], ours[f"{what}_below_400keV"] / ours[f"n_{what}"]
+            out["rates"][f"{what}_share_below_400keV"] = {"reference": a, "ours": b, "rel_diff": (b - a) / a}
     for k in ("hist_adder_E", "hist_singles_E", "panel_occupancy", "module_occupancy"):
-        c2, ndf = chi2(ref[k], ours[k])
-        out["chi2"][k] = {"chi2": c2, "ndf": ndf}
+        if k in ref and k in ours:
+            c2, ndf = chi2(ref[k], ours[k])
+            out["chi2"][k] = {"chi2": c2, "ndf": ndf}
     if "hits_run" in ref and "hist_hit_E" in ref["hits_run"]:
         for k in ("hist_hit_E", "hit_types", "hit_x_hist"):
             c2, ndf = chi2(ref["hits_run"][k], ours["hits_run"][k])
@@ -171,7 +180,7 @@ def main():
         decays = min(a.decays, 1_000_000) if name == "config2_psf" else a.decays   # config 2 is 1e6 pairs by definition
         with tempfile.TemporaryDirectory() as tmp:
             t0 = time.perf_counter()
-            ref = run_reference(name, gen_inputs.stats_config(name, decays), decays, 0 if name == "config2_psf" and False else min(a.hit_decays, decays), tmp)
+            ref = run_reference(name, gen_inputs.stats_config(name, decays), decays, min(a.hit_decays, decays), tmp)
             t1 = time.perf_counter()
             if "error" in ref:
                 print(name, "REFERENCE FAILED", ref["error"])
