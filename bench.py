@@ -183,6 +183,18 @@ def have_gpu():
     return shutil.which("nvidia-smi") is not None and subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0
 
 
+def bench_config(source):
+    """The `config` object of BOTH arms (identical keys and values: the driver compares them)."""
+    return {"workload": workload_name(source),
+            "step": "our arm: one step = the acquisition with its activity scaled so that every GPU runs FRAMES_PER_STEP frames of ~1.1 M pairs "
+                    "(>= 50 ms of kernels), sharded by frames over the GPUs; reference arm: one step = the acquisition at the shipped activity "
+                    "(1.118 M pairs, a bounded sample of the same workload -- the metric is per pair)",
+            "l2": "working set of a frame (~250 MB of queues, hit / event / sort buffers) exceeds the 126 MB L2; 256 MiB flush between timed steps",
+            "coincidence_window_us": 0.01, "rng": "Philox4x32-10, key 0x67504554, 64-bit history numbers", "time_path": "fp64",
+            "multi_gpu": "one acquisition, frames sharded round robin over the ranks (gpet_set_shard), no data-path collective; "
+                         "tallies all-reduced once over NCCL after the last step, inside the timed region"}
+
+
 def reference_line(ex, args, source, steps, warmup):
     """The reference's own implementation of the path, timed on this box: its CUDA build (oracle/_ref, texture-object
     patch only) when it travelled with the snapshot and a GPU is present -- the reference has no CPU path at all
@@ -192,16 +204,18 @@ def reference_line(ex, args, source, steps, warmup):
     if run_ref.available() and have_gpu():
         try:
             line = run_ref.bench_reference(ex, steps=steps, warmup=warmup, metric=METRIC, unit=UNIT, workload=workload_name(source))
+            line["details"] = {k: v for k, v in line["config"].items() if k != "workload"}
         except Exception as e:  # noqa: BLE001
             line = None
             print(f"reference binary unusable ({type(e).__name__}: {e}); falling back to the CPU oracle port", file=sys.stderr)
     if line is None:
         base = cpu_baseline(ex, source, npairs=4_000_000)
         v = base["value"]
-        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
                 "ms_per_step": 1e3 * 4_000_000 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(source)}, "cpu_baseline": base,
+                "dtype": "f32", "data": "synthetic", "cpu_baseline": base,
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line["config"] = bench_config(source)
     line["n_gpus"] = args.gpus
     line["impl"] = "reference"
     return line
@@ -213,7 +227,8 @@ def run_reference(args):
         return
     with tempfile.TemporaryDirectory() as tmp:
         ex = make_workdir(tmp, source=args.source)
-        print(json.dumps(reference_line(ex, args, args.source, steps=max(1, min(args.steps, 5)), warmup=1)))
+        # --steps / --warmup as given: every step is one complete run of the reference binary (~2 s of process time each)
+        print(json.dumps(reference_line(ex, args, args.source, steps=max(1, args.steps), warmup=max(0, args.warmup))))
 
 
 # algorithmic bytes one launch of each kernel must move; c = per-frame counters
@@ -239,13 +254,14 @@ ALG_BYTES = {
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--source", default=DEFAULT_SOURCE, help="source file of the example (source.txt | pointsource.txt)")
-    ap.add_argument("--e2e-frame-pairs", type=int, default=700000,
-                    help="frame size (pairs) of the end-to-end runs: two frames, so that the D2H copy of frame 0 overlaps frame 1 "
-                         "(tools/frames_sweep.py); 0 = one frame as in the resident runs")
+    ap.add_argument("--frames-per-step", type=int, default=160,
+                    help="frames (of ~1.1 M pairs) every GPU runs in one resident step: 160 x 0.34 ms = ~55 ms of kernels")
+    ap.add_argument("--e2e-frames-per-step", type=int, default=16, help="frames per GPU of an end-to-end step (35 MB of results each)")
+    ap.add_argument("--frame-pairs", type=int, default=1_240_000, help="frame capacity in pairs (the planner fills ~0.9 of it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
@@ -287,79 +303,42 @@ def main():
         ex = make_workdir(Path(tmp.name) / sub, source=source)
         ctx = api.Context(local)
         ctx.set_stream(stream.cuda_stream)
-        ctx.set_seed(0x67504554 + 1000003 * rank)   # disjoint Philox keys per rank: independent decay histories
         ctx.load_config_file(ex / "input_PET.in", base_dir=ex)
         ctx.set_digitizer(coinc_window_us=0.01)
         # coincidences reach the host as index pairs into the singles list (8 B each instead of two copied records)
         ctx.set_coincidence_format(api.Context.COINC_PAIRS)
         ctx.set_spectrum(128, 0.0, 1.0e6)
-        ctx.plan_frames(0)
+        ctx.base_atoms = [int(x["natom"]) for x in ctx.sources()]
         return ex, ctx
 
-    # Tally reduction over NCCL is part of the multi-GPU step (gpet_b200/multi.py).  Nothing in a step depends on the
-    # tallies, so the reduction of step k-1 is issued at the top of step k (after the step's start event) by a helper
-    # thread -- its host-side cost (~60 us of tensor copies and NCCL enqueue) and its NCCL kernel both overlap step k's
-    # own launches and kernels (gpet_run* is a foreign call: the GIL is free) -- and is waited for before the step's end
-    # event; the last step of a timed region also reduces its own tallies.  Every reduction therefore starts and
-    # completes inside a timed step.
-    import queue
-    nt = len(multi.TALLY_FIELDS)
-    no_tally = os.environ.get("GPET_BENCH_NO_TALLY") == "1"   # diagnostic only: what the per-step collective costs
-    carried = [None]                            # stats of the previous step, not reduced yet
-    jobs, done = queue.SimpleQueue(), queue.SimpleQueue()
+    def plan(ctx, frames_per_gpu):
+        """ONE acquisition whose activity is `frames_per_gpu x world` times the shipped one: the planner cuts it into as many
+        frames of ~1.1 M pairs (same seed on every rank: same plan), rank r runs frames f with f % world == r."""
+        scale = max(1, frames_per_gpu * world)
+        for i, n in enumerate(ctx.base_atoms):
+            ctx.set_source_atoms(i, n * scale)
+        nf = ctx.plan_frames(args.frame_pairs)
+        ctx.set_shard(rank, world)
+        return nf
 
-    def reducer():
-        torch.cuda.set_device(local)
-        side = torch.cuda.Stream(device=dev)
-        tally_host = torch.zeros(nt, dtype=torch.int64).pin_memory()
-        tally_dev = torch.zeros(nt, dtype=torch.int64, device=dev)
-        with torch.cuda.stream(side):
-            while True:
-                st = jobs.get()
-                if st is None:
-                    return
-                tally_host.copy_(torch.from_numpy(multi.stats_vector(st)))
-                tally_dev.copy_(tally_host, non_blocking=True)
-                done.put(dist.all_reduce(tally_dev, async_op=True))
+    tally_dev = torch.zeros(len(multi.TALLY_FIELDS), dtype=torch.int64, device=dev)
 
-    if world > 1 and not no_tally:
-        threading.Thread(target=reducer, daemon=True).start()
-    inflight = [0]
-
-    def issue_reduce(st):
-        if world > 1 and not no_tally:
-            jobs.put(st)
-            inflight[0] += 1
-
-    def drain():
-        while inflight[0]:
-            done.get().wait()                   # stream dependency of this step's stream on the reduction
-            inflight[0] -= 1
-
-    def one_step(ctx, resident=True, last=False):
-        if carried[0] is not None:
-            issue_reduce(carried[0])
-        st = ctx.run_resident() if resident else ctx.run(None)
-        if world > 1:
-            drain()
-            carried[0] = st
-            if last:
-                issue_reduce(st)
-                drain()
-                carried[0] = None
-        return st
-
-    def timed(ctx, nsteps, resident=True):
+    def timed(ctx, nsteps, resident=True, reduce_at_end=False):
+        """`nsteps` steps, each bracketed by CUDA events on the launching stream (resident) or by the wall clock (end to
+        end: host results), L2 flushed in between.  The tallies of all steps are all-reduced ONCE, after the last step,
+        inside the timed region (the reduction's own device time is added)."""
         times, stats = [], []
-        for _ in range(nsteps):
+        for k in range(nsteps):
             flush.fill_(1)                      # L2 flush between timed iterations
             torch.cuda.synchronize()
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             w0 = time.perf_counter()
-            if not resident:
-                ctx.plan_frames(args.e2e_frame_pairs)   # e2e: planning + descriptor upload are part of the user's call
-            st = one_step(ctx, resident, last=_ == nsteps - 1)
+            st = ctx.run_resident() if resident else ctx.run(None)
+            if reduce_at_end and k == nsteps - 1 and world > 1:
+                acc = np.sum([multi.stats_vector(x) for x in stats + [st]], axis=0)
+                tally_dev.copy_(torch.from_numpy(acc), non_blocking=True)
+                dist.all_reduce(tally_dev)      # NCCL on this stream: inside the last step's event bracket
             e1.record(stream)
             torch.cuda.synchronize()
             w1 = time.perf_counter()
@@ -367,70 +346,120 @@ def main():
             stats.append(st)
         return times, stats
 
-    def measure(ctx, steps, warmup):
+    def reduce_max_sum(ms, *counts):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        c = torch.tensor(list(counts), dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c)
+        return float(t.item()), [int(x) for x in c.tolist()]
+
+    def measure(ctx, steps, warmup, frames_per_step, e2e_frames_per_step):
+        nf = plan(ctx, frames_per_step)
         timed(ctx, warmup)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        times, stats = timed(ctx, steps)
+        times, stats = timed(ctx, steps, reduce_at_end=True)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        total_ms = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
-        pairs = torch.tensor([sum(s.pairs for s in stats)], dtype=torch.int64, device=dev)
-        coinc = torch.tensor([sum(s.coincidences for s in stats)], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-            dist.all_reduce(pairs)
-            dist.all_reduce(coinc)
-        # e2e through gpet_run: host results in pinned memory, wall clock around planning + run
+        total_ms, (pairs, coinc) = reduce_max_sum(sum(times), sum(s.pairs for s in stats), sum(s.coincidences for s in stats))
+        # e2e through gpet_run: planning + all stages + results in pinned host memory, wall clock
+        nf_e = plan(ctx, e2e_frames_per_step)
         timed(ctx, 2, resident=False)
-        e_times, e_stats = timed(ctx, max(3, min(steps, 20)), resident=False)
-        ctx.plan_frames(0)                      # back to the resident plan (per-kernel profile below)
-        e_ms = torch.tensor([sum(e_times)], dtype=torch.float64, device=dev)
-        e_pairs = torch.tensor([sum(s.pairs for s in e_stats)], dtype=torch.int64, device=dev)
         if world > 1:
-            dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-            dist.all_reduce(e_pairs)
-        return {"total_ms": float(total_ms.item()), "pairs": int(pairs.item()), "coinc": int(coinc.item()), "stats": stats,
-                "e2e_ms": float(e_ms.item()), "e2e_pairs": int(e_pairs.item()), "e2e_stats": e_stats}
+            dist.barrier()
+        e_times, e_stats = timed(ctx, max(3, min(steps, 10)), resident=False)
+        e_ms, (e_pairs,) = reduce_max_sum(sum(e_times), sum(s.pairs for s in e_stats))
+        return {"total_ms": total_ms, "pairs": pairs, "coinc": coinc, "stats": stats, "frames": nf, "e2e_ms": e_ms, "e2e_pairs": e_pairs,
+                "e2e_stats": e_stats, "e2e_frames": nf_e, "tallies": dict(zip(multi.TALLY_FIELDS, (int(x) for x in tally_dev.tolist())))}
 
     ex, ctx = make_ctx(args.source, "main")
-    m = measure(ctx, args.steps, args.warmup)
+    m = measure(ctx, args.steps, args.warmup, args.frames_per_step, args.e2e_frames_per_step)
     value = m["pairs"] / (m["total_ms"] * 1e-3)
     st = m["e2e_stats"][-1]
-    nframes = int(st.frames)
-    h2d = nframes * 4096 + 64
+    h2d = int(st.frames) * 4096 + 64
     d2h = int(st.singles * 48 + st.coincidences * (8 + 1) + 32 * 4 * st.frames)   # records, index pairs + class bytes, counters
+
+    # ---- same deliverable as the reference's timed region: adder.dat + singles.dat appended frame by frame (gPET.cu:383, 424;
+    # its hit dumps off as in gPET_nodump), wall clock of gpet_run(output_dir).  One GPU only (one host, one file system).
+    e2e_files = None
+    if world == 1 and not args.no_extra:
+        plan(ctx, 8)
+        ctx.set_transport(record_hits=0)
+        ctx.set_digitizer(coinc_window_us=0.0)
+        od = Path(tmp.name) / "files_out"
+        f_pairs, f_ms, f_bytes = 0, 0.0, 0
+        for k in range(4):
+            if od.exists():
+                shutil.rmtree(od)
+            od.mkdir()
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            stf = ctx.run(od)
+            w1 = time.perf_counter()
+            if k:                                # first pass = warm-up (pinned arenas grow)
+                f_pairs += int(stf.pairs); f_ms += (w1 - w0) * 1e3
+                f_bytes += (od / "adder.dat").stat().st_size + (od / "singles.dat").stat().st_size
+        e2e_files = {"value": f_pairs / (f_ms * 1e-3), "unit": UNIT, "bytes_written_per_step": f_bytes // 3, "steps": 3,
+                     "files": "adder.dat + singles.dat, appended frame by frame by a writer thread while the next frames compute",
+                     "timing": "wall clock around gpet_run(output_dir), files complete on return; same directory tree (tmp) as the reference arm's runs"}
+        ctx.set_transport(record_hits=1)
+        ctx.set_digitizer(coinc_window_us=0.01)
 
     extra = None
     if not args.no_extra and world == 1 and args.source == DEFAULT_SOURCE:
         ex2, ctx2 = make_ctx("pointsource.txt", "extra")
-        m2 = measure(ctx2, max(5, min(args.steps, 20)), 3)
+        m2 = measure(ctx2, max(5, min(args.steps, 10)), 3, args.frames_per_step, args.e2e_frames_per_step)
         extra = {"workload": workload_name("pointsource.txt"), "value": m2["pairs"] / (m2["total_ms"] * 1e-3),
                  "e2e": m2["e2e_pairs"] / (m2["e2e_ms"] * 1e-3), "pairs_per_step": m2["pairs"] / len(m2["stats"]), "unit": UNIT}
         ctx2.close()
 
+    # ---- the exchange path (decay-index sharding + singles exchanged by time slice with halo over NCCL), measured beside the
+    # frame-sharded headline: one acquisition of `world` x the shipped activity
+    exchange = None
+    if world > 1 and not args.no_extra:
+        try:
+            atoms = [n * world for n in ctx.base_atoms]
+            multi.run_exchange(ctx, atoms, dev, frame_pairs=args.frame_pairs)          # warm-up
+            dist.barrier(); torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            reps = 5
+            acc = None
+            for _ in range(reps):
+                r = multi.run_exchange(ctx, atoms, dev, frame_pairs=args.frame_pairs)
+                acc = r if acc is None else {k: (acc[k] + r[k] if k != "halo_flag" else acc[k] | r[k]) for k in r}
+            torch.cuda.synchronize(); dist.barrier()
+            x_ms, (x_pairs, x_sing, x_co, x_bytes, x_flag) = reduce_max_sum((time.perf_counter() - w0) * 1e3, acc["pairs"], acc["singles"],
+                                                                           acc["coincidences"], acc["bytes_sent"], acc["halo_flag"])
+            exchange = {"value": x_pairs / (x_ms * 1e-3), "unit": UNIT, "pairs": x_pairs // reps, "singles": x_sing // reps,
+                        "coincidences": x_co // reps, "nccl_bytes_per_acquisition": x_bytes // reps, "halo_too_short": int(x_flag > 0),
+                        "timing": "wall clock, stage-level calls from Python (unfused: a reference point for the exchange, not the headline)"}
+        except Exception as e:  # noqa: BLE001
+            exchange = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         # ---- per-kernel device times (CUDA events around every launch, on the launching stream) -> roofline
+        plan(ctx, 4)
+        ctx.set_shard(0, 1)
         ctx.profile(True)
-        nprof = 5
+        nprof = 3
         for _ in range(nprof):
             flush.fill_(1)
-            ctx.run_resident()
+            sp = ctx.run_resident()
         kt = ctx.kernel_times()
         ctx.profile(False)
-        s0 = m["stats"][-1]
-        fr = max(int(s0.frames), 1)
-        cnt = {"photons": 2 * s0.pairs / fr, "q1": s0.photons_phantom_out / fr, "on_panel": s0.photons_on_panel / fr,
-               "hits": s0.hits / fr, "events": s0.events_adder / fr, "alive": s0.events_threshold / fr,
-               "singles": s0.singles / fr, "coinc": s0.coincidences / fr}
+        fr = max(int(sp.frames), 1)
+        cnt = {"photons": 2 * sp.pairs / fr, "q1": sp.photons_phantom_out / fr, "on_panel": sp.photons_on_panel / fr,
+               "hits": sp.hits / fr, "events": sp.events_adder / fr, "alive": sp.events_threshold / fr,
+               "singles": sp.singles / fr, "coinc": sp.coincidences / fr}
         kernels = {}
         for name, (ms, n) in kt.items():
             alg = float(ALG_BYTES.get(name, lambda c: 0)(cnt))
-            kernels[name] = {"launches_per_step": n / nprof, "us_per_launch": 1e3 * ms / max(n, 1), "us_per_step": 1e3 * ms / nprof,
+            kernels[name] = {"launches_per_frame": n / nprof / fr, "us_per_launch": 1e3 * ms / max(n, 1), "us_per_frame": 1e3 * ms / nprof / fr,
                              "algorithmic_bytes_per_launch": alg, "achieved_gbs": alg / (ms / max(n, 1) * 1e-3) / 1e9 if ms > 0 else 0.0}
-        top = max(kernels, key=lambda k: kernels[k]["us_per_step"])
+        top = max(kernels, key=lambda k: kernels[k]["us_per_frame"])
         peaks = {}
         pk = ROOT / "MEASURED_PEAKS.json"
         if pk.exists():
@@ -443,9 +472,9 @@ def main():
         roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[top]["achieved_gbs"] / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if pk.exists() else "fallback 6650 GB/s (B200_PROFILING.md)",
-                    "us_per_launch": kernels[top]["us_per_launch"], "share_of_step": kernels[top]["us_per_step"] / sum(k["us_per_step"] for k in kernels.values()),
-                    "timing": "CUDA events bracketing every launch on the launching stream (gpet_profile_enable), 5 steps, L2 flushed between steps",
-                    "note": "Monte-Carlo transport is latency/issue bound: the algorithmic bytes are tiny against HBM (DESIGN.md section 4); see profiles/ for issue-slot and SIMT-efficiency numbers",
+                    "us_per_launch": kernels[top]["us_per_launch"], "share_of_step": kernels[top]["us_per_frame"] / sum(k["us_per_frame"] for k in kernels.values()),
+                    "timing": "CUDA events bracketing every launch on the launching stream (gpet_profile_enable), 3 runs of 4 frames, L2 flushed between runs",
+                    "note": "Monte-Carlo transport is latency/issue bound: the algorithmic bytes are tiny against HBM (DESIGN.md section 4); see profiles/ for issue-slot, SIMT-efficiency and pipe numbers",
                     "kernels": kernels}
         base = None
         if not args.no_cpu_baseline:
@@ -461,25 +490,27 @@ def main():
                 base["note"] = f"reference binary failed: {e}"
         clocks = sampler.stop()
         nsteps = len(m["stats"])
+        s0 = m["stats"][-1]
+        tl = m["tallies"] if world > 1 else dict(zip(multi.TALLY_FIELDS, (int(x) for x in np.sum([multi.stats_vector(x) for x in m["stats"]], axis=0))))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": m["total_ms"] / nsteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-"config": {"workload": workload_name(args.source), "pairs_per_step_per_gpu": m["pairs"] / nsteps / world,
-                           "frames_per_step": int(m["stats"][-1].frames), "e2e_frames_per_step": nframes, "l2": "flushed between timed steps (256 MiB write)",
-                           "coincidence_window_us": 0.01, "rng": "Philox4x32-10, key = 0x67504554 + 1000003*rank",
-                           "time_path": "fp64", "multi_gpu": "independent decay histories per rank (disjoint Philox keys), tallies all-reduced over NCCL"},
+                "dtype": "f32", "data": "synthetic", "config": bench_config(args.source),
+                "details": {"pairs_per_step_per_gpu": m["pairs"] / nsteps / world, "frames_in_the_acquisition": int(m["frames"]),
+                            "frames_per_step_per_gpu": int(s0.frames), "activity_scale": args.frames_per_step * world,
+                            "e2e_frames_per_step_per_gpu": int(st.frames), "e2e_activity_scale": args.e2e_frames_per_step * world,
+                            "frame_capacity_pairs": args.frame_pairs},
                 "clocks": clocks,
                 "e2e": {"value": m["e2e_pairs"] / (m["e2e_ms"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "timing": "wall clock around gpet_plan_frames + gpet_run (singles as 48-byte records, coincidences as index pairs into them plus one class byte each, delivered to pinned host memory; the acquisition is planned as e2e_frames_per_step frames so that the copy of a frame overlaps the next frame's kernels), max over ranks"},
+                        "timing": "wall clock around gpet_run: all stages, singles as 48-byte records and coincidences as index pairs into them plus one class byte each delivered to pinned host memory, the copy of a frame overlapping the kernels of the next; max over ranks"},
+                "e2e_files": e2e_files,
                 "gpu_launches": int(sum(s.kernel_launches for s in m["stats"])),
                 "roofline": roofline, "cpu_baseline": base,
-                "counters": {"pairs": int(s0.pairs), "hits": int(s0.hits), "events_adder": int(s0.events_adder),
-                             "singles": int(s0.singles), "coincidences": int(s0.coincidences),
-                             "trues": int(s0.trues), "scatters": int(s0.scatters), "randoms": int(s0.randoms),
+                "counters": {"pairs": tl["pairs"], "hits": tl["hits"], "events_adder": tl["events_adder"], "singles": tl["singles"],
+                             "coincidences": tl["coincidences"], "trues": tl["trues"], "scatters": tl["scatters"], "randoms": tl["randoms"],
+                             "of": "all timed steps, all ranks (one NCCL all-reduce after the last step)" if world > 1 else "all timed steps",
                              "coincidences_per_s": float(m["coinc"] / (m["total_ms"] * 1e-3))},
-                "extra": extra}
+                "exchange": exchange, "extra": extra}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    jobs.put(None)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -339,10 +339,10 @@ class Context:
         self._ck(self._l.gpet_clear_emit_window(self._h))
 
     def emit_counts(self):
-        """(singles before the window, singles inside it, halo-too-short flag) of the last digitizer pass"""
-        out = (C.c_uint64 * 3)()
+        """(singles before the window, singles inside it, halo-too-short flag, coincidences emitted) of the last digitizer pass"""
+        out = (C.c_uint64 * 4)()
         self._ck(self._l.gpet_get_emit_counts(self._h, out))
-        return int(out[0]), int(out[1]), int(out[2])
+        return int(out[0]), int(out[1]), int(out[2]), int(out[3])
 
     def copy_events_to_device(self, dst_ptr, cap):
         return self._ck(self._l.gpet_copy_events_to_device(self._h, C.c_void_p(dst_ptr), int(cap)))

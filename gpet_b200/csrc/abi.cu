@@ -679,13 +679,13 @@ int gpet_clear_emit_window(gpet_ctx* c) {
     return GPET_OK;
 }
 
-int gpet_get_emit_counts(gpet_ctx* c, uint64_t out[3]) {
+int gpet_get_emit_counts(gpet_ctx* c, uint64_t out[4]) {
     NEED_DEVICE();
     if (!out) return GPET_ERR_ARG;
     int r;
     if ((r = ensure_buffers(c))) return r;
     if ((r = read_counters(c))) return r;
-    out[0] = c->h_counters[10]; out[1] = c->h_counters[11]; out[2] = c->h_counters[15];
+    out[0] = c->h_counters[10]; out[1] = c->h_counters[11]; out[2] = c->h_counters[15]; out[3] = c->h_counters[4];
     return GPET_OK;
 }
 

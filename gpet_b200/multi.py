@@ -130,7 +130,7 @@ def digitize_slice(ctx, recv_u8, edges, rank, halo_back):
     try:
         ctx.put_events_device(recv_u8.data_ptr() if recv_u8.numel() else 0, recv_u8.shape[0])
         ctx.stage_digitize()
-        before, inside, flag = ctx.emit_counts()
+        before, inside, flag, _ = ctx.emit_counts()
         singles = ctx.fetch_singles()[before:before + inside]
         co = ctx.fetch_coincidences()
     finally:
@@ -142,3 +142,59 @@ def pair_block(npairs, rank, world):
     """Contiguous block of the pairs 0..npairs-1 that rank `rank` transports (decay-index sharding)."""
     lo = npairs * rank // world
     return lo, npairs * (rank + 1) // world - lo
+
+
+def exchange_local(per_rank_events_u8, edges, halo_back, halo_fwd):
+    """The same routing without a process group: `per_rank_events_u8[r]` are rank r's events; returns what each rank would
+    receive (concatenated in source-rank order, as all_to_all_single delivers it).  Used by the single-process tests."""
+    import torch
+    world = len(per_rank_events_u8)
+    parts = [[None] * world for _ in range(world)]
+    for r, ev in enumerate(per_rank_events_u8):
+        ev = ev.contiguous().view(-1, EVENT_BYTES)
+        t = ev.view(torch.float64).view(-1, EVENT_BYTES // 8)[:, T_WORD]
+        for j, ix in enumerate(route_by_time_slice(t, edges, halo_back, halo_fwd)):
+            parts[j][r] = ev[ix]
+    return [torch.cat(p) for p in parts]
+
+
+def run_exchange(ctx, atoms, device, group=None, frame_pairs=0):
+    """ONE acquisition sharded by decays over the ranks, digitized by time slice (the north_star data path).
+
+    `atoms`: the acquisition's atoms per source.  Rank r transports the decays of atoms // world of them (independent
+    binomial thinning of disjoint atom sets = the decays of the whole source, shared out; disjoint Philox subsequences
+    through gpet_set_first_pair) over the WHOLE time window, frame by frame; per frame the post-readout events are
+    exchanged by time slice (all-to-all-v over NCCL, device to device) and every rank digitizes its slice of the frame.
+    Returns a dict of this rank's tallies (pairs, events sent / received, singles, coincidences, halo flag, bytes sent)."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    for i, n in enumerate(atoms):
+        ctx.set_source_atoms(i, int(n) // world)      # equal shares: every rank plans the very same time slices
+    ctx.set_first_pair(rank << 40)
+    ctx.set_shard(0, 1)
+    # the frame plan must be the same time slices on every rank: plan with the capacity a rank's share needs
+    nframes = ctx.plan_frames(frame_pairs)
+    dig = ctx.get_digitizer()
+    hb, hf = halo_for(dig.dead_time_us, dig.coinc_window_us)
+    out = dict(pairs=0, events=0, received=0, singles=0, coincidences=0, halo_flag=0, bytes_sent=0, frames=nframes)
+    buf = torch.empty((1 << 22, EVENT_BYTES), dtype=torch.uint8, device=device)
+    for f in range(nframes):
+        fr = ctx.frame(f)
+        ctx.stage_front(f)
+        ctx.stage_panel_transport()
+        n = ctx.copy_events_to_device(buf.data_ptr(), buf.shape[0])
+        edges = slice_edges(fr["t0_s"] * 1e6, (fr["t0_s"] + fr["dt_s"]) * 1e6, world)
+        recv, sent = exchange_events(buf[:n], edges, hb, hf, group=group)
+        lo, hi = float(edges[rank]), float(edges[rank + 1])
+        ctx.set_emit_window(lo, hi, float("-inf") if rank == 0 else lo - hb)
+        ctx.put_events_device(recv.data_ptr() if recv.numel() else 0, recv.shape[0])
+        ctx.stage_digitize()
+        before, inside, flag, nco = ctx.emit_counts()
+        out["pairs"] += ctx.frame_pairs(f); out["events"] += int(n); out["received"] += int(recv.shape[0])
+        out["singles"] += inside; out["coincidences"] += nco
+        out["halo_flag"] |= flag; out["bytes_sent"] += sent
+    ctx.clear_emit_window()
+    ctx.set_first_pair(0)
+    return out

@@ -338,7 +338,7 @@ int gpet_set_shard(gpet_ctx* ctx, int rank, int world);
  * earlier raise counts[2] (halo too short) instead of being silently wrong. */
 int gpet_set_emit_window(gpet_ctx* ctx, double lo_us, double hi_us, double halo_start_us);
 int gpet_clear_emit_window(gpet_ctx* ctx);
-int gpet_get_emit_counts(gpet_ctx* ctx, uint64_t counts[3]);
+int gpet_get_emit_counts(gpet_ctx* ctx, uint64_t counts[4]);   /* before, inside, halo too short, coincidences emitted */
 /* The event buffer <-> caller-owned DEVICE memory (48-byte records), for exchanges between GPUs that never touch the host. */
 int64_t gpet_copy_events_to_device(gpet_ctx* ctx, void* dst_device, int64_t cap);
 int gpet_put_events_device(gpet_ctx* ctx, const void* src_device, int64_t n);

@@ -98,3 +98,72 @@ def test_owned_frames_rule():
     for world in (1, 2, 3, 8):
         cover = sorted(f for r in range(world) for f in multi.owned_frames(37, r, world))
         assert cover == list(range(37))
+
+
+# ------------------------------------------------------------------------------------------------ exchange by time slice
+def _slice_of(singles, co, lo, hi):
+    """what a rank keeps of the digitization of its list: the singles of its slice, the coincidences opened in it"""
+    s = singles[(singles["t"] >= lo) & (singles["t"] < hi)]
+    c = co[(co["a"]["t"] >= lo) & (co["a"]["t"] < hi)]
+    return s, c
+
+
+def _exchange_worker(rank, world, port, q, n_events, dead_type, dead_level):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT / "tests"))
+    import parity
+    from gpet_b200 import api, multi
+    from oracle import oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # the same list on every rank; rank r "transported" the photons with parn % world == r
+        rng = np.random.default_rng(99)
+        T = 3.0e4
+        ev = parity.random_events(n_events, rng, tmax=T, dead_fraction=0.01)
+        p, d = parity.make_digi_params(dead_type=dead_type, dead_level=dead_level, dead_time_us=2.2, coinc_window_us=0.5, coinc_policy=1,
+                                       blur_Rref=0.05)
+        mine = np.ascontiguousarray(ev[ev["parn"] % world == rank])
+        edges = multi.slice_edges(0.0, T, world)
+        hb, hf = multi.halo_for(d["dead_time_us"], d["coinc_window_us"])
+        recv, sent = multi.exchange_events(torch.from_numpy(mine.view(np.uint8).reshape(-1, 48)), edges, hb, hf)
+        got = np.ascontiguousarray(recv.numpy()).view(api.EVENT_DTYPE).reshape(-1)
+        singles, counts, co = orc.digitize(got, p)
+        s, c = _slice_of(singles, co, edges[rank], edges[rank + 1])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (s.tobytes(), c.tobytes(), got.size, sent))
+        if rank == 0:
+            want_s, _, want_c = orc.digitize(ev, p)
+            s_all = b"".join(g[0] for g in gathered)
+            c_all = b"".join(g[1] for g in gathered)
+            received = [g[2] for g in gathered]
+            q.put((s_all == want_s.tobytes(), c_all == want_c.tobytes(), want_s.size, want_c.size, received, int((ev["t"] < 1e19).sum()),
+                   [g[3] for g in gathered]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dead_type,dead_level", [(0, 3), (1, 2)])
+def test_time_slice_exchange_with_halo_reproduces_the_single_list_digitization(dead_type, dead_level):
+    """Decay-index sharding: the ranks' events are exchanged by time slice with a dead-time / coincidence-window
+    halo over the process group (gloo here, NCCL on GPUs); each rank digitizes its list and keeps its slice.  With the
+    oracle as the digitizer, the union over the ranks must be the digitization of ALL events as one list, byte for byte:
+    singles (dead time per site across the cuts) and coincidences (windows across the cuts)."""
+    import torch.multiprocessing as mp
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, q, 60000, dead_type, dead_level)) for r in range(world)]
+    for p in procs:
+        p.start()
+    same_s, same_c, ns, nc, received, alive, sent = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ns > 15000 and nc > 100
+    assert same_s and same_c
+    # every live event reaches its slice's owner once, plus the halo copies: a few per cent of traffic, not a broadcast
+    assert alive <= sum(received) < 1.1 * alive and all(s > 0 for s in sent)

@@ -10,7 +10,9 @@ def load(path):
         lines = [l for l in f if not l.startswith("==")]
     rows = []
     for row in csv.DictReader(lines):
-        v = float(row["Metric Value"])
+        if row["Metric Name"] != "gpu__time_duration.sum":   # lists taken with DRAM byte counts carry three rows per launch
+            continue
+        v = float(row["Metric Value"].replace(",", ""))
         if row["Metric Unit"] in ("ns", "nsecond"):
             v /= 1000.0
         elif row["Metric Unit"] in ("ms", "msecond"):
@@ -26,7 +28,7 @@ def short(name):
 
 def main():
     rows = load(sys.argv[1])
-    marker = sys.argv[3] if len(sys.argv) > 3 else "k_source"
+    marker = sys.argv[3] if len(sys.argv) > 3 else "k_front"
     idx = [i for i, x in enumerate(rows) if marker in x[0]]
     k = int(sys.argv[2]) if len(sys.argv) > 2 else max(0, len(idx) - 3)
     a, b = idx[k], idx[k + 1] if k + 1 < len(idx) else len(rows)
