@@ -148,8 +148,8 @@ def exchange_local(per_rank_events_u8, edges, halo_back, halo_fwd):
     """The same routing without a process group: `per_rank_events_u8[r]` are rank r's events; returns what each rank would
     receive (concatenated in source-rank order, as all_to_all_single delivers it).  Used by the single-process tests."""
     import torch
-    world = len(per_rank_events_u8)
-    parts = [[None] * world for _ in range(world)]
+    world, ndest = len(per_rank_events_u8), len(edges) - 1
+    parts = [[None] * world for _ in range(ndest)]
     for r, ev in enumerate(per_rank_events_u8):
         ev = ev.contiguous().view(-1, EVENT_BYTES)
         t = ev.view(torch.float64).view(-1, EVENT_BYTES // 8)[:, T_WORD]

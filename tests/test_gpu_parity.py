@@ -927,8 +927,7 @@ def test_time_slice_exchange_through_the_cuda_digitizer_equals_one_list(ctx, dea
     rng = np.random.default_rng(321)
     T = 5.0e4
     ev = parity.random_events(150000, rng, tmax=T, dead_fraction=0.01)
-    p, d = parity.make_digi_params(dead_type=dead_type, dead_level=dead_level, dead_time_us=2.2, coinc_window_us=0.5, coinc_policy=1,
-                                   blur_Rref=0.05)
+    p, d = parity.make_digi_params(dead_type=dead_type, dead_level=dead_level, dead_time_us=2.2, coinc_window_us=0.5, coinc_policy=1)
     parity.apply_digi_params(ctx, d)
     want_s, want_counts = ctx.digitize(ev)
     want_c = ctx.fetch_coincidences()

@@ -1,6 +1,8 @@
 """CPU suite (-m "not gpu"): pins the oracle on known-answer vectors, checks the host loaders against the independent
 numpy parsers, and checks that the C-ABI library loads and exports every declared symbol.  No compute calls."""
 import ctypes
+import os
+from pathlib import Path
 import re
 import subprocess
 
@@ -635,3 +637,76 @@ def test_cli_rejects_missing_argument():
         pytest.skip("CLI not built")
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 1 and "input_file" in r.stdout  # main.cu:28-33
+
+
+REF = Path("/root/reference")
+
+
+@pytest.mark.skipif(not (REF / "input_PET.in").exists(), reason="the reference checkout is not on this box (GPU box): the CPU suite runs where it is")
+def test_reference_input_files_verbatim(tmp_path):
+    """The reference's OWN input_PET.in, input/config8.geo, input/source.txt, input/pointsource.txt and data/isotopes.txt,
+    read where they lie (never copied): the product's loaders must parse them, and the relabelled copies under
+    examples/small_animal/ must carry exactly the same values."""
+    ref_cfg = refio.parse_config(REF / "input_PET.in")
+    ex_cfg = refio.parse_config(parity.EXAMPLE / "input_PET.in")
+    assert ref_cfg == ex_cfg
+    # the product's config parser on the reference's file: every field, via a work directory that links the reference's files
+    ex = tmp_path / "ex"
+    (ex / "input").mkdir(parents=True); (ex / "data").mkdir()
+    os.symlink(REF / "input_PET.in", ex / "input_PET.in")
+    for f in ("config8.geo", "pointsource.txt", "source.txt"):
+        os.symlink(REF / "input" / f, ex / "input" / f)
+    os.symlink(REF / "data" / "isotopes.txt", ex / "data" / "isotopes.txt")
+    mat, den = parity.gen_inputs.cylinder_phantom(n=200)        # the phantom blobs are not shipped (SURVEY F6)
+    parity.gen_inputs.write_phantom(mat, den, ex / ref_cfg["matfile"], ex / ref_cfg["denfile"])
+    with api.Context(device=-1) as c, api.Context(device=-1) as e:
+        for ctx_, root in ((c, REF), (e, parity.EXAMPLE)):
+            ctx_.load_geometry(root / "input" / "config8.geo")
+            ctx_.load_isotopes(root / "data" / "isotopes.txt")
+        assert c.panels().tobytes() == e.panels().tobytes() and c.panels().size == 8
+        assert [list(x) if hasattr(x, "__len__") else x for x in c.geometry_counts()[0]] == [9, 8, 117, 64]
+        for a, b in zip(c.isotopes(), e.isotopes()):
+            assert a["halftime"] == b["halftime"] and a["ratio"] == b["ratio"] and np.array_equal(a["coef"], b["coef"])
+        for name in ("source.txt", "pointsource.txt"):
+            c.load_source(REF / "input" / name); e.load_source(parity.EXAMPLE / "input" / name)
+            assert len(c.sources()) == len(e.sources()) > 0
+            for a, b in zip(c.sources(), e.sources()):
+                assert a["natom"] == b["natom"] and a["type"] == b["type"] and a["shape"] == b["shape"] and np.array_equal(a["coeff"], b["coeff"])
+        if parity.have_tables():
+            os.symlink(parity.PACKED, ex / "data" / "input4gPET.gpettab")
+            c.load_config_file(ex / "input_PET.in", base_dir=ex)           # the whole init chain on the reference's file
+            d, t = c.get_digitizer(), c.get_transport()
+            assert (d.readout_depth, d.readout_policy, d.dead_level, d.dead_type) == (ref_cfg["rdepth"], ref_cfg["rpolicy"], ref_cfg["dlevel"], ref_cfg["dtype"])
+            assert d.threshold_eV == ref_cfg["Eth"] and d.ewin_min == ref_cfg["Ewinmin"] and d.ewin_max == ref_cfg["Ewinmax"]
+            assert abs(d.dead_time_us - ref_cfg["dtime"]) < 1e-6 and abs(d.blur_Rref - ref_cfg["Rref"]) < 1e-7
+            assert abs(t.noncollinearity_rad - ref_cfg["nonangle"]) < 1e-9 and t.eabs_eV == ref_cfg["eabsph"]
+            assert c.sources()[0]["natom"] == 1762974000          # input_PET.in points at pointsource.txt (SURVEY F7)
+            assert c.plan_frames(0) >= 1
+        assert api.lib().gpet_peek_config_device(str(REF / "input_PET.in").encode()) == ref_cfg.get("device", 0)
+
+
+def test_division_by_a_shared_reciprocal_is_the_ieee_quotient():
+    """k_detector forms the three centroid quotients of an adder / readout merge from ONE correctly rounded reciprocal
+    (q = RN(a * rcp); RN(q + (a - b q) * rcp), transport.cu div_rcp) and crystalSearch's four divisions from reciprocals
+    that come with the panel.  The identity with IEEE division, emulated here in exact arithmetic, on the operand ranges
+    that occur: energies 1e3 .. 2e6 eV, coordinates of a few cm, the module and crystal pitches of the panel files."""
+    rng = np.random.default_rng(0)
+    n = 4_000_000
+
+    def via_rcp(a, b, rcp):
+        q0 = (a * rcp).astype(np.float32)
+        rem = (a.astype(np.float64) - b.astype(np.float64) * q0.astype(np.float64)).astype(np.float32)      # fma: one rounding
+        return (q0.astype(np.float64) + rem.astype(np.float64) * rcp.astype(np.float64)).astype(np.float32)
+
+    es = rng.uniform(1.0e3, 2.2e6, n).astype(np.float32)
+    a = (rng.uniform(-25, 25, n).astype(np.float32) * es * rng.uniform(0.05, 1.0, n).astype(np.float32)).astype(np.float32)
+    rcp = (np.float32(1.0) / es).astype(np.float32)
+    assert np.array_equal(via_rcp(a, es, rcp), (a / es).astype(np.float32))
+    for pitch in (np.float32(1.75) + np.float32(0.02), np.float32(0.21) + np.float32(0.01), np.float32(3.2) + np.float32(0.05)):
+        d = np.full(n, pitch, np.float32)
+        r = np.full(n, np.float32(np.longdouble(1.0) / np.longdouble(pitch)), np.float32)
+        y = rng.uniform(0.0, 30.0, n).astype(np.float32)
+        k = np.arange(0, 130, dtype=np.float32) * pitch
+        # multiples of the pitch and their neighbours (y = half the panel width + a coordinate: zero or a normal number, never denormal)
+        y[:389] = np.concatenate([k, np.nextafter(k[1:], np.float32(1e9)), np.nextafter(k[1:], np.float32(-1e9)), [np.float32(0.0)]])
+        assert np.array_equal(via_rcp(y, d, r), (y / d).astype(np.float32))
