@@ -147,6 +147,7 @@ void fill_source_dev(const Sources& src, const Isotopes& iso, const FramePlan& f
         d.tau_s[i] = (double)iso.halftime[src.type[i]] * 1.442695;
         d.frac[i] = -std::expm1(-fp.dt_s / d.tau_s[i]);
     }
+    for (int i = ns; i < 64; i++) d.cum_pairs[i] = cum;   // padding of the binary search in source_pair (transport.cu)
     for (int k = 0; k < iso.n() * 8 && k < 128; k++) d.iso_coef[k] = iso.coef[k];
     d.t0_s = fp.t0_s;
     d.first_pair = fp.first_pair;

@@ -232,17 +232,31 @@ __device__ __forceinline__ void store_photon(const PhotonQueue& q, unsigned slot
 // sampled direction, photon b is the acollinear partner; they share the point and the time.
 __device__ __forceinline__ void source_pair(const SourceDev* __restrict__ fr, const PhantomDev& ph, uint64_t seed,
                                             unsigned long long k, Photon& a, Photon& b) {
-    // source of pair k = number of inclusive prefix sums at or below k (monotone table): independent loads, no
-    // dependent chain through up to nsource iterations
+    // source of pair k = number of inclusive prefix sums at or below k: branch-free binary search over the table padded to 64
+    // entries (the prefix sums of the unused entries equal the frame's total, fill_source_dev), 6 steps whatever nsource is
     int s = 0;
-    for (int i = 0; i < fr->nsource - 1; i++) s += k >= fr->cum_pairs[i] ? 1 : 0;
+#pragma unroll
+    for (int step = 32; step > 0; step >>= 1) s += (k >= __ldg(&fr->cum_pairs[s + step - 1])) ? step : 0;
+    s = min(s, fr->nsource - 1);
     const unsigned long long gk = fr->first_pair + k;
     Philox rng(seed, gk, (uint32_t)kStageSource << 24);
     uint4 r0 = rng.next();
     // truncated-exponential decay time inside the frame (statistically identical to the reference's per-atom
-    // test ptime = -T_half*1.442695*log(U) < slice, gPET_kernals.cu:519-521)
+    // test ptime = -T_half*1.442695*log(U) < slice, gPET_kernals.cu:519-521): ptime = -tau log(1 - u frac).  A frame is short
+    // against the mean life (frac = 1 - exp(-dt / tau) ~ 1e-2 for F-18 and the 120 s window), where the series of
+    // -log1p(-x) = x + x^2/2 + ... converges to double precision in ten terms: ten DFMAs instead of the ~150 instructions
+    // of log1p (3 % of this kernel); longer frames / short-lived isotopes keep log1p
     double ud = u01d(r0.x, r0.y);
-    double ptime = -fr->tau_s[s] * log1p(-ud * fr->frac[s]);
+    const double xq = ud * fr->frac[s];
+    double ptime;
+    if (xq < 0.03) {
+        double acc = 1.0 / 11.0;
+#pragma unroll
+        for (int n = 10; n >= 1; n--) acc = fma(acc, xq, 1.0 / (double)n);
+        ptime = fr->tau_s[s] * (acc * xq);
+    } else {
+        ptime = -fr->tau_s[s] * log1p(-xq);
+    }
     double t_us = (fr->t0_s + ptime) * 1e6;
     uint4 r1 = rng.next();
     float x, y, z;
@@ -483,7 +497,10 @@ __device__ __forceinline__ bool panel_entry_one(const PanelDev& pd, int i, const
     if (!(fabsf(z2) < pd.lz / 2)) return false;
     pe = make_float4(0.f, y2, z2, p.E);
     ov = make_float4(lvx, lvy, lvz, __int_as_float(i));
-    t = p.t + (-(double)lx / (kSpeedOfLight * (double)lvx));
+    // flight time to the face: the reference divides in fp64, -lx / (c lvx) (gPET_kernals.cu:1003); the fp32 quotient q is
+    // already at hand and good to 6e-8 of a sub-nanosecond flight, so the time path keeps its double accumulation without the
+    // fp64 divide (2.75 % of k_front's instructions at 11 lanes)
+    t = p.t - (double)q * kInvSpeedOfLight;
     return true;
 }
 

@@ -956,24 +956,29 @@ def test_time_slice_exchange_through_the_cuda_digitizer_equals_one_list(ctx, dea
 
 
 def test_a_halo_that_is_too_short_is_reported_not_silently_wrong(ctx):
-    """Non-paralyzable dead time with a long tau: chains of kills run across the cut.  With a halo of one dead time the
-    digitizer cannot know where such a chain started and must say so (emit_counts()[2]); with a long halo it is exact."""
+    """Non-paralyzable dead time with a long tau: chains of kills run across the cut.  A halo shorter than one dead time is
+    refused outright; with a halo of two dead times the digitizer cannot always know where a chain started and must then
+    say so (emit_counts()[2]) -- flagged or exact, never silently wrong; with a long halo it is exact and says nothing."""
     from gpet_b200 import multi
     rng = np.random.default_rng(5)
     T = 2.0e4
-    ev = parity.random_events(60000, rng, tmax=T, nsites=8)
-    ev["siten"] = ev["pann"]                                                # 8 busy sites
+    ev = parity.random_events(9000, rng, tmax=T, nsites=8)                  # ~1.5 events per dead time and site
+    ev["siten"] = ev["pann"]
     p, d = parity.make_digi_params(dead_type=1, dead_level=1, dead_time_us=40.0, coinc_window_us=0.5)
     parity.apply_digi_params(ctx, d)
-    want_s, _ = ctx.digitize(ev)
+    want_s, counts = ctx.digitize(ev)
+    assert counts[1] - counts[2] > 1000                                     # dead time really kills
     edges = multi.slice_edges(0.0, T, 2)
-    for chains, expect_flag in ((1.0, True), (64.0, False)):
+    with pytest.raises(api.GpetError):
+        ctx.set_emit_window(float(edges[1]), float(edges[2]), float(edges[1]) - 39.0)
+    flags = {}
+    for chains in (2.0, 64.0):
         hb, hf = multi.halo_for(d["dead_time_us"], d["coinc_window_us"], chains=chains)
         lists = multi.exchange_local([_as_u8(ev)], edges, hb, hf)
         s1, _, flag = multi.digitize_slice(ctx, lists[1].cuda(), edges, 1, hb)
-        assert bool(flag) == expect_flag
-        if not expect_flag:
-            assert s1.tobytes() == want_s[want_s["t"] >= edges[1]].tobytes()
+        flags[chains] = flag
+        assert flag or s1.tobytes() == want_s[want_s["t"] >= edges[1]].tobytes(), chains
+    assert flags[64.0] == 0
     ctx.clear_emit_window()
 
 

@@ -469,6 +469,44 @@ def test_surface_generator_reproduces_shipped_ctd_surfaces():
     assert np.abs(r - rl["surf"][k])[:, :2].max() < 0.004  # low energies: exact; higher: the shipped table is coarse
 
 
+@pytest.mark.skipif(not (REF / "data" / "input4gCTD.cmpsf").exists(), reason="reference checkout not present")
+def test_mixing_rule_recovers_elements_and_reproduces_shipped_compound_blocks():
+    """tools/gen_tables.py builds the S(q) / F(q) of the PET materials that have no shipped block (CorticalBone, Pb, the
+    tissues) by the additivity rule from elemental functions recovered from the shipped compounds.  The rule
+    is checked on what IS shipped: the recovered H, C, O are atoms (S -> Z at large q, F(0)^2 = Z^2), and TissueICRP --
+    thirteen elements, N recovered from air, nine minor ones Thomas-Fermi scaled -- comes out of the mix within 1 %."""
+    from tools import gen_tables as g
+    ctd = refio.read_matter(REF / "data" / "input4gCTD.matter")
+    cm = refio.read_surface(REF / "data" / "input4gCTD.cmpsf", ctd["nmat"])
+    rl = refio.read_surface(REF / "data" / "input4gCTD.rayff", ctd["nmat"])
+    q = cm["sq"][0][:, 0].astype(np.float64)
+    S = {n: cm["sq"][i][:, 2].astype(np.float64) for i, n in enumerate(ctd["names"])}
+    F2 = {n: rl["sq"][i][:, 2].astype(np.float64) ** 2 for i, n in enumerate(ctd["names"])}
+    comp = g.read_compositions(REF / "data" / "input4gCTD.matter")
+    assert comp["Water"] == [(1, 2.0), (8, 1.0)] and comp["LSO"] == [(71, 2.0), (14, 1.0), (8, 5.0)]
+    el = g.elemental_functions(q, S, F2, comp)
+    for z in (1, 6, 7, 8, 71):
+        assert abs(el[z][0][-1] - z) < 0.02 * z and abs(np.sqrt(el[z][1][0]) - z) < 0.02 * z, z      # S(inf) = Z, F(0) = Z
+        assert np.all(np.diff(el[z][0]) > -5e-3 * z)                                              # S grows with q (to the 6 digits of the files)
+    s, f = g.mix(el, comp["TissueICRP"])
+    F = np.sqrt(F2["TissueICRP"])
+    assert np.max(np.abs(s / S["TissueICRP"] - 1.0)) < 0.01
+    big = F2["TissueICRP"] > 1e-3 * F2["TissueICRP"][0]
+    assert np.max(np.abs(f[big] / F[big] - 1.0)) < 0.01
+    # the compounds the elements were solved from come back exactly
+    for name in ("Water", "PE", "PMMA", "DryAir", "LSO", "LYSO"):
+        s, f = g.mix(el, comp[name])
+        # (up to the clipping of the 6-digit noise in the far tails, where the solved elemental values would dip below zero)
+        assert np.allclose(s, S[name], rtol=1e-5, atol=1e-5 * S[name][-1]) and np.allclose(f * f, F2[name], rtol=1e-5, atol=1e-5 * F2[name][0]), name
+    # what the PET set gets: shipped blocks verbatim, the rest mixed, bone and lead flagged as Thomas-Fermi scaled
+    blocks, pet = g.material_blocks(REF / "data")
+    how = {n: h for n, _, _, h in blocks}
+    assert [n for n, *_ in blocks] == list(pet["names"]) and how["Water"] == how["LSO"] == "shipped block"
+    assert "Thomas-Fermi" in how["CorticalBone"] and "20" in how["CorticalBone"] and "82" in how["Pb"]
+    bone = dict((n, (a, b)) for n, a, b, _ in blocks)["CorticalBone"]
+    assert abs(bone[0][-1, 2] - 5.288227) < 1e-3          # S -> total Z per molecule of the matter file
+
+
 @pytest.mark.skipif(not parity.have_tables(), reason="packed tables not built")
 def test_packed_pet_tables_are_sane():
     with api.Context(device=-1) as c:
@@ -639,7 +677,6 @@ def test_cli_rejects_missing_argument():
     assert r.returncode == 1 and "input_file" in r.stdout  # main.cu:28-33
 
 
-REF = Path("/root/reference")
 
 
 @pytest.mark.skipif(not (REF / "input_PET.in").exists(), reason="the reference checkout is not on this box (GPU box): the CPU suite runs where it is")
