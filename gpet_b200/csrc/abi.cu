@@ -253,7 +253,9 @@ int upload_phantom(gpet_ctx* c) {
     const Phantom& ph = c->ph;
     const size_t n = ph.nvox();
     std::vector<uint32_t> vox(n);
+    c->ph_present.assign(16, 0);
     for (size_t k = 0; k < n; k++) {
+        if (ph.mat[k] >= 0 && ph.mat[k] < 16) c->ph_present[(size_t)ph.mat[k]] = 1;
         uint32_t b;
         float d = ph.dens[k];
         memcpy(&b, &d, 4);
@@ -278,6 +280,24 @@ PhantomDev phantom_dev(const gpet_ctx* c) {
     d.dx = ph.d[0]; d.dy = ph.d[1]; d.dz = ph.d[2];
     d.rec_on = c->tr.record_psf != 0;
     for (int i = 0; i < 4; i++) d.rec[i] = c->tr.record_sphere[i];
+    // shared-memory table staging (GPET_SMEM_TABLES): the materials present in the phantom, if they fit three slots, and the
+    // energy nodes up to 600 keV (annihilation photons never exceed 511 keV (1 + a few acollinearity sigmas))
+    d.tab_nstage = 0;
+    d.tab_slot_map = ~0ull;
+    if (c->tab.loaded() && c->tab.nen > 1) {
+        bool present[16] = {};
+        int npresent = 0;
+        for (int m = 0; m < 16 && m < (int)c->ph_present.size(); m++)
+            if (c->ph_present[m]) { present[m] = true; npresent++; }
+        if (npresent >= 1 && npresent <= 3) {
+            const float e0 = c->tab.energy.front(), e1 = c->tab.energy.back();
+            const float ide = (float)(c->tab.nen - 1) / (e1 - e0);
+            d.tab_nstage = std::min(c->tab.nen, (int)(ide * (600.0e3f - e0)) + 2);
+            int slot = 0;
+            for (int m = 0; m < 16; m++)
+                if (present[m]) d.tab_slot_map = (d.tab_slot_map & ~(15ull << (4 * m))) | ((unsigned long long)slot++ << (4 * m));
+        }
+    }
     return d;
 }
 

@@ -44,6 +44,7 @@ struct gpet_ctx {
     gpet_transport_params tr{};
     float tstart = 0.f, tend = 1.f;
     std::vector<float> maj_ph, maj_det;
+    std::vector<char> ph_present;           // material ids present in the uploaded phantom (shared-memory table staging)
     int rank = 0, world = 1;
     bool emit_on = false;                   // gpet_set_emit_window: digitize a time slice with its halo
     double emit_lo = 0.0, emit_hi = 0.0, emit_trust = 0.0;

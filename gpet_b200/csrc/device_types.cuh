@@ -140,6 +140,10 @@ struct PhantomDev {
     // scatter tags, set for the fused front end only (see DetectorDev::scat_tag; the staged path tags at panel entry)
     unsigned char* scat_tag;
     unsigned scat_mask, scat_serial;
+    // shared-memory staging of the 1-D tables in the fused front end (transport.cu TabShared): energy nodes staged (0: off) and
+    // 4 bits per material id with its slot (15: not staged); set by the host from the materials present in the phantom
+    int tab_nstage;
+    unsigned long long tab_slot_map;
 };
 
 struct TablesDev {

@@ -334,11 +334,39 @@ __device__ __forceinline__ void mark_scattered(const DetectorDev& det, int parn,
 // One Woodcock flight (gPET_kernals.cu:277-335).  Returns 0: still inside, 1: the photon leaves the stage alive (escaped,
 // keeping the overshoot position -- SURVEY quirk 2 -- or below the absorption energy after a Compton, which the reference
 // still hands to the detector stage -- quirk 3), 2: photo-absorbed (tof = -0.5 in the reference).
-__device__ __forceinline__ int phantom_flight(Photon& p, Philox& rng, const PhantomDev& ph, const TablesDev& tb, float eabs) {
+// Where the flight reads its 1-D tables (majorant, cross sections of the voxel's material) from.  TabGlobal: the read-only
+// path (L1 / L2), as the reference reads its linear-filter textures (initialize.cu:425-428).  TabShared: per-block copies in
+// shared memory of the majorant and of the float4 rows of up to kSmemMats materials present in the phantom, for the energy
+// nodes photons can have (below ~600 keV); anything else falls through to the read-only path.  Same values either way.
+constexpr int kSmemMats = 3;
+struct TabGlobal {
+    const TablesDev& tb;
+    __device__ __forceinline__ float maj(int i) const { return __ldg(tb.maj_phantom + i); }
+    __device__ __forceinline__ float4 xs(int mat, int i) const { return __ldg(tb.xs + (size_t)mat * tb.nen + i); }
+};
+struct TabShared {
+    const TablesDev& tb;
+    const float* s_maj;
+    const float4* s_xs;
+    int nstage;
+    unsigned long long slot_map;   // 4 bits per material id: its slot in s_xs, 15 = not staged
+    __device__ __forceinline__ float maj(int i) const { return i < nstage ? s_maj[i] : __ldg(tb.maj_phantom + i); }
+    __device__ __forceinline__ float4 xs(int mat, int i) const {
+        const unsigned sl = (unsigned)(slot_map >> (4 * mat)) & 15u;
+        return (sl < (unsigned)kSmemMats && i < nstage) ? s_xs[sl * nstage + i] : __ldg(tb.xs + (size_t)mat * tb.nen + i);
+    }
+};
+
+template <class Tab>
+__device__ __forceinline__ int phantom_flight(Photon& p, Philox& rng, const PhantomDev& ph, const TablesDev& tb, const Tab& tab, float eabs) {
     uint4 r = rng.next();
     int ie; float fe;
     energy_index(tb, p.E, ie, fe);
-    float lammin = __fdividef(1.0f, lerp_table(tb.maj_phantom, ie, fe));
+    float lammin;
+    {
+        const float a = tab.maj(ie), b = tab.maj(ie + 1);
+        lammin = __fdividef(1.0f, fmaf(fe, b - a, a));
+    }
     float s = -lammin * __logf(u01(r.x));
     p.x = fmaf(s, p.vx, p.x); p.y = fmaf(s, p.vy, p.y); p.z = fmaf(s, p.vz, p.z);
     p.t += (double)s * kInvSpeedOfLight;
@@ -354,7 +382,13 @@ __device__ __forceinline__ int phantom_flight(Photon& p, Philox& rng, const Phan
     uint32_t vw = __ldg(ph.vox + ((size_t)iz * ph.ny + iy) * ph.nx + ix);
     int mat = (int)(vw & 15u);
     float rho = __uint_as_float(vw & ~15u);
-    Xs3 xs = lerp_xs(tb, mat, ie, fe);
+    Xs3 xs;
+    {
+        const float4 a = tab.xs(mat, ie), b = tab.xs(mat, ie + 1);
+        xs.tot = fmaf(fe, b.x - a.x, a.x);
+        xs.compt = fmaf(fe, b.y - a.y, a.y);
+        xs.rayl = fmaf(fe, b.z - a.z, a.z);
+    }
     float lamden = lammin * rho;
     float prob = 1.0f - lamden * xs.tot;
     float u = u01(r.y);
@@ -419,7 +453,7 @@ __global__ void __launch_bounds__(kThreads) k_phantom(PhotonQueue q0, PhotonQueu
         }
         bool done_alive = false;
         if (active) {
-            const int r = phantom_flight(p, rng, ph, tb, eabs);
+            const int r = phantom_flight(p, rng, ph, tb, TabGlobal{tb}, eabs);
             done_alive = r == 1;
             if (r) active = false;
         }
@@ -631,14 +665,16 @@ __global__ void __launch_bounds__(kThreads) k_panel_entry(PhotonQueue q1, Detect
 // Entered photons are staged per warp in shared memory and appended 32 at a time: one atomic on the queue count per
 // flush (warp-aggregated atomics on one line serialise at 0.67 ns each, tools/microbench/latency.cu -- with an append
 // per panel search and the ticket on the same line that was 2/3 of this kernel's time) and full-line stores.
-struct FrontStage {
-    float4 pe[kThreads / 32][32];
-    float4 ov[kThreads / 32][32];
-    double t[kThreads / 32][32];
-    int2 id[kThreads / 32][32];
+template <int NW>
+struct FrontStageT {
+    float4 pe[NW][32];
+    float4 ov[NW][32];
+    double t[NW][32];
+    int2 id[NW][32];
 };
 
-__device__ __forceinline__ void front_flush(FrontStage& st, unsigned warp, unsigned lane, unsigned n, const PhotonQueue& q2) {
+template <class FS>
+__device__ __forceinline__ void front_flush(FS& st, unsigned warp, unsigned lane, unsigned n, const PhotonQueue& q2) {
     __syncwarp();
     unsigned base = 0;
     if (lane == 0) base = atomicAdd(q2.count, n);
@@ -652,16 +688,32 @@ __device__ __forceinline__ void front_flush(FrontStage& st, unsigned warp, unsig
     __syncwarp();
 }
 
-template <bool kFromQueue>
-__global__ void __launch_bounds__(kThreads, 4) k_front(const SourceDev* __restrict__ fr, unsigned long long npairs, PhotonQueue q0,
+// kSmemTab: one block of 1024 threads per SM with the 1-D tables in shared memory (TabShared) instead of four blocks of 256
+// reading them through L1 (TabGlobal): same warps per SM, same registers; an A/B of where the tables live (GPET_SMEM_TABLES)
+constexpr int kFrontThreadsSmem = 1024;
+template <bool kFromQueue, bool kSmemTab>
+__global__ void __launch_bounds__(kSmemTab ? kFrontThreadsSmem : kThreads, kSmemTab ? 1 : 4) k_front(const SourceDev* __restrict__ fr, unsigned long long npairs, PhotonQueue q0,
                                                     PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, uint64_t seed,
                                                     PhotonQueue q2, unsigned* __restrict__ q1_count,
                                                     unsigned* __restrict__ counters, unsigned* __restrict__ ticket, int gen_min,
                                                     int entry_min, unsigned long long id_base_q) {
     extern __shared__ __align__(16) unsigned char s_front[];
+    using FrontStage = FrontStageT<(kSmemTab ? kFrontThreadsSmem : kThreads) / 32>;
     FrontStage& stage = *reinterpret_cast<FrontStage*>(s_front);
     PanelSm* s_panels = reinterpret_cast<PanelSm*>(s_front + sizeof(FrontStage));
-    stage_panels(s_panels, det);
+    // [stage | panels | (kSmemTab) 16-byte aligned: xs rows of the staged materials, then the majorant]
+    const size_t tab_off = (sizeof(FrontStage) + (size_t)det.npanels * sizeof(PanelSm) + 15) & ~(size_t)15;
+    float4* s_xs = reinterpret_cast<float4*>(s_front + tab_off);
+    float* s_maj = reinterpret_cast<float*>(s_xs + (kSmemTab ? kSmemMats * ph.tab_nstage : 0));
+    if (kSmemTab) {
+        for (int i = threadIdx.x; i < ph.tab_nstage; i += blockDim.x) s_maj[i] = __ldg(tb.maj_phantom + i);
+        for (int m = 0; m < 16; m++) {
+            const unsigned sl = (unsigned)(ph.tab_slot_map >> (4 * m)) & 15u;
+            if (sl >= (unsigned)kSmemMats) continue;
+            for (int i = threadIdx.x; i < ph.tab_nstage; i += blockDim.x) s_xs[sl * ph.tab_nstage + i] = __ldg(tb.xs + (size_t)m * tb.nen + i);
+        }
+    }
+    stage_panels(s_panels, det);   // ends with the block barrier that also publishes the tables
     enum { NEED = 0, FLY = 1, ESC = 2 };
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -713,7 +765,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_front(const SourceDev* __restri
             if (base + cnt >= nunits) exhausted = true;
         }
         if (state == FLY) {
-            const int r = phantom_flight(p, rng, ph, tb, eabs);
+            int r;
+            if (kSmemTab) r = phantom_flight(p, rng, ph, tb, TabShared{tb, s_maj, s_xs, ph.tab_nstage, ph.tab_slot_map}, eabs);
+            else r = phantom_flight(p, rng, ph, tb, TabGlobal{tb}, eabs);
             if (r == 1) state = ESC;
             else if (r == 2) state = NEED;
         }
@@ -1366,17 +1420,32 @@ int launch_panel_entry(PhotonQueue q1, PhotonQueue q2, DetectorDev det, unsigned
 int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQueue q0, PhotonQueue q1, PhotonQueue q2,
                  PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, unsigned int* counters, unsigned int* hot, uint64_t seed,
                  unsigned long long id_base, int num_sms, cudaStream_t s, bool reset) {
-    const size_t smem = sizeof(FrontStage) + (size_t)det.npanels * sizeof(PanelSm);
+    // tables in shared memory (A/B, GPET_SMEM_TABLES=1): only when the phantom's materials fit the slots
+    static const int want_smem = tune("GPET_SMEM_TABLES", 0);
+    const bool smem_tab = want_smem && ph.tab_nstage > 0;
+    using FS256 = FrontStageT<kThreads / 32>;
+    using FS1024 = FrontStageT<kFrontThreadsSmem / 32>;
+    size_t smem = (smem_tab ? sizeof(FS1024) : sizeof(FS256)) + (size_t)det.npanels * sizeof(PanelSm);
+    if (smem_tab) smem = ((smem + 15) & ~(size_t)15) + (size_t)ph.tab_nstage * (kSmemMats * sizeof(float4) + sizeof(float));
+    else ph.tab_nstage = 0;
     static ShapeCache sc{};
     const int dev = current_device();
-    if (!sc.grid[dev][0] || sc.smem[dev][0] != smem) {
-        if (smem > 48 * 1024) {
-            cudaFuncSetAttribute(k_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int v = smem_tab ? 2 : 0;
+    if (!sc.grid[dev][v] || sc.smem[dev][v] != smem) {
+        if (smem_tab) {
+            cudaFuncSetAttribute(k_front<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_front<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            sc.grid[dev][2] = persistent_grid(k_front<false, true>, num_sms, smem, kFrontThreadsSmem);
+            sc.grid[dev][3] = persistent_grid(k_front<true, true>, num_sms, smem, kFrontThreadsSmem);
+        } else {
+            if (smem > 48 * 1024) {
+                cudaFuncSetAttribute(k_front<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(k_front<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            }
+            sc.grid[dev][0] = persistent_grid(k_front<false, false>, num_sms, smem);
+            sc.grid[dev][1] = persistent_grid(k_front<true, false>, num_sms, smem);
         }
-        sc.grid[dev][0] = persistent_grid(k_front<false>, num_sms, smem);
-        sc.grid[dev][1] = persistent_grid(k_front<true>, num_sms, smem);
-        sc.smem[dev][0] = smem;
+        sc.smem[dev][v] = smem;
     }
     static const int gen_min = tune("GPET_GEN_MIN", 12), entry_min = tune("GPET_ENTRY_MIN", 12);
     unsigned* ticket = hot + kHotTicketFront;
@@ -1386,12 +1455,15 @@ int launch_front(const SourceDev* frame_dev, unsigned long long npairs, PhotonQu
         cudaMemsetAsync(counters + 8, 0, sizeof(unsigned), s);   // photons on a panel
         cudaMemsetAsync(ticket, 0, sizeof(unsigned), s);
     }
+    const int threads = smem_tab ? kFrontThreadsSmem : kThreads;
     if (frame_dev) {
-        GPET_LAUNCH("k_front", s, k_front<false><<<sc.grid[dev][0], kThreads, smem, s>>>(frame_dev, npairs, q0, ph, tb, det, eabs, seed, q2,
-                                                                                       q1.count, counters, ticket, gen_min, entry_min, 0ull));
+        auto kernel = smem_tab ? k_front<false, true> : k_front<false, false>;
+        GPET_LAUNCH("k_front", s, kernel<<<sc.grid[dev][v], threads, smem, s>>>(frame_dev, npairs, q0, ph, tb, det, eabs, seed, q2,
+                                                                             q1.count, counters, ticket, gen_min, entry_min, 0ull));
     } else {
-        GPET_LAUNCH("k_front<queue>", s, k_front<true><<<sc.grid[dev][1], kThreads, smem, s>>>(nullptr, 0ull, q0, ph, tb, det, eabs, seed, q2,
-                                                                                             q1.count, counters, ticket, gen_min, entry_min, id_base));
+        auto kernel = smem_tab ? k_front<true, true> : k_front<true, false>;
+        GPET_LAUNCH("k_front<queue>", s, kernel<<<sc.grid[dev][v + 1], threads, smem, s>>>(nullptr, 0ull, q0, ph, tb, det, eabs, seed, q2,
+                                                                                         q1.count, counters, ticket, gen_min, entry_min, id_base));
     }
     return 1;
 }

@@ -962,9 +962,8 @@ def test_a_halo_that_is_too_short_is_reported_not_silently_wrong(ctx):
     from gpet_b200 import multi
     rng = np.random.default_rng(5)
     T = 2.0e4
-    ev = parity.random_events(9000, rng, tmax=T, nsites=8)                  # ~1.5 events per dead time and site
-    ev["siten"] = ev["pann"]
-    p, d = parity.make_digi_params(dead_type=1, dead_level=1, dead_time_us=40.0, coinc_window_us=0.5)
+    ev = parity.random_events(9000, rng, tmax=T, nsites=8)                  # 8 modules of panel 0: ~1.3 events per dead time and site
+    p, d = parity.make_digi_params(dead_type=1, dead_level=2, dead_time_us=40.0, coinc_window_us=0.5)
     parity.apply_digi_params(ctx, d)
     want_s, counts = ctx.digitize(ev)
     assert counts[1] - counts[2] > 1000                                     # dead time really kills
