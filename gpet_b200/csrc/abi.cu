@@ -384,6 +384,7 @@ DigitizerDev digitizer_dev(const gpet_ctx* c) {
     d.emit_on = c->emit_on ? 1 : 0;
     d.emit_lo = c->emit_lo; d.emit_hi = c->emit_hi; d.trust_lo = c->emit_trust;
     d.pair_shift = std::min(std::max(p.coinc_pair_shift, 0), 31);
+    d.tie_site = c->in_run ? 1 : 0;
     d.scat_tag = c->d_scat_tag; d.scat_mask = c->scat_mask; d.scat_serial = c->scat_serial;
     return d;
 }

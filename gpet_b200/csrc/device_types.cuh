@@ -193,6 +193,9 @@ struct DigitizerDev {
     double emit_lo, emit_hi, trust_lo;
     // coincidence classes (k_coinc): same annihilation iff eventid >> pair_shift agree; scatter tags as in DetectorDev
     int pair_shift;
+    // equal times: 0 keep the input order (replayed lists: SURVEY quirk 11 as specified), 1 site number first, then input
+    // order (events produced by this run's detector kernel, whose order in the buffer is not defined)
+    int tie_site;
     const unsigned char* scat_tag;
     unsigned scat_mask, scat_serial;
 };

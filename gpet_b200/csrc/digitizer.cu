@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(kThreads) k_bucket_rank(const unsigned long lo
                                                           const uint2* __restrict__ bpay, const unsigned* __restrict__ bstart,
                                                           const unsigned* __restrict__ counters, TimeRange range,
                                                           unsigned long long* __restrict__ tsort, unsigned* __restrict__ order_t,
-                                                          int* __restrict__ site_t) {
+                                                          int* __restrict__ site_t, int tie_site) {
     pdl_wait();
     if (counters[kFlagLsd]) return;
     const unsigned n1 = counters[1];
@@ -430,7 +430,13 @@ __global__ void __launch_bounds__(kThreads) k_bucket_rank(const unsigned long lo
             for (unsigned q = s[u]; q < en[u]; q++) {
                 const unsigned long long kq = bkeys[q];
                 if (kq < key[u]) rank++;
-                else if (kq == key[u] && q != e && (bpay[q].x & ~kEwinBit) < idx) rank++;
+                else if (kq == key[u] && q != e) {
+                    // equal times: input order -- or, for the events of a run (their order in the buffer is whatever the
+                    // detector kernel's atomics made it), site number first, so that a run's singles do not depend on it
+                    const uint2 pq = bpay[q];
+                    if (tie_site && pq.y != pay[u].y) rank += (int)pq.y < (int)pay[u].y ? 1u : 0u;
+                    else if ((pq.x & ~kEwinBit) < idx) rank++;
+                }
             }
             const unsigned pos = s[u] + rank;
             tsort[pos] = key[u];
@@ -1059,7 +1065,7 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
     GPET_LAUNCH("k_bucket_scatter", s, launch_pdl(k_bucket_scatter, g_scatter, kThreads, s, keys, ws.site_of, ws.aux, ws.counters, tr, ws.bstart,
                                                    bkeys, ws.bpay));
     GPET_LAUNCH("k_bucket_rank", s, launch_pdl(k_bucket_rank, g_rank, kThreads, s, bkeys, ws.bpay, ws.bstart, ws.counters, tr, keys, ws.order_t,
-                                                ws.site_t));
+                                                ws.site_t, p.tie_site));
     launches += 4;
     if (with_fallback) {
         static int coop_grid = 0;

@@ -106,6 +106,9 @@ typedef struct {
     float time_blur_sigma_us, coinc_window_us; int32_t coinc_policy, coinc_min_panel_diff;
     int32_t npanels, moduleN, crystalN;
     uint64_t seed;
+    /* equal times: 0 input order; 1 site number first, then input order -- the rule gpet_run applies to the events of its
+     * own detector kernel, whose order in the buffer is not defined (DigitizerDev::tie_site) */
+    int32_t tie_site;
 } orc_digi_params;
 
 /* ------------------------------------------------------------------------------------------------ table lookups */
@@ -728,23 +731,24 @@ static void merge_sort_idx(int64_t* idx, int64_t* tmp, int64_t n, int (*less)(in
         memcpy(idx, tmp, (size_t)n * sizeof(int64_t));
     }
 }
-typedef struct { const orc_event* e; const int64_t* orig; } sort_ctx;
+typedef struct { const orc_event* e; const int64_t* orig; int tie_site; } sort_ctx;
 /* time order; ties are broken by the position in the input list (std::sort in the reference leaves ties undefined) */
 static int less_t(int64_t a, int64_t b, const void* ctx) {
     const sort_ctx* c = (const sort_ctx*)ctx;
     if (c->e[a].t != c->e[b].t) return c->e[a].t < c->e[b].t;
+    if (c->tie_site && c->e[a].siten != c->e[b].siten) return c->e[a].siten < c->e[b].siten;
     return c->orig[a] < c->orig[b];
 }
 static int less_site(int64_t a, int64_t b, const void* ctx) { const sort_ctx* c = (const sort_ctx*)ctx; return c->e[a].siten < c->e[b].siten; }
 
 /* quicksort_h(by t) (detector.cu:354-367) made deterministic; works on the first n records in place.  `orig` carries
  * each record's position in the input list and is permuted along. */
-static void sort_events(orc_event* ev, int64_t* orig, int64_t n, int by_site) {
+static void sort_events(orc_event* ev, int64_t* orig, int64_t n, int by_site, int tie_site) {
     if (n < 2) return;
     int64_t* idx = (int64_t*)malloc(sizeof(int64_t) * (size_t)n * 2);
     orc_event* cp = (orc_event*)malloc(sizeof(orc_event) * (size_t)n);
     int64_t* co = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
-    sort_ctx c = {ev, orig};
+    sort_ctx c = {ev, orig, tie_site};
     for (int64_t i = 0; i < n; i++) idx[i] = i;
     merge_sort_idx(idx, idx + n, n, by_site ? less_site : less_t, &c);
     for (int64_t i = 0; i < n; i++) { cp[i] = ev[idx[i]]; co[i] = orig[idx[i]]; }
@@ -809,7 +813,7 @@ int64_t orc_digitize(const orc_event* in, int64_t n, const orc_digi_params* p, o
             if (work[i].E < p->threshold_eV || work[i].E > 2000000.0f || !(work[i].t < ORC_MAXT * 0.1)) work[i].t = ORC_MAXT;
             else alive++;
         }
-        sort_events(work, orig, cnt, 0);
+        sort_events(work, orig, cnt, 0, 0);   /* ties inside one site stay in input order: the site numbers of the tie rule are set below */
         cnt = alive;
     }
     counts[1] = (uint64_t)cnt;
@@ -822,7 +826,7 @@ int64_t orc_digitize(const orc_event* in, int64_t n, const orc_digi_params* p, o
             else if (p->dead_level == 2) e->siten = e->pann * p->moduleN + e->modn;
         }
     }
-    sort_events(work, orig, cnt, 1);  /* stable by site on a time-sorted list == sort by site, then by t inside each site */
+    sort_events(work, orig, cnt, 1, 0);  /* stable by site on a time-sorted list == sort by site, then by t inside each site */
     /* deadtime (gPET_kernals.cu:657-698), snapshot-start semantics: tdead is float, tdead+tau an fp32 sum */
     {
         const float tau = p->dead_time_us;
@@ -843,7 +847,7 @@ int64_t orc_digitize(const orc_event* in, int64_t n, const orc_digi_params* p, o
             if (kill[i]) work[i].t = ORC_MAXT; else alive++;
         }
         free(kill);
-        sort_events(work, orig, cnt, 0);
+        sort_events(work, orig, cnt, 0, p->tie_site);
         cnt = alive;
     }
     counts[2] = (uint64_t)cnt;
@@ -853,7 +857,7 @@ int64_t orc_digitize(const orc_event* in, int64_t n, const orc_digi_params* p, o
         for (int64_t i = 0; i < cnt; i++) {
             if (work[i].E < p->ewin_min || work[i].E > p->ewin_max) work[i].t = ORC_MAXT; else alive++;
         }
-        sort_events(work, orig, cnt, 0);
+        sort_events(work, orig, cnt, 0, p->tie_site);
         cnt = alive;
     }
     counts[3] = (uint64_t)cnt;

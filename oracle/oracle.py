@@ -39,7 +39,8 @@ class DigiParams(C.Structure):
                 ("ewin_min", C.c_float), ("ewin_max", C.c_float),
                 ("time_blur_sigma_us", C.c_float), ("coinc_window_us", C.c_float),
                 ("coinc_policy", C.c_int32), ("coinc_min_panel_diff", C.c_int32),
-                ("npanels", C.c_int32), ("moduleN", C.c_int32), ("crystalN", C.c_int32), ("seed", C.c_uint64)]
+                ("npanels", C.c_int32), ("moduleN", C.c_int32), ("crystalN", C.c_int32), ("seed", C.c_uint64),
+                ("tie_site", C.c_int32)]
 
 
 _lib = None

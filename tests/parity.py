@@ -31,7 +31,7 @@ def make_digi_params(**kw):
     d = dict(readout_depth=2, readout_policy=1, threshold_eV=50000.0, blur_policy=1, blur_Eref=662000.0, blur_Rref=0.0,
              blur_slope=0.0, blur_space=0.0, dead_level=3, dead_type=0, dead_time_us=2.2, ewin_min=30000.0,
              ewin_max=700000.0, time_blur_sigma_us=0.0, coinc_window_us=0.0, coinc_policy=0, coinc_min_panel_diff=0,
-             npanels=8, moduleN=117, crystalN=64, seed=SEED)
+             npanels=8, moduleN=117, crystalN=64, seed=SEED, tie_site=0)
     d.update(kw)
     p = orc.DigiParams()
     for k, v in d.items():
