@@ -186,10 +186,11 @@ def have_gpu():
 def bench_config(source):
     """The `config` object of BOTH arms (identical keys and values: the driver compares them)."""
     return {"workload": workload_name(source),
-            "step": "our arm: one step = the acquisition with its activity scaled so that every GPU runs FRAMES_PER_STEP frames of ~1.1 M pairs "
-                    "(>= 50 ms of kernels), sharded by frames over the GPUs; reference arm: one step = the acquisition at the shipped activity "
-                    "(1.118 M pairs, a bounded sample of the same workload -- the metric is per pair)",
-            "l2": "working set of a frame (~250 MB of queues, hit / event / sort buffers) exceeds the 126 MB L2; 256 MiB flush between timed steps",
+            "step": "our arm: one step = the acquisition with its activity scaled 160 x per GPU (~179 M pairs per GPU, >= 40 ms of kernels), cut "
+                    "into frames of ~4 M pairs (the frame is this library's batch: per-frame fixed costs amortise with it), sharded by frames over "
+                    "the GPUs; reference arm: one step = the acquisition at the shipped activity (1.118 M pairs, a bounded sample of the same "
+                    "workload -- the metric is per pair)",
+            "l2": "working set of a frame (~1 GB of queues, hit / event / sort buffers) exceeds the 126 MB L2; 256 MiB flush between timed steps",
             "coincidence_window_us": 0.01, "rng": "Philox4x32-10, key 0x67504554, 64-bit history numbers", "time_path": "fp64",
             "multi_gpu": "one acquisition, frames sharded round robin over the ranks (gpet_set_shard), no data-path collective; "
                          "tallies all-reduced once over NCCL after the last step, inside the timed region"}
@@ -259,9 +260,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--source", default=DEFAULT_SOURCE, help="source file of the example (source.txt | pointsource.txt)")
     ap.add_argument("--frames-per-step", type=int, default=160,
-                    help="frames (of ~1.1 M pairs) every GPU runs in one resident step: 160 x 0.34 ms = ~55 ms of kernels")
-    ap.add_argument("--e2e-frames-per-step", type=int, default=16, help="frames per GPU of an end-to-end step (35 MB of results each)")
-    ap.add_argument("--frame-pairs", type=int, default=1_240_000, help="frame capacity in pairs (the planner fills ~0.9 of it)")
+                    help="activity scale per GPU of a resident step: the shipped acquisition (1.118 M pairs) x this = ~179 M pairs, ~50 ms of kernels")
+    ap.add_argument("--e2e-frames-per-step", type=int, default=16, help="activity scale per GPU of an end-to-end step (35 MB of results per 1.118 M pairs)")
+    ap.add_argument("--frame-pairs", type=int, default=4_600_000,
+                    help="frame capacity in pairs (the planner fills ~0.9 of it): per-frame fixed costs amortise with the frame, "
+                         "tools/bigframes_sweep.py -- 314 us per M pairs at 1.1 M pairs a frame, 262 at 4.5 M")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
@@ -303,6 +306,8 @@ def main():
         ex = make_workdir(Path(tmp.name) / sub, source=source)
         ctx = api.Context(local)
         ctx.set_stream(stream.cuda_stream)
+        # buffers for one frame: 2 photons per pair; ~1.01 hits and ~0.66 events per pair on this example (headroom on both)
+        ctx.set_capacity(2 * args.frame_pairs, int(1.3 * args.frame_pairs), int(0.9 * args.frame_pairs))
         ctx.load_config_file(ex / "input_PET.in", base_dir=ex)
         ctx.set_digitizer(coinc_window_us=0.01)
         # coincidences reach the host as index pairs into the singles list (8 B each instead of two copied records)
@@ -473,7 +478,7 @@ def main():
                     "frac": kernels[top]["achieved_gbs"] / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if pk.exists() else "fallback 6650 GB/s (B200_PROFILING.md)",
                     "us_per_launch": kernels[top]["us_per_launch"], "share_of_step": kernels[top]["us_per_frame"] / sum(k["us_per_frame"] for k in kernels.values()),
-                    "timing": "CUDA events bracketing every launch on the launching stream (gpet_profile_enable), 3 runs of 4 frames, L2 flushed between runs",
+                    "timing": "CUDA events bracketing every launch on the launching stream (gpet_profile_enable), 3 runs of the acquisition at 4 x the shipped activity (one frame of ~4.5 M pairs), L2 flushed between runs",
                     "note": "Monte-Carlo transport is latency/issue bound: the algorithmic bytes are tiny against HBM (DESIGN.md section 4); see profiles/ for issue-slot, SIMT-efficiency and pipe numbers",
                     "kernels": kernels}
         base = None
