@@ -417,9 +417,12 @@ def test_run_shipped_example_writes_reference_layouts(tmp_path):
     # replay pin: adder.dat is written BEFORE blur, as the reference does (gPET.cu:383-388); through the digitizer alone, blur
     # on as shipped and the same Philox key, it reproduces singles.dat bit for bit (the blur stream of an event is keyed by
     # its photon and readout site, both in the record)
+    # Equal times: a run orders them by the dead-time site number (the order of adder.dat is whatever the detector kernel's
+    # atomics made it), a replay keeps the input order -- so the replay gets the list in site order (stable: nothing else moves)
+    site = (adder["pann"].astype(np.int64) * 117 + adder["modn"]) * 64 + adder["cryn"]
     with api.Context(0) as c2:
         c2.load_config_file(ex / "input_PET.in", base_dir=ex)
-        again, _ = c2.digitize(adder)
+        again, _ = c2.digitize(adder[np.argsort(site, kind="stable")])
     # the dump really is the unblurred list: the photopeak of the adder is as narrow as the acollinearity leaves it
     # (E = 511 keV (1 +- delta / 2), sigma 0.95 keV), that of the singles carries the 5 % energy blur (sigma 11 keV)
     peak = adder["E"][(adder["E"] > 505e3) & (adder["E"] < 517e3)]
