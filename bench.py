@@ -370,22 +370,32 @@ def main():
         if world > 1:
             dist.barrier()
         total_ms, (pairs, coinc) = reduce_max_sum(sum(times), sum(s.pairs for s in stats), sum(s.coincidences for s in stats))
-        # e2e through gpet_run: planning + all stages + results in pinned host memory, wall clock
+        # e2e through gpet_run: planning + all stages + results in pinned host memory, wall clock.  Singles travel as 32-byte
+        # gpet_single_compact records (the run is bound by their copy; gpet_result_singles rebuilds the 48-byte Event byte for
+        # byte, tests/test_gpu_parity.py); the same run with 48-byte records is measured beside it
         nf_e = plan(ctx, e2e_frames_per_step)
-        timed(ctx, 2, resident=False)
-        if world > 1:
-            dist.barrier()
-        e_times, e_stats = timed(ctx, max(3, min(steps, 10)), resident=False)
-        e_ms, (e_pairs,) = reduce_max_sum(sum(e_times), sum(s.pairs for s in e_stats))
+        e2e = {}
+        for name, fmt in (("records48", api.Context.SINGLES_RECORDS), ("compact32", api.Context.SINGLES_COMPACT)):
+            ctx.set_singles_format(fmt)
+            timed(ctx, 2, resident=False)
+            if world > 1:
+                dist.barrier()
+            e_times, e_stats = timed(ctx, max(3, min(steps, 10)), resident=False)
+            e_ms, (e_pairs,) = reduce_max_sum(sum(e_times), sum(s.pairs for s in e_stats))
+            e2e[name] = (e_ms, e_pairs, e_stats)
+        ctx.set_singles_format(api.Context.SINGLES_RECORDS)
+        e_ms, e_pairs, e_stats = e2e["compact32"]
+        step_ms = [round(x, 3) for x in times]
         return {"total_ms": total_ms, "pairs": pairs, "coinc": coinc, "stats": stats, "frames": nf, "e2e_ms": e_ms, "e2e_pairs": e_pairs,
-                "e2e_stats": e_stats, "e2e_frames": nf_e, "tallies": dict(zip(multi.TALLY_FIELDS, (int(x) for x in tally_dev.tolist())))}
+                "e2e_stats": e_stats, "e2e_frames": nf_e, "e2e_records48": e2e["records48"][1] / (e2e["records48"][0] * 1e-3),
+                "step_ms": step_ms, "tallies": dict(zip(multi.TALLY_FIELDS, (int(x) for x in tally_dev.tolist())))}
 
     ex, ctx = make_ctx(args.source, "main")
     m = measure(ctx, args.steps, args.warmup, args.frames_per_step, args.e2e_frames_per_step)
     value = m["pairs"] / (m["total_ms"] * 1e-3)
     st = m["e2e_stats"][-1]
     h2d = int(st.frames) * 4096 + 64
-    d2h = int(st.singles * 48 + st.coincidences * (8 + 1) + 32 * 4 * st.frames)   # records, index pairs + class bytes, counters
+    d2h = int(st.singles * 32 + st.coincidences * (8 + 1) + 32 * 4 * st.frames)   # compact singles, index pairs + class bytes, counters
 
     # ---- same deliverable as the reference's timed region: adder.dat + singles.dat appended frame by frame (gPET.cu:383, 424;
     # its hit dumps off as in gPET_nodump), wall clock of gpet_run(output_dir).  One GPU only (one host, one file system).
@@ -503,10 +513,12 @@ def main():
                 "details": {"pairs_per_step_per_gpu": m["pairs"] / nsteps / world, "frames_in_the_acquisition": int(m["frames"]),
                             "frames_per_step_per_gpu": int(s0.frames), "activity_scale": args.frames_per_step * world,
                             "e2e_frames_per_step_per_gpu": int(st.frames), "e2e_activity_scale": args.e2e_frames_per_step * world,
-                            "frame_capacity_pairs": args.frame_pairs},
+                            "frame_capacity_pairs": args.frame_pairs, "step_ms_rank0": m["step_ms"]},
                 "clocks": clocks,
                 "e2e": {"value": m["e2e_pairs"] / (m["e2e_ms"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "timing": "wall clock around gpet_run: all stages, singles as 48-byte records and coincidences as index pairs into them plus one class byte each delivered to pinned host memory, the copy of a frame overlapping the kernels of the next; max over ranks"},
+                        "singles_format": "gpet_single_compact, 32 B (GPET_SINGLES_COMPACT: t, E, x, y, z, eventid, packed panel / module / crystal / photon bit; gpet_result_singles expands to the 48-byte Event on demand, byte-identical)",
+                        "with_48_byte_records": {"value": m["e2e_records48"], "unit": UNIT, "d2h_bytes_per_step": int(st.singles * 48 + st.coincidences * 9 + 128 * st.frames)},
+                        "timing": "wall clock around gpet_run: all stages, singles and coincidences (index pairs into the singles plus one class byte each) delivered to pinned host memory, the copy of a frame overlapping the kernels of the next; max over ranks"},
                 "e2e_files": e2e_files,
                 "gpu_launches": int(sum(s.kernel_launches for s in m["stats"])),
                 "roofline": roofline, "cpu_baseline": base,

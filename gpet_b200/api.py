@@ -21,6 +21,9 @@ EVENT_DTYPE = np.dtype(
      ("t", "<f8"), ("E", "<f4"), ("x", "<f4"), ("y", "<f4"), ("z", "<f4")], align=True)
 assert EVENT_DTYPE.itemsize == 48
 COINC_DTYPE = np.dtype([("a", EVENT_DTYPE), ("b", EVENT_DTYPE)], align=True)
+# gpet_single_compact (include/gpet_b200.h): ids = pann | modn << 8 | cryn << 20 | (parn & 1) << 31
+COMPACT_DTYPE = np.dtype([("t", "<f8"), ("E", "<f4"), ("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("eventid", "<i4"), ("ids", "<u4")], align=True)
+assert COMPACT_DTYPE.itemsize == 32
 assert COINC_DTYPE.itemsize == 96
 HIT_DTYPE = np.dtype(
     [("parn", "<i4"), ("pann", "<i4"), ("modn", "<i4"), ("cryn", "<i4"), ("type", "<i4"),
@@ -134,6 +137,8 @@ _SIGS = {
     "gpet_result_singles": (C.c_int64, [_P, C.POINTER(_P)]),
     "gpet_result_coincidences": (C.c_int64, [_P, C.POINTER(_P)]),
     "gpet_set_coincidence_format": (C.c_int, [_P, C.c_int]),
+    "gpet_set_singles_format": (C.c_int, [_P, C.c_int]),
+    "gpet_result_singles_compact": (C.c_int64, [_P, C.POINTER(_P)]),
     "gpet_result_coincidence_pairs": (C.c_int64, [_P, C.POINTER(_P)]),
     "gpet_result_coincidence_classes": (C.c_int64, [_P, C.POINTER(_P)]),
     "gpet_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
@@ -156,7 +161,7 @@ _SIGS = {
 _lib = None
 
 
-ABI_VERSION = 4   # GPET_ABI_VERSION of include/gpet_b200.h
+ABI_VERSION = 5   # GPET_ABI_VERSION of include/gpet_b200.h
 
 
 def lib():
@@ -537,6 +542,20 @@ class Context:
         return np.frombuffer(buf, COINC_DTYPE, n).copy()
 
     COINC_RECORDS, COINC_PAIRS = 0, 1
+    SINGLES_RECORDS, SINGLES_COMPACT = 0, 1
+
+    def set_singles_format(self, fmt):
+        """How run(None) brings singles to the host: 48-byte records, or 32-byte gpet_single_compact records that
+        result_singles() expands on demand (byte-identical)."""
+        self._ck(self._l.gpet_set_singles_format(self._h, int(fmt)))
+
+    def result_singles_compact(self):
+        p = C.c_void_p()
+        n = self._ck(self._l.gpet_result_singles_compact(self._h, C.byref(p)))
+        if n == 0:
+            return np.zeros(0, COMPACT_DTYPE)
+        buf = (C.c_char * (n * COMPACT_DTYPE.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, COMPACT_DTYPE, n).copy()
 
     def set_coincidence_format(self, fmt):
         self._ck(self._l.gpet_set_coincidence_format(self._h, int(fmt)))

@@ -3,6 +3,8 @@
 #include <cmath>
 #include <condition_variable>
 #include <deque>
+#include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <cstdio>
@@ -10,6 +12,10 @@
 #include <cstring>
 #include <string>
 #include <vector>
+
+#include <fcntl.h>
+#include <sys/types.h>
+#include <unistd.h>
 
 #include "ctx.hpp"
 #include "planner.hpp"
@@ -1046,6 +1052,7 @@ int gpet_stage_digitize(gpet_ctx* c) {
     out.singles_cap = (unsigned)c->cap_events;
     out.coinc_cap = c->coinc_cap;
     out.cls = c->cls_aos;
+    if (c->in_run && c->run_compact) out.singles_compact = c->compact_slot[c->out_slot];
     if (c->in_run && c->early_copy) {
         out.h_singles_count = c->h_slot_counters[c->out_slot] + 48;   // a spare word of the slot's pinned block
         out.ev_after_emit = c->ev_emit[c->out_slot];
@@ -1323,74 +1330,103 @@ constexpr int kRetryWithFallback = 1;   // internal: run_attempt() asks run_impl
 // magnitude) overlaps the kernels and copies of the following frames.  A job whose data is still in flight carries the
 // event that marks the end of its copy.
 struct FileWriter {
-    struct Job { std::string path; const char* p; size_t n; cudaEvent_t ready; };
-    std::thread th;
+    // Appends to the output files in the background: a pool of threads writes 8 MB chunks at their final offsets (pwrite), so one
+    // frame's adder.dat / singles.dat go to the page cache at several times the rate of one thread's write() loop.  The first push
+    // of a path opens it and takes its size as the offset (append semantics, the reference's ios::app, detector.cu:287-307); the
+    // writer is the file's only writer until it is destroyed.
+    static constexpr int kWorkers = 4;
+    static constexpr size_t kChunk = 8u << 20;
+    struct Ready {   // a CUDA event the chunks of one push wait for; destroyed with the last of them
+        cudaEvent_t ev;
+        explicit Ready(cudaEvent_t e) : ev(e) {}
+        ~Ready() { if (ev) cudaEventDestroy(ev); }
+    };
+    struct Job { int fd; off_t off; const char* p; size_t n; std::shared_ptr<Ready> ready; std::string path; };
+    struct File { int fd; off_t off; };
+    std::vector<std::thread> th;
     std::mutex m;
     std::condition_variable cv, cv_idle;
     std::deque<Job> q;
-    bool stop = false, busy = false, started = false;
+    std::map<std::string, File> files;
+    bool stop = false, started = false;
+    int busy = 0;
     int device = -1;
     std::string err;
     void start() {
         if (started) return;
         started = true;
-        th = std::thread([this] {
-            if (device >= 0) cudaSetDevice(device);   // the jobs' events live in this device's context
-            for (;;) {
-                Job j;
-                {
-                    std::unique_lock<std::mutex> lk(m);
-                    cv.wait(lk, [this] { return stop || !q.empty(); });
-                    if (q.empty()) return;
-                    j = q.front();
-                    q.pop_front();
-                    busy = true;
-                }
-                std::string e;
-                if (j.ready) {
-                    if (cudaEventSynchronize(j.ready) != cudaSuccess) e = "copy of " + j.path + " failed";
-                    cudaEventDestroy(j.ready);
-                }
-                if (e.empty() && j.n) {
-                    FILE* f = fopen(j.path.c_str(), "ab");
-                    if (!f) e = "cannot open " + j.path + " for appending";
-                    else {
-                        if (fwrite(j.p, 1, j.n, f) != j.n) e = "short write to " + j.path;
-                        fclose(f);
+        for (int w = 0; w < kWorkers; w++)
+            th.emplace_back([this] {
+                if (device >= 0) cudaSetDevice(device);   // the jobs' events live in this device's context
+                for (;;) {
+                    Job j;
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv.wait(lk, [this] { return stop || !q.empty(); });
+                        if (q.empty()) return;
+                        j = std::move(q.front());
+                        q.pop_front();
+                        busy++;
                     }
+                    std::string e;
+                    if (j.ready && j.ready->ev && cudaEventSynchronize(j.ready->ev) != cudaSuccess) e = "copy of " + j.path + " failed";
+                    size_t done = 0;
+                    while (e.empty() && done < j.n) {
+                        const ssize_t w = pwrite(j.fd, j.p + done, j.n - done, j.off + (off_t)done);
+                        if (w <= 0) e = "short write to " + j.path;
+                        else done += (size_t)w;
+                    }
+                    j.ready.reset();
+                    {
+                        std::lock_guard<std::mutex> lk(m);
+                        if (!e.empty() && err.empty()) err = e;
+                        busy--;
+                    }
+                    cv_idle.notify_all();
                 }
-                {
-                    std::lock_guard<std::mutex> lk(m);
-                    if (!e.empty() && err.empty()) err = e;
-                    busy = false;
-                }
-                cv_idle.notify_all();
-            }
-        });
+            });
     }
     void push(const std::string& path, const char* p, size_t n, cudaEvent_t ready = nullptr) {
         start();
+        std::shared_ptr<Ready> r = ready ? std::make_shared<Ready>(ready) : nullptr;
         {
             std::lock_guard<std::mutex> lk(m);
-            q.push_back(Job{path, p, n, ready});
+            auto it = files.find(path);
+            if (it == files.end()) {
+                const int fd = open(path.c_str(), O_WRONLY | O_CREAT, 0644);
+                if (fd < 0) {
+                    if (err.empty()) err = "cannot open " + path + " for appending";
+                    return;
+                }
+                it = files.emplace(path, File{fd, lseek(fd, 0, SEEK_END)}).first;
+            }
+            File& f = it->second;
+            for (size_t o = 0; o < n || (o == 0 && r); o += kChunk) {   // an empty push still retires its event
+                const size_t len = std::min(kChunk, n - o);
+                q.push_back(Job{f.fd, f.off + (off_t)o, p + o, len, r, path});
+                if (n == 0) break;
+            }
+            f.off += (off_t)n;
         }
-        cv.notify_one();
+        cv.notify_all();
     }
-    // all queued appends are on disk (or failed: the first error is returned)
+    // all queued appends are in the files (or failed: the first error is returned)
     std::string wait_idle() {
-        if (!started) return "";
+        if (!started) return err;
         std::unique_lock<std::mutex> lk(m);
-        cv_idle.wait(lk, [this] { return q.empty() && !busy; });
+        cv_idle.wait(lk, [this] { return q.empty() && busy == 0; });
         return err;
     }
     ~FileWriter() {
-        if (!started) return;
-        {
-            std::lock_guard<std::mutex> lk(m);
-            stop = true;
+        if (started) {
+            {
+                std::lock_guard<std::mutex> lk(m);
+                stop = true;
+            }
+            cv.notify_all();
+            for (auto& t : th) t.join();
         }
-        cv.notify_one();
-        th.join();
+        for (auto& kv : files) close(kv.second.fd);
     }
 };
 
@@ -1415,14 +1451,16 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
     int r;
     size_t ns_early = 0;
     char* dst_early = nullptr;
+    const size_t srec = c->run_compact ? sizeof(gpet_single_compact) : sizeof(gpet_event);   // a single on its way to the host
+    const void* singles_src = c->run_compact ? c->compact_slot[slot] : c->singles_slot[slot];
     if (c->early_copy) {
         // the singles are final once k_emit_singles is done: their copy starts now and overlaps the coincidence sorter
         CK(cudaEventSynchronize(c->ev_emit[slot]));
         ns_early = std::min<size_t>(c->h_slot_counters[slot][48], (size_t)c->cap_events);
-        if ((r = arena_reserve(c, c->res_singles, ns_early * sizeof(gpet_event)))) return r;
+        if ((r = arena_reserve(c, c->res_singles, ns_early * srec))) return r;
         dst_early = c->res_singles.p + c->res_singles.size;
         if (ns_early)
-            CK(cudaMemcpyAsync(dst_early, c->singles_slot[slot], ns_early * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->copy_stream));
+            CK(cudaMemcpyAsync(dst_early, singles_src, ns_early * srec, cudaMemcpyDeviceToHost, c->copy_stream));
     }
     CK(cudaEventSynchronize(c->ev_counters[slot]));
     patch_counters(c->h_slot_counters[slot]);
@@ -1455,23 +1493,23 @@ int retire_frame(gpet_ctx* c, int slot, RunState& rs) {
     const bool as_pairs = c->coinc_format == GPET_COINC_PAIRS;
     PinnedArena& arena_c = as_pairs ? c->res_pairs : c->res_coinc;
     const size_t rec_c = as_pairs ? 2 * sizeof(uint32_t) : sizeof(gpet_coincidence);
-    if (!c->early_copy && (r = arena_reserve(c, c->res_singles, ns * sizeof(gpet_event)))) return r;
+    if (!c->early_copy && (r = arena_reserve(c, c->res_singles, ns * srec))) return r;
     if (want_coinc && (r = arena_reserve(c, arena_c, nc * rec_c))) return r;
     if (want_coinc && (r = arena_reserve(c, c->res_cls, nc))) return r;
     char* dst_s = c->early_copy ? dst_early : c->res_singles.p + c->res_singles.size;
     char* dst_c = want_coinc ? arena_c.p + arena_c.size : nullptr;
     char* dst_k = want_coinc ? c->res_cls.p + c->res_cls.size : nullptr;
-    const size_t first_single = c->res_singles.size / sizeof(gpet_event);
+    const size_t first_single = c->res_singles.size / srec;
     if (c->early_copy && ns_early != ns) return fail(c, GPET_ERR_CUDA, "singles count changed after the emit kernel (internal error)");
     if (ns && !c->early_copy)
-        CK(cudaMemcpyAsync(dst_s, c->singles_slot[slot], ns * sizeof(gpet_event), cudaMemcpyDeviceToHost, c->copy_stream));
+        CK(cudaMemcpyAsync(dst_s, singles_src, ns * srec, cudaMemcpyDeviceToHost, c->copy_stream));
     if (want_coinc && nc) {
         CK(cudaMemcpyAsync(dst_c, as_pairs ? c->pairs_slot[slot] : c->coinc_slot[slot], nc * rec_c, cudaMemcpyDeviceToHost,
                            c->copy_stream));
         CK(cudaMemcpyAsync(dst_k, c->cls_slot[slot], nc, cudaMemcpyDeviceToHost, c->copy_stream));
     }
     CK(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
-    c->res_singles.size += ns * sizeof(gpet_event);
+    c->res_singles.size += ns * srec;
     if (want_coinc) {
         arena_c.size += nc * rec_c;
         c->res_cls.size += nc;
@@ -1667,6 +1705,24 @@ int run_attempt(gpet_ctx* c, const char* output_dir, bool resident, gpet_stats* 
     rs.writer.device = c->device;
     struct ClearWriter { gpet_ctx* c; ~ClearWriter() { c->file_writer = nullptr; } } clear_writer{c};
     c->coinc_expanded.clear();
+    c->singles_expanded.clear();
+    c->run_compact = false;
+    if (c->singles_format == GPET_SINGLES_COMPACT && !resident && rs.od.empty()) {
+        // 32-byte singles: only where gpet_result_singles can rebuild the 48-byte records bit for bit (include/gpet_b200.h)
+        if (psf_mode) return fail(c, GPET_ERR_ARG, "compact singles need device-numbered photons (source mode, not PSF input)");
+        if (c->dig.noise_mean_gap_us > 0.f) return fail(c, GPET_ERR_ARG, "compact singles cannot carry noise singles");
+        int max_id = 0;
+        for (const auto& p : c->geo.panels) max_id = std::max(max_id, p.panel < 0 ? 256 : (int)p.panel);
+        if (!c->have_geo || max_id > 255 || c->geo.moduleN > 4096 || c->geo.crystalN > 2048)
+            return fail(c, GPET_ERR_ARG, "compact singles: panel ids <= 255, <= 4096 modules per panel, <= 2048 crystals per module");
+        for (int k = 0; k < 2; k++)
+            if (!c->compact_slot[k]) {
+                char* p = nullptr;
+                if ((r = dev_alloc(c, &p, (size_t)c->cap_events * sizeof(gpet_single_compact)))) return r;
+                c->compact_slot[k] = p;
+            }
+        c->run_compact = true;
+    }
     CK(cudaMemsetAsync(c->d_pair_base, 0, 2 * sizeof(unsigned), c->stream));
     struct InRun {   // gpet_stage_digitize reads these while the run is in flight
         gpet_ctx* c;
@@ -1812,22 +1868,69 @@ int gpet_run_resident(gpet_ctx* c, gpet_stats* stats) {
     return run_impl(c, nullptr, true, stats);
 }
 
+// 48-byte records from the 32-byte ones of a GPET_SINGLES_COMPACT run (see include/gpet_b200.h for the identities)
+static const gpet_event* expanded_singles(gpet_ctx* c, size_t& n) {
+    n = c->res_singles.size / sizeof(gpet_single_compact);
+    if (c->singles_expanded.size() != n * sizeof(gpet_event)) {
+        c->singles_expanded.resize(n * sizeof(gpet_event));
+        const gpet_single_compact* in = reinterpret_cast<const gpet_single_compact*>(c->res_singles.p);
+        gpet_event* out = reinterpret_cast<gpet_event*>(c->singles_expanded.data());
+        const int dlevel = c->dig.dead_level;
+        const int rdepth = c->dig.readout_depth, rpolicy = c->dig.readout_policy;
+        const int depth = (rdepth != 3 && rpolicy == 1) ? 2 : rdepth;   // the detector kernel's readout level (transport.cu)
+        const int level = dlevel == 3 ? depth : dlevel;
+        const int moduleN = c->geo.moduleN, crystalN = c->geo.crystalN;
+        for (size_t i = 0; i < n; i++) {
+            const gpet_single_compact& s = in[i];
+            gpet_event e;
+            memset(&e, 0, sizeof(e));
+            e.pann = (int32_t)(s.ids & 0xffu); e.modn = (int32_t)((s.ids >> 8) & 0xfffu); e.cryn = (int32_t)((s.ids >> 20) & 0x7ffu);
+            e.eventid = s.eventid;
+            e.parn = (int32_t)((((uint32_t)s.eventid << 1) | (s.ids >> 31)) & 0x7fffffffu);
+            e.siten = level <= 0 ? 0 : level == 1 ? e.pann : level == 2 ? e.pann * moduleN + e.modn : (e.pann * moduleN + e.modn) * crystalN + e.cryn;
+            e.t = s.t; e.E = s.E; e.x = s.x; e.y = s.y; e.z = s.z;
+            out[i] = e;
+        }
+    }
+    return reinterpret_cast<const gpet_event*>(c->singles_expanded.data());
+}
+
 int64_t gpet_result_singles(gpet_ctx* c, const gpet_event** ptr) {
     if (!c || !ptr) return GPET_ERR_ARG;
     if (c->results_streamed) return fail(c, GPET_ERR_CAPACITY, kStreamedMsg);
+    if (c->run_compact) {
+        size_t n = 0;
+        *ptr = expanded_singles(c, n);
+        return (int64_t)n;
+    }
     *ptr = reinterpret_cast<const gpet_event*>(c->res_singles.p);
     return (int64_t)(c->res_singles.size / sizeof(gpet_event));
+}
+
+int64_t gpet_result_singles_compact(gpet_ctx* c, const gpet_single_compact** ptr) {
+    if (!c || !ptr) return GPET_ERR_ARG;
+    if (!c->run_compact) return fail(c, GPET_ERR_ARG, "the last run did not deliver compact singles (gpet_set_singles_format)");
+    *ptr = reinterpret_cast<const gpet_single_compact*>(c->res_singles.p);
+    return (int64_t)(c->res_singles.size / sizeof(gpet_single_compact));
+}
+
+int gpet_set_singles_format(gpet_ctx* c, int format) {
+    if (!c || (format != GPET_SINGLES_RECORDS && format != GPET_SINGLES_COMPACT)) return GPET_ERR_ARG;
+    c->singles_format = format;
+    return GPET_OK;
 }
 
 int64_t gpet_result_coincidences(gpet_ctx* c, const gpet_coincidence** ptr) {
     if (!c || !ptr) return GPET_ERR_ARG;
     if (c->results_streamed) return fail(c, GPET_ERR_CAPACITY, kStreamedMsg);
     if (c->coinc_format == GPET_COINC_PAIRS) {   // records on demand: gather from the singles list
-        const size_t np = c->res_pairs.size / (2 * sizeof(uint32_t)), ns = c->res_singles.size / sizeof(gpet_event);
+        const size_t np = c->res_pairs.size / (2 * sizeof(uint32_t));
+        size_t ns = c->res_singles.size / sizeof(gpet_event);
+        const gpet_event* sg = reinterpret_cast<const gpet_event*>(c->res_singles.p);
+        if (c->run_compact) sg = expanded_singles(c, ns);
         if (c->coinc_expanded.size() != np * sizeof(gpet_coincidence)) {
             c->coinc_expanded.resize(np * sizeof(gpet_coincidence));
             const uint32_t* pr = reinterpret_cast<const uint32_t*>(c->res_pairs.p);
-            const gpet_event* sg = reinterpret_cast<const gpet_event*>(c->res_singles.p);
             gpet_coincidence* out = reinterpret_cast<gpet_coincidence*>(c->coinc_expanded.data());
             for (size_t k = 0; k < np; k++) {
                 if (pr[2 * k] >= ns || pr[2 * k + 1] >= ns) return fail(c, GPET_ERR_ARG, "coincidence pair out of range");

@@ -77,6 +77,10 @@ struct gpet_ctx {
     unsigned* d_pair_base = nullptr;                     // [2]: singles of the run's earlier frames, alternating by frame
     int psf_output = 0;                                  // OUTPUTPSF of the reference (gpet_set_psf_output)
     int coinc_format = 0;                                // GPET_COINC_RECORDS / GPET_COINC_PAIRS (gpet_run only)
+    int singles_format = 0;                              // GPET_SINGLES_RECORDS / GPET_SINGLES_COMPACT (gpet_run(NULL) only)
+    bool run_compact = false;                            // the run in flight / the last run delivered 32-byte singles (res_singles holds them)
+    void* compact_slot[2] = {nullptr, nullptr};          // 32-byte singles of the frame in each slot (allocated on first use)
+    std::vector<char> singles_expanded;                  // 48-byte records built on demand from compact singles
     bool in_run = false;
     bool skip_fallback = false;                          // gpet_run's first attempt: time sort without the LSD fallback kernel
     int64_t run_frame = 0;                               // owned frames launched so far in this run

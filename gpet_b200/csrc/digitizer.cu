@@ -741,6 +741,21 @@ __global__ void __launch_bounds__(kThreads, 3) k_emit_singles(EventBuf ev, Digit
     }
 }
 
+// Singles as 32-byte records for the trip to the host (gpet_single_compact, include/gpet_b200.h): everything a 48-byte
+// Event of a source-mode run holds that is not implied by the rest.  Two 16-byte stores per single, consecutive.
+__global__ void __launch_bounds__(kThreads) k_pack_singles(const EventRec* __restrict__ singles, const unsigned* __restrict__ counters,
+                                                           unsigned singles_cap, int4* __restrict__ out) {
+    pdl_wait();
+    const unsigned n = min(counters[3], singles_cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int4* src = reinterpret_cast<const int4*>(singles + i);
+        const int4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);   // parn pann modn cryn | siten eventid t | E x y z
+        const unsigned ids = ((unsigned)a.y & 0xffu) | (((unsigned)a.z & 0xfffu) << 8) | (((unsigned)a.w & 0x7ffu) << 20) | (((unsigned)a.x & 1u) << 31);
+        out[2ull * i] = make_int4(b.z, b.w, c.x, c.y);                       // t, E, x
+        out[2ull * i + 1] = make_int4(c.z, c.w, b.y, (int)ids);              // y, z, eventid, ids
+    }
+}
+
 // ------------------------------------------------------------------------------------------- stage 5: coincidence sorter (extension)
 // Windows are opened by the first single that is not inside an earlier window and last cwin us.  A single whose
 // predecessor is at least cwin earlier is a guaranteed opener, so every single finds its own role by replaying the
@@ -1089,6 +1104,16 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
                                                 ws.spectrum_stride, ws.spec_emin, ws.spec_emax, with_fallback ? 0 : 1,
                                                 out.ev_after_emit ? out.h_singles_count : (unsigned*)nullptr));
     launches++;
+    if (out.singles_compact) {
+        static int g_pack[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev = dev >= 0 && dev < 64 ? dev : 0;
+        if (!g_pack[dev]) g_pack[dev] = 8 * num_sms;
+        GPET_LAUNCH("k_pack_singles", s, launch_pdl(k_pack_singles, g_pack[dev], kThreads, s, singles, ws.counters, out.singles_cap,
+                                                     static_cast<int4*>(out.singles_compact)));
+        launches++;
+    }
     if (out.ev_after_emit && out.h_singles_count) cudaEventRecord(out.ev_after_emit, s);
     if (p.cwin > 0.f && (out.coinc || out.pairs)) {
         GPET_LAUNCH("k_coinc", s, launch_pdl(k_coinc, g_coinc, kThreads, s, singles, ws.stime, ws.span, ws.spar, ws.seid, p, ws.counters, out.singles_cap, ws.scan_status[1],

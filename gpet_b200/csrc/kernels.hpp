@@ -60,6 +60,7 @@ struct DigitizerWorkspace {
 struct DigitizerOut {
     void* singles;                 // 48-byte records, time sorted
     unsigned int singles_cap;
+    void* singles_compact;         // optional: the same list as 32-byte gpet_single_compact records (k_pack_singles)
     void* coinc;                   // 96-byte coincidence records, or nullptr
     void* pairs;                   // uint2 index pairs into the run's singles list, or nullptr
     unsigned int coinc_cap;

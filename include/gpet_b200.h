@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GPET_ABI_VERSION 4  /* 4: 64-bit history numbers (gpet_set_first_pair), gpet_peek_config_device, results of large file runs streamed; 3: see below; 2: gpet_transport_params + record_psf / record_sphere, gpet_digitizer_params + noise_*, gpet_set_psf_output, gpet_stage_noise
+#define GPET_ABI_VERSION 5  /* 5: gpet_set_singles_format, gpet_result_singles_compact; 4: 64-bit history numbers (gpet_set_first_pair), gpet_peek_config_device, results of large file runs streamed; 3: see below; 2: gpet_transport_params + record_psf / record_sphere, gpet_digitizer_params + noise_*, gpet_set_psf_output, gpet_stage_noise
                              * 3: coincidence classes: gpet_digitizer_params + coinc_pair_shift, gpet_stats + trues / scatters / randoms,
                              *    gpet_fetch_coincidence_classes, gpet_result_coincidence_classes, gpet_mark_scattered */
 
@@ -302,6 +302,24 @@ int64_t gpet_result_coincidences(gpet_ctx* ctx, const gpet_coincidence** ptr);
  * the same files and the same records. */
 enum { GPET_COINC_RECORDS = 0, GPET_COINC_PAIRS = 1 };
 int gpet_set_coincidence_format(gpet_ctx* ctx, int format);
+/* How gpet_run(NULL) brings SINGLES to the host (extension; files always hold the reference's 48-byte Event, detector.cu:287-307).
+ * GPET_SINGLES_RECORDS (default): 48-byte records.  GPET_SINGLES_COMPACT: 32-byte records that hold the same information --
+ * end to end the run is bound by the device-to-host copy of the singles, and a third of an Event is redundant in source mode:
+ *   t, E, x, y, z as they are; eventid; ids = pann | modn << 8 | cryn << 20 | (parn & 1) << 31.
+ * parn is (eventid << 1 | parn & 1) & 0x7fffffff (two photons per annihilation, device numbering) and siten follows from the
+ * dead-time level (or, at level 3, the readout level) and the three ids.  gpet_result_singles expands them on demand, byte
+ * for byte what the 48-byte format delivers; gpet_result_singles_compact returns them as they arrived.  Refused
+ * (GPET_ERR_ARG from gpet_run) where the identity would not hold: PSF input (ids come from the file), noise singles, panel
+ * ids above 255, more than 4096 modules per panel or 2048 crystals per module; ignored by file runs. */
+enum { GPET_SINGLES_RECORDS = 0, GPET_SINGLES_COMPACT = 1 };
+typedef struct gpet_single_compact {
+    double t;
+    float E, x, y, z;
+    int32_t eventid;
+    uint32_t ids;
+} gpet_single_compact;
+int gpet_set_singles_format(gpet_ctx* ctx, int format);
+int64_t gpet_result_singles_compact(gpet_ctx* ctx, const gpet_single_compact** ptr);
 /* Phase-space dumps of gpet_run(output_dir) = the reference's OUTPUTPSF switch (constants.h:5; gPET.cu:63-114, 296-351):
  * 0 none; 1 PSF-input mode: the photons entering the phantom -> outsource.dat / idsource.dat / timesource.dat;
  * 2 source mode: those three after source sampling, and in both modes outphantom.dat / idphantom.dat / timephantom.dat

@@ -726,6 +726,46 @@ def test_coincidence_pairs_equal_coincidence_records(tmp_path):
     assert s_p[p_p[:, 0]].tobytes() == co_p["a"].tobytes() and s_p[p_p[:, 1]].tobytes() == co_p["b"].tobytes()
 
 
+@needs_tables
+@pytest.mark.parametrize("dead_level", [1, 2, 3])
+def test_compact_singles_expand_to_the_48_byte_records(tmp_path, dead_level):
+    """GPET_SINGLES_COMPACT (32-byte singles on the way to the host) is the same answer as the 48-byte Event: the expanded
+    records, the coincidences gathered through the index pairs and the class bytes are byte-identical, at every dead-time
+    level (siten is rebuilt from the level and the ids); file runs ignore the format; PSF input and noise refuse it."""
+    ex = make_example_dir(tmp_path, source="source.txt", window="0 20")
+    out = {}
+    for fmt in (api.Context.SINGLES_RECORDS, api.Context.SINGLES_COMPACT):
+        with api.Context(0) as c:
+            c.set_seed(9)
+            c.set_capacity(1 << 17, 1 << 19, 1 << 18)
+            c.load_config_file(ex / "input_PET.in", base_dir=ex)
+            c.set_digitizer(coinc_window_us=0.01, dead_level=dead_level)
+            c.set_coincidence_format(api.Context.COINC_PAIRS)
+            c.set_singles_format(fmt)
+            st = c.run(None)
+            out[fmt] = (st, c.result_singles(), c.result_coincidences(), c.result_coincidence_classes())
+            if fmt == api.Context.SINGLES_COMPACT:
+                cs = c.result_singles_compact()
+                od = tmp_path / "files"
+                od.mkdir()
+                st_f = c.run(od)                       # a file run keeps the reference layout
+                assert st_f.singles == st.singles
+                assert refio.read_events(od / "singles.dat").tobytes() == out[fmt][1].tobytes()
+                c.set_digitizer(noise_mean_gap_us=5.0, noise_interval_us=100.0)
+                with pytest.raises(api.GpetError):
+                    c.run(None)
+            else:
+                with pytest.raises(api.GpetError):
+                    c.result_singles_compact()
+    (st_r, s_r, co_r, k_r), (st_c, s_c, co_c, k_c) = out[0], out[1]
+    assert st_r.frames >= 3 and st_r.singles == st_c.singles == s_r.size > 1000 and st_r.coincidences > 100
+    assert s_r.tobytes() == s_c.tobytes()
+    assert co_r.tobytes() == co_c.tobytes() and k_r.tobytes() == k_c.tobytes()
+    assert cs.size == s_r.size and cs.dtype.itemsize == 32
+    assert np.array_equal(cs["t"], s_r["t"]) and np.array_equal(cs["E"], s_r["E"]) and np.array_equal(cs["eventid"], s_r["eventid"])
+    assert np.array_equal(cs["ids"] & 0xff, s_r["pann"]) and np.array_equal(cs["ids"] >> 31, s_r["parn"] & 1)
+
+
 # ------------------------------------------------------------------------------------------------ coincidence classes
 def paired_events(npairs, rng, tmax, nnoise=0, pair_shift=0):
     """Two events per annihilation a few ns apart (photon numbers 2k, 2k+1), dense enough in time for randoms and

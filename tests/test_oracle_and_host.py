@@ -195,7 +195,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(l, name), f"{name} declared in gpet_b200.h but not exported"
     assert set(api._SIGS) == declared, declared ^ set(api._SIGS)
-    assert api.lib().gpet_abi_version() == api.ABI_VERSION == 4
+    assert api.lib().gpet_abi_version() == api.ABI_VERSION == 5
 
 
 def test_missing_or_stale_library_fails_loudly(monkeypatch, tmp_path):
@@ -248,7 +248,7 @@ def test_ctypes_mirror_has_the_headers_struct_layouts(tmp_path):
     against the ctypes structures and numpy record types of gpet_b200/api.py."""
     structs = {"gpet_digitizer_params": api.DigitizerParams, "gpet_transport_params": api.TransportParams, "gpet_stats": api.Stats}
     records = {"gpet_event": api.EVENT_DTYPE, "gpet_coincidence": api.COINC_DTYPE, "gpet_hit": api.HIT_DTYPE,
-               "gpet_photon": api.PHOTON_DTYPE, "gpet_panel": api.PANEL_DTYPE}
+               "gpet_photon": api.PHOTON_DTYPE, "gpet_panel": api.PANEL_DTYPE, "gpet_single_compact": api.COMPACT_DTYPE}
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "gpet_b200.h"', "int main(void) {"]
     for name, st in structs.items():
         lines.append(f'printf("{name} %zu\\n", sizeof({name}));')
