@@ -261,7 +261,7 @@ def main():
     ap.add_argument("--source", default=DEFAULT_SOURCE, help="source file of the example (source.txt | pointsource.txt)")
     ap.add_argument("--frames-per-step", type=int, default=160,
                     help="activity scale per GPU of a resident step: the shipped acquisition (1.118 M pairs) x this = ~179 M pairs, ~50 ms of kernels")
-    ap.add_argument("--e2e-frames-per-step", type=int, default=16, help="activity scale per GPU of an end-to-end step (35 MB of results per 1.118 M pairs)")
+    ap.add_argument("--e2e-frames-per-step", type=int, default=64, help="activity scale per GPU of an end-to-end step (35 MB of results per 1.118 M pairs)")
     ap.add_argument("--frame-pairs", type=int, default=4_600_000,
                     help="frame capacity in pairs (the planner fills ~0.9 of it): per-frame fixed costs amortise with the frame, "
                          "tools/bigframes_sweep.py -- 314 us per M pairs at 1.1 M pairs a frame, 262 at 4.5 M")
@@ -370,6 +370,12 @@ def main():
         if world > 1:
             dist.barrier()
         total_ms, (pairs, coinc) = reduce_max_sum(sum(times), sum(s.pairs for s in stats), sum(s.coincidences for s in stats))
+        rank_ms = torch.tensor([sum(times) / max(len(times), 1)], dtype=torch.float64, device=dev)   # every rank's mean step, for the record
+        all_ms = [torch.zeros_like(rank_ms) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(all_ms, rank_ms)
+        else:
+            all_ms = [rank_ms]
         # e2e through gpet_run: planning + all stages + results in pinned host memory, wall clock.  Singles travel as 32-byte
         # gpet_single_compact records (the run is bound by their copy; gpet_result_singles rebuilds the 48-byte Event byte for
         # byte, tests/test_gpu_parity.py); the same run with 48-byte records is measured beside it
@@ -388,7 +394,7 @@ def main():
         step_ms = [round(x, 3) for x in times]
         return {"total_ms": total_ms, "pairs": pairs, "coinc": coinc, "stats": stats, "frames": nf, "e2e_ms": e_ms, "e2e_pairs": e_pairs,
                 "e2e_stats": e_stats, "e2e_frames": nf_e, "e2e_records48": e2e["records48"][1] / (e2e["records48"][0] * 1e-3),
-                "step_ms": step_ms, "tallies": dict(zip(multi.TALLY_FIELDS, (int(x) for x in tally_dev.tolist())))}
+                "step_ms": step_ms, "rank_ms": [round(float(x.item()), 3) for x in all_ms], "tallies": dict(zip(multi.TALLY_FIELDS, (int(x) for x in tally_dev.tolist())))}
 
     ex, ctx = make_ctx(args.source, "main")
     m = measure(ctx, args.steps, args.warmup, args.frames_per_step, args.e2e_frames_per_step)
@@ -483,12 +489,15 @@ def main():
         traffic = None
         tf = ROOT / "profiles" / "traffic.json"   # dram bytes per launch from the committed `ncu --set full` captures
         if tf.exists():
-            traffic = json.loads(tf.read_text()).get(args.source, {}).get(top)
+            tj = json.loads(tf.read_text())
+            traffic = tj.get(args.source, {}).get(top)
+            if traffic is not None:   # the capture is of a 1.118 M-pair frame: per launch of THIS frame size (DRAM traffic follows the photons)
+                traffic = float(traffic) * (sp.pairs / fr) / float(tj.get("_pairs_per_frame", sp.pairs / fr))
         roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[top]["achieved_gbs"] / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if pk.exists() else "fallback 6650 GB/s (B200_PROFILING.md)",
                     "us_per_launch": kernels[top]["us_per_launch"], "share_of_step": kernels[top]["us_per_frame"] / sum(k["us_per_frame"] for k in kernels.values()),
-                    "timing": "CUDA events bracketing every launch on the launching stream (gpet_profile_enable), 3 runs of the acquisition at 4 x the shipped activity (one frame of ~4.5 M pairs), L2 flushed between runs",
+                    "timing": "CUDA events bracketing every launch on the launching stream (gpet_profile_enable), 3 runs of the acquisition at 4 x the shipped activity (4.47 M pairs in %d frame(s)), L2 flushed between runs; traffic: ncu dram bytes of a 1.118 M-pair frame (profiles/traffic.json) scaled to this frame's pairs" % fr,
                     "note": "Monte-Carlo transport is latency/issue bound: the algorithmic bytes are tiny against HBM (DESIGN.md section 4); see profiles/ for issue-slot, SIMT-efficiency and pipe numbers",
                     "kernels": kernels}
         base = None
@@ -513,7 +522,7 @@ def main():
                 "details": {"pairs_per_step_per_gpu": m["pairs"] / nsteps / world, "frames_in_the_acquisition": int(m["frames"]),
                             "frames_per_step_per_gpu": int(s0.frames), "activity_scale": args.frames_per_step * world,
                             "e2e_frames_per_step_per_gpu": int(st.frames), "e2e_activity_scale": args.e2e_frames_per_step * world,
-                            "frame_capacity_pairs": args.frame_pairs, "step_ms_rank0": m["step_ms"]},
+                            "frame_capacity_pairs": args.frame_pairs, "step_ms_rank0": m["step_ms"], "mean_step_ms_by_rank": m["rank_ms"]},
                 "clocks": clocks,
                 "e2e": {"value": m["e2e_pairs"] / (m["e2e_ms"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "singles_format": "gpet_single_compact, 32 B (GPET_SINGLES_COMPACT: t, E, x, y, z, eventid, packed panel / module / crystal / photon bit; gpet_result_singles expands to the 48-byte Event on demand, byte-identical)",
