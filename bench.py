@@ -322,7 +322,15 @@ def main():
         scale = max(1, frames_per_gpu * world)
         for i, n in enumerate(ctx.base_atoms):
             ctx.set_source_atoms(i, n * scale)
-        nf = ctx.plan_frames(args.frame_pairs)
+        cap = int(args.frame_pairs)
+        nf = ctx.plan_frames(cap)
+        # every rank the same number of frames: a slightly smaller frame capacity until the count divides by the world size
+        # (346 frames over 8 ranks would leave two ranks with 44 frames and six with 43: the step is the slowest rank's)
+        for _ in range(12):
+            if nf % world == 0:
+                break
+            cap = int(cap * nf / (world * ((nf + world - 1) // world))) - 1
+            nf = ctx.plan_frames(cap)
         ctx.set_shard(rank, world)
         return nf
 

@@ -465,10 +465,13 @@ __global__ void __launch_bounds__(kThreads) k_phantom(PhotonQueue q0, PhotonQueu
 
 // ------------------------------------------------------------------------------------------- X1/X2/D1/D2: detector
 constexpr int kSlots = 6;  // distinct crystals per photon kept by the adder (reference: Event events[4], no bound check)
-// k_detector's block: 3 x 256 threads per SM at 72 registers without spills (132 us per source.txt frame); measured
-// alternatives: 4 x 256 at 64 registers with spills 147 us, 7 x 128 at 72 registers with spills 136 us
+// k_detector's block: 4 x 256 threads per SM.  The kernel retires ~2.2 instructions per cycle and SM whatever its mix (it waits
+// on dependent ALU chains -- Philox rounds -- and on L1 / L2 round trips), so resident warps are what it needs: 64 registers
+// (no spills) and 55 KB of shared memory per block (adder slots 43 KB + 16 staging rows per warp) hold 32 warps per SM with
+// up to 8 panels; more panels fall back to 3 blocks.  Round 1 / early round 2: 3 x 256 at 76 registers and 32 staging rows.
 constexpr int kDetThreads = 256;
-constexpr int kDetBlocksPerSm = 3;
+constexpr int kDetBlocksPerSm = 4;
+constexpr unsigned kStage = 16;   // hit rows and event records a warp stages before it flushes them
 
 __device__ __forceinline__ void crystal_search(const PanelDev& pd, const DetectorDev& det, float px, float py, float pz,
                                                int& m_id, int& M_id, int& L_id) {
@@ -691,6 +694,7 @@ __device__ __forceinline__ void front_flush(FS& st, unsigned warp, unsigned lane
 // kSmemTab: one block of 1024 threads per SM with the 1-D tables in shared memory (TabShared) instead of four blocks of 256
 // reading them through L1 (TabGlobal): same warps per SM, same registers; an A/B of where the tables live (GPET_SMEM_TABLES)
 constexpr int kFrontThreadsSmem = 1024;
+// (five blocks of 256 at 48 registers spill 128 bytes and are slower: 87 -> 93 us, profiles/r02q_kprof_source_front{4,5}.txt)
 template <bool kFromQueue, bool kSmemTab>
 __global__ void __launch_bounds__(kSmemTab ? kFrontThreadsSmem : kThreads, kSmemTab ? 1 : 4) k_front(const SourceDev* __restrict__ fr, unsigned long long npairs, PhotonQueue q0,
                                                     PhantomDev ph, TablesDev tb, DetectorDev det, float eabs, uint64_t seed,
@@ -961,12 +965,12 @@ __device__ __forceinline__ void crystal_search_rcp(const PanelDev& pd, const Det
 
 // per-warp staging of the rows that leave the SM: 32 hits (SoA pieces) and 32 events (48-byte records)
 struct WarpStage {
-    int4 hid[32];            // hits: parn, pann, modn, cryn
-    float4 hf[32];           // E, x, y, z
-    double ht[32];
-    int4 ev[32 * 3];         // events: record k = pieces 3k .. 3k+2
-    int htype[32];
-    int kn_src[32];          // lane of the j-th scattering photon (cooperative Klein-Nishina pass)
+    int4 hid[kStage];        // hits: parn, pann, modn, cryn
+    float4 hf[kStage];       // E, x, y, z
+    double ht[kStage];
+    int4 ev[kStage * 3];     // events: record k = pieces 3k .. 3k+2
+    int htype[kStage];
+    unsigned char kn_src[32];   // lane of the j-th scattering photon (cooperative Klein-Nishina pass)
 };
 
 constexpr int kKnMaxRounds = 8;   // rounds of one photon evaluated side by side at most (acceptance ~2/3: 8 rounds fail 2e-4 of the time)
@@ -1029,7 +1033,7 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
         const unsigned room = base < ev.capacity ? min(estaged, ev.capacity - base) : 0u;
         int4* dst = reinterpret_cast<int4*>(ev.rec + base);
 #pragma unroll
-        for (unsigned p = 0; p < 3; p++) {
+        for (unsigned p = 0; p * 32u < 3u * kStage; p++) {
             const unsigned piece = p * 32u + lane;
             if (piece < 3u * room) dst[piece] = ws.ev[piece];
         }
@@ -1131,7 +1135,7 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
             const unsigned nC = __popc(cmask);
             const unsigned R = min(32u / nC, (unsigned)kKnMaxRounds);
             const unsigned mine = __popc(cmask & lt_mask);          // this lane's number among the scattering photons
-            if (pending) ws.kn_src[mine] = (int)lane;
+            if (pending) ws.kn_src[mine] = (unsigned char)lane;
             __syncwarp();
             const unsigned jk = __ldg(&c_kn.jk[nC][lane]);
             const unsigned j = jk & 31u, k = jk >> 5;               // this lane evaluates round k of photon j
@@ -1198,15 +1202,27 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
                 const unsigned m = __ballot_sync(kFull, has);
                 if (m == 0u) break;
                 const unsigned cnt = __popc(m);
-                if (hstaged + cnt > 32u) flush_hits();
-                if (has) {
-                    const unsigned p = hstaged + __popc(m & lt_mask);
+                if (hstaged + cnt > kStage) flush_hits();
+                unsigned rank = __popc(m & lt_mask);
+                if (cnt > kStage) {   // rare: more deposits in one pass than the staging rows hold; the first kStage leave at once
+                    if (has && rank < kStage) {
+                        ws.hid[rank] = make_int4(parn, s_panels[pa].id, h_key >> 16, h_key & 0xffff);
+                        ws.hf[rank] = make_float4(pass ? h_E1 : h_E0, x, y, z);
+                        ws.ht[rank] = t;
+                        ws.htype[rank] = pass ? 2 : h_type0;
+                    }
+                    hstaged = kStage;
+                    flush_hits();
+                    rank -= kStage;   // wraps for the lanes just served: they fail the test below
+                }
+                if (has && rank < kStage) {
+                    const unsigned p = hstaged + rank;
                     ws.hid[p] = make_int4(parn, s_panels[pa].id, h_key >> 16, h_key & 0xffff);
                     ws.hf[p] = make_float4(pass ? h_E1 : h_E0, x, y, z);
                     ws.ht[p] = t;
                     ws.htype[p] = pass ? 2 : h_type0;
                 }
-                hstaged += cnt;
+                hstaged += cnt > kStage ? cnt - kStage : cnt;
             }
         }
         // ---- photon finished: readout (gPET_kernals.cu:756-813), events into the warp's staging records
@@ -1216,15 +1232,17 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
         if (mine_ev && nslot > 1 && rdepth != 3) deadmask = readout_merge_fast(sl, tid, nslot, depth, rpolicy);
         unsigned ne = mine_ev ? (unsigned)(nslot - __popc(deadmask)) : 0u;
         if (__ballot_sync(kFull, ne != 0u)) {
-            // at most kSlots events per lane: rounds of one event per lane, so that a round always fits the 32 records
+            // at most kSlots events per lane: rounds of at most one event per lane; a lane whose record does not fit the
+            // staging rows this round comes again after the flush
             int knext = 0;
 #pragma unroll 1
             while (true) {
-                const bool has = ne != 0u;
-                const unsigned m = __ballot_sync(kFull, has);
+                const bool want = ne != 0u;
+                const unsigned m = __ballot_sync(kFull, want);
                 if (m == 0u) break;
-                const unsigned cnt = __popc(m);
-                if (estaged + cnt > 32u) flush_events();
+                if (estaged + (unsigned)__popc(m) > kStage) flush_events();
+                const unsigned room = kStage - estaged, rank = __popc(m & lt_mask);   // more than kStage at once: the rest next round
+                const bool has = want && rank < room;
                 if (has) {
                     while (deadmask >> knext & 1u) knext++;
                     const int key = sl.key[knext][tid];
@@ -1235,11 +1253,11 @@ __global__ void __launch_bounds__(kDetThreads, kDetBlocksPerSm) k_detector(Photo
                     r.eventid = eid;
                     r.t = sl.t[knext][tid]; r.E = sl.E[knext][tid];
                     r.x = sl.x[knext][tid]; r.y = sl.y[knext][tid]; r.z = sl.z[knext][tid];
-                    store_event_rec(reinterpret_cast<EventRec*>(ws.ev) + (estaged + __popc(m & lt_mask)), r);
+                    store_event_rec(reinterpret_cast<EventRec*>(ws.ev) + (estaged + rank), r);
                     knext++;
                     ne--;
                 }
-                estaged += cnt;
+                estaged += min((unsigned)__popc(m), room);
             }
         }
         if (mine_ev) nslot = 0;
