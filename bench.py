@@ -186,10 +186,10 @@ def have_gpu():
 def bench_config(source):
     """The `config` object of BOTH arms (identical keys and values: the driver compares them)."""
     return {"workload": workload_name(source),
-            "step": "our arm: one step = the acquisition with its activity scaled 160 x per GPU (~179 M pairs per GPU, >= 40 ms of kernels), cut "
-                    "into frames of ~4 M pairs (the frame is this library's batch: per-frame fixed costs amortise with it), sharded by frames over "
-                    "the GPUs; reference arm: one step = the acquisition at the shipped activity (1.118 M pairs, a bounded sample of the same "
-                    "workload -- the metric is per pair)",
+            "step": "our arm: one step = the acquisition with its activity scaled 160 x (~179 M pairs per GPU, >= 40 ms of kernels) and, on N GPUs, "
+                    "its duration scaled N x (0 - 120 N s: the same event rate at every N), cut into frames of ~4 M pairs (the frame is this "
+                    "library's batch: per-frame fixed costs amortise with it), sharded by frames over the GPUs; reference arm: one step = the "
+                    "acquisition at the shipped activity (1.118 M pairs, a bounded sample of the same workload -- the metric is per pair)",
             "l2": "working set of a frame (~1 GB of queues, hit / event / sort buffers) exceeds the 126 MB L2; 256 MiB flush between timed steps",
             "coincidence_window_us": 0.01, "rng": "Philox4x32-10, key 0x67504554, 64-bit history numbers", "time_path": "fp64",
             "multi_gpu": "one acquisition, frames sharded round robin over the ranks (gpet_set_shard), no data-path collective; "
@@ -314,24 +314,34 @@ def main():
         ctx.set_coincidence_format(api.Context.COINC_PAIRS)
         ctx.set_spectrum(128, 0.0, 1.0e6)
         ctx.base_atoms = [int(x["natom"]) for x in ctx.sources()]
+        from gpet_b200 import refio
+        cfg = refio.parse_config(ex / "input_PET.in")
+        ctx.base_window = (float(cfg["tstart"]), float(cfg["tend"]))
         return ex, ctx
 
-    def plan(ctx, frames_per_gpu):
-        """ONE acquisition whose activity is `frames_per_gpu x world` times the shipped one: the planner cuts it into as many
-        frames of ~1.1 M pairs (same seed on every rank: same plan), rank r runs frames f with f % world == r."""
-        scale = max(1, frames_per_gpu * world)
+    def plan(ctx, frames_per_gpu, nranks=None):
+        """ONE acquisition: the shipped one with `frames_per_gpu` times its activity and, on N GPUs, N times its duration
+        (0 .. 120 N s).  The event RATE -- what dead time, coincidence windows and the time sort see -- is then the same at every
+        N (F-18, T1/2 6586 s: 5 % lower on average over 960 s), so every GPU does the same work per pair; scaling the activity
+        with N instead changes the workload itself (measured at N = 8: 7.5 x the random coincidences, 1.5 % fewer singles per
+        pair, +6 % digitizer time per pair on EVERY rank, profiles/r02r_bench_n8_activity_scaled.json).  The planner cuts the
+        acquisition into frames of ~4 M pairs (same seed on every rank: same plan), rank r runs frames f with f % world == r."""
+        nranks = world if nranks is None else nranks
+        scale = max(1, frames_per_gpu)
         for i, n in enumerate(ctx.base_atoms):
             ctx.set_source_atoms(i, n * scale)
+        t0, t1 = ctx.base_window
+        ctx.set_time_window(t0, t0 + (t1 - t0) * nranks)
         cap = int(args.frame_pairs)
         nf = ctx.plan_frames(cap)
         # every rank the same number of frames: a slightly smaller frame capacity until the count divides by the world size
         # (346 frames over 8 ranks would leave two ranks with 44 frames and six with 43: the step is the slowest rank's)
         for _ in range(12):
-            if nf % world == 0:
+            if nf % nranks == 0:
                 break
-            cap = int(cap * nf / (world * ((nf + world - 1) // world))) - 1
+            cap = int(cap * nf / (nranks * ((nf + nranks - 1) // nranks))) - 1
             nf = ctx.plan_frames(cap)
-        ctx.set_shard(rank, world)
+        ctx.set_shard(rank if nranks == world else 0, nranks)
         return nf
 
     tally_dev = torch.zeros(len(multi.TALLY_FIELDS), dtype=torch.int64, device=dev)
@@ -451,6 +461,7 @@ def main():
     if world > 1 and not args.no_extra:
         try:
             atoms = [n * world for n in ctx.base_atoms]
+            ctx.set_time_window(*ctx.base_window)
             multi.run_exchange(ctx, atoms, dev, frame_pairs=args.frame_pairs)          # warm-up
             dist.barrier(); torch.cuda.synchronize()
             w0 = time.perf_counter()
@@ -470,8 +481,7 @@ def main():
 
     if rank == 0:
         # ---- per-kernel device times (CUDA events around every launch, on the launching stream) -> roofline
-        plan(ctx, 4)
-        ctx.set_shard(0, 1)
+        plan(ctx, 4, nranks=1)
         ctx.profile(True)
         nprof = 3
         for _ in range(nprof):
@@ -528,8 +538,8 @@ def main():
                 "ms_per_step": m["total_ms"] / nsteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": bench_config(args.source),
                 "details": {"pairs_per_step_per_gpu": m["pairs"] / nsteps / world, "frames_in_the_acquisition": int(m["frames"]),
-                            "frames_per_step_per_gpu": int(s0.frames), "activity_scale": args.frames_per_step * world,
-                            "e2e_frames_per_step_per_gpu": int(st.frames), "e2e_activity_scale": args.e2e_frames_per_step * world,
+                            "frames_per_step_per_gpu": int(s0.frames), "activity_scale": args.frames_per_step, "duration_scale": world,
+                            "e2e_frames_per_step_per_gpu": int(st.frames), "e2e_activity_scale": args.e2e_frames_per_step,
                             "frame_capacity_pairs": args.frame_pairs, "step_ms_rank0": m["step_ms"], "mean_step_ms_by_rank": m["rank_ms"]},
                 "clocks": clocks,
                 "e2e": {"value": m["e2e_pairs"] / (m["e2e_ms"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
