@@ -1046,15 +1046,26 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = dflt;
         return num_sms * per_sm;
     };
-    static int g_prep = 0, g_scatter = 0, g_rank = 0, g_emit = 0, g_coinc = 0, g_chain = 0;
-    if (!g_prep) {
-        g_prep = resident((const void*)k_prep, 4);
-        g_scatter = resident((const void*)k_bucket_scatter, 4);
-        g_rank = resident((const void*)k_bucket_rank, 4);
-        g_emit = resident((const void*)k_emit_singles, 3);
-        g_coinc = resident((const void*)k_coinc, 4);
-        g_chain = resident((const void*)k_deadtime_chain, 4);
+    // launch shapes depend on the device (SM count): cached per device, so that contexts on different GPUs of one process never
+    // share a grid sized for another device (k_bucket_scan and the cooperative fallback rely on all their blocks being resident)
+    struct Shapes { int prep, scatter, rank, emit, coinc, chain, coop, pack; };
+    static Shapes shapes[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Shapes& sh = shapes[dev >= 0 && dev < 64 ? dev : 0];
+    if (!sh.prep) {
+        sh.prep = resident((const void*)k_prep, 4);
+        sh.scatter = resident((const void*)k_bucket_scatter, 4);
+        sh.rank = resident((const void*)k_bucket_rank, 4);
+        sh.emit = resident((const void*)k_emit_singles, 3);
+        sh.coinc = resident((const void*)k_coinc, 4);
+        sh.chain = resident((const void*)k_deadtime_chain, 4);
+        sh.pack = 8 * num_sms;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lsd_fallback, rsort::kThreads, 0);
+        sh.coop = num_sms * std::max(1, std::min(per_sm, 2));
     }
+    const int g_prep = sh.prep, g_scatter = sh.scatter, g_rank = sh.rank, g_emit = sh.emit, g_coinc = sh.coinc, g_chain = sh.chain;
     const int grid = num_sms * 4;   // k_range
     int launches = 0;
     EventRec* singles = static_cast<EventRec*>(out.singles);
@@ -1083,12 +1094,7 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
                                                 ws.site_t, p.tie_site));
     launches += 4;
     if (with_fallback) {
-        static int coop_grid = 0;
-        if (!coop_grid) {
-            int per_sm = 1;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lsd_fallback, rsort::kThreads, 0);
-            coop_grid = num_sms * std::max(1, std::min(per_sm, 2));
-        }
+        const int coop_grid = sh.coop;
         void* args[] = {&ws.tkeys[0], &ws.tkeys[1], &ws.tvals[0], &ws.tvals[1], &ws.aux, &ws.site_of, &ws.counters, &ws.st_time,
                         &ws.lookback[0], &ws.lookback[1], &ws.grid_bar, &ws.order_t, &ws.site_t};
         GPET_LAUNCH("k_lsd_fallback", s,
@@ -1105,12 +1111,7 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
                                                 out.ev_after_emit ? out.h_singles_count : (unsigned*)nullptr));
     launches++;
     if (out.singles_compact) {
-        static int g_pack[64] = {};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        dev = dev >= 0 && dev < 64 ? dev : 0;
-        if (!g_pack[dev]) g_pack[dev] = 8 * num_sms;
-        GPET_LAUNCH("k_pack_singles", s, launch_pdl(k_pack_singles, g_pack[dev], kThreads, s, singles, ws.counters, out.singles_cap,
+        GPET_LAUNCH("k_pack_singles", s, launch_pdl(k_pack_singles, sh.pack, kThreads, s, singles, ws.counters, out.singles_cap,
                                                      static_cast<int4*>(out.singles_compact)));
         launches++;
     }
