@@ -139,6 +139,7 @@ _SIGS = {
     "gpet_set_coincidence_format": (C.c_int, [_P, C.c_int]),
     "gpet_set_singles_format": (C.c_int, [_P, C.c_int]),
     "gpet_result_singles_compact": (C.c_int64, [_P, C.POINTER(_P)]),
+    "gpet_expand_singles": (C.c_int, [_P, _P, C.c_int64, _P]),
     "gpet_result_coincidence_pairs": (C.c_int64, [_P, C.POINTER(_P)]),
     "gpet_result_coincidence_classes": (C.c_int64, [_P, C.POINTER(_P)]),
     "gpet_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
@@ -548,6 +549,13 @@ class Context:
         """How run(None) brings singles to the host: 48-byte records, or 32-byte gpet_single_compact records that
         result_singles() expands on demand (byte-identical)."""
         self._ck(self._l.gpet_set_singles_format(self._h, int(fmt)))
+
+    def expand_singles(self, compact):
+        """48-byte records from 32-byte compact singles (host only; needs the geometry and the digitizer parameters)."""
+        compact = np.ascontiguousarray(compact, COMPACT_DTYPE)
+        out = np.zeros(compact.size, EVENT_DTYPE)
+        self._ck(self._l.gpet_expand_singles(self._h, _ptr(compact), compact.size, _ptr(out)))
+        return out
 
     def result_singles_compact(self):
         p = C.c_void_p()

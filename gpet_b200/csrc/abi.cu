@@ -1869,12 +1869,8 @@ int gpet_run_resident(gpet_ctx* c, gpet_stats* stats) {
 }
 
 // 48-byte records from the 32-byte ones of a GPET_SINGLES_COMPACT run (see include/gpet_b200.h for the identities)
-static const gpet_event* expanded_singles(gpet_ctx* c, size_t& n) {
-    n = c->res_singles.size / sizeof(gpet_single_compact);
-    if (c->singles_expanded.size() != n * sizeof(gpet_event)) {
-        c->singles_expanded.resize(n * sizeof(gpet_event));
-        const gpet_single_compact* in = reinterpret_cast<const gpet_single_compact*>(c->res_singles.p);
-        gpet_event* out = reinterpret_cast<gpet_event*>(c->singles_expanded.data());
+static void expand_compact(const gpet_ctx* c, const gpet_single_compact* in, size_t n, gpet_event* out) {
+    {
         const int dlevel = c->dig.dead_level;
         const int rdepth = c->dig.readout_depth, rpolicy = c->dig.readout_policy;
         const int depth = (rdepth != 3 && rpolicy == 1) ? 2 : rdepth;   // the detector kernel's readout level (transport.cu)
@@ -1892,7 +1888,22 @@ static const gpet_event* expanded_singles(gpet_ctx* c, size_t& n) {
             out[i] = e;
         }
     }
+}
+
+static const gpet_event* expanded_singles(gpet_ctx* c, size_t& n) {
+    n = c->res_singles.size / sizeof(gpet_single_compact);
+    if (c->singles_expanded.size() != n * sizeof(gpet_event)) {
+        c->singles_expanded.resize(n * sizeof(gpet_event));
+        expand_compact(c, reinterpret_cast<const gpet_single_compact*>(c->res_singles.p), n, reinterpret_cast<gpet_event*>(c->singles_expanded.data()));
+    }
     return reinterpret_cast<const gpet_event*>(c->singles_expanded.data());
+}
+
+int gpet_expand_singles(const gpet_ctx* c, const gpet_single_compact* in, int64_t n, gpet_event* out) {
+    if (!c || n < 0 || (n > 0 && (!in || !out))) return GPET_ERR_ARG;
+    if (!c->have_geo) return fail(c, GPET_ERR_ARG, "gpet_expand_singles needs the detector geometry (module / crystal counts)");
+    expand_compact(c, in, (size_t)n, out);
+    return GPET_OK;
 }
 
 int64_t gpet_result_singles(gpet_ctx* c, const gpet_event** ptr) {

@@ -320,6 +320,10 @@ typedef struct gpet_single_compact {
 } gpet_single_compact;
 int gpet_set_singles_format(gpet_ctx* ctx, int format);
 int64_t gpet_result_singles_compact(gpet_ctx* ctx, const gpet_single_compact** ptr);
+/* The same expansion for records the caller kept (e.g. stored compact): n compact singles -> n 48-byte Events, with the
+ * geometry and the digitizer parameters (dead-time level, readout depth / policy) loaded in ctx.  Host only: works on a
+ * context without a device. */
+int gpet_expand_singles(const gpet_ctx* ctx, const gpet_single_compact* in, int64_t n, gpet_event* out);
 /* Phase-space dumps of gpet_run(output_dir) = the reference's OUTPUTPSF switch (constants.h:5; gPET.cu:63-114, 296-351):
  * 0 none; 1 PSF-input mode: the photons entering the phantom -> outsource.dat / idsource.dat / timesource.dat;
  * 2 source mode: those three after source sampling, and in both modes outphantom.dat / idphantom.dat / timephantom.dat

@@ -307,6 +307,49 @@ def test_host_only_context_refuses_compute():
         assert c.get_digitizer().coinc_pair_shift == 1
 
 
+@pytest.mark.parametrize("dead_level,rdepth,rpolicy", [(0, 2, 1), (1, 2, 1), (2, 2, 1), (3, 2, 1), (3, 3, 0), (3, 1, 0), (3, 2, 0)])
+def test_compact_singles_expand_on_the_host(dead_level, rdepth, rpolicy):
+    """gpet_expand_singles (host only): 32-byte compact singles -> the 48-byte Event.  The packing is restated here in numpy
+    (include/gpet_b200.h: ids = pann | modn << 8 | cryn << 20 | (parn & 1) << 31), siten follows from the dead-time level --
+    or, at level 3, from the readout level the detector kernel used -- and the ids; parn from eventid and the photon bit."""
+    rng = np.random.default_rng(11)
+    n = 5000
+    with api.Context(device=-1) as c:
+        c.load_geometry(parity.EXAMPLE / "input" / "config8.geo")
+        cnt, _, _ = c.geometry_counts()
+        module_n, crystal_n = int(cnt[2]), int(cnt[3])
+        assert (module_n, crystal_n) == (117, 64)
+        c.set_digitizer(dead_level=dead_level, readout_depth=rdepth, readout_policy=rpolicy)
+        ev = np.zeros(n, api.EVENT_DTYPE)
+        ev["pann"] = rng.integers(0, 8, n); ev["modn"] = rng.integers(0, module_n, n); ev["cryn"] = rng.integers(0, crystal_n, n)
+        pair = rng.integers(0, 1 << 40, n, dtype=np.int64)                 # 64-bit history numbers: the record keeps 31 bits
+        which = rng.integers(0, 2, n)
+        ev["eventid"] = (pair & 0x7fffffff).astype(np.int32)
+        ev["parn"] = ((2 * pair + which) & 0x7fffffff).astype(np.int32)
+        depth = 2 if (rdepth != 3 and rpolicy == 1) else rdepth
+        level = depth if dead_level == 3 else dead_level
+        site = {0: np.zeros(n, np.int64), 1: ev["pann"].astype(np.int64), 2: ev["pann"].astype(np.int64) * module_n + ev["modn"],
+                3: (ev["pann"].astype(np.int64) * module_n + ev["modn"]) * crystal_n + ev["cryn"]}[level]
+        ev["siten"] = site
+        ev["t"] = np.sort(rng.uniform(0, 1e8, n)); ev["E"] = rng.uniform(3e4, 7e5, n)
+        ev["x"], ev["y"], ev["z"] = rng.uniform(-2, 0, n), rng.uniform(-8, 8, n), rng.uniform(-11, 11, n)
+        cs = np.zeros(n, api.COMPACT_DTYPE)
+        for f in ("t", "E", "x", "y", "z", "eventid"):
+            cs[f] = ev[f]
+        cs["ids"] = (ev["pann"].astype(np.uint32) | (ev["modn"].astype(np.uint32) << 8) | (ev["cryn"].astype(np.uint32) << 20)
+                     | ((ev["parn"].astype(np.uint32) & 1) << 31))
+        out = c.expand_singles(cs)
+        assert out.tobytes() == ev.tobytes()
+        assert c.expand_singles(cs[:0]).size == 0
+    with api.Context(device=-1) as c2:   # no geometry: refused, not guessed
+        with pytest.raises(api.GpetError):
+            c2.expand_singles(cs[:4])
+        with pytest.raises(api.GpetError):
+            c2.set_singles_format(7)
+        with pytest.raises(api.GpetError):
+            c2.result_singles_compact()
+
+
 # ------------------------------------------------------------------------------------------------ loaders
 def test_config_parser_matches_numpy_parser(tmp_path):
     cfg = refio.parse_config(parity.EXAMPLE / "input_PET.in")
