@@ -442,7 +442,7 @@ def main():
                 f_pairs += int(stf.pairs); f_ms += (w1 - w0) * 1e3
                 f_bytes += (od / "adder.dat").stat().st_size + (od / "singles.dat").stat().st_size
         e2e_files = {"value": f_pairs / (f_ms * 1e-3), "unit": UNIT, "bytes_written_per_step": f_bytes // 3, "steps": 3,
-                     "files": "adder.dat + singles.dat, appended frame by frame by a writer thread while the next frames compute",
+                     "files": "adder.dat + singles.dat, appended frame by frame by a pool of writer threads while the next frames compute",
                      "timing": "wall clock around gpet_run(output_dir), files complete on return; same directory tree (tmp) as the reference arm's runs"}
         ctx.set_transport(record_hits=1)
         ctx.set_digitizer(coinc_window_us=0.01)
@@ -521,7 +521,7 @@ def main():
         base = None
         if not args.no_cpu_baseline:
             try:
-                ref = reference_line(ex, args, args.source, steps=2, warmup=1)
+                ref = reference_line(ex, args, args.source, steps=5, warmup=1)   # median of five runs (two were too noisy)
                 base = ref["cpu_baseline"]
                 base["value"] = ref["value"]
                 if base.get("kind") == "reference":
