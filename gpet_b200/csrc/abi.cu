@@ -116,7 +116,7 @@ int ensure_buffers(gpet_ctx* c) {
     }
     if ((r = dev_alloc(c, &w.site_of, ce))) return r;
     if ((r = dev_alloc(c, &w.aux, ce))) return r;
-    if ((r = dev_alloc(c, &w.bpay, ce))) return r;
+    if ((r = dev_alloc(c, &w.bent, ce))) return r;
     if ((r = dev_alloc(c, &w.site_t, ce))) return r;
     if ((r = dev_alloc(c, &w.stime, ce))) return r;
     if ((r = dev_alloc(c, &w.span, ce))) return r;

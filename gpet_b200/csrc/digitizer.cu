@@ -356,8 +356,7 @@ __global__ void __launch_bounds__(kThreads) k_bucket_scan(const unsigned* __rest
 __global__ void __launch_bounds__(kThreads) k_bucket_scatter(const unsigned long long* __restrict__ keys,
                                                              const int* __restrict__ site_of, const unsigned* __restrict__ aux,
                                                              const unsigned* __restrict__ counters, TimeRange range,
-                                                             const unsigned* __restrict__ bstart,
-                                                             unsigned long long* __restrict__ bkeys, uint2* __restrict__ bpay) {
+                                                             const unsigned* __restrict__ bstart, uint4* __restrict__ bent) {
     pdl_wait();
     if (counters[kFlagLsd]) return;
     const unsigned n = counters[0];
@@ -381,9 +380,10 @@ __global__ void __launch_bounds__(kThreads) k_bucket_scatter(const unsigned long
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             if (key[u] == ~0ull) continue;
+            // ONE 16-byte entry per event: the scatter is bound by the number of scattered sectors written, and a key array
+            // plus a payload array cost two per event (22.6 -> 13.3 us on the 1.1 M-pair frame, 21.2 -> 15.9 us per M pairs at 4.5 M)
             const unsigned i = i0 + u * nth, o = pos[u] + (a[u] & ~kEwinBit);
-            bkeys[o] = key[u];
-            bpay[o] = make_uint2(i | (a[u] & kEwinBit), (unsigned)site[u]);
+            bent[o] = make_uint4((unsigned)key[u], (unsigned)(key[u] >> 32), i | (a[u] & kEwinBit), (unsigned)site[u]);
         }
     }
 }
@@ -393,8 +393,9 @@ __global__ void __launch_bounds__(kThreads) k_bucket_scatter(const unsigned long
 // few cache lines at most, so the walk over the slice runs out of L1 (the warp that ranks them has just loaded them).
 // No shared memory and no barrier: at frame sizes this kernel is a latency chain (load, slice bounds, walk, store), and a
 // block that staged 256 slices at a time spent 19 us on six dependent rounds whatever the frame size.
-__global__ void __launch_bounds__(kThreads) k_bucket_rank(const unsigned long long* __restrict__ bkeys,
-                                                          const uint2* __restrict__ bpay, const unsigned* __restrict__ bstart,
+__device__ __forceinline__ unsigned long long entry_key(const uint4& e) { return ((unsigned long long)e.y << 32) | e.x; }
+
+__global__ void __launch_bounds__(kThreads) k_bucket_rank(const uint4* __restrict__ bent, const unsigned* __restrict__ bstart,
                                                           const unsigned* __restrict__ counters, TimeRange range,
                                                           unsigned long long* __restrict__ tsort, unsigned* __restrict__ order_t,
                                                           int* __restrict__ site_t, int tie_site) {
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(kThreads) k_bucket_rank(const unsigned long lo
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const unsigned e = e0 + u * nth;
-            if (e < n1) { key[u] = bkeys[e]; pay[u] = bpay[e]; }
+            if (e < n1) { const uint4 en4 = bent[e]; key[u] = entry_key(en4); pay[u] = make_uint2(en4.z, en4.w); }
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -428,12 +429,13 @@ __global__ void __launch_bounds__(kThreads) k_bucket_rank(const unsigned long lo
             const unsigned idx = pay[u].x & ~kEwinBit;
             unsigned rank = 0;
             for (unsigned q = s[u]; q < en[u]; q++) {
-                const unsigned long long kq = bkeys[q];
+                const uint4 eq = bent[q];
+                const unsigned long long kq = entry_key(eq);
                 if (kq < key[u]) rank++;
                 else if (kq == key[u] && q != e) {
                     // equal times: input order -- or, for the events of a run (their order in the buffer is whatever the
                     // detector kernel's atomics made it), site number first, so that a run's singles do not depend on it
-                    const uint2 pq = bpay[q];
+                    const uint2 pq = make_uint2(eq.z, eq.w);
                     if (tie_site && pq.y != pay[u].y) rank += (int)pq.y < (int)pay[u].y ? 1u : 0u;
                     else if ((pq.x & ~kEwinBit) < idx) rank++;
                 }
@@ -1070,8 +1072,6 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
     int launches = 0;
     EventRec* singles = static_cast<EventRec*>(out.singles);
     unsigned long long* keys = ws.tkeys[0];    // by event index; after the sort: the sorted keys (tsort)
-    unsigned long long* bkeys = ws.tkeys[1];   // scatter target; ping-pong partner of the LSD fallback (the two sorts
-                                               // never run in the same frame)
     if (reset) {   // the digitizer's share of the frame state: counters[0..7], then everything behind the counter block
         cudaMemsetAsync(ws.counters, 0, 8 * sizeof(unsigned), s);
         cudaMemsetAsync(ws.counters + 10, 0, 6 * sizeof(unsigned), s);   // emit-window counts, coincidence class tallies, halo flag
@@ -1089,8 +1089,8 @@ int launch_digitize(EventBuf ev, const DigitizerOut& out, const DigitizerDev& p,
     GPET_LAUNCH("k_bucket_scan", s, launch_pdl(k_bucket_scan, (int)(kMaxBuckets / kScanTile), kThreads, s, ws.bcount, ws.bstart, ws.scan_status[2],
                                                 ws.counters, tr));
     GPET_LAUNCH("k_bucket_scatter", s, launch_pdl(k_bucket_scatter, g_scatter, kThreads, s, keys, ws.site_of, ws.aux, ws.counters, tr, ws.bstart,
-                                                   bkeys, ws.bpay));
-    GPET_LAUNCH("k_bucket_rank", s, launch_pdl(k_bucket_rank, g_rank, kThreads, s, bkeys, ws.bpay, ws.bstart, ws.counters, tr, keys, ws.order_t,
+                                                   ws.bent));
+    GPET_LAUNCH("k_bucket_rank", s, launch_pdl(k_bucket_rank, g_rank, kThreads, s, ws.bent, ws.bstart, ws.counters, tr, keys, ws.order_t,
                                                 ws.site_t, p.tie_site));
     launches += 4;
     if (with_fallback) {

@@ -23,7 +23,7 @@ struct DigitizerWorkspace {
     unsigned int* tvals[2];        // LSD fallback payload ping-pong (event index | window flag)
     int* site_of;                  // dead-time site number by event index
     unsigned int* aux;             // by event index: arrival rank in its time slice | window flag (bit 31)
-    uint2* bpay;                   // scatter target: (event index | window flag, site)
+    uint4* bent;                   // scatter target, one 16-byte entry per event: time key (lo, hi), event index | window flag, site
     unsigned int* lookback[2];     // sort_lookback_words(capacity) status words each (radix passes alternate between them)
     rsort::SortState* st_time;     // LSD fallback bookkeeping (histograms, tile counters)
     unsigned int* grid_bar;        // grid barrier of the cooperative fallback kernel (2 words, zeroed once)
