@@ -187,10 +187,10 @@ def bench_config(source):
     """The `config` object of BOTH arms (identical keys and values: the driver compares them)."""
     return {"workload": workload_name(source),
             "step": "our arm: one step = the acquisition with its activity scaled 160 x (~179 M pairs per GPU, >= 40 ms of kernels) and, on N GPUs, "
-                    "its duration scaled N x (0 - 120 N s: the same event rate at every N), cut into frames of ~4 M pairs (the frame is this "
+                    "its duration scaled N x (0 - 120 N s: the same event rate at every N), cut into frames of ~8 M pairs (~4 M in the end-to-end steps; the frame is this "
                     "library's batch: per-frame fixed costs amortise with it), sharded by frames over the GPUs; reference arm: one step = the "
                     "acquisition at the shipped activity (1.118 M pairs, a bounded sample of the same workload -- the metric is per pair)",
-            "l2": "working set of a frame (~1 GB of queues, hit / event / sort buffers) exceeds the 126 MB L2; 256 MiB flush between timed steps",
+            "l2": "working set of a frame (~2 GB of queues, hit / event / sort buffers) exceeds the 126 MB L2; 256 MiB flush between timed steps",
             "coincidence_window_us": 0.01, "rng": "Philox4x32-10, key 0x67504554, 64-bit history numbers", "time_path": "fp64",
             "multi_gpu": "one acquisition, frames sharded round robin over the ranks (gpet_set_shard), no data-path collective; "
                          "tallies all-reduced once over NCCL after the last step, inside the timed region"}
@@ -262,9 +262,12 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=160,
                     help="activity scale per GPU of a resident step: the shipped acquisition (1.118 M pairs) x this = ~179 M pairs, ~50 ms of kernels")
     ap.add_argument("--e2e-frames-per-step", type=int, default=64, help="activity scale per GPU of an end-to-end step (35 MB of results per 1.118 M pairs)")
-    ap.add_argument("--frame-pairs", type=int, default=4_600_000,
-                    help="frame capacity in pairs (the planner fills ~0.9 of it): per-frame fixed costs amortise with the frame, "
-                         "tools/bigframes_sweep.py -- 314 us per M pairs at 1.1 M pairs a frame, 262 at 4.5 M")
+    ap.add_argument("--frame-pairs", type=int, default=9_200_000,
+                    help="frame capacity in pairs of the resident steps (the planner fills ~0.9 of it): per-frame fixed costs amortise with "
+                         "the frame, tools/bigframes_sweep.py -- 304 us per M pairs at 1.1 M pairs a frame, 250 at 4.5 M, 242 at 8.9 M")
+    ap.add_argument("--e2e-frame-pairs", type=int, default=4_600_000,
+                    help="frame capacity of the end-to-end steps: smaller frames, more of them per step, so that the copy of a frame "
+                         "overlaps the kernels of the next and the pipeline's fill and drain stay short")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
@@ -319,20 +322,20 @@ def main():
         ctx.base_window = (float(cfg["tstart"]), float(cfg["tend"]))
         return ex, ctx
 
-    def plan(ctx, frames_per_gpu, nranks=None):
+    def plan(ctx, frames_per_gpu, nranks=None, frame_pairs=None):
         """ONE acquisition: the shipped one with `frames_per_gpu` times its activity and, on N GPUs, N times its duration
         (0 .. 120 N s).  The event RATE -- what dead time, coincidence windows and the time sort see -- is then the same at every
         N (F-18, T1/2 6586 s: 5 % lower on average over 960 s), so every GPU does the same work per pair; scaling the activity
         with N instead changes the workload itself (measured at N = 8: 7.5 x the random coincidences, 1.5 % fewer singles per
         pair, +6 % digitizer time per pair on EVERY rank, profiles/r02r_bench_n8_activity_scaled.json).  The planner cuts the
-        acquisition into frames of ~4 M pairs (same seed on every rank: same plan), rank r runs frames f with f % world == r."""
+        acquisition into frames of ~8 M pairs (~4 M in the end-to-end steps; same seed on every rank: same plan), rank r runs frames f with f % world == r."""
         nranks = world if nranks is None else nranks
         scale = max(1, frames_per_gpu)
         for i, n in enumerate(ctx.base_atoms):
             ctx.set_source_atoms(i, n * scale)
         t0, t1 = ctx.base_window
         ctx.set_time_window(t0, t0 + (t1 - t0) * nranks)
-        cap = int(args.frame_pairs)
+        cap = int(frame_pairs or args.frame_pairs)
         nf = ctx.plan_frames(cap)
         # every rank the same number of frames: a slightly smaller frame capacity until the count divides by the world size
         # (346 frames over 8 ranks would leave two ranks with 44 frames and six with 43: the step is the slowest rank's)
@@ -397,7 +400,7 @@ def main():
         # e2e through gpet_run: planning + all stages + results in pinned host memory, wall clock.  Singles travel as 32-byte
         # gpet_single_compact records (the run is bound by their copy; gpet_result_singles rebuilds the 48-byte Event byte for
         # byte, tests/test_gpu_parity.py); the same run with 48-byte records is measured beside it
-        nf_e = plan(ctx, e2e_frames_per_step)
+        nf_e = plan(ctx, e2e_frames_per_step, frame_pairs=args.e2e_frame_pairs)
         e2e = {}
         for name, fmt in (("records48", api.Context.SINGLES_RECORDS), ("compact32", api.Context.SINGLES_COMPACT)):
             ctx.set_singles_format(fmt)
@@ -425,7 +428,7 @@ def main():
     # its hit dumps off as in gPET_nodump), wall clock of gpet_run(output_dir).  One GPU only (one host, one file system).
     e2e_files = None
     if world == 1 and not args.no_extra:
-        plan(ctx, 8)
+        plan(ctx, 8, frame_pairs=args.e2e_frame_pairs)
         ctx.set_transport(record_hits=0)
         ctx.set_digitizer(coinc_window_us=0.0)
         od = Path(tmp.name) / "files_out"
@@ -481,7 +484,7 @@ def main():
 
     if rank == 0:
         # ---- per-kernel device times (CUDA events around every launch, on the launching stream) -> roofline
-        plan(ctx, 4, nranks=1)
+        plan(ctx, 8, nranks=1)
         ctx.profile(True)
         nprof = 3
         for _ in range(nprof):
@@ -515,7 +518,7 @@ def main():
                     "frac": kernels[top]["achieved_gbs"] / peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if pk.exists() else "fallback 6650 GB/s (B200_PROFILING.md)",
                     "us_per_launch": kernels[top]["us_per_launch"], "share_of_step": kernels[top]["us_per_frame"] / sum(k["us_per_frame"] for k in kernels.values()),
-                    "timing": "CUDA events bracketing every launch on the launching stream (gpet_profile_enable), 3 runs of the acquisition at 4 x the shipped activity (4.47 M pairs in %d frame(s)), L2 flushed between runs; traffic: ncu dram bytes of a 1.118 M-pair frame (profiles/traffic.json) scaled to this frame's pairs" % fr,
+                    "timing": "CUDA events bracketing every launch on the launching stream (gpet_profile_enable), 3 runs of the acquisition at 8 x the shipped activity (8.9 M pairs in %d frame(s)), L2 flushed between runs; traffic: ncu dram bytes of a 1.118 M-pair frame (profiles/traffic.json) scaled to this frame's pairs" % fr,
                     "note": "Monte-Carlo transport is latency/issue bound: the algorithmic bytes are tiny against HBM (DESIGN.md section 4); see profiles/ for issue-slot, SIMT-efficiency and pipe numbers",
                     "kernels": kernels}
         base = None

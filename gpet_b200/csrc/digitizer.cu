@@ -39,7 +39,7 @@ namespace gpet {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kMaxLogBuckets = 19;
+constexpr int kMaxLogBuckets = 20;   // frames of up to ~8 M pairs keep ~6 events per slice (2^19 until r02z: the rank pass grew beyond 4 M pairs)
 constexpr unsigned kMaxBuckets = 1u << kMaxLogBuckets;
 constexpr unsigned kBucketLimit = 1024;   // a fuller slice sends the time sort to the LSD fallback
 constexpr int kFlagLsd = 5;               // counters[kFlagLsd] != 0: time sort by LSD radix passes
