@@ -42,6 +42,11 @@ int main(int argc, char** argv) {
     dg.coinc_pair_shift = 0;     /* isotope source: both photons carry the pair's eventid */
     if ((rc = gpet_set_digitizer(ctx, &dg)) != GPET_OK) return die(ctx, "gpet_set_digitizer", rc);
 
+    /* coincidences as index pairs and singles as 32-byte records on their way to the host (a run like this one is bound by that
+     * copy); gpet_result_singles / gpet_result_coincidences rebuild the reference's 48-byte Event on demand, byte for byte */
+    if ((rc = gpet_set_coincidence_format(ctx, GPET_COINC_PAIRS)) != GPET_OK) return die(ctx, "gpet_set_coincidence_format", rc);
+    if ((rc = gpet_set_singles_format(ctx, GPET_SINGLES_COMPACT)) != GPET_OK) return die(ctx, "gpet_set_singles_format", rc);
+
     gpet_stats st;
     if ((rc = gpet_run(ctx, NULL, &st)) != GPET_OK) return die(ctx, "gpet_run", rc);
     printf("pairs %llu, hits %llu, events after adder %llu, thresholder %llu, deadtime %llu, singles %llu\n",
@@ -50,6 +55,18 @@ int main(int argc, char** argv) {
     printf("coincidences %llu: trues %llu, scatters %llu, randoms %llu (%.3f ms on the device, %llu frames)\n",
            (unsigned long long)st.coincidences, (unsigned long long)st.trues, (unsigned long long)st.scatters,
            (unsigned long long)st.randoms, st.ms_total, (unsigned long long)st.frames);
+
+    const gpet_single_compact* cs = NULL;
+    const gpet_event* sg = NULL;
+    const int64_t ncs = gpet_result_singles_compact(ctx, &cs), nsg = gpet_result_singles(ctx, &sg);
+    if (ncs != nsg || (uint64_t)nsg != st.singles) return die(ctx, "singles bookkeeping", GPET_ERR_ARG);
+    if (nsg > 0) {   /* the same expansion as a call of its own, for compact records a caller kept */
+        gpet_event first;
+        if ((rc = gpet_expand_singles(ctx, cs, 1, &first)) != GPET_OK) return die(ctx, "gpet_expand_singles", rc);
+        printf("first single: t = %.6f us, E = %.0f eV, panel %d module %d crystal %d (photon %d of annihilation %d)\n", first.t,
+               (double)first.E, (int)first.pann, (int)first.modn, (int)first.cryn, (int)first.parn, (int)first.eventid);
+        if (first.t != sg[0].t || first.parn != sg[0].parn || first.siten != sg[0].siten) return die(ctx, "expansion mismatch", GPET_ERR_ARG);
+    }
 
     const gpet_coincidence* co = NULL;
     const uint8_t* cls = NULL;

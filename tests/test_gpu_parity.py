@@ -652,6 +652,24 @@ def test_c_example_replays_adder_dat_like_the_oracle(tmp_path):
 
 
 @needs_tables
+def test_c_example_runs_an_acquisition_with_compact_delivery(tmp_path):
+    # examples/c/run_classify.c on the GPU: gpet_run from plain C99 with index-pair coincidences and 32-byte singles, the
+    # expansion checked inside the program (gpet_result_singles vs gpet_expand_singles), class totals adding up
+    import re
+    import subprocess
+    exe = tmp_path / "run_classify"
+    libdir = parity.ROOT / "gpet_b200"
+    subprocess.run(["gcc", "-std=c99", f"-I{parity.ROOT / 'include'}", str(parity.ROOT / "examples" / "c" / "run_classify.c"),
+                    f"-L{libdir}", "-lgpet_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    ex = make_example_dir(tmp_path, n=32)
+    r = subprocess.run([str(exe), "input_PET.in", "0.01", "0"], cwd=ex, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"coincidences (\d+): trues (\d+), scatters (\d+), randoms (\d+)", r.stdout)
+    assert m and int(m.group(1)) == int(m.group(2)) + int(m.group(3)) + int(m.group(4)) > 1000
+    assert "first single: t = " in r.stdout and re.search(r"singles (\d+)", r.stdout)
+
+
+@needs_tables
 def test_run_has_no_hidden_host_work(tmp_path):
     # The wall clock of a resident run must stay close to its device time (CUDA events inside the run): host work that
     # creeps into gpet_run (the direction table was once rebuilt at every call: +0.4 ms) doubles the step of bench.py
